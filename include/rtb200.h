@@ -1,0 +1,322 @@
+/*
+ * rtb200.h — C ABI of the B200-native path-tracing hot path.
+ *
+ * Drop-in boundary for the reference's (Witek902/Raytracer) per-pixel integrator loop and the
+ * two-level BVH ray/scene intersection it drives.  Every entry point below replaces one piece of the
+ * reference's C++ interface (file:line relative to the reference checkout):
+ *
+ *   rtb_create / rtb_destroy      Viewport::Viewport / ~Viewport          Core/Rendering/Viewport.cpp:21-28
+ *   rtb_upload_scene              Scene::BuildBVH result + CreateRenderer Core/Scene/Scene.cpp:36-126, Core/Rendering/Renderer.cpp:45-69
+ *   rtb_resize                    Viewport::Resize                        Core/Rendering/Viewport.cpp:52-115
+ *   rtb_reset                     Viewport::Reset                         Core/Rendering/Viewport.cpp:117-138
+ *   rtb_render_pass               Viewport::Render (one sample per pixel) Core/Rendering/Viewport.cpp:185-289
+ *   rtb_read_sum                  Viewport::GetSumBuffer                  Core/Rendering/Viewport.h:50
+ *   rtb_get_counters              Viewport::GetCounters                   Core/Rendering/Viewport.h:58, Core/Rendering/Counters.h:36-93
+ *   rtb_trace_batch               Scene::Traverse / Scene::Traverse_Shadow Core/Scene/Scene.cpp:219-261
+ *   rtb_sample_batch              GenericSampler::ResetPixel/GetInt       Core/Sampling/GenericSampler.cpp:75-112
+ *   rtb_primary_rays              Camera::GenerateRay via RenderTile      Core/Scene/Camera.cpp:81-118, Core/Rendering/Viewport.cpp:320-330
+ *
+ * All structs are POD, all pointers are caller-owned HOST pointers that are copied during the call
+ * (unless a name says "device").  Every function returns 0 on success or a negative RtbStatus;
+ * rtb_last_error() returns a human readable message for the calling thread's last failure.
+ * There is no CPU fallback: without a CUDA device rtb_create fails with RTB_ERR_NO_DEVICE.
+ * A context is not thread-safe; calls are synchronous unless stated otherwise.
+ */
+#ifndef RTB200_H
+#define RTB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB_API_VERSION 1
+
+typedef enum RtbStatus
+{
+    RTB_OK                = 0,
+    RTB_ERR_INVALID_ARG   = -1,
+    RTB_ERR_NO_DEVICE     = -2,
+    RTB_ERR_CUDA          = -3,
+    RTB_ERR_NO_SCENE      = -4,
+    RTB_ERR_UNSUPPORTED   = -5,
+    RTB_ERR_OUT_OF_MEMORY = -6
+} RtbStatus;
+
+/* sentinel ids, HitPoint.h:8-9 */
+#define RTB_INVALID_OBJECT 0xFFFFFFFFu
+#define RTB_LIGHT_OBJECT   0xFFFFFFFEu
+
+/* ---- scene description (flattened rt::Scene after BuildBVH) ------------------------------------ */
+
+/* BVH::Node, Core/BVH/BVH.h:22-30, verbatim 32-byte layout.  leafInfo = numLeaves | splitAxis << 30 */
+typedef struct RtbBvhNode
+{
+    float    min[3];
+    uint32_t childIndex;
+    float    max[3];
+    uint32_t leafInfo;
+} RtbBvhNode;
+
+/* math::Matrix4, four rows of four floats (row-vector convention, Core/Math/Matrix4.h:110-139) */
+typedef struct RtbMat4 { float r[4][4]; } RtbMat4;
+
+typedef enum RtbShapeType
+{
+    RTB_SHAPE_SPHERE = 0,   /* Core/Shapes/SphereShape.cpp */
+    RTB_SHAPE_BOX    = 1,   /* Core/Shapes/BoxShape.cpp    */
+    RTB_SHAPE_RECT   = 2,   /* Core/Shapes/RectShape.cpp   */
+    RTB_SHAPE_MESH   = 3    /* Core/Shapes/MeshShape.cpp   */
+} RtbShapeType;
+
+/*
+ * sphere: size[0] = radius, invSize[0] = 1/radius
+ * box   : size = half extents (w = 0), invSize = 1/size (w = 0), aux.xyz = face cdf (BoxShape.cpp:97-111)
+ * rect  : size.xy = half extents, aux.xy = texture scale
+ * mesh  : meshIndex selects RtbSceneDesc::meshes[]
+ */
+typedef struct RtbShape
+{
+    uint32_t type;
+    uint32_t meshIndex;
+    uint32_t pad0, pad1;
+    float    size[4];
+    float    invSize[4];
+    float    aux[4];
+} RtbShape;
+
+typedef enum RtbBsdfType
+{
+    RTB_BSDF_NULL = 0, RTB_BSDF_DIFFUSE, RTB_BSDF_ROUGH_DIFFUSE, RTB_BSDF_DIELECTRIC, RTB_BSDF_ROUGH_DIELECTRIC,
+    RTB_BSDF_METAL, RTB_BSDF_ROUGH_METAL, RTB_BSDF_PLASTIC, RTB_BSDF_ROUGH_PLASTIC
+} RtbBsdfType;
+
+/* rt::Material constant parameters (Core/Material/Material.h:44-75), textures are not part of this contract yet */
+typedef struct RtbMaterial
+{
+    uint32_t bsdf;
+    uint32_t flags;
+    float    roughness;
+    float    metalness;
+    float    baseColor[4];
+    float    emission[4];
+    float    IoR;
+    float    K;
+    float    pad0, pad1;
+} RtbMaterial;
+
+typedef enum RtbLightType
+{
+    RTB_LIGHT_AREA = 0, RTB_LIGHT_BACKGROUND, RTB_LIGHT_DIRECTIONAL, RTB_LIGHT_POINT, RTB_LIGHT_SPOT
+} RtbLightType;
+
+#define RTB_LIGHT_FLAG_FINITE 1u   /* ILight::Flag_IsFinite, Light.h:41 */
+#define RTB_LIGHT_FLAG_DELTA  2u   /* ILight::Flag_IsDelta,  Light.h:42 */
+
+/* one LightSceneObject (+ its ILight), in Scene::GetLights() order (Scene.cpp:43-49) */
+typedef struct RtbLight
+{
+    uint32_t type;
+    uint32_t flags;
+    uint32_t shapeIndex;     /* area lights: RtbSceneDesc::shapes[] */
+    uint32_t isDelta;        /* directional / spot */
+    float    color[4];
+    float    cosAngle;       /* directional / spot: cosf(angle) computed by the host */
+    float    pad0, pad1, pad2;
+    RtbMat4  transform;      /* light -> world */
+    RtbMat4  invTransform;   /* world -> light */
+} RtbLight;
+
+#define RTB_OBJECT_SHAPE 0u
+#define RTB_OBJECT_LIGHT 1u
+
+/* one traceable object, in top-level BVH leaf order (Scene.cpp:87-94): objectId == index here */
+typedef struct RtbObject
+{
+    uint32_t kind;           /* RTB_OBJECT_SHAPE | RTB_OBJECT_LIGHT */
+    uint32_t shapeIndex;     /* shapes[] (for lights: the area light's shape, or UINT32_MAX) */
+    uint32_t materialIndex;  /* default material of a shape object */
+    uint32_t lightIndex;     /* lights[] for RTB_OBJECT_LIGHT */
+    RtbMat4  transform;
+    RtbMat4  invTransform;
+} RtbObject;
+
+/* one MeshShape (+VertexBuffer), triangles already in BVH leaf order (MeshShape.cpp:82-95) */
+typedef struct RtbMesh
+{
+    uint32_t numNodes;
+    uint32_t numTriangles;
+    uint32_t numVertices;
+    uint32_t numMaterials;
+    const RtbBvhNode* nodes;        /* numNodes                                               */
+    const float*      triangles;    /* numTriangles * 9: v0, edge1, edge2 (Triangle.h:25-41)   */
+    const uint32_t*   indices;      /* numTriangles * 4: i0 i1 i2 materialIndex (VertexBuffer.h:18-24) */
+    const float*      shading;      /* numVertices * 8: normal3 tangent3 uv2 (VertexBuffer.h:26-31)    */
+    const uint32_t*   materialIds;  /* numMaterials: index into RtbSceneDesc::materials        */
+} RtbMesh;
+
+typedef struct RtbSceneDesc
+{
+    uint32_t numTlasNodes;   const RtbBvhNode*  tlasNodes;
+    uint32_t numObjects;     const RtbObject*   objects;
+    uint32_t numShapes;      const RtbShape*    shapes;
+    uint32_t numMeshes;      const RtbMesh*     meshes;
+    uint32_t numMaterials;   const RtbMaterial* materials;
+    uint32_t numLights;      const RtbLight*    lights;
+    uint32_t numGlobalLights; const uint32_t*   globalLights;  /* indices into lights[], Scene::GetGlobalLights() order */
+} RtbSceneDesc;
+
+/* ---- per-pass description ----------------------------------------------------------------------- */
+
+typedef enum RtbRenderer
+{
+    RTB_RENDERER_PATH_TRACER     = 0,  /* "Path Tracer"     Core/Rendering/PathTracer.cpp    */
+    RTB_RENDERER_PATH_TRACER_MIS = 1,  /* "Path Tracer MIS" Core/Rendering/PathTracerMIS.cpp */
+    RTB_RENDERER_DEBUG           = 2   /* "Debug"           Core/Rendering/DebugRenderer.cpp */
+} RtbRenderer;
+
+/* DebugRenderingMode, Core/Rendering/DebugRenderer.h:7-33 (same numeric values) */
+typedef enum RtbDebugMode
+{
+    RTB_DEBUG_CAMERA_LIGHT = 0, RTB_DEBUG_TRIANGLE_ID, RTB_DEBUG_DEPTH, RTB_DEBUG_POSITION, RTB_DEBUG_NORMALS,
+    RTB_DEBUG_TANGENTS, RTB_DEBUG_BITANGENTS, RTB_DEBUG_TEXCOORDS, RTB_DEBUG_BASE_COLOR, RTB_DEBUG_EMISSION,
+    RTB_DEBUG_ROUGHNESS, RTB_DEBUG_METALNESS, RTB_DEBUG_IOR
+} RtbDebugMode;
+
+typedef enum RtbBokehShape { RTB_BOKEH_CIRCLE = 0, RTB_BOKEH_HEXAGON = 1, RTB_BOKEH_SQUARE = 2 } RtbBokehShape;
+
+/* rt::Camera state consumed by Camera::GenerateRay (Camera.cpp:81-118) */
+typedef struct RtbCamera
+{
+    RtbMat4  localToWorld;
+    float    aspectRatio;
+    float    tanHalfFoV;        /* tanf(fov/2) computed by the host, Camera.cpp:37 */
+    uint32_t dofEnable;
+    uint32_t bokehShape;
+    float    aperture;
+    float    focalPlaneDistance;
+    float    barrelDistortionConstFactor;
+    float    barrelDistortionVariableFactor;   /* must be 0: the reference draws it from a per-thread RNG */
+} RtbCamera;
+
+#define RTB_LIGHT_SAMPLING_SINGLE 0u
+#define RTB_LIGHT_SAMPLING_ALL    1u
+
+typedef struct RtbPassDesc
+{
+    uint32_t        renderer;               /* RtbRenderer */
+    uint32_t        debugMode;              /* RtbDebugMode, RTB_RENDERER_DEBUG only */
+    RtbCamera       camera;
+    uint32_t        maxRayDepth;            /* RenderingParams::maxRayDepth            Context.h:69 */
+    uint32_t        minRussianRouletteDepth;/* RenderingParams::minRussianRouletteDepth Context.h:72 */
+    uint32_t        lightSamplingStrategy;  /* RTB_LIGHT_SAMPLING_*                    Context.h:82 */
+    uint32_t        useBlueNoise;           /* SamplingParams::useBlueNoiseDithering   Context.h:52 */
+    uint32_t        passIndex;              /* Viewport progress.passesFinished: even passes also feed secondarySum */
+    uint32_t        numSeedDims;            /* SamplingParams::dimensions              Context.h:49 */
+    const uint32_t* seed;                   /* numSeedDims Halton integers of this pass, Viewport.cpp:200-205 */
+    float           sampleOffset[2];        /* AA jitter of this pass, Viewport.cpp:235-242 */
+} RtbPassDesc;
+
+/* RayTracingCounters, Core/Rendering/Counters.h:36-41 (+ traversal work counters, Counters.h:8-33) */
+typedef struct RtbCounters
+{
+    uint64_t numRays;
+    uint64_t numShadowRays;
+    uint64_t numShadowRaysHit;
+    uint64_t numPrimaryRays;
+    uint64_t numRayBoxTests;        /* only filled when the context was created with RTB_FLAG_COUNT_TESTS */
+    uint64_t numRayTriangleTests;
+} RtbCounters;
+
+/* ---- batch test hooks ---------------------------------------------------------------------------- */
+
+/* math::Ray as Scene::Traverse sees it (Ray.h:13-28): 4 x float4 */
+typedef struct RtbRay
+{
+    float origin[4];
+    float dir[4];
+    float invDir[4];
+    float originDivDir[4];
+} RtbRay;
+
+/* HitPoint, Core/Traversal/HitPoint.h:14-51 (distance doubles as tMax for shadow queries) */
+typedef struct RtbHit
+{
+    uint32_t objectId;
+    uint32_t subObjectId;
+    float    distance;
+    float    u;
+    float    v;
+    uint32_t occluded;    /* shadow mode: 1 if Scene::Traverse_Shadow returned true */
+} RtbHit;
+
+#define RTB_TRACE_CLOSEST 0u
+#define RTB_TRACE_SHADOW  1u
+
+/* ---- context ------------------------------------------------------------------------------------ */
+
+#define RTB_FLAG_COUNT_TESTS 1u   /* per-ray box/triangle test counters (roofline algorithmic bytes) */
+
+typedef struct RtbCreateDesc
+{
+    int32_t  deviceId;        /* CUDA device ordinal */
+    uint32_t flags;
+    /* multi-GPU tile sharding: this context renders tiles t with t % numShards == shardIndex (1/0 = whole frame) */
+    uint32_t numShards;
+    uint32_t shardIndex;
+    uint32_t tileSize;        /* 0 -> 32 (RenderingParams::tileSize, Context.h:76) */
+    void*    stream;          /* cudaStream_t to launch on, NULL -> a stream owned by the context */
+} RtbCreateDesc;
+
+typedef struct RtbContext RtbContext;
+
+const char* rtb_last_error(void);
+int  rtb_api_version(void);
+
+int  rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx);
+void rtb_destroy(RtbContext* ctx);
+
+int  rtb_upload_scene(RtbContext* ctx, const RtbSceneDesc* scene);
+int  rtb_set_blue_noise(RtbContext* ctx, const uint16_t* data /* 128*128*4 u16, Data/BlueNoise128_RGBA16.dat */);
+
+int  rtb_resize(RtbContext* ctx, uint32_t width, uint32_t height);
+int  rtb_reset(RtbContext* ctx);
+
+/* enqueue one pass (asynchronous on the context's stream); rtb_synchronize / rtb_read_* wait for it */
+int  rtb_render_pass(RtbContext* ctx, const RtbPassDesc* pass);
+int  rtb_synchronize(RtbContext* ctx);
+
+/* which: 0 = sum, 1 = secondarySum.  rgb = width*height*3 floats, row 0 = top (Film.cpp:31-39) */
+int  rtb_read_sum(RtbContext* ctx, float* rgb, int which);
+/* device pointer + element count of this shard's compact film (for an NCCL all-gather by the caller) */
+int  rtb_film_device_buffer(RtbContext* ctx, int which, void** outDevicePtr, uint64_t* outNumFloats);
+/* scatter gathered shard buffers (numShards * shardFloats, device) back to raster order into hostRgb */
+int  rtb_unshard_film(RtbContext* ctx, const void* gatheredDevice, float* hostRgb);
+
+int  rtb_get_counters(RtbContext* ctx, RtbCounters* out);   /* counters of the passes since the last reset */
+
+int  rtb_trace_batch(RtbContext* ctx, const RtbRay* rays, uint64_t n, RtbHit* hits, uint32_t mode);
+/* device-resident variant used by bench.py for the kernel-only number; returns kernel milliseconds */
+int  rtb_trace_batch_device(RtbContext* ctx, const void* raysDevice, uint64_t n, void* hitsDevice, uint32_t mode, float* outMs);
+
+/* out[i*numDims + d] = d-th GenericSampler::GetInt() of pixel (xy[2i], xy[2i+1]) */
+int  rtb_sample_batch(RtbContext* ctx, const RtbPassDesc* pass, const uint32_t* xy, uint64_t n, uint32_t numDims, uint32_t* out);
+/* rays[y*width + x] = primary ray of film pixel (x, y) for this pass */
+int  rtb_primary_rays(RtbContext* ctx, const RtbPassDesc* pass, RtbRay* rays);
+
+/* per-kernel device time of the last rendered pass (CUDA events), for bench.py's roofline */
+typedef struct RtbPassTimings
+{
+    float raygenMs, traverseMs, shadeMs, shadowMs, totalMs;
+    uint32_t traverseLaunches, shadeLaunches, shadowLaunches, totalLaunches;
+    uint64_t traverseRays, shadowRays;
+} RtbPassTimings;
+int  rtb_set_profiling(RtbContext* ctx, int enable);
+int  rtb_get_pass_timings(RtbContext* ctx, RtbPassTimings* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB200_H */

@@ -1,0 +1,595 @@
+// rtref — headless harness around the UNMODIFIED algorithms of the reference (Witek902/Raytracer).
+//
+// TEST INFRASTRUCTURE ONLY (parity oracle + CPU timing baseline).  It links the patched copy of the reference
+// built by oracle/build_ref.sh and is compiled with -fno-access-control so it can read private state of
+// rt::Scene / rt::Viewport / shapes (Scene.h:83-92, SceneObject_Shape.h:29-31, MeshShape.h:53-64 ...) without
+// editing reference sources.  Nothing in the product links or executes this file.
+//
+// Sub-commands (all take --scene X.json [--data DIR]):
+//   render   Viewport::Render loop -> sum buffer, secondary sum, per-pass seed/AA script, counters
+//   flat     flatten the reference's Scene (after BuildBVH) + Camera into the RtbSceneDesc file format ("RTBS")
+//   trace    Scene::Traverse / Scene::Traverse_Shadow over a file of RtbRay -> file of RtbHit
+//   sampler  GenericSampler streams for given pixels of given passes
+//   primary  Camera::GenerateRay for every pixel exactly as Viewport::RenderTile calls it
+#include "PCH.h"
+#include "Demo.h"
+#include "SceneLoader.h"
+#include "../Core/Rendering/Renderer.h"
+#include "../Core/Rendering/DebugRenderer.h"
+#include "../Core/Rendering/Viewport.h"
+#include "../Core/Rendering/Context.h"
+#include "../Core/Scene/Scene.h"
+#include "../Core/Scene/Camera.h"
+#include "../Core/Scene/Object/SceneObject_Shape.h"
+#include "../Core/Scene/Object/SceneObject_Light.h"
+#include "../Core/Scene/Light/AreaLight.h"
+#include "../Core/Scene/Light/BackgroundLight.h"
+#include "../Core/Scene/Light/DirectionalLight.h"
+#include "../Core/Scene/Light/PointLight.h"
+#include "../Core/Scene/Light/SpotLight.h"
+#include "../Core/Shapes/SphereShape.h"
+#include "../Core/Shapes/BoxShape.h"
+#include "../Core/Shapes/RectShape.h"
+#include "../Core/Shapes/MeshShape.h"
+#include "../Core/Material/Material.h"
+#include "../Core/Traversal/TraversalContext.h"
+#include "../Core/Math/SamplingHelpers.h"
+#include "../Core/Sampling/GenericSampler.h"
+#include "../Core/Utils/Timer.h"
+#include "../Core/Utils/Memory.h"
+
+#include "rtb200.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include <thread>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
+Options gOptions;
+
+using namespace rt;
+using namespace rt::math;
+
+namespace {
+
+struct Args
+{
+    std::map<std::string, std::string> kv;
+    std::string cmd;
+
+    bool Has(const char* k) const { return kv.count(k) > 0; }
+    std::string Str(const char* k, const char* def = "") const { auto it = kv.find(k); return it == kv.end() ? def : it->second; }
+    long Int(const char* k, long def) const { auto it = kv.find(k); return it == kv.end() ? def : atol(it->second.c_str()); }
+    double Dbl(const char* k, double def) const { auto it = kv.find(k); return it == kv.end() ? def : atof(it->second.c_str()); }
+};
+
+Args ParseArgs(int argc, char** argv)
+{
+    Args a;
+    if (argc > 1) a.cmd = argv[1];
+    for (int i = 2; i < argc; ++i)
+    {
+        std::string k = argv[i];
+        if (k.rfind("--", 0) == 0)
+        {
+            k = k.substr(2);
+            if (i + 1 < argc && strncmp(argv[i + 1], "--", 2) != 0) { a.kv[k] = argv[++i]; }
+            else { a.kv[k] = "1"; }
+        }
+    }
+    return a;
+}
+
+void Die(const char* msg) { fprintf(stderr, "rtref: %s\n", msg); exit(1); }
+
+template <typename T> void WritePod(FILE* f, const T& v) { if (fwrite(&v, sizeof(T), 1, f) != 1) Die("write failed"); }
+void WriteU32(FILE* f, uint32_t v) { WritePod(f, v); }
+void WriteBytes(FILE* f, const void* p, size_t n) { if (n && fwrite(p, 1, n, f) != n) Die("write failed"); }
+
+RtbMat4 ToMat(const Matrix4& m)
+{
+    // Matrix4 is declared RT_ALIGN(32) but scene objects are allocated by Aligned<16>::operator new, so the compiler's
+    // 32-byte aligned AVX copy faults here; hide the alignment from the optimizer and copy bytes.
+    const char* p = reinterpret_cast<const char*>(&m);
+    asm volatile("" : "+r"(p));
+    RtbMat4 r;
+    memcpy(&r, p, sizeof(r));
+    return r;
+}
+
+void ToF4(const Vector4& v, float* out) { out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w; }
+
+uint32_t BsdfId(const Material* m)
+{
+    const char* n = m->GetBSDF() ? m->GetBSDF()->GetName() : "null";
+    const char* names[] = { "null", "diffuse", "roughDiffuse", "dielectric", "roughDielectric", "metal", "roughMetal", "plastic", "roughPlastic" };
+    for (uint32_t i = 0; i < 9; ++i) if (!strcmp(n, names[i])) return i;
+    Die("unknown BSDF");
+    return 0;
+}
+
+void CopyNodes(const BVH& bvh, std::vector<RtbBvhNode>& out)
+{
+    static_assert(sizeof(BVH::Node) == sizeof(RtbBvhNode), "node layout");
+    out.resize(bvh.GetNumNodes());
+    if (!out.empty()) memcpy(out.data(), bvh.GetNodes(), sizeof(RtbBvhNode) * out.size());
+    // node 1 is never written by BVHBuilder (root takes two slots, BVHBuilder.cpp:86) -> uninitialised memory
+    if (out.size() > 1) memset(&out[1], 0, sizeof(RtbBvhNode));
+}
+
+// flattened scene, owning storage
+struct Flat
+{
+    std::vector<RtbBvhNode> tlas;
+    std::vector<RtbObject> objects;
+    std::vector<RtbShape> shapes;
+    std::vector<RtbMaterial> materials;
+    std::vector<RtbLight> lights;
+    std::vector<uint32_t> globalLights;
+    struct Mesh
+    {
+        std::vector<RtbBvhNode> nodes;
+        std::vector<float> triangles;
+        std::vector<uint32_t> indices;
+        std::vector<float> shading;
+        std::vector<uint32_t> materialIds;
+        uint32_t numVertices = 0;
+    };
+    std::vector<Mesh> meshes;
+
+    std::map<const IShape*, uint32_t> shapeIds;
+    std::map<const Material*, uint32_t> materialIds;
+
+    uint32_t AddMaterial(const Material* m)
+    {
+        auto it = materialIds.find(m);
+        if (it != materialIds.end()) return it->second;
+        RtbMaterial r;
+        memset(&r, 0, sizeof(r));
+        r.bsdf = BsdfId(m);
+        if (m->baseColor.texture || m->emission.texture || m->roughness.texture || m->metalness.texture || m->normalMap || m->maskMap) r.flags |= 1u; // textured (unsupported)
+        if (m->isDispersive) r.flags |= 2u;
+        r.roughness = m->roughness.baseValue;
+        r.metalness = m->metalness.baseValue;
+        ToF4(m->baseColor.baseValue, r.baseColor);
+        ToF4(m->emission.baseValue, r.emission);
+        r.IoR = m->IoR;
+        r.K = m->K;
+        const uint32_t id = (uint32_t)materials.size();
+        materials.push_back(r);
+        materialIds[m] = id;
+        return id;
+    }
+
+    uint32_t AddShape(const IShape* s)
+    {
+        auto it = shapeIds.find(s);
+        if (it != shapeIds.end()) return it->second;
+        RtbShape r;
+        memset(&r, 0, sizeof(r));
+        r.meshIndex = UINT32_MAX;
+        if (const SphereShape* sp = dynamic_cast<const SphereShape*>(s))
+        {
+            r.type = RTB_SHAPE_SPHERE;
+            r.size[0] = sp->mRadius;
+            r.invSize[0] = sp->mInvRadius;
+        }
+        else if (const BoxShape* bx = dynamic_cast<const BoxShape*>(s))
+        {
+            r.type = RTB_SHAPE_BOX;
+            ToF4(bx->mSize, r.size);
+            ToF4(bx->mInvSize, r.invSize);
+            r.aux[0] = bx->mFaceCdf.x; r.aux[1] = bx->mFaceCdf.y; r.aux[2] = bx->mFaceCdf.z;
+        }
+        else if (const RectShape* rc = dynamic_cast<const RectShape*>(s))
+        {
+            r.type = RTB_SHAPE_RECT;
+            r.size[0] = rc->mSize.x; r.size[1] = rc->mSize.y;
+            r.aux[0] = rc->mTextureScale.x; r.aux[1] = rc->mTextureScale.y;
+            if (rc->mEnableSolidAngleSampling) Die("rect solid angle sampling not supported");
+        }
+        else if (const MeshShape* ms = dynamic_cast<const MeshShape*>(s))
+        {
+            r.type = RTB_SHAPE_MESH;
+            r.meshIndex = (uint32_t)meshes.size();
+            Mesh m;
+            CopyNodes(ms->mBVH, m.nodes);
+            const VertexBuffer& vb = ms->mVertexBuffer;
+            const uint32_t nt = vb.mNumTriangles, nv = vb.mNumVertices;
+            m.numVertices = nv;
+            m.triangles.resize((size_t)nt * 9);
+            static_assert(sizeof(ProcessedTriangle) == 36, "tri layout");
+            if (nt) memcpy(m.triangles.data(), vb.mPreprocessedTriangles, (size_t)nt * 36);
+            m.indices.resize((size_t)nt * 4);
+            if (nt) memcpy(m.indices.data(), vb.mBuffer + vb.mVertexIndexBufferOffset, (size_t)nt * 16);
+            m.shading.resize((size_t)nv * 8);
+            if (nv) memcpy(m.shading.data(), vb.mBuffer + vb.mShadingDataBufferOffset, (size_t)nv * 32);
+            for (uint32_t i = 0; i < vb.mMaterials.Size(); ++i) m.materialIds.push_back(AddMaterial(vb.mMaterials[i].get()));
+            meshes.push_back(std::move(m));
+        }
+        else
+        {
+            Die("unsupported shape type (csg?)");
+        }
+        const uint32_t id = (uint32_t)shapes.size();
+        shapes.push_back(r);
+        shapeIds[s] = id;
+        return id;
+    }
+
+    void Build(const Scene& scene)
+    {
+        CopyNodes(scene.mTraceableObjectsBVH, tlas);
+
+        std::map<const LightSceneObject*, uint32_t> lightIds;
+        for (const LightSceneObject* lo : scene.mLights)
+        {
+            const ILight& l = lo->GetLight();
+            RtbLight r;
+            memset(&r, 0, sizeof(r));
+            r.type = (uint32_t)l.GetType();
+            r.flags = (uint32_t)l.GetFlags();
+            r.shapeIndex = UINT32_MAX;
+            ToF4(l.GetColor().rgbValues, r.color);
+            if (const AreaLight* al = dynamic_cast<const AreaLight*>(&l)) { r.shapeIndex = AddShape(al->GetShape().get()); if (al->mTexture) Die("textured area light"); }
+            if (const BackgroundLight* bl = dynamic_cast<const BackgroundLight*>(&l)) { if (bl->mTexture) Die("textured background light"); }
+            if (const DirectionalLight* dl = dynamic_cast<const DirectionalLight*>(&l)) { r.cosAngle = dl->mCosAngle; r.isDelta = dl->mIsDelta; }
+            if (const SpotLight* sl = dynamic_cast<const SpotLight*>(&l)) { r.cosAngle = sl->mCosAngle; r.isDelta = sl->mIsDelta; }
+            r.transform = ToMat(lo->GetBaseTransform());
+            r.invTransform = ToMat(lo->GetBaseInverseTransform());
+            lightIds[lo] = (uint32_t)lights.size();
+            lights.push_back(r);
+        }
+        for (const LightSceneObject* lo : scene.mGlobalLights) globalLights.push_back(lightIds.at(lo));
+
+        for (const ITraceableSceneObject* obj : scene.mTraceableObjects)
+        {
+            RtbObject r;
+            memset(&r, 0, sizeof(r));
+            r.shapeIndex = r.materialIndex = r.lightIndex = UINT32_MAX;
+            r.transform = ToMat(obj->GetBaseTransform());
+            r.invTransform = ToMat(obj->GetBaseInverseTransform());
+            if (const ShapeSceneObject* so = dynamic_cast<const ShapeSceneObject*>(obj))
+            {
+                r.kind = RTB_OBJECT_SHAPE;
+                r.shapeIndex = AddShape(so->mShape.get());
+                r.materialIndex = AddMaterial(so->mDefaultMaterial.get());
+            }
+            else if (const LightSceneObject* lo = dynamic_cast<const LightSceneObject*>(obj))
+            {
+                r.kind = RTB_OBJECT_LIGHT;
+                r.lightIndex = lightIds.at(lo);
+                r.shapeIndex = lights[r.lightIndex].shapeIndex;
+            }
+            else Die("unsupported traceable object");
+            objects.push_back(r);
+        }
+    }
+
+    void Write(const char* path, const Camera& camera) const
+    {
+        FILE* f = fopen(path, "wb");
+        if (!f) Die("cannot open output");
+        WriteU32(f, 0x53425452u); // 'RTBS'
+        WriteU32(f, 1);
+        WriteU32(f, (uint32_t)tlas.size());      WriteBytes(f, tlas.data(), tlas.size() * sizeof(RtbBvhNode));
+        WriteU32(f, (uint32_t)objects.size());   WriteBytes(f, objects.data(), objects.size() * sizeof(RtbObject));
+        WriteU32(f, (uint32_t)shapes.size());    WriteBytes(f, shapes.data(), shapes.size() * sizeof(RtbShape));
+        WriteU32(f, (uint32_t)meshes.size());
+        for (const Mesh& m : meshes)
+        {
+            WriteU32(f, (uint32_t)m.nodes.size());
+            WriteU32(f, (uint32_t)(m.triangles.size() / 9));
+            WriteU32(f, m.numVertices);
+            WriteU32(f, (uint32_t)m.materialIds.size());
+            WriteBytes(f, m.nodes.data(), m.nodes.size() * sizeof(RtbBvhNode));
+            WriteBytes(f, m.triangles.data(), m.triangles.size() * 4);
+            WriteBytes(f, m.indices.data(), m.indices.size() * 4);
+            WriteBytes(f, m.shading.data(), m.shading.size() * 4);
+            WriteBytes(f, m.materialIds.data(), m.materialIds.size() * 4);
+        }
+        WriteU32(f, (uint32_t)materials.size()); WriteBytes(f, materials.data(), materials.size() * sizeof(RtbMaterial));
+        WriteU32(f, (uint32_t)lights.size());    WriteBytes(f, lights.data(), lights.size() * sizeof(RtbLight));
+        WriteU32(f, (uint32_t)globalLights.size()); WriteBytes(f, globalLights.data(), globalLights.size() * 4);
+
+        RtbCamera c;
+        memset(&c, 0, sizeof(c));
+        c.localToWorld = ToMat(camera.mLocalToWorld);
+        c.aspectRatio = camera.mAspectRatio;
+        c.tanHalfFoV = camera.mTanHalfFoV;
+        c.dofEnable = camera.mDOF.enable;
+        c.bokehShape = (uint32_t)camera.mDOF.bokehShape;
+        c.aperture = camera.mDOF.aperture;
+        c.focalPlaneDistance = camera.mDOF.focalPlaneDistance;
+        c.barrelDistortionConstFactor = camera.barrelDistortionConstFactor;
+        c.barrelDistortionVariableFactor = camera.barrelDistortionVariableFactor;
+        WritePod(f, c);
+        WritePod(f, camera.mFieldOfView);
+        fclose(f);
+    }
+};
+
+bool LoadSceneFile(const Args& a, Scene& scene, Camera& camera, uint32 w, uint32 h)
+{
+    gOptions.dataPath = a.Str("data", "");
+    if (!helpers::LoadScene(a.Str("scene"), scene, camera)) { fprintf(stderr, "rtref: scene load failed\n"); return false; }
+    if (!scene.BuildBVH()) return false;
+    camera.SetPerspective((float)w / (float)h, camera.mFieldOfView);
+    return true;
+}
+
+RenderingParams MakeParams(const Args& a)
+{
+    RenderingParams p;
+    const long threads = a.Int("threads", 0);
+    p.numThreads = threads > 0 ? (uint32)threads : std::thread::hardware_concurrency();
+    p.maxRayDepth = (uint32)a.Int("depth", 8);
+    p.minRussianRouletteDepth = (uint32)a.Int("rr-depth", 1);
+    p.samplingParams.dimensions = (uint32)a.Int("dims", 128);
+    p.samplingParams.useBlueNoiseDithering = a.Int("blue-noise", 1) != 0;
+    p.lightSamplingStrategy = a.Str("strategy", "all") == "single" ? LightSamplingStrategy::Single : LightSamplingStrategy::All;
+    p.antiAliasingSpread = (float)a.Dbl("aa-spread", 0.5);
+    return p;
+}
+
+int CmdRender(const Args& a)
+{
+    const uint32 w = (uint32)a.Int("width", 256), h = (uint32)a.Int("height", 256), passes = (uint32)a.Int("passes", 1);
+    const std::string rendererName = a.Str("renderer", "Path Tracer MIS");
+    Scene scene; Camera camera;
+    if (!LoadSceneFile(a, scene, camera, w, h)) return 1;
+
+    Viewport vp;
+    const RenderingParams params = MakeParams(a);
+    vp.SetRenderingParams(params);
+    vp.Resize(w, h);
+    RendererPtr renderer = CreateRenderer(rendererName, scene);
+    if (!renderer) Die("unknown renderer");
+    if (rendererName == "Debug") static_cast<DebugRenderer*>(renderer.get())->mRenderingMode = (DebugRenderingMode)a.Int("debug-mode", 1);
+    vp.SetRenderer(renderer);
+    vp.Reset();
+
+    FILE* script = a.Has("dump-passes") ? fopen(a.Str("dump-passes").c_str(), "wb") : nullptr;
+    if (script) { WriteU32(script, passes); WriteU32(script, params.samplingParams.dimensions); }
+
+    const uint32 warmup = (uint32)a.Int("warmup", 0);
+    uint64 rays = 0, shadow = 0, shadowHit = 0, primary = 0;
+    double seconds = 0.0;
+    for (uint32 i = 0; i < passes + warmup; ++i)
+    {
+        // same draw Viewport::Render makes from its private generator (Viewport.cpp:235) - taken from a COPY so the
+        // real stream is untouched
+        Random rngCopy = vp.mRandomGenerator;
+        const Vector4 u = SamplingHelpers::GetFloatNormal2(rngCopy.GetFloat2());
+        const Vector4 sampleOffset = u * params.antiAliasingSpread;
+
+        Timer t;
+        vp.Render(camera);
+        const double dt = t.Stop();
+
+        if (script && i >= warmup)
+        {
+            for (uint32 d = 0; d < params.samplingParams.dimensions; ++d) WriteU32(script, vp.mHaltonSequence.GetInt(d));
+            WritePod(script, sampleOffset.x);
+            WritePod(script, sampleOffset.y);
+        }
+        if (i >= warmup)
+        {
+            seconds += dt;
+            const RayTracingCounters& c = vp.GetCounters();
+            rays += c.numRays; shadow += c.numShadowRays; shadowHit += c.numShadowRaysHit; primary += c.numPrimaryRays;
+        }
+    }
+    if (script) fclose(script);
+
+    if (a.Has("dump-sum"))
+    {
+        FILE* f = fopen(a.Str("dump-sum").c_str(), "wb");
+        WriteBytes(f, vp.GetSumBuffer().GetData(), (size_t)w * h * 12);
+        fclose(f);
+    }
+    if (a.Has("dump-sum2"))
+    {
+        FILE* f = fopen(a.Str("dump-sum2").c_str(), "wb");
+        WriteBytes(f, vp.mSecondarySum.GetData(), (size_t)w * h * 12);
+        fclose(f);
+    }
+    printf("{\"scene\": \"%s\", \"width\": %u, \"height\": %u, \"passes\": %u, \"renderer\": \"%s\", \"threads\": %u, "
+           "\"seconds\": %.6f, \"numPrimaryRays\": %llu, \"numRays\": %llu, \"numShadowRays\": %llu, \"numShadowRaysHit\": %llu, "
+           "\"mrays_per_s\": %.4f, \"msamples_per_s\": %.4f}\n",
+           a.Str("scene").c_str(), w, h, passes, rendererName.c_str(), params.numThreads, seconds,
+           (unsigned long long)primary, (unsigned long long)rays, (unsigned long long)shadow, (unsigned long long)shadowHit,
+           seconds > 0 ? (rays + shadow) / seconds * 1e-6 : 0.0, seconds > 0 ? primary / seconds * 1e-6 : 0.0);
+    return 0;
+}
+
+int CmdFlat(const Args& a)
+{
+    const uint32 w = (uint32)a.Int("width", 256), h = (uint32)a.Int("height", 256);
+    Scene scene; Camera camera;
+    if (!LoadSceneFile(a, scene, camera, w, h)) return 1;
+    Flat flat;
+    flat.Build(scene);
+    flat.Write(a.Str("out").c_str(), camera);
+    printf("{\"objects\": %zu, \"shapes\": %zu, \"meshes\": %zu, \"materials\": %zu, \"lights\": %zu, \"tlasNodes\": %zu}\n",
+           flat.objects.size(), flat.shapes.size(), flat.meshes.size(), flat.materials.size(), flat.lights.size(), flat.tlas.size());
+    return 0;
+}
+
+Ray ToRay(const RtbRay& r)
+{
+    Ray ray;
+    ray.origin = Vector4(r.origin);
+    ray.dir = Vector4(r.dir);
+    ray.invDir = Vector4(r.invDir);
+    ray.originDivDir = Vector4(r.originDivDir);
+    return ray;
+}
+
+void FromRay(const Ray& ray, RtbRay& r)
+{
+    ToF4(ray.origin, r.origin); ToF4(ray.dir, r.dir); ToF4(ray.invDir, r.invDir); ToF4(ray.originDivDir, r.originDivDir);
+}
+
+int CmdTrace(const Args& a)
+{
+    Scene scene; Camera camera;
+    if (!LoadSceneFile(a, scene, camera, 256, 256)) return 1;
+    FILE* f = fopen(a.Str("rays").c_str(), "rb");
+    if (!f) Die("cannot open rays");
+    fseek(f, 0, SEEK_END); const size_t bytes = ftell(f); fseek(f, 0, SEEK_SET);
+    const size_t n = bytes / sizeof(RtbRay);
+    std::vector<RtbRay> rays(n);
+    if (n && fread(rays.data(), sizeof(RtbRay), n, f) != n) Die("read failed");
+    fclose(f);
+    // shadow mode: per-ray tMax comes from a parallel float file (HitPoint::distance preset, PathTracerMIS.cpp:86)
+    const bool shadow = a.Int("shadow", 0) != 0;
+    std::vector<float> tmax(n, std::numeric_limits<float>::infinity());
+    if (a.Has("tmax"))
+    {
+        FILE* tf = fopen(a.Str("tmax").c_str(), "rb");
+        if (!tf || fread(tmax.data(), 4, n, tf) != n) Die("cannot read tmax");
+        fclose(tf);
+    }
+    std::vector<RtbHit> hits(n);
+    RenderingContext ctx;
+    Timer t;
+    for (size_t i = 0; i < n; ++i)
+    {
+        const Ray ray = ToRay(rays[i]);
+        HitPoint hp;
+        hp.u = 0.0f; hp.v = 0.0f; hp.subObjectId = 0;
+        RtbHit& o = hits[i];
+        memset(&o, 0, sizeof(o));
+        if (shadow)
+        {
+            hp.distance = tmax[i];
+            o.occluded = scene.Traverse_Shadow({ ray, hp, ctx }) ? 1u : 0u;
+        }
+        else
+        {
+            scene.Traverse({ ray, hp, ctx });
+        }
+        o.objectId = hp.objectId; o.subObjectId = hp.subObjectId; o.distance = hp.distance; o.u = hp.u; o.v = hp.v;
+    }
+    const double s = t.Stop();
+    FILE* of = fopen(a.Str("out").c_str(), "wb");
+    WriteBytes(of, hits.data(), n * sizeof(RtbHit));
+    fclose(of);
+    printf("{\"rays\": %zu, \"seconds\": %.6f, \"mrays_per_s\": %.4f}\n", n, s, s > 0 ? n / s * 1e-6 : 0.0);
+    return 0;
+}
+
+// pass script reader (written by CmdRender --dump-passes)
+struct PassScript
+{
+    uint32 numPasses = 0, numDims = 0;
+    std::vector<uint32> seeds;
+    std::vector<float> offsets;
+    void Load(const std::string& path)
+    {
+        FILE* f = fopen(path.c_str(), "rb");
+        if (!f) Die("cannot open pass script");
+        if (fread(&numPasses, 4, 1, f) != 1 || fread(&numDims, 4, 1, f) != 1) Die("bad pass script");
+        seeds.resize((size_t)numPasses * numDims); offsets.resize((size_t)numPasses * 2);
+        for (uint32 p = 0; p < numPasses; ++p)
+        {
+            if (fread(&seeds[(size_t)p * numDims], 4, numDims, f) != numDims) Die("bad pass script");
+            if (fread(&offsets[(size_t)p * 2], 4, 2, f) != 2) Die("bad pass script");
+        }
+        fclose(f);
+    }
+};
+
+int CmdSampler(const Args& a)
+{
+    // streams for a grid of pixels: out[pass][pixel][dim]
+    PassScript ps; ps.Load(a.Str("passes"));
+    const uint32 w = (uint32)a.Int("width", 16), h = (uint32)a.Int("height", 16), nd = (uint32)a.Int("num-dims", 16);
+    const bool blue = a.Int("blue-noise", 1) != 0;
+    FILE* of = fopen(a.Str("out").c_str(), "wb");
+    GenericSampler sampler;
+    Random fallback;
+    sampler.fallbackGenerator = &fallback;
+    for (uint32 p = 0; p < ps.numPasses; ++p)
+    {
+        DynArray<uint32> seed(ps.numDims);
+        for (uint32 d = 0; d < ps.numDims; ++d) seed[d] = ps.seeds[(size_t)p * ps.numDims + d];
+        sampler.ResetFrame(seed, blue);
+        for (uint32 y = 0; y < h; ++y) for (uint32 x = 0; x < w; ++x)
+        {
+            sampler.ResetPixel(x, y);
+            for (uint32 d = 0; d < nd; ++d) WriteU32(of, sampler.GetInt());
+        }
+    }
+    fclose(of);
+    return 0;
+}
+
+int CmdPrimary(const Args& a)
+{
+    const uint32 w = (uint32)a.Int("width", 64), h = (uint32)a.Int("height", 64);
+    Scene scene; Camera camera;
+    if (!LoadSceneFile(a, scene, camera, w, h)) return 1;
+    PassScript ps; ps.Load(a.Str("passes"));
+    const uint32 pass = (uint32)a.Int("pass", 0);
+    RenderingContext ctx;
+    DynArray<uint32> seed(ps.numDims);
+    for (uint32 d = 0; d < ps.numDims; ++d) seed[d] = ps.seeds[(size_t)pass * ps.numDims + d];
+    ctx.sampler.ResetFrame(seed, a.Int("blue-noise", 1) != 0);
+    ctx.sampler.fallbackGenerator = &ctx.randomGenerator;
+    const Vector4 sampleOffset(ps.offsets[pass * 2], ps.offsets[pass * 2 + 1], 0.0f, 0.0f);
+    // mirrors Viewport::RenderTile (Viewport.cpp:300-330)
+    const Vector4 filmSize = Vector4::FromIntegers(w, h, 1, 1);
+    const Vector4 invSize = VECTOR_ONE2 / filmSize;
+    std::vector<RtbRay> rays((size_t)w * h);
+    for (uint32 y = 0; y < h; ++y)
+    {
+        const uint32 realY = h - 1u - y;
+        for (uint32 x = 0; x < w; ++x)
+        {
+            const Vector4 coords = (Vector4::FromIntegers(x, realY, 0, 0) + sampleOffset) * invSize;
+            ctx.sampler.ResetPixel(x, y);
+            ctx.time = 0.0f;
+            const Ray ray = camera.GenerateRay(coords, ctx);
+            FromRay(ray, rays[(size_t)y * w + x]);
+        }
+    }
+    FILE* of = fopen(a.Str("out").c_str(), "wb");
+    WriteBytes(of, rays.data(), rays.size() * sizeof(RtbRay));
+    fclose(of);
+    return 0;
+}
+
+} // namespace
+
+static void CrashHandler(int sig)
+{
+    void* frames[64];
+    const int n = backtrace(frames, 64);
+    fprintf(stderr, "rtref: fatal signal %d\n", sig);
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+
+int main(int argc, char** argv)
+{
+    signal(SIGSEGV, CrashHandler);
+    signal(SIGILL, CrashHandler);
+    SetFlushDenormalsToZero();
+    InitMemory();
+    const Args a = ParseArgs(argc, argv);
+    if (a.cmd == "render") return CmdRender(a);
+    if (a.cmd == "flat") return CmdFlat(a);
+    if (a.cmd == "trace") return CmdTrace(a);
+    if (a.cmd == "sampler") return CmdSampler(a);
+    if (a.cmd == "primary") return CmdPrimary(a);
+    fprintf(stderr, "usage: rtref render|flat|trace|sampler|primary --scene X.json [options]\n");
+    return 2;
+}
