@@ -1,0 +1,301 @@
+// hostsim — g++ build of the DEVICE headers (raytracer_b200/csrc/rtb_*.h), one pixel at a time on the CPU.
+//
+// TEST TOOL ONLY.  The authoring container has no GPU, so the numerics of the device code (operation order, FMA
+// placement, SSE min/max semantics ...) are debugged here against the oracle before a B200 run.  It is NOT part of
+// the product: librtb200.so does not contain it, the raytracer_b200 package cannot reach it, and rtb_create() fails
+// without a CUDA device.  Built by tests/hostsim/build.sh, used by tests/test_hostsim_parity.py.
+//
+//   hostsim render <scene.rtb> <passes.bin> <width> <height> <out.sum> [renderer 0|1|2] [maxDepth] [debugMode] [strategyAll]
+//   hostsim trace  <scene.rtb> <rays.bin> <out.hits> [shadow tmax.bin]
+//   hostsim sampler <passes.bin> <w> <h> <numDims> <out.u32> <bluenoise.dat|->
+//   hostsim primary <scene.rtb> <passes.bin> <pass> <w> <h> <out.rays>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <xmmintrin.h>
+#include <pmmintrin.h>
+
+#include "../../raytracer_b200/csrc/rtb_integrator.h"
+#include "../../raytracer_b200/csrc/rtb_upload.h"
+#include "../../raytracer_b200/csrc/rtb_scene_file.h"
+
+using namespace rtb;
+
+static void die(const std::string& m) { fprintf(stderr, "hostsim: %s\n", m.c_str()); exit(1); }
+
+struct Passes
+{
+    uint32_t numPasses = 0, numDims = 0;
+    std::vector<uint32_t> seeds;
+    std::vector<float> offsets;
+    void load(const char* path)
+    {
+        FILE* f = fopen(path, "rb");
+        if (!f) die("cannot open passes");
+        if (fread(&numPasses, 4, 1, f) != 1 || fread(&numDims, 4, 1, f) != 1) die("bad passes");
+        seeds.resize((size_t)numPasses * numDims); offsets.resize((size_t)numPasses * 2);
+        for (uint32_t p = 0; p < numPasses; ++p)
+        {
+            if (fread(&seeds[(size_t)p * numDims], 4, numDims, f) != numDims) die("bad passes");
+            if (fread(&offsets[(size_t)p * 2], 4, 2, f) != 2) die("bad passes");
+        }
+        fclose(f);
+    }
+};
+
+struct World
+{
+    SceneFile file;
+    HostScene hs;
+    std::vector<DMesh> meshViews;
+    std::vector<uint16_t> blueNoise;
+    SceneView S;
+
+    void load(const char* path)
+    {
+        std::string err;
+        if (!file.Load(path, err)) die(err);
+        const RtbSceneDesc d = file.View();
+        if (!build_host_scene(d, hs, err)) die(err);
+        meshViews.resize(hs.meshes.size());
+        for (size_t i = 0; i < hs.meshes.size(); ++i)
+        {
+            DMesh& v = meshViews[i];
+            const HostMesh& m = hs.meshes[i];
+            v.nodes = m.nodes.data(); v.tris = m.tris.data(); v.indices = m.indices.data(); v.shading = m.shading.data();
+            v.materialIds = m.materialIds.data();
+            v.numNodes = (uint32_t)m.nodes.size(); v.numTriangles = (uint32_t)m.tris.size();
+            v.numVertices = (uint32_t)m.shading.size(); v.numMaterials = (uint32_t)m.materialIds.size();
+        }
+        memset(&S, 0, sizeof(S));
+        S.tlas = hs.tlas.data(); S.objTrace = hs.objTrace.data(); S.objShade = hs.objShade.data();
+        S.shapes = hs.shapes.data(); S.meshes = meshViews.data(); S.materials = hs.materials.data();
+        S.lights = hs.lights.data(); S.globalLights = hs.globalLights.data();
+        S.numTlasNodes = (uint32_t)hs.tlas.size(); S.numObjects = (uint32_t)hs.objTrace.size();
+        S.numLights = (uint32_t)hs.lights.size(); S.numGlobalLights = (uint32_t)hs.globalLights.size();
+        S.blueNoise = nullptr;
+    }
+
+    void loadBlueNoise(const char* path)
+    {
+        FILE* f = fopen(path, "rb");
+        if (!f) return;
+        blueNoise.resize(128 * 128 * 4);
+        if (fread(blueNoise.data(), 2, blueNoise.size(), f) != blueNoise.size()) die("bad blue noise file");
+        fclose(f);
+        S.blueNoise = blueNoise.data();
+    }
+};
+
+static void fillCamera(PassParams& P, const RtbCamera& c, uint32_t w, uint32_t h, float tanHalfFoV)
+{
+    P.camLocalToWorld = load_m4(c.localToWorld);
+    P.aspectRatio = (float)w / (float)h;
+    P.tanHalfFoV = tanHalfFoV;
+    P.dofEnable = c.dofEnable; P.bokehShape = c.bokehShape; P.aperture = c.aperture; P.focalPlaneDistance = c.focalPlaneDistance;
+    P.barrelConst = c.barrelDistortionConstFactor; P.barrelVar = c.barrelDistortionVariableFactor;
+    P.width = w; P.height = h;
+}
+
+// immediate-mode sink: shadow rays are traced on the spot, in light order
+struct HostSink
+{
+    const SceneView& S;
+    V3 result;
+    V4 lightSum;
+    uint64_t shadowRays = 0, shadowRaysHit = 0;
+    explicit HostSink(const SceneView& s) : S(s) { result = v3s(0.0f); lightSum = v4s(0.0f); }
+    void add(const V4& thr, const V4& c) { result = mul_add(xyz(thr), xyz(c), result); }
+    void shadow(const Ray& ray, float tMax, const V4& contribution)
+    {
+        shadowRays++;
+        const bool occluded = scene_traverse_shadow<false>(S, ray, tMax, nullptr);
+        if (!occluded) { shadowRaysHit++; lightSum = lightSum + contribution; }
+        else lightSum = lightSum + v4s(0.0f);
+    }
+    void end_lights(const V4& thr)
+    {
+        result = mul_add(xyz(thr), xyz(lightSum), result);
+        lightSum = v4s(0.0f);
+    }
+};
+
+static int cmdRender(int argc, char** argv)
+{
+    if (argc < 7) die("usage: render scene passes w h out [renderer] [depth] [debugMode] [all] [bluenoise] [fovTan]");
+    World world; world.load(argv[2]);
+    Passes passes; passes.load(argv[3]);
+    const uint32_t w = atoi(argv[4]), h = atoi(argv[5]);
+    const uint32_t renderer = argc > 7 ? atoi(argv[7]) : 1;
+    const uint32_t maxDepth = argc > 8 ? atoi(argv[8]) : 8;
+    const uint32_t debugMode = argc > 9 ? atoi(argv[9]) : 1;
+    const uint32_t all = argc > 10 ? atoi(argv[10]) : 1;
+    if (argc > 11 && strcmp(argv[11], "-") != 0) world.loadBlueNoise(argv[11]);
+
+    PassParams P;
+    memset(&P, 0, sizeof(P));
+    fillCamera(P, world.file.camera, w, h, tanf(world.file.fieldOfView * 0.5f));
+    P.renderer = renderer; P.debugMode = debugMode; P.maxRayDepth = maxDepth; P.minRussianRouletteDepth = 1;
+    P.lightSamplingAll = all; P.useBlueNoise = world.S.blueNoise != nullptr; P.numSeedDims = passes.numDims;
+
+    std::vector<float> sum((size_t)w * h * 3, 0.0f);
+    uint64_t numRays = 0, numShadow = 0, numShadowHit = 0;
+    for (uint32_t p = 0; p < passes.numPasses; ++p)
+    {
+        P.passIndex = p;
+        P.seed = &passes.seeds[(size_t)p * passes.numDims];
+        P.sampleOffsetX = passes.offsets[p * 2]; P.sampleOffsetY = passes.offsets[p * 2 + 1];
+        for (uint32_t y = 0; y < h; ++y) for (uint32_t x = 0; x < w; ++x)
+        {
+            PathState ps;
+            init_path(P, world.S.blueNoise, x, y, ps);
+            HostSink sink(world.S);
+            for (;;)
+            {
+                Hit hit;
+                hit.objectId = RTB_INVALID_OBJECT; hit.subObjectId = 0; hit.distance = INFINITY; hit.u = 0.0f; hit.v = 0.0f;
+                scene_traverse<false>(world.S, ps.ray, hit, nullptr);
+                bool alive = false;
+                uint32_t ns = 0;
+                if (renderer == RTB_RENDERER_PATH_TRACER_MIS) alive = shade_vertex_mis(world.S, P, ps, hit, sink, ns);
+                else if (renderer == RTB_RENDERER_PATH_TRACER) alive = shade_vertex_pt(world.S, P, ps, hit, sink);
+                else shade_debug(world.S, P, ps, hit, sink);
+                if (!alive) break;
+            }
+            numRays += (uint64_t)ps.depth + 1;
+            numShadow += sink.shadowRays; numShadowHit += sink.shadowRaysHit;
+            float* px = &sum[((size_t)y * w + x) * 3];
+            px[0] = px[0] + sink.result.x; px[1] = px[1] + sink.result.y; px[2] = px[2] + sink.result.z;
+        }
+    }
+    FILE* f = fopen(argv[6], "wb");
+    fwrite(sum.data(), 4, sum.size(), f);
+    fclose(f);
+    printf("{\"numRays\": %llu, \"numShadowRays\": %llu, \"numShadowRaysHit\": %llu}\n",
+           (unsigned long long)numRays, (unsigned long long)numShadow, (unsigned long long)numShadowHit);
+    return 0;
+}
+
+static int cmdTrace(int argc, char** argv)
+{
+    if (argc < 5) die("usage: trace scene rays out [tmax]");
+    World world; world.load(argv[2]);
+    FILE* f = fopen(argv[3], "rb");
+    if (!f) die("cannot open rays");
+    fseek(f, 0, SEEK_END); const size_t n = ftell(f) / sizeof(RtbRay); fseek(f, 0, SEEK_SET);
+    std::vector<RtbRay> rays(n);
+    if (n && fread(rays.data(), sizeof(RtbRay), n, f) != n) die("read failed");
+    fclose(f);
+    const bool shadow = argc > 5;
+    std::vector<float> tmax(n, INFINITY);
+    if (shadow)
+    {
+        FILE* tf = fopen(argv[5], "rb");
+        if (!tf || fread(tmax.data(), 4, n, tf) != n) die("cannot read tmax");
+        fclose(tf);
+    }
+    std::vector<RtbHit> hits(n);
+    for (size_t i = 0; i < n; ++i)
+    {
+        Ray r;
+        r.origin = v3(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]);
+        r.dir = v3(rays[i].dir[0], rays[i].dir[1], rays[i].dir[2]);
+        r.invDir = v3(rays[i].invDir[0], rays[i].invDir[1], rays[i].invDir[2]);
+        r.originDivDir = v3(rays[i].originDivDir[0], rays[i].originDivDir[1], rays[i].originDivDir[2]);
+        Hit hit;
+        hit.objectId = RTB_INVALID_OBJECT; hit.subObjectId = 0; hit.distance = INFINITY; hit.u = 0.0f; hit.v = 0.0f;
+        RtbHit& o = hits[i];
+        memset(&o, 0, sizeof(o));
+        if (shadow) { hit.distance = tmax[i]; o.occluded = scene_traverse_shadow<false>(world.S, r, tmax[i], nullptr) ? 1u : 0u; }
+        else scene_traverse<false>(world.S, r, hit, nullptr);
+        o.objectId = hit.objectId; o.subObjectId = hit.subObjectId; o.distance = hit.distance; o.u = hit.u; o.v = hit.v;
+    }
+    FILE* of = fopen(argv[4], "wb");
+    fwrite(hits.data(), sizeof(RtbHit), n, of);
+    fclose(of);
+    return 0;
+}
+
+static int cmdSampler(int argc, char** argv)
+{
+    if (argc < 8) die("usage: sampler passes w h numDims out bluenoise|-");
+    Passes passes; passes.load(argv[2]);
+    const uint32_t w = atoi(argv[3]), h = atoi(argv[4]), nd = atoi(argv[5]);
+    std::vector<uint16_t> bn;
+    if (strcmp(argv[7], "-") != 0)
+    {
+        FILE* f = fopen(argv[7], "rb");
+        if (!f) die("cannot open blue noise");
+        bn.resize(128 * 128 * 4);
+        if (fread(bn.data(), 2, bn.size(), f) != bn.size()) die("bad blue noise");
+        fclose(f);
+    }
+    FILE* of = fopen(argv[6], "wb");
+    PassParams P;
+    memset(&P, 0, sizeof(P));
+    P.numSeedDims = passes.numDims; P.useBlueNoise = !bn.empty();
+    for (uint32_t p = 0; p < passes.numPasses; ++p)
+    {
+        P.seed = &passes.seeds[(size_t)p * passes.numDims];
+        for (uint32_t y = 0; y < h; ++y) for (uint32_t x = 0; x < w; ++x)
+        {
+            Sampler s;
+            sampler_reset_pixel(s, x, y);
+            for (uint32_t d = 0; d < nd; ++d)
+            {
+                const uint32_t v = sampler_get_int(s, P, bn.empty() ? nullptr : bn.data());
+                fwrite(&v, 4, 1, of);
+            }
+        }
+    }
+    fclose(of);
+    return 0;
+}
+
+static int cmdPrimary(int argc, char** argv)
+{
+    if (argc < 8) die("usage: primary scene passes pass w h out");
+    World world; world.load(argv[2]);
+    Passes passes; passes.load(argv[3]);
+    const uint32_t pass = atoi(argv[4]), w = atoi(argv[5]), h = atoi(argv[6]);
+    PassParams P;
+    memset(&P, 0, sizeof(P));
+    fillCamera(P, world.file.camera, w, h, tanf(world.file.fieldOfView * 0.5f));
+    P.numSeedDims = passes.numDims;
+    P.seed = &passes.seeds[(size_t)pass * passes.numDims];
+    P.sampleOffsetX = passes.offsets[pass * 2]; P.sampleOffsetY = passes.offsets[pass * 2 + 1];
+    std::vector<RtbRay> rays((size_t)w * h);
+    for (uint32_t y = 0; y < h; ++y) for (uint32_t x = 0; x < w; ++x)
+    {
+        Sampler s;
+        sampler_reset_pixel(s, x, y);
+        const Ray r = generate_primary_ray(P, x, y, s, nullptr);
+        RtbRay& o = rays[(size_t)y * w + x];
+        memset(&o, 0, sizeof(o));
+        o.origin[0] = r.origin.x; o.origin[1] = r.origin.y; o.origin[2] = r.origin.z;
+        o.dir[0] = r.dir.x; o.dir[1] = r.dir.y; o.dir[2] = r.dir.z;
+        o.invDir[0] = r.invDir.x; o.invDir[1] = r.invDir.y; o.invDir[2] = r.invDir.z;
+        o.originDivDir[0] = r.originDivDir.x; o.originDivDir[1] = r.originDivDir.y; o.originDivDir[2] = r.originDivDir.z;
+    }
+    FILE* of = fopen(argv[7], "wb");
+    fwrite(rays.data(), sizeof(RtbRay), rays.size(), of);
+    fclose(of);
+    return 0;
+}
+
+int main(int argc, char** argv)
+{
+    // the reference runs with FTZ + DAZ (Core/Math/Math.cpp:27-34); the CUDA build uses -ftz=true
+    _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);
+    _MM_SET_DENORMALS_ZERO_MODE(_MM_DENORMALS_ZERO_ON);
+    if (argc < 2) die("usage: hostsim render|trace|sampler|primary ...");
+    const std::string cmd = argv[1];
+    if (cmd == "render") return cmdRender(argc, argv);
+    if (cmd == "trace") return cmdTrace(argc, argv);
+    if (cmd == "sampler") return cmdSampler(argc, argv);
+    if (cmd == "primary") return cmdPrimary(argc, argv);
+    die("unknown command");
+    return 2;
+}
