@@ -1,0 +1,361 @@
+"""ctypes binding of the C ABI declared in include/rtb200.h (librtb200.so, CUDA sm_100a).
+
+This is plumbing for tests and bench.py: every call goes straight into the extern "C" entry points, the same ones a
+C++ host (raytracer_b200/host) or the reference's own Viewport would bind.  There is no CPU fallback: if the shared
+library is missing or no CUDA device is present the calls fail loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librtb200.so")
+
+RTB_INVALID_OBJECT = 0xFFFFFFFF
+RTB_LIGHT_OBJECT = 0xFFFFFFFE
+RTB_RENDERER_PATH_TRACER, RTB_RENDERER_PATH_TRACER_MIS, RTB_RENDERER_DEBUG = 0, 1, 2
+RTB_TRACE_CLOSEST, RTB_TRACE_SHADOW = 0, 1
+RTB_LIGHT_SAMPLING_SINGLE, RTB_LIGHT_SAMPLING_ALL = 0, 1
+RTB_FLAG_COUNT_TESTS = 1
+RENDERER_NAMES = {"Path Tracer": 0, "Path Tracer MIS": 1, "Debug": 2}   # CreateRenderer names, Renderer.cpp:45-69
+
+
+class RtbBvhNode(C.Structure):
+    _fields_ = [("min", C.c_float * 3), ("childIndex", C.c_uint32), ("max", C.c_float * 3), ("leafInfo", C.c_uint32)]
+
+
+class RtbMat4(C.Structure):
+    _fields_ = [("r", (C.c_float * 4) * 4)]
+
+
+class RtbShape(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("meshIndex", C.c_uint32), ("pad0", C.c_uint32), ("pad1", C.c_uint32),
+                ("size", C.c_float * 4), ("invSize", C.c_float * 4), ("aux", C.c_float * 4)]
+
+
+class RtbMaterial(C.Structure):
+    _fields_ = [("bsdf", C.c_uint32), ("flags", C.c_uint32), ("roughness", C.c_float), ("metalness", C.c_float),
+                ("baseColor", C.c_float * 4), ("emission", C.c_float * 4), ("IoR", C.c_float), ("K", C.c_float),
+                ("pad0", C.c_float), ("pad1", C.c_float)]
+
+
+class RtbLight(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("flags", C.c_uint32), ("shapeIndex", C.c_uint32), ("isDelta", C.c_uint32),
+                ("color", C.c_float * 4), ("cosAngle", C.c_float), ("pad0", C.c_float), ("pad1", C.c_float), ("pad2", C.c_float),
+                ("transform", RtbMat4), ("invTransform", RtbMat4)]
+
+
+class RtbObject(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("shapeIndex", C.c_uint32), ("materialIndex", C.c_uint32), ("lightIndex", C.c_uint32),
+                ("transform", RtbMat4), ("invTransform", RtbMat4)]
+
+
+class RtbMesh(C.Structure):
+    _fields_ = [("numNodes", C.c_uint32), ("numTriangles", C.c_uint32), ("numVertices", C.c_uint32), ("numMaterials", C.c_uint32),
+                ("nodes", C.c_void_p), ("triangles", C.c_void_p), ("indices", C.c_void_p), ("shading", C.c_void_p),
+                ("materialIds", C.c_void_p)]
+
+
+class RtbSceneDesc(C.Structure):
+    _fields_ = [("numTlasNodes", C.c_uint32), ("tlasNodes", C.c_void_p),
+                ("numObjects", C.c_uint32), ("objects", C.c_void_p),
+                ("numShapes", C.c_uint32), ("shapes", C.c_void_p),
+                ("numMeshes", C.c_uint32), ("meshes", C.c_void_p),
+                ("numMaterials", C.c_uint32), ("materials", C.c_void_p),
+                ("numLights", C.c_uint32), ("lights", C.c_void_p),
+                ("numGlobalLights", C.c_uint32), ("globalLights", C.c_void_p)]
+
+
+class RtbCamera(C.Structure):
+    _fields_ = [("localToWorld", RtbMat4), ("aspectRatio", C.c_float), ("tanHalfFoV", C.c_float),
+                ("dofEnable", C.c_uint32), ("bokehShape", C.c_uint32), ("aperture", C.c_float),
+                ("focalPlaneDistance", C.c_float), ("barrelDistortionConstFactor", C.c_float),
+                ("barrelDistortionVariableFactor", C.c_float)]
+
+
+class RtbPassDesc(C.Structure):
+    _fields_ = [("renderer", C.c_uint32), ("debugMode", C.c_uint32), ("camera", RtbCamera),
+                ("maxRayDepth", C.c_uint32), ("minRussianRouletteDepth", C.c_uint32),
+                ("lightSamplingStrategy", C.c_uint32), ("useBlueNoise", C.c_uint32),
+                ("passIndex", C.c_uint32), ("numSeedDims", C.c_uint32), ("seed", C.c_void_p),
+                ("sampleOffset", C.c_float * 2)]
+
+
+class RtbCounters(C.Structure):
+    _fields_ = [("numRays", C.c_uint64), ("numShadowRays", C.c_uint64), ("numShadowRaysHit", C.c_uint64),
+                ("numPrimaryRays", C.c_uint64), ("numRayBoxTests", C.c_uint64), ("numRayTriangleTests", C.c_uint64)]
+
+
+class RtbCreateDesc(C.Structure):
+    _fields_ = [("deviceId", C.c_int32), ("flags", C.c_uint32), ("numShards", C.c_uint32), ("shardIndex", C.c_uint32),
+                ("tileSize", C.c_uint32), ("stream", C.c_void_p)]
+
+
+class RtbPassTimings(C.Structure):
+    _fields_ = [("raygenMs", C.c_float), ("traverseMs", C.c_float), ("shadeMs", C.c_float), ("shadowMs", C.c_float),
+                ("totalMs", C.c_float), ("traverseLaunches", C.c_uint32), ("shadeLaunches", C.c_uint32),
+                ("shadowLaunches", C.c_uint32), ("totalLaunches", C.c_uint32), ("traverseRays", C.c_uint64),
+                ("shadowRays", C.c_uint64)]
+
+
+RAY_DTYPE = np.dtype([("origin", np.float32, 4), ("dir", np.float32, 4), ("invDir", np.float32, 4), ("originDivDir", np.float32, 4)])
+HIT_DTYPE = np.dtype([("objectId", np.uint32), ("subObjectId", np.uint32), ("distance", np.float32), ("u", np.float32),
+                      ("v", np.float32), ("occluded", np.uint32)])
+
+# every symbol include/rtb200.h declares (checked by tests/test_capi_symbols.py)
+EXPORTED_SYMBOLS = [
+    "rtb_last_error", "rtb_api_version", "rtb_create", "rtb_destroy", "rtb_upload_scene", "rtb_set_blue_noise",
+    "rtb_resize", "rtb_reset", "rtb_render_pass", "rtb_synchronize", "rtb_read_sum", "rtb_film_device_buffer",
+    "rtb_unshard_film", "rtb_get_counters", "rtb_trace_batch", "rtb_trace_batch_device", "rtb_sample_batch",
+    "rtb_primary_rays", "rtb_set_profiling", "rtb_get_pass_timings",
+]
+
+_lib = None
+
+
+class RtbError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """dlopen librtb200.so (no fallback: raises if it has not been built)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RtbError("%s not found - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(raytracer_b200/csrc/build.sh); there is no CPU fallback" % p)
+    lib = C.CDLL(p)
+    lib.rtb_last_error.restype = C.c_char_p
+    lib.rtb_api_version.restype = C.c_int
+    lib.rtb_create.argtypes = [C.POINTER(RtbCreateDesc), C.POINTER(C.c_void_p)]
+    lib.rtb_destroy.argtypes = [C.c_void_p]
+    lib.rtb_destroy.restype = None
+    lib.rtb_upload_scene.argtypes = [C.c_void_p, C.POINTER(RtbSceneDesc)]
+    lib.rtb_set_blue_noise.argtypes = [C.c_void_p, C.c_void_p]
+    lib.rtb_resize.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    lib.rtb_reset.argtypes = [C.c_void_p]
+    lib.rtb_render_pass.argtypes = [C.c_void_p, C.POINTER(RtbPassDesc)]
+    lib.rtb_synchronize.argtypes = [C.c_void_p]
+    lib.rtb_read_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.rtb_film_device_buffer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.rtb_unshard_film.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.rtb_get_counters.argtypes = [C.c_void_p, C.POINTER(RtbCounters)]
+    lib.rtb_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
+    lib.rtb_trace_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
+    lib.rtb_sample_batch.argtypes = [C.c_void_p, C.POINTER(RtbPassDesc), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+    lib.rtb_primary_rays.argtypes = [C.c_void_p, C.POINTER(RtbPassDesc), C.c_void_p]
+    lib.rtb_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    lib.rtb_get_pass_timings.argtypes = [C.c_void_p, C.POINTER(RtbPassTimings)]
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _check(lib, rc):
+    if rc != 0:
+        raise RtbError("rtb error %d: %s" % (rc, lib.rtb_last_error().decode()))
+
+
+# ---- "RTBS" flat scene files (raytracer_b200/csrc/rtb_scene_file.h) ------------------------------------------------
+
+class SceneFile:
+    """Parsed RTBS file: numpy views of every array + a ctypes RtbSceneDesc pointing into them."""
+
+    def __init__(self, path):
+        data = np.fromfile(path, dtype=np.uint8)
+        self._buf = data
+        pos = 0
+
+        def u32():
+            nonlocal pos
+            v = int(data[pos:pos + 4].view(np.uint32)[0])
+            pos += 4
+            return v
+
+        def arr(nbytes):
+            nonlocal pos
+            a = np.ascontiguousarray(data[pos:pos + nbytes])
+            pos += nbytes
+            return a
+
+        assert u32() == 0x53425452 and u32() == 1, "not an RTBS v1 file"
+        n = u32(); self.tlas = arr(n * C.sizeof(RtbBvhNode)); self.num_tlas = n
+        n = u32(); self.objects = arr(n * C.sizeof(RtbObject)); self.num_objects = n
+        n = u32(); self.shapes = arr(n * C.sizeof(RtbShape)); self.num_shapes = n
+        self.meshes = []
+        for _ in range(u32()):
+            nn, nt, nv, nm = u32(), u32(), u32(), u32()
+            self.meshes.append(dict(numNodes=nn, numTriangles=nt, numVertices=nv, numMaterials=nm,
+                                    nodes=arr(nn * 32), triangles=arr(nt * 36), indices=arr(nt * 16),
+                                    shading=arr(nv * 32), materialIds=arr(nm * 4)))
+        n = u32(); self.materials = arr(n * C.sizeof(RtbMaterial)); self.num_materials = n
+        n = u32(); self.lights = arr(n * C.sizeof(RtbLight)); self.num_lights = n
+        n = u32(); self.global_lights = arr(n * 4); self.num_global_lights = n
+        self.camera = RtbCamera.from_buffer_copy(arr(C.sizeof(RtbCamera)).tobytes())
+        self.field_of_view = float(arr(4).view(np.float32)[0])
+        self.num_triangles = sum(m["numTriangles"] for m in self.meshes)
+
+    def desc(self):
+        self._mesh_structs = (RtbMesh * max(1, len(self.meshes)))()
+        for i, m in enumerate(self.meshes):
+            s = self._mesh_structs[i]
+            s.numNodes, s.numTriangles, s.numVertices, s.numMaterials = m["numNodes"], m["numTriangles"], m["numVertices"], m["numMaterials"]
+            s.nodes, s.triangles, s.indices = m["nodes"].ctypes.data, m["triangles"].ctypes.data, m["indices"].ctypes.data
+            s.shading, s.materialIds = m["shading"].ctypes.data, m["materialIds"].ctypes.data
+        d = RtbSceneDesc()
+        d.numTlasNodes, d.tlasNodes = self.num_tlas, self.tlas.ctypes.data
+        d.numObjects, d.objects = self.num_objects, self.objects.ctypes.data
+        d.numShapes, d.shapes = self.num_shapes, self.shapes.ctypes.data
+        d.numMeshes, d.meshes = len(self.meshes), C.addressof(self._mesh_structs)
+        d.numMaterials, d.materials = self.num_materials, self.materials.ctypes.data
+        d.numLights, d.lights = self.num_lights, self.lights.ctypes.data
+        d.numGlobalLights, d.globalLights = self.num_global_lights, self.global_lights.ctypes.data
+        return d
+
+
+class PassScript:
+    """Per-pass Halton seed vectors + AA offsets (written by the oracle's `rtref render --dump-passes`)."""
+
+    def __init__(self, path=None, seeds=None, offsets=None):
+        if path is not None:
+            raw = np.fromfile(path, dtype=np.uint32)
+            self.num_passes, self.num_dims = int(raw[0]), int(raw[1])
+            body = raw[2:].reshape(self.num_passes, self.num_dims + 2)
+            self.seeds = np.ascontiguousarray(body[:, :self.num_dims])
+            self.offsets = np.ascontiguousarray(body[:, self.num_dims:]).view(np.float32)
+        else:
+            self.seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+            self.offsets = np.ascontiguousarray(offsets, dtype=np.float32)
+            self.num_passes, self.num_dims = self.seeds.shape
+
+
+def load_blue_noise(path=None):
+    """128x128x4 uint16 table, returned in the interleaved RGBA16 order GenericSampler reads (GenericSampler.cpp:91-96)."""
+    p = path or os.path.join(_HERE, "data", "blue_noise_128.rtbn")
+    raw = np.fromfile(p, dtype=np.uint16)
+    assert raw.size == 4 + 4 * 128 * 128 and raw[0] == 0x5442 and raw[1] == 0x4E52, "bad blue noise file"
+    planar = raw[4:].reshape(4, 128, 128)
+    return np.ascontiguousarray(np.transpose(planar, (1, 2, 0)))
+
+
+class Context:
+    """Thin RAII wrapper around RtbContext*."""
+
+    def __init__(self, device=0, flags=0, num_shards=1, shard_index=0, tile_size=0, stream=None, blue_noise=True):
+        self.lib = load_library()
+        d = RtbCreateDesc(device, flags, num_shards, shard_index, tile_size, stream)
+        h = C.c_void_p()
+        _check(self.lib, self.lib.rtb_create(C.byref(d), C.byref(h)))
+        self.h = h
+        self.width = self.height = 0
+        if blue_noise:
+            bn = load_blue_noise()
+            _check(self.lib, self.lib.rtb_set_blue_noise(self.h, bn.ctypes.data))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rtb_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def upload_scene(self, scene_file):
+        d = scene_file.desc()
+        _check(self.lib, self.lib.rtb_upload_scene(self.h, C.byref(d)))
+
+    def resize(self, w, h):
+        _check(self.lib, self.lib.rtb_resize(self.h, w, h))
+        self.width, self.height = w, h
+
+    def reset(self):
+        _check(self.lib, self.lib.rtb_reset(self.h))
+
+    def make_pass(self, camera, seeds, offset, pass_index, renderer=RTB_RENDERER_PATH_TRACER_MIS, max_depth=8,
+                  rr_depth=1, strategy=RTB_LIGHT_SAMPLING_ALL, blue_noise=True, debug_mode=1):
+        p = RtbPassDesc()
+        p.renderer, p.debugMode = renderer, debug_mode
+        p.camera = camera
+        p.maxRayDepth, p.minRussianRouletteDepth = max_depth, rr_depth
+        p.lightSamplingStrategy, p.useBlueNoise = strategy, 1 if blue_noise else 0
+        p.passIndex, p.numSeedDims = pass_index, len(seeds)
+        self._seed_keepalive = np.ascontiguousarray(seeds, dtype=np.uint32)
+        p.seed = self._seed_keepalive.ctypes.data
+        p.sampleOffset[0], p.sampleOffset[1] = float(offset[0]), float(offset[1])
+        return p
+
+    def render_pass(self, p):
+        _check(self.lib, self.lib.rtb_render_pass(self.h, C.byref(p)))
+
+    def synchronize(self):
+        _check(self.lib, self.lib.rtb_synchronize(self.h))
+
+    def read_sum(self, which=0):
+        out = np.empty((self.height, self.width, 3), dtype=np.float32)
+        _check(self.lib, self.lib.rtb_read_sum(self.h, out.ctypes.data, which))
+        return out
+
+    def film_device_buffer(self, which=0):
+        p, n = C.c_void_p(), C.c_uint64()
+        _check(self.lib, self.lib.rtb_film_device_buffer(self.h, which, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def unshard_film(self, gathered_device_ptr):
+        out = np.empty((self.height, self.width, 3), dtype=np.float32)
+        _check(self.lib, self.lib.rtb_unshard_film(self.h, gathered_device_ptr, out.ctypes.data))
+        return out
+
+    def counters(self):
+        c = RtbCounters()
+        _check(self.lib, self.lib.rtb_get_counters(self.h, C.byref(c)))
+        return {k: int(getattr(c, k)) for k, _ in RtbCounters._fields_}
+
+    def trace_batch(self, rays, mode=RTB_TRACE_CLOSEST, tmax=None):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.zeros(len(rays), dtype=HIT_DTYPE)
+        if tmax is not None:
+            hits["distance"] = tmax
+        _check(self.lib, self.lib.rtb_trace_batch(self.h, rays.ctypes.data, len(rays), hits.ctypes.data, mode))
+        return hits
+
+    def trace_batch_device(self, rays_ptr, n, hits_ptr, mode=RTB_TRACE_CLOSEST):
+        ms = C.c_float()
+        _check(self.lib, self.lib.rtb_trace_batch_device(self.h, rays_ptr, n, hits_ptr, mode, C.byref(ms)))
+        return ms.value
+
+    def sample_batch(self, p, xy, num_dims):
+        xy = np.ascontiguousarray(xy, dtype=np.uint32)
+        out = np.empty((len(xy), num_dims), dtype=np.uint32)
+        _check(self.lib, self.lib.rtb_sample_batch(self.h, C.byref(p), xy.ctypes.data, len(xy), num_dims, out.ctypes.data))
+        return out
+
+    def primary_rays(self, p):
+        out = np.empty(self.width * self.height, dtype=RAY_DTYPE)
+        _check(self.lib, self.lib.rtb_primary_rays(self.h, C.byref(p), out.ctypes.data))
+        return out
+
+    def set_profiling(self, enable):
+        _check(self.lib, self.lib.rtb_set_profiling(self.h, 1 if enable else 0))
+
+    def pass_timings(self):
+        t = RtbPassTimings()
+        _check(self.lib, self.lib.rtb_get_pass_timings(self.h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in RtbPassTimings._fields_}
+
+
+def camera_for(scene_file, width, height):
+    """Camera of the scene file at a given aspect ratio (Camera::SetPerspective, Camera.cpp:30-49).
+
+    tanHalfFoV is taken from the file (the host computed it with tanf, Camera.cpp:37); only the aspect changes.
+    """
+    cam = RtbCamera.from_buffer_copy(bytes(scene_file.camera))
+    cam.aspectRatio = float(np.float32(width) / np.float32(height))
+    return cam

@@ -1,0 +1,11 @@
+#!/usr/bin/env bash
+# Build librtb200.so (sm_100a only).  --fmad=false + IEEE div/sqrt + FTZ mirror the exact-math oracle's arithmetic:
+# FMA appears only where the reference calls an explicit fused intrinsic (rtb_math.h).
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/../librtb200.so"
+nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
+     --fmad=false -ftz=true -prec-div=true -prec-sqrt=true \
+     -Xptxas -v -shared -Xcompiler -fPIC -Xcompiler -O2 \
+     -o "$OUT" "$HERE/rtb_kernels.cu" "$@"
+echo "built $OUT"

@@ -1,0 +1,971 @@
+// rtb_kernels.cu — sm_100a wavefront kernels + the extern "C" boundary (include/rtb200.h).
+//
+// One pass (= one sample per pixel of this context's pixel shard) is enqueued as
+//
+//   k_raygen                       camera rays + path state for every pixel of the shard        (Viewport::RenderTile 300-330)
+//   for depth = 0 .. maxRayDepth:
+//     k_traverse   closest hit     two-level BVH, one ray per thread, persistent grid           (Scene::Traverse)
+//     k_shade      per path vertex emission / light hit / miss / NEE sampling / RR / BSDF sample (PathTracerMIS::RenderPixel body)
+//                                  -> compacts surviving paths into the other path buffer (warp ballot + one atomic per warp)
+//                                  -> writes this vertex' shadow rays + a compacted list of paths that own some
+//     k_shadow     any hit         per path: its shadow rays in light order, radiance added if unoccluded (Scene::Traverse_Shadow)
+//   k_film                         sum += pass colour (+ secondarySum on even passes)             (Film::AccumulateColor)
+//
+// Everything is stream-ordered on one stream with device-resident queue counters: no host round trip inside a pass.
+// Per-pixel radiance is accumulated in `passColor` in exactly the reference's order (emission, then the NEE sum of
+// that vertex, then the next vertex ...) because shade(d) -> shadow(d) -> shade(d+1) are ordered and every pixel
+// has exactly one path per pass.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdarg>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rtb_integrator.h"
+#include "rtb_upload.h"
+
+using namespace rtb;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// device data
+// ---------------------------------------------------------------------------------------------------------------------
+
+#define RTB_MAX_DEPTH_SLOTS 64
+
+struct PathBuf
+{
+    float4* p0;   // origin.xyz, dir.x
+    float4* p1;   // dir.yz, invDir.xy
+    float4* p2;   // invDir.z, originDivDir.xyz
+    float4* p3;   // throughput
+    uint4*  p4;   // pixel slot, sampler salt, dim | depth << 16 | lastSpecular << 31, lastPdfW bits
+};
+
+struct Control
+{
+    uint32_t pathCount[RTB_MAX_DEPTH_SLOTS + 2];     // live paths entering depth d
+    uint32_t shadowPathCount[RTB_MAX_DEPTH_SLOTS + 2];
+    unsigned long long numRays, numShadowRays, numShadowRaysHit, numBoxTests, numTriTests;
+};
+
+struct Wavefront
+{
+    PathBuf  buf[2];
+    uint4*   hit0;        // objectId, subObjectId, distance bits, u bits
+    float*   hit1;        // v
+    float4*  passColor;   // per pixel slot: radiance of this pass (xyz)
+    // shadow rays of the current depth: ray r of the path at input index i lives at i * raysPerPath + r
+    float4*  sr0;         // origin.xyz, tMax
+    float4*  sr1;         // dir.xyz, contribution.x
+    float4*  sr2;         // invDir.xyz, contribution.y
+    float4*  sr3;         // originDivDir.xyz, contribution.z
+    float4*  shThr;       // per input index: throughput.xyz at that vertex, pixel slot bits
+    uint32_t* shCount;    // per input index: number of shadow rays
+    uint32_t* shList;     // compacted input indices that own >= 1 shadow ray
+    Control* ctl;
+    const uint32_t* pixelList;   // pixel slot -> y * width + x
+    uint32_t numPixels;
+    uint32_t raysPerPath;
+};
+
+__device__ __forceinline__ void store_path(const PathBuf& b, uint32_t i, const PathState& ps)
+{
+    b.p0[i] = make_float4(ps.ray.origin.x, ps.ray.origin.y, ps.ray.origin.z, ps.ray.dir.x);
+    b.p1[i] = make_float4(ps.ray.dir.y, ps.ray.dir.z, ps.ray.invDir.x, ps.ray.invDir.y);
+    b.p2[i] = make_float4(ps.ray.invDir.z, ps.ray.originDivDir.x, ps.ray.originDivDir.y, ps.ray.originDivDir.z);
+    b.p3[i] = make_float4(ps.throughput.x, ps.throughput.y, ps.throughput.z, ps.throughput.w);
+    b.p4[i] = make_uint4(ps.pixel, ps.sampler.salt, (ps.sampler.dim & 0xFFFFu) | ((ps.depth & 0x7FFFu) << 16) | (ps.lastSpecular << 31), __float_as_uint(ps.lastPdfW));
+}
+
+__device__ __forceinline__ void load_ray(const PathBuf& b, uint32_t i, Ray& r)
+{
+    const float4 a = b.p0[i], c = b.p1[i], d = b.p2[i];
+    r.origin = v3(a.x, a.y, a.z);
+    r.dir = v3(a.w, c.x, c.y);
+    r.invDir = v3(c.z, c.w, d.x);
+    r.originDivDir = v3(d.y, d.z, d.w);
+}
+
+__device__ __forceinline__ void load_path(const PathBuf& b, uint32_t i, const Wavefront& W, uint32_t width, PathState& ps)
+{
+    load_ray(b, i, ps.ray);
+    const float4 t = b.p3[i];
+    ps.throughput = v4(t.x, t.y, t.z, t.w);
+    const uint4 m = b.p4[i];
+    ps.pixel = m.x;
+    ps.sampler.salt = m.y;
+    ps.sampler.dim = m.z & 0xFFFFu;
+    ps.depth = (m.z >> 16) & 0x7FFFu;
+    ps.lastSpecular = m.z >> 31;
+    ps.lastPdfW = __uint_as_float(m.w);
+    const uint32_t pix = W.pixelList[m.x];
+    const uint32_t x = pix % width, y = pix / width;
+    ps.sampler.bnOffset = 4u * (128u * (y & 127u) + (x & 127u));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const __grid_constant__ Wavefront W)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < W.numPixels; i += stride)
+    {
+        const uint32_t pix = W.pixelList[i];
+        PathState ps;
+        init_path(P, S.blueNoise, pix % P.width, pix / P.width, ps);
+        ps.pixel = i;
+        store_path(W.buf[0], i, ps);
+        W.passColor[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+}
+
+template <bool kCount>
+__global__ void __launch_bounds__(128) k_traverse(const __grid_constant__ SceneView S, const __grid_constant__ Wavefront W, uint32_t depth)
+{
+    const uint32_t count = W.ctl->pathCount[depth];
+    const PathBuf& in = W.buf[depth & 1];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+    {
+        Ray ray;
+        load_ray(in, i, ray);
+        Hit hit;
+        hit.objectId = RTB_INVALID_OBJECT; hit.subObjectId = 0; hit.distance = INFINITY; hit.u = 0.0f; hit.v = 0.0f;
+        scene_traverse<kCount>(S, ray, hit, &cnt);
+        W.hit0[i] = make_uint4(hit.objectId, hit.subObjectId, __float_as_uint(hit.distance), __float_as_uint(hit.u));
+        W.hit1[i] = hit.v;
+    }
+    if (kCount)
+    {
+        atomicAdd(&W.ctl->numBoxTests, (unsigned long long)cnt.boxTests);
+        atomicAdd(&W.ctl->numTriTests, (unsigned long long)cnt.triTests);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&W.ctl->numRays, (unsigned long long)count);
+}
+
+struct DeviceSink
+{
+    V3 result;
+    bool dirty;
+    const Wavefront& W;
+    uint32_t rayBase, numRays;
+    V4 lightThr;
+    __device__ DeviceSink(const Wavefront& w, uint32_t base) : W(w), rayBase(base), numRays(0) { dirty = false; result = v3s(0.0f); lightThr = v4s(0.0f); }
+    __device__ void add(const V4& thr, const V4& c) { result = mul_add(xyz(thr), xyz(c), result); dirty = true; }
+    __device__ void shadow(const Ray& ray, float tMax, const V4& c)
+    {
+        const uint32_t j = rayBase + numRays++;
+        W.sr0[j] = make_float4(ray.origin.x, ray.origin.y, ray.origin.z, tMax);
+        W.sr1[j] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, c.x);
+        W.sr2[j] = make_float4(ray.invDir.x, ray.invDir.y, ray.invDir.z, c.y);
+        W.sr3[j] = make_float4(ray.originDivDir.x, ray.originDivDir.y, ray.originDivDir.z, c.z);
+    }
+    __device__ void end_lights(const V4& thr) { lightThr = thr; }
+};
+
+__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const __grid_constant__ Wavefront W, uint32_t depth)
+{
+    const uint32_t count = W.ctl->pathCount[depth];
+    const PathBuf& in = W.buf[depth & 1];
+    const PathBuf& out = W.buf[(depth + 1) & 1];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    // loop bound rounded up to a whole warp so that every lane takes part in the ballots
+    const uint32_t countUp = (count + 31u) & ~31u;
+    unsigned long long shadowRaysLocal = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < countUp; i += stride)
+    {
+        bool alive = false;
+        uint32_t numShadow = 0;
+        PathState ps;
+        if (i < count)
+        {
+            load_path(in, i, W, P.width, ps);
+            const uint4 h0 = W.hit0[i];
+            Hit hit;
+            hit.objectId = h0.x; hit.subObjectId = h0.y; hit.distance = __uint_as_float(h0.z); hit.u = __uint_as_float(h0.w);
+            hit.v = W.hit1[i];
+
+            const float4 pc = W.passColor[ps.pixel];
+            DeviceSink sink(W, i * W.raysPerPath);
+            sink.result = v3(pc.x, pc.y, pc.z);
+            if (P.renderer == RTB_RENDERER_PATH_TRACER_MIS) alive = shade_vertex_mis(S, P, ps, hit, sink, numShadow);
+            else if (P.renderer == RTB_RENDERER_PATH_TRACER) alive = shade_vertex_pt(S, P, ps, hit, sink);
+            else shade_debug(S, P, ps, hit, sink);
+            if (sink.dirty) W.passColor[ps.pixel] = make_float4(sink.result.x, sink.result.y, sink.result.z, 0.0f);
+            if (numShadow)
+            {
+                W.shThr[i] = make_float4(sink.lightThr.x, sink.lightThr.y, sink.lightThr.z, __uint_as_float(ps.pixel));
+                W.shCount[i] = numShadow;
+                shadowRaysLocal += numShadow;
+            }
+        }
+        // stream compaction of the survivors (one atomic per warp)
+        const uint32_t aliveMask = __ballot_sync(0xFFFFFFFFu, alive);
+        if (aliveMask)
+        {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&W.ctl->pathCount[depth + 1], __popc(aliveMask));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (alive) store_path(out, base + __popc(aliveMask & ((1u << lane) - 1u)), ps);
+        }
+        // compacted list of paths that own shadow rays
+        const uint32_t shMask = __ballot_sync(0xFFFFFFFFu, numShadow != 0);
+        if (shMask)
+        {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&W.ctl->shadowPathCount[depth], __popc(shMask));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (numShadow) W.shList[base + __popc(shMask & ((1u << lane) - 1u))] = i;
+        }
+    }
+    // counters: one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) shadowRaysLocal += __shfl_down_sync(0xFFFFFFFFu, shadowRaysLocal, o);
+    if (lane == 0 && shadowRaysLocal) atomicAdd(&W.ctl->numShadowRays, shadowRaysLocal);
+}
+
+template <bool kCount>
+__global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ SceneView S, const __grid_constant__ Wavefront W, uint32_t depth)
+{
+    const uint32_t count = W.ctl->shadowPathCount[depth];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long visibleLocal = 0;
+    TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride)
+    {
+        const uint32_t i = W.shList[j];
+        const uint32_t n = W.shCount[i];
+        const uint32_t base = i * W.raysPerPath;
+        // SampleLights: accumulatedColor += SampleLight(light) in light order (PathTracerMIS.cpp:142-148)
+        V3 sum = v3s(0.0f);
+        for (uint32_t r = 0; r < n; ++r)
+        {
+            const float4 a = W.sr0[base + r], b = W.sr1[base + r], c = W.sr2[base + r], d = W.sr3[base + r];
+            Ray ray;
+            ray.origin = v3(a.x, a.y, a.z); ray.dir = v3(b.x, b.y, b.z); ray.invDir = v3(c.x, c.y, c.z); ray.originDivDir = v3(d.x, d.y, d.z);
+            const bool occluded = scene_traverse_shadow<kCount>(S, ray, a.w, &cnt);
+            if (!occluded) { sum = sum + v3(b.w, c.w, d.w); visibleLocal++; }
+            else sum = sum + v3s(0.0f);
+        }
+        const float4 t = W.shThr[i];
+        const uint32_t pixel = __float_as_uint(t.w);
+        const float4 pc = W.passColor[pixel];
+        const V3 res = mul_add(v3(t.x, t.y, t.z), sum, v3(pc.x, pc.y, pc.z));
+        W.passColor[pixel] = make_float4(res.x, res.y, res.z, 0.0f);
+    }
+    for (int o = 16; o > 0; o >>= 1) visibleLocal += __shfl_down_sync(0xFFFFFFFFu, visibleLocal, o);
+    if (lane == 0 && visibleLocal) atomicAdd(&W.ctl->numShadowRaysHit, visibleLocal);
+    if (kCount)
+    {
+        atomicAdd(&W.ctl->numBoxTests, (unsigned long long)cnt.boxTests);
+        atomicAdd(&W.ctl->numTriTests, (unsigned long long)cnt.triTests);
+    }
+}
+
+// Film::AccumulateColor, Film.cpp:25-39: sum += colour; secondarySum += colour on even passes
+__global__ void __launch_bounds__(256) k_film(const __grid_constant__ Wavefront W, float* __restrict__ sum, float* __restrict__ sum2, uint32_t evenPass)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < W.numPixels; i += stride)
+    {
+        const float4 c = W.passColor[i];
+        float* s = sum + (size_t)i * 3;
+        s[0] = s[0] + c.x; s[1] = s[1] + c.y; s[2] = s[2] + c.z;
+        if (evenPass)
+        {
+            float* t = sum2 + (size_t)i * 3;
+            t[0] = t[0] + c.x; t[1] = t[1] + c.y; t[2] = t[2] + c.z;
+        }
+    }
+}
+
+// raster (y * width + x) <- pixel slots; src may hold several shards back to back (all-gathered film)
+__global__ void __launch_bounds__(256) k_unshard(const float* __restrict__ src, float* __restrict__ dstRaster, const uint32_t* __restrict__ pixelListAll, uint32_t total)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+    {
+        const uint32_t pix = pixelListAll[i];
+        if (pix == 0xFFFFFFFFu) continue;     // padding slot
+        dstRaster[(size_t)pix * 3 + 0] = src[(size_t)i * 3 + 0];
+        dstRaster[(size_t)pix * 3 + 1] = src[(size_t)i * 3 + 1];
+        dstRaster[(size_t)pix * 3 + 2] = src[(size_t)i * 3 + 2];
+    }
+}
+
+// test hooks ------------------------------------------------------------------------------------------------------------
+
+template <bool kCount>
+__global__ void __launch_bounds__(128) k_trace_batch(const __grid_constant__ SceneView S, const RtbRay* __restrict__ rays, RtbHit* __restrict__ hits, unsigned long long n, uint32_t mode, Control* ctl)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        const float4* p = reinterpret_cast<const float4*>(rays + i);
+        const float4 o = p[0], d = p[1], id = p[2], od = p[3];
+        Ray ray;
+        ray.origin = v3(o.x, o.y, o.z); ray.dir = v3(d.x, d.y, d.z); ray.invDir = v3(id.x, id.y, id.z); ray.originDivDir = v3(od.x, od.y, od.z);
+        RtbHit out;
+        if (mode == RTB_TRACE_SHADOW)
+        {
+            // hits[i].distance is the preset tMax (HitPoint::distance, PathTracerMIS.cpp:86)
+            const float tMax = hits[i].distance;
+            out.objectId = RTB_INVALID_OBJECT; out.subObjectId = 0; out.distance = tMax; out.u = 0.0f; out.v = 0.0f;
+            out.occluded = scene_traverse_shadow<kCount>(S, ray, tMax, &cnt) ? 1u : 0u;
+        }
+        else
+        {
+            Hit hit;
+            hit.objectId = RTB_INVALID_OBJECT; hit.subObjectId = 0; hit.distance = INFINITY; hit.u = 0.0f; hit.v = 0.0f;
+            scene_traverse<kCount>(S, ray, hit, &cnt);
+            out.objectId = hit.objectId; out.subObjectId = hit.subObjectId; out.distance = hit.distance; out.u = hit.u; out.v = hit.v; out.occluded = 0;
+        }
+        hits[i] = out;
+    }
+    if (kCount)
+    {
+        atomicAdd(&ctl->numBoxTests, (unsigned long long)cnt.boxTests);
+        atomicAdd(&ctl->numTriTests, (unsigned long long)cnt.triTests);
+    }
+}
+
+__global__ void k_sample_batch(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const uint32_t* __restrict__ xy, unsigned long long n, uint32_t numDims, uint32_t* __restrict__ out)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Sampler s;
+    sampler_reset_pixel(s, xy[2 * i], xy[2 * i + 1]);
+    for (uint32_t d = 0; d < numDims; ++d) out[i * numDims + d] = sampler_get_int(s, P, S.blueNoise);
+}
+
+__global__ void k_primary_rays(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, RtbRay* __restrict__ rays)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.width * P.height) return;
+    PathState ps;
+    init_path(P, S.blueNoise, i % P.width, i / P.width, ps);
+    RtbRay r;
+    r.origin[0] = ps.ray.origin.x; r.origin[1] = ps.ray.origin.y; r.origin[2] = ps.ray.origin.z; r.origin[3] = 0.0f;
+    r.dir[0] = ps.ray.dir.x; r.dir[1] = ps.ray.dir.y; r.dir[2] = ps.ray.dir.z; r.dir[3] = 0.0f;
+    r.invDir[0] = ps.ray.invDir.x; r.invDir[1] = ps.ray.invDir.y; r.invDir[2] = ps.ray.invDir.z; r.invDir[3] = 0.0f;
+    r.originDivDir[0] = ps.ray.originDivDir.x; r.originDivDir[1] = ps.ray.originDivDir.y; r.originDivDir[2] = ps.ray.originDivDir.z; r.originDivDir[3] = 0.0f;
+    rays[i] = r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side: context + extern "C"
+// ---------------------------------------------------------------------------------------------------------------------
+
+static thread_local std::string gLastError;
+
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    gLastError = buf;
+    return code;
+}
+
+#define RTB_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(RTB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+template <typename T> struct DevArray
+{
+    T* ptr = nullptr;
+    size_t count = 0;
+    cudaError_t alloc(size_t n)
+    {
+        release();
+        count = n;
+        if (n == 0) return cudaSuccess;
+        return cudaMalloc(&ptr, n * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T>& v, cudaStream_t s)
+    {
+        cudaError_t e = alloc(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpyAsync(ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; count = 0; }
+};
+
+struct DeviceMesh
+{
+    DevArray<DNode> nodes;
+    DevArray<DTri> tris;
+    DevArray<DVertexIndices> indices;
+    DevArray<DVertexShading> shading;
+    DevArray<uint32_t> materialIds;
+};
+
+struct RtbContext
+{
+    int device = 0;
+    uint32_t flags = 0;
+    uint32_t numShards = 1, shardIndex = 0, tileSize = 32;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    int numSMs = 148;
+
+    // scene
+    bool hasScene = false;
+    DevArray<DNode> tlas;
+    DevArray<DObjectTrace> objTrace;
+    DevArray<DObjectShade> objShade;
+    DevArray<RtbShape> shapes;
+    std::vector<DeviceMesh> meshes;
+    DevArray<DMesh> meshViews;
+    DevArray<RtbMaterial> materials;
+    DevArray<DLight> lights;
+    DevArray<uint32_t> globalLights;
+    DevArray<uint16_t> blueNoise;
+    SceneView view;
+    uint32_t numLights = 0;
+
+    // film + wavefront
+    uint32_t width = 0, height = 0;
+    uint32_t numPixels = 0;        // pixels of this shard
+    uint32_t shardSlots = 0;       // padded slot count (equal on every shard)
+    uint32_t raysPerPath = 0;
+    DevArray<uint32_t> pixelList;     // this shard
+    DevArray<uint32_t> pixelListAll;  // all shards back to back, padded with 0xFFFFFFFF
+    DevArray<float> sum, sum2;
+    DevArray<float> raster;           // scratch for read-back
+    DevArray<float4> p[2][4];
+    DevArray<uint4> p4[2];
+    DevArray<uint4> hit0;
+    DevArray<float> hit1;
+    DevArray<float4> passColor, sr0, sr1, sr2, sr3, shThr;
+    DevArray<uint32_t> shCount, shList;
+    DevArray<Control> ctl;
+    DevArray<uint32_t> seed;
+    Wavefront wf;
+
+    RtbCounters counters;
+    uint32_t passesSinceReset = 0;
+
+    // profiling
+    bool profiling = false;
+    std::vector<cudaEvent_t> events;
+    RtbPassTimings timings;
+};
+
+static void free_scene(RtbContext* c)
+{
+    c->tlas.release(); c->objTrace.release(); c->objShade.release(); c->shapes.release();
+    for (DeviceMesh& m : c->meshes) { m.nodes.release(); m.tris.release(); m.indices.release(); m.shading.release(); m.materialIds.release(); }
+    c->meshes.clear();
+    c->meshViews.release(); c->materials.release(); c->lights.release(); c->globalLights.release();
+    c->hasScene = false;
+}
+
+static void free_film(RtbContext* c)
+{
+    c->pixelList.release(); c->pixelListAll.release(); c->sum.release(); c->sum2.release(); c->raster.release();
+    for (int b = 0; b < 2; ++b) { for (int k = 0; k < 4; ++k) c->p[b][k].release(); c->p4[b].release(); }
+    c->hit0.release(); c->hit1.release(); c->passColor.release();
+    c->sr0.release(); c->sr1.release(); c->sr2.release(); c->sr3.release(); c->shThr.release(); c->shCount.release(); c->shList.release();
+}
+
+static int alloc_shadow(RtbContext* c)
+{
+    // shadow-ray storage depends on both the film size and the number of lights sampled per vertex
+    const uint32_t rpp = c->numLights > 0 ? c->numLights : 1;
+    if (c->numPixels == 0) return RTB_OK;
+    if (rpp == c->raysPerPath && c->sr0.count == (size_t)c->numPixels * rpp) return RTB_OK;
+    c->raysPerPath = rpp;
+    const size_t n = (size_t)c->numPixels * rpp;
+    RTB_CUDA(c->sr0.alloc(n)); RTB_CUDA(c->sr1.alloc(n)); RTB_CUDA(c->sr2.alloc(n)); RTB_CUDA(c->sr3.alloc(n));
+    return RTB_OK;
+}
+
+static void fill_wavefront(RtbContext* c)
+{
+    Wavefront& w = c->wf;
+    for (int b = 0; b < 2; ++b)
+    {
+        w.buf[b].p0 = c->p[b][0].ptr; w.buf[b].p1 = c->p[b][1].ptr; w.buf[b].p2 = c->p[b][2].ptr; w.buf[b].p3 = c->p[b][3].ptr;
+        w.buf[b].p4 = c->p4[b].ptr;
+    }
+    w.hit0 = c->hit0.ptr; w.hit1 = c->hit1.ptr; w.passColor = c->passColor.ptr;
+    w.sr0 = c->sr0.ptr; w.sr1 = c->sr1.ptr; w.sr2 = c->sr2.ptr; w.sr3 = c->sr3.ptr;
+    w.shThr = c->shThr.ptr; w.shCount = c->shCount.ptr; w.shList = c->shList.ptr;
+    w.ctl = c->ctl.ptr;
+    w.pixelList = c->pixelList.ptr;
+    w.numPixels = c->numPixels;
+    w.raysPerPath = c->raysPerPath;
+}
+
+extern "C" {
+
+const char* rtb_last_error(void) { return gLastError.c_str(); }
+int rtb_api_version(void) { return RTB_API_VERSION; }
+
+int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
+{
+    if (!desc || !outCtx) return fail(RTB_ERR_INVALID_ARG, "rtb_create: null argument");
+    *outCtx = nullptr;
+    int deviceCount = 0;
+    cudaError_t e = cudaGetDeviceCount(&deviceCount);
+    if (e != cudaSuccess || deviceCount == 0)
+        return fail(RTB_ERR_NO_DEVICE, "rtb_create: no CUDA device (%s) - this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (desc->deviceId < 0 || desc->deviceId >= deviceCount) return fail(RTB_ERR_INVALID_ARG, "rtb_create: device %d out of range (%d devices)", desc->deviceId, deviceCount);
+    const uint32_t numShards = desc->numShards ? desc->numShards : 1;
+    if (desc->shardIndex >= numShards) return fail(RTB_ERR_INVALID_ARG, "rtb_create: shardIndex %u >= numShards %u", desc->shardIndex, numShards);
+    RTB_CUDA(cudaSetDevice(desc->deviceId));
+    RtbContext* c = new (std::nothrow) RtbContext();
+    if (!c) return fail(RTB_ERR_OUT_OF_MEMORY, "rtb_create: out of host memory");
+    c->device = desc->deviceId;
+    c->flags = desc->flags;
+    c->numShards = numShards;
+    c->shardIndex = desc->shardIndex;
+    c->tileSize = desc->tileSize ? desc->tileSize : 32;
+    if (desc->stream) { c->stream = (cudaStream_t)desc->stream; c->ownStream = false; }
+    else
+    {
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete c; return fail(RTB_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
+        c->ownStream = true;
+    }
+    cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, c->device);
+    e = c->ctl.alloc(1);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->ctl.ptr, 0, sizeof(Control), c->stream);
+    if (e != cudaSuccess) { delete c; return fail(RTB_ERR_CUDA, "control block allocation failed: %s", cudaGetErrorString(e)); }
+    memset(&c->view, 0, sizeof(c->view));
+    memset(&c->wf, 0, sizeof(c->wf));
+    memset(&c->counters, 0, sizeof(c->counters));
+    memset(&c->timings, 0, sizeof(c->timings));
+    *outCtx = c;
+    return RTB_OK;
+}
+
+void rtb_destroy(RtbContext* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_scene(c);
+    free_film(c);
+    c->blueNoise.release(); c->ctl.release(); c->seed.release();
+    for (cudaEvent_t ev : c->events) cudaEventDestroy(ev);
+    if (c->ownStream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int rtb_set_blue_noise(RtbContext* c, const uint16_t* data)
+{
+    if (!c) return fail(RTB_ERR_INVALID_ARG, "null context");
+    RTB_CUDA(cudaSetDevice(c->device));
+    if (!data) { c->blueNoise.release(); c->view.blueNoise = nullptr; return RTB_OK; }
+    RTB_CUDA(c->blueNoise.alloc(128 * 128 * 4));
+    RTB_CUDA(cudaMemcpyAsync(c->blueNoise.ptr, data, 128 * 128 * 4 * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+    RTB_CUDA(cudaStreamSynchronize(c->stream));
+    c->view.blueNoise = c->blueNoise.ptr;
+    return RTB_OK;
+}
+
+int rtb_upload_scene(RtbContext* c, const RtbSceneDesc* scene)
+{
+    if (!c || !scene) return fail(RTB_ERR_INVALID_ARG, "rtb_upload_scene: null argument");
+    RTB_CUDA(cudaSetDevice(c->device));
+    HostScene hs;
+    std::string err;
+    if (!build_host_scene(*scene, hs, err)) return fail(RTB_ERR_INVALID_ARG, "rtb_upload_scene: %s", err.c_str());
+    RTB_CUDA(cudaStreamSynchronize(c->stream));
+    free_scene(c);
+    cudaStream_t s = c->stream;
+    RTB_CUDA(c->tlas.upload(hs.tlas, s));
+    RTB_CUDA(c->objTrace.upload(hs.objTrace, s));
+    RTB_CUDA(c->objShade.upload(hs.objShade, s));
+    RTB_CUDA(c->shapes.upload(hs.shapes, s));
+    RTB_CUDA(c->materials.upload(hs.materials, s));
+    RTB_CUDA(c->lights.upload(hs.lights, s));
+    RTB_CUDA(c->globalLights.upload(hs.globalLights, s));
+    c->meshes.resize(hs.meshes.size());
+    std::vector<DMesh> views(hs.meshes.size());
+    for (size_t i = 0; i < hs.meshes.size(); ++i)
+    {
+        DeviceMesh& dm = c->meshes[i];
+        const HostMesh& hm = hs.meshes[i];
+        RTB_CUDA(dm.nodes.upload(hm.nodes, s));
+        RTB_CUDA(dm.tris.upload(hm.tris, s));
+        RTB_CUDA(dm.indices.upload(hm.indices, s));
+        RTB_CUDA(dm.shading.upload(hm.shading, s));
+        RTB_CUDA(dm.materialIds.upload(hm.materialIds, s));
+        DMesh& v = views[i];
+        v.nodes = dm.nodes.ptr; v.tris = dm.tris.ptr; v.indices = dm.indices.ptr; v.shading = dm.shading.ptr; v.materialIds = dm.materialIds.ptr;
+        v.numNodes = (uint32_t)hm.nodes.size(); v.numTriangles = (uint32_t)hm.tris.size();
+        v.numVertices = (uint32_t)hm.shading.size(); v.numMaterials = (uint32_t)hm.materialIds.size();
+    }
+    RTB_CUDA(c->meshViews.upload(views, s));
+    RTB_CUDA(cudaStreamSynchronize(s));   // host vectors go out of scope
+
+    SceneView& v = c->view;
+    v.tlas = c->tlas.ptr; v.objTrace = c->objTrace.ptr; v.objShade = c->objShade.ptr; v.shapes = c->shapes.ptr;
+    v.meshes = c->meshViews.ptr; v.materials = c->materials.ptr; v.lights = c->lights.ptr; v.globalLights = c->globalLights.ptr;
+    v.blueNoise = c->blueNoise.ptr;
+    v.numTlasNodes = (uint32_t)hs.tlas.size(); v.numObjects = (uint32_t)hs.objTrace.size();
+    v.numLights = (uint32_t)hs.lights.size(); v.numGlobalLights = (uint32_t)hs.globalLights.size();
+    c->numLights = v.numLights;
+    c->hasScene = true;
+    int rc = alloc_shadow(c);
+    if (rc != RTB_OK) return rc;
+    fill_wavefront(c);
+    return RTB_OK;
+}
+
+int rtb_resize(RtbContext* c, uint32_t width, uint32_t height)
+{
+    if (!c) return fail(RTB_ERR_INVALID_ARG, "null context");
+    if (width == 0 || height == 0 || width > 65536 || height > 65536) return fail(RTB_ERR_INVALID_ARG, "rtb_resize: invalid viewport size %ux%u", width, height);   // Viewport.cpp:52-58
+    RTB_CUDA(cudaSetDevice(c->device));
+    RTB_CUDA(cudaStreamSynchronize(c->stream));
+    free_film(c);
+    c->width = width; c->height = height;
+
+    // tile-interleaved sharding: tile t (row-major over the tile grid) belongs to shard t % numShards; inside a tile
+    // pixels are row-major.  Every shard is padded to the same slot count so that one all-gather reassembles the film.
+    const uint32_t ts = c->tileSize;
+    const uint32_t tilesX = (width + ts - 1) / ts, tilesY = (height + ts - 1) / ts;
+    std::vector<std::vector<uint32_t>> lists(c->numShards);
+    for (uint32_t ty = 0; ty < tilesY; ++ty) for (uint32_t tx = 0; tx < tilesX; ++tx)
+    {
+        std::vector<uint32_t>& l = lists[(ty * tilesX + tx) % c->numShards];
+        for (uint32_t y = ty * ts; y < (ty + 1) * ts && y < height; ++y)
+            for (uint32_t x = tx * ts; x < (tx + 1) * ts && x < width; ++x) l.push_back(y * width + x);
+    }
+    size_t maxSlots = 0;
+    for (const auto& l : lists) if (l.size() > maxSlots) maxSlots = l.size();
+    c->shardSlots = (uint32_t)maxSlots;
+    c->numPixels = (uint32_t)lists[c->shardIndex].size();
+    std::vector<uint32_t> all((size_t)c->numShards * maxSlots, 0xFFFFFFFFu);
+    for (uint32_t s = 0; s < c->numShards; ++s) memcpy(&all[(size_t)s * maxSlots], lists[s].data(), lists[s].size() * 4);
+    RTB_CUDA(c->pixelList.upload(lists[c->shardIndex], c->stream));
+    RTB_CUDA(c->pixelListAll.upload(all, c->stream));
+    RTB_CUDA(cudaStreamSynchronize(c->stream));
+
+    const size_t n = c->numPixels;
+    RTB_CUDA(c->sum.alloc(maxSlots * 3)); RTB_CUDA(c->sum2.alloc(maxSlots * 3));
+    RTB_CUDA(c->raster.alloc((size_t)width * height * 3));
+    for (int b = 0; b < 2; ++b) { for (int k = 0; k < 4; ++k) RTB_CUDA(c->p[b][k].alloc(n)); RTB_CUDA(c->p4[b].alloc(n)); }
+    RTB_CUDA(c->hit0.alloc(n)); RTB_CUDA(c->hit1.alloc(n)); RTB_CUDA(c->passColor.alloc(n));
+    RTB_CUDA(c->shThr.alloc(n)); RTB_CUDA(c->shCount.alloc(n)); RTB_CUDA(c->shList.alloc(n));
+    c->raysPerPath = 0;
+    int rc = alloc_shadow(c);
+    if (rc != RTB_OK) return rc;
+    fill_wavefront(c);
+    return rtb_reset(c);
+}
+
+int rtb_reset(RtbContext* c)
+{
+    if (!c) return fail(RTB_ERR_INVALID_ARG, "null context");
+    RTB_CUDA(cudaSetDevice(c->device));
+    if (c->sum.ptr)
+    {
+        RTB_CUDA(cudaMemsetAsync(c->sum.ptr, 0, c->sum.count * sizeof(float), c->stream));
+        RTB_CUDA(cudaMemsetAsync(c->sum2.ptr, 0, c->sum2.count * sizeof(float), c->stream));
+    }
+    RTB_CUDA(cudaMemsetAsync(c->ctl.ptr, 0, sizeof(Control), c->stream));
+    memset(&c->counters, 0, sizeof(c->counters));
+    c->passesSinceReset = 0;
+    return RTB_OK;
+}
+
+static int fill_pass_params(RtbContext* c, const RtbPassDesc* pass, PassParams& P, bool uploadSeed)
+{
+    if (pass->renderer > RTB_RENDERER_DEBUG) return fail(RTB_ERR_INVALID_ARG, "unknown renderer id %u", pass->renderer);   // CreateRenderer, Renderer.cpp:45-69
+    if (pass->maxRayDepth >= 255u || pass->maxRayDepth >= RTB_MAX_DEPTH_SLOTS) return fail(RTB_ERR_INVALID_ARG, "maxRayDepth %u too large (limit %u)", pass->maxRayDepth, RTB_MAX_DEPTH_SLOTS - 1);
+    if (pass->camera.barrelDistortionVariableFactor != 0.0f) return fail(RTB_ERR_UNSUPPORTED, "variable barrel distortion draws from a per-thread RNG in the reference and is not supported");
+    if (pass->numSeedDims > 0 && !pass->seed) return fail(RTB_ERR_INVALID_ARG, "seed pointer is null");
+    memset(&P, 0, sizeof(P));
+    P.camLocalToWorld = load_m4(pass->camera.localToWorld);
+    P.aspectRatio = pass->camera.aspectRatio; P.tanHalfFoV = pass->camera.tanHalfFoV;
+    P.dofEnable = pass->camera.dofEnable; P.bokehShape = pass->camera.bokehShape;
+    P.aperture = pass->camera.aperture; P.focalPlaneDistance = pass->camera.focalPlaneDistance;
+    P.barrelConst = pass->camera.barrelDistortionConstFactor; P.barrelVar = 0.0f;
+    P.width = c->width; P.height = c->height;
+    P.sampleOffsetX = pass->sampleOffset[0]; P.sampleOffsetY = pass->sampleOffset[1];
+    P.renderer = pass->renderer; P.debugMode = pass->debugMode;
+    P.maxRayDepth = pass->maxRayDepth; P.minRussianRouletteDepth = pass->minRussianRouletteDepth;
+    P.lightSamplingAll = pass->lightSamplingStrategy == RTB_LIGHT_SAMPLING_ALL ? 1u : 0u;
+    P.useBlueNoise = (pass->useBlueNoise && c->blueNoise.ptr) ? 1u : 0u;
+    P.passIndex = pass->passIndex; P.numSeedDims = pass->numSeedDims;
+    if (uploadSeed)
+    {
+        if (c->seed.count < pass->numSeedDims || !c->seed.ptr) { RTB_CUDA(cudaStreamSynchronize(c->stream)); RTB_CUDA(c->seed.alloc(pass->numSeedDims > 64 ? pass->numSeedDims : 64)); }
+        if (pass->numSeedDims) RTB_CUDA(cudaMemcpyAsync(c->seed.ptr, pass->seed, pass->numSeedDims * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    }
+    P.seed = c->seed.ptr;
+    return RTB_OK;
+}
+
+static cudaEvent_t next_event(RtbContext* c, size_t& cursor)
+{
+    if (cursor >= c->events.size()) { cudaEvent_t ev; cudaEventCreate(&ev); c->events.push_back(ev); }
+    cudaEvent_t ev = c->events[cursor++];
+    cudaEventRecord(ev, c->stream);
+    return ev;
+}
+
+int rtb_render_pass(RtbContext* c, const RtbPassDesc* pass)
+{
+    if (!c || !pass) return fail(RTB_ERR_INVALID_ARG, "rtb_render_pass: null argument");
+    if (!c->hasScene) return fail(RTB_ERR_NO_SCENE, "rtb_render_pass: no scene uploaded");       // Viewport.cpp:194-198 ("Missing renderer")
+    if (c->width == 0 || c->height == 0) return fail(RTB_ERR_INVALID_ARG, "rtb_render_pass: viewport has no size");
+    RTB_CUDA(cudaSetDevice(c->device));
+
+    // the reference silently switches to a per-thread RNG beyond SamplingParams::dimensions (GenericSampler.cpp:106-109);
+    // that is irreproducible, so refuse it up front.  Worst case per path: SURVEY appendix B.
+    if (pass->renderer != RTB_RENDERER_DEBUG)
+    {
+        const uint32_t L = pass->renderer == RTB_RENDERER_PATH_TRACER_MIS ? (pass->lightSamplingStrategy == RTB_LIGHT_SAMPLING_ALL ? c->numLights : (c->numLights ? 1u : 0u)) : 0u;
+        const uint32_t D = pass->maxRayDepth;
+        const uint32_t needed = (pass->camera.dofEnable ? 2u : 0u) + 3u * L * (D + 1u) + 4u * D;
+        if (needed > pass->numSeedDims)
+            return fail(RTB_ERR_INVALID_ARG, "rtb_render_pass: %u sample dimensions needed (lights=%u, maxRayDepth=%u) but only %u seeded", needed, L, D, pass->numSeedDims);
+    }
+
+    PassParams P;
+    int rc = fill_pass_params(c, pass, P, true);
+    if (rc != RTB_OK) return rc;
+    if (c->numPixels == 0) { c->passesSinceReset++; return RTB_OK; }
+
+    const bool count = (c->flags & RTB_FLAG_COUNT_TESTS) != 0;
+    cudaStream_t s = c->stream;
+    // queue counters of this pass: everything except the cumulative ray counters
+    RTB_CUDA(cudaMemsetAsync(c->ctl.ptr, 0, offsetof(Control, numRays), s));
+    RTB_CUDA(cudaMemcpyAsync(&c->ctl.ptr->pathCount[0], &c->numPixels, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+
+    const int blocks128 = c->numSMs * 8;
+    const int blocks256 = c->numSMs * 4;
+    size_t ev = 0;
+    std::vector<cudaEvent_t> marks;
+    const bool prof = c->profiling;
+    if (prof) marks.push_back(next_event(c, ev));
+    k_raygen<<<blocks256, 256, 0, s>>>(c->view, P, c->wf);
+    if (prof) marks.push_back(next_event(c, ev));
+    const uint32_t depthLimit = pass->renderer == RTB_RENDERER_DEBUG ? 0u : pass->maxRayDepth;
+    for (uint32_t d = 0; d <= depthLimit; ++d)
+    {
+        if (count) k_traverse<true><<<blocks128, 128, 0, s>>>(c->view, c->wf, d);
+        else k_traverse<false><<<blocks128, 128, 0, s>>>(c->view, c->wf, d);
+        if (prof) marks.push_back(next_event(c, ev));
+        k_shade<<<blocks128, 128, 0, s>>>(c->view, P, c->wf, d);
+        if (prof) marks.push_back(next_event(c, ev));
+        if (pass->renderer == RTB_RENDERER_PATH_TRACER_MIS && c->numLights > 0)
+        {
+            if (count) k_shadow<true><<<blocks128, 128, 0, s>>>(c->view, c->wf, d);
+            else k_shadow<false><<<blocks128, 128, 0, s>>>(c->view, c->wf, d);
+        }
+        if (prof) marks.push_back(next_event(c, ev));
+    }
+    k_film<<<blocks256, 256, 0, s>>>(c->wf, c->sum.ptr, c->sum2.ptr, (pass->passIndex % 2 == 0) ? 1u : 0u);
+    if (prof) marks.push_back(next_event(c, ev));
+    RTB_CUDA(cudaGetLastError());
+    c->counters.numPrimaryRays += c->numPixels;     // Viewport.cpp:429
+    c->passesSinceReset++;
+
+    if (prof)
+    {
+        RTB_CUDA(cudaStreamSynchronize(s));
+        RtbPassTimings& t = c->timings;
+        memset(&t, 0, sizeof(t));
+        auto ms = [&](size_t a, size_t b) { float v = 0.0f; cudaEventElapsedTime(&v, marks[a], marks[b]); return v; };
+        t.raygenMs = ms(0, 1);
+        size_t k = 1;
+        for (uint32_t d = 0; d <= depthLimit; ++d)
+        {
+            t.traverseMs += ms(k, k + 1); t.shadeMs += ms(k + 1, k + 2); t.shadowMs += ms(k + 2, k + 3);
+            k += 3;
+            t.traverseLaunches++; t.shadeLaunches++;
+            if (pass->renderer == RTB_RENDERER_PATH_TRACER_MIS && c->numLights > 0) t.shadowLaunches++;
+        }
+        t.totalMs = ms(0, marks.size() - 1);
+        t.totalLaunches = 2 + t.traverseLaunches + t.shadeLaunches + t.shadowLaunches;
+        Control h;
+        RTB_CUDA(cudaMemcpy(&h, c->ctl.ptr, sizeof(Control), cudaMemcpyDeviceToHost));
+        for (uint32_t d = 0; d <= depthLimit; ++d) t.traverseRays += h.pathCount[d];
+        t.shadowRays = 0;   // filled by rtb_get_counters deltas on the caller side
+    }
+    return RTB_OK;
+}
+
+int rtb_synchronize(RtbContext* c)
+{
+    if (!c) return fail(RTB_ERR_INVALID_ARG, "null context");
+    RTB_CUDA(cudaSetDevice(c->device));
+    RTB_CUDA(cudaStreamSynchronize(c->stream));
+    return RTB_OK;
+}
+
+int rtb_film_device_buffer(RtbContext* c, int which, void** outDevicePtr, uint64_t* outNumFloats)
+{
+    if (!c || !outDevicePtr || !outNumFloats) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    if (!c->sum.ptr) return fail(RTB_ERR_INVALID_ARG, "viewport has no size");
+    *outDevicePtr = which == 0 ? c->sum.ptr : c->sum2.ptr;
+    *outNumFloats = (uint64_t)c->shardSlots * 3;
+    return RTB_OK;
+}
+
+int rtb_unshard_film(RtbContext* c, const void* gatheredDevice, float* hostRgb)
+{
+    if (!c || !gatheredDevice || !hostRgb) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    if (!c->sum.ptr) return fail(RTB_ERR_INVALID_ARG, "viewport has no size");
+    RTB_CUDA(cudaSetDevice(c->device));
+    const uint32_t total = c->numShards * c->shardSlots;
+    k_unshard<<<c->numSMs * 4, 256, 0, c->stream>>>((const float*)gatheredDevice, c->raster.ptr, c->pixelListAll.ptr, total);
+    RTB_CUDA(cudaGetLastError());
+    RTB_CUDA(cudaMemcpyAsync(hostRgb, c->raster.ptr, (size_t)c->width * c->height * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    RTB_CUDA(cudaStreamSynchronize(c->stream));
+    return RTB_OK;
+}
+
+int rtb_read_sum(RtbContext* c, float* rgb, int which)
+{
+    if (!c || !rgb) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    if (!c->sum.ptr) return fail(RTB_ERR_INVALID_ARG, "viewport has no size");
+    RTB_CUDA(cudaSetDevice(c->device));
+    if (c->numShards > 1)
+    {
+        // only this shard's pixels are known here: the rest of the raster stays zero
+        RTB_CUDA(cudaMemsetAsync(c->raster.ptr, 0, c->raster.count * sizeof(float), c->stream));
+        k_unshard<<<c->numSMs * 4, 256, 0, c->stream>>>(which == 0 ? c->sum.ptr : c->sum2.ptr, c->raster.ptr, c->pixelList.ptr, c->numPixels);
+    }
+    else
+    {
+        k_unshard<<<c->numSMs * 4, 256, 0, c->stream>>>(which == 0 ? c->sum.ptr : c->sum2.ptr, c->raster.ptr, c->pixelListAll.ptr, c->shardSlots);
+    }
+    RTB_CUDA(cudaGetLastError());
+    RTB_CUDA(cudaMemcpyAsync(rgb, c->raster.ptr, (size_t)c->width * c->height * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    RTB_CUDA(cudaStreamSynchronize(c->stream));
+    return RTB_OK;
+}
+
+int rtb_get_counters(RtbContext* c, RtbCounters* out)
+{
+    if (!c || !out) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    RTB_CUDA(cudaSetDevice(c->device));
+    RTB_CUDA(cudaStreamSynchronize(c->stream));
+    Control h;
+    RTB_CUDA(cudaMemcpy(&h, c->ctl.ptr, sizeof(Control), cudaMemcpyDeviceToHost));
+    *out = c->counters;
+    out->numRays = h.numRays;
+    out->numShadowRays = h.numShadowRays;
+    out->numShadowRaysHit = h.numShadowRaysHit;
+    out->numRayBoxTests = h.numBoxTests;
+    out->numRayTriangleTests = h.numTriTests;
+    return RTB_OK;
+}
+
+int rtb_trace_batch_device(RtbContext* c, const void* raysDevice, uint64_t n, void* hitsDevice, uint32_t mode, float* outMs)
+{
+    if (!c || (n && (!raysDevice || !hitsDevice))) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    if (!c->hasScene) return fail(RTB_ERR_NO_SCENE, "rtb_trace_batch: no scene uploaded");
+    if (mode > RTB_TRACE_SHADOW) return fail(RTB_ERR_INVALID_ARG, "unknown trace mode %u", mode);
+    RTB_CUDA(cudaSetDevice(c->device));
+    if (n == 0) { if (outMs) *outMs = 0.0f; return RTB_OK; }
+    const bool count = (c->flags & RTB_FLAG_COUNT_TESTS) != 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (outMs) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream); }
+    const int blocks = c->numSMs * 8;
+    if (count) k_trace_batch<true><<<blocks, 128, 0, c->stream>>>(c->view, (const RtbRay*)raysDevice, (RtbHit*)hitsDevice, n, mode, c->ctl.ptr);
+    else k_trace_batch<false><<<blocks, 128, 0, c->stream>>>(c->view, (const RtbRay*)raysDevice, (RtbHit*)hitsDevice, n, mode, c->ctl.ptr);
+    RTB_CUDA(cudaGetLastError());
+    if (outMs)
+    {
+        cudaEventRecord(e1, c->stream);
+        RTB_CUDA(cudaEventSynchronize(e1));
+        cudaEventElapsedTime(outMs, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    return RTB_OK;
+}
+
+int rtb_trace_batch(RtbContext* c, const RtbRay* rays, uint64_t n, RtbHit* hits, uint32_t mode)
+{
+    if (!c || (n && (!rays || !hits))) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    if (!c->hasScene) return fail(RTB_ERR_NO_SCENE, "rtb_trace_batch: no scene uploaded");
+    RTB_CUDA(cudaSetDevice(c->device));
+    if (n == 0) return RTB_OK;
+    RtbRay* dRays = nullptr; RtbHit* dHits = nullptr;
+    RTB_CUDA(cudaMalloc(&dRays, n * sizeof(RtbRay)));
+    cudaError_t e = cudaMalloc(&dHits, n * sizeof(RtbHit));
+    if (e != cudaSuccess) { cudaFree(dRays); return fail(RTB_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    cudaMemcpyAsync(dRays, rays, n * sizeof(RtbRay), cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(dHits, hits, n * sizeof(RtbHit), cudaMemcpyHostToDevice, c->stream);   // shadow mode: carries tMax
+    int rc = rtb_trace_batch_device(c, dRays, n, dHits, mode, nullptr);
+    if (rc == RTB_OK)
+    {
+        e = cudaMemcpyAsync(hits, dHits, n * sizeof(RtbHit), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(RTB_ERR_CUDA, "trace batch failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(dRays); cudaFree(dHits);
+    return rc;
+}
+
+int rtb_sample_batch(RtbContext* c, const RtbPassDesc* pass, const uint32_t* xy, uint64_t n, uint32_t numDims, uint32_t* out)
+{
+    if (!c || !pass || (n && (!xy || !out))) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    RTB_CUDA(cudaSetDevice(c->device));
+    if (n == 0 || numDims == 0) return RTB_OK;
+    PassParams P;
+    int rc = fill_pass_params(c, pass, P, true);
+    if (rc != RTB_OK) return rc;
+    uint32_t* dXy = nullptr; uint32_t* dOut = nullptr;
+    RTB_CUDA(cudaMalloc(&dXy, n * 2 * sizeof(uint32_t)));
+    cudaError_t e = cudaMalloc(&dOut, n * numDims * sizeof(uint32_t));
+    if (e != cudaSuccess) { cudaFree(dXy); return fail(RTB_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    cudaMemcpyAsync(dXy, xy, n * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    SceneView v = c->view;
+    k_sample_batch<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(v, P, dXy, n, numDims, dOut);
+    e = cudaMemcpyAsync(out, dOut, n * numDims * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dXy); cudaFree(dOut);
+    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "sample batch failed: %s", cudaGetErrorString(e));
+    return RTB_OK;
+}
+
+int rtb_primary_rays(RtbContext* c, const RtbPassDesc* pass, RtbRay* rays)
+{
+    if (!c || !pass || !rays) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    if (c->width == 0) return fail(RTB_ERR_INVALID_ARG, "viewport has no size");
+    RTB_CUDA(cudaSetDevice(c->device));
+    PassParams P;
+    int rc = fill_pass_params(c, pass, P, true);
+    if (rc != RTB_OK) return rc;
+    const size_t n = (size_t)c->width * c->height;
+    RtbRay* d = nullptr;
+    RTB_CUDA(cudaMalloc(&d, n * sizeof(RtbRay)));
+    k_primary_rays<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->view, P, d);
+    cudaError_t e = cudaMemcpyAsync(rays, d, n * sizeof(RtbRay), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "primary rays failed: %s", cudaGetErrorString(e));
+    return RTB_OK;
+}
+
+int rtb_set_profiling(RtbContext* c, int enable)
+{
+    if (!c) return fail(RTB_ERR_INVALID_ARG, "null context");
+    c->profiling = enable != 0;
+    return RTB_OK;
+}
+
+int rtb_get_pass_timings(RtbContext* c, RtbPassTimings* out)
+{
+    if (!c || !out) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    *out = c->timings;
+    return RTB_OK;
+}
+
+} // extern "C"

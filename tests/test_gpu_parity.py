@@ -1,0 +1,209 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (include/rtb200.h), against the golden fixtures
+generated from the real reference (tests/golden/make_golden.py) and, where the prebuilt oracle binary travelled to
+this box (oracle/_ref), against the reference itself run live on the same inputs.
+
+Bar: BIT-EXACT float32 sum buffers, hit records, sampler integers and ray counters (oracle = exact-math build of the
+reference: IEEE div/sqrt, no FMA contraction; see DESIGN.md "Oracle").
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from raytracer_b200 import capi
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(device=0)
+    yield c
+    c.close()
+
+
+def render_golden_case(ctx, scene, renderer, which=0):
+    meta = json.load(open(util.golden("%s_%s.json" % (scene, renderer))))
+    w, h = meta["width"], meta["height"]
+    sf = capi.SceneFile(util.golden(scene + ".rtb"))
+    ps = capi.PassScript(util.golden(scene + ".passes"))
+    ctx.upload_scene(sf)
+    ctx.resize(w, h)
+    cam = capi.camera_for(sf, w, h)
+    rid, dbg = util.RENDERER_IDS[renderer]
+    for p in range(meta["passes"]):
+        ctx.render_pass(ctx.make_pass(cam, ps.seeds[p], ps.offsets[p], p, renderer=rid, debug_mode=dbg, max_depth=8))
+    return meta, ctx.read_sum(which), ctx.counters()
+
+
+@pytest.mark.parametrize("scene,renderer", util.GOLDEN_RENDERS)
+def test_sum_buffer_bit_exact(ctx, scene, renderer):
+    meta, img, counters = render_golden_case(ctx, scene, renderer)
+    want = util.load_sum(util.golden("%s_%s.sum" % (scene, renderer)), meta["width"], meta["height"])
+    util.assert_bit_identical(img, want, "%s/%s sum buffer" % (scene, renderer))
+    assert counters["numPrimaryRays"] == meta["numPrimaryRays"]
+    if renderer in ("mis", "pt"):
+        assert counters["numRays"] == meta["numRays"]
+        assert counters["numShadowRays"] == meta["numShadowRays"]
+        assert counters["numShadowRaysHit"] == meta["numShadowRaysHit"]
+
+
+@pytest.mark.parametrize("scene", ["c1_sphere_area", "cornell", "materials", "mesh_small"])
+def test_secondary_sum_bit_exact(ctx, scene):
+    meta, img, _ = render_golden_case(ctx, scene, "mis", which=1)
+    want = util.load_sum(util.golden("%s_mis.sum2" % scene), meta["width"], meta["height"])
+    util.assert_bit_identical(img, want, "%s secondary sum" % scene)
+
+
+@pytest.mark.parametrize("scene", ["cornell", "materials", "mesh_small"])
+def test_trace_batch_closest(ctx, scene):
+    ctx.upload_scene(capi.SceneFile(util.golden(scene + ".rtb")))
+    rays = np.fromfile(util.golden(scene + ".rays"), dtype=capi.RAY_DTYPE)
+    want = np.fromfile(util.golden(scene + ".hits"), dtype=capi.HIT_DTYPE)
+    got = ctx.trace_batch(rays, capi.RTB_TRACE_CLOSEST)
+    assert (got["objectId"] == want["objectId"]).all()
+    hit = want["objectId"] != capi.RTB_INVALID_OBJECT
+    assert hit.sum() > 100, "fixture should contain hits"
+    assert (got["subObjectId"][hit] == want["subObjectId"][hit]).all()
+    util.assert_bit_identical(got["distance"], want["distance"], "%s hit distance" % scene)
+    mesh = hit & (want["subObjectId"] < 0xFFFFFFF0) & np.isin(want["objectId"], mesh_object_ids(scene))
+    util.assert_bit_identical(got["u"][mesh], want["u"][mesh], "%s hit u" % scene)
+    util.assert_bit_identical(got["v"][mesh], want["v"][mesh], "%s hit v" % scene)
+
+
+def mesh_object_ids(scene):
+    sf = capi.SceneFile(util.golden(scene + ".rtb"))
+    objs = np.frombuffer(sf.objects.tobytes(), dtype=np.uint32).reshape(sf.num_objects, 36)
+    shapes = np.frombuffer(sf.shapes.tobytes(), dtype=np.uint32).reshape(sf.num_shapes, 16)
+    ids = []
+    for i in range(sf.num_objects):
+        kind, shape_index = objs[i, 0], objs[i, 1]
+        if kind == 0 and shapes[shape_index, 0] == 3:
+            ids.append(i)
+    return np.array(ids, dtype=np.uint32)
+
+
+@pytest.mark.parametrize("scene", ["cornell", "materials", "mesh_small"])
+def test_trace_batch_shadow(ctx, scene):
+    ctx.upload_scene(capi.SceneFile(util.golden(scene + ".rtb")))
+    rays = np.fromfile(util.golden(scene + ".rays"), dtype=capi.RAY_DTYPE)
+    tmax = np.fromfile(util.golden(scene + ".tmax"), dtype=np.float32)
+    want = np.fromfile(util.golden(scene + ".shadow_hits"), dtype=capi.HIT_DTYPE)
+    got = ctx.trace_batch(rays, capi.RTB_TRACE_SHADOW, tmax=tmax)
+    assert 0 < want["occluded"].sum() < len(want)
+    assert (got["occluded"] == want["occluded"]).all()
+
+
+def test_trace_batch_empty(ctx):
+    ctx.upload_scene(capi.SceneFile(util.golden("cornell.rtb")))
+    got = ctx.trace_batch(np.zeros(0, dtype=capi.RAY_DTYPE))
+    assert len(got) == 0
+
+
+@pytest.mark.parametrize("blue", [True, False])
+def test_sampler_streams_integer_exact(ctx, blue):
+    ps = capi.PassScript(util.golden("cornell.passes"))
+    want = np.fromfile(util.golden("sampler_bn.u32" if blue else "sampler_nobn.u32"), dtype=np.uint32).reshape(ps.num_passes, 20, 24, 40)
+    sf = capi.SceneFile(util.golden("cornell.rtb"))
+    ctx.upload_scene(sf)
+    ctx.resize(64, 64)
+    cam = capi.camera_for(sf, 64, 64)
+    ys, xs = np.mgrid[0:20, 0:24]
+    xy = np.stack([xs.ravel(), ys.ravel()], axis=1).astype(np.uint32)
+    for p in range(ps.num_passes):
+        got = ctx.sample_batch(ctx.make_pass(cam, ps.seeds[p], ps.offsets[p], p, blue_noise=blue), xy, 40)
+        assert (got.reshape(20, 24, 40) == want[p]).all(), "pass %d" % p
+
+
+@pytest.mark.parametrize("scene", ["cornell", "mesh_small"])
+def test_primary_rays_bit_exact(ctx, scene):
+    sf = capi.SceneFile(util.golden(scene + ".rtb"))
+    ps = capi.PassScript(util.golden(scene + ".passes"))
+    ctx.upload_scene(sf)
+    ctx.resize(64, 64)
+    cam = capi.camera_for(sf, 64, 64)
+    got = ctx.primary_rays(ctx.make_pass(cam, ps.seeds[1], ps.offsets[1], 1))
+    want = np.fromfile(util.golden(scene + ".primary"), dtype=capi.RAY_DTYPE)
+    for f in ("origin", "dir", "invDir", "originDivDir"):
+        util.assert_bit_identical(got[f][:, :3], want[f][:, :3], "%s primary %s" % (scene, f))
+
+
+def test_error_paths(ctx):
+    sf = capi.SceneFile(util.golden("cornell.rtb"))
+    ps = capi.PassScript(util.golden("cornell.passes"))
+    ctx.upload_scene(sf)
+    with pytest.raises(capi.RtbError):
+        ctx.resize(0, 10)                      # Viewport::Resize rejects empty sizes (Viewport.cpp:52-58)
+    ctx.resize(32, 32)
+    cam = capi.camera_for(sf, 32, 32)
+    with pytest.raises(capi.RtbError):         # not enough seeded dimensions -> refuse instead of an RNG fallback
+        ctx.render_pass(ctx.make_pass(cam, ps.seeds[0][:8], ps.offsets[0], 0))
+    with pytest.raises(capi.RtbError):
+        ctx.render_pass(ctx.make_pass(cam, ps.seeds[0], ps.offsets[0], 0, renderer=7))
+    c2 = capi.Context(device=0)
+    c2.resize(16, 16)
+    with pytest.raises(capi.RtbError):         # no scene uploaded (Viewport: "Missing renderer", Viewport.cpp:194-198)
+        c2.render_pass(c2.make_pass(cam, ps.seeds[0], ps.offsets[0], 0))
+    c2.close()
+
+
+def test_empty_scene_is_black(ctx, tmp_path):
+    """RenderingTest.EmptyScene (Tests/RaytracingTests.cpp:263-285): an empty scene renders exactly zero."""
+    sf = capi.SceneFile(util.golden("cornell.rtb"))
+    ps = capi.PassScript(util.golden("cornell.passes"))
+    sf.num_tlas = sf.num_objects = sf.num_lights = sf.num_global_lights = 0
+    ctx.upload_scene(sf)
+    ctx.resize(32, 32)
+    cam = capi.camera_for(sf, 32, 32)
+    for rid in (0, 1):
+        ctx.reset()
+        ctx.render_pass(ctx.make_pass(cam, ps.seeds[0], ps.offsets[0], 0, renderer=rid))
+        assert (ctx.read_sum() == 0.0).all()
+
+
+def test_sharded_render_is_bit_identical(ctx):
+    """Tile-interleaved shards (the multi-GPU decomposition) reassemble to exactly the single-context image."""
+    scene = "mesh_small"
+    meta, full, _ = render_golden_case(ctx, scene, "mis")
+    w, h = meta["width"], meta["height"]
+    sf = capi.SceneFile(util.golden(scene + ".rtb"))
+    ps = capi.PassScript(util.golden(scene + ".passes"))
+    cam = capi.camera_for(sf, w, h)
+    acc = np.zeros_like(full)
+    n = 3
+    for s in range(n):
+        c = capi.Context(device=0, num_shards=n, shard_index=s, tile_size=16)
+        c.upload_scene(sf)
+        c.resize(w, h)
+        for p in range(meta["passes"]):
+            c.render_pass(c.make_pass(cam, ps.seeds[p], ps.offsets[p], p))
+        part = c.read_sum()
+        assert ((acc != 0) & (part != 0)).sum() == 0, "shards overlap"
+        acc += part
+        c.close()
+    util.assert_bit_identical(acc, full, "sharded film")
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="prebuilt oracle/_ref/exact did not travel to this box")
+@pytest.mark.parametrize("scene,w,h,passes", [("cornell", 200, 152, 6), ("mesh_small", 160, 90, 5), ("materials", 96, 128, 3)])
+def test_live_oracle_larger_ragged_sizes(ctx, tmp_path, scene, w, h, passes):
+    """Same inputs through the real reference, live on this box's CPU, at sizes that are not tile multiples."""
+    sj = os.path.join(util.GOLDEN, "scenes", scene + ".json")
+    data = os.path.join(util.GOLDEN, "scenes") + "/"
+    dims = 256 if scene == "materials" else 128
+    sump, passp, flatp = str(tmp_path / "o.sum"), str(tmp_path / "o.passes"), str(tmp_path / "o.rtb")
+    meta = util.run_rtref(["render", "--scene", sj, "--data", data, "--width", w, "--height", h, "--passes", passes, "--dims", dims,
+                           "--depth", 8, "--strategy", "all", "--dump-sum", sump, "--dump-passes", passp], seed="777")
+    util.run_rtref(["flat", "--scene", sj, "--data", data, "--width", w, "--height", h, "--out", flatp])
+    sf = capi.SceneFile(flatp)
+    ps = capi.PassScript(passp)
+    ctx.upload_scene(sf)
+    ctx.resize(w, h)
+    cam = capi.camera_for(sf, w, h)
+    for p in range(passes):
+        ctx.render_pass(ctx.make_pass(cam, ps.seeds[p], ps.offsets[p], p))
+    util.assert_bit_identical(ctx.read_sum(), util.load_sum(sump, w, h), "%s live oracle" % scene)
+    c = ctx.counters()
+    assert (c["numRays"], c["numShadowRays"], c["numShadowRaysHit"]) == (meta["numRays"], meta["numShadowRays"], meta["numShadowRaysHit"])

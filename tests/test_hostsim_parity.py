@@ -1,0 +1,82 @@
+"""CPU-side checks (no GPU): the DEVICE headers compiled with g++ (tests/hostsim, a test tool that is not part of the
+product) reproduce the golden fixtures of the real reference bit for bit.  This is how the numerics of the CUDA code
+are debugged in the authoring container, where there is no GPU; the `-m gpu` tests then check the real kernels."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from raytracer_b200 import capi
+from tests import util
+
+HOSTSIM_DIR = os.path.join(util.ROOT, "tests", "hostsim")
+HOSTSIM = os.path.join(HOSTSIM_DIR, "hostsim")
+
+
+@pytest.fixture(scope="module")
+def hostsim(tmp_path_factory):
+    subprocess.run(["bash", os.path.join(HOSTSIM_DIR, "build.sh")], check=True)
+    bn = tmp_path_factory.mktemp("bn") / "bn.dat"
+    capi.load_blue_noise().tofile(str(bn))     # interleaved RGBA16 layout the sampler reads
+    return str(bn)
+
+
+@pytest.mark.parametrize("scene,renderer", util.GOLDEN_RENDERS)
+def test_hostsim_sum_buffer_bit_exact(hostsim, tmp_path, scene, renderer):
+    meta = json.load(open(util.golden("%s_%s.json" % (scene, renderer))))
+    rid, dbg = util.RENDERER_IDS[renderer]
+    out = str(tmp_path / "out.sum")
+    r = subprocess.run([HOSTSIM, "render", util.golden(scene + ".rtb"), util.golden(scene + ".passes"), str(meta["width"]), str(meta["height"]),
+                        out, str(rid), "8", str(dbg), "1", hostsim], stdout=subprocess.PIPE, text=True, check=True)
+    counters = json.loads(r.stdout.strip().splitlines()[-1])
+    want = util.load_sum(util.golden("%s_%s.sum" % (scene, renderer)), meta["width"], meta["height"])
+    util.assert_bit_identical(util.load_sum(out, meta["width"], meta["height"]), want, "%s/%s" % (scene, renderer))
+    if renderer in ("mis", "pt"):
+        assert counters["numRays"] == meta["numRays"]
+        assert counters["numShadowRays"] == meta["numShadowRays"]
+        assert counters["numShadowRaysHit"] == meta["numShadowRaysHit"]
+
+
+@pytest.mark.parametrize("scene", ["cornell", "materials", "mesh_small"])
+def test_hostsim_trace_batch(hostsim, tmp_path, scene):
+    out = str(tmp_path / "hits")
+    subprocess.run([HOSTSIM, "trace", util.golden(scene + ".rtb"), util.golden(scene + ".rays"), out], check=True)
+    got = np.fromfile(out, dtype=capi.HIT_DTYPE)
+    want = np.fromfile(util.golden(scene + ".hits"), dtype=capi.HIT_DTYPE)
+    assert (got["objectId"] == want["objectId"]).all()
+    util.assert_bit_identical(got["distance"], want["distance"], "distance")
+    subprocess.run([HOSTSIM, "trace", util.golden(scene + ".rtb"), util.golden(scene + ".rays"), out, util.golden(scene + ".tmax")], check=True)
+    got = np.fromfile(out, dtype=capi.HIT_DTYPE)
+    want = np.fromfile(util.golden(scene + ".shadow_hits"), dtype=capi.HIT_DTYPE)
+    assert (got["occluded"] == want["occluded"]).all()
+
+
+@pytest.mark.parametrize("blue", [True, False])
+def test_hostsim_sampler(hostsim, tmp_path, blue):
+    out = str(tmp_path / "s.u32")
+    subprocess.run([HOSTSIM, "sampler", util.golden("cornell.passes"), "24", "20", "40", out, hostsim if blue else "-"], check=True)
+    want = np.fromfile(util.golden("sampler_bn.u32" if blue else "sampler_nobn.u32"), dtype=np.uint32)
+    assert (np.fromfile(out, dtype=np.uint32) == want).all()
+
+
+@pytest.mark.parametrize("scene", ["cornell", "mesh_small"])
+def test_hostsim_primary_rays(hostsim, tmp_path, scene):
+    out = str(tmp_path / "p.rays")
+    subprocess.run([HOSTSIM, "primary", util.golden(scene + ".rtb"), util.golden(scene + ".passes"), "1", "64", "64", out], check=True)
+    got = np.fromfile(out, dtype=capi.RAY_DTYPE)
+    want = np.fromfile(util.golden(scene + ".primary"), dtype=capi.RAY_DTYPE)
+    for f in ("origin", "dir", "invDir", "originDivDir"):
+        util.assert_bit_identical(got[f][:, :3], want[f][:, :3], f)
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
+def test_golden_fixtures_reproduce_from_the_reference(tmp_path):
+    """The committed fixtures are what the real reference produces today (pins the oracle: fixed seed, exact math)."""
+    scn = os.path.join(util.GOLDEN, "scenes")
+    out = str(tmp_path / "c.sum")
+    meta = util.run_rtref(["render", "--scene", os.path.join(scn, "cornell.json"), "--data", scn + "/", "--width", 64, "--height", 64,
+                           "--passes", 4, "--dims", 128, "--depth", 8, "--strategy", "all", "--dump-sum", out])
+    util.assert_bit_identical(util.load_sum(out, 64, 64), util.load_sum(util.golden("cornell_mis.sum"), 64, 64), "cornell golden")
+    assert meta["numRays"] == json.load(open(util.golden("cornell_mis.json")))["numRays"]

@@ -1,0 +1,61 @@
+"""Shared helpers for the parity tests."""
+import json
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+ORACLE_EXACT = os.path.join(ROOT, "oracle", "_ref", "exact")
+ORACLE_AVX = os.path.join(ROOT, "oracle", "_ref", "avx")
+
+RENDERER_IDS = {"mis": (1, 0), "pt": (0, 0), "dbgtri": (2, 1), "dbgdepth": (2, 2)}   # (RtbRenderer, RtbDebugMode)
+GOLDEN_RENDERS = [
+    ("c1_sphere_area", "mis"),
+    ("cornell", "mis"), ("cornell", "pt"), ("cornell", "dbgtri"), ("cornell", "dbgdepth"),
+    ("materials", "mis"), ("materials", "pt"),
+    ("mesh_small", "mis"), ("mesh_small", "pt"), ("mesh_small", "dbgtri"), ("mesh_small", "dbgdepth"),
+]
+
+
+def golden(name):
+    return os.path.join(GOLDEN, name)
+
+
+def load_sum(path, w, h):
+    return np.fromfile(path, dtype=np.float32).reshape(h, w, 3)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_bit_identical(a, b, what):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    assert a.shape == b.shape, "%s: shape %s vs %s" % (what, a.shape, b.shape)
+    same = bits(a) == bits(b)
+    if not same.all():
+        bad = np.argwhere(~same)
+        rel = np.abs(a - b) / np.maximum(np.abs(b), 1e-3)
+        raise AssertionError("%s: %d of %d floats differ bitwise (first at %s: got %r want %r, max rel %.3e)"
+                             % (what, bad.shape[0], same.size, bad[0].tolist(), a[tuple(bad[0])], b[tuple(bad[0])], float(rel.max())))
+
+
+def oracle_available(variant="exact"):
+    root = ORACLE_EXACT if variant == "exact" else ORACLE_AVX
+    return os.path.exists(os.path.join(root, "rtref")) and os.path.exists(os.path.join(root, "libCore.so"))
+
+
+def run_rtref(args, variant="exact", seed="12345", timeout=1800):
+    """Run the oracle harness (the real reference) - test infrastructure only."""
+    root = ORACLE_EXACT if variant == "exact" else ORACLE_AVX
+    run_dir = os.path.join(root, "run")
+    os.makedirs(run_dir, exist_ok=True)
+    env = dict(os.environ, RT_FIXED_SEED=seed)
+    r = subprocess.run([os.path.join(root, "rtref")] + [str(a) for a in args], cwd=run_dir, env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    assert r.returncode == 0, "rtref failed: %s\n%s" % (args, r.stderr[-2000:])
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    return json.loads(lines[-1]) if lines else None
