@@ -287,7 +287,7 @@ RTB_HD void shade_debug(const SceneView& S, const PassParams& P, PathState& ps, 
     }
     case RTB_DEBUG_DEPTH:
     {
-        const float invDepth = 1.0f - 1.0f / (1.0f + hit.distance / 10.0f);
+        const float invDepth = 1.0f - 1.0f / (1.0f + fdiv(hit.distance, 10.0f));
         c = v4s(invDepth);
         break;
     }

@@ -40,6 +40,17 @@ RTB_HD uint32_t f2bits(float f) { union { uint32_t u; float f; } c; c.f = f; ret
 // single-rounding fused multiply-add; the only place FMA is allowed to appear
 RTB_HD float fma_(float a, float b, float c) { return fmaf(a, b, c); }
 
+// IEEE division by a value the compiler can see is a constant: under -ftz=true nvcc rewrites `x / 10.0f` into
+// `x * 0.1f` (mul.rn.ftz by the rounded reciprocal), which is one ulp off; the intrinsic keeps div.rn.
+RTB_HD float fdiv(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+
 // _mm_min_ps(a, b): a < b ? a : b   (second operand on NaN / equal)   Vector4ImplSSE.h:388-391
 RTB_HD float sse_min(float a, float b) { return a < b ? a : b; }
 // _mm_max_ps(a, b): a > b ? a : b                                     Vector4ImplSSE.h:393-396
@@ -251,8 +262,8 @@ RTB_HD void cartesian_to_spherical(const V3& in, float& u, float& v)
 {
     const float theta = fast_acos(s_clamp(in.y, -1.0f, 1.0f));
     const float phi = s_abs(in.x) > FLT_EPSILON ? fast_atan2(in.z, in.x) : 0.0f;
-    u = phi / (2.0f * RTB_PI) + 0.5f;
-    v = theta / RTB_PI;
+    u = fdiv(phi, 2.0f * RTB_PI) + 0.5f;
+    v = fdiv(theta, RTB_PI);
 }
 
 // BuildOrthonormalBasis                                               Geometry.cpp:15-33
