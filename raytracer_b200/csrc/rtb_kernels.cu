@@ -7,8 +7,9 @@
 //     k_traverse   closest hit     two-level BVH, one ray per thread, persistent grid           (Scene::Traverse)
 //     k_shade      per path vertex emission / light hit / miss / NEE sampling / RR / BSDF sample (PathTracerMIS::RenderPixel body)
 //                                  -> compacts surviving paths into the other path buffer (warp ballot + one atomic per warp)
-//                                  -> writes this vertex' shadow rays + a compacted list of paths that own some
-//     k_shadow     any hit         per path: its shadow rays in light order, radiance added if unoccluded (Scene::Traverse_Shadow)
+//                                  -> writes this vertex' shadow rays + compacted lists of the rays and of the paths that own some
+//     k_shadow     any hit         one shadow ray per thread; an occluded ray zeroes its contribution      (Scene::Traverse_Shadow)
+//     k_resolve                    per path: sum of its contributions in light order -> pass colour         (PathTracerMIS::SampleLights)
 //   k_film                         sum += pass colour (+ secondarySum on even passes)             (Film::AccumulateColor)
 //
 // Everything is stream-ordered on one stream with device-resident queue counters: no host round trip inside a pass.
@@ -46,6 +47,7 @@ struct Control
 {
     uint32_t pathCount[RTB_MAX_DEPTH_SLOTS + 2];     // live paths entering depth d
     uint32_t shadowPathCount[RTB_MAX_DEPTH_SLOTS + 2];
+    uint32_t shadowRayCount[RTB_MAX_DEPTH_SLOTS + 2];
     unsigned long long numRays, numShadowRays, numShadowRaysHit, numBoxTests, numTriTests;
 };
 
@@ -63,6 +65,7 @@ struct Wavefront
     float4*  shThr;       // per input index: throughput.xyz at that vertex, pixel slot bits
     uint32_t* shCount;    // per input index: number of shadow rays
     uint32_t* shList;     // compacted input indices that own >= 1 shadow ray
+    uint32_t* rayList;    // compacted shadow-ray slots (i * raysPerPath + r) of the current depth
     Control* ctl;
     const uint32_t* pixelList;   // pixel slot -> y * width + x
     uint32_t numPixels;
@@ -213,14 +216,31 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneView
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
             if (alive) store_path(out, base + __popc(aliveMask & ((1u << lane) - 1u)), ps);
         }
-        // compacted list of paths that own shadow rays
+        // compacted lists of the paths that own shadow rays and of the rays themselves (warp prefix sum, two atomics per warp)
         const uint32_t shMask = __ballot_sync(0xFFFFFFFFu, numShadow != 0);
         if (shMask)
         {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&W.ctl->shadowPathCount[depth], __popc(shMask));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (numShadow) W.shList[base + __popc(shMask & ((1u << lane) - 1u))] = i;
+            uint32_t incl = numShadow;
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= (uint32_t)o) incl += up;
+            }
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            uint32_t pathBase = 0, rayBase = 0;
+            if (lane == 0)
+            {
+                pathBase = atomicAdd(&W.ctl->shadowPathCount[depth], __popc(shMask));
+                rayBase = atomicAdd(&W.ctl->shadowRayCount[depth], total);
+            }
+            pathBase = __shfl_sync(0xFFFFFFFFu, pathBase, 0);
+            rayBase = __shfl_sync(0xFFFFFFFFu, rayBase, 0);
+            if (numShadow)
+            {
+                W.shList[pathBase + __popc(shMask & ((1u << lane) - 1u))] = i;
+                const uint32_t first = rayBase + incl - numShadow;
+                for (uint32_t r = 0; r < numShadow; ++r) W.rayList[first + r] = i * W.raysPerPath + r;
+            }
         }
     }
     // counters: one atomic per warp
@@ -231,32 +251,24 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneView
 template <bool kCount>
 __global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ SceneView S, const __grid_constant__ Wavefront W, uint32_t depth)
 {
-    const uint32_t count = W.ctl->shadowPathCount[depth];
+    const uint32_t count = W.ctl->shadowRayCount[depth];
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
     unsigned long long visibleLocal = 0;
     TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride)
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
     {
-        const uint32_t i = W.shList[j];
-        const uint32_t n = W.shCount[i];
-        const uint32_t base = i * W.raysPerPath;
-        // SampleLights: accumulatedColor += SampleLight(light) in light order (PathTracerMIS.cpp:142-148)
-        V3 sum = v3s(0.0f);
-        for (uint32_t r = 0; r < n; ++r)
+        const uint32_t j = W.rayList[k];
+        const float4 a = W.sr0[j], b = W.sr1[j], c = W.sr2[j], d = W.sr3[j];
+        Ray ray;
+        ray.origin = v3(a.x, a.y, a.z); ray.dir = v3(b.x, b.y, b.z); ray.invDir = v3(c.x, c.y, c.z); ray.originDivDir = v3(d.x, d.y, d.z);
+        const bool occluded = scene_traverse_shadow<kCount>(S, ray, a.w, &cnt);
+        if (occluded)
         {
-            const float4 a = W.sr0[base + r], b = W.sr1[base + r], c = W.sr2[base + r], d = W.sr3[base + r];
-            Ray ray;
-            ray.origin = v3(a.x, a.y, a.z); ray.dir = v3(b.x, b.y, b.z); ray.invDir = v3(c.x, c.y, c.z); ray.originDivDir = v3(d.x, d.y, d.z);
-            const bool occluded = scene_traverse_shadow<kCount>(S, ray, a.w, &cnt);
-            if (!occluded) { sum = sum + v3(b.w, c.w, d.w); visibleLocal++; }
-            else sum = sum + v3s(0.0f);
+            // SampleLight returns RayColor::Zero() for an occluded light (PathTracerMIS.cpp:92-96)
+            W.sr1[j].w = 0.0f; W.sr2[j].w = 0.0f; W.sr3[j].w = 0.0f;
         }
-        const float4 t = W.shThr[i];
-        const uint32_t pixel = __float_as_uint(t.w);
-        const float4 pc = W.passColor[pixel];
-        const V3 res = mul_add(v3(t.x, t.y, t.z), sum, v3(pc.x, pc.y, pc.z));
-        W.passColor[pixel] = make_float4(res.x, res.y, res.z, 0.0f);
+        else visibleLocal++;
     }
     for (int o = 16; o > 0; o >>= 1) visibleLocal += __shfl_down_sync(0xFFFFFFFFu, visibleLocal, o);
     if (lane == 0 && visibleLocal) atomicAdd(&W.ctl->numShadowRaysHit, visibleLocal);
@@ -264,6 +276,27 @@ __global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ SceneVie
     {
         atomicAdd(&W.ctl->numBoxTests, (unsigned long long)cnt.boxTests);
         atomicAdd(&W.ctl->numTriTests, (unsigned long long)cnt.triTests);
+    }
+}
+
+// PathTracerMIS::SampleLights: accumulatedColor += SampleLight(light) in light order (PathTracerMIS.cpp:142-148), then
+// resultColor.MulAndAccumulate(throughput, accumulatedColor) (PathTracerMIS.cpp:320)
+__global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ Wavefront W, uint32_t depth)
+{
+    const uint32_t count = W.ctl->shadowPathCount[depth];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride)
+    {
+        const uint32_t i = W.shList[j];
+        const uint32_t n = W.shCount[i];
+        const uint32_t base = i * W.raysPerPath;
+        V3 sum = v3s(0.0f);
+        for (uint32_t r = 0; r < n; ++r) sum = sum + v3(W.sr1[base + r].w, W.sr2[base + r].w, W.sr3[base + r].w);
+        const float4 t = W.shThr[i];
+        const uint32_t pixel = __float_as_uint(t.w);
+        const float4 pc = W.passColor[pixel];
+        const V3 res = mul_add(v3(t.x, t.y, t.z), sum, v3(pc.x, pc.y, pc.z));
+        W.passColor[pixel] = make_float4(res.x, res.y, res.z, 0.0f);
     }
 }
 
@@ -444,7 +477,7 @@ struct RtbContext
     DevArray<uint4> hit0;
     DevArray<float> hit1;
     DevArray<float4> passColor, sr0, sr1, sr2, sr3, shThr;
-    DevArray<uint32_t> shCount, shList;
+    DevArray<uint32_t> shCount, shList, rayList;
     DevArray<Control> ctl;
     DevArray<uint32_t> seed;
     Wavefront wf;
@@ -472,7 +505,7 @@ static void free_film(RtbContext* c)
     c->pixelList.release(); c->pixelListAll.release(); c->sum.release(); c->sum2.release(); c->raster.release();
     for (int b = 0; b < 2; ++b) { for (int k = 0; k < 4; ++k) c->p[b][k].release(); c->p4[b].release(); }
     c->hit0.release(); c->hit1.release(); c->passColor.release();
-    c->sr0.release(); c->sr1.release(); c->sr2.release(); c->sr3.release(); c->shThr.release(); c->shCount.release(); c->shList.release();
+    c->sr0.release(); c->sr1.release(); c->sr2.release(); c->sr3.release(); c->shThr.release(); c->shCount.release(); c->shList.release(); c->rayList.release();
 }
 
 static int alloc_shadow(RtbContext* c)
@@ -484,6 +517,7 @@ static int alloc_shadow(RtbContext* c)
     c->raysPerPath = rpp;
     const size_t n = (size_t)c->numPixels * rpp;
     RTB_CUDA(c->sr0.alloc(n)); RTB_CUDA(c->sr1.alloc(n)); RTB_CUDA(c->sr2.alloc(n)); RTB_CUDA(c->sr3.alloc(n));
+    RTB_CUDA(c->rayList.alloc(n));
     return RTB_OK;
 }
 
@@ -497,7 +531,7 @@ static void fill_wavefront(RtbContext* c)
     }
     w.hit0 = c->hit0.ptr; w.hit1 = c->hit1.ptr; w.passColor = c->passColor.ptr;
     w.sr0 = c->sr0.ptr; w.sr1 = c->sr1.ptr; w.sr2 = c->sr2.ptr; w.sr3 = c->sr3.ptr;
-    w.shThr = c->shThr.ptr; w.shCount = c->shCount.ptr; w.shList = c->shList.ptr;
+    w.shThr = c->shThr.ptr; w.shCount = c->shCount.ptr; w.shList = c->shList.ptr; w.rayList = c->rayList.ptr;
     w.ctl = c->ctl.ptr;
     w.pixelList = c->pixelList.ptr;
     w.numPixels = c->numPixels;
@@ -765,6 +799,7 @@ int rtb_render_pass(RtbContext* c, const RtbPassDesc* pass)
         {
             if (count) k_shadow<true><<<blocks128, 128, 0, s>>>(c->view, c->wf, d);
             else k_shadow<false><<<blocks128, 128, 0, s>>>(c->view, c->wf, d);
+            k_resolve<<<blocks256, 256, 0, s>>>(c->wf, d);
         }
         if (prof) marks.push_back(next_event(c, ev));
     }
@@ -787,14 +822,14 @@ int rtb_render_pass(RtbContext* c, const RtbPassDesc* pass)
             t.traverseMs += ms(k, k + 1); t.shadeMs += ms(k + 1, k + 2); t.shadowMs += ms(k + 2, k + 3);
             k += 3;
             t.traverseLaunches++; t.shadeLaunches++;
-            if (pass->renderer == RTB_RENDERER_PATH_TRACER_MIS && c->numLights > 0) t.shadowLaunches++;
+            if (pass->renderer == RTB_RENDERER_PATH_TRACER_MIS && c->numLights > 0) t.shadowLaunches += 2;
         }
         t.totalMs = ms(0, marks.size() - 1);
         t.totalLaunches = 2 + t.traverseLaunches + t.shadeLaunches + t.shadowLaunches;
         Control h;
         RTB_CUDA(cudaMemcpy(&h, c->ctl.ptr, sizeof(Control), cudaMemcpyDeviceToHost));
         for (uint32_t d = 0; d <= depthLimit; ++d) t.traverseRays += h.pathCount[d];
-        t.shadowRays = 0;   // filled by rtb_get_counters deltas on the caller side
+        for (uint32_t d = 0; d <= depthLimit; ++d) t.shadowRays += h.shadowRayCount[d];
     }
     return RTB_OK;
 }

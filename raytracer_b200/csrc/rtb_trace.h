@@ -27,7 +27,7 @@ struct Hit
 
 struct TraceCounters { uint32_t boxTests, triTests; };
 
-#define RTB_STACK_SIZE 96      // BVH::MaxDepth is 128 (BVH.h:20); upload verifies the real depth of every tree fits
+#define RTB_STACK_SIZE 64      // BVH::MaxDepth is 128 (BVH.h:20); upload verifies the real depth of every tree fits
 
 // Intersect_BoxRay, Geometry.h:57-86
 RTB_HD bool box_ray(const Ray& ray, float minx, float miny, float minz, float maxx, float maxy, float maxz, float& outDistance)
@@ -44,6 +44,31 @@ RTB_HD bool box_ray(const Ray& ray, float minx, float miny, float minz, float ma
     const float tFar = sse_min(lmaxx, sse_min(lmaxy, lmaxz));
     outDistance = tNear;
     return (tFar >= tNear) && (tFar >= 0.0f);
+}
+
+// Same test for a ray whose invDir and originDivDir are all finite.  Then no slab distance can be NaN (an fma of
+// finite operands is finite or +-inf), and on NaN-free inputs _mm_min_ps / _mm_max_ps differ from fminf / fmaxf
+// only in the sign of a zero result, which none of the consumers (>=, <) can see.  fminf / fmaxf are single FMNMX
+// instructions; the select form above costs a compare + select each.
+RTB_HD bool box_ray_finite(const Ray& ray, float minx, float miny, float minz, float maxx, float maxy, float maxz, float& outDistance)
+{
+    const float t1x = fma_(minx, ray.invDir.x, -ray.originDivDir.x);
+    const float t1y = fma_(miny, ray.invDir.y, -ray.originDivDir.y);
+    const float t1z = fma_(minz, ray.invDir.z, -ray.originDivDir.z);
+    const float t2x = fma_(maxx, ray.invDir.x, -ray.originDivDir.x);
+    const float t2y = fma_(maxy, ray.invDir.y, -ray.originDivDir.y);
+    const float t2z = fma_(maxz, ray.invDir.z, -ray.originDivDir.z);
+    const float tNear = fmaxf(fminf(t1x, t2x), fmaxf(fminf(t1y, t2y), fminf(t1z, t2z)));
+    const float tFar = fminf(fmaxf(t1x, t2x), fminf(fmaxf(t1y, t2y), fmaxf(t1z, t2z)));
+    outDistance = tNear;
+    return (tFar >= tNear) && (tFar >= 0.0f);
+}
+
+RTB_HD bool is_finite_bits(float x) { return (f2bits(x) & 0x7F800000u) != 0x7F800000u; }
+RTB_HD bool ray_is_finite(const Ray& r)
+{
+    return is_finite_bits(r.invDir.x) && is_finite_bits(r.invDir.y) && is_finite_bits(r.invDir.z) &&
+           is_finite_bits(r.originDivDir.x) && is_finite_bits(r.originDivDir.y) && is_finite_bits(r.originDivDir.z);
 }
 
 // Intersect_BoxRay_TwoSided, Geometry.h:100-130
@@ -152,273 +177,303 @@ RTB_HD DNode load_node(const DNode* nodes, uint32_t index)
 }
 
 #define RTB_NUM_LEAVES(info) ((info) & 0x3FFFFFFFu)
+#define RTB_ENTRY_OBJECT 0xFFFFFFFFu    // stack entry {k, RTB_ENTRY_OBJECT}: "traverse object k" (otherwise {childIndex, leafInfo} of a node)
 
-// MeshShape::Traverse -> GenericTraverse<MeshShape> + MeshShape::Traverse_Leaf
-template <bool kCount>
-RTB_HD void mesh_traverse(const DMesh& mesh, const Ray& ray, uint32_t objectID, Hit& hit, uint32_t* stack, TraceCounters* cnt)
+// IShape::Traverse (Shape.cpp:19-45) / LightSceneObject::Traverse (SceneObject_Light.cpp:27-38) for analytic shapes
+RTB_HD void analytic_closest(const DObjectTrace& obj, const Ray& ray, uint32_t objectID, Hit& hit)
 {
-    if (mesh.numNodes == 0) return;
-    uint32_t stackSize = 0;
-    DNode node = load_node(mesh.nodes, 0);
-    for (;;)
-    {
-        const uint32_t numLeaves = RTB_NUM_LEAVES(node.leafInfo);
-        if (numLeaves != 0)
-        {
-            if (kCount) cnt->triTests += numLeaves;
-            for (uint32_t i = 0; i < numLeaves; ++i)
-            {
-                const uint32_t triangleIndex = node.childIndex + i;
-                V3 v0, e1, e2;
-                load_tri(mesh.tris, triangleIndex, v0, e1, e2);
-                float u, v, distance;
-                if (triangle_ray(ray, v0, e1, e2, u, v, distance))
-                {
-                    if (distance < hit.distance)
-                    {
-                        hit.distance = distance;
-                        hit.subObjectId = triangleIndex;
-                        hit.objectId = objectID;
-                        hit.u = u;
-                        hit.v = v;
-                    }
-                }
-            }
-        }
-        else
-        {
-            const uint32_t childA = node.childIndex;
-            const DNode a = load_node(mesh.nodes, childA);
-            const DNode b = load_node(mesh.nodes, childA + 1);
-            float distanceA, distanceB;
-            bool hitA = box_ray(ray, a.minx, a.miny, a.minz, a.maxx, a.maxy, a.maxz, distanceA);
-            bool hitB = box_ray(ray, b.minx, b.miny, b.minz, b.maxx, b.maxy, b.maxz, distanceB);
-            hitA &= (distanceA < hit.distance);
-            hitB &= (distanceB < hit.distance);
-            if (kCount) cnt->boxTests += 2;
-            if (hitA && hitB)
-            {
-                // visit the nearer child first (Traversal_Single.h:65-75)
-                if (distanceB < distanceA) { node = b; stack[stackSize++] = childA; }
-                else                       { node = a; stack[stackSize++] = childA + 1; }
-                continue;
-            }
-            if (hitA) { node = a; continue; }
-            if (hitB) { node = b; continue; }
-        }
-        if (stackSize == 0) break;
-        node = load_node(mesh.nodes, stack[--stackSize]);
-    }
-}
-
-// MeshShape::Traverse_Shadow -> GenericTraverse_Shadow<MeshShape> + MeshShape::Traverse_Leaf_Shadow
-template <bool kCount>
-RTB_HD bool mesh_traverse_shadow(const DMesh& mesh, const Ray& ray, float maxDistance, uint32_t* stack, TraceCounters* cnt)
-{
-    if (mesh.numNodes == 0) return false;
-    uint32_t stackSize = 0;
-    DNode node = load_node(mesh.nodes, 0);
-    for (;;)
-    {
-        const uint32_t numLeaves = RTB_NUM_LEAVES(node.leafInfo);
-        if (numLeaves != 0)
-        {
-            if (kCount) cnt->triTests += numLeaves;
-            for (uint32_t i = 0; i < numLeaves; ++i)
-            {
-                V3 v0, e1, e2;
-                load_tri(mesh.tris, node.childIndex + i, v0, e1, e2);
-                float u, v, distance;
-                if (triangle_ray(ray, v0, e1, e2, u, v, distance))
-                {
-                    if (distance < maxDistance) return true;
-                }
-            }
-        }
-        else
-        {
-            const uint32_t childA = node.childIndex;
-            const DNode a = load_node(mesh.nodes, childA);
-            const DNode b = load_node(mesh.nodes, childA + 1);
-            float distanceA, distanceB;
-            bool hitA = box_ray(ray, a.minx, a.miny, a.minz, a.maxx, a.maxy, a.maxz, distanceA);
-            bool hitB = box_ray(ray, b.minx, b.miny, b.minz, b.maxx, b.maxy, b.maxz, distanceB);
-            hitA &= (distanceA < maxDistance);
-            hitB &= (distanceB < maxDistance);
-            if (kCount) cnt->boxTests += 2;
-            // no distance ordering for shadow rays (Traversal_Single.h:151-156)
-            if (hitA && hitB) { node = a; stack[stackSize++] = childA + 1; continue; }
-            if (hitA) { node = a; continue; }
-            if (hitB) { node = b; continue; }
-        }
-        if (stackSize == 0) break;
-        node = load_node(mesh.nodes, stack[--stackSize]);
-    }
-    return false;
-}
-
-// Scene::Traverse_Object, Scene.cpp:128-145
-template <bool kCount>
-RTB_HD void traverse_object(const SceneView& S, const Ray& worldRay, uint32_t objectID, Hit& hit, uint32_t* stack, TraceCounters* cnt)
-{
-    const DObjectTrace& obj = S.objTrace[objectID];
-    const Ray ray = transform_ray_unsafe(obj.invTransform, worldRay);
+    if (obj.shapeType == RTB_NO_SHAPE) return;          // point / spot lights: TestRayHit is always false
+    ShapeIntersection isect;
+    if (!shape_intersect(obj.shapeType, obj.size, ray, isect)) return;
     if (obj.kind == RTB_OBJECT_SHAPE)
     {
-        if (obj.shapeType == RTB_SHAPE_MESH)
+        if (isect.nearDist > 0.0f && isect.nearDist < hit.distance)
         {
-            mesh_traverse<kCount>(S.meshes[obj.meshIndex], ray, objectID, hit, stack, cnt);
+            hit.distance = isect.nearDist; hit.objectId = objectID; hit.subObjectId = isect.subObjectId;
             return;
         }
-        // IShape::Traverse, Shape.cpp:19-45
-        ShapeIntersection isect;
-        if (shape_intersect(obj.shapeType, obj.size, ray, isect))
+        if (isect.farDist > 0.0f && isect.farDist < hit.distance)
         {
-            if (isect.nearDist > 0.0f && isect.nearDist < hit.distance)
-            {
-                hit.distance = isect.nearDist; hit.objectId = objectID; hit.subObjectId = isect.subObjectId;
-                return;
-            }
-            if (isect.farDist > 0.0f && isect.farDist < hit.distance)
-            {
-                hit.distance = isect.farDist; hit.objectId = objectID; hit.subObjectId = isect.subObjectId;
-                return;
-            }
+            hit.distance = isect.farDist; hit.objectId = objectID; hit.subObjectId = isect.subObjectId;
         }
     }
     else
     {
-        // LightSceneObject::Traverse + AreaLight::TestRayHit (point/spot lights never report a hit)
-        if (obj.shapeType == RTB_NO_SHAPE) return;
-        ShapeIntersection isect;
-        if (shape_intersect(obj.shapeType, obj.size, ray, isect))
+        const float lightDistance = isect.nearDist;     // AreaLight::TestRayHit, AreaLight.cpp:30-41
+        if (lightDistance > 0.0f && lightDistance < hit.distance)
         {
-            const float lightDistance = isect.nearDist;
-            if (lightDistance > 0.0f && lightDistance < hit.distance)
-            {
-                hit.distance = lightDistance; hit.objectId = objectID; hit.subObjectId = RTB_LIGHT_OBJECT;
-            }
+            hit.distance = lightDistance; hit.objectId = objectID; hit.subObjectId = RTB_LIGHT_OBJECT;
         }
     }
 }
 
-// Scene::Traverse_Object_Shadow, Scene.cpp:147-165
-template <bool kCount>
-RTB_HD bool traverse_object_shadow(const SceneView& S, const Ray& worldRay, uint32_t objectID, float maxDistance, uint32_t* stack, TraceCounters* cnt)
+// IShape::Traverse_Shadow (Shape.cpp:47-57) / LightSceneObject::Traverse_Shadow (SceneObject_Light.cpp:40-53)
+RTB_HD bool analytic_shadow(const DObjectTrace& obj, const Ray& ray, float maxDistance)
 {
-    const DObjectTrace& obj = S.objTrace[objectID];
-    const Ray ray = transform_ray_unsafe(obj.invTransform, worldRay);
-    if (obj.kind == RTB_OBJECT_SHAPE)
-    {
-        if (obj.shapeType == RTB_SHAPE_MESH)
-        {
-            return mesh_traverse_shadow<kCount>(S.meshes[obj.meshIndex], ray, maxDistance, stack, cnt);
-        }
-        // IShape::Traverse_Shadow, Shape.cpp:47-57
-        ShapeIntersection isect;
-        if (!shape_intersect(obj.shapeType, obj.size, ray, isect)) return false;
-        return isect.farDist > 0.0f && isect.nearDist < maxDistance;
-    }
-    // LightSceneObject::Traverse_Shadow, SceneObject_Light.cpp:40-53
     if (obj.shapeType == RTB_NO_SHAPE) return false;
     ShapeIntersection isect;
-    if (shape_intersect(obj.shapeType, obj.size, ray, isect))
-    {
-        if (isect.nearDist < maxDistance) return true;
-    }
-    return false;
+    if (!shape_intersect(obj.shapeType, obj.size, ray, isect)) return false;
+    if (obj.kind == RTB_OBJECT_SHAPE) return isect.farDist > 0.0f && isect.nearDist < maxDistance;
+    return isect.nearDist < maxDistance;
 }
 
-// Scene::Traverse, Scene.cpp:219-243.  `hit` must be preset (objectId = RTB_INVALID_OBJECT, distance = +inf).
-// Note: the top-level box tests use ray.originDivDir exactly as stored - the integrator offsets ray.origin AFTER
-// constructing the ray without refreshing originDivDir (PathTracerMIS.cpp:392-393) and that stale value is part of
-// the reference's behaviour; Traverse_Object rebuilds the ray in object space.
+// One stack entry = what a node visit needs: {childIndex, leafInfo}.  A node's box is only needed when its parent
+// is visited (both children sit in one aligned 64-byte block), so neither a popped node nor the nearer child we
+// descend into is ever fetched again: memory traffic is exactly one 64-byte block per visited inner node.
+struct StackEntry { uint32_t a, b; };
+
+RTB_HD void node_header(const DNode* nodes, uint32_t index, uint32_t& childIndex, uint32_t& leafInfo)
+{
+    childIndex = nodes[index].childIndex;
+    leafInfo = nodes[index].leafInfo;
+}
+
+// Scene::Traverse (Scene.cpp:219-243) = GenericTraverse<Scene> -> Scene::Traverse_Leaf -> Traverse_Object ->
+// GenericTraverse<MeshShape> -> MeshShape::Traverse_Leaf, flattened into ONE loop over ONE stack so that all lanes of
+// a warp execute the same instruction stream whatever level of the two-level BVH they are in (the nested form ran
+// at 2-8 active lanes per warp instruction).  The visiting order is exactly the reference's: near child first,
+// objects of a top-level leaf one after the other, each mesh traversed to completion before the next object.
+//
+// `hit` must be preset (objectId = RTB_INVALID_OBJECT, distance = +inf).  The top-level box tests use
+// ray.originDivDir exactly as stored: the integrator offsets ray.origin AFTER constructing the ray without
+// refreshing originDivDir (PathTracerMIS.cpp:392-393) and that stale value is part of the reference's behaviour;
+// Traverse_Object rebuilds the ray in object space.
 template <bool kCount>
-RTB_HD void scene_traverse(const SceneView& S, const Ray& ray, Hit& hit, TraceCounters* cnt)
+RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, TraceCounters* cnt)
 {
     if (S.numObjects == 0) return;
-    uint32_t stack[RTB_STACK_SIZE];
-    if (S.numObjects == 1)
-    {
-        traverse_object<kCount>(S, ray, 0, hit, stack, cnt);
-        return;
-    }
-    if (S.numTlasNodes == 0) return;
-    // GenericTraverse<Scene>: the object-level stack lives in the lower part, mesh traversal uses the part above it
+    StackEntry stack[RTB_STACK_SIZE];
     uint32_t stackSize = 0;
-    DNode node = load_node(S.tlas, 0);
+    uint32_t blasBase = 0;
+    bool inBlas = false;
+    const DNode* nodes = S.tlas;
+    const DTri* tris = nullptr;
+    Ray ray = worldRay;
+    const bool worldFinite = ray_is_finite(worldRay);
+    bool finite = worldFinite;
+    uint32_t objectID = 0;
+    bool have = false;                 // {curChild, curInfo} describe a node still to be visited
+    uint32_t curChild = 0, curInfo = 0;
+
+    if (S.numObjects == 1) { stack[0].a = 0u; stack[0].b = RTB_ENTRY_OBJECT; stackSize = 1; }      // BVH bypass, Scene.cpp:231-235
+    else if (S.numTlasNodes != 0) { node_header(S.tlas, 0, curChild, curInfo); have = true; }
+
     for (;;)
     {
-        const uint32_t numLeaves = RTB_NUM_LEAVES(node.leafInfo);
-        if (numLeaves != 0)
+        // inner nodes: GenericTraverse, Traversal_Single.h:36-91
+        while (have && RTB_NUM_LEAVES(curInfo) == 0)
         {
-            for (uint32_t i = 0; i < numLeaves; ++i)
-            {
-                traverse_object<kCount>(S, ray, node.childIndex + i, hit, stack + stackSize, cnt);
-            }
-        }
-        else
-        {
-            const uint32_t childA = node.childIndex;
-            const DNode a = load_node(S.tlas, childA);
-            const DNode b = load_node(S.tlas, childA + 1);
+            const DNode a = load_node(nodes, curChild);
+            const DNode b = load_node(nodes, curChild + 1);
             float distanceA, distanceB;
-            bool hitA = box_ray(ray, a.minx, a.miny, a.minz, a.maxx, a.maxy, a.maxz, distanceA);
-            bool hitB = box_ray(ray, b.minx, b.miny, b.minz, b.maxx, b.maxy, b.maxz, distanceB);
+            bool hitA, hitB;
+            if (finite)
+            {
+                hitA = box_ray_finite(ray, a.minx, a.miny, a.minz, a.maxx, a.maxy, a.maxz, distanceA);
+                hitB = box_ray_finite(ray, b.minx, b.miny, b.minz, b.maxx, b.maxy, b.maxz, distanceB);
+            }
+            else
+            {
+                hitA = box_ray(ray, a.minx, a.miny, a.minz, a.maxx, a.maxy, a.maxz, distanceA);
+                hitB = box_ray(ray, b.minx, b.miny, b.minz, b.maxx, b.maxy, b.maxz, distanceB);
+            }
             hitA &= (distanceA < hit.distance);
             hitB &= (distanceB < hit.distance);
             if (kCount) cnt->boxTests += 2;
             if (hitA && hitB)
             {
-                if (distanceB < distanceA) { node = b; stack[stackSize++] = childA; }
-                else                       { node = a; stack[stackSize++] = childA + 1; }
-                continue;
+                // visit the nearer child first, push the other (Traversal_Single.h:65-75)
+                const bool bFirst = distanceB < distanceA;
+                StackEntry e;
+                e.a = bFirst ? a.childIndex : b.childIndex;
+                e.b = bFirst ? a.leafInfo : b.leafInfo;
+                stack[stackSize++] = e;
+                curChild = bFirst ? b.childIndex : a.childIndex;
+                curInfo = bFirst ? b.leafInfo : a.leafInfo;
             }
-            if (hitA) { node = a; continue; }
-            if (hitB) { node = b; continue; }
+            else if (hitA) { curChild = a.childIndex; curInfo = a.leafInfo; }
+            else if (hitB) { curChild = b.childIndex; curInfo = b.leafInfo; }
+            else have = false;
+        }
+
+        if (have)
+        {
+            const uint32_t numLeaves = RTB_NUM_LEAVES(curInfo);
+            if (inBlas)
+            {
+                // MeshShape::Traverse_Leaf, MeshShape.cpp:134-168
+                if (kCount) cnt->triTests += numLeaves;
+                for (uint32_t i = 0; i < numLeaves; ++i)
+                {
+                    const uint32_t triangleIndex = curChild + i;
+                    V3 v0, e1, e2;
+                    load_tri(tris, triangleIndex, v0, e1, e2);
+                    float u, v, distance;
+                    if (triangle_ray(ray, v0, e1, e2, u, v, distance))
+                    {
+                        if (distance < hit.distance)
+                        {
+                            hit.distance = distance;
+                            hit.subObjectId = triangleIndex;
+                            hit.objectId = objectID;
+                            hit.u = u;
+                            hit.v = v;
+                        }
+                    }
+                }
+            }
+            else
+            {
+                // Scene::Traverse_Leaf, Scene.cpp:167-178: objects in order -> push in reverse
+                for (uint32_t i = numLeaves; i-- > 0;) { stack[stackSize].a = curChild + i; stack[stackSize].b = RTB_ENTRY_OBJECT; stackSize++; }
+            }
+            have = false;
+        }
+
+        // pop
+        if (inBlas && stackSize == blasBase)
+        {
+            // mesh finished: back to the top level with the world-space ray
+            inBlas = false; nodes = S.tlas; ray = worldRay; finite = worldFinite;
         }
         if (stackSize == 0) break;
-        node = load_node(S.tlas, stack[--stackSize]);
-    }
-}
-
-// Scene::Traverse_Shadow, Scene.cpp:245-261
-template <bool kCount>
-RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& ray, float maxDistance, TraceCounters* cnt)
-{
-    if (S.numObjects == 0) return false;
-    uint32_t stack[RTB_STACK_SIZE];
-    if (S.numObjects == 1) return traverse_object_shadow<kCount>(S, ray, 0, maxDistance, stack, cnt);
-    if (S.numTlasNodes == 0) return false;
-    uint32_t stackSize = 0;
-    DNode node = load_node(S.tlas, 0);
-    for (;;)
-    {
-        const uint32_t numLeaves = RTB_NUM_LEAVES(node.leafInfo);
-        if (numLeaves != 0)
+        const StackEntry e = stack[--stackSize];
+        if (e.b == RTB_ENTRY_OBJECT)
         {
-            for (uint32_t i = 0; i < numLeaves; ++i)
+            // Scene::Traverse_Object, Scene.cpp:128-145
+            objectID = e.a;
+            const DObjectTrace& obj = S.objTrace[objectID];
+            const Ray localRay = transform_ray_unsafe(obj.invTransform, worldRay);
+            if (obj.kind == RTB_OBJECT_SHAPE && obj.shapeType == RTB_SHAPE_MESH)
             {
-                if (traverse_object_shadow<kCount>(S, ray, node.childIndex + i, maxDistance, stack + stackSize, cnt)) return true;
+                const DMesh& mesh = S.meshes[obj.meshIndex];
+                if (mesh.numNodes != 0)
+                {
+                    inBlas = true; blasBase = stackSize; nodes = mesh.nodes; tris = mesh.tris; ray = localRay; finite = ray_is_finite(localRay);
+                    node_header(nodes, 0, curChild, curInfo);
+                    have = true;
+                }
+            }
+            else
+            {
+                analytic_closest(obj, localRay, objectID, hit);
             }
         }
         else
         {
-            const uint32_t childA = node.childIndex;
-            const DNode a = load_node(S.tlas, childA);
-            const DNode b = load_node(S.tlas, childA + 1);
+            curChild = e.a; curInfo = e.b; have = true;
+        }
+    }
+}
+
+// Scene::Traverse_Shadow (Scene.cpp:245-261), same flattening.  The result is a boolean "any triangle / shape closer
+// than maxDistance among the leaves whose ancestors pass the box test", which does not depend on the visiting order;
+// the reference's A-then-B order (Traversal_Single.h:151-156) is kept anyway.
+template <bool kCount>
+RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float maxDistance, TraceCounters* cnt)
+{
+    if (S.numObjects == 0) return false;
+    StackEntry stack[RTB_STACK_SIZE];
+    uint32_t stackSize = 0;
+    uint32_t blasBase = 0;
+    bool inBlas = false;
+    const DNode* nodes = S.tlas;
+    const DTri* tris = nullptr;
+    Ray ray = worldRay;
+    const bool worldFinite = ray_is_finite(worldRay);
+    bool finite = worldFinite;
+    bool have = false;
+    uint32_t curChild = 0, curInfo = 0;
+
+    if (S.numObjects == 1) { stack[0].a = 0u; stack[0].b = RTB_ENTRY_OBJECT; stackSize = 1; }
+    else if (S.numTlasNodes != 0) { node_header(S.tlas, 0, curChild, curInfo); have = true; }
+
+    for (;;)
+    {
+        while (have && RTB_NUM_LEAVES(curInfo) == 0)
+        {
+            const DNode a = load_node(nodes, curChild);
+            const DNode b = load_node(nodes, curChild + 1);
             float distanceA, distanceB;
-            bool hitA = box_ray(ray, a.minx, a.miny, a.minz, a.maxx, a.maxy, a.maxz, distanceA);
-            bool hitB = box_ray(ray, b.minx, b.miny, b.minz, b.maxx, b.maxy, b.maxz, distanceB);
+            bool hitA, hitB;
+            if (finite)
+            {
+                hitA = box_ray_finite(ray, a.minx, a.miny, a.minz, a.maxx, a.maxy, a.maxz, distanceA);
+                hitB = box_ray_finite(ray, b.minx, b.miny, b.minz, b.maxx, b.maxy, b.maxz, distanceB);
+            }
+            else
+            {
+                hitA = box_ray(ray, a.minx, a.miny, a.minz, a.maxx, a.maxy, a.maxz, distanceA);
+                hitB = box_ray(ray, b.minx, b.miny, b.minz, b.maxx, b.maxy, b.maxz, distanceB);
+            }
             hitA &= (distanceA < maxDistance);
             hitB &= (distanceB < maxDistance);
             if (kCount) cnt->boxTests += 2;
-            if (hitA && hitB) { node = a; stack[stackSize++] = childA + 1; continue; }
-            if (hitA) { node = a; continue; }
-            if (hitB) { node = b; continue; }
+            if (hitA && hitB)
+            {
+                StackEntry e; e.a = b.childIndex; e.b = b.leafInfo;
+                stack[stackSize++] = e;
+                curChild = a.childIndex; curInfo = a.leafInfo;
+            }
+            else if (hitA) { curChild = a.childIndex; curInfo = a.leafInfo; }
+            else if (hitB) { curChild = b.childIndex; curInfo = b.leafInfo; }
+            else have = false;
+        }
+
+        if (have)
+        {
+            const uint32_t numLeaves = RTB_NUM_LEAVES(curInfo);
+            if (inBlas)
+            {
+                // MeshShape::Traverse_Leaf_Shadow, MeshShape.cpp:175-207
+                if (kCount) cnt->triTests += numLeaves;
+                bool occluded = false;
+                for (uint32_t i = 0; i < numLeaves; ++i)
+                {
+                    V3 v0, e1, e2;
+                    load_tri(tris, curChild + i, v0, e1, e2);
+                    float u, v, distance;
+                    if (triangle_ray(ray, v0, e1, e2, u, v, distance) && distance < maxDistance) occluded = true;
+                }
+                if (occluded) return true;
+            }
+            else
+            {
+                for (uint32_t i = numLeaves; i-- > 0;) { stack[stackSize].a = curChild + i; stack[stackSize].b = RTB_ENTRY_OBJECT; stackSize++; }
+            }
+            have = false;
+        }
+
+        if (inBlas && stackSize == blasBase)
+        {
+            inBlas = false; nodes = S.tlas; ray = worldRay; finite = worldFinite;
         }
         if (stackSize == 0) break;
-        node = load_node(S.tlas, stack[--stackSize]);
+        const StackEntry e = stack[--stackSize];
+        if (e.b == RTB_ENTRY_OBJECT)
+        {
+            // Scene::Traverse_Object_Shadow, Scene.cpp:147-165
+            const DObjectTrace& obj = S.objTrace[e.a];
+            const Ray localRay = transform_ray_unsafe(obj.invTransform, worldRay);
+            if (obj.kind == RTB_OBJECT_SHAPE && obj.shapeType == RTB_SHAPE_MESH)
+            {
+                const DMesh& mesh = S.meshes[obj.meshIndex];
+                if (mesh.numNodes != 0)
+                {
+                    inBlas = true; blasBase = stackSize; nodes = mesh.nodes; tris = mesh.tris; ray = localRay; finite = ray_is_finite(localRay);
+                    node_header(nodes, 0, curChild, curInfo);
+                    have = true;
+                }
+            }
+            else if (analytic_shadow(obj, localRay, maxDistance))
+            {
+                return true;
+            }
+        }
+        else
+        {
+            curChild = e.a; curInfo = e.b; have = true;
+        }
     }
     return false;
 }
