@@ -1,0 +1,109 @@
+// rt_capi.cpp — C entry points of the host object model (librtb200_host.so) for Python tests / bench.py and other FFI
+// users.  Thin: every function forwards to the C++ classes in rt_scene.h / rt_loader.h / rt_viewport.h, which in turn
+// call the extern "C" rtb_* boundary of librtb200.so.
+#include <cstring>
+#include <string>
+
+#include "rt_loader.h"
+#include "rt_viewport.h"
+
+namespace {
+
+struct SceneHandle
+{
+    rt::Scene scene;
+    rt::Camera camera;
+};
+
+void SetErr(char* buf, size_t len, const std::string& msg)
+{
+    if (!buf || len == 0) return;
+    strncpy(buf, msg.c_str(), len - 1);
+    buf[len - 1] = 0;
+}
+
+} // namespace
+
+extern "C" {
+
+// helpers::LoadScene + Scene::BuildBVH (Demo/Demo.cpp:156-198 SwitchScene)
+void* rtbh_scene_load(const char* jsonPath, const char* dataPath, char* err, size_t errLen)
+{
+    SceneHandle* h = new SceneHandle();
+    std::string msg;
+    if (!rt::helpers::LoadScene(jsonPath, dataPath ? dataPath : "", h->scene, h->camera, msg)) { SetErr(err, errLen, msg); delete h; return nullptr; }
+    if (!h->scene.BuildBVH()) { SetErr(err, errLen, "Scene::BuildBVH failed"); delete h; return nullptr; }
+    return h;
+}
+
+void rtbh_scene_free(void* scene) { delete static_cast<SceneHandle*>(scene); }
+
+// flat RTBS file of the scene + camera at the given aspect (what rtb_upload_scene receives)
+int rtbh_scene_save_flat(void* scene, const char* path, uint32_t width, uint32_t height)
+{
+    SceneHandle* h = static_cast<SceneHandle*>(scene);
+    rtb::SceneFile flat;
+    h->scene.Flatten(flat);
+    rt::Camera cam = h->camera;
+    cam.SetPerspective((float)width / (float)height, cam.mFieldOfView);
+    cam.Describe(flat.camera);
+    flat.fieldOfView = cam.mFieldOfView;
+    return flat.Save(path) ? 0 : -1;
+}
+
+void rtbh_scene_stats(void* scene, uint32_t* numObjects, uint32_t* numLights, uint32_t* numTlasNodes)
+{
+    SceneHandle* h = static_cast<SceneHandle*>(scene);
+    if (numObjects) *numObjects = (uint32_t)h->scene.GetNumTraceableObjects();
+    if (numLights) *numLights = (uint32_t)h->scene.GetLights().size();
+    if (numTlasNodes) *numTlasNodes = h->scene.GetBVH().GetNumNodes();
+}
+
+void* rtbh_viewport_create(void* scene, int deviceId, uint32_t numShards, uint32_t shardIndex, uint32_t flags, const char* blueNoisePath, char* err, size_t errLen)
+{
+    rt::ViewportB200* vp = new rt::ViewportB200();
+    if (!vp->Create(deviceId, numShards, shardIndex, flags, blueNoisePath ? blueNoisePath : "")) { SetErr(err, errLen, vp->GetLastError()); delete vp; return nullptr; }
+    if (scene && !vp->SetScene(static_cast<SceneHandle*>(scene)->scene)) { SetErr(err, errLen, vp->GetLastError()); delete vp; return nullptr; }
+    return vp;
+}
+
+void rtbh_viewport_free(void* vp) { delete static_cast<rt::ViewportB200*>(vp); }
+const char* rtbh_viewport_last_error(void* vp) { return static_cast<rt::ViewportB200*>(vp)->GetLastError().c_str(); }
+void* rtbh_viewport_context(void* vp) { return static_cast<rt::ViewportB200*>(vp)->GetContext(); }
+
+int rtbh_viewport_set_renderer(void* vp, const char* name, uint32_t debugMode)
+{
+    rt::ViewportB200* v = static_cast<rt::ViewportB200*>(vp);
+    v->SetDebugMode(debugMode);
+    return v->SetRenderer(name) ? 0 : -1;
+}
+
+int rtbh_viewport_set_params(void* vp, uint32_t dimensions, uint32_t useBlueNoise, float aaSpread, uint32_t maxRayDepth, uint32_t minRRDepth, uint32_t strategy, uint64_t seed)
+{
+    rt::ViewportB200* v = static_cast<rt::ViewportB200*>(vp);
+    rt::RenderingParams p;
+    p.dimensions = dimensions; p.useBlueNoiseDithering = useBlueNoise != 0; p.antiAliasingSpread = aaSpread;
+    p.maxRayDepth = maxRayDepth; p.minRussianRouletteDepth = minRRDepth; p.lightSamplingStrategy = strategy;
+    v->SetRenderingParams(p);
+    v->SetSeed(seed);
+    return 0;
+}
+
+int rtbh_viewport_resize(void* vp, uint32_t w, uint32_t h) { return static_cast<rt::ViewportB200*>(vp)->Resize(w, h) ? 0 : -1; }
+void rtbh_viewport_reset(void* vp) { static_cast<rt::ViewportB200*>(vp)->Reset(); }
+
+// Viewport::Render x numPasses with the scene's camera at the viewport's aspect ratio
+int rtbh_viewport_render(void* vp, void* scene, uint32_t numPasses)
+{
+    rt::ViewportB200* v = static_cast<rt::ViewportB200*>(vp);
+    rt::Camera cam = static_cast<SceneHandle*>(scene)->camera;
+    cam.SetPerspective((float)v->GetWidth() / (float)v->GetHeight(), cam.mFieldOfView);
+    for (uint32_t i = 0; i < numPasses; ++i) if (!v->Render(cam)) return -1;
+    return 0;
+}
+
+int rtbh_viewport_synchronize(void* vp) { return static_cast<rt::ViewportB200*>(vp)->Synchronize() ? 0 : -1; }
+int rtbh_viewport_read_sum(void* vp, float* rgb, int which) { return static_cast<rt::ViewportB200*>(vp)->GetSumBuffer(rgb, which) ? 0 : -1; }
+int rtbh_viewport_counters(void* vp, RtbCounters* out) { return static_cast<rt::ViewportB200*>(vp)->GetCounters(*out) ? 0 : -1; }
+
+} // extern "C"

@@ -1,0 +1,321 @@
+// rt_viewport.h — ViewportB200: the reference's Viewport public interface (Core/Rendering/Viewport.h:37-58) re-hosted
+// on the CUDA path.  Render() reproduces the host prologue of Viewport::Render in the same order (Halton NextSample ->
+// per-pass seed vector, Viewport.cpp:200-205; Gaussian AA offset, 235-242) and then enqueues one rtb_render_pass.
+//
+//   HaltonSequence   Core/Sampling/HaltonSampler.cpp:84-206 (scrambled Halton, double precision, host only)
+//   Random           Core/Math/Random.cpp:33-67 (xoroshiro128+); seeded from a splitmix64 stream of a user seed
+//                    instead of /dev/urandom so that renders are reproducible
+//   GetFloatNormal2  Core/Math/SamplingHelpers.cpp:145-149 (Box-Muller with FastLog + polynomial sin)
+#pragma once
+
+#include <cmath>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "rt_scene.h"
+#include "../csrc/rtb_math.h"
+
+namespace rt {
+
+class Random
+{
+public:
+    explicit Random(uint64_t seed = 0x853c49e6748fea9bULL) { Reset(seed); }
+    void Reset(uint64_t seed)
+    {
+        mState = seed;
+        mSeed[0] = Next(); mSeed[1] = Next();
+        if (mSeed[0] == 0 && mSeed[1] == 0) mSeed[0] = 1;
+    }
+    // xoroshiro128+, Random.cpp:33-47
+    uint64_t GetLong()
+    {
+        const uint64_t s0 = mSeed[0];
+        uint64_t s1 = mSeed[1];
+        const uint64_t result = s0 + s1;
+        s1 ^= s0;
+        mSeed[0] = ((s0 << 24) | (s0 >> 40)) ^ s1 ^ (s1 << 16);
+        mSeed[1] = (s1 << 37) | (s1 >> 27);
+        return result;
+    }
+    uint32_t GetInt() { return static_cast<uint32_t>(GetLong()); }
+    // Random.cpp:54-59
+    float GetFloat() { union { uint32_t u; float f; } r; r.u = (GetInt() & 0x007fffffu) | 0x3f800000u; return r.f - 1.0f; }
+    double GetDouble() { return static_cast<double>(GetLong()) / static_cast<double>(UINT64_MAX); }
+private:
+    uint64_t Next()   // splitmix64
+    {
+        mState += 0x9E3779B97F4A7C15ULL;
+        uint64_t z = mState;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+    }
+    uint64_t mState = 0;
+    uint64_t mSeed[2];
+};
+
+// scrambled Halton sequence with random start (HaltonSampler.cpp): digit expansion per dimension in base p_d, digits
+// permuted by a per-dimension random permutation, radical inverse accumulated in double precision
+class HaltonSequence
+{
+public:
+    static constexpr uint32_t Width = 64;
+
+    void Initialize(uint32_t dims, Random& rng)
+    {
+        mDims = dims;
+        mBase.assign(dims, 0); mStarts.assign(dims, 0);
+        mRnd.assign(dims, std::vector<double>(Width + 1, 0.0));
+        mDigit.assign(dims, std::vector<uint64_t>(Width + 1, 0));
+        mPower.assign(dims, std::vector<uint64_t>(Width, 0));
+        mPerm.assign(dims, std::vector<uint64_t>());
+        if (dims == 0) return;
+        // InitPrimes
+        uint32_t prime = 1, m = 0;
+        while (m < dims)
+        {
+            prime++;
+            bool isPrime = true;
+            for (uint64_t i = 2; i <= (uint64_t)std::sqrt((double)prime); i++) if (prime % i == 0) { isPrime = false; break; }
+            if (isPrime) mBase[m++] = prime;
+        }
+        // InitStart: random starting index, built digit by digit from a uniform double
+        for (uint32_t i = 0; i < dims; i++)
+        {
+            double r = rng.GetDouble();
+            const uint64_t base = mBase[i];
+            uint64_t z = 0, b = base;
+            while (r > 1.0e-16)
+            {
+                if (r >= 1.0 / b)
+                {
+                    const uint64_t cnt = (uint64_t)std::floor(r * b);
+                    r = r - cnt * 1.0 / b;
+                    z += cnt * b / base;
+                }
+                b *= base;
+            }
+            mStarts[i] = z;
+        }
+        // InitPowerBuffer
+        for (uint32_t d = 0; d < dims; d++)
+            for (uint32_t j = 0; j < Width; j++) mPower[d][j] = j == 0 ? mBase[d] : mPower[d][j - 1] * mBase[d];
+        // InitPermutation: random transposition shuffle that keeps digit 0 fixed unless swapped explicitly
+        for (uint32_t i = 0; i < dims; i++)
+        {
+            mPerm[i].resize(mBase[i]);
+            for (uint64_t j = 0; j < mBase[i]; j++) mPerm[i][j] = j;
+            for (uint64_t j = 1; j < mBase[i]; j++)
+            {
+                const uint64_t tmp = (uint64_t)std::floor(rng.GetDouble() * mBase[i]);
+                if (tmp != 0 && tmp < mBase[i]) std::swap(mPerm[i][j], mPerm[i][tmp]);
+            }
+        }
+        // InitExpansion
+        for (uint32_t i = 0; i < dims; i++)
+        {
+            uint64_t n = mStarts[i] - 1;
+            int j = 0;
+            while (n > 0 && j < (int)Width) { mDigit[i][j] = n % mBase[i]; n = n / mBase[i]; j++; }
+            j--;
+            while (j >= 0)
+            {
+                const uint64_t d = mPerm[i][mDigit[i][j]];
+                mRnd[i][j] = mRnd[i][j + 1] + d * 1.0 / mPower[i][j];
+                j--;
+            }
+        }
+    }
+
+    uint32_t GetNumDimensions() const { return mDims; }
+
+    void NextSample()
+    {
+        for (uint32_t i = 0; i < mDims; i++)
+        {
+            int j = 0;
+            while (mDigit[i][j] + 1 >= mBase[i] && j + 1 < (int)Width) j++;
+            mDigit[i][j]++;
+            uint64_t d = mPerm[i][mDigit[i][j]];
+            mRnd[i][j] = mRnd[i][j + 1] + d * 1.0 / mPower[i][j];
+            for (j = j - 1; j >= 0; j--)
+            {
+                mDigit[i][j] = 0;
+                d = mPerm[i][0];
+                mRnd[i][j] = mRnd[i][j + 1] + d * 1.0 / mPower[i][j];
+            }
+        }
+    }
+
+    // HaltonSampler.h:26
+    uint32_t GetInt(uint32_t dimension) const { return uint32_t(mRnd[dimension][0] * (double)UINT32_MAX); }
+
+private:
+    uint32_t mDims = 0;
+    std::vector<uint64_t> mStarts;
+    std::vector<uint32_t> mBase;
+    std::vector<std::vector<double>> mRnd;
+    std::vector<std::vector<uint64_t>> mDigit, mPower, mPerm;
+};
+
+// FastLog, Transcendental.cpp:196-227 (scalar)
+inline float FastLog(float x)
+{
+    union { float f; int32_t i; } a, m;
+    a.f = x;
+    const int32_t e = (a.i - 0x3f2aaaab) & 0xff800000;
+    m.i = a.i - e;
+    const float i = 1.19209290e-7f * (float)e;
+    const float f = m.f - 1.0f;
+    const float s = f * f;
+    float r = 0.230836749f * f - 0.279208571f;
+    const float t = 0.331826031f * f - 0.498910338f;
+    r = r * s + t;
+    r = r * s + f;
+    r = i * 0.693147182f + r;
+    return r;
+}
+
+// LightSamplingStrategy / SamplingParams / RenderingParams subset, Context.h:28-90
+struct RenderingParams
+{
+    uint32_t dimensions = 64;
+    bool useBlueNoiseDithering = true;
+    float antiAliasingSpread = 0.5f;
+    uint32_t maxRayDepth = 20;
+    uint32_t minRussianRouletteDepth = 1;
+    uint32_t lightSamplingStrategy = RTB_LIGHT_SAMPLING_SINGLE;
+};
+
+class ViewportB200
+{
+public:
+    ViewportB200() = default;
+    ~ViewportB200() { if (mCtx) rtb_destroy(mCtx); }
+    ViewportB200(const ViewportB200&) = delete;
+    ViewportB200& operator=(const ViewportB200&) = delete;
+
+    const std::string& GetLastError() const { return mError; }
+    RtbContext* GetContext() const { return mCtx; }
+
+    bool Create(int deviceId, uint32_t numShards, uint32_t shardIndex, uint32_t flags, const std::string& blueNoisePath)
+    {
+        RtbCreateDesc d;
+        memset(&d, 0, sizeof(d));
+        d.deviceId = deviceId; d.numShards = numShards; d.shardIndex = shardIndex; d.flags = flags;
+        if (rtb_create(&d, &mCtx) != RTB_OK) return Error();
+        if (!blueNoisePath.empty())
+        {
+            std::vector<uint16_t> bn;
+            if (!LoadBlueNoise(blueNoisePath, bn)) { mError = "Failed to load blue noise texture: " + blueNoisePath; return false; }
+            if (rtb_set_blue_noise(mCtx, bn.data()) != RTB_OK) return Error();
+        }
+        return true;
+    }
+
+    // the scene must outlive nothing here: it is flattened and copied to the device (CreateRenderer + SetRenderer)
+    bool SetScene(const Scene& scene)
+    {
+        rtb::SceneFile flat;
+        scene.Flatten(flat);
+        const RtbSceneDesc d = flat.View();
+        if (rtb_upload_scene(mCtx, &d) != RTB_OK) return Error();
+        mHasScene = true;
+        return true;
+    }
+
+    // CreateRenderer names, Renderer.cpp:45-69
+    bool SetRenderer(const std::string& name)
+    {
+        if (name == "Path Tracer") mRenderer = RTB_RENDERER_PATH_TRACER;
+        else if (name == "Path Tracer MIS") mRenderer = RTB_RENDERER_PATH_TRACER_MIS;
+        else if (name == "Debug") mRenderer = RTB_RENDERER_DEBUG;
+        else { mError = "Unknown renderer name: '" + name + "' (supported: 'Path Tracer', 'Path Tracer MIS', 'Debug')"; return false; }
+        return true;
+    }
+    void SetDebugMode(uint32_t mode) { mDebugMode = mode; }
+
+    bool Resize(uint32_t width, uint32_t height)
+    {
+        if (rtb_resize(mCtx, width, height) != RTB_OK) return Error();
+        mWidth = width; mHeight = height;
+        Reset();
+        return true;
+    }
+
+    bool SetRenderingParams(const RenderingParams& p) { mParams = p; return true; }
+    void SetSeed(uint64_t seed) { mSeedValue = seed; }
+
+    // Viewport::Reset, Viewport.cpp:117-138
+    void Reset()
+    {
+        mRandom.Reset(mSeedValue);
+        mHalton.Initialize(mParams.dimensions, mRandom);
+        mPassesFinished = 0;
+        if (mCtx) rtb_reset(mCtx);
+    }
+
+    // Viewport::Render, Viewport.cpp:185-289 (asynchronous: call Synchronize / GetSumBuffer to wait)
+    bool Render(const Camera& camera)
+    {
+        if (mWidth == 0 || mHeight == 0) return false;
+        if (!mHasScene) { mError = "Viewport: Missing renderer"; return false; }
+        mHalton.NextSample();
+        std::vector<uint32_t> seed(mHalton.GetNumDimensions());
+        for (uint32_t i = 0; i < seed.size(); ++i) seed[i] = mHalton.GetInt(i);
+        // GetFloatNormal2(rng.GetFloat2()) * antiAliasingSpread
+        const float u0 = mRandom.GetFloat(), u1 = mRandom.GetFloat();
+        float s, c;
+        rtb::sin_cos(2.0f * RTB_PI * u1, s, c);
+        const float radius = sqrtf(-2.0f * FastLog(u0));
+        RtbPassDesc pass;
+        memset(&pass, 0, sizeof(pass));
+        pass.renderer = mRenderer; pass.debugMode = mDebugMode;
+        camera.Describe(pass.camera);
+        pass.maxRayDepth = mParams.maxRayDepth; pass.minRussianRouletteDepth = mParams.minRussianRouletteDepth;
+        pass.lightSamplingStrategy = mParams.lightSamplingStrategy; pass.useBlueNoise = mParams.useBlueNoiseDithering;
+        pass.passIndex = mPassesFinished; pass.numSeedDims = (uint32_t)seed.size(); pass.seed = seed.data();
+        pass.sampleOffset[0] = radius * s * mParams.antiAliasingSpread;
+        pass.sampleOffset[1] = radius * c * mParams.antiAliasingSpread;
+        if (rtb_render_pass(mCtx, &pass) != RTB_OK) return Error();
+        mPassesFinished++;
+        return true;
+    }
+
+    bool Synchronize() { return rtb_synchronize(mCtx) == RTB_OK || Error(); }
+    bool GetSumBuffer(float* rgb, int which = 0) { return rtb_read_sum(mCtx, rgb, which) == RTB_OK || Error(); }
+    bool GetCounters(RtbCounters& c) { return rtb_get_counters(mCtx, &c) == RTB_OK || Error(); }
+    uint32_t GetWidth() const { return mWidth; }
+    uint32_t GetHeight() const { return mHeight; }
+    uint32_t GetPassesFinished() const { return mPassesFinished; }
+
+    static bool LoadBlueNoise(const std::string& path, std::vector<uint16_t>& interleaved)
+    {
+        FILE* f = fopen(path.c_str(), "rb");
+        if (!f) return false;
+        std::vector<uint16_t> raw(4 + 4 * 128 * 128);
+        const bool ok = fread(raw.data(), 2, raw.size(), f) == raw.size() && raw[0] == 0x5442 && raw[1] == 0x4E52;
+        fclose(f);
+        if (!ok) return false;
+        interleaved.resize(128 * 128 * 4);
+        for (int l = 0; l < 4; ++l) for (int p = 0; p < 128 * 128; ++p) interleaved[p * 4 + l] = raw[4 + l * 128 * 128 + p];
+        return true;
+    }
+
+private:
+    bool Error() { mError = rtb_last_error(); return false; }
+
+    RtbContext* mCtx = nullptr;
+    bool mHasScene = false;
+    uint32_t mRenderer = RTB_RENDERER_PATH_TRACER_MIS, mDebugMode = RTB_DEBUG_TRIANGLE_ID;
+    uint32_t mWidth = 0, mHeight = 0, mPassesFinished = 0;
+    RenderingParams mParams;
+    uint64_t mSeedValue = 12345;
+    Random mRandom;
+    HaltonSequence mHalton;
+    std::string mError;
+};
+
+} // namespace rt

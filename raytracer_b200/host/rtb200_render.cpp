@@ -1,0 +1,78 @@
+// rtb200_render — headless command line renderer over the host object model (the reference ships an interactive
+// viewer, Demo/Main.cpp:6-46; its flags are mirrored where they make sense: -w -h -s --renderer --data).
+//
+//   rtb200_render -s scene.json --data DIR -w 1920 -h 1080 --spp 64 --renderer "Path Tracer MIS" --depth 8
+//                 --dims 128 --strategy all --seed 12345 --device 0 --out sum.f32 [--flat scene.rtb]
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "rt_loader.h"
+#include "rt_viewport.h"
+
+int main(int argc, char** argv)
+{
+    std::map<std::string, std::string> a;
+    for (int i = 1; i < argc; ++i)
+    {
+        std::string k = argv[i];
+        if (k[0] == '-' && i + 1 < argc) { a[k] = argv[++i]; }
+    }
+    auto get = [&](const char* k, const char* d) { auto it = a.find(k); return it == a.end() ? std::string(d) : it->second; };
+    const std::string scenePath = get("-s", get("--scene", "").c_str());
+    if (scenePath.empty())
+    {
+        fprintf(stderr, "usage: rtb200_render -s scene.json [--data DIR] [-w W] [-h H] [--spp N] [--renderer NAME] [--depth D] [--dims K]\n"
+                        "                     [--strategy all|single] [--seed S] [--device I] [--bluenoise FILE] [--out sum.f32] [--flat scene.rtb]\n");
+        return 2;
+    }
+    const uint32_t w = atoi(get("-w", "1280").c_str()), h = atoi(get("-h", "720").c_str()), spp = atoi(get("--spp", "16").c_str());
+    rt::Scene scene; rt::Camera camera;
+    std::string err;
+    if (!rt::helpers::LoadScene(scenePath, get("--data", ""), scene, camera, err)) { fprintf(stderr, "[ERROR] %s\n", err.c_str()); return 1; }
+    if (!scene.BuildBVH()) { fprintf(stderr, "[ERROR] BuildBVH failed\n"); return 1; }
+    camera.SetPerspective((float)w / (float)h, camera.mFieldOfView);
+    if (a.count("--flat"))
+    {
+        rtb::SceneFile flat;
+        scene.Flatten(flat);
+        camera.Describe(flat.camera);
+        flat.fieldOfView = camera.mFieldOfView;
+        if (!flat.Save(a["--flat"])) { fprintf(stderr, "[ERROR] cannot write %s\n", a["--flat"].c_str()); return 1; }
+        if (spp == 0) return 0;
+    }
+    rt::ViewportB200 vp;
+    if (!vp.Create(atoi(get("--device", "0").c_str()), 1, 0, 0, get("--bluenoise", ""))) { fprintf(stderr, "[ERROR] %s\n", vp.GetLastError().c_str()); return 1; }
+    if (!vp.SetScene(scene)) { fprintf(stderr, "[ERROR] %s\n", vp.GetLastError().c_str()); return 1; }
+    rt::RenderingParams p;
+    p.maxRayDepth = atoi(get("--depth", "8").c_str());
+    p.dimensions = atoi(get("--dims", "128").c_str());
+    p.lightSamplingStrategy = get("--strategy", "all") == "single" ? RTB_LIGHT_SAMPLING_SINGLE : RTB_LIGHT_SAMPLING_ALL;
+    vp.SetRenderingParams(p);
+    vp.SetSeed(strtoull(get("--seed", "12345").c_str(), nullptr, 10));
+    if (!vp.SetRenderer(get("--renderer", "Path Tracer MIS"))) { fprintf(stderr, "[ERROR] %s\n", vp.GetLastError().c_str()); return 1; }
+    if (!vp.Resize(w, h)) { fprintf(stderr, "[ERROR] %s\n", vp.GetLastError().c_str()); return 1; }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t i = 0; i < spp; ++i) if (!vp.Render(camera)) { fprintf(stderr, "[ERROR] %s\n", vp.GetLastError().c_str()); return 1; }
+    vp.Synchronize();
+    const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    RtbCounters c;
+    vp.GetCounters(c);
+    printf("{\"width\": %u, \"height\": %u, \"passes\": %u, \"seconds\": %.6f, \"numPrimaryRays\": %llu, \"numRays\": %llu, \"numShadowRays\": %llu, "
+           "\"numShadowRaysHit\": %llu, \"mrays_per_s\": %.3f, \"msamples_per_s\": %.3f}\n", w, h, spp, s,
+           (unsigned long long)c.numPrimaryRays, (unsigned long long)c.numRays, (unsigned long long)c.numShadowRays, (unsigned long long)c.numShadowRaysHit,
+           (c.numRays + c.numShadowRays) / s * 1e-6, c.numPrimaryRays / s * 1e-6);
+    if (a.count("--out"))
+    {
+        std::vector<float> img((size_t)w * h * 3);
+        if (!vp.GetSumBuffer(img.data())) { fprintf(stderr, "[ERROR] %s\n", vp.GetLastError().c_str()); return 1; }
+        FILE* f = fopen(a["--out"].c_str(), "wb");
+        fwrite(img.data(), 4, img.size(), f);
+        fclose(f);
+    }
+    return 0;
+}
