@@ -226,8 +226,10 @@ typedef struct RtbCounters
     uint64_t numShadowRays;
     uint64_t numShadowRaysHit;
     uint64_t numPrimaryRays;
-    uint64_t numRayBoxTests;        /* only filled when the context was created with RTB_FLAG_COUNT_TESTS */
+    uint64_t numRayBoxTests;        /* closest-hit rays; only filled when the context was created with RTB_FLAG_COUNT_TESTS */
     uint64_t numRayTriangleTests;
+    uint64_t numShadowBoxTests;     /* shadow rays, same flag */
+    uint64_t numShadowTriangleTests;
 } RtbCounters;
 
 /* ---- batch test hooks ---------------------------------------------------------------------------- */

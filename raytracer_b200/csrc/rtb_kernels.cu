@@ -48,7 +48,7 @@ struct Control
     uint32_t pathCount[RTB_MAX_DEPTH_SLOTS + 2];     // live paths entering depth d
     uint32_t shadowPathCount[RTB_MAX_DEPTH_SLOTS + 2];
     uint32_t shadowRayCount[RTB_MAX_DEPTH_SLOTS + 2];
-    unsigned long long numRays, numShadowRays, numShadowRaysHit, numBoxTests, numTriTests;
+    unsigned long long numRays, numShadowRays, numShadowRaysHit, numBoxTests, numTriTests, numShadowBoxTests, numShadowTriTests;
 };
 
 struct Wavefront
@@ -274,8 +274,8 @@ __global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ SceneVie
     if (lane == 0 && visibleLocal) atomicAdd(&W.ctl->numShadowRaysHit, visibleLocal);
     if (kCount)
     {
-        atomicAdd(&W.ctl->numBoxTests, (unsigned long long)cnt.boxTests);
-        atomicAdd(&W.ctl->numTriTests, (unsigned long long)cnt.triTests);
+        atomicAdd(&W.ctl->numShadowBoxTests, (unsigned long long)cnt.boxTests);
+        atomicAdd(&W.ctl->numShadowTriTests, (unsigned long long)cnt.triTests);
     }
 }
 
@@ -363,8 +363,8 @@ __global__ void __launch_bounds__(128) k_trace_batch(const __grid_constant__ Sce
     }
     if (kCount)
     {
-        atomicAdd(&ctl->numBoxTests, (unsigned long long)cnt.boxTests);
-        atomicAdd(&ctl->numTriTests, (unsigned long long)cnt.triTests);
+        atomicAdd(mode == RTB_TRACE_SHADOW ? &ctl->numShadowBoxTests : &ctl->numBoxTests, (unsigned long long)cnt.boxTests);
+        atomicAdd(mode == RTB_TRACE_SHADOW ? &ctl->numShadowTriTests : &ctl->numTriTests, (unsigned long long)cnt.triTests);
     }
 }
 
@@ -898,6 +898,8 @@ int rtb_get_counters(RtbContext* c, RtbCounters* out)
     out->numShadowRaysHit = h.numShadowRaysHit;
     out->numRayBoxTests = h.numBoxTests;
     out->numRayTriangleTests = h.numTriTests;
+    out->numShadowBoxTests = h.numShadowBoxTests;
+    out->numShadowTriangleTests = h.numShadowTriTests;
     return RTB_OK;
 }
 

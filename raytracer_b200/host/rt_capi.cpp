@@ -59,10 +59,10 @@ void rtbh_scene_stats(void* scene, uint32_t* numObjects, uint32_t* numLights, ui
     if (numTlasNodes) *numTlasNodes = h->scene.GetBVH().GetNumNodes();
 }
 
-void* rtbh_viewport_create(void* scene, int deviceId, uint32_t numShards, uint32_t shardIndex, uint32_t flags, const char* blueNoisePath, char* err, size_t errLen)
+void* rtbh_viewport_create(void* scene, int deviceId, uint32_t numShards, uint32_t shardIndex, uint32_t flags, const char* blueNoisePath, void* cudaStream, char* err, size_t errLen)
 {
     rt::ViewportB200* vp = new rt::ViewportB200();
-    if (!vp->Create(deviceId, numShards, shardIndex, flags, blueNoisePath ? blueNoisePath : "")) { SetErr(err, errLen, vp->GetLastError()); delete vp; return nullptr; }
+    if (!vp->Create(deviceId, numShards, shardIndex, flags, blueNoisePath ? blueNoisePath : "", cudaStream)) { SetErr(err, errLen, vp->GetLastError()); delete vp; return nullptr; }
     if (scene && !vp->SetScene(static_cast<SceneHandle*>(scene)->scene)) { SetErr(err, errLen, vp->GetLastError()); delete vp; return nullptr; }
     return vp;
 }

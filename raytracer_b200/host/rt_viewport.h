@@ -200,11 +200,11 @@ public:
     const std::string& GetLastError() const { return mError; }
     RtbContext* GetContext() const { return mCtx; }
 
-    bool Create(int deviceId, uint32_t numShards, uint32_t shardIndex, uint32_t flags, const std::string& blueNoisePath)
+    bool Create(int deviceId, uint32_t numShards, uint32_t shardIndex, uint32_t flags, const std::string& blueNoisePath, void* cudaStream = nullptr)
     {
         RtbCreateDesc d;
         memset(&d, 0, sizeof(d));
-        d.deviceId = deviceId; d.numShards = numShards; d.shardIndex = shardIndex; d.flags = flags;
+        d.deviceId = deviceId; d.numShards = numShards; d.shardIndex = shardIndex; d.flags = flags; d.stream = cudaStream;
         if (rtb_create(&d, &mCtx) != RTB_OK) return Error();
         if (!blueNoisePath.empty())
         {

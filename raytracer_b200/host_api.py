@@ -30,7 +30,7 @@ def load_host_library():
     lib.rtbh_scene_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.rtbh_scene_stats.restype = None
     lib.rtbh_viewport_create.restype = C.c_void_p
-    lib.rtbh_viewport_create.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_char_p, C.c_size_t]
+    lib.rtbh_viewport_create.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_void_p, C.c_char_p, C.c_size_t]
     lib.rtbh_viewport_free.argtypes = [C.c_void_p]
     lib.rtbh_viewport_free.restype = None
     lib.rtbh_viewport_last_error.restype = C.c_char_p
@@ -80,12 +80,12 @@ class Scene:
 class Viewport:
     """rt::ViewportB200: Viewport's public methods (Core/Rendering/Viewport.h:37-58) on the CUDA path."""
 
-    def __init__(self, scene, device=0, num_shards=1, shard_index=0, flags=0, blue_noise=True):
+    def __init__(self, scene, device=0, num_shards=1, shard_index=0, flags=0, blue_noise=True, stream=None):
         self.lib = load_host_library()
         self.scene = scene
         err = C.create_string_buffer(1024)
         bn = BLUE_NOISE_PATH.encode() if blue_noise else None
-        self.h = self.lib.rtbh_viewport_create(scene.h, device, num_shards, shard_index, flags, bn, err, len(err))
+        self.h = self.lib.rtbh_viewport_create(scene.h, device, num_shards, shard_index, flags, bn, stream, err, len(err))
         if not self.h:
             raise capi.RtbError("viewport creation failed: %s" % err.value.decode())
         self.width = self.height = 0
