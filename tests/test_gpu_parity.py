@@ -207,3 +207,38 @@ def test_live_oracle_larger_ragged_sizes(ctx, tmp_path, scene, w, h, passes):
     util.assert_bit_identical(ctx.read_sum(), util.load_sum(sump, w, h), "%s live oracle" % scene)
     c = ctx.counters()
     assert (c["numRays"], c["numShadowRays"], c["numShadowRaysHit"]) == (meta["numRays"], meta["numShadowRays"], meta["numShadowRaysHit"])
+
+
+def test_gathered_shards_unshard_to_the_full_frame(ctx):
+    """What bench.py does at N > 1, emulated on one GPU: per-shard compact films concatenated (the all-gather result)
+    and scattered back to raster order by rtb_unshard_film; also checks the layout against raytracer_b200.sharding."""
+    import torch
+    from raytracer_b200 import sharding
+    from bench import CudaArray
+
+    scene = "cornell"
+    meta, full, _ = render_golden_case(ctx, scene, "mis")
+    w, h = meta["width"], meta["height"]
+    sf = capi.SceneFile(util.golden(scene + ".rtb"))
+    ps = capi.PassScript(util.golden(scene + ".passes"))
+    cam = capi.camera_for(sf, w, h)
+    n = 4
+    parts, ctxs = [], []
+    for s in range(n):
+        c = capi.Context(device=0, num_shards=n, shard_index=s, tile_size=8)
+        c.upload_scene(sf)
+        c.resize(w, h)
+        for p in range(meta["passes"]):
+            c.render_pass(c.make_pass(cam, ps.seeds[p], ps.offsets[p], p))
+        c.synchronize()
+        ptr, cnt = c.film_device_buffer(0)
+        parts.append(torch.as_tensor(CudaArray(ptr, cnt), device="cuda").clone())
+        ctxs.append(c)
+    gathered = torch.cat(parts)
+    torch.cuda.synchronize()
+    img = ctxs[0].unshard_film(gathered.data_ptr())
+    util.assert_bit_identical(img, full, "unsharded film")
+    img2 = sharding.unshard(gathered.cpu().numpy().reshape(-1, 3), w, h, n, tile_size=8)
+    util.assert_bit_identical(img2, full, "python unshard of the same buffers")
+    for c in ctxs:
+        c.close()
