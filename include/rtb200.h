@@ -9,7 +9,7 @@
  *   rtb_upload_scene              Scene::BuildBVH result + CreateRenderer Core/Scene/Scene.cpp:36-126, Core/Rendering/Renderer.cpp:45-69
  *   rtb_resize                    Viewport::Resize                        Core/Rendering/Viewport.cpp:52-115
  *   rtb_reset                     Viewport::Reset                         Core/Rendering/Viewport.cpp:117-138
- *   rtb_render_pass               Viewport::Render (one sample per pixel) Core/Rendering/Viewport.cpp:185-289
+ *   rtb_render_pass(es)           Viewport::Render (one sample per pixel) Core/Rendering/Viewport.cpp:185-289
  *   rtb_read_sum                  Viewport::GetSumBuffer                  Core/Rendering/Viewport.h:50
  *   rtb_get_counters              Viewport::GetCounters                   Core/Rendering/Viewport.h:58, Core/Rendering/Counters.h:36-93
  *   rtb_trace_batch               Scene::Traverse / Scene::Traverse_Shadow Core/Scene/Scene.cpp:219-261
@@ -288,6 +288,10 @@ int  rtb_reset(RtbContext* ctx);
 
 /* enqueue one pass (asynchronous on the context's stream); rtb_synchronize / rtb_read_* wait for it */
 int  rtb_render_pass(RtbContext* ctx, const RtbPassDesc* pass);
+/* `count` passes at once: consecutive passes that differ only in (seed, sampleOffset, passIndex + 1) are traced in ONE
+ * wavefront (more rays per launch, fewer launches); the film receives them in pass order, so the result is bit-identical
+ * to `count` calls of rtb_render_pass */
+int  rtb_render_passes(RtbContext* ctx, const RtbPassDesc* passes, uint32_t count);
 int  rtb_synchronize(RtbContext* ctx);
 
 /* which: 0 = sum, 1 = secondarySum.  rgb = width*height*3 floats, row 0 = top (Film.cpp:31-39) */

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librtb200.so")
+LIB_PATH = os.environ.get("RTB200_LIB", os.path.join(_HERE, "librtb200.so"))   # override only for A/B builds of the same sources
 
 RTB_INVALID_OBJECT = 0xFFFFFFFF
 RTB_LIGHT_OBJECT = 0xFFFFFFFE
@@ -107,7 +107,7 @@ HIT_DTYPE = np.dtype([("objectId", np.uint32), ("subObjectId", np.uint32), ("dis
 # every symbol include/rtb200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = [
     "rtb_last_error", "rtb_api_version", "rtb_create", "rtb_destroy", "rtb_upload_scene", "rtb_set_blue_noise",
-    "rtb_resize", "rtb_reset", "rtb_render_pass", "rtb_synchronize", "rtb_read_sum", "rtb_film_device_buffer",
+    "rtb_resize", "rtb_reset", "rtb_render_pass", "rtb_render_passes", "rtb_synchronize", "rtb_read_sum", "rtb_film_device_buffer",
     "rtb_unshard_film", "rtb_get_counters", "rtb_trace_batch", "rtb_trace_batch_device", "rtb_sample_batch",
     "rtb_primary_rays", "rtb_set_profiling", "rtb_get_pass_timings",
 ]
@@ -139,6 +139,7 @@ def load_library(path=None):
     lib.rtb_resize.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
     lib.rtb_reset.argtypes = [C.c_void_p]
     lib.rtb_render_pass.argtypes = [C.c_void_p, C.POINTER(RtbPassDesc)]
+    lib.rtb_render_passes.argtypes = [C.c_void_p, C.POINTER(RtbPassDesc), C.c_uint32]
     lib.rtb_synchronize.argtypes = [C.c_void_p]
     lib.rtb_read_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.rtb_film_device_buffer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
@@ -295,6 +296,18 @@ class Context:
 
     def render_pass(self, p):
         _check(self.lib, self.lib.rtb_render_pass(self.h, C.byref(p)))
+
+    def render_passes(self, camera, seeds, offsets, first_pass=0, **kw):
+        """rtb_render_passes: seeds (n, dims) uint32, offsets (n, 2) float32; consecutive passes share wavefronts."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        n = len(seeds)
+        arr = (RtbPassDesc * n)()
+        for i in range(n):
+            p = self.make_pass(camera, seeds[i], offsets[i], first_pass + i, **kw)
+            p.seed = seeds[i].ctypes.data
+            arr[i] = p
+        self._batch_keepalive = seeds
+        _check(self.lib, self.lib.rtb_render_passes(self.h, arr, n))
 
     def synchronize(self):
         _check(self.lib, self.lib.rtb_synchronize(self.h))

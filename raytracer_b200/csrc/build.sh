@@ -3,7 +3,7 @@
 # FMA appears only where the reference calls an explicit fused intrinsic (rtb_math.h).
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
-OUT="$HERE/../librtb200.so"
+OUT="${RTB_OUT:-$HERE/../librtb200.so}"
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
      --fmad=false -ftz=true -prec-div=true -prec-sqrt=true \
      -Xptxas -v -shared -Xcompiler -fPIC -Xcompiler -O2 \

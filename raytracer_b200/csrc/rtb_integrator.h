@@ -11,7 +11,7 @@
 //
 // Radiance bookkeeping goes through a Sink (see rtb_kernels.cu / tests/hostsim):
 //   sink.add(thr, c)                     resultColor.MulAndAccumulate(thr, c)
-//   sink.shadow(ray, tMax, contribution) one NEE sample whose visibility is still unknown (light order preserved)
+//   sink.shadow(ray, tMax, contribution, light) one NEE sample whose visibility is still unknown (light order preserved)
 //   sink.end_lights(thr)                 resultColor.MulAndAccumulate(thr, sum of the visible contributions)
 #pragma once
 
@@ -25,6 +25,7 @@ struct PathState
     V4       throughput;
     Sampler  sampler;
     uint32_t pixel;
+    uint32_t passSlot;      // which pass of the batch in flight (0 when passes are rendered one at a time)
     uint32_t depth;
     float    lastPdfW;
     uint32_t lastSpecular;
@@ -34,10 +35,14 @@ struct PathState
 RTB_HD float combine_mis(const float samplePdf, const float otherPdf) { return samplePdf / (samplePdf + otherPdf); }
 RTB_HD float pdf_a_to_w(const float pdfA, const float distance, const float cosThere) { return (pdfA * s_sqr(distance)) / s_abs(cosThere); }
 
-RTB_HD void init_path(const PassParams& P, const uint16_t* blueNoise, uint32_t x, uint32_t y, PathState& ps)
+RTB_HD void init_path(const PassParams& P, const uint16_t* blueNoise, uint32_t x, uint32_t y, uint32_t passSlot, PathState& ps)
 {
     sampler_reset_pixel(ps.sampler, x, y);
-    ps.ray = generate_primary_ray(P, x, y, ps.sampler, blueNoise);
+    ps.sampler.seedBase = passSlot * P.numSeedDims;
+    ps.passSlot = passSlot;
+    const float offX = P.sampleOffsets ? P.sampleOffsets[2 * passSlot] : P.sampleOffsetX;
+    const float offY = P.sampleOffsets ? P.sampleOffsets[2 * passSlot + 1] : P.sampleOffsetY;
+    ps.ray = generate_primary_ray(P, x, y, offX, offY, ps.sampler, blueNoise);
     ps.throughput = v4s(1.0f);      // RayColor::One() = (1, 1, 1, 1)
     ps.pixel = y * P.width + x;
     ps.depth = 0;
@@ -125,7 +130,7 @@ RTB_HD bool shade_vertex_mis(const SceneView& S, const PassParams& P, PathState&
         {
             // the reference picks with a per-thread RNG (PathTracerMIS.cpp:136); here: a counter-based hash of the
             // sampler state, which is reproducible but only statistically equivalent
-            first = (uint32_t)(hash64(((uint64_t)ps.pixel << 32) ^ ((uint64_t)P.passIndex << 8) ^ ps.depth ^ 0x9E3779B97F4A7C15ULL) % S.numLights);
+            first = (uint32_t)(hash64(((uint64_t)ps.pixel << 32) ^ ((uint64_t)(P.passIndex + ps.passSlot) << 8) ^ ps.depth ^ 0x9E3779B97F4A7C15ULL) % S.numLights);
             last = first + 1;
         }
         const bool isLastPathSegment = ps.depth >= P.maxRayDepth;
@@ -154,7 +159,7 @@ RTB_HD bool shade_vertex_mis(const SceneView& S, const PassParams& P, PathState&
                 weight = combine_mis(ir.directPdfW * lightPickProbability, bsdfPdfW);
             }
             const V4 contribution = (radiance * factor) * (weight / (lightPickProbability * ir.directPdfW));
-            sink.shadow(shadowRay, tMax, contribution);
+            sink.shadow(shadowRay, tMax, contribution, li);
             numShadowRays++;
         }
         sink.end_lights(ps.throughput);

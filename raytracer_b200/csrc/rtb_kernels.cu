@@ -34,6 +34,12 @@ using namespace rtb;
 
 #define RTB_MAX_DEPTH_SLOTS 64
 
+// 64 registers -> 8 CTAs of 128 threads per SM: the traversal kernels are latency bound, occupancy is worth more than
+// the few spilled bytes (measured: 72 regs / 7 CTAs 4.4 ms, 64 regs / 8 CTAs 3.6 ms per pass for k_traverse)
+#ifndef RTB_TRAV_MINBLOCKS
+#define RTB_TRAV_MINBLOCKS 8
+#endif
+
 struct PathBuf
 {
     float4* p0;   // origin.xyz, dir.x
@@ -68,8 +74,10 @@ struct Wavefront
     uint32_t* rayList;    // compacted shadow-ray slots (i * raysPerPath + r) of the current depth
     Control* ctl;
     const uint32_t* pixelList;   // pixel slot -> y * width + x
-    uint32_t numPixels;
+    uint32_t numPixels;          // pixel slots of this shard
     uint32_t raysPerPath;
+    uint32_t batch;              // passes in flight in this wavefront (pass slot b uses passColor[b * numPixels + pixel])
+    uint32_t firstPassIndex;     // Viewport pass index of pass slot 0
 };
 
 __device__ __forceinline__ void store_path(const PathBuf& b, uint32_t i, const PathState& ps)
@@ -78,7 +86,7 @@ __device__ __forceinline__ void store_path(const PathBuf& b, uint32_t i, const P
     b.p1[i] = make_float4(ps.ray.dir.y, ps.ray.dir.z, ps.ray.invDir.x, ps.ray.invDir.y);
     b.p2[i] = make_float4(ps.ray.invDir.z, ps.ray.originDivDir.x, ps.ray.originDivDir.y, ps.ray.originDivDir.z);
     b.p3[i] = make_float4(ps.throughput.x, ps.throughput.y, ps.throughput.z, ps.throughput.w);
-    b.p4[i] = make_uint4(ps.pixel, ps.sampler.salt, (ps.sampler.dim & 0xFFFFu) | ((ps.depth & 0x7FFFu) << 16) | (ps.lastSpecular << 31), __float_as_uint(ps.lastPdfW));
+    b.p4[i] = make_uint4(ps.pixel | (ps.passSlot << 26), ps.sampler.salt, (ps.sampler.dim & 0xFFFFu) | ((ps.depth & 0x7FFFu) << 16) | (ps.lastSpecular << 31), __float_as_uint(ps.lastPdfW));
 }
 
 __device__ __forceinline__ void load_ray(const PathBuf& b, uint32_t i, Ray& r)
@@ -90,21 +98,23 @@ __device__ __forceinline__ void load_ray(const PathBuf& b, uint32_t i, Ray& r)
     r.originDivDir = v3(d.y, d.z, d.w);
 }
 
-__device__ __forceinline__ void load_path(const PathBuf& b, uint32_t i, const Wavefront& W, uint32_t width, PathState& ps)
+__device__ __forceinline__ void load_path(const PathBuf& b, uint32_t i, const Wavefront& W, uint32_t width, uint32_t numSeedDims, PathState& ps)
 {
     load_ray(b, i, ps.ray);
     const float4 t = b.p3[i];
     ps.throughput = v4(t.x, t.y, t.z, t.w);
     const uint4 m = b.p4[i];
-    ps.pixel = m.x;
+    ps.pixel = m.x & 0x03FFFFFFu;
+    ps.passSlot = m.x >> 26;
     ps.sampler.salt = m.y;
     ps.sampler.dim = m.z & 0xFFFFu;
     ps.depth = (m.z >> 16) & 0x7FFFu;
     ps.lastSpecular = m.z >> 31;
     ps.lastPdfW = __uint_as_float(m.w);
-    const uint32_t pix = W.pixelList[m.x];
+    const uint32_t pix = W.pixelList[ps.pixel];
     const uint32_t x = pix % width, y = pix / width;
     ps.sampler.bnOffset = 4u * (128u * (y & 127u) + (x & 127u));
+    ps.sampler.seedBase = ps.passSlot * numSeedDims;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -114,19 +124,21 @@ __device__ __forceinline__ void load_path(const PathBuf& b, uint32_t i, const Wa
 __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const __grid_constant__ Wavefront W)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < W.numPixels; i += stride)
+    const uint32_t total = W.numPixels * W.batch;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
     {
-        const uint32_t pix = W.pixelList[i];
+        const uint32_t passSlot = i / W.numPixels, slot = i - passSlot * W.numPixels;
+        const uint32_t pix = W.pixelList[slot];
         PathState ps;
-        init_path(P, S.blueNoise, pix % P.width, pix / P.width, ps);
-        ps.pixel = i;
+        init_path(P, S.blueNoise, pix % P.width, pix / P.width, passSlot, ps);
+        ps.pixel = slot;
         store_path(W.buf[0], i, ps);
         W.passColor[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
 
 template <bool kCount>
-__global__ void __launch_bounds__(128) k_traverse(const __grid_constant__ SceneView S, const __grid_constant__ Wavefront W, uint32_t depth)
+__global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_traverse(const __grid_constant__ SceneView S, const __grid_constant__ Wavefront W, uint32_t depth)
 {
     const uint32_t count = W.ctl->pathCount[depth];
     const PathBuf& in = W.buf[depth & 1];
@@ -159,7 +171,9 @@ struct DeviceSink
     V4 lightThr;
     __device__ DeviceSink(const Wavefront& w, uint32_t base) : W(w), rayBase(base), numRays(0) { dirty = false; result = v3s(0.0f); lightThr = v4s(0.0f); }
     __device__ void add(const V4& thr, const V4& c) { result = mul_add(xyz(thr), xyz(c), result); dirty = true; }
-    __device__ void shadow(const Ray& ray, float tMax, const V4& c)
+    // slots are filled in emission order = light order (a measured alternative, one ray list per light so that rays
+    // towards the same light are traced together, did not pay: 40.9 vs 40.4 ms per 8 passes for k_shadow)
+    __device__ void shadow(const Ray& ray, float tMax, const V4& c, uint32_t)
     {
         const uint32_t j = rayBase + numRays++;
         W.sr0[j] = make_float4(ray.origin.x, ray.origin.y, ray.origin.z, tMax);
@@ -187,22 +201,23 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneView
         PathState ps;
         if (i < count)
         {
-            load_path(in, i, W, P.width, ps);
+            load_path(in, i, W, P.width, P.numSeedDims, ps);
             const uint4 h0 = W.hit0[i];
             Hit hit;
             hit.objectId = h0.x; hit.subObjectId = h0.y; hit.distance = __uint_as_float(h0.z); hit.u = __uint_as_float(h0.w);
             hit.v = W.hit1[i];
 
-            const float4 pc = W.passColor[ps.pixel];
+            const uint32_t colorIndex = ps.passSlot * W.numPixels + ps.pixel;
+            const float4 pc = W.passColor[colorIndex];
             DeviceSink sink(W, i * W.raysPerPath);
             sink.result = v3(pc.x, pc.y, pc.z);
             if (P.renderer == RTB_RENDERER_PATH_TRACER_MIS) alive = shade_vertex_mis(S, P, ps, hit, sink, numShadow);
             else if (P.renderer == RTB_RENDERER_PATH_TRACER) alive = shade_vertex_pt(S, P, ps, hit, sink);
             else shade_debug(S, P, ps, hit, sink);
-            if (sink.dirty) W.passColor[ps.pixel] = make_float4(sink.result.x, sink.result.y, sink.result.z, 0.0f);
+            if (sink.dirty) W.passColor[colorIndex] = make_float4(sink.result.x, sink.result.y, sink.result.z, 0.0f);
             if (numShadow)
             {
-                W.shThr[i] = make_float4(sink.lightThr.x, sink.lightThr.y, sink.lightThr.z, __uint_as_float(ps.pixel));
+                W.shThr[i] = make_float4(sink.lightThr.x, sink.lightThr.y, sink.lightThr.z, __uint_as_float(colorIndex));
                 W.shCount[i] = numShadow;
                 shadowRaysLocal += numShadow;
             }
@@ -249,7 +264,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneView
 }
 
 template <bool kCount>
-__global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ SceneView S, const __grid_constant__ Wavefront W, uint32_t depth)
+__global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid_constant__ SceneView S, const __grid_constant__ Wavefront W, uint32_t depth)
 {
     const uint32_t count = W.ctl->shadowRayCount[depth];
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -300,20 +315,24 @@ __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ Wavefro
     }
 }
 
-// Film::AccumulateColor, Film.cpp:25-39: sum += colour; secondarySum += colour on even passes
-__global__ void __launch_bounds__(256) k_film(const __grid_constant__ Wavefront W, float* __restrict__ sum, float* __restrict__ sum2, uint32_t evenPass)
+// Film::AccumulateColor, Film.cpp:25-39: sum += colour; secondarySum += colour on even passes.  The passes of a batch
+// are added in pass order, so the float sums are the ones the reference gets pass after pass.
+__global__ void __launch_bounds__(256) k_film(const __grid_constant__ Wavefront W, float* __restrict__ sum, float* __restrict__ sum2)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < W.numPixels; i += stride)
     {
-        const float4 c = W.passColor[i];
         float* s = sum + (size_t)i * 3;
-        s[0] = s[0] + c.x; s[1] = s[1] + c.y; s[2] = s[2] + c.z;
-        if (evenPass)
+        float* t = sum2 + (size_t)i * 3;
+        float s0 = s[0], s1 = s[1], s2 = s[2], t0 = t[0], t1 = t[1], t2 = t[2];
+        for (uint32_t b = 0; b < W.batch; ++b)
         {
-            float* t = sum2 + (size_t)i * 3;
-            t[0] = t[0] + c.x; t[1] = t[1] + c.y; t[2] = t[2] + c.z;
+            const float4 c = W.passColor[(size_t)b * W.numPixels + i];
+            s0 = s0 + c.x; s1 = s1 + c.y; s2 = s2 + c.z;
+            if (((W.firstPassIndex + b) & 1u) == 0u) { t0 = t0 + c.x; t1 = t1 + c.y; t2 = t2 + c.z; }
         }
+        s[0] = s0; s[1] = s1; s[2] = s2;
+        t[0] = t0; t[1] = t1; t[2] = t2;
     }
 }
 
@@ -382,7 +401,7 @@ __global__ void k_primary_rays(const __grid_constant__ SceneView S, const __grid
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.width * P.height) return;
     PathState ps;
-    init_path(P, S.blueNoise, i % P.width, i / P.width, ps);
+    init_path(P, S.blueNoise, i % P.width, i / P.width, 0, ps);
     RtbRay r;
     r.origin[0] = ps.ray.origin.x; r.origin[1] = ps.ray.origin.y; r.origin[2] = ps.ray.origin.z; r.origin[3] = 0.0f;
     r.dir[0] = ps.ray.dir.x; r.dir[1] = ps.ray.dir.y; r.dir[2] = ps.ray.dir.z; r.dir[3] = 0.0f;
@@ -468,6 +487,7 @@ struct RtbContext
     uint32_t numPixels = 0;        // pixels of this shard
     uint32_t shardSlots = 0;       // padded slot count (equal on every shard)
     uint32_t raysPerPath = 0;
+    uint32_t maxBatch = 1;         // passes per wavefront (sized at resize so that a wavefront has a few million paths)
     DevArray<uint32_t> pixelList;     // this shard
     DevArray<uint32_t> pixelListAll;  // all shards back to back, padded with 0xFFFFFFFF
     DevArray<float> sum, sum2;
@@ -479,11 +499,16 @@ struct RtbContext
     DevArray<float4> passColor, sr0, sr1, sr2, sr3, shThr;
     DevArray<uint32_t> shCount, shList, rayList;
     DevArray<Control> ctl;
-    DevArray<uint32_t> seed;
+    DevArray<uint32_t> seed;       // maxBatch x numSeedDims
+    DevArray<float> offsets;       // maxBatch x 2
     Wavefront wf;
 
     RtbCounters counters;
     uint32_t passesSinceReset = 0;
+    std::vector<uint32_t> stagingSeeds;
+    std::vector<float> stagingOffsets;
+
+    int simpleBlocksPerSM = 8;           // CTAs per SM of the persistent grid-stride kernels
 
     // profiling
     bool profiling = false;
@@ -513,9 +538,9 @@ static int alloc_shadow(RtbContext* c)
     // shadow-ray storage depends on both the film size and the number of lights sampled per vertex
     const uint32_t rpp = c->numLights > 0 ? c->numLights : 1;
     if (c->numPixels == 0) return RTB_OK;
-    if (rpp == c->raysPerPath && c->sr0.count == (size_t)c->numPixels * rpp) return RTB_OK;
+    if (rpp == c->raysPerPath && c->sr0.count == (size_t)c->numPixels * c->maxBatch * rpp) return RTB_OK;
     c->raysPerPath = rpp;
-    const size_t n = (size_t)c->numPixels * rpp;
+    const size_t n = (size_t)c->numPixels * c->maxBatch * rpp;
     RTB_CUDA(c->sr0.alloc(n)); RTB_CUDA(c->sr1.alloc(n)); RTB_CUDA(c->sr2.alloc(n)); RTB_CUDA(c->sr3.alloc(n));
     RTB_CUDA(c->rayList.alloc(n));
     return RTB_OK;
@@ -570,6 +595,7 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
         c->ownStream = true;
     }
     cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, c->device);
+    if (const char* t = getenv("RTB_SIMPLE_BLOCKS")) c->simpleBlocksPerSM = atoi(t) > 0 ? atoi(t) : 8;
     e = c->ctl.alloc(1);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->ctl.ptr, 0, sizeof(Control), c->stream);
     if (e != cudaSuccess) { delete c; return fail(RTB_ERR_CUDA, "control block allocation failed: %s", cudaGetErrorString(e)); }
@@ -588,7 +614,7 @@ void rtb_destroy(RtbContext* c)
     cudaStreamSynchronize(c->stream);
     free_scene(c);
     free_film(c);
-    c->blueNoise.release(); c->ctl.release(); c->seed.release();
+    c->blueNoise.release(); c->ctl.release(); c->seed.release(); c->offsets.release();
     for (cudaEvent_t ev : c->events) cudaEventDestroy(ev);
     if (c->ownStream) cudaStreamDestroy(c->stream);
     delete c;
@@ -686,7 +712,19 @@ int rtb_resize(RtbContext* c, uint32_t width, uint32_t height)
     RTB_CUDA(c->pixelListAll.upload(all, c->stream));
     RTB_CUDA(cudaStreamSynchronize(c->stream));
 
-    const size_t n = c->numPixels;
+    // passes per wavefront: enough paths in flight to keep 148 SMs busy through the deep (sparse) bounces, bounded by memory
+    {
+        uint32_t target = 8u << 20;
+        if (const char* t = getenv("RTB_BATCH_PATHS")) target = (uint32_t)strtoul(t, nullptr, 10);
+        uint32_t b = c->numPixels ? (target + c->numPixels - 1) / c->numPixels : 1u;
+        if (b < 1u) b = 1u;
+        if (b > 16u) b = 16u;
+        if (c->numPixels >= (1u << 26)) b = 1u;
+        if (const char* t = getenv("RTB_MAX_BATCH")) b = (uint32_t)atoi(t) > 0 ? (uint32_t)atoi(t) : b;
+        if (b > 63u) b = 63u;
+        c->maxBatch = b;
+    }
+    const size_t n = (size_t)c->numPixels * c->maxBatch;
     RTB_CUDA(c->sum.alloc(maxSlots * 3)); RTB_CUDA(c->sum2.alloc(maxSlots * 3));
     RTB_CUDA(c->raster.alloc((size_t)width * height * 3));
     for (int b = 0; b < 2; ++b) { for (int k = 0; k < 4; ++k) RTB_CUDA(c->p[b][k].alloc(n)); RTB_CUDA(c->p4[b].alloc(n)); }
@@ -735,7 +773,8 @@ static int fill_pass_params(RtbContext* c, const RtbPassDesc* pass, PassParams& 
     P.passIndex = pass->passIndex; P.numSeedDims = pass->numSeedDims;
     if (uploadSeed)
     {
-        if (c->seed.count < pass->numSeedDims || !c->seed.ptr) { RTB_CUDA(cudaStreamSynchronize(c->stream)); RTB_CUDA(c->seed.alloc(pass->numSeedDims > 64 ? pass->numSeedDims : 64)); }
+        // single-pass helpers (rtb_sample_batch / rtb_primary_rays)
+        if (c->seed.count < pass->numSeedDims || !c->seed.ptr) { RTB_CUDA(cudaStreamSynchronize(c->stream)); RTB_CUDA(c->seed.alloc((size_t)c->maxBatch * (pass->numSeedDims > 64 ? pass->numSeedDims : 64))); }
         if (pass->numSeedDims) RTB_CUDA(cudaMemcpyAsync(c->seed.ptr, pass->seed, pass->numSeedDims * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     }
     P.seed = c->seed.ptr;
@@ -750,81 +789,92 @@ static cudaEvent_t next_event(RtbContext* c, size_t& cursor)
     return ev;
 }
 
-int rtb_render_pass(RtbContext* c, const RtbPassDesc* pass)
+// one wavefront of `batch` consecutive passes that share everything but (seed, sampleOffset, passIndex)
+static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch)
 {
-    if (!c || !pass) return fail(RTB_ERR_INVALID_ARG, "rtb_render_pass: null argument");
-    if (!c->hasScene) return fail(RTB_ERR_NO_SCENE, "rtb_render_pass: no scene uploaded");       // Viewport.cpp:194-198 ("Missing renderer")
-    if (c->width == 0 || c->height == 0) return fail(RTB_ERR_INVALID_ARG, "rtb_render_pass: viewport has no size");
-    RTB_CUDA(cudaSetDevice(c->device));
-
-    // the reference silently switches to a per-thread RNG beyond SamplingParams::dimensions (GenericSampler.cpp:106-109);
-    // that is irreproducible, so refuse it up front.  Worst case per path: SURVEY appendix B.
-    if (pass->renderer != RTB_RENDERER_DEBUG)
-    {
-        const uint32_t L = pass->renderer == RTB_RENDERER_PATH_TRACER_MIS ? (pass->lightSamplingStrategy == RTB_LIGHT_SAMPLING_ALL ? c->numLights : (c->numLights ? 1u : 0u)) : 0u;
-        const uint32_t D = pass->maxRayDepth;
-        const uint32_t needed = (pass->camera.dofEnable ? 2u : 0u) + 3u * L * (D + 1u) + 4u * D;
-        if (needed > pass->numSeedDims)
-            return fail(RTB_ERR_INVALID_ARG, "rtb_render_pass: %u sample dimensions needed (lights=%u, maxRayDepth=%u) but only %u seeded", needed, L, D, pass->numSeedDims);
-    }
-
+    const RtbPassDesc* pass = &passes[0];
     PassParams P;
-    int rc = fill_pass_params(c, pass, P, true);
+    int rc = fill_pass_params(c, pass, P, false);
     if (rc != RTB_OK) return rc;
-    if (c->numPixels == 0) { c->passesSinceReset++; return RTB_OK; }
+    cudaStream_t s = c->stream;
+
+    // per-pass seed vectors + AA offsets of the batch (stream ordered: the previous batch's kernels are done with them)
+    const uint32_t dims = pass->numSeedDims;
+    if (c->seed.count < (size_t)c->maxBatch * (dims ? dims : 1) || !c->seed.ptr)
+    {
+        RTB_CUDA(cudaStreamSynchronize(s));
+        RTB_CUDA(c->seed.alloc((size_t)c->maxBatch * (dims > 64 ? dims : 64)));
+    }
+    if (!c->offsets.ptr) RTB_CUDA(c->offsets.alloc((size_t)64 * 2));
+    c->stagingSeeds.resize((size_t)batch * dims);
+    c->stagingOffsets.resize((size_t)batch * 2);
+    for (uint32_t b = 0; b < batch; ++b)
+    {
+        if (dims) memcpy(&c->stagingSeeds[(size_t)b * dims], passes[b].seed, dims * sizeof(uint32_t));
+        c->stagingOffsets[2 * b] = passes[b].sampleOffset[0];
+        c->stagingOffsets[2 * b + 1] = passes[b].sampleOffset[1];
+    }
+    if (dims) RTB_CUDA(cudaMemcpyAsync(c->seed.ptr, c->stagingSeeds.data(), (size_t)batch * dims * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    RTB_CUDA(cudaMemcpyAsync(c->offsets.ptr, c->stagingOffsets.data(), (size_t)batch * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    P.seed = c->seed.ptr;
+    P.sampleOffsets = c->offsets.ptr;
+
+    Wavefront W = c->wf;
+    W.batch = batch;
+    W.firstPassIndex = pass->passIndex;
+    const uint32_t numPaths = c->numPixels * batch;
 
     const bool count = (c->flags & RTB_FLAG_COUNT_TESTS) != 0;
-    cudaStream_t s = c->stream;
-    // queue counters of this pass: everything except the cumulative ray counters
+    // queue counters of this wavefront: everything except the cumulative ray counters
     RTB_CUDA(cudaMemsetAsync(c->ctl.ptr, 0, offsetof(Control, numRays), s));
-    RTB_CUDA(cudaMemcpyAsync(&c->ctl.ptr->pathCount[0], &c->numPixels, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    RTB_CUDA(cudaMemcpyAsync(&c->ctl.ptr->pathCount[0], &numPaths, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
 
-    const int blocks128 = c->numSMs * 8;
+    const int blocks128 = c->numSMs * c->simpleBlocksPerSM;
     const int blocks256 = c->numSMs * 4;
     size_t ev = 0;
     std::vector<cudaEvent_t> marks;
     const bool prof = c->profiling;
     if (prof) marks.push_back(next_event(c, ev));
-    k_raygen<<<blocks256, 256, 0, s>>>(c->view, P, c->wf);
+    k_raygen<<<blocks256, 256, 0, s>>>(c->view, P, W);
     if (prof) marks.push_back(next_event(c, ev));
     const uint32_t depthLimit = pass->renderer == RTB_RENDERER_DEBUG ? 0u : pass->maxRayDepth;
+    const bool shadows = pass->renderer == RTB_RENDERER_PATH_TRACER_MIS && c->numLights > 0;
     for (uint32_t d = 0; d <= depthLimit; ++d)
     {
-        if (count) k_traverse<true><<<blocks128, 128, 0, s>>>(c->view, c->wf, d);
-        else k_traverse<false><<<blocks128, 128, 0, s>>>(c->view, c->wf, d);
+        if (count) k_traverse<true><<<blocks128, 128, 0, s>>>(c->view, W, d);
+        else k_traverse<false><<<blocks128, 128, 0, s>>>(c->view, W, d);
         if (prof) marks.push_back(next_event(c, ev));
-        k_shade<<<blocks128, 128, 0, s>>>(c->view, P, c->wf, d);
+        k_shade<<<blocks128, 128, 0, s>>>(c->view, P, W, d);
         if (prof) marks.push_back(next_event(c, ev));
-        if (pass->renderer == RTB_RENDERER_PATH_TRACER_MIS && c->numLights > 0)
+        if (shadows)
         {
-            if (count) k_shadow<true><<<blocks128, 128, 0, s>>>(c->view, c->wf, d);
-            else k_shadow<false><<<blocks128, 128, 0, s>>>(c->view, c->wf, d);
-            k_resolve<<<blocks256, 256, 0, s>>>(c->wf, d);
+            if (count) k_shadow<true><<<blocks128, 128, 0, s>>>(c->view, W, d);
+            else k_shadow<false><<<blocks128, 128, 0, s>>>(c->view, W, d);
+            k_resolve<<<blocks256, 256, 0, s>>>(W, d);
         }
         if (prof) marks.push_back(next_event(c, ev));
     }
-    k_film<<<blocks256, 256, 0, s>>>(c->wf, c->sum.ptr, c->sum2.ptr, (pass->passIndex % 2 == 0) ? 1u : 0u);
+    k_film<<<blocks256, 256, 0, s>>>(W, c->sum.ptr, c->sum2.ptr);
     if (prof) marks.push_back(next_event(c, ev));
     RTB_CUDA(cudaGetLastError());
-    c->counters.numPrimaryRays += c->numPixels;     // Viewport.cpp:429
-    c->passesSinceReset++;
+    c->counters.numPrimaryRays += (uint64_t)c->numPixels * batch;     // Viewport.cpp:429
+    c->passesSinceReset += batch;
 
     if (prof)
     {
         RTB_CUDA(cudaStreamSynchronize(s));
         RtbPassTimings& t = c->timings;
-        memset(&t, 0, sizeof(t));
         auto ms = [&](size_t a, size_t b) { float v = 0.0f; cudaEventElapsedTime(&v, marks[a], marks[b]); return v; };
-        t.raygenMs = ms(0, 1);
+        t.raygenMs += ms(0, 1);
         size_t k = 1;
         for (uint32_t d = 0; d <= depthLimit; ++d)
         {
             t.traverseMs += ms(k, k + 1); t.shadeMs += ms(k + 1, k + 2); t.shadowMs += ms(k + 2, k + 3);
             k += 3;
             t.traverseLaunches++; t.shadeLaunches++;
-            if (pass->renderer == RTB_RENDERER_PATH_TRACER_MIS && c->numLights > 0) t.shadowLaunches += 2;
+            if (shadows) t.shadowLaunches += 2;
         }
-        t.totalMs = ms(0, marks.size() - 1);
+        t.totalMs += ms(0, marks.size() - 1);
         t.totalLaunches = 2 + t.traverseLaunches + t.shadeLaunches + t.shadowLaunches;
         Control h;
         RTB_CUDA(cudaMemcpy(&h, c->ctl.ptr, sizeof(Control), cudaMemcpyDeviceToHost));
@@ -832,6 +882,58 @@ int rtb_render_pass(RtbContext* c, const RtbPassDesc* pass)
         for (uint32_t d = 0; d <= depthLimit; ++d) t.shadowRays += h.shadowRayCount[d];
     }
     return RTB_OK;
+}
+
+int rtb_render_passes(RtbContext* c, const RtbPassDesc* passes, uint32_t count)
+{
+    if (!c || (count && !passes)) return fail(RTB_ERR_INVALID_ARG, "rtb_render_passes: null argument");
+    if (!c->hasScene) return fail(RTB_ERR_NO_SCENE, "rtb_render_passes: no scene uploaded");       // Viewport.cpp:194-198 ("Missing renderer")
+    if (c->width == 0 || c->height == 0) return fail(RTB_ERR_INVALID_ARG, "rtb_render_passes: viewport has no size");
+    RTB_CUDA(cudaSetDevice(c->device));
+
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        const RtbPassDesc* pass = &passes[i];
+        // the reference silently switches to a per-thread RNG beyond SamplingParams::dimensions (GenericSampler.cpp:106-109);
+        // that is irreproducible, so refuse it up front.  Worst case per path: SURVEY appendix B.
+        if (pass->renderer != RTB_RENDERER_DEBUG)
+        {
+            const uint32_t L = pass->renderer == RTB_RENDERER_PATH_TRACER_MIS ? (pass->lightSamplingStrategy == RTB_LIGHT_SAMPLING_ALL ? c->numLights : (c->numLights ? 1u : 0u)) : 0u;
+            const uint32_t D = pass->maxRayDepth;
+            const uint32_t needed = (pass->camera.dofEnable ? 2u : 0u) + 3u * L * (D + 1u) + 4u * D;
+            if (needed > pass->numSeedDims)
+                return fail(RTB_ERR_INVALID_ARG, "rtb_render_pass: %u sample dimensions needed (lights=%u, maxRayDepth=%u) but only %u seeded", needed, L, D, pass->numSeedDims);
+        }
+        PassParams P;
+        int rc = fill_pass_params(c, pass, P, false);     // validates renderer id, depth, camera, seed pointer
+        if (rc != RTB_OK) return rc;
+    }
+    if (c->profiling) memset(&c->timings, 0, sizeof(c->timings));
+    if (c->numPixels == 0) { c->passesSinceReset += count; return RTB_OK; }
+
+    // consecutive passes that differ only in (seed, sampleOffset, passIndex = previous + 1) share a wavefront
+    auto same = [](const RtbPassDesc& a, const RtbPassDesc& b)
+    {
+        return a.renderer == b.renderer && a.debugMode == b.debugMode && memcmp(&a.camera, &b.camera, sizeof(RtbCamera)) == 0 &&
+               a.maxRayDepth == b.maxRayDepth && a.minRussianRouletteDepth == b.minRussianRouletteDepth &&
+               a.lightSamplingStrategy == b.lightSamplingStrategy && a.useBlueNoise == b.useBlueNoise && a.numSeedDims == b.numSeedDims;
+    };
+    uint32_t i = 0;
+    while (i < count)
+    {
+        uint32_t n = 1;
+        while (i + n < count && n < c->maxBatch && same(passes[i], passes[i + n]) && passes[i + n].passIndex == passes[i].passIndex + n) n++;
+        int rc = render_batch(c, passes + i, n);
+        if (rc != RTB_OK) return rc;
+        i += n;
+    }
+    return RTB_OK;
+}
+
+int rtb_render_pass(RtbContext* c, const RtbPassDesc* pass)
+{
+    if (!c || !pass) return fail(RTB_ERR_INVALID_ARG, "rtb_render_pass: null argument");
+    return rtb_render_passes(c, pass, 1);
 }
 
 int rtb_synchronize(RtbContext* c)

@@ -20,13 +20,14 @@ struct PassParams
     float    barrelConst, barrelVar;
     // film
     uint32_t width, height;
-    float    sampleOffsetX, sampleOffsetY;
+    float    sampleOffsetX, sampleOffsetY;     // AA offset of pass slot 0 (used when sampleOffsets is null)
+    const float* sampleOffsets;                // batched passes: 2 floats per pass slot
     // integrator (Context.h:55-90)
     uint32_t renderer, debugMode;
     uint32_t maxRayDepth, minRussianRouletteDepth;
     uint32_t lightSamplingAll, useBlueNoise;
     uint32_t passIndex, numSeedDims;
-    const uint32_t* seed;         // numSeedDims Halton integers of this pass
+    const uint32_t* seed;         // numSeedDims Halton integers per pass slot (slot k starts at k * numSeedDims)
 };
 
 struct Sampler
@@ -34,6 +35,7 @@ struct Sampler
     uint32_t salt;
     uint32_t dim;          // mSamplesGenerated
     uint32_t bnOffset;     // 4 * (128 * (y & 127) + (x & 127))
+    uint32_t seedBase;     // passSlot * numSeedDims: which pass of a batch this pixel sample belongs to
 };
 
 // Math.h:269-277 (MurmurHash3 finalizer)
@@ -53,6 +55,7 @@ RTB_HD void sampler_reset_pixel(Sampler& s, uint32_t x, uint32_t y)
     s.bnOffset = 4u * (128u * (y & 127u) + (x & 127u));
     s.salt = (uint32_t)hash64((uint64_t)(x | (y << 16)));
     s.dim = 0;
+    s.seedBase = 0;
 }
 
 // GenericSampler::GetInt, GenericSampler.cpp:83-112.  Dimensions beyond numSeedDims fall back to a per-thread RNG in
@@ -60,7 +63,7 @@ RTB_HD void sampler_reset_pixel(Sampler& s, uint32_t x, uint32_t y)
 // start a pass whose worst-case dimension count exceeds numSeedDims (see rtb_render_pass).
 RTB_HD uint32_t sampler_get_int(Sampler& s, const PassParams& P, const uint16_t* blueNoise)
 {
-    uint32_t sample = s.dim < P.numSeedDims ? P.seed[s.dim] : 0u;
+    uint32_t sample = s.dim < P.numSeedDims ? P.seed[s.seedBase + s.dim] : 0u;
     if (s.dim < 4u && P.useBlueNoise && blueNoise != nullptr)
     {
         sample += (uint32_t)blueNoise[s.bnOffset + s.dim] << 16;
@@ -82,13 +85,13 @@ RTB_HD float sampler_get_float(Sampler& s, const PassParams& P, const uint16_t* 
 }
 
 // Viewport::RenderTile coordinates + Camera::GenerateRay.  (x, y) is the film pixel, row 0 = top.
-RTB_HD Ray generate_primary_ray(const PassParams& P, uint32_t x, uint32_t y, Sampler& s, const uint16_t* blueNoise)
+RTB_HD Ray generate_primary_ray(const PassParams& P, uint32_t x, uint32_t y, float sampleOffsetX, float sampleOffsetY, Sampler& s, const uint16_t* blueNoise)
 {
     // coords = (FromIntegers(x, realY) + sampleOffset) * (1 / filmSize)          Viewport.cpp:297-321
     const uint32_t realY = P.height - 1u - y;
     const float invW = 1.0f / (float)(int32_t)P.width, invH = 1.0f / (float)(int32_t)P.height;
-    const float cx = ((float)(int32_t)x + P.sampleOffsetX) * invW;
-    const float cy = ((float)(int32_t)realY + P.sampleOffsetY) * invH;
+    const float cx = ((float)(int32_t)x + sampleOffsetX) * invW;
+    const float cy = ((float)(int32_t)realY + sampleOffsetY) * invH;
 
     // UnipolarToBipolar = fmsub(x, 2, 1)                                           Vector4ImplSSE.h:598-601
     float ox = fma_(cx, 2.0f, -1.0f), oy = fma_(cy, 2.0f, -1.0f);

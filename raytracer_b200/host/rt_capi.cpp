@@ -98,8 +98,7 @@ int rtbh_viewport_render(void* vp, void* scene, uint32_t numPasses)
     rt::ViewportB200* v = static_cast<rt::ViewportB200*>(vp);
     rt::Camera cam = static_cast<SceneHandle*>(scene)->camera;
     cam.SetPerspective((float)v->GetWidth() / (float)v->GetHeight(), cam.mFieldOfView);
-    for (uint32_t i = 0; i < numPasses; ++i) if (!v->Render(cam)) return -1;
-    return 0;
+    return v->RenderPasses(cam, numPasses) ? 0 : -1;
 }
 
 int rtbh_viewport_synchronize(void* vp) { return static_cast<rt::ViewportB200*>(vp)->Synchronize() ? 0 : -1; }

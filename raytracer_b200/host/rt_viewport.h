@@ -258,29 +258,40 @@ public:
     }
 
     // Viewport::Render, Viewport.cpp:185-289 (asynchronous: call Synchronize / GetSumBuffer to wait)
-    bool Render(const Camera& camera)
+    bool Render(const Camera& camera) { return RenderPasses(camera, 1); }
+
+    // `count` consecutive Render() calls handed to the device at once (rtb_render_passes): the host prologue runs per
+    // pass in the reference's order, the device traces the passes in shared wavefronts and adds them to the film in
+    // pass order, so the image is the one `count` Render() calls produce.
+    bool RenderPasses(const Camera& camera, uint32_t count)
     {
         if (mWidth == 0 || mHeight == 0) return false;
         if (!mHasScene) { mError = "Viewport: Missing renderer"; return false; }
-        mHalton.NextSample();
-        std::vector<uint32_t> seed(mHalton.GetNumDimensions());
-        for (uint32_t i = 0; i < seed.size(); ++i) seed[i] = mHalton.GetInt(i);
-        // GetFloatNormal2(rng.GetFloat2()) * antiAliasingSpread
-        const float u0 = mRandom.GetFloat(), u1 = mRandom.GetFloat();
-        float s, c;
-        rtb::sin_cos(2.0f * RTB_PI * u1, s, c);
-        const float radius = sqrtf(-2.0f * FastLog(u0));
-        RtbPassDesc pass;
-        memset(&pass, 0, sizeof(pass));
-        pass.renderer = mRenderer; pass.debugMode = mDebugMode;
-        camera.Describe(pass.camera);
-        pass.maxRayDepth = mParams.maxRayDepth; pass.minRussianRouletteDepth = mParams.minRussianRouletteDepth;
-        pass.lightSamplingStrategy = mParams.lightSamplingStrategy; pass.useBlueNoise = mParams.useBlueNoiseDithering;
-        pass.passIndex = mPassesFinished; pass.numSeedDims = (uint32_t)seed.size(); pass.seed = seed.data();
-        pass.sampleOffset[0] = radius * s * mParams.antiAliasingSpread;
-        pass.sampleOffset[1] = radius * c * mParams.antiAliasingSpread;
-        if (rtb_render_pass(mCtx, &pass) != RTB_OK) return Error();
-        mPassesFinished++;
+        if (count == 0) return true;
+        const uint32_t dims = mHalton.GetNumDimensions();
+        std::vector<uint32_t> seeds((size_t)count * dims);
+        std::vector<RtbPassDesc> passes(count);
+        for (uint32_t p = 0; p < count; ++p)
+        {
+            mHalton.NextSample();                                                   // Viewport.cpp:200-205
+            for (uint32_t i = 0; i < dims; ++i) seeds[(size_t)p * dims + i] = mHalton.GetInt(i);
+            // GetFloatNormal2(rng.GetFloat2()) * antiAliasingSpread                // Viewport.cpp:235-242
+            const float u0 = mRandom.GetFloat(), u1 = mRandom.GetFloat();
+            float s, c;
+            rtb::sin_cos(2.0f * RTB_PI * u1, s, c);
+            const float radius = sqrtf(-2.0f * FastLog(u0));
+            RtbPassDesc& pass = passes[p];
+            memset(&pass, 0, sizeof(pass));
+            pass.renderer = mRenderer; pass.debugMode = mDebugMode;
+            camera.Describe(pass.camera);
+            pass.maxRayDepth = mParams.maxRayDepth; pass.minRussianRouletteDepth = mParams.minRussianRouletteDepth;
+            pass.lightSamplingStrategy = mParams.lightSamplingStrategy; pass.useBlueNoise = mParams.useBlueNoiseDithering;
+            pass.passIndex = mPassesFinished + p; pass.numSeedDims = dims; pass.seed = dims ? &seeds[(size_t)p * dims] : nullptr;
+            pass.sampleOffset[0] = radius * s * mParams.antiAliasingSpread;
+            pass.sampleOffset[1] = radius * c * mParams.antiAliasingSpread;
+        }
+        if (rtb_render_passes(mCtx, passes.data(), count) != RTB_OK) return Error();
+        mPassesFinished += count;
         return true;
     }
 

@@ -108,7 +108,7 @@ struct HostSink
     uint64_t shadowRays = 0, shadowRaysHit = 0;
     explicit HostSink(const SceneView& s) : S(s) { result = v3s(0.0f); lightSum = v4s(0.0f); }
     void add(const V4& thr, const V4& c) { result = mul_add(xyz(thr), xyz(c), result); }
-    void shadow(const Ray& ray, float tMax, const V4& contribution)
+    void shadow(const Ray& ray, float tMax, const V4& contribution, uint32_t)
     {
         shadowRays++;
         const bool occluded = scene_traverse_shadow<false>(S, ray, tMax, nullptr);
@@ -150,7 +150,7 @@ static int cmdRender(int argc, char** argv)
         for (uint32_t y = 0; y < h; ++y) for (uint32_t x = 0; x < w; ++x)
         {
             PathState ps;
-            init_path(P, world.S.blueNoise, x, y, ps);
+            init_path(P, world.S.blueNoise, x, y, 0, ps);
             HostSink sink(world.S);
             for (;;)
             {
@@ -271,7 +271,7 @@ static int cmdPrimary(int argc, char** argv)
     {
         Sampler s;
         sampler_reset_pixel(s, x, y);
-        const Ray r = generate_primary_ray(P, x, y, s, nullptr);
+        const Ray r = generate_primary_ray(P, x, y, P.sampleOffsetX, P.sampleOffsetY, s, nullptr);
         RtbRay& o = rays[(size_t)y * w + x];
         memset(&o, 0, sizeof(o));
         o.origin[0] = r.origin.x; o.origin[1] = r.origin.y; o.origin[2] = r.origin.z;

@@ -242,3 +242,22 @@ def test_gathered_shards_unshard_to_the_full_frame(ctx):
     util.assert_bit_identical(img2, full, "python unshard of the same buffers")
     for c in ctxs:
         c.close()
+
+
+@pytest.mark.parametrize("scene", ["cornell", "mesh_small"])
+def test_batched_passes_are_bit_identical_to_single_passes(ctx, scene):
+    """rtb_render_passes traces several passes in one wavefront; the film must equal pass-by-pass rendering exactly."""
+    meta = json.load(open(util.golden("%s_mis.json" % scene)))
+    w, h = meta["width"], meta["height"]
+    sf = capi.SceneFile(util.golden(scene + ".rtb"))
+    ps = capi.PassScript(util.golden(scene + ".passes"))
+    ctx.upload_scene(sf)
+    ctx.resize(w, h)
+    cam = capi.camera_for(sf, w, h)
+    ctx.render_passes(cam, ps.seeds[:meta["passes"]], ps.offsets[:meta["passes"]], 0)
+    for which, name in ((0, "sum"), (1, "sum2")):
+        want = util.load_sum(util.golden("%s_mis.%s" % (scene, name)), w, h)
+        util.assert_bit_identical(ctx.read_sum(which), want, "%s batched %s" % (scene, name))
+    c = ctx.counters()
+    assert (c["numRays"], c["numShadowRays"], c["numShadowRaysHit"], c["numPrimaryRays"]) == \
+           (meta["numRays"], meta["numShadowRays"], meta["numShadowRaysHit"], meta["numPrimaryRays"])

@@ -38,16 +38,16 @@ def main():
         cam = capi.camera_for(sf, w, h)
         ctx.set_profiling(True)
         agg = {}
-        for p in range(3):
-            ctx.render_pass(ctx.make_pass(cam, rng.integers(0, 2**32, 128, dtype=np.uint32), rng.normal(size=2) * 0.5, p))
+        nb = int(os.environ.get("QB_BATCH", "8"))
+        for p in range(2):
+            ctx.render_passes(cam, rng.integers(0, 2**32, (nb, 128), dtype=np.uint32), rng.normal(size=(nb, 2)) * 0.5, p * nb)
             t = ctx.pass_timings()
-            print("profiled pass %d: %s" % (p, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in t.items()}))
+            print("profiled %d passes: %s" % (nb, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in t.items()}))
         ctx.set_profiling(False)
         ctx.reset()
         ctx.synchronize()
         t0 = time.perf_counter()
-        for p in range(passes):
-            ctx.render_pass(ctx.make_pass(cam, rng.integers(0, 2**32, 128, dtype=np.uint32), rng.normal(size=2) * 0.5, p))
+        ctx.render_passes(cam, rng.integers(0, 2**32, (passes, 128), dtype=np.uint32), rng.normal(size=(passes, 2)) * 0.5, 0)
         ctx.synchronize()
         dt = time.perf_counter() - t0
         c = ctx.counters()
