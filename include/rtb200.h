@@ -230,6 +230,7 @@ typedef struct RtbCounters
     uint64_t numRayTriangleTests;
     uint64_t numShadowBoxTests;     /* shadow rays, same flag */
     uint64_t numShadowTriangleTests;
+    uint64_t numKernelLaunches;     /* CUDA kernels launched by rtb_render_pass(es) since the last reset */
 } RtbCounters;
 
 /* ---- batch test hooks ---------------------------------------------------------------------------- */

@@ -1,0 +1,523 @@
+/*
+ * rt_restate.c — plain C restatement of the integer / traversal core of the reference hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (part of the oracle): nothing in the product links, imports or executes this file.
+ * It shares no code with raytracer_b200/ - every function is written from the reference's algorithm and cites the
+ * reference file:line it follows.  PARITY IS PINNED: tests/test_oracle_restate.py checks every output against the
+ * golden vectors generated from the real reference (oracle/_ref/exact, see tests/golden/make_golden.py):
+ *   sampler   GenericSampler streams                      (sampler_bn.u32 / sampler_nobn.u32)
+ *   primary   Camera::GenerateRay for every pixel         (<scene>.primary)
+ *   trace     Scene::Traverse / Traverse_Shadow           (<scene>.hits / .shadow_hits)
+ *   debug     DebugRenderer TriangleID / Depth sum buffer (<scene>_dbgtri.sum / _dbgdepth.sum)
+ * The full integrator (BSDFs, lights, MIS) is NOT restated here: for it the oracle is the reference itself
+ * (oracle/_ref), whose sum buffers are the committed fixtures.
+ *
+ * Build: gcc -O2 -std=c11 -ffp-contract=off -mfma -msse4.1 (oracle/restate/build.sh).  FTZ/DAZ on, like the
+ * reference (Core/Math/Math.cpp:27-34).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <xmmintrin.h>
+#include <pmmintrin.h>
+
+#include "../../include/rtb200.h"
+
+typedef struct { float x, y, z; } vec3;
+typedef struct { vec3 o, d, inv, odd; } ray_t;           /* math::Ray, Core/Math/Ray.h:13-28 */
+typedef struct { uint32_t object, sub; float t, u, v; } hit_t;   /* HitPoint, Core/Traversal/HitPoint.h:14-51 */
+
+/* ---- scene file (RTBS, see raytracer_b200/csrc/rtb_scene_file.h for the layout; read independently here) --------- */
+typedef struct
+{
+    uint32_t numNodes, numTris, numVerts, numMats;
+    RtbBvhNode* nodes; float* tris; uint32_t* indices; float* shading; uint32_t* matIds;
+} mesh_t;
+
+typedef struct
+{
+    uint32_t numTlas, numObjects, numShapes, numMeshes, numMaterials, numLights, numGlobal;
+    RtbBvhNode* tlas; RtbObject* objects; RtbShape* shapes; mesh_t* meshes; RtbMaterial* materials; RtbLight* lights; uint32_t* global;
+    RtbCamera camera; float fov;
+} scene_t;
+
+static void die(const char* m) { fprintf(stderr, "rt_restate: %s\n", m); exit(1); }
+
+static void* read_block(FILE* f, size_t bytes)
+{
+    void* p = malloc(bytes ? bytes : 1);
+    if (bytes && fread(p, 1, bytes, f) != bytes) die("truncated scene file");
+    return p;
+}
+static uint32_t read_u32(FILE* f) { uint32_t v; if (fread(&v, 4, 1, f) != 1) die("truncated scene file"); return v; }
+
+static void load_scene(const char* path, scene_t* s)
+{
+    FILE* f = fopen(path, "rb");
+    if (!f) die("cannot open scene");
+    if (read_u32(f) != 0x53425452u || read_u32(f) != 1) die("not an RTBS v1 file");
+    s->numTlas = read_u32(f); s->tlas = read_block(f, (size_t)s->numTlas * sizeof(RtbBvhNode));
+    s->numObjects = read_u32(f); s->objects = read_block(f, (size_t)s->numObjects * sizeof(RtbObject));
+    s->numShapes = read_u32(f); s->shapes = read_block(f, (size_t)s->numShapes * sizeof(RtbShape));
+    s->numMeshes = read_u32(f);
+    s->meshes = calloc(s->numMeshes ? s->numMeshes : 1, sizeof(mesh_t));
+    for (uint32_t i = 0; i < s->numMeshes; ++i)
+    {
+        mesh_t* m = &s->meshes[i];
+        m->numNodes = read_u32(f); m->numTris = read_u32(f); m->numVerts = read_u32(f); m->numMats = read_u32(f);
+        m->nodes = read_block(f, (size_t)m->numNodes * 32); m->tris = read_block(f, (size_t)m->numTris * 36);
+        m->indices = read_block(f, (size_t)m->numTris * 16); m->shading = read_block(f, (size_t)m->numVerts * 32);
+        m->matIds = read_block(f, (size_t)m->numMats * 4);
+    }
+    s->numMaterials = read_u32(f); s->materials = read_block(f, (size_t)s->numMaterials * sizeof(RtbMaterial));
+    s->numLights = read_u32(f); s->lights = read_block(f, (size_t)s->numLights * sizeof(RtbLight));
+    s->numGlobal = read_u32(f); s->global = read_block(f, (size_t)s->numGlobal * 4);
+    if (fread(&s->camera, sizeof(RtbCamera), 1, f) != 1 || fread(&s->fov, 4, 1, f) != 1) die("truncated scene file");
+    fclose(f);
+}
+
+/* ---- SSE semantics, scalar (Core/Math/Vector4ImplSSE.h) -------------------------------------------------------- */
+static float minps(float a, float b) { return a < b ? a : b; }     /* _mm_min_ps: second operand on NaN, :388-391 */
+static float maxps(float a, float b) { return a > b ? a : b; }     /* _mm_max_ps, :393-396 */
+/* _mm_dp_ps 0x7F (:451-454): (x*x' + y*y') + (z*z' + 0) */
+static float dp3(vec3 a, vec3 b) { return (a.x * b.x + a.y * b.y) + (a.z * b.z + 0.0f); }
+/* Cross3 (:476-484): a.yzx * b.zxy, then fnmadd(a.zxy, b.yzx, .) */
+static vec3 cross(vec3 a, vec3 b)
+{
+    vec3 r = { fmaf(-a.z, b.y, a.y * b.z), fmaf(-a.x, b.z, a.z * b.x), fmaf(-a.y, b.x, a.x * b.y) };
+    return r;
+}
+static float absbits(float x) { union { float f; uint32_t u; } c; c.f = x; c.u &= 0x7fffffffu; return c.f; }
+
+/* Matrix4::TransformPoint / TransformVector (Core/Math/Matrix4.h:110-139) */
+static vec3 xform_point(const RtbMat4* m, vec3 a)
+{
+    vec3 t = { fmaf(a.x, m->r[0][0], m->r[3][0]), fmaf(a.x, m->r[0][1], m->r[3][1]), fmaf(a.x, m->r[0][2], m->r[3][2]) };
+    t.x = fmaf(a.y, m->r[1][0], t.x); t.y = fmaf(a.y, m->r[1][1], t.y); t.z = fmaf(a.y, m->r[1][2], t.z);
+    t.x = fmaf(a.z, m->r[2][0], t.x); t.y = fmaf(a.z, m->r[2][1], t.y); t.z = fmaf(a.z, m->r[2][2], t.z);
+    return t;
+}
+static vec3 xform_vector(const RtbMat4* m, vec3 a)
+{
+    vec3 t = { a.x * m->r[0][0], a.x * m->r[0][1], a.x * m->r[0][2] };
+    t.x = fmaf(a.y, m->r[1][0], t.x); t.y = fmaf(a.y, m->r[1][1], t.y); t.z = fmaf(a.y, m->r[1][2], t.z);
+    t.x = fmaf(a.z, m->r[2][0], t.x); t.y = fmaf(a.z, m->r[2][1], t.y); t.z = fmaf(a.z, m->r[2][2], t.z);
+    return t;
+}
+
+/* Ray(origin, direction) via Vector4::InvNormalized (Ray.h:23-28, Vector4Impl.h:90-98) */
+static ray_t ray_make(vec3 o, vec3 dir)
+{
+    ray_t r;
+    const float len = sqrtf(dp3(dir, dir));
+    const float ix = 1.0f / dir.x, iy = 1.0f / dir.y, iz = 1.0f / dir.z, il = 1.0f / len;
+    r.o = o;
+    r.inv.x = len * ix; r.inv.y = len * iy; r.inv.z = len * iz;
+    r.d.x = dir.x * il; r.d.y = dir.y * il; r.d.z = dir.z * il;
+    r.odd.x = o.x * r.inv.x; r.odd.y = o.y * r.inv.y; r.odd.z = o.z * r.inv.z;
+    return r;
+}
+/* Matrix4::TransformRay_Unsafe -> Ray::BuildUnsafe (Matrix4.h:245-250, Ray.h:31-39) */
+static ray_t ray_to_local(const RtbMat4* inv, const ray_t* w)
+{
+    ray_t r;
+    r.o = xform_point(inv, w->o);
+    r.d = xform_vector(inv, w->d);
+    r.inv.x = 1.0f / r.d.x; r.inv.y = 1.0f / r.d.y; r.inv.z = 1.0f / r.d.z;
+    r.odd.x = r.o.x * r.inv.x; r.odd.y = r.o.y * r.inv.y; r.odd.z = r.o.z * r.inv.z;
+    return r;
+}
+
+/* ---- intersectors (Core/Math/Geometry.h) ------------------------------------------------------------------------- */
+/* Intersect_BoxRay, :57-86: slab distances with one fmsub per plane, near = max of mins, far = min of maxes */
+static int box_ray(const ray_t* r, const float* bmin, const float* bmax, float* outNear, float* outFar)
+{
+    const float a0 = fmaf(bmin[0], r->inv.x, -r->odd.x), a1 = fmaf(bmin[1], r->inv.y, -r->odd.y), a2 = fmaf(bmin[2], r->inv.z, -r->odd.z);
+    const float b0 = fmaf(bmax[0], r->inv.x, -r->odd.x), b1 = fmaf(bmax[1], r->inv.y, -r->odd.y), b2 = fmaf(bmax[2], r->inv.z, -r->odd.z);
+    const float lo0 = minps(a0, b0), lo1 = minps(a1, b1), lo2 = minps(a2, b2);
+    const float hi0 = maxps(a0, b0), hi1 = maxps(a1, b1), hi2 = maxps(a2, b2);
+    const float tn = maxps(lo0, maxps(lo1, lo2));
+    const float tf = minps(hi0, minps(hi1, hi2));
+    *outNear = tn;
+    if (outFar) *outFar = tf;
+    return (tf >= tn) && (tf >= 0.0f);
+}
+
+/* Intersect_TriangleRay, SSE branch, :132-167: strict > 0 on u, v, t and NOT (u + v > 1); true division */
+static int tri_ray(const ray_t* r, const float* tri, float* u, float* v, float* t)
+{
+    const vec3 v0 = { tri[0], tri[1], tri[2] }, e1 = { tri[3], tri[4], tri[5] }, e2 = { tri[6], tri[7], tri[8] };
+    const vec3 tvec = { r->o.x - v0.x, r->o.y - v0.y, r->o.z - v0.z };
+    const vec3 pvec = cross(r->d, e2);
+    const vec3 qvec = cross(tvec, e1);
+    const float det = dp3(e1, pvec), uu = dp3(tvec, pvec), vv = dp3(r->d, qvec), tt = dp3(e2, qvec);
+    const float sum = (uu + vv) / det;
+    *u = uu / det; *v = vv / det; *t = tt / det;
+    return !(sum > 1.0f) && (*v > 0.0f) && (*t > 0.0f) && (*u > 0.0f);
+}
+
+/* shape Intersect: SphereShape.cpp:29-46 (double), BoxShape.cpp:118-125 + Geometry.h:100-130, RectShape.cpp:32-49 */
+static int shape_intersect(const RtbShape* s, const ray_t* r, float* nearD, float* farD, uint32_t* sub)
+{
+    *sub = 0xFFFFFFFFu;
+    if (s->type == RTB_SHAPE_SPHERE)
+    {
+        const vec3 no = { 0.0f - r->o.x, 0.0f - r->o.y, 0.0f - r->o.z };
+        const double rd = (double)s->size[0];
+        const double v = (double)dp3(r->d, no);
+        const double det = rd * rd - (double)dp3(r->o, r->o) + v * v;
+        if (det <= 0.0) return 0;
+        const double sq = sqrt(det);
+        *nearD = (float)(v - sq); *farD = (float)(v + sq); *sub = 0;
+        return *farD > *nearD;
+    }
+    if (s->type == RTB_SHAPE_BOX)
+    {
+        const float bmin[3] = { 0.0f - s->size[0], 0.0f - s->size[1], 0.0f - s->size[2] };
+        *sub = 0;
+        box_ray(r, bmin, s->size, nearD, farD);
+        return *nearD < *farD;
+    }
+    if (s->type == RTB_SHAPE_RECT)
+    {
+        const float t = -r->o.z * r->inv.z;
+        if (t > 1.1920929e-7f)
+        {
+            const float px = fmaf(r->d.x, t, r->o.x), py = fmaf(r->d.y, t, r->o.y);
+            if (absbits(px) < s->size[0] && absbits(py) < s->size[1]) { *nearD = t; *farD = t; return 1; }
+        }
+    }
+    return 0;
+}
+
+#define LEAVES(n) ((n)->leafInfo & 0x3FFFFFFFu)
+
+/* GenericTraverse<MeshShape> + MeshShape::Traverse_Leaf (Traversal_Single.h:15-96, MeshShape.cpp:134-168) */
+static void mesh_closest(const mesh_t* m, const ray_t* r, uint32_t objectId, hit_t* h)
+{
+    const RtbBvhNode* stack[128];
+    uint32_t sp = 0;
+    if (m->numNodes == 0) return;
+    for (const RtbBvhNode* cur = m->nodes;;)
+    {
+        if (LEAVES(cur) != 0)
+        {
+            for (uint32_t i = 0; i < LEAVES(cur); ++i)
+            {
+                float u, v, t;
+                const uint32_t ti = cur->childIndex + i;
+                if (tri_ray(r, m->tris + (size_t)ti * 9, &u, &v, &t) && t < h->t) { h->t = t; h->sub = ti; h->object = objectId; h->u = u; h->v = v; }
+            }
+        }
+        else
+        {
+            const RtbBvhNode* a = m->nodes + cur->childIndex;
+            const RtbBvhNode* b = a + 1;
+            float da, db;
+            int ha = box_ray(r, a->min, a->max, &da, NULL), hb = box_ray(r, b->min, b->max, &db, NULL);
+            ha &= (da < h->t); hb &= (db < h->t);
+            if (ha && hb) { if (db < da) { const RtbBvhNode* t = a; a = b; b = t; } cur = a; stack[sp++] = b; continue; }
+            if (ha) { cur = a; continue; }
+            if (hb) { cur = b; continue; }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+}
+
+/* GenericTraverse_Shadow<MeshShape> + Traverse_Leaf_Shadow (Traversal_Single.h:98-179, MeshShape.cpp:175-207) */
+static int mesh_shadow(const mesh_t* m, const ray_t* r, float tmax)
+{
+    const RtbBvhNode* stack[128];
+    uint32_t sp = 0;
+    if (m->numNodes == 0) return 0;
+    for (const RtbBvhNode* cur = m->nodes;;)
+    {
+        if (LEAVES(cur) != 0)
+        {
+            for (uint32_t i = 0; i < LEAVES(cur); ++i)
+            {
+                float u, v, t;
+                if (tri_ray(r, m->tris + (size_t)(cur->childIndex + i) * 9, &u, &v, &t) && t < tmax) return 1;
+            }
+        }
+        else
+        {
+            const RtbBvhNode* a = m->nodes + cur->childIndex;
+            const RtbBvhNode* b = a + 1;
+            float da, db;
+            int ha = box_ray(r, a->min, a->max, &da, NULL), hb = box_ray(r, b->min, b->max, &db, NULL);
+            ha &= (da < tmax); hb &= (db < tmax);
+            if (ha && hb) { cur = a; stack[sp++] = b; continue; }
+            if (ha) { cur = a; continue; }
+            if (hb) { cur = b; continue; }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+    return 0;
+}
+
+/* Scene::Traverse_Object (Scene.cpp:128-145) + IShape::Traverse (Shape.cpp:19-45) + LightSceneObject::Traverse
+ * (SceneObject_Light.cpp:27-38) */
+static void object_closest(const scene_t* s, const ray_t* world, uint32_t id, hit_t* h)
+{
+    const RtbObject* o = &s->objects[id];
+    const ray_t r = ray_to_local(&o->invTransform, world);
+    if (o->shapeIndex == 0xFFFFFFFFu) return;                       /* point / spot light: TestRayHit is false */
+    const RtbShape* sh = &s->shapes[o->shapeIndex];
+    if (o->kind == RTB_OBJECT_SHAPE && sh->type == RTB_SHAPE_MESH) { mesh_closest(&s->meshes[sh->meshIndex], &r, id, h); return; }
+    float n, f; uint32_t sub;
+    if (!shape_intersect(sh, &r, &n, &f, &sub)) return;
+    if (o->kind == RTB_OBJECT_LIGHT) { if (n > 0.0f && n < h->t) { h->t = n; h->object = id; h->sub = RTB_LIGHT_OBJECT; } return; }
+    if (n > 0.0f && n < h->t) { h->t = n; h->object = id; h->sub = sub; return; }
+    if (f > 0.0f && f < h->t) { h->t = f; h->object = id; h->sub = sub; }
+}
+
+/* Scene::Traverse_Object_Shadow (Scene.cpp:147-165) + IShape::Traverse_Shadow (Shape.cpp:47-57) +
+ * LightSceneObject::Traverse_Shadow (SceneObject_Light.cpp:40-53) */
+static int object_shadow(const scene_t* s, const ray_t* world, uint32_t id, float tmax)
+{
+    const RtbObject* o = &s->objects[id];
+    const ray_t r = ray_to_local(&o->invTransform, world);
+    if (o->shapeIndex == 0xFFFFFFFFu) return 0;
+    const RtbShape* sh = &s->shapes[o->shapeIndex];
+    if (o->kind == RTB_OBJECT_SHAPE && sh->type == RTB_SHAPE_MESH) return mesh_shadow(&s->meshes[sh->meshIndex], &r, tmax);
+    float n, f; uint32_t sub;
+    if (!shape_intersect(sh, &r, &n, &f, &sub)) return 0;
+    if (o->kind == RTB_OBJECT_LIGHT) return n < tmax;
+    return f > 0.0f && n < tmax;
+}
+
+/* Scene::Traverse (Scene.cpp:219-243): 1-object bypass, else GenericTraverse<Scene> + Scene::Traverse_Leaf */
+static void scene_closest(const scene_t* s, const ray_t* r, hit_t* h)
+{
+    const RtbBvhNode* stack[128];
+    uint32_t sp = 0;
+    if (s->numObjects == 0) return;
+    if (s->numObjects == 1) { object_closest(s, r, 0, h); return; }
+    if (s->numTlas == 0) return;
+    for (const RtbBvhNode* cur = s->tlas;;)
+    {
+        if (LEAVES(cur) != 0)
+        {
+            for (uint32_t i = 0; i < LEAVES(cur); ++i) object_closest(s, r, cur->childIndex + i, h);
+        }
+        else
+        {
+            const RtbBvhNode* a = s->tlas + cur->childIndex;
+            const RtbBvhNode* b = a + 1;
+            float da, db;
+            int ha = box_ray(r, a->min, a->max, &da, NULL), hb = box_ray(r, b->min, b->max, &db, NULL);
+            ha &= (da < h->t); hb &= (db < h->t);
+            if (ha && hb) { if (db < da) { const RtbBvhNode* t = a; a = b; b = t; } cur = a; stack[sp++] = b; continue; }
+            if (ha) { cur = a; continue; }
+            if (hb) { cur = b; continue; }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+}
+
+/* Scene::Traverse_Shadow (Scene.cpp:245-261) */
+static int scene_shadow(const scene_t* s, const ray_t* r, float tmax)
+{
+    const RtbBvhNode* stack[128];
+    uint32_t sp = 0;
+    if (s->numObjects == 0) return 0;
+    if (s->numObjects == 1) return object_shadow(s, r, 0, tmax);
+    if (s->numTlas == 0) return 0;
+    for (const RtbBvhNode* cur = s->tlas;;)
+    {
+        if (LEAVES(cur) != 0)
+        {
+            for (uint32_t i = 0; i < LEAVES(cur); ++i) if (object_shadow(s, r, cur->childIndex + i, tmax)) return 1;
+        }
+        else
+        {
+            const RtbBvhNode* a = s->tlas + cur->childIndex;
+            const RtbBvhNode* b = a + 1;
+            float da, db;
+            int ha = box_ray(r, a->min, a->max, &da, NULL), hb = box_ray(r, b->min, b->max, &db, NULL);
+            ha &= (da < tmax); hb &= (db < tmax);
+            if (ha && hb) { cur = a; stack[sp++] = b; continue; }
+            if (ha) { cur = a; continue; }
+            if (hb) { cur = b; continue; }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+    return 0;
+}
+
+/* ---- sampler (Core/Sampling/GenericSampler.cpp:56-112) + MurmurHash3 finalizer (Core/Math/Math.h:269-277) ------- */
+static uint64_t murmur64(uint64_t h) { h ^= h >> 33; h *= 0xff51afd7ed558ccdULL; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 33; return h; }
+typedef struct { uint32_t salt, generated, bx, by; } sampler_t;
+static void sampler_reset(sampler_t* s, uint32_t x, uint32_t y) { s->bx = x & 127u; s->by = y & 127u; s->salt = (uint32_t)murmur64((uint64_t)(x | (y << 16))); s->generated = 0; }
+static uint32_t sampler_int(sampler_t* s, const uint32_t* seed, uint32_t dims, const uint16_t* blue)
+{
+    uint32_t v = s->generated < dims ? seed[s->generated] : 0u;
+    if (blue && s->generated < 4u) v += (uint32_t)blue[4u * (128u * s->by + s->bx) + s->generated] << 16;
+    else { uint32_t x = s->salt; v += x; x ^= x << 13; x ^= x >> 17; x ^= x << 5; s->salt = x; }
+    s->generated++;
+    return v;
+}
+
+/* Viewport::RenderTile coordinates (Viewport.cpp:297-321) + Camera::GenerateRay without DOF (Camera.cpp:81-118) */
+static ray_t primary_ray(const RtbCamera* c, uint32_t w, uint32_t h, uint32_t x, uint32_t y, float offx, float offy)
+{
+    const float aspect = (float)w / (float)h;
+    const float cx = ((float)(int32_t)x + offx) * (1.0f / (float)(int32_t)w);
+    const float cy = ((float)(int32_t)(h - 1u - y) + offy) * (1.0f / (float)(int32_t)h);
+    const float ox = fmaf(cx, 2.0f, -1.0f), oy = fmaf(cy, 2.0f, -1.0f);          /* UnipolarToBipolar = fmsub(x, 2, 1) */
+    const float sx = ox * aspect;
+    const float (*m)[4] = c->localToWorld.r;
+    vec3 dir;
+    dir.x = fmaf(fmaf(m[0][0], sx, m[1][0] * oy), c->tanHalfFoV, m[2][0]);
+    dir.y = fmaf(fmaf(m[0][1], sx, m[1][1] * oy), c->tanHalfFoV, m[2][1]);
+    dir.z = fmaf(fmaf(m[0][2], sx, m[1][2] * oy), c->tanHalfFoV, m[2][2]);
+    const vec3 o = { m[3][0], m[3][1], m[3][2] };
+    return ray_make(o, dir);
+}
+
+/* HSVtoRGB (Core/Color/ColorHelpers.h:134-156) + DebugRenderer TriangleID / Depth (DebugRenderer.cpp:94-108) */
+static void debug_color(uint32_t mode, const hit_t* h, float* rgb)
+{
+    rgb[0] = rgb[1] = rgb[2] = 0.0f;
+    if (h->t == INFINITY) return;
+    if (h->sub == RTB_LIGHT_OBJECT) { rgb[0] = 1.0f; rgb[1] = 1.0f; return; }
+    if (mode == 2) { const float d = 1.0f - 1.0f / (1.0f + h->t / 10.0f); rgb[0] = rgb[1] = rgb[2] = d; return; }
+    const uint64_t k = murmur64((uint64_t)h->object | ((uint64_t)h->sub << 32));
+    const float hue = (float)(uint32_t)k / (float)UINT32_MAX;
+    const float sat = 0.5f + 0.5f * (float)(uint32_t)(k >> 32) / (float)UINT32_MAX;
+    const float val = 1.0f;
+    const int hi = (int)(hue * 6.0f);
+    const float f = hue * 6 - hi, p = val * (1 - sat), q = val * (1 - f * sat), t = val * (1 - (1 - f) * sat);
+    switch (hi)
+    {
+    case 0: rgb[0] = val; rgb[1] = t; rgb[2] = p; break;
+    case 1: rgb[0] = q; rgb[1] = val; rgb[2] = p; break;
+    case 2: rgb[0] = p; rgb[1] = val; rgb[2] = t; break;
+    case 3: rgb[0] = p; rgb[1] = q; rgb[2] = val; break;
+    case 4: rgb[0] = t; rgb[1] = p; rgb[2] = val; break;
+    case 5: rgb[0] = val; rgb[1] = p; rgb[2] = q; break;
+    default: break;
+    }
+}
+
+/* ---- pass script (seeds + AA offsets, written by rtref render --dump-passes) ------------------------------------ */
+typedef struct { uint32_t passes, dims; uint32_t* seeds; float* offsets; } passes_t;
+static void load_passes(const char* path, passes_t* p)
+{
+    FILE* f = fopen(path, "rb");
+    if (!f) die("cannot open pass script");
+    p->passes = read_u32(f); p->dims = read_u32(f);
+    p->seeds = malloc((size_t)p->passes * p->dims * 4 + 4); p->offsets = malloc((size_t)p->passes * 8 + 4);
+    for (uint32_t i = 0; i < p->passes; ++i)
+    {
+        if (fread(p->seeds + (size_t)i * p->dims, 4, p->dims, f) != p->dims || fread(p->offsets + 2 * i, 4, 2, f) != 2) die("bad pass script");
+    }
+    fclose(f);
+}
+
+static ray_t ray_from_file(const RtbRay* r)
+{
+    ray_t o;
+    o.o.x = r->origin[0]; o.o.y = r->origin[1]; o.o.z = r->origin[2];
+    o.d.x = r->dir[0]; o.d.y = r->dir[1]; o.d.z = r->dir[2];
+    o.inv.x = r->invDir[0]; o.inv.y = r->invDir[1]; o.inv.z = r->invDir[2];
+    o.odd.x = r->originDivDir[0]; o.odd.y = r->originDivDir[1]; o.odd.z = r->originDivDir[2];
+    return o;
+}
+
+int main(int argc, char** argv)
+{
+    _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);
+    _MM_SET_DENORMALS_ZERO_MODE(_MM_DENORMALS_ZERO_ON);
+    if (argc < 2) die("usage: rt_restate trace|sampler|primary|debug ...");
+
+    if (!strcmp(argv[1], "trace") && argc >= 5)
+    {
+        /* trace <scene.rtb> <rays> <out.hits> [tmax file -> shadow mode] */
+        scene_t s; load_scene(argv[2], &s);
+        FILE* f = fopen(argv[3], "rb"); if (!f) die("cannot open rays");
+        fseek(f, 0, SEEK_END); const size_t n = (size_t)ftell(f) / sizeof(RtbRay); fseek(f, 0, SEEK_SET);
+        RtbRay* rays = malloc(n * sizeof(RtbRay) + 1);
+        if (fread(rays, sizeof(RtbRay), n, f) != n) die("read failed");
+        fclose(f);
+        float* tmax = NULL;
+        if (argc > 5) { tmax = malloc(n * 4 + 4); FILE* t = fopen(argv[5], "rb"); if (!t || fread(tmax, 4, n, t) != n) die("cannot read tmax"); fclose(t); }
+        RtbHit* hits = calloc(n ? n : 1, sizeof(RtbHit));
+        for (size_t i = 0; i < n; ++i)
+        {
+            const ray_t r = ray_from_file(&rays[i]);
+            hit_t h = { RTB_INVALID_OBJECT, 0, INFINITY, 0.0f, 0.0f };
+            if (tmax) { h.t = tmax[i]; hits[i].occluded = (uint32_t)scene_shadow(&s, &r, tmax[i]); }
+            else scene_closest(&s, &r, &h);
+            hits[i].objectId = h.object; hits[i].subObjectId = h.sub; hits[i].distance = h.t; hits[i].u = h.u; hits[i].v = h.v;
+        }
+        FILE* o = fopen(argv[4], "wb"); fwrite(hits, sizeof(RtbHit), n, o); fclose(o);
+        return 0;
+    }
+    if (!strcmp(argv[1], "sampler") && argc >= 8)
+    {
+        /* sampler <passes> <w> <h> <numDims> <out> <interleaved blue noise file | -> */
+        passes_t p; load_passes(argv[2], &p);
+        const uint32_t w = (uint32_t)atoi(argv[3]), h = (uint32_t)atoi(argv[4]), nd = (uint32_t)atoi(argv[5]);
+        uint16_t* blue = NULL;
+        if (strcmp(argv[7], "-")) { blue = malloc(128 * 128 * 4 * 2); FILE* b = fopen(argv[7], "rb"); if (!b || fread(blue, 2, 128 * 128 * 4, b) != 128 * 128 * 4) die("bad blue noise"); fclose(b); }
+        FILE* o = fopen(argv[6], "wb");
+        for (uint32_t i = 0; i < p.passes; ++i)
+            for (uint32_t y = 0; y < h; ++y) for (uint32_t x = 0; x < w; ++x)
+            {
+                sampler_t s; sampler_reset(&s, x, y);
+                for (uint32_t d = 0; d < nd; ++d) { const uint32_t v = sampler_int(&s, p.seeds + (size_t)i * p.dims, p.dims, blue); fwrite(&v, 4, 1, o); }
+            }
+        fclose(o);
+        return 0;
+    }
+    if ((!strcmp(argv[1], "primary") || !strcmp(argv[1], "debug")) && argc >= 8)
+    {
+        /* primary <scene> <passes> <pass> <w> <h> <out.rays>      debug <scene> <passes> <mode 1|2> <w> <h> <out.sum> */
+        scene_t s; load_scene(argv[2], &s);
+        passes_t p; load_passes(argv[3], &p);
+        const uint32_t arg = (uint32_t)atoi(argv[4]), w = (uint32_t)atoi(argv[5]), h = (uint32_t)atoi(argv[6]);
+        FILE* o = fopen(argv[7], "wb");
+        if (!strcmp(argv[1], "primary"))
+        {
+            for (uint32_t y = 0; y < h; ++y) for (uint32_t x = 0; x < w; ++x)
+            {
+                const ray_t r = primary_ray(&s.camera, w, h, x, y, p.offsets[2 * arg], p.offsets[2 * arg + 1]);
+                RtbRay out; memset(&out, 0, sizeof(out));
+                out.origin[0] = r.o.x; out.origin[1] = r.o.y; out.origin[2] = r.o.z;
+                out.dir[0] = r.d.x; out.dir[1] = r.d.y; out.dir[2] = r.d.z;
+                out.invDir[0] = r.inv.x; out.invDir[1] = r.inv.y; out.invDir[2] = r.inv.z;
+                out.originDivDir[0] = r.odd.x; out.originDivDir[1] = r.odd.y; out.originDivDir[2] = r.odd.z;
+                fwrite(&out, sizeof(out), 1, o);
+            }
+        }
+        else
+        {
+            /* DebugRenderer over all passes of the script, Film::AccumulateColor sum (Film.cpp:31-39) */
+            float* sum = calloc((size_t)w * h * 3, 4);
+            for (uint32_t i = 0; i < p.passes; ++i)
+                for (uint32_t y = 0; y < h; ++y) for (uint32_t x = 0; x < w; ++x)
+                {
+                    const ray_t r = primary_ray(&s.camera, w, h, x, y, p.offsets[2 * i], p.offsets[2 * i + 1]);
+                    hit_t hit = { RTB_INVALID_OBJECT, 0, INFINITY, 0.0f, 0.0f };
+                    scene_closest(&s, &r, &hit);
+                    float rgb[3];
+                    debug_color(arg, &hit, rgb);
+                    float* px = sum + ((size_t)y * w + x) * 3;
+                    px[0] = px[0] + rgb[0]; px[1] = px[1] + rgb[1]; px[2] = px[2] + rgb[2];
+                }
+            fwrite(sum, 4, (size_t)w * h * 3, o);
+        }
+        fclose(o);
+        return 0;
+    }
+    die("bad arguments");
+    return 2;
+}

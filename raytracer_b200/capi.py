@@ -85,7 +85,7 @@ class RtbPassDesc(C.Structure):
 class RtbCounters(C.Structure):
     _fields_ = [("numRays", C.c_uint64), ("numShadowRays", C.c_uint64), ("numShadowRaysHit", C.c_uint64),
                 ("numPrimaryRays", C.c_uint64), ("numRayBoxTests", C.c_uint64), ("numRayTriangleTests", C.c_uint64),
-                ("numShadowBoxTests", C.c_uint64), ("numShadowTriangleTests", C.c_uint64)]
+                ("numShadowBoxTests", C.c_uint64), ("numShadowTriangleTests", C.c_uint64), ("numKernelLaunches", C.c_uint64)]
 
 
 class RtbCreateDesc(C.Structure):

@@ -858,6 +858,7 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
     if (prof) marks.push_back(next_event(c, ev));
     RTB_CUDA(cudaGetLastError());
     c->counters.numPrimaryRays += (uint64_t)c->numPixels * batch;     // Viewport.cpp:429
+    c->counters.numKernelLaunches += 2u + (depthLimit + 1u) * (shadows ? 4u : 2u);
     c->passesSinceReset += batch;
 
     if (prof)
