@@ -27,7 +27,16 @@ struct Hit
 
 struct TraceCounters { uint32_t boxTests, triTests; };
 
-#define RTB_STACK_SIZE 64      // BVH::MaxDepth is 128 (BVH.h:20); upload verifies the real depth of every tree fits
+#define RTB_STACK_SIZE 64
+#ifndef RTB_LDG256
+#define RTB_LDG256 1
+#endif
+#ifndef RTB_SHADOW_POSTPONE
+#define RTB_SHADOW_POSTPONE 1
+#endif
+#ifndef RTB_SHADOW_NEAR_FIRST
+#define RTB_SHADOW_NEAR_FIRST 1
+#endif      // BVH::MaxDepth is 128 (BVH.h:20); upload verifies the real depth of every tree fits
 
 // Intersect_BoxRay, Geometry.h:57-86
 RTB_HD bool box_ray(const Ray& ray, float minx, float miny, float minz, float maxx, float maxy, float maxz, float& outDistance)
@@ -164,7 +173,15 @@ RTB_HD void load_tri(const DTri* tris, uint32_t index, V3& v0, V3& e1, V3& e2)
 
 RTB_HD DNode load_node(const DNode* nodes, uint32_t index)
 {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && RTB_LDG256
+    // one 256-bit load per node (LDG.E.ENL2.256, sm_100+): the traversal kernels are bound by L1 data-pipe wavefronts
+    // (70-80 % of peak in ncu), and a divergent lane costs one wavefront per load instruction whatever its width
+    DNode n;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(n.minx), "=f"(n.miny), "=f"(n.minz), "=r"(n.childIndex), "=f"(n.maxx), "=f"(n.maxy), "=f"(n.maxz), "=r"(n.leafInfo)
+        : "l"(nodes + index));
+    return n;
+#elif defined(__CUDA_ARCH__)
     const float4* p = reinterpret_cast<const float4*>(nodes + index);
     const float4 a = __ldg(p), b = __ldg(p + 1);
     DNode n;
@@ -245,6 +262,7 @@ RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, Tr
     StackEntry stack[RTB_STACK_SIZE];
     uint32_t stackSize = 0;
     uint32_t blasBase = 0;
+    uint32_t popFloor = RTB_STACK_SIZE;     // entries above it are plain nodes of the mesh being traversed
     bool inBlas = false;
     const DNode* nodes = S.tlas;
     const DTri* tris = nullptr;
@@ -293,6 +311,13 @@ RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, Tr
             }
             else if (hitA) { curChild = a.childIndex; curInfo = a.leafInfo; }
             else if (hitB) { curChild = b.childIndex; curInfo = b.leafInfo; }
+            else if (stackSize > popFloor)
+            {
+                // both children missed: take the next pending node of this mesh right here, so that the lane stays in
+                // the inner loop with the rest of its warp instead of idling until every lane has left it
+                const StackEntry e = stack[--stackSize];
+                curChild = e.a; curInfo = e.b;
+            }
             else have = false;
         }
 
@@ -334,7 +359,7 @@ RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, Tr
         if (inBlas && stackSize == blasBase)
         {
             // mesh finished: back to the top level with the world-space ray
-            inBlas = false; nodes = S.tlas; ray = worldRay; finite = worldFinite;
+            inBlas = false; popFloor = RTB_STACK_SIZE; nodes = S.tlas; ray = worldRay; finite = worldFinite;
         }
         if (stackSize == 0) break;
         const StackEntry e = stack[--stackSize];
@@ -349,7 +374,7 @@ RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, Tr
                 const DMesh& mesh = S.meshes[obj.meshIndex];
                 if (mesh.numNodes != 0)
                 {
-                    inBlas = true; blasBase = stackSize; nodes = mesh.nodes; tris = mesh.tris; ray = localRay; finite = ray_is_finite(localRay);
+                    inBlas = true; blasBase = stackSize; popFloor = stackSize; nodes = mesh.nodes; tris = mesh.tris; ray = localRay; finite = ray_is_finite(localRay);
                     node_header(nodes, 0, curChild, curInfo);
                     have = true;
                 }
@@ -376,6 +401,7 @@ RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float
     StackEntry stack[RTB_STACK_SIZE];
     uint32_t stackSize = 0;
     uint32_t blasBase = 0;
+    uint32_t popFloor = RTB_STACK_SIZE;     // entries above it are plain nodes of the mesh being traversed
     bool inBlas = false;
     const DNode* nodes = S.tlas;
     const DTri* tris = nullptr;
@@ -388,10 +414,32 @@ RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float
     if (S.numObjects == 1) { stack[0].a = 0u; stack[0].b = RTB_ENTRY_OBJECT; stackSize = 1; }
     else if (S.numTlasNodes != 0) { node_header(S.tlas, 0, curChild, curInfo); have = true; }
 
+#if RTB_SHADOW_POSTPONE
+    uint32_t pendChild = 0, pendInfo = 0;   // a mesh leaf whose triangle tests are postponed (any-hit: order is free)
+#endif
     for (;;)
     {
+        // (the two loop forms compile to very different reconvergence code: with `while (have) { if (leaf) break; ... }`
+        //  and no postponing, k_shadow measured 35 % slower than with the plain condition below)
+#if RTB_SHADOW_POSTPONE
+        while (have)
+        {
+            if (RTB_NUM_LEAVES(curInfo) != 0)
+            {
+                // keep the lane in the node loop past its first leaf: fewer, fuller leaf phases per warp
+                if (inBlas && pendInfo == 0 && stackSize > popFloor)
+                {
+                    pendChild = curChild; pendInfo = curInfo;
+                    const StackEntry e = stack[--stackSize];
+                    curChild = e.a; curInfo = e.b;
+                    continue;
+                }
+                break;
+            }
+#else
         while (have && RTB_NUM_LEAVES(curInfo) == 0)
         {
+#endif
             const DNode a = load_node(nodes, curChild);
             const DNode b = load_node(nodes, curChild + 1);
             float distanceA, distanceB;
@@ -411,15 +459,47 @@ RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float
             if (kCount) cnt->boxTests += 2;
             if (hitA && hitB)
             {
+#if RTB_SHADOW_NEAR_FIRST
+                // any-hit: the visiting order is free (see above); the nearer child is the likelier occluder
+                const bool swap = distanceB < distanceA;
+                StackEntry e; e.a = swap ? a.childIndex : b.childIndex; e.b = swap ? a.leafInfo : b.leafInfo;
+                stack[stackSize++] = e;
+                curChild = swap ? b.childIndex : a.childIndex; curInfo = swap ? b.leafInfo : a.leafInfo;
+#else
                 StackEntry e; e.a = b.childIndex; e.b = b.leafInfo;
                 stack[stackSize++] = e;
                 curChild = a.childIndex; curInfo = a.leafInfo;
+#endif
             }
             else if (hitA) { curChild = a.childIndex; curInfo = a.leafInfo; }
             else if (hitB) { curChild = b.childIndex; curInfo = b.leafInfo; }
+            else if (stackSize > popFloor)
+            {
+                // both children missed: take the next pending node of this mesh right here, so that the lane stays in
+                // the inner loop with the rest of its warp instead of idling until every lane has left it
+                const StackEntry e = stack[--stackSize];
+                curChild = e.a; curInfo = e.b;
+            }
             else have = false;
         }
 
+#if RTB_SHADOW_POSTPONE
+        if (pendInfo != 0)
+        {
+            const uint32_t numLeaves = RTB_NUM_LEAVES(pendInfo);
+            if (kCount) cnt->triTests += numLeaves;
+            bool occluded = false;
+            for (uint32_t i = 0; i < numLeaves; ++i)
+            {
+                V3 v0, e1, e2;
+                load_tri(tris, pendChild + i, v0, e1, e2);
+                float u, v, distance;
+                if (triangle_ray(ray, v0, e1, e2, u, v, distance) && distance < maxDistance) occluded = true;
+            }
+            if (occluded) return true;
+            pendInfo = 0;
+        }
+#endif
         if (have)
         {
             const uint32_t numLeaves = RTB_NUM_LEAVES(curInfo);
@@ -446,7 +526,7 @@ RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float
 
         if (inBlas && stackSize == blasBase)
         {
-            inBlas = false; nodes = S.tlas; ray = worldRay; finite = worldFinite;
+            inBlas = false; popFloor = RTB_STACK_SIZE; nodes = S.tlas; ray = worldRay; finite = worldFinite;
         }
         if (stackSize == 0) break;
         const StackEntry e = stack[--stackSize];
@@ -460,7 +540,7 @@ RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float
                 const DMesh& mesh = S.meshes[obj.meshIndex];
                 if (mesh.numNodes != 0)
                 {
-                    inBlas = true; blasBase = stackSize; nodes = mesh.nodes; tris = mesh.tris; ray = localRay; finite = ray_is_finite(localRay);
+                    inBlas = true; blasBase = stackSize; popFloor = stackSize; nodes = mesh.nodes; tris = mesh.tris; ray = localRay; finite = ray_is_finite(localRay);
                     node_header(nodes, 0, curChild, curInfo);
                     have = true;
                 }

@@ -1,6 +1,7 @@
 """Host-side statement of the multi-GPU film decomposition used by rtb_resize (raytracer_b200/csrc/rtb_kernels.cu):
 tile t (row-major over the grid of tile_size x tile_size tiles, RenderingParams::tileSize = 32 in the reference,
-Context.h:76) belongs to shard t % num_shards; inside a tile pixels are row-major; every shard is padded to the same
+Context.h:76) belongs to shard t % num_shards; inside a tile pixels go in 8x4 blocks (row-major over
+the blocks and inside a block, one warp per block); every shard is padded to the same
 number of slots so ONE all-gather of equal-sized buffers reassembles the frame."""
 import numpy as np
 
@@ -11,9 +12,12 @@ def shard_pixel_lists(width, height, num_shards, tile_size=32):
     lists = [[] for _ in range(num_shards)]
     for ty in range(tiles_y):
         for tx in range(tiles_x):
-            ys = np.arange(ty * tile_size, min((ty + 1) * tile_size, height))
-            xs = np.arange(tx * tile_size, min((tx + 1) * tile_size, width))
-            lists[(ty * tiles_x + tx) % num_shards].append((ys[:, None] * width + xs[None, :]).ravel())
+            y1, x1 = min((ty + 1) * tile_size, height), min((tx + 1) * tile_size, width)
+            for by in range(ty * tile_size, y1, 4):
+                for bx in range(tx * tile_size, x1, 8):
+                    ys = np.arange(by, min(by + 4, y1))
+                    xs = np.arange(bx, min(bx + 8, x1))
+                    lists[(ty * tiles_x + tx) % num_shards].append((ys[:, None] * width + xs[None, :]).ravel())
     out = [np.concatenate(l).astype(np.uint32) if l else np.zeros(0, np.uint32) for l in lists]
     slots = max(len(o) for o in out)
     return out, slots
