@@ -36,6 +36,9 @@ using namespace rtb;
 
 // 64 registers -> 8 CTAs of 128 threads per SM: the traversal kernels are latency bound, occupancy is worth more than
 // the few spilled bytes (measured: 72 regs / 7 CTAs 4.4 ms, 64 regs / 8 CTAs 3.6 ms per pass for k_traverse)
+#ifndef RTB_SHADE_MINBLOCKS
+#define RTB_SHADE_MINBLOCKS 6     // measured k_shade per 8 passes: 4 CTAs/SM (128 regs) 9.13 ms, 5: 8.81, 6 (80 regs): 8.20, 8: 8.60
+#endif
 #ifndef RTB_TRAV_MINBLOCKS
 #define RTB_TRAV_MINBLOCKS 8
 #endif
@@ -54,6 +57,7 @@ struct Control
     uint32_t pathCount[RTB_MAX_DEPTH_SLOTS + 2];     // live paths entering depth d
     uint32_t shadowPathCount[RTB_MAX_DEPTH_SLOTS + 2];
     uint32_t shadowRayCount[RTB_MAX_DEPTH_SLOTS + 2];
+    uint32_t shadowCursor[RTB_MAX_DEPTH_SLOTS + 2];   // next unfetched entry of rayList (k_shadow's dynamic fetch)
     unsigned long long numRays, numShadowRays, numShadowRaysHit, numBoxTests, numTriTests, numShadowBoxTests, numShadowTriTests;
 };
 
@@ -184,7 +188,7 @@ struct DeviceSink
     __device__ void end_lights(const V4& thr) { lightThr = thr; }
 };
 
-__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const __grid_constant__ Wavefront W, uint32_t depth)
+__global__ void __launch_bounds__(128, RTB_SHADE_MINBLOCKS) k_shade(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const __grid_constant__ Wavefront W, uint32_t depth)
 {
     const uint32_t count = W.ctl->pathCount[depth];
     const PathBuf& in = W.buf[depth & 1];
@@ -263,14 +267,70 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ SceneView
     if (lane == 0 && shadowRaysLocal) atomicAdd(&W.ctl->numShadowRays, shadowRaysLocal);
 }
 
+// RTB_SHADOW_REFILL = n > 0: persistent warps that fetch new shadow rays when at least n lanes are idle.  Measured on the
+// bench scene (k_shadow + k_resolve per 8 passes): no refill 33.2 ms, n = 24: 33.0, 16: 33.6, 8: 37.0, 4: 38.3, 1: 38.4.
+// Fuller warps do not help: the kernel is bound by L1 data-pipe wavefronts and L2 latency (ncu: l1tex wavefronts
+// 65-70 % of peak at 10-12 active lanes), and mixed-age rays lose the shared top-of-tree fetches.  Kept off.
+#ifndef RTB_SHADOW_REFILL
+#define RTB_SHADOW_REFILL 0
+#endif
+
 template <bool kCount>
 __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid_constant__ SceneView S, const __grid_constant__ Wavefront W, uint32_t depth)
 {
     const uint32_t count = W.ctl->shadowRayCount[depth];
-    const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
     unsigned long long visibleLocal = 0;
     TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
+#if RTB_SHADOW_REFILL
+    // persistent warps with dynamic fetch (experiment, see above)
+    ShadowWalk walk;
+    StackEntry stack[RTB_STACK_SIZE];
+    bool active = false, exhausted = false;
+    uint32_t j = 0;
+    for (;;)
+    {
+        const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
+        if (!exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= RTB_SHADOW_REFILL))
+        {
+            const uint32_t want = __popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&W.ctl->shadowCursor[depth], want);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            exhausted = base + want >= count;
+            if (!active)
+            {
+                const uint32_t k = base + __popc(idle & ((1u << lane) - 1u));
+                if (k < count)
+                {
+                    j = W.rayList[k];
+                    const float4 a = W.sr0[j], b = W.sr1[j], c = W.sr2[j], d = W.sr3[j];
+                    Ray ray;
+                    ray.origin = v3(a.x, a.y, a.z); ray.dir = v3(b.x, b.y, b.z); ray.invDir = v3(c.x, c.y, c.z); ray.originDivDir = v3(d.x, d.y, d.z);
+                    if (walk.begin(S, stack, ray, a.w)) active = true;
+                    else visibleLocal++;
+                }
+            }
+        }
+        if (__ballot_sync(0xFFFFFFFFu, active) == 0u)
+        {
+            if (exhausted) break;
+            continue;
+        }
+        if (active)
+        {
+            const int r = walk.step<kCount>(S, stack, &cnt);
+            if (r != ShadowWalk::kContinue)
+            {
+                active = false;
+                // SampleLight returns RayColor::Zero() for an occluded light (PathTracerMIS.cpp:92-96)
+                if (r == ShadowWalk::kOccluded) { W.sr1[j].w = 0.0f; W.sr2[j].w = 0.0f; W.sr3[j].w = 0.0f; }
+                else visibleLocal++;
+            }
+        }
+    }
+#else
+    const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
     {
         const uint32_t j = W.rayList[k];
@@ -285,6 +345,7 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
         }
         else visibleLocal++;
     }
+#endif
     for (int o = 16; o > 0; o >>= 1) visibleLocal += __shfl_down_sync(0xFFFFFFFFu, visibleLocal, o);
     if (lane == 0 && visibleLocal) atomicAdd(&W.ctl->numShadowRaysHit, visibleLocal);
     if (kCount)
@@ -853,8 +914,10 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
         if (prof) marks.push_back(next_event(c, ev));
         if (shadows)
         {
-            if (count) k_shadow<true><<<blocks128, 128, 0, s>>>(c->view, W, d);
-            else k_shadow<false><<<blocks128, 128, 0, s>>>(c->view, W, d);
+            // resident warps only: they fetch rays dynamically until the list is empty
+            const int shadowBlocks = RTB_SHADOW_REFILL ? c->numSMs * RTB_TRAV_MINBLOCKS : blocks128;
+            if (count) k_shadow<true><<<shadowBlocks, 128, 0, s>>>(c->view, W, d);
+            else k_shadow<false><<<shadowBlocks, 128, 0, s>>>(c->view, W, d);
             k_resolve<<<blocks256, 256, 0, s>>>(W, d);
         }
         if (prof) marks.push_back(next_event(c, ev));

@@ -31,9 +31,6 @@ struct TraceCounters { uint32_t boxTests, triTests; };
 #ifndef RTB_LDG256
 #define RTB_LDG256 1
 #endif
-#ifndef RTB_SHADOW_POSTPONE
-#define RTB_SHADOW_POSTPONE 1
-#endif
 #ifndef RTB_SHADOW_NEAR_FIRST
 #define RTB_SHADOW_NEAR_FIRST 1
 #endif      // BVH::MaxDepth is 128 (BVH.h:20); upload verifies the real depth of every tree fits
@@ -391,42 +388,70 @@ RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, Tr
     }
 }
 
-// Scene::Traverse_Shadow (Scene.cpp:245-261), same flattening.  The result is a boolean "any triangle / shape closer
-// than maxDistance among the leaves whose ancestors pass the box test", which does not depend on the visiting order;
-// the reference's A-then-B order (Traversal_Single.h:151-156) is kept anyway.
-template <bool kCount>
-RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float maxDistance, TraceCounters* cnt)
+// Scene::Traverse_Shadow (Scene.cpp:245-261), same flattening, as a resumable walk: begin() + step() until done.
+// The result is a boolean "any triangle / shape closer than maxDistance among the leaves whose ancestors pass the box
+// test".  It does not depend on the visiting order, so this any-hit walk is free to (a) descend into the NEARER child
+// first (the reference goes A then B, Traversal_Single.h:151-156) and (b) postpone the triangle tests of one leaf
+// and keep walking nodes, which gives fewer and fuller leaf phases per warp.  One step() = one node phase (until the
+// lane holds up to two leaves or runs out of nodes) + the leaf tests + one pop; k_shadow refills finished lanes
+// between steps.
+struct ShadowWalk
 {
-    if (S.numObjects == 0) return false;
-    StackEntry stack[RTB_STACK_SIZE];
-    uint32_t stackSize = 0;
-    uint32_t blasBase = 0;
-    uint32_t popFloor = RTB_STACK_SIZE;     // entries above it are plain nodes of the mesh being traversed
-    bool inBlas = false;
-    const DNode* nodes = S.tlas;
-    const DTri* tris = nullptr;
-    Ray ray = worldRay;
-    const bool worldFinite = ray_is_finite(worldRay);
-    bool finite = worldFinite;
-    bool have = false;
-    uint32_t curChild = 0, curInfo = 0;
+    enum { kContinue = 0, kOccluded = 1, kVisible = 2 };
 
-    if (S.numObjects == 1) { stack[0].a = 0u; stack[0].b = RTB_ENTRY_OBJECT; stackSize = 1; }
-    else if (S.numTlasNodes != 0) { node_header(S.tlas, 0, curChild, curInfo); have = true; }
+    // (the stack itself is a separate local array handed to begin()/step(): with the array inside, the whole struct
+    //  would live in local memory instead of registers)
+    uint32_t stackSize, blasBase;
+    uint32_t popFloor;                     // entries above it are plain nodes of the mesh being traversed
+    bool inBlas, finite, worldFinite, have;
+    const DNode* nodes;
+    const DTri* tris;
+    Ray ray, world;
+    float maxDistance;
+    uint32_t curChild, curInfo;
+    uint32_t pendChild, pendInfo;          // a mesh leaf whose triangle tests are postponed
 
-#if RTB_SHADOW_POSTPONE
-    uint32_t pendChild = 0, pendInfo = 0;   // a mesh leaf whose triangle tests are postponed (any-hit: order is free)
-#endif
-    for (;;)
+    // false: nothing to traverse (the ray is unoccluded)
+    RTB_HD bool begin(const SceneView& S, StackEntry* stack, const Ray& worldRay, float tMax)
     {
-        // (the two loop forms compile to very different reconvergence code: with `while (have) { if (leaf) break; ... }`
-        //  and no postponing, k_shadow measured 35 % slower than with the plain condition below)
-#if RTB_SHADOW_POSTPONE
+        if (S.numObjects == 0) return false;
+        stackSize = 0; blasBase = 0; popFloor = RTB_STACK_SIZE; inBlas = false;
+        nodes = S.tlas; tris = nullptr;
+        ray = worldRay; world = worldRay; maxDistance = tMax;
+        worldFinite = ray_is_finite(worldRay); finite = worldFinite;
+        have = false; curChild = 0; curInfo = 0; pendChild = 0; pendInfo = 0;
+        if (S.numObjects == 1) { stack[0].a = 0u; stack[0].b = RTB_ENTRY_OBJECT; stackSize = 1; }
+        else if (S.numTlasNodes != 0) { node_header(S.tlas, 0, curChild, curInfo); have = true; }
+        else return false;
+        return true;
+    }
+
+    template <bool kCount>
+    RTB_HD bool leaf_occludes(uint32_t first, uint32_t info, TraceCounters* cnt) const
+    {
+        // MeshShape::Traverse_Leaf_Shadow, MeshShape.cpp:175-207
+        const uint32_t numLeaves = RTB_NUM_LEAVES(info);
+        if (kCount) cnt->triTests += numLeaves;
+        bool occluded = false;
+        for (uint32_t i = 0; i < numLeaves; ++i)
+        {
+            V3 v0, e1, e2;
+            load_tri(tris, first + i, v0, e1, e2);
+            float u, v, distance;
+            if (triangle_ray(ray, v0, e1, e2, u, v, distance) && distance < maxDistance) occluded = true;
+        }
+        return occluded;
+    }
+
+    template <bool kCount>
+    RTB_HD int step(const SceneView& S, StackEntry* stack, TraceCounters* cnt)
+    {
+        // (the form of this loop matters: `while (have) { if (leaf) break; ... }` WITHOUT the postponing measured 35 %
+        //  slower than `while (have && !leaf)`: ptxas places the reconvergence points differently)
         while (have)
         {
             if (RTB_NUM_LEAVES(curInfo) != 0)
             {
-                // keep the lane in the node loop past its first leaf: fewer, fuller leaf phases per warp
                 if (inBlas && pendInfo == 0 && stackSize > popFloor)
                 {
                     pendChild = curChild; pendInfo = curInfo;
@@ -436,10 +461,6 @@ RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float
                 }
                 break;
             }
-#else
-        while (have && RTB_NUM_LEAVES(curInfo) == 0)
-        {
-#endif
             const DNode a = load_node(nodes, curChild);
             const DNode b = load_node(nodes, curChild + 1);
             float distanceA, distanceB;
@@ -459,82 +480,53 @@ RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float
             if (kCount) cnt->boxTests += 2;
             if (hitA && hitB)
             {
-#if RTB_SHADOW_NEAR_FIRST
-                // any-hit: the visiting order is free (see above); the nearer child is the likelier occluder
                 const bool swap = distanceB < distanceA;
                 StackEntry e; e.a = swap ? a.childIndex : b.childIndex; e.b = swap ? a.leafInfo : b.leafInfo;
                 stack[stackSize++] = e;
                 curChild = swap ? b.childIndex : a.childIndex; curInfo = swap ? b.leafInfo : a.leafInfo;
-#else
-                StackEntry e; e.a = b.childIndex; e.b = b.leafInfo;
-                stack[stackSize++] = e;
-                curChild = a.childIndex; curInfo = a.leafInfo;
-#endif
             }
             else if (hitA) { curChild = a.childIndex; curInfo = a.leafInfo; }
             else if (hitB) { curChild = b.childIndex; curInfo = b.leafInfo; }
             else if (stackSize > popFloor)
             {
                 // both children missed: take the next pending node of this mesh right here, so that the lane stays in
-                // the inner loop with the rest of its warp instead of idling until every lane has left it
+                // the node loop with the rest of its warp instead of idling until every lane has left it
                 const StackEntry e = stack[--stackSize];
                 curChild = e.a; curInfo = e.b;
             }
             else have = false;
         }
 
-#if RTB_SHADOW_POSTPONE
         if (pendInfo != 0)
         {
-            const uint32_t numLeaves = RTB_NUM_LEAVES(pendInfo);
-            if (kCount) cnt->triTests += numLeaves;
-            bool occluded = false;
-            for (uint32_t i = 0; i < numLeaves; ++i)
-            {
-                V3 v0, e1, e2;
-                load_tri(tris, pendChild + i, v0, e1, e2);
-                float u, v, distance;
-                if (triangle_ray(ray, v0, e1, e2, u, v, distance) && distance < maxDistance) occluded = true;
-            }
-            if (occluded) return true;
+            if (leaf_occludes<kCount>(pendChild, pendInfo, cnt)) return kOccluded;
             pendInfo = 0;
         }
-#endif
         if (have)
         {
-            const uint32_t numLeaves = RTB_NUM_LEAVES(curInfo);
             if (inBlas)
             {
-                // MeshShape::Traverse_Leaf_Shadow, MeshShape.cpp:175-207
-                if (kCount) cnt->triTests += numLeaves;
-                bool occluded = false;
-                for (uint32_t i = 0; i < numLeaves; ++i)
-                {
-                    V3 v0, e1, e2;
-                    load_tri(tris, curChild + i, v0, e1, e2);
-                    float u, v, distance;
-                    if (triangle_ray(ray, v0, e1, e2, u, v, distance) && distance < maxDistance) occluded = true;
-                }
-                if (occluded) return true;
+                if (leaf_occludes<kCount>(curChild, curInfo, cnt)) return kOccluded;
             }
             else
             {
-                for (uint32_t i = numLeaves; i-- > 0;) { stack[stackSize].a = curChild + i; stack[stackSize].b = RTB_ENTRY_OBJECT; stackSize++; }
+                // Scene::Traverse_Leaf_Shadow, Scene.cpp:180-194: one stack entry per object of the top-level leaf
+                for (uint32_t i = RTB_NUM_LEAVES(curInfo); i-- > 0;) { stack[stackSize].a = curChild + i; stack[stackSize].b = RTB_ENTRY_OBJECT; stackSize++; }
             }
             have = false;
         }
 
         if (inBlas && stackSize == blasBase)
         {
-            inBlas = false; popFloor = RTB_STACK_SIZE; nodes = S.tlas; ray = worldRay; finite = worldFinite;
+            inBlas = false; popFloor = RTB_STACK_SIZE; nodes = S.tlas; ray = world; finite = worldFinite;
         }
-        if (stackSize == 0) break;
+        if (stackSize == 0) return kVisible;
         const StackEntry e = stack[--stackSize];
         if (e.b == RTB_ENTRY_OBJECT)
         {
             // Scene::Traverse_Object_Shadow, Scene.cpp:147-165
             const DObjectTrace& obj = S.objTrace[e.a];
-            const Ray localRay = transform_ray_unsafe(obj.invTransform, worldRay);
+            const Ray localRay = transform_ray_unsafe(obj.invTransform, world);
             if (obj.kind == RTB_OBJECT_SHAPE && obj.shapeType == RTB_SHAPE_MESH)
             {
                 const DMesh& mesh = S.meshes[obj.meshIndex];
@@ -547,15 +539,28 @@ RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float
             }
             else if (analytic_shadow(obj, localRay, maxDistance))
             {
-                return true;
+                return kOccluded;
             }
         }
         else
         {
             curChild = e.a; curInfo = e.b; have = true;
         }
+        return kContinue;
     }
-    return false;
+};
+
+template <bool kCount>
+RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float maxDistance, TraceCounters* cnt)
+{
+    ShadowWalk w;
+    StackEntry stack[RTB_STACK_SIZE];
+    if (!w.begin(S, stack, worldRay, maxDistance)) return false;
+    for (;;)
+    {
+        const int r = w.step<kCount>(S, stack, cnt);
+        if (r != ShadowWalk::kContinue) return r == ShadowWalk::kOccluded;
+    }
 }
 
 } // namespace rtb
