@@ -214,15 +214,32 @@ def run_gpu(args):
 
     # ---- end to end through the public API with host buffers: every step reads the film back to the host ---------------
     vp.reset()
-    host_img = np.empty((HEIGHT, WIDTH, 3), dtype=np.float32)
+    pinned = [capi.PinnedImage(WIDTH, HEIGHT), capi.PinnedImage(WIDTH, HEIGHT)]   # page-locked host frames (rtb_host_alloc)
     e2e_steps = max(4, min(args.steps, 16))
-    vp.render(1); vp.read_sum(out=host_img)
+    e2e_count = [0]
+
+    def e2e_step():
+        # every step ends with the frame as of this pass in host memory (rank 0 when sharded).  The read-back is
+        # asynchronous: snapshot in stream order, copy on a second stream while the next pass renders; the timed
+        # region closes with a synchronize, so every copy is inside it.
+        dst = pinned[e2e_count[0] & 1]
+        e2e_count[0] += 1
+        vp.render(1)                      # H2D: this pass' seed vector + pass descriptor
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, film)
+            if rank == 0:
+                rc = lib.rtb_unshard_film_async(ctx, C.c_void_p(gathered.data_ptr()), C.c_void_p(dst.ptr))
+                assert rc == 0, lib.rtb_last_error()
+        else:
+            rc = lib.rtb_read_sum_async(ctx, C.c_void_p(dst.ptr), 0)
+            assert rc == 0, lib.rtb_last_error()
+
+    e2e_step()
     sync_all()
     c0 = vp.counters()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        vp.render(1)                      # H2D: this pass' seed vector + pass descriptor (pageable host memory)
-        vp.read_sum(out=host_img)         # D2H: the accumulated film, raster order
+        e2e_step()
     sync_all()
     e2e_s = time.perf_counter() - t0
     c1 = vp.counters()
@@ -290,7 +307,10 @@ def run_gpu(args):
                                 "sample": "2 timed + 1 warm-up passes of %dx%d of the same scene with the reference's AVX2 build on all host threads" % (WIDTH // 2, HEIGHT // 2),
                                 "msamples_per_s": meta["msamples_per_s"], "host_cores": os.cpu_count()}
 
+    assert np.isfinite(pinned[0].array).all() and pinned[0].array.mean() > 0
     vp.close()
+    for im in pinned:
+        im.close()
     if rank == 0:
         value = rays / seconds * 1e-6
         line = {
@@ -304,7 +324,8 @@ def run_gpu(args):
             "gpu_launches": gpu_launches,
             "e2e": {"value": e2e_rays / e2e_s * 1e-6, "unit": "Mray/s", "steps": e2e_steps,
                     "h2d_bytes_per_step": DIMS * 4 + C.sizeof(capi.RtbPassDesc), "d2h_bytes_per_step": WIDTH * HEIGHT * 12,
-                    "api": "raytracer_b200.host_api.Viewport.render + read_sum (ViewportB200::Render / GetSumBuffer over the C ABI)"},
+                    "api": ("per step: raytracer_b200.host_api.Viewport.render (ViewportB200::Render) + rtb_read_sum_async (GetSumBuffer) into a page-locked host frame, synchronize at the end" if world == 1 else
+                            "per step: Viewport.render on every rank, NCCL all-gather of the shard films, rtb_unshard_film_async into rank 0's page-locked host frame, synchronize at the end")},
             "wall_s_timed_region": wall_s,
             "clocks": sampler.summary(),
             "roofline": roofline,

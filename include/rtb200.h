@@ -301,6 +301,16 @@ int  rtb_read_sum(RtbContext* ctx, float* rgb, int which);
 int  rtb_film_device_buffer(RtbContext* ctx, int which, void** outDevicePtr, uint64_t* outNumFloats);
 /* scatter gathered shard buffers (numShards * shardFloats, device) back to raster order into hostRgb */
 int  rtb_unshard_film(RtbContext* ctx, const void* gatheredDevice, float* hostRgb);
+/* asynchronous variants: the film is snapshotted in stream order (so later passes do not leak into it) and copied to
+ * the host on a second stream while the next passes render; the data is complete after rtb_synchronize.  At most two
+ * read-backs are in flight (the third waits for the first).  The host buffer should be page-locked (rtb_host_alloc). */
+int  rtb_read_sum_async(RtbContext* ctx, float* rgb, int which);
+int  rtb_unshard_film_async(RtbContext* ctx, const void* gatheredDevice, float* hostRgb);
+/* page-locked host memory for the rgb / hostRgb arguments above (the reference's Viewport owns its sum Bitmap,
+ * Viewport.h:121; an adapter that wants full-speed read-back allocates that bitmap here).  Any host pointer works,
+ * pinned ones copy at PCIe rate.  NULL on failure (rtb_last_error). */
+void* rtb_host_alloc(uint64_t bytes);
+void  rtb_host_free(void* p);
 
 int  rtb_get_counters(RtbContext* ctx, RtbCounters* out);   /* counters of the passes since the last reset */
 

@@ -108,7 +108,7 @@ HIT_DTYPE = np.dtype([("objectId", np.uint32), ("subObjectId", np.uint32), ("dis
 EXPORTED_SYMBOLS = [
     "rtb_last_error", "rtb_api_version", "rtb_create", "rtb_destroy", "rtb_upload_scene", "rtb_set_blue_noise",
     "rtb_resize", "rtb_reset", "rtb_render_pass", "rtb_render_passes", "rtb_synchronize", "rtb_read_sum", "rtb_film_device_buffer",
-    "rtb_unshard_film", "rtb_get_counters", "rtb_trace_batch", "rtb_trace_batch_device", "rtb_sample_batch",
+    "rtb_unshard_film", "rtb_read_sum_async", "rtb_unshard_film_async", "rtb_host_alloc", "rtb_host_free", "rtb_get_counters", "rtb_trace_batch", "rtb_trace_batch_device", "rtb_sample_batch",
     "rtb_primary_rays", "rtb_set_profiling", "rtb_get_pass_timings",
 ]
 
@@ -144,6 +144,12 @@ def load_library(path=None):
     lib.rtb_read_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.rtb_film_device_buffer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.rtb_unshard_film.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.rtb_read_sum_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.rtb_unshard_film_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.rtb_host_alloc.argtypes = [C.c_uint64]
+    lib.rtb_host_alloc.restype = C.c_void_p
+    lib.rtb_host_free.argtypes = [C.c_void_p]
+    lib.rtb_host_free.restype = None
     lib.rtb_get_counters.argtypes = [C.c_void_p, C.POINTER(RtbCounters)]
     lib.rtb_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
     lib.rtb_trace_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
@@ -234,6 +240,25 @@ class PassScript:
             self.num_passes, self.num_dims = self.seeds.shape
 
 
+class PinnedImage:
+    """height x width x 3 float32 array in page-locked host memory (rtb_host_alloc), for rtb_read_sum / rtb_unshard_film."""
+
+    def __init__(self, width, height):
+        self.lib = load_library()
+        self.nbytes = width * height * 12
+        self.ptr = self.lib.rtb_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise RtbError(self.lib.rtb_last_error().decode())
+        buf = (C.c_float * (width * height * 3)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=np.float32).reshape(height, width, 3)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            self.lib.rtb_host_free(self.ptr)
+            self.ptr = None
+
+
 def load_blue_noise(path=None):
     """128x128x4 uint16 table, returned in the interleaved RGBA16 order GenericSampler reads (GenericSampler.cpp:91-96)."""
     p = path or os.path.join(_HERE, "data", "blue_noise_128.rtbn")
@@ -321,6 +346,10 @@ class Context:
         p, n = C.c_void_p(), C.c_uint64()
         _check(self.lib, self.lib.rtb_film_device_buffer(self.h, which, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def read_sum_async(self, pinned, which=0):
+        """Snapshot + asynchronous copy into a PinnedImage; complete after synchronize()."""
+        _check(self.lib, self.lib.rtb_read_sum_async(self.h, pinned.ptr, which))
 
     def unshard_film(self, gathered_device_ptr):
         out = np.empty((self.height, self.width, 3), dtype=np.float32)

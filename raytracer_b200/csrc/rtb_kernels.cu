@@ -553,6 +553,10 @@ struct RtbContext
     DevArray<uint32_t> pixelListAll;  // all shards back to back, padded with 0xFFFFFFFF
     DevArray<float> sum, sum2;
     DevArray<float> raster;           // scratch for read-back
+    DevArray<float> rasterAsync[2];   // double-buffered snapshots for the asynchronous read-back
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t snapReady[2] = {nullptr, nullptr}, snapCopied[2] = {nullptr, nullptr};
+    uint32_t snapIndex = 0;
     DevArray<float4> p[2][4];
     DevArray<uint4> p4[2];
     DevArray<uint4> hit0;
@@ -590,7 +594,7 @@ static void free_scene(RtbContext* c)
 
 static void free_film(RtbContext* c)
 {
-    c->pixelList.release(); c->pixelListAll.release(); c->sum.release(); c->sum2.release(); c->raster.release();
+    c->pixelList.release(); c->pixelListAll.release(); c->sum.release(); c->sum2.release(); c->raster.release(); c->rasterAsync[0].release(); c->rasterAsync[1].release();
     for (int b = 0; b < 2; ++b) { for (int k = 0; k < 4; ++k) c->p[b][k].release(); c->p4[b].release(); }
     c->hit0.release(); c->hit1.release(); c->passColor.release();
     c->sr0.release(); c->sr1.release(); c->sr2.release(); c->sr3.release(); c->shThr.release(); c->shCount.release(); c->shList.release(); c->rayList.release();
@@ -679,6 +683,12 @@ void rtb_destroy(RtbContext* c)
     free_film(c);
     c->blueNoise.release(); c->ctl.release(); c->seed.release(); c->offsets.release();
     for (cudaEvent_t ev : c->events) cudaEventDestroy(ev);
+    if (c->copyStream)
+    {
+        cudaStreamSynchronize(c->copyStream);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->snapReady[i]); cudaEventDestroy(c->snapCopied[i]); }
+        cudaStreamDestroy(c->copyStream);
+    }
     if (c->ownStream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -751,6 +761,7 @@ int rtb_resize(RtbContext* c, uint32_t width, uint32_t height)
     if (width == 0 || height == 0 || width > 65536 || height > 65536) return fail(RTB_ERR_INVALID_ARG, "rtb_resize: invalid viewport size %ux%u", width, height);   // Viewport.cpp:52-58
     RTB_CUDA(cudaSetDevice(c->device));
     RTB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->copyStream) RTB_CUDA(cudaStreamSynchronize(c->copyStream));
     free_film(c);
     c->width = width; c->height = height;
 
@@ -1016,6 +1027,7 @@ int rtb_synchronize(RtbContext* c)
     if (!c) return fail(RTB_ERR_INVALID_ARG, "null context");
     RTB_CUDA(cudaSetDevice(c->device));
     RTB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->copyStream) RTB_CUDA(cudaStreamSynchronize(c->copyStream));
     return RTB_OK;
 }
 
@@ -1039,6 +1051,72 @@ int rtb_unshard_film(RtbContext* c, const void* gatheredDevice, float* hostRgb)
     RTB_CUDA(cudaMemcpyAsync(hostRgb, c->raster.ptr, (size_t)c->width * c->height * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     RTB_CUDA(cudaStreamSynchronize(c->stream));
     return RTB_OK;
+}
+
+// Asynchronous read-back: the film is snapshotted to one of two raster buffers on the render stream, and copied to the
+// host on a second stream, so the copy of pass k overlaps the kernels of pass k+1.  `gatheredDevice` null: this
+// context's own film (rtb_read_sum semantics), else the all-gathered shard films (rtb_unshard_film semantics).
+static int read_back_async(RtbContext* c, const void* gatheredDevice, float* hostRgb, int which)
+{
+    if (!c || !hostRgb) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    if (!c->sum.ptr) return fail(RTB_ERR_INVALID_ARG, "viewport has no size");
+    RTB_CUDA(cudaSetDevice(c->device));
+    if (!c->copyStream)
+    {
+        RTB_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i)
+        {
+            RTB_CUDA(cudaEventCreateWithFlags(&c->snapReady[i], cudaEventDisableTiming));
+            RTB_CUDA(cudaEventCreateWithFlags(&c->snapCopied[i], cudaEventDisableTiming));
+            RTB_CUDA(cudaEventRecord(c->snapCopied[i], c->copyStream));
+        }
+    }
+    const uint32_t b = c->snapIndex++ & 1u;
+    const size_t n = (size_t)c->width * c->height * 3;
+    if (c->rasterAsync[b].count != n) RTB_CUDA(c->rasterAsync[b].alloc(n));
+    float* dst = c->rasterAsync[b].ptr;
+    RTB_CUDA(cudaStreamWaitEvent(c->stream, c->snapCopied[b], 0));       // the copy that last used this buffer is done
+    if (gatheredDevice)
+    {
+        k_unshard<<<c->numSMs * 4, 256, 0, c->stream>>>((const float*)gatheredDevice, dst, c->pixelListAll.ptr, c->numShards * c->shardSlots);
+    }
+    else if (c->numShards > 1)
+    {
+        RTB_CUDA(cudaMemsetAsync(dst, 0, n * sizeof(float), c->stream));
+        k_unshard<<<c->numSMs * 4, 256, 0, c->stream>>>(which == 0 ? c->sum.ptr : c->sum2.ptr, dst, c->pixelList.ptr, c->numPixels);
+    }
+    else
+    {
+        k_unshard<<<c->numSMs * 4, 256, 0, c->stream>>>(which == 0 ? c->sum.ptr : c->sum2.ptr, dst, c->pixelListAll.ptr, c->shardSlots);
+    }
+    RTB_CUDA(cudaGetLastError());
+    c->counters.numKernelLaunches++;
+    RTB_CUDA(cudaEventRecord(c->snapReady[b], c->stream));
+    RTB_CUDA(cudaStreamWaitEvent(c->copyStream, c->snapReady[b], 0));
+    RTB_CUDA(cudaMemcpyAsync(hostRgb, dst, n * sizeof(float), cudaMemcpyDeviceToHost, c->copyStream));
+    RTB_CUDA(cudaEventRecord(c->snapCopied[b], c->copyStream));
+    return RTB_OK;
+}
+
+int rtb_read_sum_async(RtbContext* c, float* rgb, int which) { return read_back_async(c, nullptr, rgb, which); }
+
+int rtb_unshard_film_async(RtbContext* c, const void* gatheredDevice, float* hostRgb)
+{
+    if (!gatheredDevice) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    return read_back_async(c, gatheredDevice, hostRgb, 0);
+}
+
+void* rtb_host_alloc(uint64_t bytes)
+{
+    void* p = nullptr;
+    const cudaError_t e = cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { fail(RTB_ERR_CUDA, "rtb_host_alloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+
+void rtb_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
 }
 
 int rtb_read_sum(RtbContext* c, float* rgb, int which)

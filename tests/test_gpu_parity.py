@@ -261,3 +261,33 @@ def test_batched_passes_are_bit_identical_to_single_passes(ctx, scene):
     c = ctx.counters()
     assert (c["numRays"], c["numShadowRays"], c["numShadowRaysHit"], c["numPrimaryRays"]) == \
            (meta["numRays"], meta["numShadowRays"], meta["numShadowRaysHit"], meta["numPrimaryRays"])
+
+
+def test_async_read_back_snapshots_every_pass(ctx):
+    """rtb_read_sum_async after pass k must deliver the film as of pass k even though pass k+1 is already running
+    (double-buffered snapshot on the render stream, copy on a second stream); three read-backs in flight exercise
+    the buffer reuse."""
+    meta = json.load(open(util.golden("cornell_mis.json")))
+    w, h = meta["width"], meta["height"]
+    sf = capi.SceneFile(util.golden("cornell.rtb"))
+    ps = capi.PassScript(util.golden("cornell.passes"))
+    ctx.upload_scene(sf)
+    ctx.resize(w, h)
+    cam = capi.camera_for(sf, w, h)
+    n = min(3, meta["passes"])
+    want = []
+    for p in range(n):
+        ctx.render_pass(ctx.make_pass(cam, ps.seeds[p], ps.offsets[p], p))
+        want.append(ctx.read_sum().copy())
+    ctx.reset()
+    pinned = [capi.PinnedImage(w, h) for _ in range(n)]
+    try:
+        for p in range(n):
+            ctx.render_pass(ctx.make_pass(cam, ps.seeds[p], ps.offsets[p], p))
+            ctx.read_sum_async(pinned[p])
+        ctx.synchronize()
+        for p in range(n):
+            util.assert_bit_identical(pinned[p].array, want[p], "async read-back after pass %d" % p)
+    finally:
+        for im in pinned:
+            im.close()

@@ -14,3 +14,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:"k_traverse|k_shadow" -s 36 -c 4 -o gpurun_out/prof_$TAG \
     python tools/quick_bench.py 1920 1080 4 > gpurun_out/ncu_$TAG.log 2>&1
 ls -la gpurun_out | tail -8
+# DRAM traffic of every k_traverse / k_shadow launch of ONE 8-pass wavefront (9 depths): bench.py's roofline.traffic
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"k_traverse|k_shadow" -s 36 -c 18 \
+    --csv --log-file gpurun_out/dram_$TAG.csv python tools/quick_bench.py 1920 1080 8 > gpurun_out/dram_$TAG.log 2>&1
