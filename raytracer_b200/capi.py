@@ -337,8 +337,9 @@ class Context:
     def synchronize(self):
         _check(self.lib, self.lib.rtb_synchronize(self.h))
 
-    def read_sum(self, which=0):
-        out = np.empty((self.height, self.width, 3), dtype=np.float32)
+    def read_sum(self, which=0, out=None):
+        if out is None:
+            out = np.empty((self.height, self.width, 3), dtype=np.float32)
         _check(self.lib, self.lib.rtb_read_sum(self.h, out.ctypes.data, which))
         return out
 

@@ -906,7 +906,11 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
     RTB_CUDA(cudaMemsetAsync(c->ctl.ptr, 0, offsetof(Control, numRays), s));
     RTB_CUDA(cudaMemcpyAsync(&c->ctl.ptr->pathCount[0], &numPaths, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
 
-    const int blocks128 = c->numSMs * c->simpleBlocksPerSM;
+    // grids: oversubscribed grid-stride launches, but never more CTAs than the wavefront can have work for (a small
+    // shard's single pass would otherwise spend its time retiring ~19 000 empty CTAs per launch)
+    const int blocksCap = c->numSMs * c->simpleBlocksPerSM;
+    const int blocks128 = (int)std::min<size_t>((size_t)blocksCap, std::max<size_t>(1, ((size_t)numPaths + 127) / 128));
+    const int blocksShadow = (int)std::min<size_t>((size_t)blocksCap, std::max<size_t>(1, ((size_t)numPaths * std::max<uint32_t>(1u, W.raysPerPath) + 127) / 128));
     const int blocks256 = c->numSMs * 4;
     size_t ev = 0;
     std::vector<cudaEvent_t> marks;
@@ -926,7 +930,7 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
         if (shadows)
         {
             // resident warps only: they fetch rays dynamically until the list is empty
-            const int shadowBlocks = RTB_SHADOW_REFILL ? c->numSMs * RTB_TRAV_MINBLOCKS : blocks128;
+            const int shadowBlocks = RTB_SHADOW_REFILL ? c->numSMs * RTB_TRAV_MINBLOCKS : blocksShadow;
             if (count) k_shadow<true><<<shadowBlocks, 128, 0, s>>>(c->view, W, d);
             else k_shadow<false><<<shadowBlocks, 128, 0, s>>>(c->view, W, d);
             k_resolve<<<blocks256, 256, 0, s>>>(W, d);
