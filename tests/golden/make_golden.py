@@ -36,6 +36,7 @@ SCENES = {
     # name: (sampler dimensions, renderers)
     "c1_sphere_area": (128, ["mis"]),
     "cornell": (128, ["mis", "pt", "dbgtri", "dbgdepth"]),
+    "cornell_dof": (128, ["mis"]),      # depth of field: 2 extra sampler dimensions per primary ray
     "materials": (256, ["mis", "pt"]),
     "mesh_small": (128, ["mis", "pt", "dbgtri", "dbgdepth"]),
 }

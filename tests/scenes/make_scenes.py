@@ -301,6 +301,9 @@ def write_all(out_dir, sponza=False):
     dump("c1_sphere_area", scene_c1())
     dump("cornell", scene_cornell())
     dump("materials", scene_materials())
+    dof = scene_cornell()
+    dof["camera"].update({"enableDOF": True, "aperture": 0.15, "focalPlaneDistance": 3.5})    # circle bokeh, Camera.cpp:100-116
+    dump("cornell_dof", dof)
 
     w, mats = build_atrium(0.09)
     w.write(os.path.join(out_dir, "MODELS", "mesh_small.obj"), "mesh_small.mtl", mats)

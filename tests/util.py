@@ -14,6 +14,7 @@ RENDERER_IDS = {"mis": (1, 0), "pt": (0, 0), "dbgtri": (2, 1), "dbgdepth": (2, 2
 GOLDEN_RENDERS = [
     ("c1_sphere_area", "mis"),
     ("cornell", "mis"), ("cornell", "pt"), ("cornell", "dbgtri"), ("cornell", "dbgdepth"),
+    ("cornell_dof", "mis"),
     ("materials", "mis"), ("materials", "pt"),
     ("mesh_small", "mis"), ("mesh_small", "pt"), ("mesh_small", "dbgtri"), ("mesh_small", "dbgdepth"),
 ]
