@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RTB_API_VERSION 1
+#define RTB_API_VERSION 2   /* 2: textures (RtbTexture, RtbMaterialTextures, RtbSceneDesc::textures ...) */
 
 typedef enum RtbStatus
 {
@@ -93,7 +93,8 @@ typedef enum RtbBsdfType
     RTB_BSDF_METAL, RTB_BSDF_ROUGH_METAL, RTB_BSDF_PLASTIC, RTB_BSDF_ROUGH_PLASTIC
 } RtbBsdfType;
 
-/* rt::Material constant parameters (Core/Material/Material.h:44-75), textures are not part of this contract yet */
+/* rt::Material constant parameters (Core/Material/Material.h:44-75); the textures that modulate them are bound by the
+ * parallel RtbSceneDesc::materialTextures array */
 typedef struct RtbMaterial
 {
     uint32_t bsdf;
@@ -106,6 +107,52 @@ typedef struct RtbMaterial
     float    K;
     float    pad0, pad1;
 } RtbMaterial;
+
+/* ---- textures (ITexture, Core/Textures/Texture.h:14-34) ---------------------------------------------- */
+
+typedef enum RtbTextureType
+{
+    RTB_TEXTURE_BITMAP       = 0,  /* BitmapTexture,       Core/Textures/BitmapTexture.cpp:32-93 (wrap + smooth-step bilinear) */
+    RTB_TEXTURE_CHECKERBOARD = 1,  /* CheckerboardTexture, Core/Textures/CheckerboardTexture.cpp:32-41 */
+    RTB_TEXTURE_NOISE        = 2,  /* NoiseTexture,        Core/Textures/NoiseTexture.cpp:59-162 (2-D simplex noise octaves) */
+    RTB_TEXTURE_MIX          = 3   /* MixTexture,          Core/Textures/MixTexture.cpp:24-31 */
+} RtbTextureType;
+
+#define RTB_NO_TEXTURE 0xFFFFFFFFu
+#define RTB_MAX_MIX_DEPTH 4u       /* a mix texture may nest other mix textures this deep */
+
+/*
+ * bitmap      : texels = width*height RGBA float quadruples, row-major, texel (x, y) at texels[4*(y*width + x)], holding
+ *               EXACTLY what Bitmap::GetPixel(x, y) returns (Core/Utils/Bitmap.cpp:335-518): the storage format is decoded
+ *               and the sRGB -> linear conversion of gamma-space bitmaps is already applied by the host
+ * checkerboard: colorA, colorB
+ * noise       : colorA, colorB, numOctaves
+ * mix         : texA, texB, texWeight = indices of EARLIER entries of RtbSceneDesc::textures
+ */
+typedef struct RtbTexture
+{
+    uint32_t type;           /* RtbTextureType */
+    uint32_t width, height;
+    uint32_t numOctaves;
+    uint32_t texA, texB, texWeight;
+    uint32_t pad0;
+    float    colorA[4];
+    float    colorB[4];
+    const float* texels;
+} RtbTexture;
+
+/* the optional textures of one rt::Material (Material.h:63-77, MaterialParameter.h:12-33); RTB_NO_TEXTURE = none */
+typedef struct RtbMaterialTextures
+{
+    uint32_t baseColor;          /* value = baseValue * texture (4 lanes) */
+    uint32_t emission;
+    uint32_t roughness;          /* value = baseValue * texture.x */
+    uint32_t metalness;
+    uint32_t normalMap;          /* Material::GetNormalVector, Material.cpp:120-138; Scene.cpp:328-337 */
+    uint32_t maskMap;            /* carried for completeness: Material::GetMaskValue has no caller in the reference */
+    float    normalMapStrength;
+    uint32_t pad0;
+} RtbMaterialTextures;
 
 typedef enum RtbLightType
 {
@@ -166,6 +213,11 @@ typedef struct RtbSceneDesc
     uint32_t numMaterials;   const RtbMaterial* materials;
     uint32_t numLights;      const RtbLight*    lights;
     uint32_t numGlobalLights; const uint32_t*   globalLights;  /* indices into lights[], Scene::GetGlobalLights() order */
+    /* textures: all optional (numTextures = 0, null pointers = a scene without textures) */
+    uint32_t numTextures;    const RtbTexture*  textures;
+    const RtbMaterialTextures* materialTextures;   /* numMaterials entries, or NULL */
+    const uint32_t*            lightTextures;      /* numLights entries (BackgroundLight::mTexture, BackgroundLight.cpp:45-61;
+                                                      RTB_NO_TEXTURE = none), or NULL */
 } RtbSceneDesc;
 
 /* ---- per-pass description ----------------------------------------------------------------------- */

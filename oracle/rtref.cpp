@@ -32,6 +32,11 @@
 #include "../Core/Shapes/RectShape.h"
 #include "../Core/Shapes/MeshShape.h"
 #include "../Core/Material/Material.h"
+#include "../Core/Textures/BitmapTexture.h"
+#include "../Core/Textures/CheckerboardTexture.h"
+#include "../Core/Textures/NoiseTexture.h"
+#include "../Core/Textures/MixTexture.h"
+#include "../Core/Utils/Bitmap.h"
 #include "../Core/Traversal/TraversalContext.h"
 #include "../Core/Math/SamplingHelpers.h"
 #include "../Core/Sampling/GenericSampler.h"
@@ -146,6 +151,60 @@ struct Flat
     std::map<const IShape*, uint32_t> shapeIds;
     std::map<const Material*, uint32_t> materialIds;
 
+    // textures (RTBS version 2 section)
+    struct Texture { RtbTexture desc; std::vector<float> texels; };
+    std::vector<Texture> textures;
+    std::vector<RtbMaterialTextures> materialTextures;
+    std::vector<uint32_t> lightTextures;
+    std::map<const ITexture*, uint32_t> textureIds;
+    bool anyTexture = false;
+
+    uint32_t AddTexture(const ITexture* t)
+    {
+        if (!t) return RTB_NO_TEXTURE;
+        auto it = textureIds.find(t);
+        if (it != textureIds.end()) return it->second;
+        Texture r;
+        memset(&r.desc, 0, sizeof(r.desc));
+        if (const BitmapTexture* bt = dynamic_cast<const BitmapTexture*>(t))
+        {
+            const Bitmap* b = bt->mBitmap.get();
+            if (!b) Die("bitmap texture without bitmap");
+            if (bt->mFilter != BitmapTextureFilter::Bilinear_SmoothStep) Die("unexpected bitmap filter");
+            r.desc.type = RTB_TEXTURE_BITMAP;
+            r.desc.width = b->GetWidth(); r.desc.height = b->GetHeight();
+            r.texels.resize((size_t)r.desc.width * r.desc.height * 4);
+            // the texels are DEFINED as what the reference's own Bitmap::GetPixel returns
+            for (uint32_t y = 0; y < r.desc.height; ++y)
+                for (uint32_t x = 0; x < r.desc.width; ++x)
+                    ToF4(b->GetPixel(x, y), &r.texels[4 * ((size_t)y * r.desc.width + x)]);
+        }
+        else if (const CheckerboardTexture* ct = dynamic_cast<const CheckerboardTexture*>(t))
+        {
+            r.desc.type = RTB_TEXTURE_CHECKERBOARD;
+            ToF4(ct->mColorA, r.desc.colorA); ToF4(ct->mColorB, r.desc.colorB);
+        }
+        else if (const NoiseTexture* nt = dynamic_cast<const NoiseTexture*>(t))
+        {
+            r.desc.type = RTB_TEXTURE_NOISE;
+            ToF4(nt->mColorA, r.desc.colorA); ToF4(nt->mColorB, r.desc.colorB);
+            r.desc.numOctaves = nt->mNumOctaves;
+        }
+        else if (const MixTexture* mt = dynamic_cast<const MixTexture*>(t))
+        {
+            r.desc.type = RTB_TEXTURE_MIX;
+            r.desc.texA = AddTexture(mt->mTextureA.get());
+            r.desc.texB = AddTexture(mt->mTextureB.get());
+            r.desc.texWeight = AddTexture(mt->mTextureMask.get());
+        }
+        else Die("unsupported texture class");
+        const uint32_t id = (uint32_t)textures.size();
+        textures.push_back(std::move(r));
+        textureIds[t] = id;
+        anyTexture = true;
+        return id;
+    }
+
     uint32_t AddMaterial(const Material* m)
     {
         auto it = materialIds.find(m);
@@ -153,7 +212,17 @@ struct Flat
         RtbMaterial r;
         memset(&r, 0, sizeof(r));
         r.bsdf = BsdfId(m);
-        if (m->baseColor.texture || m->emission.texture || m->roughness.texture || m->metalness.texture || m->normalMap || m->maskMap) r.flags |= 1u; // textured (unsupported)
+        if (m->baseColor.texture || m->emission.texture || m->roughness.texture || m->metalness.texture || m->normalMap || m->maskMap) r.flags |= 1u; // textured
+        RtbMaterialTextures mt;
+        memset(&mt, 0, sizeof(mt));
+        mt.baseColor = AddTexture(m->baseColor.texture.get());
+        mt.emission = AddTexture(m->emission.texture.get());
+        mt.roughness = AddTexture(m->roughness.texture.get());
+        mt.metalness = AddTexture(m->metalness.texture.get());
+        mt.normalMap = AddTexture(m->normalMap.get());
+        mt.maskMap = AddTexture(m->maskMap.get());
+        mt.normalMapStrength = m->normalMapStrength;
+        materialTextures.push_back(mt);
         if (m->isDispersive) r.flags |= 2u;
         r.roughness = m->roughness.baseValue;
         r.metalness = m->metalness.baseValue;
@@ -237,8 +306,10 @@ struct Flat
             r.flags = (uint32_t)l.GetFlags();
             r.shapeIndex = UINT32_MAX;
             ToF4(l.GetColor().rgbValues, r.color);
-            if (const AreaLight* al = dynamic_cast<const AreaLight*>(&l)) { r.shapeIndex = AddShape(al->GetShape().get()); if (al->mTexture) Die("textured area light"); }
-            if (const BackgroundLight* bl = dynamic_cast<const BackgroundLight*>(&l)) { if (bl->mTexture) Die("textured background light"); }
+            if (const AreaLight* al = dynamic_cast<const AreaLight*>(&l)) { r.shapeIndex = AddShape(al->GetShape().get()); }
+            uint32_t lightTexture = RTB_NO_TEXTURE;
+            if (const BackgroundLight* bl = dynamic_cast<const BackgroundLight*>(&l)) lightTexture = AddTexture(bl->mTexture.get());
+            lightTextures.push_back(lightTexture);     // (AreaLight::mTexture is never evaluated: AreaLight.cpp:49-58, 136-146)
             if (const DirectionalLight* dl = dynamic_cast<const DirectionalLight*>(&l)) { r.cosAngle = dl->mCosAngle; r.isDelta = dl->mIsDelta; }
             if (const SpotLight* sl = dynamic_cast<const SpotLight*>(&l)) { r.cosAngle = sl->mCosAngle; r.isDelta = sl->mIsDelta; }
             r.transform = ToMat(lo->GetBaseTransform());
@@ -277,7 +348,7 @@ struct Flat
         FILE* f = fopen(path, "wb");
         if (!f) Die("cannot open output");
         WriteU32(f, 0x53425452u); // 'RTBS'
-        WriteU32(f, 1);
+        WriteU32(f, anyTexture ? 2 : 1);
         WriteU32(f, (uint32_t)tlas.size());      WriteBytes(f, tlas.data(), tlas.size() * sizeof(RtbBvhNode));
         WriteU32(f, (uint32_t)objects.size());   WriteBytes(f, objects.data(), objects.size() * sizeof(RtbObject));
         WriteU32(f, (uint32_t)shapes.size());    WriteBytes(f, shapes.data(), shapes.size() * sizeof(RtbShape));
@@ -311,6 +382,18 @@ struct Flat
         c.barrelDistortionVariableFactor = camera.barrelDistortionVariableFactor;
         WritePod(f, c);
         WritePod(f, camera.mFieldOfView);
+        if (anyTexture)
+        {
+            WriteU32(f, (uint32_t)textures.size());
+            for (const Texture& t : textures)
+            {
+                const uint32_t h[8] = { t.desc.type, t.desc.width, t.desc.height, t.desc.numOctaves, t.desc.texA, t.desc.texB, t.desc.texWeight, 0u };
+                WriteBytes(f, h, sizeof(h)); WriteBytes(f, t.desc.colorA, 16); WriteBytes(f, t.desc.colorB, 16);
+                WriteBytes(f, t.texels.data(), t.texels.size() * 4);
+            }
+            WriteU32(f, (uint32_t)materialTextures.size()); WriteBytes(f, materialTextures.data(), materialTextures.size() * sizeof(RtbMaterialTextures));
+            WriteU32(f, (uint32_t)lightTextures.size()); WriteBytes(f, lightTextures.data(), lightTextures.size() * 4);
+        }
         fclose(f);
     }
 };

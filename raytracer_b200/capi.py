@@ -40,6 +40,21 @@ class RtbMaterial(C.Structure):
                 ("pad0", C.c_float), ("pad1", C.c_float)]
 
 
+class RtbTexture(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32), ("numOctaves", C.c_uint32),
+                ("texA", C.c_uint32), ("texB", C.c_uint32), ("texWeight", C.c_uint32), ("pad0", C.c_uint32),
+                ("colorA", C.c_float * 4), ("colorB", C.c_float * 4), ("texels", C.c_void_p)]
+
+
+class RtbMaterialTextures(C.Structure):
+    _fields_ = [("baseColor", C.c_uint32), ("emission", C.c_uint32), ("roughness", C.c_uint32), ("metalness", C.c_uint32),
+                ("normalMap", C.c_uint32), ("maskMap", C.c_uint32), ("normalMapStrength", C.c_float), ("pad0", C.c_uint32)]
+
+
+RTB_TEXTURE_BITMAP, RTB_TEXTURE_CHECKERBOARD, RTB_TEXTURE_NOISE, RTB_TEXTURE_MIX = 0, 1, 2, 3
+RTB_NO_TEXTURE = 0xFFFFFFFF
+
+
 class RtbLight(C.Structure):
     _fields_ = [("type", C.c_uint32), ("flags", C.c_uint32), ("shapeIndex", C.c_uint32), ("isDelta", C.c_uint32),
                 ("color", C.c_float * 4), ("cosAngle", C.c_float), ("pad0", C.c_float), ("pad1", C.c_float), ("pad2", C.c_float),
@@ -64,7 +79,9 @@ class RtbSceneDesc(C.Structure):
                 ("numMeshes", C.c_uint32), ("meshes", C.c_void_p),
                 ("numMaterials", C.c_uint32), ("materials", C.c_void_p),
                 ("numLights", C.c_uint32), ("lights", C.c_void_p),
-                ("numGlobalLights", C.c_uint32), ("globalLights", C.c_void_p)]
+                ("numGlobalLights", C.c_uint32), ("globalLights", C.c_void_p),
+                ("numTextures", C.c_uint32), ("textures", C.c_void_p),
+                ("materialTextures", C.c_void_p), ("lightTextures", C.c_void_p)]
 
 
 class RtbCamera(C.Structure):
@@ -189,7 +206,9 @@ class SceneFile:
             pos += nbytes
             return a
 
-        assert u32() == 0x53425452 and u32() == 1, "not an RTBS v1 file"
+        assert u32() == 0x53425452, "not an RTBS file"
+        version = u32()
+        assert version in (1, 2), "not an RTBS v1/v2 file"
         n = u32(); self.tlas = arr(n * C.sizeof(RtbBvhNode)); self.num_tlas = n
         n = u32(); self.objects = arr(n * C.sizeof(RtbObject)); self.num_objects = n
         n = u32(); self.shapes = arr(n * C.sizeof(RtbShape)); self.num_shapes = n
@@ -205,6 +224,23 @@ class SceneFile:
         self.camera = RtbCamera.from_buffer_copy(arr(C.sizeof(RtbCamera)).tobytes())
         self.field_of_view = float(arr(4).view(np.float32)[0])
         self.num_triangles = sum(m["numTriangles"] for m in self.meshes)
+        # version 2: textures
+        self.textures, self.material_textures, self.light_textures = [], None, None
+        if version >= 2:
+            for _ in range(u32()):
+                h = arr(32).view(np.uint32)
+                ca, cb = arr(16).view(np.float32), arr(16).view(np.float32)
+                t = dict(type=int(h[0]), width=int(h[1]), height=int(h[2]), numOctaves=int(h[3]), texA=int(h[4]), texB=int(h[5]),
+                         texWeight=int(h[6]), colorA=ca, colorB=cb, texels=None)
+                if t["type"] == RTB_TEXTURE_BITMAP:
+                    t["texels"] = arr(t["width"] * t["height"] * 16)
+                self.textures.append(t)
+            n = u32()
+            if n:
+                self.material_textures = arr(n * C.sizeof(RtbMaterialTextures))
+            n = u32()
+            if n:
+                self.light_textures = arr(n * 4)
 
     def desc(self):
         self._mesh_structs = (RtbMesh * max(1, len(self.meshes)))()
@@ -221,6 +257,18 @@ class SceneFile:
         d.numMaterials, d.materials = self.num_materials, self.materials.ctypes.data
         d.numLights, d.lights = self.num_lights, self.lights.ctypes.data
         d.numGlobalLights, d.globalLights = self.num_global_lights, self.global_lights.ctypes.data
+        self._texture_structs = (RtbTexture * max(1, len(self.textures)))()
+        for i, t in enumerate(self.textures):
+            s = self._texture_structs[i]
+            s.type, s.width, s.height, s.numOctaves = t["type"], t["width"], t["height"], t["numOctaves"]
+            s.texA, s.texB, s.texWeight = t["texA"], t["texB"], t["texWeight"]
+            for k in range(4):
+                s.colorA[k], s.colorB[k] = float(t["colorA"][k]), float(t["colorB"][k])
+            s.texels = t["texels"].ctypes.data if t["texels"] is not None else None
+        d.numTextures = len(self.textures)
+        d.textures = C.addressof(self._texture_structs) if self.textures else None
+        d.materialTextures = self.material_textures.ctypes.data if self.material_textures is not None else None
+        d.lightTextures = self.light_textures.ctypes.data if self.light_textures is not None else None
         return d
 
 

@@ -29,6 +29,11 @@ struct PathState
     uint32_t depth;
     float    lastPdfW;
     uint32_t lastSpecular;
+    // material of the vertex this path bounced from (RTB_NO_MATERIAL on the camera ray).  The reference reuses one
+    // IntersectionData for the whole path (PathTracerMIS.cpp:259, 286) and a light's EvaluateIntersection does not set
+    // its material (SceneObject_Light.cpp:63-74), so Scene::EvaluateIntersection (Scene.cpp:328) applies the PREVIOUS
+    // vertex' normal map to the frame of a directly hit area light - which changes cosAtLight and the MIS weight.
+    uint32_t lastMaterial;
 };
 
 // CombineMis / PdfAtoW, PathTracerMIS.cpp:16-29 (FastDivide is a true division in the exact-math oracle)
@@ -48,6 +53,7 @@ RTB_HD void init_path(const PassParams& P, const uint16_t* blueNoise, uint32_t x
     ps.depth = 0;
     ps.lastPdfW = 1.0f;
     ps.lastSpecular = 1u;
+    ps.lastMaterial = RTB_NO_MATERIAL;
 }
 
 // generate the secondary ray: Ray(position, dir); ray.origin += ray.dir * 0.001 (originDivDir is NOT refreshed)
@@ -58,7 +64,7 @@ RTB_HD void spawn_ray(PathState& ps, const V3& position, const V3& dirWorld)
 }
 
 // returns true if the path continues (ps holds the next ray), false if it terminated
-template <typename Sink>
+template <bool kTex = true, typename Sink>
 RTB_HD bool shade_vertex_mis(const SceneView& S, const PassParams& P, PathState& ps, const Hit& hit, Sink& sink, uint32_t& numShadowRays)
 {
     const float lightPickProbability = P.lightSamplingAll ? 1.0f : 1.0f / (float)S.numLights;   // GetLightPickingProbability
@@ -73,7 +79,7 @@ RTB_HD bool shade_vertex_mis(const SceneView& S, const PassParams& P, PathState&
             const DLight& light = S.lights[S.globalLights[i]];
             const Ray lightSpaceRay = transform_ray_unsafe(light.invTransform, ray);
             float directPdfW = 0.0f;
-            const V4 lightContribution = light_radiance(S, light, lightSpaceRay, v3s(0.0f), 1.0f, directPdfW);
+            const V4 lightContribution = light_radiance<kTex>(S, light, lightSpaceRay, v3s(0.0f), 1.0f, directPdfW);
             if (!almost_zero(lightContribution))
             {
                 float misWeight = 1.0f;
@@ -86,7 +92,7 @@ RTB_HD bool shade_vertex_mis(const SceneView& S, const PassParams& P, PathState&
     }
 
     Vertex vx;
-    if (hit.distance < FLT_MAX) evaluate_intersection(S, ray, hit, vx);
+    if (hit.distance < FLT_MAX) evaluate_intersection<kTex>(S, ray, hit, vx, ps.lastMaterial);
 
     // we hit a light directly                                            PathTracerMIS.cpp:290-302, 174-212
     if (hit.subObjectId == RTB_LIGHT_OBJECT)
@@ -96,7 +102,7 @@ RTB_HD bool shade_vertex_mis(const SceneView& S, const PassParams& P, PathState&
         const V3 lightSpaceHitPoint = transform_point(light.invTransform, vx.position);
         const float cosAtLight = -dot3(vx.normal, ray.dir);
         float directPdfA = 0.0f;
-        V4 lightContribution = light_radiance(S, light, lightSpaceRay, lightSpaceHitPoint, cosAtLight, directPdfA);
+        V4 lightContribution = light_radiance<kTex>(S, light, lightSpaceRay, lightSpaceHitPoint, cosAtLight, directPdfA);
         if (!almost_zero(lightContribution))
         {
             float misWeight = 1.0f;
@@ -116,7 +122,7 @@ RTB_HD bool shade_vertex_mis(const SceneView& S, const PassParams& P, PathState&
     }
 
     vx.outgoingDirWorld = neg(ray.dir);
-    evaluate_shading_data(S, vx);
+    evaluate_shading_data<kTex>(S, vx);
     const V3 outLocal = world_to_local(vx, vx.outgoingDirWorld);
 
     // accumulate emission color                                          PathTracerMIS.cpp:309-317
@@ -141,7 +147,7 @@ RTB_HD bool shade_vertex_mis(const SceneView& S, const PassParams& P, PathState&
             const float u1 = sampler_get_float(ps.sampler, P, S.blueNoise);
             const float u2 = sampler_get_float(ps.sampler, P, S.blueNoise);
             IlluminateResult ir;
-            const V4 radiance = light_illuminate(S, light, vx, u0, u1, u2, ir);
+            const V4 radiance = light_illuminate<kTex>(S, light, vx, u0, u1, u2, ir);
             if (almost_zero(radiance)) continue;
             float bsdfPdfW = 0.0f;
             const V4 factor = bsdf_evaluate(vx, outLocal, world_to_local(vx, neg(ir.directionToLight)), bsdfPdfW);
@@ -191,11 +197,12 @@ RTB_HD bool shade_vertex_mis(const SceneView& S, const PassParams& P, PathState&
     // generate secondary ray                                             PathTracerMIS.cpp:392-395
     spawn_ray(ps, vx.position, local_to_world(vx, bs.incomingDir));
     ps.depth++;
+    ps.lastMaterial = vx.materialIndex;
     return true;
 }
 
 // PathTracer::RenderPixel loop body (BSDF sampling only), PathTracer.cpp:74-172
-template <typename Sink>
+template <bool kTex = true, typename Sink>
 RTB_HD bool shade_vertex_pt(const SceneView& S, const PassParams& P, PathState& ps, const Hit& hit, Sink& sink)
 {
     const Ray& ray = ps.ray;
@@ -208,13 +215,13 @@ RTB_HD bool shade_vertex_pt(const SceneView& S, const PassParams& P, PathState& 
             const DLight& light = S.lights[S.globalLights[i]];
             const Ray lightSpaceRay = transform_ray_unsafe(light.invTransform, ray);
             float pdf = 0.0f;
-            result = result + light_radiance(S, light, lightSpaceRay, v3s(0.0f), 1.0f, pdf);
+            result = result + light_radiance<kTex>(S, light, lightSpaceRay, v3s(0.0f), 1.0f, pdf);
         }
         sink.add(ps.throughput, result);
         return false;
     }
     Vertex vx;
-    evaluate_intersection(S, ray, hit, vx);
+    evaluate_intersection<kTex>(S, ray, hit, vx, ps.lastMaterial);
     vx.outgoingDirWorld = neg(ray.dir);
     if (hit.subObjectId == RTB_LIGHT_OBJECT)
     {
@@ -224,10 +231,10 @@ RTB_HD bool shade_vertex_pt(const SceneView& S, const PassParams& P, PathState& 
         const Ray lightSpaceRay = transform_ray_unsafe(light.invTransform, ray);
         const V3 lightSpaceHitPoint = transform_point(light.invTransform, vx.position);
         float pdf = 0.0f;
-        sink.add(ps.throughput, light_radiance(S, light, lightSpaceRay, lightSpaceHitPoint, cosAtLight, pdf));
+        sink.add(ps.throughput, light_radiance<kTex>(S, light, lightSpaceRay, lightSpaceHitPoint, cosAtLight, pdf));
         return false;
     }
-    evaluate_shading_data(S, vx);
+    evaluate_shading_data<kTex>(S, vx);
     sink.add(ps.throughput, vx.emission);
     if (ps.depth >= P.maxRayDepth) return false;
     if (ps.depth >= P.minRussianRouletteDepth)
@@ -247,6 +254,7 @@ RTB_HD bool shade_vertex_pt(const SceneView& S, const PassParams& P, PathState& 
     if (almost_zero(ps.throughput)) return false;
     spawn_ray(ps, vx.position, local_to_world(vx, bs.incomingDir));
     ps.depth++;
+    ps.lastMaterial = vx.materialIndex;
     return true;
 }
 
@@ -268,7 +276,7 @@ RTB_HD V4 hsv_to_rgb(const float hue, const float saturation, const float value)
 }
 
 // DebugRenderer::RenderPixel, DebugRenderer.cpp:26-178 (primary hit visualisation; never continues)
-template <typename Sink>
+template <bool kTex = true, typename Sink>
 RTB_HD void shade_debug(const SceneView& S, const PassParams& P, PathState& ps, const Hit& hit, Sink& sink)
 {
     const V4 one = v4s(1.0f);
@@ -278,8 +286,8 @@ RTB_HD void shade_debug(const SceneView& S, const PassParams& P, PathState& ps, 
     vx.outgoingDirWorld = neg(ps.ray.dir);
     if (P.debugMode != RTB_DEBUG_TRIANGLE_ID && P.debugMode != RTB_DEBUG_DEPTH)
     {
-        if (hit.distance < FLT_MAX) evaluate_intersection(S, ps.ray, hit, vx);
-        evaluate_shading_data(S, vx);
+        if (hit.distance < FLT_MAX) evaluate_intersection<kTex>(S, ps.ray, hit, vx, RTB_NO_MATERIAL);
+        evaluate_shading_data<kTex>(S, vx);
     }
     V4 c = v4s(0.0f);
     switch (P.debugMode)

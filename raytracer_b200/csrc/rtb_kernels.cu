@@ -49,7 +49,7 @@ struct PathBuf
     float4* p1;   // dir.yz, invDir.xy
     float4* p2;   // invDir.z, originDivDir.xyz
     float4* p3;   // throughput
-    uint4*  p4;   // pixel slot, sampler salt, dim | depth << 16 | lastSpecular << 31, lastPdfW bits
+    uint4*  p4;   // pixel slot | pass slot << 26, sampler salt, dim (12 bits) | depth << 12 (7) | lastSpecular << 19 | lastMaterial << 20 (12, 0xFFF = none), lastPdfW bits
 };
 
 struct Control
@@ -90,7 +90,7 @@ __device__ __forceinline__ void store_path(const PathBuf& b, uint32_t i, const P
     b.p1[i] = make_float4(ps.ray.dir.y, ps.ray.dir.z, ps.ray.invDir.x, ps.ray.invDir.y);
     b.p2[i] = make_float4(ps.ray.invDir.z, ps.ray.originDivDir.x, ps.ray.originDivDir.y, ps.ray.originDivDir.z);
     b.p3[i] = make_float4(ps.throughput.x, ps.throughput.y, ps.throughput.z, ps.throughput.w);
-    b.p4[i] = make_uint4(ps.pixel | (ps.passSlot << 26), ps.sampler.salt, (ps.sampler.dim & 0xFFFFu) | ((ps.depth & 0x7FFFu) << 16) | (ps.lastSpecular << 31), __float_as_uint(ps.lastPdfW));
+    b.p4[i] = make_uint4(ps.pixel | (ps.passSlot << 26), ps.sampler.salt, (ps.sampler.dim & 0xFFFu) | ((ps.depth & 0x7Fu) << 12) | ((ps.lastSpecular & 1u) << 19) | ((ps.lastMaterial & 0xFFFu) << 20), __float_as_uint(ps.lastPdfW));
 }
 
 __device__ __forceinline__ void load_ray(const PathBuf& b, uint32_t i, Ray& r)
@@ -111,9 +111,10 @@ __device__ __forceinline__ void load_path(const PathBuf& b, uint32_t i, const Wa
     ps.pixel = m.x & 0x03FFFFFFu;
     ps.passSlot = m.x >> 26;
     ps.sampler.salt = m.y;
-    ps.sampler.dim = m.z & 0xFFFFu;
-    ps.depth = (m.z >> 16) & 0x7FFFu;
-    ps.lastSpecular = m.z >> 31;
+    ps.sampler.dim = m.z & 0xFFFu;
+    ps.depth = (m.z >> 12) & 0x7Fu;
+    ps.lastSpecular = (m.z >> 19) & 1u;
+    ps.lastMaterial = (m.z >> 20) == 0xFFFu ? RTB_NO_MATERIAL : (m.z >> 20);
     ps.lastPdfW = __uint_as_float(m.w);
     const uint32_t pix = W.pixelList[ps.pixel];
     const uint32_t x = pix % width, y = pix / width;
@@ -148,13 +149,19 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_traverse(const __gr
     const PathBuf& in = W.buf[depth & 1];
     const uint32_t stride = gridDim.x * blockDim.x;
     TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
+#if RTB_SMEM_STACK > 0
+    __shared__ SharedStackEntry smemStack[RTB_SMEM_STACK * RTB_STACK_THREADS];
+    SharedStackEntry* const sstack = smemStack + threadIdx.x;
+#else
+    SharedStackEntry* const sstack = nullptr;
+#endif
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
     {
         Ray ray;
         load_ray(in, i, ray);
         Hit hit;
         hit.objectId = RTB_INVALID_OBJECT; hit.subObjectId = 0; hit.distance = INFINITY; hit.u = 0.0f; hit.v = 0.0f;
-        scene_traverse<kCount>(S, ray, hit, &cnt);
+        scene_traverse<kCount>(S, ray, hit, &cnt, sstack);
         W.hit0[i] = make_uint4(hit.objectId, hit.subObjectId, __float_as_uint(hit.distance), __float_as_uint(hit.u));
         W.hit1[i] = hit.v;
     }
@@ -188,6 +195,7 @@ struct DeviceSink
     __device__ void end_lights(const V4& thr) { lightThr = thr; }
 };
 
+template <bool kTex>
 __global__ void __launch_bounds__(128, RTB_SHADE_MINBLOCKS) k_shade(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const __grid_constant__ Wavefront W, uint32_t depth)
 {
     const uint32_t count = W.ctl->pathCount[depth];
@@ -215,9 +223,9 @@ __global__ void __launch_bounds__(128, RTB_SHADE_MINBLOCKS) k_shade(const __grid
             const float4 pc = W.passColor[colorIndex];
             DeviceSink sink(W, i * W.raysPerPath);
             sink.result = v3(pc.x, pc.y, pc.z);
-            if (P.renderer == RTB_RENDERER_PATH_TRACER_MIS) alive = shade_vertex_mis(S, P, ps, hit, sink, numShadow);
-            else if (P.renderer == RTB_RENDERER_PATH_TRACER) alive = shade_vertex_pt(S, P, ps, hit, sink);
-            else shade_debug(S, P, ps, hit, sink);
+            if (P.renderer == RTB_RENDERER_PATH_TRACER_MIS) alive = shade_vertex_mis<kTex>(S, P, ps, hit, sink, numShadow);
+            else if (P.renderer == RTB_RENDERER_PATH_TRACER) alive = shade_vertex_pt<kTex>(S, P, ps, hit, sink);
+            else shade_debug<kTex>(S, P, ps, hit, sink);
             if (sink.dirty) W.passColor[colorIndex] = make_float4(sink.result.x, sink.result.y, sink.result.z, 0.0f);
             if (numShadow)
             {
@@ -282,6 +290,12 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
     const uint32_t lane = threadIdx.x & 31u;
     unsigned long long visibleLocal = 0;
     TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
+#if RTB_SMEM_STACK > 0
+    __shared__ SharedStackEntry smemStack[RTB_SMEM_STACK * RTB_STACK_THREADS];
+    SharedStackEntry* const sstack = smemStack + threadIdx.x;
+#else
+    SharedStackEntry* const sstack = nullptr;
+#endif
 #if RTB_SHADOW_REFILL
     // persistent warps with dynamic fetch (experiment, see above)
     ShadowWalk walk;
@@ -307,7 +321,7 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
                     const float4 a = W.sr0[j], b = W.sr1[j], c = W.sr2[j], d = W.sr3[j];
                     Ray ray;
                     ray.origin = v3(a.x, a.y, a.z); ray.dir = v3(b.x, b.y, b.z); ray.invDir = v3(c.x, c.y, c.z); ray.originDivDir = v3(d.x, d.y, d.z);
-                    if (walk.begin(S, stack, ray, a.w)) active = true;
+                    if (walk.begin(S, stack, ray, a.w, sstack)) active = true;
                     else visibleLocal++;
                 }
             }
@@ -319,7 +333,7 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
         }
         if (active)
         {
-            const int r = walk.step<kCount>(S, stack, &cnt);
+            const int r = walk.step<kCount>(S, stack, &cnt, sstack);
             if (r != ShadowWalk::kContinue)
             {
                 active = false;
@@ -337,7 +351,7 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
         const float4 a = W.sr0[j], b = W.sr1[j], c = W.sr2[j], d = W.sr3[j];
         Ray ray;
         ray.origin = v3(a.x, a.y, a.z); ray.dir = v3(b.x, b.y, b.z); ray.invDir = v3(c.x, c.y, c.z); ray.originDivDir = v3(d.x, d.y, d.z);
-        const bool occluded = scene_traverse_shadow<kCount>(S, ray, a.w, &cnt);
+        const bool occluded = scene_traverse_shadow<kCount>(S, ray, a.w, &cnt, sstack);
         if (occluded)
         {
             // SampleLight returns RayColor::Zero() for an occluded light (PathTracerMIS.cpp:92-96)
@@ -418,6 +432,12 @@ __global__ void __launch_bounds__(128) k_trace_batch(const __grid_constant__ Sce
 {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
+#if RTB_SMEM_STACK > 0
+    __shared__ SharedStackEntry smemStack[RTB_SMEM_STACK * RTB_STACK_THREADS];
+    SharedStackEntry* const sstack = smemStack + threadIdx.x;
+#else
+    SharedStackEntry* const sstack = nullptr;
+#endif
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     {
         const float4* p = reinterpret_cast<const float4*>(rays + i);
@@ -430,13 +450,13 @@ __global__ void __launch_bounds__(128) k_trace_batch(const __grid_constant__ Sce
             // hits[i].distance is the preset tMax (HitPoint::distance, PathTracerMIS.cpp:86)
             const float tMax = hits[i].distance;
             out.objectId = RTB_INVALID_OBJECT; out.subObjectId = 0; out.distance = tMax; out.u = 0.0f; out.v = 0.0f;
-            out.occluded = scene_traverse_shadow<kCount>(S, ray, tMax, &cnt) ? 1u : 0u;
+            out.occluded = scene_traverse_shadow<kCount>(S, ray, tMax, &cnt, sstack) ? 1u : 0u;
         }
         else
         {
             Hit hit;
             hit.objectId = RTB_INVALID_OBJECT; hit.subObjectId = 0; hit.distance = INFINITY; hit.u = 0.0f; hit.v = 0.0f;
-            scene_traverse<kCount>(S, ray, hit, &cnt);
+            scene_traverse<kCount>(S, ray, hit, &cnt, sstack);
             out.objectId = hit.objectId; out.subObjectId = hit.subObjectId; out.distance = hit.distance; out.u = hit.u; out.v = hit.v; out.occluded = 0;
         }
         hits[i] = out;
@@ -540,6 +560,9 @@ struct RtbContext
     DevArray<DLight> lights;
     DevArray<uint32_t> globalLights;
     DevArray<uint16_t> blueNoise;
+    DevArray<DTexture> textures;
+    std::vector<DevArray<float>> texels;      // one per texture (empty for procedural ones)
+    DevArray<RtbMaterialTextures> materialTextures;
     SceneView view;
     uint32_t numLights = 0;
 
@@ -589,6 +612,9 @@ static void free_scene(RtbContext* c)
     for (DeviceMesh& m : c->meshes) { m.nodes.release(); m.tris.release(); m.indices.release(); m.shading.release(); m.materialIds.release(); }
     c->meshes.clear();
     c->meshViews.release(); c->materials.release(); c->lights.release(); c->globalLights.release();
+    c->textures.release(); c->materialTextures.release();
+    for (DevArray<float>& t : c->texels) t.release();
+    c->texels.clear();
     c->hasScene = false;
 }
 
@@ -712,6 +738,8 @@ int rtb_upload_scene(RtbContext* c, const RtbSceneDesc* scene)
     HostScene hs;
     std::string err;
     if (!build_host_scene(*scene, hs, err)) return fail(RTB_ERR_INVALID_ARG, "rtb_upload_scene: %s", err.c_str());
+    if (!hs.materialTextures.empty() && hs.materials.size() > 4094u)     // 12 bits of the packed path state (PathState::lastMaterial)
+        return fail(RTB_ERR_UNSUPPORTED, "rtb_upload_scene: %zu materials; textured scenes are limited to 4094", hs.materials.size());
     RTB_CUDA(cudaStreamSynchronize(c->stream));
     free_scene(c);
     cudaStream_t s = c->stream;
@@ -739,12 +767,25 @@ int rtb_upload_scene(RtbContext* c, const RtbSceneDesc* scene)
         v.numVertices = (uint32_t)hm.shading.size(); v.numMaterials = (uint32_t)hm.materialIds.size();
     }
     RTB_CUDA(c->meshViews.upload(views, s));
+    // textures: bitmap texels stay float4 in HBM (rtb_texture.h); the descriptors get the device pointers
+    c->texels.resize(hs.textures.size());
+    for (size_t i = 0; i < hs.textures.size(); ++i)
+    {
+        if (!hs.texelSources[i]) continue;
+        const size_t n = (size_t)hs.textures[i].width * hs.textures[i].height * 4;
+        RTB_CUDA(c->texels[i].alloc(n));
+        RTB_CUDA(cudaMemcpyAsync(c->texels[i].ptr, hs.texelSources[i], n * sizeof(float), cudaMemcpyHostToDevice, s));
+        hs.textures[i].texels = c->texels[i].ptr;
+    }
+    RTB_CUDA(c->textures.upload(hs.textures, s));
+    RTB_CUDA(c->materialTextures.upload(hs.materialTextures, s));
     RTB_CUDA(cudaStreamSynchronize(s));   // host vectors go out of scope
 
     SceneView& v = c->view;
     v.tlas = c->tlas.ptr; v.objTrace = c->objTrace.ptr; v.objShade = c->objShade.ptr; v.shapes = c->shapes.ptr;
     v.meshes = c->meshViews.ptr; v.materials = c->materials.ptr; v.lights = c->lights.ptr; v.globalLights = c->globalLights.ptr;
     v.blueNoise = c->blueNoise.ptr;
+    v.textures = c->textures.ptr; v.materialTextures = c->materialTextures.ptr;
     v.numTlasNodes = (uint32_t)hs.tlas.size(); v.numObjects = (uint32_t)hs.objTrace.size();
     v.numLights = (uint32_t)hs.lights.size(); v.numGlobalLights = (uint32_t)hs.globalLights.size();
     c->numLights = v.numLights;
@@ -835,6 +876,7 @@ static int fill_pass_params(RtbContext* c, const RtbPassDesc* pass, PassParams& 
     if (pass->maxRayDepth >= 255u || pass->maxRayDepth >= RTB_MAX_DEPTH_SLOTS) return fail(RTB_ERR_INVALID_ARG, "maxRayDepth %u too large (limit %u)", pass->maxRayDepth, RTB_MAX_DEPTH_SLOTS - 1);
     if (pass->camera.barrelDistortionVariableFactor != 0.0f) return fail(RTB_ERR_UNSUPPORTED, "variable barrel distortion draws from a per-thread RNG in the reference and is not supported");
     if (pass->numSeedDims > 0 && !pass->seed) return fail(RTB_ERR_INVALID_ARG, "seed pointer is null");
+    if (pass->numSeedDims > 4095u) return fail(RTB_ERR_INVALID_ARG, "numSeedDims %u too large (limit 4095)", pass->numSeedDims);   // 12 bits of the packed path state
     memset(&P, 0, sizeof(P));
     P.camLocalToWorld = load_m4(pass->camera.localToWorld);
     P.aspectRatio = pass->camera.aspectRatio; P.tanHalfFoV = pass->camera.tanHalfFoV;
@@ -920,12 +962,14 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
     if (prof) marks.push_back(next_event(c, ev));
     const uint32_t depthLimit = pass->renderer == RTB_RENDERER_DEBUG ? 0u : pass->maxRayDepth;
     const bool shadows = pass->renderer == RTB_RENDERER_PATH_TRACER_MIS && c->numLights > 0;
+    const bool textured = c->textures.count > 0;     // scenes without textures run the k_shade that has no texture calls compiled in
     for (uint32_t d = 0; d <= depthLimit; ++d)
     {
         if (count) k_traverse<true><<<blocks128, 128, 0, s>>>(c->view, W, d);
         else k_traverse<false><<<blocks128, 128, 0, s>>>(c->view, W, d);
         if (prof) marks.push_back(next_event(c, ev));
-        k_shade<<<blocks128, 128, 0, s>>>(c->view, P, W, d);
+        if (textured) k_shade<true><<<blocks128, 128, 0, s>>>(c->view, P, W, d);
+        else k_shade<false><<<blocks128, 128, 0, s>>>(c->view, P, W, d);
         if (prof) marks.push_back(next_event(c, ev));
         if (shadows)
         {
@@ -964,6 +1008,10 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
         RTB_CUDA(cudaMemcpy(&h, c->ctl.ptr, sizeof(Control), cudaMemcpyDeviceToHost));
         for (uint32_t d = 0; d <= depthLimit; ++d) t.traverseRays += h.pathCount[d];
         for (uint32_t d = 0; d <= depthLimit; ++d) t.shadowRays += h.shadowRayCount[d];
+        if (getenv("RTB_PROFILE_DEPTHS"))      // development aid: per-depth breakdown of this wavefront
+            for (uint32_t d = 0; d <= depthLimit; ++d)
+                fprintf(stderr, "depth %u: paths %u traverse %.3f ms, shade %.3f ms, shadow rays %u shadow+resolve %.3f ms\n", d, h.pathCount[d],
+                        ms(1 + 3 * d, 2 + 3 * d), ms(2 + 3 * d, 3 + 3 * d), h.shadowRayCount[d], ms(3 + 3 * d, 4 + 3 * d));
     }
     return RTB_OK;
 }

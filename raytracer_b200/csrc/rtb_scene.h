@@ -24,6 +24,7 @@ struct __attribute__((aligned(16))) DNode   // == RtbBvhNode
 struct __attribute__((aligned(16))) DTri { float v0x, v0y, v0z, pad0, e1x, e1y, e1z, pad1, e2x, e2y, e2z, pad2; };
 
 #define RTB_NO_SHAPE 0xFFFFFFFFu
+#define RTB_NO_MATERIAL 0xFFFFFFFFu
 
 // traversal-time view of one traceable object (objectId == index)
 struct __attribute__((aligned(16))) DObjectTrace
@@ -65,9 +66,22 @@ struct __attribute__((aligned(16))) DLight
 {
     uint32_t type, flags, shapeIndex, isDelta;
     V4       color;
-    float    cosAngle, pad0, pad1, pad2;
+    float    cosAngle;
+    uint32_t textureIndex;   // background light: environment map (RTB_NO_TEXTURE = none)
+    float    pad1, pad2;
     M4       transform;      // light -> world
     M4       invTransform;   // world -> light
+};
+
+// one ITexture (rtb_texture.h); bitmap texels = width*height RGBA float quadruples in HBM, row-major: one bilinear
+// lookup is 4 aligned 16-byte loads
+struct __attribute__((aligned(16))) DTexture
+{
+    uint32_t type, width, height, numOctaves;
+    uint32_t texA, texB, texWeight, pad0;
+    V4       colorA, colorB;
+    const float* texels;
+    uint64_t pad1;
 };
 
 struct SceneView
@@ -81,6 +95,8 @@ struct SceneView
     const DLight*       lights;
     const uint32_t*     globalLights;
     const uint16_t*     blueNoise;       // 128*128*4, may be null
+    const DTexture*     textures;        // null without textures
+    const RtbMaterialTextures* materialTextures;   // per material, null without textured materials
     uint32_t            numTlasNodes;
     uint32_t            numObjects;
     uint32_t            numLights;

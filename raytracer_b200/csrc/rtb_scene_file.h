@@ -12,6 +12,11 @@
 //   u32 n, RtbLight[n]
 //   u32 n, u32[n]               global lights
 //   RtbCamera, f32 fieldOfView
+// version 2 (written only when the scene has textures, so texture-less files stay readable by v1 readers) appends
+//   u32 n, per texture { u32 type, width, height, numOctaves, texA, texB, texWeight, pad; f32 colorA[4], colorB[4];
+//                        f32 texels[width*height*4] for bitmaps }
+//   u32 n (0 or numMaterials), RtbMaterialTextures[n]
+//   u32 n (0 or numLights), u32[n]      light textures
 #pragma once
 
 #include <cstdio>
@@ -44,6 +49,17 @@ struct SceneFile
     std::vector<uint32_t> globalLights;
     RtbCamera camera;
     float fieldOfView = 0.0f;
+    struct Texture
+    {
+        RtbTexture desc;              // desc.texels is filled by View()
+        std::vector<float> texels;
+    };
+    std::vector<Texture> textures;
+    std::vector<RtbTexture> textureViews;
+    std::vector<RtbMaterialTextures> materialTextures;   // empty or one per material
+    std::vector<uint32_t> lightTextures;                 // empty or one per light
+
+    bool HasTextures() const { return !textures.empty() || !materialTextures.empty() || !lightTextures.empty(); }
 
     SceneFile() { memset(&camera, 0, sizeof(camera)); }
 
@@ -70,6 +86,15 @@ struct SceneFile
         d.numMaterials = (uint32_t)materials.size();      d.materials = materials.data();
         d.numLights = (uint32_t)lights.size();            d.lights = lights.data();
         d.numGlobalLights = (uint32_t)globalLights.size(); d.globalLights = globalLights.data();
+        textureViews.resize(textures.size());
+        for (size_t i = 0; i < textures.size(); ++i)
+        {
+            textureViews[i] = textures[i].desc;
+            textureViews[i].texels = textures[i].texels.empty() ? nullptr : textures[i].texels.data();
+        }
+        d.numTextures = (uint32_t)textureViews.size();    d.textures = textureViews.empty() ? nullptr : textureViews.data();
+        d.materialTextures = materialTextures.size() == materials.size() && !materials.empty() ? materialTextures.data() : nullptr;
+        d.lightTextures = lightTextures.size() == lights.size() && !lights.empty() ? lightTextures.data() : nullptr;
         return d;
     }
 
@@ -92,7 +117,7 @@ struct SceneFile
     bool LoadFrom(FILE* f, std::string& err)
     {
         uint32_t magic = 0, version = 0, n = 0;
-        if (!ReadU32(f, magic) || !ReadU32(f, version) || magic != 0x53425452u || version != 1) { err = "not an RTBS v1 file"; return false; }
+        if (!ReadU32(f, magic) || !ReadU32(f, version) || magic != 0x53425452u || (version != 1 && version != 2)) { err = "not an RTBS v1/v2 file"; return false; }
         if (!ReadU32(f, n) || !ReadVec(f, tlas, n)) { err = "truncated (tlas)"; return false; }
         if (!ReadU32(f, n) || !ReadVec(f, objects, n)) { err = "truncated (objects)"; return false; }
         if (!ReadU32(f, n) || !ReadVec(f, shapes, n)) { err = "truncated (shapes)"; return false; }
@@ -110,6 +135,23 @@ struct SceneFile
         if (!ReadU32(f, n) || !ReadVec(f, lights, n)) { err = "truncated (lights)"; return false; }
         if (!ReadU32(f, n) || !ReadVec(f, globalLights, n)) { err = "truncated (global lights)"; return false; }
         if (fread(&camera, sizeof(camera), 1, f) != 1 || fread(&fieldOfView, 4, 1, f) != 1) { err = "truncated (camera)"; return false; }
+        textures.clear(); materialTextures.clear(); lightTextures.clear();
+        if (version >= 2)
+        {
+            if (!ReadU32(f, n)) { err = "truncated (textures)"; return false; }
+            textures.resize(n);
+            for (Texture& t : textures)
+            {
+                memset(&t.desc, 0, sizeof(t.desc));
+                uint32_t h[8];
+                if (fread(h, 4, 8, f) != 8 || fread(t.desc.colorA, 4, 4, f) != 4 || fread(t.desc.colorB, 4, 4, f) != 4) { err = "truncated (texture header)"; return false; }
+                t.desc.type = h[0]; t.desc.width = h[1]; t.desc.height = h[2]; t.desc.numOctaves = h[3];
+                t.desc.texA = h[4]; t.desc.texB = h[5]; t.desc.texWeight = h[6];
+                if (t.desc.type == RTB_TEXTURE_BITMAP && !ReadVec(f, t.texels, (size_t)t.desc.width * t.desc.height * 4)) { err = "truncated (texels)"; return false; }
+            }
+            if (!ReadU32(f, n) || !ReadVec(f, materialTextures, n)) { err = "truncated (material textures)"; return false; }
+            if (!ReadU32(f, n) || !ReadVec(f, lightTextures, n)) { err = "truncated (light textures)"; return false; }
+        }
         return true;
     }
 
@@ -120,7 +162,7 @@ struct SceneFile
     {
         FILE* f = fopen(path.c_str(), "wb");
         if (!f) return false;
-        WriteU32(f, 0x53425452u); WriteU32(f, 1);
+        WriteU32(f, 0x53425452u); WriteU32(f, HasTextures() ? 2 : 1);
         WriteU32(f, (uint32_t)tlas.size()); WriteVec(f, tlas);
         WriteU32(f, (uint32_t)objects.size()); WriteVec(f, objects);
         WriteU32(f, (uint32_t)shapes.size()); WriteVec(f, shapes);
@@ -136,6 +178,18 @@ struct SceneFile
         WriteU32(f, (uint32_t)globalLights.size()); WriteVec(f, globalLights);
         fwrite(&camera, sizeof(camera), 1, f);
         fwrite(&fieldOfView, 4, 1, f);
+        if (HasTextures())
+        {
+            WriteU32(f, (uint32_t)textures.size());
+            for (const Texture& t : textures)
+            {
+                const uint32_t h[8] = { t.desc.type, t.desc.width, t.desc.height, t.desc.numOctaves, t.desc.texA, t.desc.texB, t.desc.texWeight, 0u };
+                fwrite(h, 4, 8, f); fwrite(t.desc.colorA, 4, 4, f); fwrite(t.desc.colorB, 4, 4, f);
+                if (t.desc.type == RTB_TEXTURE_BITMAP) WriteVec(f, t.texels);
+            }
+            WriteU32(f, (uint32_t)materialTextures.size()); WriteVec(f, materialTextures);
+            WriteU32(f, (uint32_t)lightTextures.size()); WriteVec(f, lightTextures);
+        }
         fclose(f);
         return true;
     }

@@ -10,6 +10,7 @@
 
 #include "rtb_trace.h"
 #include "rtb_sampler.h"
+#include "rtb_texture.h"
 
 namespace rtb {
 
@@ -93,7 +94,9 @@ RTB_HD int32_t cube_side(const V3& p, float& outU, float& outV)
 
 // Scene::EvaluateIntersection (+ per-shape EvaluateIntersection + Material::EvaluateShadingData).
 // `wantMaterial` is false for light hits (LightSceneObject::EvaluateIntersection leaves the material untouched).
-RTB_HD void evaluate_intersection(const SceneView& S, const Ray& ray, const Hit& hit, Vertex& vx)
+// kTex = false compiles the texture lookups out (scenes without textures run a k_shade without the calls)
+template <bool kTex = true>
+RTB_HD void evaluate_intersection(const SceneView& S, const Ray& ray, const Hit& hit, Vertex& vx, uint32_t staleMaterial)
 {
     const DObjectShade& obj = S.objShade[hit.objectId];
     const M4& transform = obj.transform;
@@ -157,7 +160,24 @@ RTB_HD void evaluate_intersection(const SceneView& S, const Ray& ray, const Hit&
         normal = normalize3(n);
     }
 
-    // Scene.cpp:339-348 (no normal maps in this contract)
+    // normal mapping, Scene.cpp:323-337.  A light object does not set IntersectionData::material, so the reference
+    // applies the normal map of the material the path bounced from (see PathState::lastMaterial), with the light
+    // shape's own texture coordinates; on a camera ray the material is still null and nothing is applied.
+    const uint32_t normalMapMaterial = obj.kind == RTB_OBJECT_SHAPE ? vx.materialIndex : staleMaterial;
+    if (kTex && S.materialTextures != nullptr && normalMapMaterial != RTB_NO_MATERIAL)
+    {
+        const RtbMaterialTextures& mt = S.materialTextures[normalMapMaterial];
+        if (mt.normalMap != RTB_NO_TEXTURE)
+        {
+            const V3 bitangent = cross3(tangent, normal);
+            const V3 localNormal = material_normal_vector(S, mt, vx.texU, vx.texV);
+            V3 newNormal = tangent * localNormal.x;
+            newNormal = mul_add(bitangent, localNormal.y, newNormal);
+            newNormal = mul_add(normal, localNormal.z, newNormal);
+            normal = normalize3(newNormal);             // FastNormalized3 (exact in the oracle)
+        }
+    }
+    // Scene.cpp:339-348
     tangent = normalize3(orthogonalize(tangent, normal));
     vx.normal = transform_vector(transform, normal);
     vx.tangent = transform_vector(transform, tangent);
@@ -165,7 +185,9 @@ RTB_HD void evaluate_intersection(const SceneView& S, const Ray& ray, const Hit&
     vx.position = worldPosition;
 }
 
-// Material::EvaluateShadingData (constant parameters), Material.cpp:151-158
+// Material::EvaluateShadingData, Material.cpp:151-158: every parameter is baseValue * texture(uv) when it has a texture
+// (MaterialParameter::Evaluate, MaterialParameter.h:22-32; a float parameter takes the texture's x lane)
+template <bool kTex = true>
 RTB_HD void evaluate_shading_data(const SceneView& S, Vertex& vx)
 {
     const RtbMaterial& m = S.materials[vx.materialIndex];
@@ -173,6 +195,14 @@ RTB_HD void evaluate_shading_data(const SceneView& S, Vertex& vx)
     vx.emission = v4(m.emission[0], m.emission[1], m.emission[2], m.emission[3]);
     vx.roughness = m.roughness; vx.metalness = m.metalness; vx.IoR = m.IoR; vx.K = m.K;
     vx.bsdf = m.bsdf;
+    if (kTex && S.materialTextures != nullptr)
+    {
+        const RtbMaterialTextures& mt = S.materialTextures[vx.materialIndex];
+        if (mt.baseColor != RTB_NO_TEXTURE) vx.baseColor = vx.baseColor * texture_evaluate(S, mt.baseColor, vx.texU, vx.texV);
+        if (mt.emission != RTB_NO_TEXTURE) vx.emission = vx.emission * texture_evaluate(S, mt.emission, vx.texU, vx.texV);
+        if (mt.roughness != RTB_NO_TEXTURE) vx.roughness = vx.roughness * texture_evaluate(S, mt.roughness, vx.texU, vx.texV).x;
+        if (mt.metalness != RTB_NO_TEXTURE) vx.metalness = vx.metalness * texture_evaluate(S, mt.metalness, vx.texU, vx.texV).x;
+    }
 }
 
 // ---- Microfacet (GGX), Microfacet.h:10-60 -----------------------------------------------------------------------
@@ -713,7 +743,20 @@ RTB_HD float shape_pdf(const RtbShape& s, const V3& ref, const V3& point)
 
 struct IlluminateResult { V3 directionToLight; float distance, directPdfW, cosAtLight; };
 
+// BackgroundLight::GetBackgroundColor, BackgroundLight.cpp:45-61: colour * max(0, environment map at the spherical
+// coordinates of `dir`)
+template <bool kTex>
+RTB_HD V4 background_color(const SceneView& S, const DLight& light, const V3& dir)
+{
+    if (!kTex || light.textureIndex == RTB_NO_TEXTURE) return light.color;
+    float u, v;
+    cartesian_to_spherical(dir, u, v);
+    const V4 t = texture_evaluate(S, light.textureIndex, u, v);
+    return light.color * v4(sse_max(0.0f, t.x), sse_max(0.0f, t.y), sse_max(0.0f, t.z), sse_max(0.0f, t.w));
+}
+
 // ILight::Illuminate for every light type; returns the radiance (RayColor, 4 lanes)
+template <bool kTex = true>
 RTB_HD V4 light_illuminate(const SceneView& S, const DLight& light, const Vertex& vx, float u0, float u1, float u2, IlluminateResult& out)
 {
     out.directionToLight = v3s(0.0f); out.distance = -1.0f; out.directPdfW = -1.0f; out.cosAtLight = -1.0f;
@@ -739,7 +782,7 @@ RTB_HD V4 light_illuminate(const SceneView& S, const DLight& light, const Vertex
         out.directPdfW = uniform_hemisphere_pdf();
         out.distance = FLT_MAX;
         out.cosAtLight = 1.0f;
-        return light.color;
+        return background_color<kTex>(S, light, out.directionToLight);      // world-space direction ("TODO include light rotation")
     }
     case RTB_LIGHT_DIRECTIONAL:
     {
@@ -791,6 +834,7 @@ RTB_HD V4 light_illuminate(const SceneView& S, const DLight& light, const Vertex
 
 // ILight::GetRadiance for a ray that hit the light (area) or escaped (background / directional).
 // `lightRay` is the ray in light space, `lightSpaceHit` the hit point in light space.
+template <bool kTex = true>
 RTB_HD V4 light_radiance(const SceneView& S, const DLight& light, const Ray& lightRay, const V3& lightSpaceHit, float cosAtLight, float& outDirectPdfA)
 {
     switch (light.type)
@@ -803,7 +847,7 @@ RTB_HD V4 light_radiance(const SceneView& S, const DLight& light, const Ray& lig
     case RTB_LIGHT_BACKGROUND:
         // BackgroundLight::GetRadiance, BackgroundLight.cpp:78-90
         outDirectPdfA = uniform_hemisphere_pdf();
-        return light.color;
+        return background_color<kTex>(S, light, lightRay.dir);               // param.ray = the light-space ray
     case RTB_LIGHT_DIRECTIONAL:
         // DirectionalLight::GetRadiance, DirectionalLight.cpp:93-118
         if (light.isDelta) return v4s(0.0f);

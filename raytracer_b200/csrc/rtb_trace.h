@@ -236,6 +236,45 @@ RTB_HD bool analytic_shadow(const DObjectTrace& obj, const Ray& ray, float maxDi
 // descend into is ever fetched again: memory traffic is exactly one 64-byte block per visited inner node.
 struct StackEntry { uint32_t a, b; };
 
+// RTB_SMEM_STACK = K > 0: the K lowest stack entries of every thread live in shared memory (entry i of thread t at
+// sstack[i * RTB_STACK_THREADS + t]: whatever entry each lane of a warp touches, the 32 lanes hit 32 different
+// 8-byte bank pairs, i.e. always 2 conflict-free wavefronts), deeper entries stay in the local-memory array.
+// Divergent lanes pushing / popping at different depths of a local-memory stack cost one L1 wavefront per distinct
+// depth instead.
+#ifndef RTB_SMEM_STACK
+#define RTB_SMEM_STACK 0
+#endif
+#define RTB_STACK_THREADS 128
+#if defined(__CUDA_ARCH__) && RTB_SMEM_STACK > 0
+#define RTB_SSTACK 1
+typedef uint2 SharedStackEntry;
+#else
+#define RTB_SSTACK 0
+struct SharedStackEntry { uint32_t x, y; };
+#endif
+
+RTB_HD void stk_put(StackEntry* stack, SharedStackEntry* sstack, uint32_t i, uint32_t a, uint32_t b)
+{
+#if RTB_SSTACK
+    if (i < RTB_SMEM_STACK) { sstack[i * RTB_STACK_THREADS] = make_uint2(a, b); return; }
+    i -= RTB_SMEM_STACK;
+#else
+    (void)sstack;
+#endif
+    stack[i].a = a; stack[i].b = b;
+}
+
+RTB_HD StackEntry stk_get(const StackEntry* stack, const SharedStackEntry* sstack, uint32_t i)
+{
+#if RTB_SSTACK
+    if (i < RTB_SMEM_STACK) { const uint2 v = sstack[i * RTB_STACK_THREADS]; StackEntry e; e.a = v.x; e.b = v.y; return e; }
+    i -= RTB_SMEM_STACK;
+#else
+    (void)sstack;
+#endif
+    return stack[i];
+}
+
 RTB_HD void node_header(const DNode* nodes, uint32_t index, uint32_t& childIndex, uint32_t& leafInfo)
 {
     childIndex = nodes[index].childIndex;
@@ -253,7 +292,7 @@ RTB_HD void node_header(const DNode* nodes, uint32_t index, uint32_t& childIndex
 // refreshing originDivDir (PathTracerMIS.cpp:392-393) and that stale value is part of the reference's behaviour;
 // Traverse_Object rebuilds the ray in object space.
 template <bool kCount>
-RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, TraceCounters* cnt)
+RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, TraceCounters* cnt, SharedStackEntry* sstack = nullptr)
 {
     if (S.numObjects == 0) return;
     StackEntry stack[RTB_STACK_SIZE];
@@ -270,7 +309,7 @@ RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, Tr
     bool have = false;                 // {curChild, curInfo} describe a node still to be visited
     uint32_t curChild = 0, curInfo = 0;
 
-    if (S.numObjects == 1) { stack[0].a = 0u; stack[0].b = RTB_ENTRY_OBJECT; stackSize = 1; }      // BVH bypass, Scene.cpp:231-235
+    if (S.numObjects == 1) { stk_put(stack, sstack, 0, 0u, RTB_ENTRY_OBJECT); stackSize = 1; }      // BVH bypass, Scene.cpp:231-235
     else if (S.numTlasNodes != 0) { node_header(S.tlas, 0, curChild, curInfo); have = true; }
 
     for (;;)
@@ -299,10 +338,7 @@ RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, Tr
             {
                 // visit the nearer child first, push the other (Traversal_Single.h:65-75)
                 const bool bFirst = distanceB < distanceA;
-                StackEntry e;
-                e.a = bFirst ? a.childIndex : b.childIndex;
-                e.b = bFirst ? a.leafInfo : b.leafInfo;
-                stack[stackSize++] = e;
+                stk_put(stack, sstack, stackSize++, bFirst ? a.childIndex : b.childIndex, bFirst ? a.leafInfo : b.leafInfo);
                 curChild = bFirst ? b.childIndex : a.childIndex;
                 curInfo = bFirst ? b.leafInfo : a.leafInfo;
             }
@@ -312,7 +348,7 @@ RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, Tr
             {
                 // both children missed: take the next pending node of this mesh right here, so that the lane stays in
                 // the inner loop with the rest of its warp instead of idling until every lane has left it
-                const StackEntry e = stack[--stackSize];
+                const StackEntry e = stk_get(stack, sstack, --stackSize);
                 curChild = e.a; curInfo = e.b;
             }
             else have = false;
@@ -347,7 +383,7 @@ RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, Tr
             else
             {
                 // Scene::Traverse_Leaf, Scene.cpp:167-178: objects in order -> push in reverse
-                for (uint32_t i = numLeaves; i-- > 0;) { stack[stackSize].a = curChild + i; stack[stackSize].b = RTB_ENTRY_OBJECT; stackSize++; }
+                for (uint32_t i = numLeaves; i-- > 0;) { stk_put(stack, sstack, stackSize, curChild + i, RTB_ENTRY_OBJECT); stackSize++; }
             }
             have = false;
         }
@@ -359,7 +395,7 @@ RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, Tr
             inBlas = false; popFloor = RTB_STACK_SIZE; nodes = S.tlas; ray = worldRay; finite = worldFinite;
         }
         if (stackSize == 0) break;
-        const StackEntry e = stack[--stackSize];
+        const StackEntry e = stk_get(stack, sstack, --stackSize);
         if (e.b == RTB_ENTRY_OBJECT)
         {
             // Scene::Traverse_Object, Scene.cpp:128-145
@@ -412,7 +448,7 @@ struct ShadowWalk
     uint32_t pendChild, pendInfo;          // a mesh leaf whose triangle tests are postponed
 
     // false: nothing to traverse (the ray is unoccluded)
-    RTB_HD bool begin(const SceneView& S, StackEntry* stack, const Ray& worldRay, float tMax)
+    RTB_HD bool begin(const SceneView& S, StackEntry* stack, const Ray& worldRay, float tMax, SharedStackEntry* sstack = nullptr)
     {
         if (S.numObjects == 0) return false;
         stackSize = 0; blasBase = 0; popFloor = RTB_STACK_SIZE; inBlas = false;
@@ -420,7 +456,7 @@ struct ShadowWalk
         ray = worldRay; world = worldRay; maxDistance = tMax;
         worldFinite = ray_is_finite(worldRay); finite = worldFinite;
         have = false; curChild = 0; curInfo = 0; pendChild = 0; pendInfo = 0;
-        if (S.numObjects == 1) { stack[0].a = 0u; stack[0].b = RTB_ENTRY_OBJECT; stackSize = 1; }
+        if (S.numObjects == 1) { stk_put(stack, sstack, 0, 0u, RTB_ENTRY_OBJECT); stackSize = 1; }
         else if (S.numTlasNodes != 0) { node_header(S.tlas, 0, curChild, curInfo); have = true; }
         else return false;
         return true;
@@ -444,7 +480,7 @@ struct ShadowWalk
     }
 
     template <bool kCount>
-    RTB_HD int step(const SceneView& S, StackEntry* stack, TraceCounters* cnt)
+    RTB_HD int step(const SceneView& S, StackEntry* stack, TraceCounters* cnt, SharedStackEntry* sstack = nullptr)
     {
         // (the form of this loop matters: `while (have) { if (leaf) break; ... }` WITHOUT the postponing measured 35 %
         //  slower than `while (have && !leaf)`: ptxas places the reconvergence points differently)
@@ -455,7 +491,7 @@ struct ShadowWalk
                 if (inBlas && pendInfo == 0 && stackSize > popFloor)
                 {
                     pendChild = curChild; pendInfo = curInfo;
-                    const StackEntry e = stack[--stackSize];
+                    const StackEntry e = stk_get(stack, sstack, --stackSize);
                     curChild = e.a; curInfo = e.b;
                     continue;
                 }
@@ -481,8 +517,7 @@ struct ShadowWalk
             if (hitA && hitB)
             {
                 const bool swap = distanceB < distanceA;
-                StackEntry e; e.a = swap ? a.childIndex : b.childIndex; e.b = swap ? a.leafInfo : b.leafInfo;
-                stack[stackSize++] = e;
+                stk_put(stack, sstack, stackSize++, swap ? a.childIndex : b.childIndex, swap ? a.leafInfo : b.leafInfo);
                 curChild = swap ? b.childIndex : a.childIndex; curInfo = swap ? b.leafInfo : a.leafInfo;
             }
             else if (hitA) { curChild = a.childIndex; curInfo = a.leafInfo; }
@@ -491,7 +526,7 @@ struct ShadowWalk
             {
                 // both children missed: take the next pending node of this mesh right here, so that the lane stays in
                 // the node loop with the rest of its warp instead of idling until every lane has left it
-                const StackEntry e = stack[--stackSize];
+                const StackEntry e = stk_get(stack, sstack, --stackSize);
                 curChild = e.a; curInfo = e.b;
             }
             else have = false;
@@ -511,7 +546,7 @@ struct ShadowWalk
             else
             {
                 // Scene::Traverse_Leaf_Shadow, Scene.cpp:180-194: one stack entry per object of the top-level leaf
-                for (uint32_t i = RTB_NUM_LEAVES(curInfo); i-- > 0;) { stack[stackSize].a = curChild + i; stack[stackSize].b = RTB_ENTRY_OBJECT; stackSize++; }
+                for (uint32_t i = RTB_NUM_LEAVES(curInfo); i-- > 0;) { stk_put(stack, sstack, stackSize, curChild + i, RTB_ENTRY_OBJECT); stackSize++; }
             }
             have = false;
         }
@@ -521,7 +556,7 @@ struct ShadowWalk
             inBlas = false; popFloor = RTB_STACK_SIZE; nodes = S.tlas; ray = world; finite = worldFinite;
         }
         if (stackSize == 0) return kVisible;
-        const StackEntry e = stack[--stackSize];
+        const StackEntry e = stk_get(stack, sstack, --stackSize);
         if (e.b == RTB_ENTRY_OBJECT)
         {
             // Scene::Traverse_Object_Shadow, Scene.cpp:147-165
@@ -551,14 +586,14 @@ struct ShadowWalk
 };
 
 template <bool kCount>
-RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float maxDistance, TraceCounters* cnt)
+RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float maxDistance, TraceCounters* cnt, SharedStackEntry* sstack = nullptr)
 {
     ShadowWalk w;
     StackEntry stack[RTB_STACK_SIZE];
-    if (!w.begin(S, stack, worldRay, maxDistance)) return false;
+    if (!w.begin(S, stack, worldRay, maxDistance, sstack)) return false;
     for (;;)
     {
-        const int r = w.step<kCount>(S, stack, cnt);
+        const int r = w.step<kCount>(S, stack, cnt, sstack);
         if (r != ShadowWalk::kContinue) return r == ShadowWalk::kOccluded;
     }
 }

@@ -5,6 +5,7 @@
 #include <vector>
 #include <string>
 #include <cstring>
+#include <algorithm>
 
 #include "rtb_trace.h"
 
@@ -29,6 +30,10 @@ struct HostScene
     std::vector<RtbMaterial> materials;
     std::vector<DLight> lights;
     std::vector<uint32_t> globalLights;
+    std::vector<DTexture> textures;                      // texels pointers are patched after the device upload
+    std::vector<const float*> texelSources;              // host texels of every bitmap texture (caller-owned), else null
+    std::vector<RtbMaterialTextures> materialTextures;   // empty = no material has a texture
+    bool hasLightTextures = false;
     uint32_t maxTlasDepth = 0, maxBlasDepth = 0;
 };
 
@@ -79,7 +84,58 @@ inline bool build_host_scene(const RtbSceneDesc& d, HostScene& out, std::string&
     for (uint32_t i = 0; i < d.numMaterials; ++i)
     {
         if (d.materials[i].bsdf > RTB_BSDF_ROUGH_PLASTIC) { err = "unknown BSDF id"; return false; }
-        if (d.materials[i].flags & 1u) { err = "textured materials are not supported by this contract"; return false; }
+        if ((d.materials[i].flags & 1u) && !d.materialTextures) { err = "material is flagged as textured but the scene carries no materialTextures"; return false; }
+    }
+
+    // textures: a mix texture may only reference EARLIER textures (so there are no cycles) and nests at most RTB_MAX_MIX_DEPTH deep
+    if (d.numTextures && !d.textures) { err = "numTextures > 0 but textures is null"; return false; }
+    out.textures.resize(d.numTextures);
+    out.texelSources.assign(d.numTextures, nullptr);
+    std::vector<uint32_t> mixDepth(d.numTextures, 0u);
+    for (uint32_t i = 0; i < d.numTextures; ++i)
+    {
+        const RtbTexture& s = d.textures[i];
+        DTexture& t = out.textures[i];
+        memset(&t, 0, sizeof(t));
+        t.type = s.type; t.width = s.width; t.height = s.height; t.numOctaves = s.numOctaves;
+        t.texA = s.texA; t.texB = s.texB; t.texWeight = s.texWeight;
+        t.colorA = v4(s.colorA[0], s.colorA[1], s.colorA[2], s.colorA[3]);
+        t.colorB = v4(s.colorB[0], s.colorB[1], s.colorB[2], s.colorB[3]);
+        switch (s.type)
+        {
+        case RTB_TEXTURE_BITMAP:
+            if (s.width == 0 || s.height == 0 || s.width > 65536u || s.height > 65536u || !s.texels) { err = "bitmap texture without texels or with an invalid size"; return false; }
+            out.texelSources[i] = s.texels;
+            break;
+        case RTB_TEXTURE_CHECKERBOARD:
+            break;
+        case RTB_TEXTURE_NOISE:
+            if (s.numOctaves == 0 || s.numOctaves > 20) { err = "noise texture: numOctaves must be in 1..20"; return false; }     // NoiseTexture.cpp:51
+            break;
+        case RTB_TEXTURE_MIX:
+            if (s.texA >= i || s.texB >= i || s.texWeight >= i) { err = "mix texture must reference earlier textures"; return false; }   // MixTexture.cpp:15-17 asserts non-null
+            mixDepth[i] = 1u + std::max(mixDepth[s.texA], std::max(mixDepth[s.texB], mixDepth[s.texWeight]));
+            if (mixDepth[i] > RTB_MAX_MIX_DEPTH) { err = "mix textures are nested too deep"; return false; }
+            break;
+        default:
+            err = "unknown texture type"; return false;
+        }
+    }
+    if (d.materialTextures)
+    {
+        bool any = false;
+        for (uint32_t i = 0; i < d.numMaterials; ++i)
+        {
+            const RtbMaterialTextures& mt = d.materialTextures[i];
+            const uint32_t ids[6] = { mt.baseColor, mt.emission, mt.roughness, mt.metalness, mt.normalMap, mt.maskMap };
+            for (uint32_t id : ids)
+            {
+                if (id == RTB_NO_TEXTURE) continue;
+                if (id >= d.numTextures) { err = "material texture index out of bounds"; return false; }
+                any = true;
+            }
+        }
+        if (any) out.materialTextures.assign(d.materialTextures, d.materialTextures + d.numMaterials);
     }
 
     out.meshes.resize(d.numMeshes);
@@ -124,6 +180,13 @@ inline bool build_host_scene(const RtbSceneDesc& d, HostScene& out, std::string&
         l.type = s.type; l.flags = s.flags; l.shapeIndex = s.shapeIndex; l.isDelta = s.isDelta;
         l.color = v4(s.color[0], s.color[1], s.color[2], s.color[3]);
         l.cosAngle = s.cosAngle;
+        l.textureIndex = RTB_NO_TEXTURE;
+        if (d.lightTextures && d.lightTextures[i] != RTB_NO_TEXTURE)
+        {
+            if (d.lightTextures[i] >= d.numTextures) { err = "light texture index out of bounds"; return false; }
+            // only BackgroundLight evaluates its texture (BackgroundLight.cpp:45-61); AreaLight's is commented out (AreaLight.cpp:49-58, 136-146)
+            if (s.type == RTB_LIGHT_BACKGROUND) { l.textureIndex = d.lightTextures[i]; out.hasLightTextures = true; }
+        }
         l.transform = to_m4(s.transform);
         l.invTransform = to_m4(s.invTransform);
         if (s.type > RTB_LIGHT_SPOT) { err = "unknown light type"; return false; }

@@ -2,7 +2,9 @@
 // Demo/SceneLoader.cpp (692-820; shapes 418-499, lights 501-618, camera 652-690, materials 364-416, transforms
 // 180-207) and Demo/MeshLoader.cpp (120-377: vertex welding by (v, vn, vt) index triple, degenerate-triangle filter,
 // per-face normals, Lengyel tangents).  Errors are reported the way the reference does: a message + `false`.
-// Textures are outside this contract: a scene that references one is rejected with a clear message.
+// Textures follow Demo/SceneLoader.cpp:218-242 (TryParseTextureName) and 269-362 (ParseTexture): a name is first looked
+// up among the scene's "textures", else loaded as a bitmap file relative to the data path; a file that cannot be
+// loaded leaves the parameter untextured, as in the reference.
 #pragma once
 
 #include <cstdio>
@@ -17,6 +19,7 @@ namespace rt {
 namespace helpers {
 
 using MaterialsMap = std::map<std::string, MaterialPtr>;
+using TexturesMap = std::map<std::string, TexturePtr>;
 
 struct LoadError { std::string message; };
 
@@ -78,7 +81,12 @@ inline float NextObjReal(const char*& tok)
     return static_cast<float>(v);
 }
 
-struct ObjMaterial { std::string name; float diffuse[3] = { 0, 0, 0 }; float emission[3] = { 0, 0, 0 }; bool hasTexture = false; };
+struct ObjMaterial
+{
+    std::string name; float diffuse[3] = { 0, 0, 0 }; float emission[3] = { 0, 0, 0 };
+    std::string diffuseTexname, normalTexname, alphaTexname;     // map_Kd, norm, map_d (tiny_obj_loader material_t)
+    bool hasTextureOptions = false;
+};
 
 struct ObjIndex { int v, vn, vt; bool operator==(const ObjIndex& o) const { return v == o.v && vn == o.vn && vt == o.vt; } };
 struct ObjIndexHash { size_t operator()(const ObjIndex& k) const { return (size_t)k.v * 73856093u ^ (size_t)(k.vn + 1) * 19349663u ^ (size_t)(k.vt + 1) * 83492791u; } };
@@ -114,7 +122,18 @@ inline bool LoadMtl(const std::string& path, std::vector<ObjMaterial>& out, std:
         }
         else if (t[0] == 'K' && t[1] == 'd' && (t[2] == ' ' || t[2] == '\t')) { t += 2; for (int i = 0; i < 3; ++i) cur.diffuse[i] = NextObjReal(t); }
         else if (t[0] == 'K' && t[1] == 'e' && (t[2] == ' ' || t[2] == '\t')) { t += 2; for (int i = 0; i < 3; ++i) cur.emission[i] = NextObjReal(t); }
-        else if (!strncmp(t, "map_Kd", 6) || !strncmp(t, "map_d", 5) || !strncmp(t, "norm", 4)) cur.hasTexture = true;
+        else if ((!strncmp(t, "map_Kd", 6) && (t[6] == ' ' || t[6] == '\t')) || (!strncmp(t, "map_d", 5) && (t[5] == ' ' || t[5] == '\t')) ||
+                 (!strncmp(t, "norm", 4) && (t[4] == ' ' || t[4] == '\t')))
+        {
+            // tinyobj::ParseTextureNameAndOption (External/tiny_obj_loader.h:399, 962-977): without options the name is the rest of the line
+            std::string& dst = t[0] == 'n' ? cur.normalTexname : (t[4] == 'K' ? cur.diffuseTexname : cur.alphaTexname);
+            t += (t[0] == 'n' ? 5 : (t[4] == 'K' ? 7 : 6));
+            t += strspn(t, " \t");
+            std::string n(t);
+            while (!n.empty() && (n.back() == '\r' || n.back() == '\n')) n.pop_back();
+            if (!n.empty() && n[0] == '-') { cur.hasTextureOptions = true; n.clear(); }     // texture options (-blendu, -s ...): refused by LoadMesh
+            dst = n;
+        }
     }
     if (have) { ids[cur.name] = (int)out.size(); out.push_back(cur); }
     return true;
@@ -281,12 +300,21 @@ inline MeshShapePtr LoadMesh(const std::string& filePath, MaterialsMap& outMater
     // materials from the .mtl (LoadMaterial, MeshLoader.cpp:78-94) or the default material (96-109)
     for (const ObjMaterial& m : obj.materials)
     {
-        if (m.hasTexture) { Fail(err, "Mesh '" + filePath + "': textured .mtl materials are not supported"); return nullptr; }
+        if (m.hasTextureOptions) { Fail(err, "Mesh '" + filePath + "': .mtl texture options (-blendu, -s, ...) are not supported"); return nullptr; }
         auto material = std::make_shared<Material>();
         material->SetBsdf("diffuse");
         material->debugName = m.name;
         material->baseColor = Vector4(m.diffuse[0], m.diffuse[1], m.diffuse[2], 0.0f);
         material->emission = Vector4(m.emission[0], m.emission[1], m.emission[2], 0.0f);
+        {
+            // LoadMaterial, MeshLoader.cpp:86-88: textures relative to the mesh's directory
+            const std::string meshBaseDir = filePath.substr(0, filePath.find_last_of("\\/")) + "/";
+            std::string terr;
+            material->baseColorTexture = LoadTexture(meshBaseDir, m.diffuseTexname, terr);
+            material->normalMap = LoadTexture(meshBaseDir, m.normalTexname, terr);
+            material->maskMap = LoadTexture(meshBaseDir, m.alphaTexname, terr);
+            if (!terr.empty()) { Fail(err, "Mesh '" + filePath + "': " + terr); return nullptr; }
+        }
         material->roughness = 0.075f;
         material->Compile();
         desc.materials.push_back(material);
@@ -359,13 +387,75 @@ inline bool TryParseTransform(const json::Value& parent, const char* name, Vecto
     return true;
 }
 
-inline bool RejectTextures(const json::Value& v, std::initializer_list<const char*> names, LoadError& err)
+// TryParseTextureName, SceneLoader.cpp:218-242: a name defined under "textures", else a bitmap file under the data path;
+// a file that cannot be loaded leaves outValue empty and is NOT an error
+inline bool TryParseTextureName(const json::Value& v, const char* name, const std::string& dataPath, const TexturesMap& textures, TexturePtr& outValue, LoadError& err)
 {
-    for (const char* n : names) if (v.HasMember(n)) return Fail(err, std::string("'") + n + "': textures are not supported by this build");
+    if (!v.HasMember(name)) return true;
+    if (!v[name].IsString()) return Fail(err, std::string("Texture path '") + name + "' must be a string");
+    const std::string textureName = v[name].string;
+    const auto it = textures.find(textureName);
+    if (it != textures.end()) { outValue = it->second; return true; }
+    std::string terr;
+    outValue = LoadTexture(dataPath, textureName, terr);
+    if (!terr.empty()) return Fail(err, terr);
     return true;
 }
 
-inline MaterialPtr ParseMaterial(const json::Value& v, LoadError& err)
+inline bool TryParseInt(const json::Value& v, const char* name, bool optional, int32_t& out, LoadError& err)
+{
+    if (!v.HasMember(name)) return optional ? true : Fail(err, std::string("Missing '") + name + "' property");
+    if (!v[name].IsInt()) return Fail(err, std::string("Property '") + name + "' must be an integer");
+    out = v[name].GetInt();
+    return true;
+}
+
+// ParseTexture, SceneLoader.cpp:269-362
+inline TexturePtr ParseTexture(const json::Value& v, const std::string& dataPath, const TexturesMap& textures, std::string& outName, LoadError& err)
+{
+    if (!v.IsObject()) { Fail(err, "Texture description must be a structure"); return nullptr; }
+    if (!v.HasMember("name")) { Fail(err, "Texture is missing 'name' field"); return nullptr; }
+    const std::string name = v["name"].string;
+    if (name.empty()) { Fail(err, "Texture name cannot be empty"); return nullptr; }
+    outName = name;
+    if (!v.HasMember("type")) { Fail(err, "Texture is missing 'type' field"); return nullptr; }
+    const std::string type = v["type"].string;
+    if (type.empty()) { Fail(err, "Texture type cannot be empty"); return nullptr; }
+    if (type == "bitmap")
+    {
+        if (!v.HasMember("path")) { Fail(err, "Texture is missing 'path' field"); return nullptr; }
+        std::string terr;
+        BitmapPtr bitmap = LoadBitmapObject(dataPath, v["path"].string, terr);
+        if (!terr.empty()) { Fail(err, terr); return nullptr; }
+        if (!bitmap || bitmap->GetWidth() == 0 || bitmap->GetHeight() == 0) { Fail(err, "Failed to load source image from file '" + dataPath + v["path"].string + "'"); return nullptr; }
+        return std::make_shared<BitmapTexture>(bitmap);
+    }
+    if (type == "checkerboard" || type == "noise")
+    {
+        Vector4 colorA(0.0f), colorB(0.0f);
+        if (!TryParseVector(v, "colorA", 3, false, colorA, err)) return nullptr;
+        if (!TryParseVector(v, "colorB", 3, false, colorB, err)) return nullptr;
+        if (type == "checkerboard") return std::make_shared<CheckerboardTexture>(colorA, colorB);
+        int32_t numOctaves = 1;
+        if (!TryParseInt(v, "octaves", true, numOctaves, err)) return nullptr;
+        numOctaves = numOctaves > 20 ? 20 : (numOctaves < 1 ? 1 : numOctaves);
+        return std::make_shared<NoiseTexture>(colorA, colorB, (uint32_t)numOctaves);
+    }
+    if (type == "mix")
+    {
+        TexturePtr texA, texB, texWeight;
+        if (!TryParseTextureName(v, "textureA", dataPath, textures, texA, err)) return nullptr;
+        if (!TryParseTextureName(v, "textureB", dataPath, textures, texB, err)) return nullptr;
+        if (!TryParseTextureName(v, "weight", dataPath, textures, texWeight, err)) return nullptr;
+        // MixTexture asserts all three (MixTexture.cpp:15-17); a release build of the reference would crash on the first lookup
+        if (!texA || !texB || !texWeight) { Fail(err, "Mix texture '" + name + "' needs 'textureA', 'textureB' and 'weight'"); return nullptr; }
+        return std::make_shared<MixTexture>(texA, texB, texWeight);
+    }
+    Fail(err, "Invalid texture type name: '" + type + "'");
+    return nullptr;
+}
+
+inline MaterialPtr ParseMaterial(const json::Value& v, const std::string& dataPath, const TexturesMap& textures, LoadError& err)
 {
     if (!v.IsObject()) { Fail(err, "Material description must be a structure"); return nullptr; }
     if (!v.HasMember("name")) { Fail(err, "Material is missing 'name' field"); return nullptr; }
@@ -381,7 +471,12 @@ inline MaterialPtr ParseMaterial(const json::Value& v, LoadError& err)
     if (!TryParseVector(v, "emissionColor", 3, true, m->emission, err)) return nullptr;
     if (!TryParseFloat(v, "roughness", true, m->roughness, err)) return nullptr;
     if (!TryParseFloat(v, "metalness", true, m->metalness, err)) return nullptr;
-    if (!RejectTextures(v, { "baseColorTexture", "emissionTexture", "roughnessTexture", "metalnessTexture", "normalMap", "maskMap" }, err)) return nullptr;
+    if (!TryParseTextureName(v, "baseColorTexture", dataPath, textures, m->baseColorTexture, err)) return nullptr;
+    if (!TryParseTextureName(v, "emissionTexture", dataPath, textures, m->emissionTexture, err)) return nullptr;
+    if (!TryParseTextureName(v, "roughnessTexture", dataPath, textures, m->roughnessTexture, err)) return nullptr;
+    if (!TryParseTextureName(v, "metalnessTexture", dataPath, textures, m->metalnessTexture, err)) return nullptr;
+    if (!TryParseTextureName(v, "normalMap", dataPath, textures, m->normalMap, err)) return nullptr;
+    if (!TryParseTextureName(v, "maskMap", dataPath, textures, m->maskMap, err)) return nullptr;
     if (!TryParseFloat(v, "normalMapStrength", true, m->normalMapStrength, err)) return nullptr;
     if (!TryParseFloat(v, "IoR", true, m->IoR, err)) return nullptr;
     if (!TryParseFloat(v, "K", true, m->K, err)) return nullptr;
@@ -447,13 +542,12 @@ inline bool ParseObject(const json::Value& v, const std::string& dataPath, Scene
     return true;
 }
 
-inline bool ParseLight(const json::Value& v, const std::string& dataPath, Scene& scene, LoadError& err)
+inline bool ParseLight(const json::Value& v, const std::string& dataPath, Scene& scene, const TexturesMap& textures, LoadError& err)
 {
     if (!v.IsObject()) return Fail(err, "Light description must be a structure");
     if (!v.HasMember("type")) return Fail(err, "Light is missing 'type' field");
     Vector4 color;
     if (!TryParseVector(v, "color", 3, false, color, err)) return false;
-    if (!RejectTextures(v, { "texture" }, err)) return false;
     LightPtr light;
     const std::string type = v["type"].string;
     if (type == "area")
@@ -463,7 +557,9 @@ inline bool ParseLight(const json::Value& v, const std::string& dataPath, Scene&
         ShapePtr shape = ParseShape(v["shape"], dataPath, dummy, err);
         if (!shape) return false;
         if (shape->GetType() == RTB_SHAPE_MESH) return Fail(err, "mesh area lights are not supported (MeshShape::Sample is unimplemented in the reference)");
-        light = std::make_unique<AreaLight>(std::move(shape), color);
+        auto areaLight = std::make_unique<AreaLight>(std::move(shape), color);
+        if (!TryParseTextureName(v, "texture", dataPath, textures, areaLight->mTexture, err)) return false;
+        light = std::move(areaLight);
     }
     else if (type == "point") light = std::make_unique<PointLight>(color);
     else if (type == "spot")
@@ -478,7 +574,12 @@ inline bool ParseLight(const json::Value& v, const std::string& dataPath, Scene&
         if (!TryParseFloat(v, "angle", true, angle, err)) return false;
         light = std::make_unique<DirectionalLight>(color, math::DegToRad(angle));
     }
-    else if (type == "background") light = std::make_unique<BackgroundLight>(color);
+    else if (type == "background")
+    {
+        auto backgroundLight = std::make_unique<BackgroundLight>(color);
+        if (!TryParseTextureName(v, "texture", dataPath, textures, backgroundLight->mTexture, err)) return false;
+        light = std::move(backgroundLight);
+    }
     else return Fail(err, "Unknown light type: '" + type + "'");   // incl. "sphere": that loader branch never creates a light (SceneLoader.cpp:587-597)
     auto object = std::make_unique<LightSceneObject>(std::move(light));
     Vector4 t, q;
@@ -500,7 +601,7 @@ inline bool ParseCamera(const json::Value& v, Camera& camera, LoadError& err)
     if (!TryParseBool(v, "enableDOF", true, camera.mDOF.enable, err)) return false;
     if (!TryParseFloat(v, "aperture", true, camera.mDOF.aperture, err)) return false;
     if (!TryParseFloat(v, "focalPlaneDistance", true, camera.mDOF.focalPlaneDistance, err)) return false;
-    if (!RejectTextures(v, { "bokehTexture" }, err)) return false;
+    if (v.HasMember("bokehTexture")) return Fail(err, "'bokehTexture': texture-shaped bokeh is not supported (Camera.cpp:205-214 samples it through the importance map)");
     return true;
 }
 
@@ -519,14 +620,27 @@ inline bool LoadScene(const std::string& path, const std::string& dataPath, Scen
 
     MaterialsMap materials;
     bool ok = true;
-    if (d.HasMember("textures") && d["textures"].IsArray() && d["textures"].Size() > 0) ok = Fail(err, "'textures': textures are not supported by this build");
+    TexturesMap textures;
+    if (d.HasMember("textures"))
+    {
+        const json::Value& a = d["textures"];
+        if (!a.IsArray()) ok = Fail(err, "'textures' is expected to be an array");
+        for (size_t i = 0; ok && i < a.Size(); ++i)
+        {
+            std::string name;
+            TexturePtr t = ParseTexture(a[i], dataPath, textures, name, err);
+            if (!t) { ok = Fail(err, "invalid texture"); break; }
+            if (textures.count(name) > 0) { ok = Fail(err, "Duplicated texture: '" + name + "'"); break; }
+            textures[name] = t;
+        }
+    }
     if (ok && d.HasMember("materials"))
     {
         const json::Value& a = d["materials"];
         if (!a.IsArray()) ok = Fail(err, "'materials' is expected to be an array");
         for (size_t i = 0; ok && i < a.Size(); ++i)
         {
-            MaterialPtr m = ParseMaterial(a[i], err);
+            MaterialPtr m = ParseMaterial(a[i], dataPath, textures, err);
             if (!m) { ok = false; break; }
             if (materials.count(m->debugName) > 0) { ok = Fail(err, "Duplicated material: '" + m->debugName + "'"); break; }
             materials[m->debugName] = m;
@@ -542,7 +656,7 @@ inline bool LoadScene(const std::string& path, const std::string& dataPath, Scen
     {
         const json::Value& a = d["lights"];
         if (!a.IsArray()) ok = Fail(err, "'lights' is expected to be an array");
-        for (size_t i = 0; ok && i < a.Size(); ++i) ok = ParseLight(a[i], dataPath, scene, err);
+        for (size_t i = 0; ok && i < a.Size(); ++i) ok = ParseLight(a[i], dataPath, scene, textures, err);
     }
     if (ok && d.HasMember("camera")) ok = ParseCamera(d["camera"], camera, err);
     if (!ok) errorMessage = err.message;

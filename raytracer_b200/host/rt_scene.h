@@ -15,9 +15,11 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <functional>
 
 #include "rt_math.h"
 #include "rt_bvh.h"
+#include "rt_texture.h"
 #include "../csrc/rtb_scene_file.h"
 
 namespace rt {
@@ -40,6 +42,8 @@ public:
     float IoR = 1.5f;
     float K = 4.0f;
     bool isDispersive = false;
+    // MaterialParameter<T>::texture (MaterialParameter.h:14-15) + Material::maskMap / normalMap (Material.h:76-77)
+    TexturePtr baseColorTexture, emissionTexture, roughnessTexture, metalnessTexture, normalMap, maskMap;
 
     static constexpr const char* DefaultBsdfName = "diffuse";
 
@@ -236,6 +240,7 @@ public:
     Box GetBoundingBox() const override { return mShape->GetBoundingBox(); }
     uint32_t GetFlags() const override { return Flag_IsFinite; }
     const ShapePtr& GetShape() const { return mShape; }
+    TexturePtr mTexture;      // parsed like the reference does, never evaluated (AreaLight.cpp:49-58, 136-146 are commented out)
 private:
     ShapePtr mShape;
 };
@@ -247,6 +252,7 @@ public:
     uint32_t GetType() const override { return RTB_LIGHT_BACKGROUND; }
     Box GetBoundingBox() const override { return Box::Full(); }
     uint32_t GetFlags() const override { return Flag_None; }
+    TexturePtr mTexture;      // environment map, BackgroundLight.cpp:45-61
 };
 
 class DirectionalLight : public ILight
@@ -403,6 +409,45 @@ public:
         std::map<const IShape*, uint32_t> shapeIds;
         std::map<const Material*, uint32_t> materialIds;
 
+        // textures are emitted children first, so a mix texture only references earlier entries
+        std::map<const ITexture*, uint32_t> textureIds;
+        std::function<uint32_t(const ITexture*)> addTexture = [&](const ITexture* t) -> uint32_t
+        {
+            if (!t) return RTB_NO_TEXTURE;
+            auto it = textureIds.find(t);
+            if (it != textureIds.end()) return it->second;
+            rtb::SceneFile::Texture r;
+            memset(&r.desc, 0, sizeof(r.desc));
+            r.desc.type = t->GetType();
+            if (t->GetType() == RTB_TEXTURE_BITMAP)
+            {
+                const Bitmap& b = *static_cast<const BitmapTexture*>(t)->GetBitmap();
+                r.desc.width = b.GetWidth(); r.desc.height = b.GetHeight();
+                r.texels = b.GetTexels();
+            }
+            else if (t->GetType() == RTB_TEXTURE_CHECKERBOARD)
+            {
+                const CheckerboardTexture* c = static_cast<const CheckerboardTexture*>(t);
+                for (int i = 0; i < 4; ++i) { r.desc.colorA[i] = c->mColorA[i]; r.desc.colorB[i] = c->mColorB[i]; }
+            }
+            else if (t->GetType() == RTB_TEXTURE_NOISE)
+            {
+                const NoiseTexture* n = static_cast<const NoiseTexture*>(t);
+                for (int i = 0; i < 4; ++i) { r.desc.colorA[i] = n->mColorA[i]; r.desc.colorB[i] = n->mColorB[i]; }
+                r.desc.numOctaves = n->mNumOctaves;
+            }
+            else
+            {
+                const MixTexture* m = static_cast<const MixTexture*>(t);
+                r.desc.texA = addTexture(m->mTextureA.get());
+                r.desc.texB = addTexture(m->mTextureB.get());
+                r.desc.texWeight = addTexture(m->mTextureMask.get());
+            }
+            const uint32_t id = (uint32_t)out.textures.size();
+            out.textures.push_back(std::move(r));
+            textureIds[t] = id;
+            return id;
+        };
         auto addMaterial = [&](const Material* m) -> uint32_t
         {
             auto it = materialIds.find(m);
@@ -410,6 +455,17 @@ public:
             RtbMaterial r;
             memset(&r, 0, sizeof(r));
             r.bsdf = m->GetBsdfId();
+            if (m->baseColorTexture || m->emissionTexture || m->roughnessTexture || m->metalnessTexture || m->normalMap || m->maskMap) r.flags |= 1u;
+            RtbMaterialTextures mt;
+            memset(&mt, 0, sizeof(mt));
+            mt.baseColor = addTexture(m->baseColorTexture.get());
+            mt.emission = addTexture(m->emissionTexture.get());
+            mt.roughness = addTexture(m->roughnessTexture.get());
+            mt.metalness = addTexture(m->metalnessTexture.get());
+            mt.normalMap = addTexture(m->normalMap.get());
+            mt.maskMap = addTexture(m->maskMap.get());
+            mt.normalMapStrength = m->normalMapStrength;
+            out.materialTextures.push_back(mt);
             if (m->isDispersive) r.flags |= 2u;
             r.roughness = m->roughness; r.metalness = m->metalness;
             for (int i = 0; i < 4; ++i) { r.baseColor[i] = m->baseColor[i]; r.emission[i] = m->emission[i]; }
@@ -456,6 +512,7 @@ public:
             r.type = l.GetType(); r.flags = l.GetFlags(); r.shapeIndex = 0xFFFFFFFFu;
             for (int i = 0; i < 4; ++i) r.color[i] = l.GetColor()[i];
             if (l.GetType() == RTB_LIGHT_AREA) r.shapeIndex = addShape(static_cast<const AreaLight&>(l).GetShape().get());
+            out.lightTextures.push_back(l.GetType() == RTB_LIGHT_BACKGROUND ? addTexture(static_cast<const BackgroundLight&>(l).mTexture.get()) : RTB_NO_TEXTURE);
             if (l.GetType() == RTB_LIGHT_DIRECTIONAL) { r.cosAngle = static_cast<const DirectionalLight&>(l).mCosAngle; r.isDelta = static_cast<const DirectionalLight&>(l).mIsDelta; }
             if (l.GetType() == RTB_LIGHT_SPOT) { r.cosAngle = static_cast<const SpotLight&>(l).mCosAngle; r.isDelta = static_cast<const SpotLight&>(l).mIsDelta; }
             r.transform = toMat(lo->GetBaseTransform());
@@ -488,6 +545,8 @@ public:
             }
             out.objects.push_back(r);
         }
+        // a scene without any texture stays an RTBS v1 file / a texture-less RtbSceneDesc
+        if (out.textures.empty()) { out.materialTextures.clear(); out.lightTextures.clear(); }
     }
 
 private:

@@ -39,8 +39,11 @@ SCENES = {
     "cornell_dof": (128, ["mis"]),      # depth of field: 2 extra sampler dimensions per primary ray
     "materials": (256, ["mis", "pt"]),
     "mesh_small": (128, ["mis", "pt", "dbgtri", "dbgdepth"]),
+    # every texture kind on every material slot + normal maps + environment map (RTBS v2 file with float texels)
+    "textures": (192, ["mis", "pt", "dbgbase", "dbgnorm", "dbgrough", "dbguv"]),
 }
-RENDERERS = {"mis": ("Path Tracer MIS", 0), "pt": ("Path Tracer", 0), "dbgtri": ("Debug", 1), "dbgdepth": ("Debug", 2)}
+RENDERERS = {"mis": ("Path Tracer MIS", 0), "pt": ("Path Tracer", 0), "dbgtri": ("Debug", 1), "dbgdepth": ("Debug", 2),
+             "dbgbase": ("Debug", 8), "dbgnorm": ("Debug", 4), "dbgrough": ("Debug", 10), "dbguv": ("Debug", 7)}
 
 
 def rtref(*args):

@@ -76,6 +76,9 @@ struct World
         S.numTlasNodes = (uint32_t)hs.tlas.size(); S.numObjects = (uint32_t)hs.objTrace.size();
         S.numLights = (uint32_t)hs.lights.size(); S.numGlobalLights = (uint32_t)hs.globalLights.size();
         S.blueNoise = nullptr;
+        for (size_t i = 0; i < hs.textures.size(); ++i) hs.textures[i].texels = hs.texelSources[i];     // host pointers (owned by `file`)
+        S.textures = hs.textures.empty() ? nullptr : hs.textures.data();
+        S.materialTextures = hs.materialTextures.empty() ? nullptr : hs.materialTextures.data();
     }
 
     void loadBlueNoise(const char* path)
@@ -142,6 +145,8 @@ static int cmdRender(int argc, char** argv)
 
     std::vector<float> sum((size_t)w * h * 3, 0.0f);
     uint64_t numRays = 0, numShadow = 0, numShadowHit = 0;
+    int dbgX = -1, dbgY = -1;      // RTB_DEBUG_PIXEL=x,y prints every path vertex of that pixel
+    if (const char* e = getenv("RTB_DEBUG_PIXEL")) sscanf(e, "%d,%d", &dbgX, &dbgY);
     for (uint32_t p = 0; p < passes.numPasses; ++p)
     {
         P.passIndex = p;
@@ -162,6 +167,9 @@ static int cmdRender(int argc, char** argv)
                 if (renderer == RTB_RENDERER_PATH_TRACER_MIS) alive = shade_vertex_mis(world.S, P, ps, hit, sink, ns);
                 else if (renderer == RTB_RENDERER_PATH_TRACER) alive = shade_vertex_pt(world.S, P, ps, hit, sink);
                 else shade_debug(world.S, P, ps, hit, sink);
+                if (dbgX == (int)x && dbgY == (int)y)
+                    fprintf(stderr, "pass %u depth %u: hit obj %u sub %u dist %.9g u %.9g v %.9g -> result %.9g %.9g %.9g alive %d shadow %u thr %.9g %.9g %.9g\n", p, ps.depth, hit.objectId, hit.subObjectId,
+                            hit.distance, hit.u, hit.v, sink.result.x, sink.result.y, sink.result.z, (int)alive, ns, ps.throughput.x, ps.throughput.y, ps.throughput.z);
                 if (!alive) break;
             }
             numRays += (uint64_t)ps.depth + 1;

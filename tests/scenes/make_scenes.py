@@ -14,6 +14,10 @@ Scenes:
     materials        all nine BSDFs on spheres/boxes, area(sphere) + point + spot + background lights
     mesh_small       ~2.3k-triangle OBJ (two materials from a .mtl) + analytic metal/glass spheres, background +
                      directional light (the two-light pattern of Data/TestScenes/sponza.json:19-31)
+    textures         every texture kind of the reference's loader (checkerboard, noise, bitmap, nested mix; bitmap files
+                     referenced by name from materials; 24-bit, 8-bit palette and 8-bit grey BMPs generated here) on
+                     base colour / emission / roughness / metalness / normal map, a textured OBJ (vt + map_Kd + norm),
+                     a rect with textureScale, an environment-mapped background light, a missing texture file
     sponza_class     BASELINE config 3/4: ~262k-triangle atrium (floor/ceiling height fields, two rows of faceted
                      columns, arches, drapes), diffuse mesh materials + metal + dielectric analytic spheres,
                      background + 1-degree directional light
@@ -290,6 +294,102 @@ def scene_atrium(obj_rel_path):
     }
 
 
+# ---- BMP files + the texture scene ----------------------------------------------------------------------------
+
+def write_bmp(path, w, h, bits, pixel, palette=None):
+    """Uncompressed BMP as the reference's loader reads it (Core/Utils/BitmapBMP.cpp:46-139): 24-bit BGR, or 8-bit with
+    a palette of len(palette) BGRA entries (biClrUsed > 0), or 8-bit grey without palette (biClrUsed == 0)."""
+    import struct
+    bpp = 3 if bits == 24 else 1
+    stride = (w * bpp + 3) & ~3
+    rows = bytearray()
+    for y in range(h):
+        row = bytearray()
+        for x in range(w):
+            v = pixel(x, y)
+            row += bytes(v) if bits == 24 else bytes([v])
+        row += bytes(stride - len(row))
+        rows += row
+    pal = b"".join(bytes(c) for c in (palette or []))
+    off = 14 + 40 + len(pal)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<HIHHI", 0x4D42, off + len(rows), 0, 0, off))
+        f.write(struct.pack("<IIIHHIIIIII", 40, w, h, 1, bits, 0, len(rows), 2835, 2835, len(palette or []), 0))
+        f.write(pal)
+        f.write(rows)
+
+
+def write_texture_files(out_dir):
+    tex = os.path.join(out_dir, "TEXTURES")
+    os.makedirs(tex, exist_ok=True)
+    # (b, g, r) per pixel
+    write_bmp(os.path.join(tex, "tiles.bmp"), 16, 8, 24, lambda x, y: ((x ^ y) * 37 % 256, y * 32 % 256, x * 16 % 256 if (x + y) % 3 else 255))
+    write_bmp(os.path.join(tex, "normal.bmp"), 8, 8, 24,
+              lambda x, y: (255, int(128 + 70 * math.cos(y * 0.9 + x * 0.3)), int(128 + 70 * math.sin(x * 0.8))))
+    write_bmp(os.path.join(tex, "env.bmp"), 32, 16, 24,
+              lambda x, y: (min(255, 90 + 10 * y), min(255, 60 + 8 * y + (150 if (x, y) == (20, 5) else 0)), min(255, 40 + 4 * x + (200 if (x, y) == (20, 5) else 0))))
+    palette = [((i * 53) % 256, (i * 97 + 30) % 256, (255 - i * 16) % 256, (i * 17) % 256) for i in range(16)]
+    write_bmp(os.path.join(tex, "pal.bmp"), 13, 5, 8, lambda x, y: (x * 3 + y * 5) % 16, palette)
+    write_bmp(os.path.join(tex, "grey.bmp"), 6, 6, 8, lambda x, y: (x * 40 + y * 9) % 256)
+
+
+def write_textured_mesh(out_dir):
+    """A folded strip with texture coordinates; the .mtl binds a diffuse texture and a normal map by file name."""
+    n = 6
+    lines = ["mtllib textured.mtl"]
+    for i in range(n + 1):
+        x = -1.5 + 3.0 * i / n
+        for j, z in enumerate((-0.6, 0.6)):
+            lines.append("v %.6f %.6f %.6f" % (x, 0.25 * math.sin(i * 1.3) + 0.1 * j, z))
+    for i in range(n + 1):
+        for j in range(2):
+            lines.append("vt %.6f %.6f" % (1.7 * i / n - 0.2, 0.9 * j + 0.05 * i))
+    lines.append("usemtl cloth")
+    for i in range(n):
+        a, b, c, d = 2 * i + 1, 2 * i + 2, 2 * i + 4, 2 * i + 3
+        lines.append("f %d/%d %d/%d %d/%d" % (a, a, b, b, c, c))
+        lines.append("f %d/%d %d/%d %d/%d" % (a, a, c, c, d, d))
+    with open(os.path.join(out_dir, "MODELS", "textured.obj"), "w") as f:
+        f.write("\n".join(lines) + "\n")
+    with open(os.path.join(out_dir, "MODELS", "textured.mtl"), "w") as f:
+        f.write("newmtl cloth\nKd 0.9 0.8 0.7\nKe 0 0 0\nmap_Kd ../TEXTURES/tiles.bmp\nnorm ../TEXTURES/normal.bmp\n\n")
+
+
+def scene_textures():
+    return {
+        "textures": [
+            {"name": "checker", "type": "checkerboard", "colorA": [0.9, 0.9, 0.9], "colorB": [0.1, 0.1, 0.3]},
+            {"name": "clouds", "type": "noise", "colorA": [0.0, 0.0, 0.0], "colorB": [1.0, 1.0, 1.0], "octaves": 4},
+            {"name": "tiles", "type": "bitmap", "path": "TEXTURES/tiles.bmp"},
+            {"name": "blend", "type": "mix", "textureA": "checker", "textureB": "tiles", "weight": "clouds"},
+            {"name": "blend2", "type": "mix", "textureA": "blend", "textureB": "TEXTURES/pal.bmp", "weight": "checker"},
+        ],
+        "materials": [
+            mat("floor", "diffuse", (1.0, 1.0, 1.0), baseColorTexture="blend"),
+            mat("ball", "roughMetal", (0.95, 0.9, 0.8), roughness=0.8, roughnessTexture="clouds", baseColorTexture="TEXTURES/pal.bmp"),
+            mat("crate", "diffuse", (0.9, 0.9, 0.9), baseColorTexture="tiles", normalMap="TEXTURES/normal.bmp", normalMapStrength=0.7),
+            mat("glow", "diffuse", (0.2, 0.2, 0.2), emissionColor=[2.0, 1.5, 1.0], emissionTexture="checker"),
+            mat("coat", "roughPlastic", (0.8, 0.8, 0.8), roughness=0.4, metalness=0.9, metalnessTexture="TEXTURES/grey.bmp", baseColorTexture="blend2"),
+            mat("ghost", "diffuse", (0.3, 0.7, 0.4), baseColorTexture="TEXTURES/missing.bmp"),
+            mat("meshfallback", "diffuse", (0.7, 0.7, 0.7)),
+        ],
+        "objects": [
+            {"type": "rect", "size": [6.0, 6.0], "textureScale": [0.25, 0.4], "transform": xform((0.0, -1.0, 0.0), (-90.0, 0.0, 0.0)), "material": "floor"},
+            {"type": "sphere", "radius": 0.8, "transform": xform((-2.2, -0.2, 0.3)), "material": "ball"},
+            {"type": "box", "size": [0.6, 0.6, 0.6], "transform": xform((0.0, -0.4, 0.8), (0.0, 30.0, 0.0)), "material": "crate"},
+            {"type": "sphere", "radius": 0.35, "transform": xform((1.2, -0.65, -0.9)), "material": "glow"},
+            {"type": "box", "size": [0.5, 0.8, 0.4], "transform": xform((2.3, -0.2, 0.6), (0.0, -20.0, 0.0)), "material": "coat"},
+            {"type": "sphere", "radius": 0.4, "transform": xform((-0.9, -0.6, -1.2)), "material": "ghost"},
+            {"type": "mesh", "path": "MODELS/textured.obj", "transform": xform((0.3, 0.6, 1.6), (20.0, 0.0, 0.0)), "material": "meshfallback"},
+        ],
+        "lights": [
+            {"type": "background", "color": [1.0, 1.0, 1.0], "texture": "TEXTURES/env.bmp"},
+            {"type": "area", "color": [9.0, 9.0, 8.0], "transform": xform((0.0, 3.0, -0.5), (90.0, 0.0, 0.0)), "shape": {"type": "plane", "size": [0.8, 0.8]}},
+        ],
+        "camera": {"transform": xform((0.0, 1.2, -5.5), (14.0, 0.0, 0.0)), "fieldOfView": 55.0},
+    }
+
+
 def write_all(out_dir, sponza=False):
     os.makedirs(out_dir, exist_ok=True)
     os.makedirs(os.path.join(out_dir, "MODELS"), exist_ok=True)
@@ -304,6 +404,9 @@ def write_all(out_dir, sponza=False):
     dof = scene_cornell()
     dof["camera"].update({"enableDOF": True, "aperture": 0.15, "focalPlaneDistance": 3.5})    # circle bokeh, Camera.cpp:100-116
     dump("cornell_dof", dof)
+    write_texture_files(out_dir)
+    write_textured_mesh(out_dir)
+    dump("textures", scene_textures())
 
     w, mats = build_atrium(0.09)
     w.write(os.path.join(out_dir, "MODELS", "mesh_small.obj"), "mesh_small.mtl", mats)

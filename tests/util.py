@@ -10,13 +10,15 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 ORACLE_EXACT = os.path.join(ROOT, "oracle", "_ref", "exact")
 ORACLE_AVX = os.path.join(ROOT, "oracle", "_ref", "avx")
 
-RENDERER_IDS = {"mis": (1, 0), "pt": (0, 0), "dbgtri": (2, 1), "dbgdepth": (2, 2)}   # (RtbRenderer, RtbDebugMode)
+RENDERER_IDS = {"mis": (1, 0), "pt": (0, 0), "dbgtri": (2, 1), "dbgdepth": (2, 2),
+                "dbgbase": (2, 8), "dbgnorm": (2, 4), "dbgrough": (2, 10), "dbguv": (2, 7)}   # (RtbRenderer, RtbDebugMode)
 GOLDEN_RENDERS = [
     ("c1_sphere_area", "mis"),
     ("cornell", "mis"), ("cornell", "pt"), ("cornell", "dbgtri"), ("cornell", "dbgdepth"),
     ("cornell_dof", "mis"),
     ("materials", "mis"), ("materials", "pt"),
     ("mesh_small", "mis"), ("mesh_small", "pt"), ("mesh_small", "dbgtri"), ("mesh_small", "dbgdepth"),
+    ("textures", "mis"), ("textures", "pt"), ("textures", "dbgbase"), ("textures", "dbgnorm"), ("textures", "dbgrough"), ("textures", "dbguv"),
 ]
 
 
