@@ -81,6 +81,38 @@ def make_rays(rng, n, lo, hi):
     return rays
 
 
+REFERENCE_DATA = "/root/reference/Data"
+
+
+def make_reference_scenes(out):
+    """The reference's OWN test scenes (Data/TestScenes/*.json, read in place, never copied): for every scene its
+    loader accepts, the flattened Scene + MIS / PT sum buffers at 32x32 x 3 passes -> tests/golden/refscenes/."""
+    import glob
+    if not os.path.isdir(REFERENCE_DATA):
+        print("no %s: tests/golden/refscenes left as committed" % REFERENCE_DATA)
+        return
+    dst = os.path.join(out, "refscenes")
+    os.makedirs(dst, exist_ok=True)
+    w = h = 32
+    manifest = {}
+    for path in sorted(glob.glob(os.path.join(REFERENCE_DATA, "TestScenes", "*.json"))):
+        name = os.path.basename(path)[:-5]
+        base = os.path.join(dst, name)
+        common = ["--scene", path, "--data", REFERENCE_DATA + "/", "--width", w, "--height", h]
+        try:
+            rtref("flat", *common, "--out", base + ".rtb")
+        except SystemExit:
+            manifest[name] = {"loads": False}        # the reference itself rejects (or crashes on) this scene
+            continue
+        entry = {"loads": True, "width": w, "height": h, "passes": 3, "dims": 256}
+        for r in ("mis", "pt"):
+            c = rtref("render", *common, "--passes", 3, "--dims", 256, "--renderer", RENDERERS[r][0], "--depth", 8, "--strategy", "all",
+                      "--dump-sum", "%s_%s.sum" % (base, r), "--dump-passes", base + ".passes")
+            entry[r] = {k: c[k] for k in ("numPrimaryRays", "numRays", "numShadowRays", "numShadowRaysHit")}
+        manifest[name] = entry
+    json.dump(manifest, open(os.path.join(dst, "manifest.json"), "w"), indent=1, sort_keys=True)
+
+
 def main():
     out = HERE
     scn = os.path.join(out, "scenes")
@@ -115,6 +147,7 @@ def main():
                   "--tmax", os.path.join(out, name + ".tmax"), "--out", os.path.join(out, name + ".shadow_hits"))
         if name in ("cornell", "mesh_small"):
             rtref("primary", *common, "--passes", os.path.join(out, name + ".passes"), "--pass", 1, "--out", os.path.join(out, name + ".primary"))
+    make_reference_scenes(out)
     # sampler streams: 16x16 pixels (offset into the 128-tile by using a 200-wide virtual row is not needed: x,y < 16)
     p = os.path.join(out, "cornell.passes")
     rtref("sampler", "--scene", "unused", "--passes", p, "--width", 24, "--height", 20, "--num-dims", 40, "--blue-noise", 1, "--out", os.path.join(out, "sampler_bn.u32"))

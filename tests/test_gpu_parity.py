@@ -50,7 +50,27 @@ def test_sum_buffer_bit_exact(ctx, scene, renderer):
         assert counters["numShadowRaysHit"] == meta["numShadowRaysHit"]
 
 
-@pytest.mark.parametrize("scene", ["c1_sphere_area", "cornell", "materials", "mesh_small"])
+@pytest.mark.parametrize("scene,renderer", util.REFERENCE_SCENE_RENDERS)
+def test_reference_test_scenes_bit_exact(ctx, scene, renderer):
+    """The reference's OWN Data/TestScenes (every one its loader accepts), flattened from the reference's Scene object and
+    rendered by the reference (tests/golden/refscenes, make_golden.py): same sum buffer and ray counters, bit for bit."""
+    e = util.reference_scene_manifest()[scene]
+    base = os.path.join(util.GOLDEN, "refscenes", scene)
+    sf = capi.SceneFile(base + ".rtb")
+    ps = capi.PassScript(base + ".passes")
+    ctx.upload_scene(sf)
+    ctx.resize(e["width"], e["height"])
+    cam = capi.camera_for(sf, e["width"], e["height"])
+    rid, dbg = util.RENDERER_IDS[renderer]
+    for p in range(e["passes"]):
+        ctx.render_pass(ctx.make_pass(cam, ps.seeds[p], ps.offsets[p], p, renderer=rid, debug_mode=dbg, max_depth=8))
+    util.assert_bit_identical(ctx.read_sum(), util.load_sum("%s_%s.sum" % (base, renderer), e["width"], e["height"]), "%s/%s" % (scene, renderer))
+    counters = ctx.counters()
+    for k, v in e[renderer].items():
+        assert counters[k] == v, k
+
+
+@pytest.mark.parametrize("scene", ["c1_sphere_area", "cornell", "materials", "mesh_small", "textures"])
 def test_secondary_sum_bit_exact(ctx, scene):
     meta, img, _ = render_golden_case(ctx, scene, "mis", which=1)
     want = util.load_sum(util.golden("%s_mis.sum2" % scene), meta["width"], meta["height"])

@@ -39,6 +39,21 @@ def test_hostsim_sum_buffer_bit_exact(hostsim, tmp_path, scene, renderer):
         assert counters["numShadowRaysHit"] == meta["numShadowRaysHit"]
 
 
+@pytest.mark.parametrize("scene,renderer", util.REFERENCE_SCENE_RENDERS)
+def test_hostsim_reference_test_scenes(hostsim, tmp_path, scene, renderer):
+    """The device headers on the reference's own Data/TestScenes (tests/golden/refscenes)."""
+    e = util.reference_scene_manifest()[scene]
+    base = os.path.join(util.GOLDEN, "refscenes", scene)
+    out = str(tmp_path / "out.sum")
+    rid, dbg = util.RENDERER_IDS[renderer]
+    r = subprocess.run([HOSTSIM, "render", base + ".rtb", base + ".passes", str(e["width"]), str(e["height"]), out, str(rid), "8", str(dbg), "1", hostsim],
+                       stdout=subprocess.PIPE, text=True, check=True)
+    counters = json.loads(r.stdout.strip().splitlines()[-1])
+    util.assert_bit_identical(util.load_sum(out, e["width"], e["height"]), util.load_sum("%s_%s.sum" % (base, renderer), e["width"], e["height"]), "%s/%s" % (scene, renderer))
+    for k in ("numRays", "numShadowRays", "numShadowRaysHit"):
+        assert counters[k] == e[renderer][k], k
+
+
 @pytest.mark.parametrize("scene", ["cornell", "materials", "mesh_small"])
 def test_hostsim_trace_batch(hostsim, tmp_path, scene):
     out = str(tmp_path / "hits")

@@ -62,3 +62,12 @@ def run_rtref(args, variant="exact", seed="12345", timeout=1800):
     assert r.returncode == 0, "rtref failed: %s\n%s" % (args, r.stderr[-2000:])
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     return json.loads(lines[-1]) if lines else None
+
+
+def reference_scene_manifest():
+    """tests/golden/refscenes: the reference's own Data/TestScenes rendered by the reference (make_golden.py)."""
+    p = os.path.join(GOLDEN, "refscenes", "manifest.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+REFERENCE_SCENE_RENDERS = [(n, r) for n, e in sorted(reference_scene_manifest().items()) if e.get("loads") for r in ("mis", "pt")]
