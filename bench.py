@@ -143,7 +143,8 @@ def run_gpu(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    # every kernel of the path is launched on this torch stream, so torch.cuda.Event on it brackets them
+    # main stream of the context: the wavefront streams fork from it and rtb_join makes it wait for them again, so
+    # torch.cuda.Event records on it bracket every kernel of the timed region
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
 
@@ -189,6 +190,7 @@ def run_gpu(args):
     t0 = time.perf_counter()
     ev0.record()
     vp.render(args.steps)
+    lib.rtb_join(ctx)                                    # the torch stream waits (on the device) for the wavefront streams
     if world > 1:
         dist.all_gather_into_tensor(gathered, film)      # ONE collective per frame
     ev1.record()
@@ -226,6 +228,7 @@ def run_gpu(args):
         e2e_count[0] += 1
         vp.render(1)                      # H2D: this pass' seed vector + pass descriptor
         if world > 1:
+            lib.rtb_join(ctx)
             dist.all_gather_into_tensor(gathered, film)
             if rank == 0:
                 rc = lib.rtb_unshard_film_async(ctx, C.c_void_p(gathered.data_ptr()), C.c_void_p(dst.ptr))

@@ -346,6 +346,12 @@ int  rtb_render_pass(RtbContext* ctx, const RtbPassDesc* pass);
  * to `count` calls of rtb_render_pass */
 int  rtb_render_passes(RtbContext* ctx, const RtbPassDesc* passes, uint32_t count);
 int  rtb_synchronize(RtbContext* ctx);
+/* Passes are enqueued on the context's own wavefront streams (several wavefronts in flight; the film still receives
+ * them in pass order).  Everything in this API that looks at the result (rtb_read_*, rtb_unshard_*, rtb_get_counters,
+ * rtb_film_device_buffer, rtb_reset, rtb_synchronize) orders itself after them.  rtb_join does only that: it makes the
+ * main stream (RtbCreateDesc::stream) wait, on the device, for every pass enqueued so far - for callers that go on to
+ * enqueue their own work on that stream.  It does not block the host. */
+int  rtb_join(RtbContext* ctx);
 
 /* which: 0 = sum, 1 = secondarySum.  rgb = width*height*3 floats, row 0 = top (Film.cpp:31-39) */
 int  rtb_read_sum(RtbContext* ctx, float* rgb, int which);

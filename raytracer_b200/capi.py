@@ -124,7 +124,7 @@ HIT_DTYPE = np.dtype([("objectId", np.uint32), ("subObjectId", np.uint32), ("dis
 # every symbol include/rtb200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = [
     "rtb_last_error", "rtb_api_version", "rtb_create", "rtb_destroy", "rtb_upload_scene", "rtb_set_blue_noise",
-    "rtb_resize", "rtb_reset", "rtb_render_pass", "rtb_render_passes", "rtb_synchronize", "rtb_read_sum", "rtb_film_device_buffer",
+    "rtb_resize", "rtb_reset", "rtb_render_pass", "rtb_render_passes", "rtb_synchronize", "rtb_join", "rtb_read_sum", "rtb_film_device_buffer",
     "rtb_unshard_film", "rtb_read_sum_async", "rtb_unshard_film_async", "rtb_host_alloc", "rtb_host_free", "rtb_get_counters", "rtb_trace_batch", "rtb_trace_batch_device", "rtb_sample_batch",
     "rtb_primary_rays", "rtb_set_profiling", "rtb_get_pass_timings",
 ]
@@ -158,6 +158,7 @@ def load_library(path=None):
     lib.rtb_render_pass.argtypes = [C.c_void_p, C.POINTER(RtbPassDesc)]
     lib.rtb_render_passes.argtypes = [C.c_void_p, C.POINTER(RtbPassDesc), C.c_uint32]
     lib.rtb_synchronize.argtypes = [C.c_void_p]
+    lib.rtb_join.argtypes = [C.c_void_p]
     lib.rtb_read_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.rtb_film_device_buffer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.rtb_unshard_film.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]

@@ -33,6 +33,8 @@ using namespace rtb;
 // ---------------------------------------------------------------------------------------------------------------------
 
 #define RTB_MAX_DEPTH_SLOTS 64
+// shared-memory traversal stack: at most 227 KB per CTA = 454 entries x 128 threads x 4 B (rtb_trace.h)
+#define RTB_MAX_SMEM_STACK_ENTRIES (RTB_SMEM_STACK ? 440u : (uint32_t)RTB_STACK_SIZE)
 
 // 64 registers -> 8 CTAs of 128 threads per SM: the traversal kernels are latency bound, occupancy is worth more than
 // the few spilled bytes (measured: 72 regs / 7 CTAs 4.4 ms, 64 regs / 8 CTAs 3.6 ms per pass for k_traverse)
@@ -52,12 +54,18 @@ struct PathBuf
     uint4*  p4;   // pixel slot | pass slot << 26, sampler salt, dim (12 bits) | depth << 12 (7) | lastSpecular << 19 | lastMaterial << 20 (12, 0xFFF = none), lastPdfW bits
 };
 
+// queue counters of ONE wavefront (every wavefront slot has its own)
 struct Control
 {
     uint32_t pathCount[RTB_MAX_DEPTH_SLOTS + 2];     // live paths entering depth d
     uint32_t shadowPathCount[RTB_MAX_DEPTH_SLOTS + 2];
     uint32_t shadowRayCount[RTB_MAX_DEPTH_SLOTS + 2];
     uint32_t shadowCursor[RTB_MAX_DEPTH_SLOTS + 2];   // next unfetched entry of rayList (k_shadow's dynamic fetch)
+};
+
+// cumulative ray counters of the context (shared by all wavefront slots; atomics)
+struct Totals
+{
     unsigned long long numRays, numShadowRays, numShadowRaysHit, numBoxTests, numTriTests, numShadowBoxTests, numShadowTriTests;
 };
 
@@ -77,6 +85,7 @@ struct Wavefront
     uint32_t* shList;     // compacted input indices that own >= 1 shadow ray
     uint32_t* rayList;    // compacted shadow-ray slots (i * raysPerPath + r) of the current depth
     Control* ctl;
+    Totals*  tot;
     const uint32_t* pixelList;   // pixel slot -> y * width + x
     uint32_t numPixels;          // pixel slots of this shard
     uint32_t raysPerPath;
@@ -130,6 +139,13 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ SceneVie
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t total = W.numPixels * W.batch;
+    if (blockIdx.x == 0)
+    {
+        // queue counters of this wavefront (the kernels that read them are launched after this one on the same stream)
+        uint32_t* words = reinterpret_cast<uint32_t*>(W.ctl);
+        for (uint32_t i = threadIdx.x; i < sizeof(Control) / 4u; i += blockDim.x) words[i] = i == 0u ? total : 0u;
+        static_assert(offsetof(Control, pathCount) == 0, "pathCount[0] is word 0");
+    }
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
     {
         const uint32_t passSlot = i / W.numPixels, slot = i - passSlot * W.numPixels;
@@ -150,10 +166,10 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_traverse(const __gr
     const uint32_t stride = gridDim.x * blockDim.x;
     TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
 #if RTB_SMEM_STACK > 0
-    __shared__ SharedStackEntry smemStack[RTB_SMEM_STACK * RTB_STACK_THREADS];
-    SharedStackEntry* const sstack = smemStack + threadIdx.x;
+    extern __shared__ uint32_t smemStack[];     // stackEntries x 128 words (dynamic, sized by the scene's BVH depth)
+    uint32_t* const sstack = smemStack + threadIdx.x;
 #else
-    SharedStackEntry* const sstack = nullptr;
+    uint32_t* const sstack = nullptr;
 #endif
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
     {
@@ -167,10 +183,10 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_traverse(const __gr
     }
     if (kCount)
     {
-        atomicAdd(&W.ctl->numBoxTests, (unsigned long long)cnt.boxTests);
-        atomicAdd(&W.ctl->numTriTests, (unsigned long long)cnt.triTests);
+        atomicAdd(&W.tot->numBoxTests, (unsigned long long)cnt.boxTests);
+        atomicAdd(&W.tot->numTriTests, (unsigned long long)cnt.triTests);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&W.ctl->numRays, (unsigned long long)count);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&W.tot->numRays, (unsigned long long)count);
 }
 
 struct DeviceSink
@@ -272,7 +288,7 @@ __global__ void __launch_bounds__(128, RTB_SHADE_MINBLOCKS) k_shade(const __grid
     }
     // counters: one atomic per warp
     for (int o = 16; o > 0; o >>= 1) shadowRaysLocal += __shfl_down_sync(0xFFFFFFFFu, shadowRaysLocal, o);
-    if (lane == 0 && shadowRaysLocal) atomicAdd(&W.ctl->numShadowRays, shadowRaysLocal);
+    if (lane == 0 && shadowRaysLocal) atomicAdd(&W.tot->numShadowRays, shadowRaysLocal);
 }
 
 // RTB_SHADOW_REFILL = n > 0: persistent warps that fetch new shadow rays when at least n lanes are idle.  Measured on the
@@ -291,15 +307,15 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
     unsigned long long visibleLocal = 0;
     TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
 #if RTB_SMEM_STACK > 0
-    __shared__ SharedStackEntry smemStack[RTB_SMEM_STACK * RTB_STACK_THREADS];
-    SharedStackEntry* const sstack = smemStack + threadIdx.x;
+    extern __shared__ uint32_t smemStack[];     // stackEntries x 128 words (dynamic, sized by the scene's BVH depth)
+    uint32_t* const sstack = smemStack + threadIdx.x;
 #else
-    SharedStackEntry* const sstack = nullptr;
+    uint32_t* const sstack = nullptr;
 #endif
 #if RTB_SHADOW_REFILL
     // persistent warps with dynamic fetch (experiment, see above)
     ShadowWalk walk;
-    StackEntry stack[RTB_STACK_SIZE];
+    uint32_t stack[RTB_LOCAL_STACK_SIZE];
     bool active = false, exhausted = false;
     uint32_t j = 0;
     for (;;)
@@ -361,11 +377,11 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
     }
 #endif
     for (int o = 16; o > 0; o >>= 1) visibleLocal += __shfl_down_sync(0xFFFFFFFFu, visibleLocal, o);
-    if (lane == 0 && visibleLocal) atomicAdd(&W.ctl->numShadowRaysHit, visibleLocal);
+    if (lane == 0 && visibleLocal) atomicAdd(&W.tot->numShadowRaysHit, visibleLocal);
     if (kCount)
     {
-        atomicAdd(&W.ctl->numShadowBoxTests, (unsigned long long)cnt.boxTests);
-        atomicAdd(&W.ctl->numShadowTriTests, (unsigned long long)cnt.triTests);
+        atomicAdd(&W.tot->numShadowBoxTests, (unsigned long long)cnt.boxTests);
+        atomicAdd(&W.tot->numShadowTriTests, (unsigned long long)cnt.triTests);
     }
 }
 
@@ -428,15 +444,15 @@ __global__ void __launch_bounds__(256) k_unshard(const float* __restrict__ src, 
 // test hooks ------------------------------------------------------------------------------------------------------------
 
 template <bool kCount>
-__global__ void __launch_bounds__(128) k_trace_batch(const __grid_constant__ SceneView S, const RtbRay* __restrict__ rays, RtbHit* __restrict__ hits, unsigned long long n, uint32_t mode, Control* ctl)
+__global__ void __launch_bounds__(128) k_trace_batch(const __grid_constant__ SceneView S, const RtbRay* __restrict__ rays, RtbHit* __restrict__ hits, unsigned long long n, uint32_t mode, Totals* tot)
 {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
 #if RTB_SMEM_STACK > 0
-    __shared__ SharedStackEntry smemStack[RTB_SMEM_STACK * RTB_STACK_THREADS];
-    SharedStackEntry* const sstack = smemStack + threadIdx.x;
+    extern __shared__ uint32_t smemStack[];     // stackEntries x 128 words (dynamic, sized by the scene's BVH depth)
+    uint32_t* const sstack = smemStack + threadIdx.x;
 #else
-    SharedStackEntry* const sstack = nullptr;
+    uint32_t* const sstack = nullptr;
 #endif
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     {
@@ -463,8 +479,8 @@ __global__ void __launch_bounds__(128) k_trace_batch(const __grid_constant__ Sce
     }
     if (kCount)
     {
-        atomicAdd(mode == RTB_TRACE_SHADOW ? &ctl->numShadowBoxTests : &ctl->numBoxTests, (unsigned long long)cnt.boxTests);
-        atomicAdd(mode == RTB_TRACE_SHADOW ? &ctl->numShadowTriTests : &ctl->numTriTests, (unsigned long long)cnt.triTests);
+        atomicAdd(mode == RTB_TRACE_SHADOW ? &tot->numShadowBoxTests : &tot->numBoxTests, (unsigned long long)cnt.boxTests);
+        atomicAdd(mode == RTB_TRACE_SHADOW ? &tot->numShadowTriTests : &tot->numTriTests, (unsigned long long)cnt.triTests);
     }
 }
 
@@ -565,6 +581,7 @@ struct RtbContext
     DevArray<RtbMaterialTextures> materialTextures;
     SceneView view;
     uint32_t numLights = 0;
+    size_t stackBytes = 0;         // dynamic shared memory of the traversal kernels: the scene's worst-case stack x 128 threads x 4 B
 
     // film + wavefront
     uint32_t width = 0, height = 0;
@@ -580,21 +597,37 @@ struct RtbContext
     cudaStream_t copyStream = nullptr;
     cudaEvent_t snapReady[2] = {nullptr, nullptr}, snapCopied[2] = {nullptr, nullptr};
     uint32_t snapIndex = 0;
-    DevArray<float4> p[2][4];
-    DevArray<uint4> p4[2];
-    DevArray<uint4> hit0;
-    DevArray<float> hit1;
-    DevArray<float4> passColor, sr0, sr1, sr2, sr3, shThr;
-    DevArray<uint32_t> shCount, shList, rayList;
-    DevArray<Control> ctl;
-    DevArray<uint32_t> seed;       // maxBatch x numSeedDims
-    DevArray<float> offsets;       // maxBatch x 2
-    Wavefront wf;
+
+    // Wavefront slots: consecutive wavefronts (one per rtb_render_pass call, or per batch of rtb_render_passes) go to
+    // the slots round robin, each on its own stream with its own queues, so the sparse deep bounces of one wavefront
+    // overlap the dense first bounces of the next (and a small shard's latency-bound launch chains run several at a
+    // time).  Only k_film touches the film: the k_film launches are chained in pass order by events, so every pixel
+    // still receives its passes in order and the sums are bit-identical to one-wavefront-at-a-time rendering.
+    struct Slot
+    {
+        DevArray<float4> p[2][4];
+        DevArray<uint4> p4[2];
+        DevArray<uint4> hit0;
+        DevArray<float> hit1;
+        DevArray<float4> passColor, sr0, sr1, sr2, sr3, shThr;
+        DevArray<uint32_t> shCount, shList, rayList;
+        DevArray<Control> ctl;
+        DevArray<uint32_t> seed;       // maxBatch x numSeedDims seed integers, then maxBatch x 2 AA offsets
+        std::vector<uint32_t> stagingSeeds;
+        cudaStream_t stream = nullptr;
+        cudaEvent_t filmDone = nullptr;   // recorded after this slot's last k_film
+        Wavefront wf;
+    };
+    std::vector<Slot> slots;
+    uint32_t nextSlot = 0;
+    cudaEvent_t lastFilm = nullptr;       // filmDone of the most recent wavefront (null: none since the last join point)
+    cudaEvent_t mainMark = nullptr;       // position of the main stream when a wavefront was enqueued
+    bool slotsNeedMain = true;            // the main stream holds work the slots must wait for (reset / resize / upload)
+    DevArray<Totals> totals;
+    DevArray<uint32_t> seed;              // single-pass helpers (rtb_sample_batch / rtb_primary_rays)
 
     RtbCounters counters;
     uint32_t passesSinceReset = 0;
-    std::vector<uint32_t> stagingSeeds;
-    std::vector<float> stagingOffsets;
 
     // CTAs per SM of the grid-stride kernels.  8 are resident; launching 16x as many lets the hardware scheduler
     // even out the very uneven per-warp traversal times (measured: 8 -> 71.1, 32 -> 69.3, 128 -> 67.8, 1024 -> 70.0 ms / 8 passes)
@@ -621,9 +654,29 @@ static void free_scene(RtbContext* c)
 static void free_film(RtbContext* c)
 {
     c->pixelList.release(); c->pixelListAll.release(); c->sum.release(); c->sum2.release(); c->raster.release(); c->rasterAsync[0].release(); c->rasterAsync[1].release();
-    for (int b = 0; b < 2; ++b) { for (int k = 0; k < 4; ++k) c->p[b][k].release(); c->p4[b].release(); }
-    c->hit0.release(); c->hit1.release(); c->passColor.release();
-    c->sr0.release(); c->sr1.release(); c->sr2.release(); c->sr3.release(); c->shThr.release(); c->shCount.release(); c->shList.release(); c->rayList.release();
+    for (RtbContext::Slot& t : c->slots)
+    {
+        for (int b = 0; b < 2; ++b) { for (int k = 0; k < 4; ++k) t.p[b][k].release(); t.p4[b].release(); }
+        t.hit0.release(); t.hit1.release(); t.passColor.release();
+        t.sr0.release(); t.sr1.release(); t.sr2.release(); t.sr3.release(); t.shThr.release(); t.shCount.release(); t.shList.release(); t.rayList.release();
+    }
+}
+
+static cudaError_t sync_all(RtbContext* c)
+{
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    for (RtbContext::Slot& t : c->slots) if (e == cudaSuccess && t.stream) e = cudaStreamSynchronize(t.stream);
+    if (e == cudaSuccess && c->copyStream) e = cudaStreamSynchronize(c->copyStream);
+    c->lastFilm = nullptr;
+    return e;
+}
+
+// the main stream waits for every wavefront in flight (the k_film launches are chained, so the last one is enough)
+static cudaError_t join_slots(RtbContext* c)
+{
+    if (!c->lastFilm) return cudaSuccess;
+    const cudaError_t e = cudaStreamWaitEvent(c->stream, c->lastFilm, 0);
+    return e;
 }
 
 static int alloc_shadow(RtbContext* c)
@@ -631,29 +684,36 @@ static int alloc_shadow(RtbContext* c)
     // shadow-ray storage depends on both the film size and the number of lights sampled per vertex
     const uint32_t rpp = c->numLights > 0 ? c->numLights : 1;
     if (c->numPixels == 0) return RTB_OK;
-    if (rpp == c->raysPerPath && c->sr0.count == (size_t)c->numPixels * c->maxBatch * rpp) return RTB_OK;
-    c->raysPerPath = rpp;
     const size_t n = (size_t)c->numPixels * c->maxBatch * rpp;
-    RTB_CUDA(c->sr0.alloc(n)); RTB_CUDA(c->sr1.alloc(n)); RTB_CUDA(c->sr2.alloc(n)); RTB_CUDA(c->sr3.alloc(n));
-    RTB_CUDA(c->rayList.alloc(n));
+    if (rpp == c->raysPerPath && !c->slots.empty() && c->slots[0].sr0.count == n) return RTB_OK;
+    c->raysPerPath = rpp;
+    for (RtbContext::Slot& t : c->slots)
+    {
+        RTB_CUDA(t.sr0.alloc(n)); RTB_CUDA(t.sr1.alloc(n)); RTB_CUDA(t.sr2.alloc(n)); RTB_CUDA(t.sr3.alloc(n));
+        RTB_CUDA(t.rayList.alloc(n));
+    }
     return RTB_OK;
 }
 
 static void fill_wavefront(RtbContext* c)
 {
-    Wavefront& w = c->wf;
-    for (int b = 0; b < 2; ++b)
+    for (RtbContext::Slot& t : c->slots)
     {
-        w.buf[b].p0 = c->p[b][0].ptr; w.buf[b].p1 = c->p[b][1].ptr; w.buf[b].p2 = c->p[b][2].ptr; w.buf[b].p3 = c->p[b][3].ptr;
-        w.buf[b].p4 = c->p4[b].ptr;
+        Wavefront& w = t.wf;
+        for (int b = 0; b < 2; ++b)
+        {
+            w.buf[b].p0 = t.p[b][0].ptr; w.buf[b].p1 = t.p[b][1].ptr; w.buf[b].p2 = t.p[b][2].ptr; w.buf[b].p3 = t.p[b][3].ptr;
+            w.buf[b].p4 = t.p4[b].ptr;
+        }
+        w.hit0 = t.hit0.ptr; w.hit1 = t.hit1.ptr; w.passColor = t.passColor.ptr;
+        w.sr0 = t.sr0.ptr; w.sr1 = t.sr1.ptr; w.sr2 = t.sr2.ptr; w.sr3 = t.sr3.ptr;
+        w.shThr = t.shThr.ptr; w.shCount = t.shCount.ptr; w.shList = t.shList.ptr; w.rayList = t.rayList.ptr;
+        w.ctl = t.ctl.ptr;
+        w.tot = c->totals.ptr;
+        w.pixelList = c->pixelList.ptr;
+        w.numPixels = c->numPixels;
+        w.raysPerPath = c->raysPerPath;
     }
-    w.hit0 = c->hit0.ptr; w.hit1 = c->hit1.ptr; w.passColor = c->passColor.ptr;
-    w.sr0 = c->sr0.ptr; w.sr1 = c->sr1.ptr; w.sr2 = c->sr2.ptr; w.sr3 = c->sr3.ptr;
-    w.shThr = c->shThr.ptr; w.shCount = c->shCount.ptr; w.shList = c->shList.ptr; w.rayList = c->rayList.ptr;
-    w.ctl = c->ctl.ptr;
-    w.pixelList = c->pixelList.ptr;
-    w.numPixels = c->numPixels;
-    w.raysPerPath = c->raysPerPath;
 }
 
 extern "C" {
@@ -689,11 +749,32 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
     }
     cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, c->device);
     if (const char* t = getenv("RTB_SIMPLE_BLOCKS")) c->simpleBlocksPerSM = atoi(t) > 0 ? atoi(t) : 128;
-    e = c->ctl.alloc(1);
-    if (e == cudaSuccess) e = cudaMemsetAsync(c->ctl.ptr, 0, sizeof(Control), c->stream);
-    if (e != cudaSuccess) { delete c; return fail(RTB_ERR_CUDA, "control block allocation failed: %s", cudaGetErrorString(e)); }
+    // the traversal stacks live in dynamic shared memory (rtb_trace.h): allow up to the 227 KB a CTA may have
+    {
+        const int maxStack = (int)((size_t)RTB_MAX_SMEM_STACK_ENTRIES * RTB_STACK_THREADS * sizeof(uint32_t));
+        cudaFuncSetAttribute(k_traverse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+        cudaFuncSetAttribute(k_traverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+        cudaFuncSetAttribute(k_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+        cudaFuncSetAttribute(k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+        cudaFuncSetAttribute(k_trace_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+        cudaFuncSetAttribute(k_trace_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+    }
+    // wavefront slots (see RtbContext::Slot); RTB_SLOTS overrides the count for experiments
+    int numSlots = 4;
+    if (const char* t = getenv("RTB_SLOTS")) numSlots = atoi(t) >= 1 && atoi(t) <= 16 ? atoi(t) : numSlots;
+    c->slots.resize(numSlots);
+    e = c->totals.alloc(1);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->totals.ptr, 0, sizeof(Totals), c->stream);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->mainMark, cudaEventDisableTiming);
+    for (RtbContext::Slot& t : c->slots)
+    {
+        memset(&t.wf, 0, sizeof(t.wf));
+        if (e == cudaSuccess) e = t.ctl.alloc(1);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t.filmDone, cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) { rtb_destroy(c); return fail(RTB_ERR_CUDA, "control block allocation failed: %s", cudaGetErrorString(e)); }
     memset(&c->view, 0, sizeof(c->view));
-    memset(&c->wf, 0, sizeof(c->wf));
     memset(&c->counters, 0, sizeof(c->counters));
     memset(&c->timings, 0, sizeof(c->timings));
     *outCtx = c;
@@ -705,9 +786,17 @@ void rtb_destroy(RtbContext* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (RtbContext::Slot& t : c->slots) if (t.stream) cudaStreamSynchronize(t.stream);
     free_scene(c);
     free_film(c);
-    c->blueNoise.release(); c->ctl.release(); c->seed.release(); c->offsets.release();
+    c->blueNoise.release(); c->totals.release(); c->seed.release();
+    for (RtbContext::Slot& t : c->slots)
+    {
+        t.ctl.release(); t.seed.release();
+        if (t.filmDone) cudaEventDestroy(t.filmDone);
+        if (t.stream) cudaStreamDestroy(t.stream);
+    }
+    if (c->mainMark) cudaEventDestroy(c->mainMark);
     for (cudaEvent_t ev : c->events) cudaEventDestroy(ev);
     if (c->copyStream)
     {
@@ -737,11 +826,12 @@ int rtb_upload_scene(RtbContext* c, const RtbSceneDesc* scene)
     RTB_CUDA(cudaSetDevice(c->device));
     HostScene hs;
     std::string err;
-    if (!build_host_scene(*scene, hs, err)) return fail(RTB_ERR_INVALID_ARG, "rtb_upload_scene: %s", err.c_str());
+    if (!build_host_scene(*scene, hs, err, RTB_MAX_SMEM_STACK_ENTRIES)) return fail(RTB_ERR_INVALID_ARG, "rtb_upload_scene: %s", err.c_str());
     if (!hs.materialTextures.empty() && hs.materials.size() > 4094u)     // 12 bits of the packed path state (PathState::lastMaterial)
         return fail(RTB_ERR_UNSUPPORTED, "rtb_upload_scene: %zu materials; textured scenes are limited to 4094", hs.materials.size());
-    RTB_CUDA(cudaStreamSynchronize(c->stream));
+    RTB_CUDA(sync_all(c));
     free_scene(c);
+    c->slotsNeedMain = true;
     cudaStream_t s = c->stream;
     RTB_CUDA(c->tlas.upload(hs.tlas, s));
     RTB_CUDA(c->objTrace.upload(hs.objTrace, s));
@@ -789,6 +879,9 @@ int rtb_upload_scene(RtbContext* c, const RtbSceneDesc* scene)
     v.numTlasNodes = (uint32_t)hs.tlas.size(); v.numObjects = (uint32_t)hs.objTrace.size();
     v.numLights = (uint32_t)hs.lights.size(); v.numGlobalLights = (uint32_t)hs.globalLights.size();
     c->numLights = v.numLights;
+    c->stackBytes = RTB_SMEM_STACK ? (size_t)hs.stackEntries * RTB_STACK_THREADS * sizeof(uint32_t) : 0;
+    if (getenv("RTB_PROFILE_DEPTHS")) fprintf(stderr, "scene: top-level BVH depth %u (largest leaf %u), deepest mesh BVH %u -> %u stack entries, %zu B shared memory per CTA\n",
+                                              hs.maxTlasDepth, hs.maxTlasLeaf, hs.maxBlasDepth, hs.stackEntries, c->stackBytes);
     c->hasScene = true;
     int rc = alloc_shadow(c);
     if (rc != RTB_OK) return rc;
@@ -801,9 +894,9 @@ int rtb_resize(RtbContext* c, uint32_t width, uint32_t height)
     if (!c) return fail(RTB_ERR_INVALID_ARG, "null context");
     if (width == 0 || height == 0 || width > 65536 || height > 65536) return fail(RTB_ERR_INVALID_ARG, "rtb_resize: invalid viewport size %ux%u", width, height);   // Viewport.cpp:52-58
     RTB_CUDA(cudaSetDevice(c->device));
-    RTB_CUDA(cudaStreamSynchronize(c->stream));
-    if (c->copyStream) RTB_CUDA(cudaStreamSynchronize(c->copyStream));
+    RTB_CUDA(sync_all(c));
     free_film(c);
+    c->slotsNeedMain = true;
     c->width = width; c->height = height;
 
     // tile-interleaved sharding: tile t (row-major over the tile grid) belongs to shard t % numShards.  Every shard is padded to the same slot count so that one all-gather reassembles the film.
@@ -845,9 +938,12 @@ int rtb_resize(RtbContext* c, uint32_t width, uint32_t height)
     const size_t n = (size_t)c->numPixels * c->maxBatch;
     RTB_CUDA(c->sum.alloc(maxSlots * 3)); RTB_CUDA(c->sum2.alloc(maxSlots * 3));
     RTB_CUDA(c->raster.alloc((size_t)width * height * 3));
-    for (int b = 0; b < 2; ++b) { for (int k = 0; k < 4; ++k) RTB_CUDA(c->p[b][k].alloc(n)); RTB_CUDA(c->p4[b].alloc(n)); }
-    RTB_CUDA(c->hit0.alloc(n)); RTB_CUDA(c->hit1.alloc(n)); RTB_CUDA(c->passColor.alloc(n));
-    RTB_CUDA(c->shThr.alloc(n)); RTB_CUDA(c->shCount.alloc(n)); RTB_CUDA(c->shList.alloc(n));
+    for (RtbContext::Slot& t : c->slots)
+    {
+        for (int b = 0; b < 2; ++b) { for (int k = 0; k < 4; ++k) RTB_CUDA(t.p[b][k].alloc(n)); RTB_CUDA(t.p4[b].alloc(n)); }
+        RTB_CUDA(t.hit0.alloc(n)); RTB_CUDA(t.hit1.alloc(n)); RTB_CUDA(t.passColor.alloc(n));
+        RTB_CUDA(t.shThr.alloc(n)); RTB_CUDA(t.shCount.alloc(n)); RTB_CUDA(t.shList.alloc(n));
+    }
     c->raysPerPath = 0;
     int rc = alloc_shadow(c);
     if (rc != RTB_OK) return rc;
@@ -859,12 +955,15 @@ int rtb_reset(RtbContext* c)
 {
     if (!c) return fail(RTB_ERR_INVALID_ARG, "null context");
     RTB_CUDA(cudaSetDevice(c->device));
+    RTB_CUDA(join_slots(c));       // wavefronts still in flight belong to the frame being discarded: let them finish first
+    c->lastFilm = nullptr;
     if (c->sum.ptr)
     {
         RTB_CUDA(cudaMemsetAsync(c->sum.ptr, 0, c->sum.count * sizeof(float), c->stream));
         RTB_CUDA(cudaMemsetAsync(c->sum2.ptr, 0, c->sum2.count * sizeof(float), c->stream));
     }
-    RTB_CUDA(cudaMemsetAsync(c->ctl.ptr, 0, sizeof(Control), c->stream));
+    RTB_CUDA(cudaMemsetAsync(c->totals.ptr, 0, sizeof(Totals), c->stream));
+    c->slotsNeedMain = true;
     memset(&c->counters, 0, sizeof(c->counters));
     c->passesSinceReset = 0;
     return RTB_OK;
@@ -893,18 +992,18 @@ static int fill_pass_params(RtbContext* c, const RtbPassDesc* pass, PassParams& 
     if (uploadSeed)
     {
         // single-pass helpers (rtb_sample_batch / rtb_primary_rays)
-        if (c->seed.count < pass->numSeedDims || !c->seed.ptr) { RTB_CUDA(cudaStreamSynchronize(c->stream)); RTB_CUDA(c->seed.alloc((size_t)c->maxBatch * (pass->numSeedDims > 64 ? pass->numSeedDims : 64))); }
+        if (c->seed.count < pass->numSeedDims || !c->seed.ptr) { RTB_CUDA(cudaStreamSynchronize(c->stream)); RTB_CUDA(c->seed.alloc(pass->numSeedDims > 64 ? pass->numSeedDims : 64)); }
         if (pass->numSeedDims) RTB_CUDA(cudaMemcpyAsync(c->seed.ptr, pass->seed, pass->numSeedDims * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     }
     P.seed = c->seed.ptr;
     return RTB_OK;
 }
 
-static cudaEvent_t next_event(RtbContext* c, size_t& cursor)
+static cudaEvent_t next_event(RtbContext* c, size_t& cursor, cudaStream_t stream)
 {
     if (cursor >= c->events.size()) { cudaEvent_t ev; cudaEventCreate(&ev); c->events.push_back(ev); }
     cudaEvent_t ev = c->events[cursor++];
-    cudaEventRecord(ev, c->stream);
+    cudaEventRecord(ev, stream);
     return ev;
 }
 
@@ -915,38 +1014,47 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
     PassParams P;
     int rc = fill_pass_params(c, pass, P, false);
     if (rc != RTB_OK) return rc;
-    cudaStream_t s = c->stream;
+    // this wavefront's slot: own stream, own queues.  Profiling measures one wavefront at a time on slot 0.
+    const bool prof = c->profiling;
+    RtbContext::Slot& slot = c->slots[prof ? 0u : (c->nextSlot++ % (uint32_t)c->slots.size())];
+    cudaStream_t s = slot.stream;
+    // position of the main stream now: everything the caller enqueued there before this call (film resets, reads of
+    // the film such as snapshots or an all-gather) ...
+    RTB_CUDA(cudaEventRecord(c->mainMark, c->stream));
+    if (c->slotsNeedMain || prof)
+    {
+        // ... must be visible to the whole wavefront after a reset / resize / scene upload
+        for (RtbContext::Slot& t : c->slots) RTB_CUDA(cudaStreamWaitEvent(t.stream, c->mainMark, 0));
+        c->slotsNeedMain = false;
+    }
 
-    // per-pass seed vectors + AA offsets of the batch (stream ordered: the previous batch's kernels are done with them)
+    if (getenv("RTB_SERIALIZE_SLOTS") && c->lastFilm) RTB_CUDA(cudaStreamWaitEvent(s, c->lastFilm, 0));     // debugging aid: no overlap between wavefronts
+    // per-pass seed vectors + AA offsets of the batch (stream ordered: the slot's previous wavefront is done with them)
     const uint32_t dims = pass->numSeedDims;
-    if (c->seed.count < (size_t)c->maxBatch * (dims ? dims : 1) || !c->seed.ptr)
+    // one upload: [batch x dims seed integers][batch x 2 AA offsets]
+    const size_t words = (size_t)batch * (dims + 2u);
+    if (slot.seed.count < (size_t)c->maxBatch * (dims + 2u) || !slot.seed.ptr)
     {
         RTB_CUDA(cudaStreamSynchronize(s));
-        RTB_CUDA(c->seed.alloc((size_t)c->maxBatch * (dims > 64 ? dims : 64)));
+        RTB_CUDA(slot.seed.alloc((size_t)c->maxBatch * ((dims > 64 ? dims : 64) + 2u)));
     }
-    if (!c->offsets.ptr) RTB_CUDA(c->offsets.alloc((size_t)64 * 2));
-    c->stagingSeeds.resize((size_t)batch * dims);
-    c->stagingOffsets.resize((size_t)batch * 2);
+    slot.stagingSeeds.resize(words);
     for (uint32_t b = 0; b < batch; ++b)
     {
-        if (dims) memcpy(&c->stagingSeeds[(size_t)b * dims], passes[b].seed, dims * sizeof(uint32_t));
-        c->stagingOffsets[2 * b] = passes[b].sampleOffset[0];
-        c->stagingOffsets[2 * b + 1] = passes[b].sampleOffset[1];
+        if (dims) memcpy(&slot.stagingSeeds[(size_t)b * dims], passes[b].seed, dims * sizeof(uint32_t));
+        memcpy(&slot.stagingSeeds[(size_t)batch * dims + 2u * b], passes[b].sampleOffset, 2 * sizeof(float));
     }
-    if (dims) RTB_CUDA(cudaMemcpyAsync(c->seed.ptr, c->stagingSeeds.data(), (size_t)batch * dims * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    RTB_CUDA(cudaMemcpyAsync(c->offsets.ptr, c->stagingOffsets.data(), (size_t)batch * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
-    P.seed = c->seed.ptr;
-    P.sampleOffsets = c->offsets.ptr;
+    RTB_CUDA(cudaMemcpyAsync(slot.seed.ptr, slot.stagingSeeds.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    P.seed = slot.seed.ptr;
+    P.sampleOffsets = reinterpret_cast<const float*>(slot.seed.ptr + (size_t)batch * dims);
 
-    Wavefront W = c->wf;
+    Wavefront W = slot.wf;
     W.batch = batch;
     W.firstPassIndex = pass->passIndex;
     const uint32_t numPaths = c->numPixels * batch;
 
     const bool count = (c->flags & RTB_FLAG_COUNT_TESTS) != 0;
-    // queue counters of this wavefront: everything except the cumulative ray counters
-    RTB_CUDA(cudaMemsetAsync(c->ctl.ptr, 0, offsetof(Control, numRays), s));
-    RTB_CUDA(cudaMemcpyAsync(&c->ctl.ptr->pathCount[0], &numPaths, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    // (k_raygen initialises the queue counters of this wavefront)
 
     // grids: oversubscribed grid-stride launches, but never more CTAs than the wavefront can have work for (a small
     // shard's single pass would otherwise spend its time retiring ~19 000 empty CTAs per launch)
@@ -956,33 +1064,38 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
     const int blocks256 = c->numSMs * 4;
     size_t ev = 0;
     std::vector<cudaEvent_t> marks;
-    const bool prof = c->profiling;
-    if (prof) marks.push_back(next_event(c, ev));
+    if (prof) marks.push_back(next_event(c, ev, s));
     k_raygen<<<blocks256, 256, 0, s>>>(c->view, P, W);
-    if (prof) marks.push_back(next_event(c, ev));
+    if (prof) marks.push_back(next_event(c, ev, s));
     const uint32_t depthLimit = pass->renderer == RTB_RENDERER_DEBUG ? 0u : pass->maxRayDepth;
     const bool shadows = pass->renderer == RTB_RENDERER_PATH_TRACER_MIS && c->numLights > 0;
     const bool textured = c->textures.count > 0;     // scenes without textures run the k_shade that has no texture calls compiled in
     for (uint32_t d = 0; d <= depthLimit; ++d)
     {
-        if (count) k_traverse<true><<<blocks128, 128, 0, s>>>(c->view, W, d);
-        else k_traverse<false><<<blocks128, 128, 0, s>>>(c->view, W, d);
-        if (prof) marks.push_back(next_event(c, ev));
+        if (count) k_traverse<true><<<blocks128, 128, c->stackBytes, s>>>(c->view, W, d);
+        else k_traverse<false><<<blocks128, 128, c->stackBytes, s>>>(c->view, W, d);
+        if (prof) marks.push_back(next_event(c, ev, s));
         if (textured) k_shade<true><<<blocks128, 128, 0, s>>>(c->view, P, W, d);
         else k_shade<false><<<blocks128, 128, 0, s>>>(c->view, P, W, d);
-        if (prof) marks.push_back(next_event(c, ev));
+        if (prof) marks.push_back(next_event(c, ev, s));
         if (shadows)
         {
             // resident warps only: they fetch rays dynamically until the list is empty
             const int shadowBlocks = RTB_SHADOW_REFILL ? c->numSMs * RTB_TRAV_MINBLOCKS : blocksShadow;
-            if (count) k_shadow<true><<<shadowBlocks, 128, 0, s>>>(c->view, W, d);
-            else k_shadow<false><<<shadowBlocks, 128, 0, s>>>(c->view, W, d);
+            if (count) k_shadow<true><<<shadowBlocks, 128, c->stackBytes, s>>>(c->view, W, d);
+            else k_shadow<false><<<shadowBlocks, 128, c->stackBytes, s>>>(c->view, W, d);
             k_resolve<<<blocks256, 256, 0, s>>>(W, d);
         }
-        if (prof) marks.push_back(next_event(c, ev));
+        if (prof) marks.push_back(next_event(c, ev, s));
     }
+    // the film: after the previous wavefront's k_film (pass order) and after whatever the caller had enqueued on the main
+    // stream when this wavefront was submitted (e.g. a snapshot or an all-gather still reading the film)
+    if (c->lastFilm) RTB_CUDA(cudaStreamWaitEvent(s, c->lastFilm, 0));
+    RTB_CUDA(cudaStreamWaitEvent(s, c->mainMark, 0));
     k_film<<<blocks256, 256, 0, s>>>(W, c->sum.ptr, c->sum2.ptr);
-    if (prof) marks.push_back(next_event(c, ev));
+    RTB_CUDA(cudaEventRecord(slot.filmDone, s));
+    c->lastFilm = slot.filmDone;
+    if (prof) marks.push_back(next_event(c, ev, s));
     RTB_CUDA(cudaGetLastError());
     c->counters.numPrimaryRays += (uint64_t)c->numPixels * batch;     // Viewport.cpp:429
     c->counters.numKernelLaunches += 2u + (depthLimit + 1u) * (shadows ? 4u : 2u);
@@ -1005,7 +1118,7 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
         t.totalMs += ms(0, marks.size() - 1);
         t.totalLaunches = 2 + t.traverseLaunches + t.shadeLaunches + t.shadowLaunches;
         Control h;
-        RTB_CUDA(cudaMemcpy(&h, c->ctl.ptr, sizeof(Control), cudaMemcpyDeviceToHost));
+        RTB_CUDA(cudaMemcpy(&h, slot.ctl.ptr, sizeof(Control), cudaMemcpyDeviceToHost));
         for (uint32_t d = 0; d <= depthLimit; ++d) t.traverseRays += h.pathCount[d];
         for (uint32_t d = 0; d <= depthLimit; ++d) t.shadowRays += h.shadowRayCount[d];
         if (getenv("RTB_PROFILE_DEPTHS"))      // development aid: per-depth breakdown of this wavefront
@@ -1078,8 +1191,15 @@ int rtb_synchronize(RtbContext* c)
 {
     if (!c) return fail(RTB_ERR_INVALID_ARG, "null context");
     RTB_CUDA(cudaSetDevice(c->device));
-    RTB_CUDA(cudaStreamSynchronize(c->stream));
-    if (c->copyStream) RTB_CUDA(cudaStreamSynchronize(c->copyStream));
+    RTB_CUDA(sync_all(c));
+    return RTB_OK;
+}
+
+int rtb_join(RtbContext* c)
+{
+    if (!c) return fail(RTB_ERR_INVALID_ARG, "null context");
+    RTB_CUDA(cudaSetDevice(c->device));
+    RTB_CUDA(join_slots(c));
     return RTB_OK;
 }
 
@@ -1087,6 +1207,8 @@ int rtb_film_device_buffer(RtbContext* c, int which, void** outDevicePtr, uint64
 {
     if (!c || !outDevicePtr || !outNumFloats) return fail(RTB_ERR_INVALID_ARG, "null argument");
     if (!c->sum.ptr) return fail(RTB_ERR_INVALID_ARG, "viewport has no size");
+    RTB_CUDA(cudaSetDevice(c->device));
+    RTB_CUDA(join_slots(c));      // what the caller enqueues on the main stream next sees every pass rendered so far
     *outDevicePtr = which == 0 ? c->sum.ptr : c->sum2.ptr;
     *outNumFloats = (uint64_t)c->shardSlots * 3;
     return RTB_OK;
@@ -1097,6 +1219,7 @@ int rtb_unshard_film(RtbContext* c, const void* gatheredDevice, float* hostRgb)
     if (!c || !gatheredDevice || !hostRgb) return fail(RTB_ERR_INVALID_ARG, "null argument");
     if (!c->sum.ptr) return fail(RTB_ERR_INVALID_ARG, "viewport has no size");
     RTB_CUDA(cudaSetDevice(c->device));
+    RTB_CUDA(join_slots(c));
     const uint32_t total = c->numShards * c->shardSlots;
     k_unshard<<<c->numSMs * 4, 256, 0, c->stream>>>((const float*)gatheredDevice, c->raster.ptr, c->pixelListAll.ptr, total);
     RTB_CUDA(cudaGetLastError());
@@ -1123,6 +1246,7 @@ static int read_back_async(RtbContext* c, const void* gatheredDevice, float* hos
             RTB_CUDA(cudaEventRecord(c->snapCopied[i], c->copyStream));
         }
     }
+    RTB_CUDA(join_slots(c));
     const uint32_t b = c->snapIndex++ & 1u;
     const size_t n = (size_t)c->width * c->height * 3;
     if (c->rasterAsync[b].count != n) RTB_CUDA(c->rasterAsync[b].alloc(n));
@@ -1176,6 +1300,7 @@ int rtb_read_sum(RtbContext* c, float* rgb, int which)
     if (!c || !rgb) return fail(RTB_ERR_INVALID_ARG, "null argument");
     if (!c->sum.ptr) return fail(RTB_ERR_INVALID_ARG, "viewport has no size");
     RTB_CUDA(cudaSetDevice(c->device));
+    RTB_CUDA(join_slots(c));
     if (c->numShards > 1)
     {
         // only this shard's pixels are known here: the rest of the raster stays zero
@@ -1196,9 +1321,9 @@ int rtb_get_counters(RtbContext* c, RtbCounters* out)
 {
     if (!c || !out) return fail(RTB_ERR_INVALID_ARG, "null argument");
     RTB_CUDA(cudaSetDevice(c->device));
-    RTB_CUDA(cudaStreamSynchronize(c->stream));
-    Control h;
-    RTB_CUDA(cudaMemcpy(&h, c->ctl.ptr, sizeof(Control), cudaMemcpyDeviceToHost));
+    RTB_CUDA(sync_all(c));
+    Totals h;
+    RTB_CUDA(cudaMemcpy(&h, c->totals.ptr, sizeof(Totals), cudaMemcpyDeviceToHost));
     *out = c->counters;
     out->numRays = h.numRays;
     out->numShadowRays = h.numShadowRays;
@@ -1221,8 +1346,8 @@ int rtb_trace_batch_device(RtbContext* c, const void* raysDevice, uint64_t n, vo
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (outMs) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream); }
     const int blocks = c->numSMs * 8;
-    if (count) k_trace_batch<true><<<blocks, 128, 0, c->stream>>>(c->view, (const RtbRay*)raysDevice, (RtbHit*)hitsDevice, n, mode, c->ctl.ptr);
-    else k_trace_batch<false><<<blocks, 128, 0, c->stream>>>(c->view, (const RtbRay*)raysDevice, (RtbHit*)hitsDevice, n, mode, c->ctl.ptr);
+    if (count) k_trace_batch<true><<<blocks, 128, c->stackBytes, c->stream>>>(c->view, (const RtbRay*)raysDevice, (RtbHit*)hitsDevice, n, mode, c->totals.ptr);
+    else k_trace_batch<false><<<blocks, 128, c->stackBytes, c->stream>>>(c->view, (const RtbRay*)raysDevice, (RtbHit*)hitsDevice, n, mode, c->totals.ptr);
     RTB_CUDA(cudaGetLastError());
     if (outMs)
     {

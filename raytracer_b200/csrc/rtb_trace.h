@@ -236,43 +236,63 @@ RTB_HD bool analytic_shadow(const DObjectTrace& obj, const Ray& ray, float maxDi
 // descend into is ever fetched again: memory traffic is exactly one 64-byte block per visited inner node.
 struct StackEntry { uint32_t a, b; };
 
-// RTB_SMEM_STACK = K > 0: the K lowest stack entries of every thread live in shared memory (entry i of thread t at
-// sstack[i * RTB_STACK_THREADS + t]: whatever entry each lane of a warp touches, the 32 lanes hit 32 different
-// 8-byte bank pairs, i.e. always 2 conflict-free wavefronts), deeper entries stay in the local-memory array.
-// Divergent lanes pushing / popping at different depths of a local-memory stack cost one L1 wavefront per distinct
-// depth instead.
+// Stack storage.  An entry is packed into 32 bits: index (26 bits) | count (6 bits), count 0 = inner node (index of its
+// first child), 1..62 = leaf with that many items starting at index, 63 = "traverse object `index`".  rtb_upload_scene
+// refuses trees that do not fit (>= 2^26 nodes / items, leaves with more than 62 items).
+//
+// On the device the whole stack lives in SHARED memory (RTB_SMEM_STACK = 1, the default): entry i of thread t at
+// sstack[i * RTB_STACK_THREADS + t], so whatever depth each lane of a warp is at, the 32 lanes touch 32 different
+// banks (one conflict-free wavefront per push / pop), and the kernels are launched with `stackEntries * 512` bytes
+// of dynamic shared memory, stackEntries = the scene's worst-case stack occupancy computed at upload.
+// Why not local memory: with several wavefronts in flight on different streams (RtbContext::Slot) a local-memory
+// stack was CORRUPTED on the B200 (driver 580): a few hundred of 65 536 x 8 paths came back with wrong hits whenever
+// kernels of different streams overlapped, never when they were serialised (event chain or CUDA_LAUNCH_BLOCKING),
+// compute-sanitizer memcheck / initcheck clean, and gone as soon as the entries in use lived in shared memory
+// (tools/slot_probe.py).  RTB_SMEM_STACK = 0 keeps the local-memory stack (host build, experiments).
 #ifndef RTB_SMEM_STACK
-#define RTB_SMEM_STACK 0
+#define RTB_SMEM_STACK 1
 #endif
 #define RTB_STACK_THREADS 128
 #if defined(__CUDA_ARCH__) && RTB_SMEM_STACK > 0
 #define RTB_SSTACK 1
-typedef uint2 SharedStackEntry;
+#define RTB_LOCAL_STACK_SIZE 1
 #else
 #define RTB_SSTACK 0
-struct SharedStackEntry { uint32_t x, y; };
+#define RTB_LOCAL_STACK_SIZE RTB_STACK_SIZE
 #endif
+#define RTB_PACK_INDEX_BITS 26u
+#define RTB_PACK_MAX_INDEX ((1u << RTB_PACK_INDEX_BITS) - 1u)
+#define RTB_PACK_OBJECT 63u
+#define RTB_PACK_MAX_LEAF 62u
 
-RTB_HD void stk_put(StackEntry* stack, SharedStackEntry* sstack, uint32_t i, uint32_t a, uint32_t b)
+// b = leafInfo of a node (numLeaves | splitAxis << 30), or RTB_ENTRY_OBJECT
+RTB_HD void stk_put(uint32_t* stack, uint32_t* sstack, uint32_t i, uint32_t a, uint32_t b)
 {
+    const uint32_t count = b == 0xFFFFFFFFu ? RTB_PACK_OBJECT : (b & 0x3FFFFFFFu);
+    const uint32_t packed = a | (count << RTB_PACK_INDEX_BITS);
 #if RTB_SSTACK
-    if (i < RTB_SMEM_STACK) { sstack[i * RTB_STACK_THREADS] = make_uint2(a, b); return; }
-    i -= RTB_SMEM_STACK;
+    (void)stack;
+    sstack[i * RTB_STACK_THREADS] = packed;
 #else
     (void)sstack;
+    stack[i] = packed;
 #endif
-    stack[i].a = a; stack[i].b = b;
 }
 
-RTB_HD StackEntry stk_get(const StackEntry* stack, const SharedStackEntry* sstack, uint32_t i)
+RTB_HD StackEntry stk_get(const uint32_t* stack, const uint32_t* sstack, uint32_t i)
 {
 #if RTB_SSTACK
-    if (i < RTB_SMEM_STACK) { const uint2 v = sstack[i * RTB_STACK_THREADS]; StackEntry e; e.a = v.x; e.b = v.y; return e; }
-    i -= RTB_SMEM_STACK;
+    (void)stack;
+    const uint32_t packed = sstack[i * RTB_STACK_THREADS];
 #else
     (void)sstack;
+    const uint32_t packed = stack[i];
 #endif
-    return stack[i];
+    StackEntry e;
+    e.a = packed & RTB_PACK_MAX_INDEX;
+    const uint32_t count = packed >> RTB_PACK_INDEX_BITS;
+    e.b = count == RTB_PACK_OBJECT ? 0xFFFFFFFFu : count;
+    return e;
 }
 
 RTB_HD void node_header(const DNode* nodes, uint32_t index, uint32_t& childIndex, uint32_t& leafInfo)
@@ -292,13 +312,13 @@ RTB_HD void node_header(const DNode* nodes, uint32_t index, uint32_t& childIndex
 // refreshing originDivDir (PathTracerMIS.cpp:392-393) and that stale value is part of the reference's behaviour;
 // Traverse_Object rebuilds the ray in object space.
 template <bool kCount>
-RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, TraceCounters* cnt, SharedStackEntry* sstack = nullptr)
+RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, TraceCounters* cnt, uint32_t* sstack = nullptr)
 {
     if (S.numObjects == 0) return;
-    StackEntry stack[RTB_STACK_SIZE];
+    uint32_t stack[RTB_LOCAL_STACK_SIZE];
     uint32_t stackSize = 0;
     uint32_t blasBase = 0;
-    uint32_t popFloor = RTB_STACK_SIZE;     // entries above it are plain nodes of the mesh being traversed
+    uint32_t popFloor = 0xFFFFFFFFu;     // entries above it are plain nodes of the mesh being traversed
     bool inBlas = false;
     const DNode* nodes = S.tlas;
     const DTri* tris = nullptr;
@@ -392,7 +412,7 @@ RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, Tr
         if (inBlas && stackSize == blasBase)
         {
             // mesh finished: back to the top level with the world-space ray
-            inBlas = false; popFloor = RTB_STACK_SIZE; nodes = S.tlas; ray = worldRay; finite = worldFinite;
+            inBlas = false; popFloor = 0xFFFFFFFFu; nodes = S.tlas; ray = worldRay; finite = worldFinite;
         }
         if (stackSize == 0) break;
         const StackEntry e = stk_get(stack, sstack, --stackSize);
@@ -448,10 +468,10 @@ struct ShadowWalk
     uint32_t pendChild, pendInfo;          // a mesh leaf whose triangle tests are postponed
 
     // false: nothing to traverse (the ray is unoccluded)
-    RTB_HD bool begin(const SceneView& S, StackEntry* stack, const Ray& worldRay, float tMax, SharedStackEntry* sstack = nullptr)
+    RTB_HD bool begin(const SceneView& S, uint32_t* stack, const Ray& worldRay, float tMax, uint32_t* sstack = nullptr)
     {
         if (S.numObjects == 0) return false;
-        stackSize = 0; blasBase = 0; popFloor = RTB_STACK_SIZE; inBlas = false;
+        stackSize = 0; blasBase = 0; popFloor = 0xFFFFFFFFu; inBlas = false;
         nodes = S.tlas; tris = nullptr;
         ray = worldRay; world = worldRay; maxDistance = tMax;
         worldFinite = ray_is_finite(worldRay); finite = worldFinite;
@@ -480,7 +500,7 @@ struct ShadowWalk
     }
 
     template <bool kCount>
-    RTB_HD int step(const SceneView& S, StackEntry* stack, TraceCounters* cnt, SharedStackEntry* sstack = nullptr)
+    RTB_HD int step(const SceneView& S, uint32_t* stack, TraceCounters* cnt, uint32_t* sstack = nullptr)
     {
         // (the form of this loop matters: `while (have) { if (leaf) break; ... }` WITHOUT the postponing measured 35 %
         //  slower than `while (have && !leaf)`: ptxas places the reconvergence points differently)
@@ -553,7 +573,7 @@ struct ShadowWalk
 
         if (inBlas && stackSize == blasBase)
         {
-            inBlas = false; popFloor = RTB_STACK_SIZE; nodes = S.tlas; ray = world; finite = worldFinite;
+            inBlas = false; popFloor = 0xFFFFFFFFu; nodes = S.tlas; ray = world; finite = worldFinite;
         }
         if (stackSize == 0) return kVisible;
         const StackEntry e = stk_get(stack, sstack, --stackSize);
@@ -586,10 +606,10 @@ struct ShadowWalk
 };
 
 template <bool kCount>
-RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float maxDistance, TraceCounters* cnt, SharedStackEntry* sstack = nullptr)
+RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float maxDistance, TraceCounters* cnt, uint32_t* sstack = nullptr)
 {
     ShadowWalk w;
-    StackEntry stack[RTB_STACK_SIZE];
+    uint32_t stack[RTB_LOCAL_STACK_SIZE];
     if (!w.begin(S, stack, worldRay, maxDistance, sstack)) return false;
     for (;;)
     {

@@ -34,15 +34,17 @@ struct HostScene
     std::vector<const float*> texelSources;              // host texels of every bitmap texture (caller-owned), else null
     std::vector<RtbMaterialTextures> materialTextures;   // empty = no material has a texture
     bool hasLightTextures = false;
-    uint32_t maxTlasDepth = 0, maxBlasDepth = 0;
+    uint32_t maxTlasDepth = 0, maxBlasDepth = 0, maxTlasLeaf = 0;
+    uint32_t stackEntries = 0;      // worst-case occupancy of the traversal stack (rtb_trace.h)
 };
 
 inline M4 to_m4(const RtbMat4& m) { return load_m4(m); }
 
 // depth of a reference-format BVH (BVH::CalculateStats, BVH.cpp:112-143); returns 0 on a malformed tree
-inline uint32_t bvh_depth(const RtbBvhNode* nodes, uint32_t numNodes, uint32_t numLeafItems, std::string& err)
+inline uint32_t bvh_depth(const RtbBvhNode* nodes, uint32_t numNodes, uint32_t numLeafItems, std::string& err, uint32_t* outMaxLeaf = nullptr)
 {
     if (numNodes == 0) return 0;
+    if (numNodes > RTB_PACK_MAX_INDEX || numLeafItems > RTB_PACK_MAX_INDEX) { err = "BVH too large for the packed traversal stack (2^26 nodes / items)"; return 0; }
     struct Item { uint32_t node, depth; };
     std::vector<Item> stack;
     stack.push_back({ 0u, 1u });
@@ -59,6 +61,8 @@ inline uint32_t bvh_depth(const RtbBvhNode* nodes, uint32_t numNodes, uint32_t n
         if (numLeaves != 0)
         {
             if ((uint64_t)n.childIndex + numLeaves > numLeafItems) { err = "BVH leaf range out of bounds"; return 0; }
+            if (numLeaves > RTB_PACK_MAX_LEAF) { err = "BVH leaf with more than 62 items"; return 0; }
+            if (outMaxLeaf && numLeaves > *outMaxLeaf) *outMaxLeaf = numLeaves;
         }
         else
         {
@@ -69,7 +73,7 @@ inline uint32_t bvh_depth(const RtbBvhNode* nodes, uint32_t numNodes, uint32_t n
     return maxDepth;
 }
 
-inline bool build_host_scene(const RtbSceneDesc& d, HostScene& out, std::string& err)
+inline bool build_host_scene(const RtbSceneDesc& d, HostScene& out, std::string& err, uint32_t maxStackEntries = RTB_STACK_SIZE)
 {
     out = HostScene();
     static_assert(sizeof(DNode) == sizeof(RtbBvhNode), "node layout");
@@ -238,11 +242,14 @@ inline bool build_host_scene(const RtbSceneDesc& d, HostScene& out, std::string&
 
     if (d.numObjects > 1)
     {
-        const uint32_t depth = bvh_depth(d.tlasNodes, d.numTlasNodes, d.numObjects, err);
+        const uint32_t depth = bvh_depth(d.tlasNodes, d.numTlasNodes, d.numObjects, err, &out.maxTlasLeaf);
         if (d.numTlasNodes && depth == 0) return false;
         out.maxTlasDepth = depth;
     }
-    if (out.maxTlasDepth + out.maxBlasDepth + 2 > RTB_STACK_SIZE)
+    if (d.numObjects > RTB_PACK_MAX_INDEX) { err = "too many objects for the packed traversal stack"; return false; }
+    // one pending sibling per level of either tree + the object entries of one top-level leaf (+ the 1-object bypass entry)
+    out.stackEntries = out.maxTlasDepth + out.maxBlasDepth + out.maxTlasLeaf + 2;
+    if (out.stackEntries > maxStackEntries)
     {
         err = "BVH too deep for the traversal stack";
         return false;

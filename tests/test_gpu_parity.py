@@ -283,6 +283,42 @@ def test_batched_passes_are_bit_identical_to_single_passes(ctx, scene):
            (meta["numRays"], meta["numShadowRays"], meta["numShadowRaysHit"], meta["numPrimaryRays"])
 
 
+@pytest.mark.parametrize("scene", ["mesh_small", "textures"])
+def test_wavefronts_in_flight_are_bit_identical(scene):
+    """Pass-by-pass calls put every pass into its own wavefront slot (own stream): up to four wavefronts overlap on the
+    GPU.  The film, the secondary film and the ray counters must equal ONE batched wavefront of the same passes, every
+    time (this is the test that caught the corrupted local-memory traversal stack, see rtb_trace.h)."""
+    meta = json.load(open(util.golden("%s_mis.json" % scene)))
+    sf = capi.SceneFile(util.golden(scene + ".rtb"))
+    w = h = 256
+    n = 8
+    rng = np.random.default_rng(5)
+    seeds = rng.integers(0, 2**32, (n, meta["dims"]), dtype=np.uint32)
+    offs = (rng.normal(size=(n, 2)) * 0.5).astype(np.float32)
+
+    def run(single, reads_between=False):
+        with capi.Context(device=0) as c:
+            c.upload_scene(sf)
+            c.resize(w, h)
+            cam = capi.camera_for(sf, w, h)
+            if single:
+                for p in range(n):
+                    c.render_pass(c.make_pass(cam, seeds[p], offs[p], p))
+                    if reads_between and p == 3:
+                        c.read_sum()                # a join point in the middle of the frame
+            else:
+                c.render_passes(cam, seeds, offs, 0)
+            return c.read_sum(), c.read_sum(1), c.counters()
+
+    want = run(False)
+    for rep in range(3):
+        got = run(True, reads_between=(rep == 2))
+        util.assert_bit_identical(got[0], want[0], "%s sum, repetition %d" % (scene, rep))
+        util.assert_bit_identical(got[1], want[1], "%s secondary sum, repetition %d" % (scene, rep))
+        for k in ("numRays", "numShadowRays", "numShadowRaysHit", "numPrimaryRays"):
+            assert got[2][k] == want[2][k], k
+
+
 def test_async_read_back_snapshots_every_pass(ctx):
     """rtb_read_sum_async after pass k must deliver the film as of pass k even though pass k+1 is already running
     (double-buffered snapshot on the render stream, copy on a second stream); three read-backs in flight exercise
