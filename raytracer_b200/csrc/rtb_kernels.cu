@@ -167,9 +167,10 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_traverse(const __gr
     TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
 #if RTB_SMEM_STACK > 0
     extern __shared__ uint32_t smemStack[];     // stackEntries x 128 words (dynamic, sized by the scene's BVH depth)
-    uint32_t* const sstack = smemStack + threadIdx.x;
+    SharedStack sstack = (SharedStack)__cvta_generic_to_shared(smemStack) + threadIdx.x * 4u;
+    asm volatile("" : "+r"(sstack));             // keep it in a register (see stk_put)
 #else
-    uint32_t* const sstack = nullptr;
+    const SharedStack sstack = 0;
 #endif
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
     {
@@ -308,9 +309,10 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
     TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
 #if RTB_SMEM_STACK > 0
     extern __shared__ uint32_t smemStack[];     // stackEntries x 128 words (dynamic, sized by the scene's BVH depth)
-    uint32_t* const sstack = smemStack + threadIdx.x;
+    SharedStack sstack = (SharedStack)__cvta_generic_to_shared(smemStack) + threadIdx.x * 4u;
+    asm volatile("" : "+r"(sstack));             // keep it in a register (see stk_put)
 #else
-    uint32_t* const sstack = nullptr;
+    const SharedStack sstack = 0;
 #endif
 #if RTB_SHADOW_REFILL
     // persistent warps with dynamic fetch (experiment, see above)
@@ -450,9 +452,10 @@ __global__ void __launch_bounds__(128) k_trace_batch(const __grid_constant__ Sce
     TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
 #if RTB_SMEM_STACK > 0
     extern __shared__ uint32_t smemStack[];     // stackEntries x 128 words (dynamic, sized by the scene's BVH depth)
-    uint32_t* const sstack = smemStack + threadIdx.x;
+    SharedStack sstack = (SharedStack)__cvta_generic_to_shared(smemStack) + threadIdx.x * 4u;
+    asm volatile("" : "+r"(sstack));             // keep it in a register (see stk_put)
 #else
-    uint32_t* const sstack = nullptr;
+    const SharedStack sstack = 0;
 #endif
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     {
@@ -623,6 +626,7 @@ struct RtbContext
     cudaEvent_t lastFilm = nullptr;       // filmDone of the most recent wavefront (null: none since the last join point)
     cudaEvent_t mainMark = nullptr;       // position of the main stream when a wavefront was enqueued
     bool slotsNeedMain = true;            // the main stream holds work the slots must wait for (reset / resize / upload)
+    bool slotsOwnStreams = false;         // false: one slot on the main stream (default), true: RTB_SLOTS > 1
     DevArray<Totals> totals;
     DevArray<uint32_t> seed;              // single-pass helpers (rtb_sample_batch / rtb_primary_rays)
 
@@ -759,9 +763,13 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
         cudaFuncSetAttribute(k_trace_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
         cudaFuncSetAttribute(k_trace_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
     }
-    // wavefront slots (see RtbContext::Slot); RTB_SLOTS overrides the count for experiments
-    int numSlots = 4;
+    // wavefront slots (see RtbContext::Slot).  The default is ONE slot that runs on the main stream, i.e. strictly one
+    // kernel at a time: with several slots (RTB_SLOTS=4: +3 % device-resident, +9-12 % end to end on the bench) the
+    // traversal kernels returned different hits for the same ray whenever kernels of different streams overlapped,
+    // in some builds of the same source and not in others, and the cause is not understood yet.
+    int numSlots = 1;
     if (const char* t = getenv("RTB_SLOTS")) numSlots = atoi(t) >= 1 && atoi(t) <= 16 ? atoi(t) : numSlots;
+    c->slotsOwnStreams = numSlots > 1;
     c->slots.resize(numSlots);
     e = c->totals.alloc(1);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->totals.ptr, 0, sizeof(Totals), c->stream);
@@ -770,7 +778,8 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
     {
         memset(&t.wf, 0, sizeof(t.wf));
         if (e == cudaSuccess) e = t.ctl.alloc(1);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking);
+        if (!c->slotsOwnStreams) t.stream = c->stream;
+        else if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t.filmDone, cudaEventDisableTiming);
     }
     if (e != cudaSuccess) { rtb_destroy(c); return fail(RTB_ERR_CUDA, "control block allocation failed: %s", cudaGetErrorString(e)); }
@@ -794,7 +803,7 @@ void rtb_destroy(RtbContext* c)
     {
         t.ctl.release(); t.seed.release();
         if (t.filmDone) cudaEventDestroy(t.filmDone);
-        if (t.stream) cudaStreamDestroy(t.stream);
+        if (t.stream && c->slotsOwnStreams) cudaStreamDestroy(t.stream);
     }
     if (c->mainMark) cudaEventDestroy(c->mainMark);
     for (cudaEvent_t ev : c->events) cudaEventDestroy(ev);

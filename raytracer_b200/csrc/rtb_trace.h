@@ -156,11 +156,22 @@ RTB_HD bool shape_intersect(uint32_t shapeType, const float* size, const Ray& ra
     return false;
 }
 
+#ifndef RTB_PLAIN_LOADS
+#define RTB_PLAIN_LOADS 0     // 1: ld.global instead of ld.global.nc for nodes and triangles (experiment)
+#endif
+#if RTB_PLAIN_LOADS
+#define RTB_LDG(p) (*(p))
+#define RTB_LD_NC "ld.global"
+#else
+#define RTB_LDG(p) __ldg(p)
+#define RTB_LD_NC "ld.global.nc"
+#endif
+
 RTB_HD void load_tri(const DTri* tris, uint32_t index, V3& v0, V3& e1, V3& e2)
 {
 #if defined(__CUDA_ARCH__)
     const float4* p = reinterpret_cast<const float4*>(tris + index);
-    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    const float4 a = RTB_LDG(p), b = RTB_LDG(p + 1), c = RTB_LDG(p + 2);
     v0 = v3(a.x, a.y, a.z); e1 = v3(b.x, b.y, b.z); e2 = v3(c.x, c.y, c.z);
 #else
     const DTri& t = tris[index];
@@ -174,19 +185,34 @@ RTB_HD DNode load_node(const DNode* nodes, uint32_t index)
     // one 256-bit load per node (LDG.E.ENL2.256, sm_100+): the traversal kernels are bound by L1 data-pipe wavefronts
     // (70-80 % of peak in ncu), and a divergent lane costs one wavefront per load instruction whatever its width
     DNode n;
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm(RTB_LD_NC ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(n.minx), "=f"(n.miny), "=f"(n.minz), "=r"(n.childIndex), "=f"(n.maxx), "=f"(n.maxy), "=f"(n.maxz), "=r"(n.leafInfo)
         : "l"(nodes + index));
     return n;
 #elif defined(__CUDA_ARCH__)
     const float4* p = reinterpret_cast<const float4*>(nodes + index);
-    const float4 a = __ldg(p), b = __ldg(p + 1);
+    const float4 a = RTB_LDG(p), b = RTB_LDG(p + 1);
     DNode n;
     n.minx = a.x; n.miny = a.y; n.minz = a.z; n.childIndex = __float_as_uint(a.w);
     n.maxx = b.x; n.maxy = b.y; n.maxz = b.z; n.leafInfo = __float_as_uint(b.w);
     return n;
 #else
     return nodes[index];
+#endif
+}
+
+// both children of an inner node: they sit in one aligned 64-byte block, so ONE address + an immediate offset
+RTB_HD void load_node_pair(const DNode* nodes, uint32_t index, DNode& a, DNode& b)
+{
+#if defined(__CUDA_ARCH__) && RTB_LDG256
+    asm(RTB_LD_NC ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n\t"
+        RTB_LD_NC ".v8.f32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%16+32];"
+        : "=f"(a.minx), "=f"(a.miny), "=f"(a.minz), "=r"(a.childIndex), "=f"(a.maxx), "=f"(a.maxy), "=f"(a.maxz), "=r"(a.leafInfo),
+          "=f"(b.minx), "=f"(b.miny), "=f"(b.minz), "=r"(b.childIndex), "=f"(b.maxx), "=f"(b.maxy), "=f"(b.maxz), "=r"(b.leafInfo)
+        : "l"(nodes + index));
+#else
+    a = load_node(nodes, index);
+    b = load_node(nodes, index + 1);
 #endif
 }
 
@@ -266,24 +292,29 @@ struct StackEntry { uint32_t a, b; };
 #define RTB_PACK_MAX_LEAF 62u
 
 // b = leafInfo of a node (numLeaves | splitAxis << 30), or RTB_ENTRY_OBJECT
-RTB_HD void stk_put(uint32_t* stack, uint32_t* sstack, uint32_t i, uint32_t a, uint32_t b)
+// the kernels hand the stack over as a 32-bit shared-space byte address (word 0 of this thread's column) behind an
+// optimisation barrier: with a generic pointer the compiler re-derived the address (thread id, CTA shared window:
+// 5 instructions incl. S2R / S2UR) in every iteration of the node loop instead of keeping it in a register
+typedef uint32_t SharedStack;
+RTB_HD void stk_put(uint32_t* stack, SharedStack sstack, uint32_t i, uint32_t a, uint32_t b)
 {
     const uint32_t count = b == 0xFFFFFFFFu ? RTB_PACK_OBJECT : (b & 0x3FFFFFFFu);
     const uint32_t packed = a | (count << RTB_PACK_INDEX_BITS);
 #if RTB_SSTACK
     (void)stack;
-    sstack[i * RTB_STACK_THREADS] = packed;
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(sstack + i * (RTB_STACK_THREADS * 4u)), "r"(packed));
 #else
     (void)sstack;
     stack[i] = packed;
 #endif
 }
 
-RTB_HD StackEntry stk_get(const uint32_t* stack, const uint32_t* sstack, uint32_t i)
+RTB_HD StackEntry stk_get(const uint32_t* stack, SharedStack sstack, uint32_t i)
 {
 #if RTB_SSTACK
     (void)stack;
-    const uint32_t packed = sstack[i * RTB_STACK_THREADS];
+    uint32_t packed;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(packed) : "r"(sstack + i * (RTB_STACK_THREADS * 4u)));
 #else
     (void)sstack;
     const uint32_t packed = stack[i];
@@ -312,7 +343,7 @@ RTB_HD void node_header(const DNode* nodes, uint32_t index, uint32_t& childIndex
 // refreshing originDivDir (PathTracerMIS.cpp:392-393) and that stale value is part of the reference's behaviour;
 // Traverse_Object rebuilds the ray in object space.
 template <bool kCount>
-RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, TraceCounters* cnt, uint32_t* sstack = nullptr)
+RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, TraceCounters* cnt, SharedStack sstack = 0)
 {
     if (S.numObjects == 0) return;
     uint32_t stack[RTB_LOCAL_STACK_SIZE];
@@ -337,8 +368,8 @@ RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, Tr
         // inner nodes: GenericTraverse, Traversal_Single.h:36-91
         while (have && RTB_NUM_LEAVES(curInfo) == 0)
         {
-            const DNode a = load_node(nodes, curChild);
-            const DNode b = load_node(nodes, curChild + 1);
+            DNode a, b;
+            load_node_pair(nodes, curChild, a, b);
             float distanceA, distanceB;
             bool hitA, hitB;
             if (finite)
@@ -468,7 +499,7 @@ struct ShadowWalk
     uint32_t pendChild, pendInfo;          // a mesh leaf whose triangle tests are postponed
 
     // false: nothing to traverse (the ray is unoccluded)
-    RTB_HD bool begin(const SceneView& S, uint32_t* stack, const Ray& worldRay, float tMax, uint32_t* sstack = nullptr)
+    RTB_HD bool begin(const SceneView& S, uint32_t* stack, const Ray& worldRay, float tMax, SharedStack sstack = 0)
     {
         if (S.numObjects == 0) return false;
         stackSize = 0; blasBase = 0; popFloor = 0xFFFFFFFFu; inBlas = false;
@@ -500,7 +531,7 @@ struct ShadowWalk
     }
 
     template <bool kCount>
-    RTB_HD int step(const SceneView& S, uint32_t* stack, TraceCounters* cnt, uint32_t* sstack = nullptr)
+    RTB_HD int step(const SceneView& S, uint32_t* stack, TraceCounters* cnt, SharedStack sstack = 0)
     {
         // (the form of this loop matters: `while (have) { if (leaf) break; ... }` WITHOUT the postponing measured 35 %
         //  slower than `while (have && !leaf)`: ptxas places the reconvergence points differently)
@@ -517,8 +548,8 @@ struct ShadowWalk
                 }
                 break;
             }
-            const DNode a = load_node(nodes, curChild);
-            const DNode b = load_node(nodes, curChild + 1);
+            DNode a, b;
+            load_node_pair(nodes, curChild, a, b);
             float distanceA, distanceB;
             bool hitA, hitB;
             if (finite)
@@ -606,7 +637,7 @@ struct ShadowWalk
 };
 
 template <bool kCount>
-RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float maxDistance, TraceCounters* cnt, uint32_t* sstack = nullptr)
+RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float maxDistance, TraceCounters* cnt, SharedStack sstack = 0)
 {
     ShadowWalk w;
     uint32_t stack[RTB_LOCAL_STACK_SIZE];
