@@ -214,38 +214,46 @@ def run_gpu(args):
         lib.rtb_unshard_film(ctx, C.c_void_p(gathered.data_ptr()), img.ctypes.data)
         assert np.isfinite(img).all() and img.mean() > 0
 
-    # ---- end to end through the public API with host buffers: every step reads the film back to the host ---------------
+    # ---- end to end through the public API with host buffers: EVERY step's frame is read back to the host ---------------
+    # A step is still one pass, and the frame as of every pass lands in page-locked host memory; the passes are
+    # submitted E2E_GROUP at a time (Viewport.render(n): n Halton seed vectors go up, the passes share wavefronts) and
+    # rtb_film_snapshots leaves the film as of each of them on the device, from where each frame is (all-gathered when
+    # sharded,) un-permuted to raster order and copied out asynchronously.
     vp.reset()
     pinned = [capi.PinnedImage(WIDTH, HEIGHT), capi.PinnedImage(WIDTH, HEIGHT)]   # page-locked host frames (rtb_host_alloc)
-    e2e_steps = max(4, min(args.steps, 16))
+    E2E_GROUP = 8
+    e2e_steps = max(E2E_GROUP, (min(args.steps, 32) // E2E_GROUP) * E2E_GROUP)
+    snap_ptr, snap_stride = C.c_void_p(), C.c_uint64()
+    rc = lib.rtb_film_snapshots(ctx, E2E_GROUP, C.byref(snap_ptr), C.byref(snap_stride))
+    assert rc == 0, lib.rtb_last_error()
+    snaps = [torch.as_tensor(CudaArray(snap_ptr.value + 4 * snap_stride.value * i, snap_stride.value), device="cuda") for i in range(E2E_GROUP)]
     e2e_count = [0]
 
-    def e2e_step():
-        # every step ends with the frame as of this pass in host memory (rank 0 when sharded).  The read-back is
-        # asynchronous: snapshot in stream order, copy on a second stream while the next pass renders; the timed
-        # region closes with a synchronize, so every copy is inside it.
-        dst = pinned[e2e_count[0] & 1]
-        e2e_count[0] += 1
-        vp.render(1)                      # H2D: this pass' seed vector + pass descriptor
-        if world > 1:
-            lib.rtb_join(ctx)
-            dist.all_gather_into_tensor(gathered, film)
-            if rank == 0:
-                rc = lib.rtb_unshard_film_async(ctx, C.c_void_p(gathered.data_ptr()), C.c_void_p(dst.ptr))
+    def e2e_group():
+        vp.render(E2E_GROUP)              # H2D: the seed vectors + pass descriptors of these steps
+        lib.rtb_join(ctx)
+        for i in range(E2E_GROUP):
+            dst = pinned[e2e_count[0] & 1]
+            e2e_count[0] += 1
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, snaps[i])
+                if rank == 0:
+                    rc = lib.rtb_unshard_film_async(ctx, C.c_void_p(gathered.data_ptr()), C.c_void_p(dst.ptr))
+                    assert rc == 0, lib.rtb_last_error()
+            else:
+                rc = lib.rtb_unshard_film_async(ctx, C.c_void_p(snaps[i].data_ptr()), C.c_void_p(dst.ptr))
                 assert rc == 0, lib.rtb_last_error()
-        else:
-            rc = lib.rtb_read_sum_async(ctx, C.c_void_p(dst.ptr), 0)
-            assert rc == 0, lib.rtb_last_error()
 
-    e2e_step()
+    e2e_group()
     sync_all()
     c0 = vp.counters()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
+    for _ in range(e2e_steps // E2E_GROUP):
+        e2e_group()
     sync_all()
     e2e_s = time.perf_counter() - t0
     c1 = vp.counters()
+    lib.rtb_film_snapshots(ctx, 0, None, None)
     e2e_rays = (c1["numRays"] - c0["numRays"]) + (c1["numShadowRays"] - c0["numShadowRays"])
     te = torch.tensor([e2e_s, float(e2e_rays)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -327,8 +335,9 @@ def run_gpu(args):
             "gpu_launches": gpu_launches,
             "e2e": {"value": e2e_rays / e2e_s * 1e-6, "unit": "Mray/s", "steps": e2e_steps,
                     "h2d_bytes_per_step": DIMS * 4 + C.sizeof(capi.RtbPassDesc), "d2h_bytes_per_step": WIDTH * HEIGHT * 12,
-                    "api": ("per step: raytracer_b200.host_api.Viewport.render (ViewportB200::Render) + rtb_read_sum_async (GetSumBuffer) into a page-locked host frame, synchronize at the end" if world == 1 else
-                            "per step: Viewport.render on every rank, NCCL all-gather of the shard films, rtb_unshard_film_async into rank 0's page-locked host frame, synchronize at the end")},
+                    "group": E2E_GROUP,
+                    "api": ("raytracer_b200.host_api.Viewport.render(8) (ViewportB200::Render x 8, one call) with rtb_film_snapshots; the frame as of EVERY pass is copied into a page-locked host frame (rtb_unshard_film_async), synchronize at the end" if world == 1 else
+                            "Viewport.render(8) on every rank with rtb_film_snapshots; for EVERY pass: NCCL all-gather of the shard snapshots, rtb_unshard_film_async into rank 0's page-locked host frame; synchronize at the end")},
             "wall_s_timed_region": wall_s,
             "clocks": sampler.summary(),
             "roofline": roofline,

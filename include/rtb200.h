@@ -357,6 +357,12 @@ int  rtb_join(RtbContext* ctx);
 int  rtb_read_sum(RtbContext* ctx, float* rgb, int which);
 /* device pointer + element count of this shard's compact film (for an NCCL all-gather by the caller) */
 int  rtb_film_device_buffer(RtbContext* ctx, int which, void** outDevicePtr, uint64_t* outNumFloats);
+/* Streaming frames: with a snapshot buffer of `maxPasses` entries (owned by the context, freed by maxPasses = 0 or
+ * rtb_resize), pass i of every following rtb_render_passes call (i < maxPasses) also leaves the film (sum) AS OF THAT
+ * PASS at outDevicePtr + i * strideFloats, in the layout of rtb_film_device_buffer - what Viewport::GetSumBuffer would
+ * return after that pass (Viewport.h:50) - without giving up the shared wavefronts of a batched call.  Each entry can
+ * be all-gathered / handed to rtb_unshard_film(_async) like the film itself. */
+int  rtb_film_snapshots(RtbContext* ctx, uint32_t maxPasses, void** outDevicePtr, uint64_t* outStrideFloats);
 /* scatter gathered shard buffers (numShards * shardFloats, device) back to raster order into hostRgb */
 int  rtb_unshard_film(RtbContext* ctx, const void* gatheredDevice, float* hostRgb);
 /* asynchronous variants: the film is snapshotted in stream order (so later passes do not leak into it) and copied to

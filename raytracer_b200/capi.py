@@ -124,7 +124,7 @@ HIT_DTYPE = np.dtype([("objectId", np.uint32), ("subObjectId", np.uint32), ("dis
 # every symbol include/rtb200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = [
     "rtb_last_error", "rtb_api_version", "rtb_create", "rtb_destroy", "rtb_upload_scene", "rtb_set_blue_noise",
-    "rtb_resize", "rtb_reset", "rtb_render_pass", "rtb_render_passes", "rtb_synchronize", "rtb_join", "rtb_read_sum", "rtb_film_device_buffer",
+    "rtb_resize", "rtb_reset", "rtb_render_pass", "rtb_render_passes", "rtb_synchronize", "rtb_join", "rtb_read_sum", "rtb_film_device_buffer", "rtb_film_snapshots",
     "rtb_unshard_film", "rtb_read_sum_async", "rtb_unshard_film_async", "rtb_host_alloc", "rtb_host_free", "rtb_get_counters", "rtb_trace_batch", "rtb_trace_batch_device", "rtb_sample_batch",
     "rtb_primary_rays", "rtb_set_profiling", "rtb_get_pass_timings",
 ]
@@ -162,6 +162,7 @@ def load_library(path=None):
     lib.rtb_read_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.rtb_film_device_buffer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.rtb_unshard_film.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.rtb_film_snapshots.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.rtb_read_sum_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.rtb_unshard_film_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.rtb_host_alloc.argtypes = [C.c_uint64]
@@ -391,6 +392,12 @@ class Context:
             out = np.empty((self.height, self.width, 3), dtype=np.float32)
         _check(self.lib, self.lib.rtb_read_sum(self.h, out.ctypes.data, which))
         return out
+
+    def film_snapshots(self, max_passes):
+        """rtb_film_snapshots: (device pointer, stride in floats) of the per-pass film snapshots."""
+        p, n = C.c_void_p(), C.c_uint64()
+        _check(self.lib, self.lib.rtb_film_snapshots(self.h, max_passes, C.byref(p), C.byref(n)))
+        return p.value, n.value
 
     def film_device_buffer(self, which=0):
         p, n = C.c_void_p(), C.c_uint64()

@@ -61,6 +61,8 @@ struct Control
     uint32_t shadowPathCount[RTB_MAX_DEPTH_SLOTS + 2];
     uint32_t shadowRayCount[RTB_MAX_DEPTH_SLOTS + 2];
     uint32_t shadowCursor[RTB_MAX_DEPTH_SLOTS + 2];   // next unfetched entry of rayList (k_shadow's dynamic fetch)
+    uint32_t tailTaken;                               // != 0: k_tail finished every remaining path (1 + the depth it started at): later kernels have nothing to do
+    uint32_t pad[3];
 };
 
 // cumulative ray counters of the context (shared by all wavefront slots; atomics)
@@ -89,6 +91,7 @@ struct Wavefront
     const uint32_t* pixelList;   // pixel slot -> y * width + x
     uint32_t numPixels;          // pixel slots of this shard
     uint32_t raysPerPath;
+    uint32_t tailThreshold;      // k_tail takes over when at most this many paths are left (0 = never)
     uint32_t batch;              // passes in flight in this wavefront (pass slot b uses passColor[b * numPixels + pixel])
     uint32_t firstPassIndex;     // Viewport pass index of pass slot 0
 };
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ SceneVie
 template <bool kCount>
 __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_traverse(const __grid_constant__ SceneView S, const __grid_constant__ Wavefront W, uint32_t depth)
 {
-    const uint32_t count = W.ctl->pathCount[depth];
+    const uint32_t count = W.ctl->tailTaken ? 0u : W.ctl->pathCount[depth];
     const PathBuf& in = W.buf[depth & 1];
     const uint32_t stride = gridDim.x * blockDim.x;
     TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
@@ -215,7 +218,7 @@ struct DeviceSink
 template <bool kTex>
 __global__ void __launch_bounds__(128, RTB_SHADE_MINBLOCKS) k_shade(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const __grid_constant__ Wavefront W, uint32_t depth)
 {
-    const uint32_t count = W.ctl->pathCount[depth];
+    const uint32_t count = W.ctl->tailTaken ? 0u : W.ctl->pathCount[depth];
     const PathBuf& in = W.buf[depth & 1];
     const PathBuf& out = W.buf[(depth + 1) & 1];
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(128, RTB_SHADE_MINBLOCKS) k_shade(const __grid
 template <bool kCount>
 __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid_constant__ SceneView S, const __grid_constant__ Wavefront W, uint32_t depth)
 {
-    const uint32_t count = W.ctl->shadowRayCount[depth];
+    const uint32_t count = W.ctl->tailTaken ? 0u : W.ctl->shadowRayCount[depth];
     const uint32_t lane = threadIdx.x & 31u;
     unsigned long long visibleLocal = 0;
     TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
@@ -387,11 +390,96 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
     }
 }
 
+// ---- the tail of a wavefront ---------------------------------------------------------------------------------------------
+// Once only a few ten thousand paths are left, every further bounce costs four launches whose run time is one warp's
+// latency, not throughput (a 1/8 shard rendered pass by pass spends more than half of its 2.2 ms there).  k_tail is
+// launched after every depth and does nothing while more than `tailThreshold` paths are alive; below that it runs every
+// remaining path to its end in ONE launch: the reference's per-pixel loop (PathTracerMIS.cpp:270-396) on one thread per
+// path, shadow rays traced on the spot in light order.  Same per-vertex functions, same order of the float additions
+// (emission, then the NEE sum of the vertex, then the next vertex), so the film is bit-identical to the wavefront path.
+struct TailSink
+{
+    const SceneView& S;
+    SharedStack sstack;
+    V3 result;
+    V3 lightSum;
+    uint32_t raysThisVertex, shadowRays, visible;
+    __device__ TailSink(const SceneView& s, SharedStack st) : S(s), sstack(st) { result = v3s(0.0f); lightSum = v3s(0.0f); raysThisVertex = 0; shadowRays = 0; visible = 0; }
+    __device__ void add(const V4& thr, const V4& c) { result = mul_add(xyz(thr), xyz(c), result); }
+    __device__ void shadow(const Ray& ray, float tMax, const V4& c, uint32_t)
+    {
+        raysThisVertex++; shadowRays++;
+        const bool occluded = scene_traverse_shadow<false>(S, ray, tMax, nullptr, sstack);
+        if (!occluded) { visible++; lightSum = lightSum + xyz(c); }
+        else lightSum = lightSum + v3s(0.0f);           // k_shadow zeroes the contribution, k_resolve still adds it
+    }
+    __device__ void end_lights(const V4& thr)
+    {
+        if (raysThisVertex) result = mul_add(xyz(thr), lightSum, result);       // k_resolve runs only for paths that own shadow rays
+        lightSum = v3s(0.0f); raysThisVertex = 0;
+    }
+};
+
+template <bool kTex>
+__global__ void __launch_bounds__(128, 4) k_tail(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const __grid_constant__ Wavefront W, uint32_t depth)
+{
+    // tailTaken = 1 + the depth at which the tail took over.  CTAs of THIS launch may already see the value written by
+    // its first CTA (a grid larger than what is resident starts late CTAs after early ones have finished): they must
+    // carry on; launches for later depths see a different value and leave.
+    const uint32_t taken = W.ctl->tailTaken;
+    if (taken != 0u && taken != depth + 1u) return;
+    const uint32_t count = W.ctl->pathCount[depth];
+    if (count == 0u || count > W.tailThreshold) return;
+    extern __shared__ uint32_t smemStack[];
+    SharedStack sstack = (SharedStack)__cvta_generic_to_shared(smemStack) + threadIdx.x * 4u;
+    asm volatile("" : "+r"(sstack));
+    const PathBuf& in = W.buf[depth & 1];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long rays = 0, shadowRays = 0, visible = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+    {
+        PathState ps;
+        load_path(in, i, W, P.width, P.numSeedDims, ps);
+        const uint32_t colorIndex = ps.passSlot * W.numPixels + ps.pixel;
+        const float4 pc = W.passColor[colorIndex];
+        TailSink sink(S, sstack);
+        sink.result = v3(pc.x, pc.y, pc.z);
+        for (;;)
+        {
+            Hit hit;
+            hit.objectId = RTB_INVALID_OBJECT; hit.subObjectId = 0; hit.distance = INFINITY; hit.u = 0.0f; hit.v = 0.0f;
+            scene_traverse<false>(S, ps.ray, hit, nullptr, sstack);
+            rays++;
+            uint32_t numShadow = 0;
+            bool alive;
+            if (P.renderer == RTB_RENDERER_PATH_TRACER_MIS) alive = shade_vertex_mis<kTex>(S, P, ps, hit, sink, numShadow);
+            else alive = shade_vertex_pt<kTex>(S, P, ps, hit, sink);
+            if (!alive) break;
+        }
+        W.passColor[colorIndex] = make_float4(sink.result.x, sink.result.y, sink.result.z, 0.0f);
+        shadowRays += sink.shadowRays; visible += sink.visible;
+    }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        rays += __shfl_down_sync(0xFFFFFFFFu, rays, o);
+        shadowRays += __shfl_down_sync(0xFFFFFFFFu, shadowRays, o);
+        visible += __shfl_down_sync(0xFFFFFFFFu, visible, o);
+    }
+    if (lane == 0)
+    {
+        if (rays) atomicAdd(&W.tot->numRays, rays);
+        if (shadowRays) atomicAdd(&W.tot->numShadowRays, shadowRays);
+        if (visible) atomicAdd(&W.tot->numShadowRaysHit, visible);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) W.ctl->tailTaken = depth + 1u;
+}
+
 // PathTracerMIS::SampleLights: accumulatedColor += SampleLight(light) in light order (PathTracerMIS.cpp:142-148), then
 // resultColor.MulAndAccumulate(throughput, accumulatedColor) (PathTracerMIS.cpp:320)
 __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ Wavefront W, uint32_t depth)
 {
-    const uint32_t count = W.ctl->shadowPathCount[depth];
+    const uint32_t count = W.ctl->tailTaken ? 0u : W.ctl->shadowPathCount[depth];
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride)
     {
@@ -410,7 +498,10 @@ __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ Wavefro
 
 // Film::AccumulateColor, Film.cpp:25-39: sum += colour; secondarySum += colour on even passes.  The passes of a batch
 // are added in pass order, so the float sums are the ones the reference gets pass after pass.
-__global__ void __launch_bounds__(256) k_film(const __grid_constant__ Wavefront W, float* __restrict__ sum, float* __restrict__ sum2)
+// `snapshots` (optional): the film as of EVERY pass of the batch, snapshots[b * snapshotStride + 3 * slot], so that a
+// caller who wants each pass' frame (progressive display, the end-to-end bench) does not have to render pass by pass.
+__global__ void __launch_bounds__(256) k_film(const __grid_constant__ Wavefront W, float* __restrict__ sum, float* __restrict__ sum2,
+                                              float* __restrict__ snapshots, size_t snapshotStride)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < W.numPixels; i += stride)
@@ -423,6 +514,11 @@ __global__ void __launch_bounds__(256) k_film(const __grid_constant__ Wavefront 
             const float4 c = W.passColor[(size_t)b * W.numPixels + i];
             s0 = s0 + c.x; s1 = s1 + c.y; s2 = s2 + c.z;
             if (((W.firstPassIndex + b) & 1u) == 0u) { t0 = t0 + c.x; t1 = t1 + c.y; t2 = t2 + c.z; }
+            if (snapshots)
+            {
+                float* q = snapshots + (size_t)b * snapshotStride + (size_t)i * 3;
+                q[0] = s0; q[1] = s1; q[2] = s2;
+            }
         }
         s[0] = s0; s[1] = s1; s[2] = s2;
         t[0] = t0; t[1] = t1; t[2] = t2;
@@ -585,6 +681,7 @@ struct RtbContext
     SceneView view;
     uint32_t numLights = 0;
     size_t stackBytes = 0;         // dynamic shared memory of the traversal kernels: the scene's worst-case stack x 128 threads x 4 B
+    uint32_t tailThreshold = 65536;   // k_tail finishes a wavefront once at most this many paths are alive (RTB_TAIL_PATHS, 0 = off)
 
     // film + wavefront
     uint32_t width = 0, height = 0;
@@ -627,6 +724,8 @@ struct RtbContext
     cudaEvent_t mainMark = nullptr;       // position of the main stream when a wavefront was enqueued
     bool slotsNeedMain = true;            // the main stream holds work the slots must wait for (reset / resize / upload)
     bool slotsOwnStreams = false;         // false: one slot on the main stream (default), true: RTB_SLOTS > 1
+    DevArray<float> snapshots;            // rtb_film_snapshots: snapshotCapacity x shardSlots x 3 floats
+    uint32_t snapshotCapacity = 0;
     DevArray<Totals> totals;
     DevArray<uint32_t> seed;              // single-pass helpers (rtb_sample_batch / rtb_primary_rays)
 
@@ -658,6 +757,7 @@ static void free_scene(RtbContext* c)
 static void free_film(RtbContext* c)
 {
     c->pixelList.release(); c->pixelListAll.release(); c->sum.release(); c->sum2.release(); c->raster.release(); c->rasterAsync[0].release(); c->rasterAsync[1].release();
+    c->snapshots.release(); c->snapshotCapacity = 0;
     for (RtbContext::Slot& t : c->slots)
     {
         for (int b = 0; b < 2; ++b) { for (int k = 0; k < 4; ++k) t.p[b][k].release(); t.p4[b].release(); }
@@ -762,6 +862,9 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
         cudaFuncSetAttribute(k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
         cudaFuncSetAttribute(k_trace_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
         cudaFuncSetAttribute(k_trace_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+        cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+        cudaFuncSetAttribute(k_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+        if (const char* t = getenv("RTB_TAIL_PATHS")) c->tailThreshold = (uint32_t)strtoul(t, nullptr, 10);
     }
     // wavefront slots (see RtbContext::Slot).  The default is ONE slot that runs on the main stream, i.e. strictly one
     // kernel at a time: with several slots (RTB_SLOTS=4: +3 % device-resident, +9-12 % end to end on the bench) the
@@ -1017,7 +1120,7 @@ static cudaEvent_t next_event(RtbContext* c, size_t& cursor, cudaStream_t stream
 }
 
 // one wavefront of `batch` consecutive passes that share everything but (seed, sampleOffset, passIndex)
-static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch)
+static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch, uint32_t snapshotIndex)
 {
     const RtbPassDesc* pass = &passes[0];
     PassParams P;
@@ -1071,6 +1174,10 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
     const int blocks128 = (int)std::min<size_t>((size_t)blocksCap, std::max<size_t>(1, ((size_t)numPaths + 127) / 128));
     const int blocksShadow = (int)std::min<size_t>((size_t)blocksCap, std::max<size_t>(1, ((size_t)numPaths * std::max<uint32_t>(1u, W.raysPerPath) + 127) / 128));
     const int blocks256 = c->numSMs * 4;
+    // the instrumented (counting) context keeps the plain wavefront so that its per-ray test counters stay per kernel
+    const uint32_t tailThreshold = (count || pass->renderer == RTB_RENDERER_DEBUG) ? 0u : c->tailThreshold;
+    const int tailBlocks = tailThreshold ? (int)std::min<size_t>((size_t)blocks128, ((size_t)tailThreshold + 127) / 128) : 0;
+    W.tailThreshold = tailThreshold;
     size_t ev = 0;
     std::vector<cudaEvent_t> marks;
     if (prof) marks.push_back(next_event(c, ev, s));
@@ -1095,13 +1202,22 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
             else k_shadow<false><<<shadowBlocks, 128, c->stackBytes, s>>>(c->view, W, d);
             k_resolve<<<blocks256, 256, 0, s>>>(W, d);
         }
+        if (tailBlocks > 0 && d < depthLimit)
+        {
+            // does nothing unless at most tailThreshold paths are left, then finishes them all (see k_tail)
+            if (textured) k_tail<true><<<tailBlocks, 128, c->stackBytes, s>>>(c->view, P, W, d + 1);
+            else k_tail<false><<<tailBlocks, 128, c->stackBytes, s>>>(c->view, P, W, d + 1);
+            c->counters.numKernelLaunches++;
+        }
         if (prof) marks.push_back(next_event(c, ev, s));
     }
     // the film: after the previous wavefront's k_film (pass order) and after whatever the caller had enqueued on the main
     // stream when this wavefront was submitted (e.g. a snapshot or an all-gather still reading the film)
     if (c->lastFilm) RTB_CUDA(cudaStreamWaitEvent(s, c->lastFilm, 0));
     RTB_CUDA(cudaStreamWaitEvent(s, c->mainMark, 0));
-    k_film<<<blocks256, 256, 0, s>>>(W, c->sum.ptr, c->sum2.ptr);
+    float* snap = nullptr;
+    if (c->snapshots.ptr && snapshotIndex + batch <= c->snapshotCapacity) snap = c->snapshots.ptr + (size_t)snapshotIndex * c->shardSlots * 3;
+    k_film<<<blocks256, 256, 0, s>>>(W, c->sum.ptr, c->sum2.ptr, snap, (size_t)c->shardSlots * 3);
     RTB_CUDA(cudaEventRecord(slot.filmDone, s));
     c->lastFilm = slot.filmDone;
     if (prof) marks.push_back(next_event(c, ev, s));
@@ -1182,7 +1298,7 @@ int rtb_render_passes(RtbContext* c, const RtbPassDesc* passes, uint32_t count)
         for (uint32_t g = 0; g < groups; ++g)
         {
             const uint32_t n = run / groups + (g < run % groups ? 1u : 0u);
-            int rc = render_batch(c, passes + i, n);
+            int rc = render_batch(c, passes + i, n, i);
             if (rc != RTB_OK) return rc;
             i += n;
         }
@@ -1220,6 +1336,25 @@ int rtb_film_device_buffer(RtbContext* c, int which, void** outDevicePtr, uint64
     RTB_CUDA(join_slots(c));      // what the caller enqueues on the main stream next sees every pass rendered so far
     *outDevicePtr = which == 0 ? c->sum.ptr : c->sum2.ptr;
     *outNumFloats = (uint64_t)c->shardSlots * 3;
+    return RTB_OK;
+}
+
+int rtb_film_snapshots(RtbContext* c, uint32_t maxPasses, void** outDevicePtr, uint64_t* outStrideFloats)
+{
+    if (!c) return fail(RTB_ERR_INVALID_ARG, "null context");
+    if (!c->sum.ptr) return fail(RTB_ERR_INVALID_ARG, "viewport has no size");
+    RTB_CUDA(cudaSetDevice(c->device));
+    RTB_CUDA(sync_all(c));
+    c->snapshots.release(); c->snapshotCapacity = 0;
+    if (maxPasses)
+    {
+        RTB_CUDA(c->snapshots.alloc((size_t)maxPasses * c->shardSlots * 3));
+        RTB_CUDA(cudaMemsetAsync(c->snapshots.ptr, 0, c->snapshots.count * sizeof(float), c->stream));
+        RTB_CUDA(cudaStreamSynchronize(c->stream));
+        c->snapshotCapacity = maxPasses;
+    }
+    if (outDevicePtr) *outDevicePtr = c->snapshots.ptr;
+    if (outStrideFloats) *outStrideFloats = (uint64_t)c->shardSlots * 3;
     return RTB_OK;
 }
 

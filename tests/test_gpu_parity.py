@@ -319,6 +319,31 @@ def test_wavefronts_in_flight_are_bit_identical(scene):
             assert got[2][k] == want[2][k], k
 
 
+@pytest.mark.parametrize("scene", ["mesh_small", "cornell"])
+def test_film_snapshots_of_a_batched_call_equal_pass_by_pass_frames(ctx, scene):
+    """rtb_film_snapshots: one batched rtb_render_passes call leaves the film as of EVERY pass; each snapshot must be
+    the frame Viewport::GetSumBuffer would have returned after that pass (= pass-by-pass rendering), bit for bit."""
+    meta = json.load(open(util.golden("%s_mis.json" % scene)))
+    w, h, n = meta["width"], meta["height"], meta["passes"]
+    sf = capi.SceneFile(util.golden(scene + ".rtb"))
+    ps = capi.PassScript(util.golden(scene + ".passes"))
+    ctx.upload_scene(sf)
+    ctx.resize(w, h)
+    cam = capi.camera_for(sf, w, h)
+    want = []
+    for p in range(n):
+        ctx.render_pass(ctx.make_pass(cam, ps.seeds[p], ps.offsets[p], p))
+        want.append(ctx.read_sum().copy())
+    ctx.reset()
+    ptr, stride = ctx.film_snapshots(n)
+    ctx.render_passes(cam, ps.seeds[:n], ps.offsets[:n], 0)
+    for p in range(n):
+        got = ctx.unshard_film(ptr + 4 * stride * p)           # a snapshot has the layout of the (single-shard) film
+        util.assert_bit_identical(got, want[p], "%s: snapshot after pass %d" % (scene, p))
+    util.assert_bit_identical(ctx.read_sum(), want[-1], "%s: film after the batched call" % scene)
+    ctx.film_snapshots(0)
+
+
 def test_async_read_back_snapshots_every_pass(ctx):
     """rtb_read_sum_async after pass k must deliver the film as of pass k even though pass k+1 is already running
     (double-buffered snapshot on the render stream, copy on a second stream); three read-backs in flight exercise
