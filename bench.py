@@ -318,7 +318,8 @@ def run_gpu(args):
                                 "sample": "2 timed + 1 warm-up passes of %dx%d of the same scene with the reference's AVX2 build on all host threads" % (WIDTH // 2, HEIGHT // 2),
                                 "msamples_per_s": meta["msamples_per_s"], "host_cores": os.cpu_count()}
 
-    assert np.isfinite(pinned[0].array).all() and pinned[0].array.mean() > 0
+    if rank == 0:      # the frames are gathered on rank 0 only
+        assert np.isfinite(pinned[0].array).all() and pinned[0].array.mean() > 0
     vp.close()
     for im in pinned:
         im.close()

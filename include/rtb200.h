@@ -366,8 +366,8 @@ int  rtb_film_snapshots(RtbContext* ctx, uint32_t maxPasses, void** outDevicePtr
 /* scatter gathered shard buffers (numShards * shardFloats, device) back to raster order into hostRgb */
 int  rtb_unshard_film(RtbContext* ctx, const void* gatheredDevice, float* hostRgb);
 /* asynchronous variants: the film is snapshotted in stream order (so later passes do not leak into it) and copied to
- * the host on a second stream while the next passes render; the data is complete after rtb_synchronize.  At most two
- * read-backs are in flight (the third waits for the first).  The host buffer should be page-locked (rtb_host_alloc). */
+ * the host on a second stream while the next passes render; the data is complete after rtb_synchronize.  At most twelve
+ * read-backs are in flight (the thirteenth waits for the first).  The host buffer should be page-locked (rtb_host_alloc). */
 int  rtb_read_sum_async(RtbContext* ctx, float* rgb, int which);
 int  rtb_unshard_film_async(RtbContext* ctx, const void* gatheredDevice, float* hostRgb);
 /* page-locked host memory for the rgb / hostRgb arguments above (the reference's Viewport owns its sum Bitmap,

@@ -33,6 +33,7 @@ using namespace rtb;
 // ---------------------------------------------------------------------------------------------------------------------
 
 #define RTB_MAX_DEPTH_SLOTS 64
+#define RTB_SNAP_RING 12      // raster snapshots in flight for rtb_read_sum_async / rtb_unshard_film_async
 // shared-memory traversal stack: at most 227 KB per CTA = 454 entries x 128 threads x 4 B (rtb_trace.h)
 #define RTB_MAX_SMEM_STACK_ENTRIES (RTB_SMEM_STACK ? 440u : (uint32_t)RTB_STACK_SIZE)
 
@@ -693,9 +694,11 @@ struct RtbContext
     DevArray<uint32_t> pixelListAll;  // all shards back to back, padded with 0xFFFFFFFF
     DevArray<float> sum, sum2;
     DevArray<float> raster;           // scratch for read-back
-    DevArray<float> rasterAsync[2];   // double-buffered snapshots for the asynchronous read-back
+    // ring of raster snapshots for the asynchronous read-back: the render stream only waits for a copy when the ring
+    // wraps, so a group of frames (rtb_film_snapshots) can be in flight on the copy stream while the next passes render
+    DevArray<float> rasterAsync[RTB_SNAP_RING];
     cudaStream_t copyStream = nullptr;
-    cudaEvent_t snapReady[2] = {nullptr, nullptr}, snapCopied[2] = {nullptr, nullptr};
+    cudaEvent_t snapReady[RTB_SNAP_RING] = {}, snapCopied[RTB_SNAP_RING] = {};
     uint32_t snapIndex = 0;
 
     // Wavefront slots: consecutive wavefronts (one per rtb_render_pass call, or per batch of rtb_render_passes) go to
@@ -756,7 +759,8 @@ static void free_scene(RtbContext* c)
 
 static void free_film(RtbContext* c)
 {
-    c->pixelList.release(); c->pixelListAll.release(); c->sum.release(); c->sum2.release(); c->raster.release(); c->rasterAsync[0].release(); c->rasterAsync[1].release();
+    c->pixelList.release(); c->pixelListAll.release(); c->sum.release(); c->sum2.release(); c->raster.release();
+    for (int i = 0; i < RTB_SNAP_RING; ++i) c->rasterAsync[i].release();
     c->snapshots.release(); c->snapshotCapacity = 0;
     for (RtbContext::Slot& t : c->slots)
     {
@@ -913,7 +917,7 @@ void rtb_destroy(RtbContext* c)
     if (c->copyStream)
     {
         cudaStreamSynchronize(c->copyStream);
-        for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->snapReady[i]); cudaEventDestroy(c->snapCopied[i]); }
+        for (int i = 0; i < RTB_SNAP_RING; ++i) { cudaEventDestroy(c->snapReady[i]); cudaEventDestroy(c->snapCopied[i]); }
         cudaStreamDestroy(c->copyStream);
     }
     if (c->ownStream) cudaStreamDestroy(c->stream);
@@ -1383,7 +1387,7 @@ static int read_back_async(RtbContext* c, const void* gatheredDevice, float* hos
     if (!c->copyStream)
     {
         RTB_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < RTB_SNAP_RING; ++i)
         {
             RTB_CUDA(cudaEventCreateWithFlags(&c->snapReady[i], cudaEventDisableTiming));
             RTB_CUDA(cudaEventCreateWithFlags(&c->snapCopied[i], cudaEventDisableTiming));
@@ -1391,7 +1395,7 @@ static int read_back_async(RtbContext* c, const void* gatheredDevice, float* hos
         }
     }
     RTB_CUDA(join_slots(c));
-    const uint32_t b = c->snapIndex++ & 1u;
+    const uint32_t b = c->snapIndex++ % RTB_SNAP_RING;
     const size_t n = (size_t)c->width * c->height * 3;
     if (c->rasterAsync[b].count != n) RTB_CUDA(c->rasterAsync[b].alloc(n));
     float* dst = c->rasterAsync[b].ptr;
