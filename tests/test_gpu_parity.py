@@ -285,9 +285,10 @@ def test_batched_passes_are_bit_identical_to_single_passes(ctx, scene):
 
 @pytest.mark.parametrize("scene", ["mesh_small", "textures"])
 def test_wavefronts_in_flight_are_bit_identical(scene):
-    """Pass-by-pass calls put every pass into its own wavefront slot (own stream): up to four wavefronts overlap on the
-    GPU.  The film, the secondary film and the ray counters must equal ONE batched wavefront of the same passes, every
-    time (this is the test that caught the corrupted local-memory traversal stack, see rtb_trace.h)."""
+    """Pass-by-pass rendering (with RTB_SLOTS > 1: every pass in its own wavefront slot / stream, several wavefronts
+    overlapping on the GPU; by default one slot, one kernel at a time) against ONE batched wavefront of the same passes:
+    film, secondary film and ray counters must be equal, every time.  Run with RTB_SLOTS=4 this is the detector of the
+    open overlap problem described in DESIGN.md section 4."""
     meta = json.load(open(util.golden("%s_mis.json" % scene)))
     sf = capi.SceneFile(util.golden(scene + ".rtb"))
     w = h = 256
