@@ -2,7 +2,7 @@
 // the plugin surface: same class names, same construction rules, same failure behaviour.  Nothing is evaluated on
 // the host: Scene::Flatten turns these objects into the POD RtbTexture array that rtb_upload_scene copies to HBM.
 //
-//   Bitmap (BMP subset)          Core/Utils/Bitmap.cpp:197-333 (Init, Load), Core/Utils/BitmapBMP.cpp:46-139 (LoadBMP),
+//   Bitmap (BMP + DDS)           Core/Utils/Bitmap.cpp:197-333 (Init, Load), BitmapBMP.cpp:46-139, BitmapDDS.cpp:228-540, BlockCompression.cpp,
 //                                Bitmap::GetPixel Core/Utils/Bitmap.cpp:335-518, Convert_sRGB_To_Linear Color/ColorHelpers.h:17-27
 //   BitmapTexture                Core/Textures/BitmapTexture.cpp:17-21 (filter = Bilinear_SmoothStep)
 //   CheckerboardTexture          Core/Textures/CheckerboardTexture.cpp:9-25
@@ -10,10 +10,11 @@
 //   MixTexture                   Core/Textures/MixTexture.cpp:8-17
 //
 // Bitmap decodes into the float quadruples the reference's Bitmap::GetPixel returns for every texel (format decode +
-// sRGB -> linear for gamma-space files), which is what the device samples.  DDS and OpenEXR containers are
-// recognised and REFUSED with an error (the reference would load them; silently dropping the texture would render a
-// different image); any other unreadable file yields "no texture" exactly like the reference (Bitmap::Load fails,
-// helpers::LoadTexture returns nullptr, Demo/MeshLoader.cpp:31-76).
+// sRGB -> linear for gamma-space files), which is what the device samples.  BMP and DDS (Core/Utils/BitmapDDS.cpp:
+// uncompressed 8 / 16 / 32-bit integer, half and float layouts, R11G11B10, R9G9B9E5, BC1 / BC4 / BC5 blocks) are read;
+// OpenEXR containers are recognised and REFUSED with an error (the reference reads them through the third-party
+// tinyexr; silently dropping the texture would render a different image); any other unreadable file yields "no
+// texture" exactly like the reference (Bitmap::Load fails, helpers::LoadTexture returns nullptr, MeshLoader.cpp:31-76).
 #pragma once
 
 #include <cmath>
@@ -34,6 +35,14 @@ using math::Vector4;
 class Bitmap
 {
 public:
+    // the subset of Bitmap::Format (Core/Utils/Bitmap.h:16-42) the BMP and DDS readers can produce
+    enum class Format : uint8_t
+    {
+        Unknown = 0, R8_UNorm, R8G8_UNorm, B8G8R8_UNorm, B8G8R8A8_UNorm, R8G8B8A8_UNorm, B8G8R8A8_UNorm_Palette, B5G6R5_UNorm,
+        R16_UNorm, R16G16_UNorm, R16G16B16A16_UNorm, R32_Float, R32G32_Float, R32G32B32_Float, R32G32B32A32_Float,
+        R11G11B10_Float, R16_Half, R16G16_Half, R16G16B16A16_Half, R9G9B9E5_SharedExp, BC1, BC4, BC5,
+    };
+
     uint32_t GetWidth() const { return mWidth; }
     uint32_t GetHeight() const { return mHeight; }
     const std::vector<float>& GetTexels() const { return mTexels; }     // width*height*4, texel (x,y) = GetPixel(x,y)
@@ -44,30 +53,210 @@ public:
     {
         FILE* file = fopen(path, "rb");
         if (!file) return false;                         // "Failed to load source image from file"
-        const bool ok = LoadBMP(file);
+        bool ok = LoadBMP(file);
         if (!ok && mError.empty())
         {
-            // the reference would now try its DDS and OpenEXR readers
+            fseek(file, 0, SEEK_SET);
+            ok = LoadDDS(file, path);
+        }
+        if (!ok && mError.empty())
+        {
+            // the reference would now try its OpenEXR reader (Bitmap::LoadEXR, third-party tinyexr)
             uint8_t magic[4] = { 0, 0, 0, 0 };
             fseek(file, 0, SEEK_SET);
-            if (fread(magic, 1, 4, file) == 4)
-            {
-                if (!memcmp(magic, "DDS ", 4)) mError = std::string("DDS bitmaps are not supported by this build: '") + path + "'";
-                if (magic[0] == 0x76 && magic[1] == 0x2F && magic[2] == 0x31 && magic[3] == 0x01) mError = std::string("OpenEXR bitmaps are not supported by this build: '") + path + "'";
-            }
+            if (fread(magic, 1, 4, file) == 4 && magic[0] == 0x76 && magic[1] == 0x2F && magic[2] == 0x31 && magic[3] == 0x01)
+                mError = std::string("OpenEXR bitmaps are not supported by this build: '") + path + "'";
         }
         fclose(file);
+        if (ok) Decode();
         return ok;
     }
 
 private:
-    static float Unorm8(uint8_t b) { return static_cast<float>(b) * (1.0f / 255.0f); }     // every 8-bit path of GetPixel reduces to this (see header)
+    // ---- raw storage as the reference keeps it (Bitmap::Init, Bitmap.cpp:197-254: data + a zeroed 64-byte margin) ----
+    Format mFormat = Format::Unknown;
+    bool mLinearSpace = true;
+    uint32_t mStride = 0;
+    std::vector<uint8_t> mData, mPalette;
+
+    static uint32_t BitsPerPixel(Format f)              // Bitmap::BitsPerPixel, Bitmap.cpp:17-49
+    {
+        switch (f)
+        {
+        case Format::R8_UNorm: case Format::B8G8R8A8_UNorm_Palette: return 8;
+        case Format::R8G8_UNorm: case Format::B5G6R5_UNorm: case Format::R16_UNorm: case Format::R16_Half: return 16;
+        case Format::B8G8R8_UNorm: return 24;
+        case Format::B8G8R8A8_UNorm: case Format::R8G8B8A8_UNorm: case Format::R16G16_UNorm: case Format::R32_Float:
+        case Format::R11G11B10_Float: case Format::R16G16_Half: case Format::R9G9B9E5_SharedExp: return 32;
+        case Format::R16G16B16A16_UNorm: case Format::R32G32_Float: case Format::R16G16B16A16_Half: return 64;
+        case Format::R32G32B32_Float: return 96;
+        case Format::R32G32B32A32_Float: return 128;
+        case Format::BC1: case Format::BC4: return 4;
+        case Format::BC5: return 8;
+        default: return 0;
+        }
+    }
+
+    bool Init(uint32_t width, uint32_t height, Format format, uint32_t stride, bool linearSpace)
+    {
+        const uint32_t minStride = (uint32_t)((uint64_t)width * BitsPerPixel(format) / 8);
+        mStride = stride > minStride ? stride : minStride;
+        const uint64_t dataSize = (uint64_t)height * mStride;
+        if (dataSize == 0) return false;
+        if (width > 65536u || height > 65536u) { mError = "bitmap larger than 65536 texels per side"; return false; }
+        mData.assign((size_t)dataSize + 64, 0);
+        mWidth = width; mHeight = height; mFormat = format; mLinearSpace = linearSpace;
+        return true;
+    }
+    size_t DataSize() const { return mData.size() - 64; }
+
+    static float Unorm8(uint32_t b) { return static_cast<float>(b) * (1.0f / 255.0f); }     // every 8-bit path of GetPixel reduces to this
     // Convert_sRGB_To_Linear, ColorHelpers.h:17-27 (two fused multiply-adds and a multiply, per lane)
     static float SrgbToLinear(float c)
     {
         float r = std::fmaf(c, 0.305306011f, 0.682171111f);
         r = std::fmaf(c, r, 0.012522878f);
         return r * c;
+    }
+    static float BitsToFloat(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+    static uint16_t Load16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
+    static uint32_t Load32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+    static float LoadF32(const uint8_t* p) { float v; memcpy(&v, p, 4); return v; }
+
+    // Half::ToFloat, software path (Math/HalfImpl.h:68-105; the oracle is not built with RT_USE_FP16C)
+    static float HalfToFloat(uint16_t value)
+    {
+        uint32_t mantissa = static_cast<uint32_t>(value & 0x03FF);
+        uint32_t exponent = (value & 0x7C00);
+        if (exponent == 0x7C00) exponent = 0x8f;
+        else if (exponent != 0) exponent = static_cast<uint32_t>((static_cast<int>(value) >> 10) & 0x1F);
+        else if (mantissa != 0)
+        {
+            exponent = 1;
+            do { exponent--; mantissa <<= 1; } while ((mantissa & 0x0400) == 0);
+            mantissa &= 0x03FF;
+        }
+        else exponent = static_cast<uint32_t>(-112);
+        return BitsToFloat(((static_cast<uint32_t>(value) & 0x8000) << 16) | ((exponent + 112) << 23) | (mantissa << 13));
+    }
+
+    // helper::DecodeBC_Grayscale, BlockCompression.cpp:72-100
+    static float DecodeBCGrayscale(const uint8_t* blockData, uint32_t x, uint32_t y)
+    {
+        const float intColor0 = blockData[0], intColor1 = blockData[1];
+        const float color0 = intColor0 / 255.0f, color1 = intColor1 / 255.0f;
+        uint64_t code; memcpy(&code, blockData + 2, 8);
+        const uint32_t index = (uint32_t)((code >> (uint64_t)(3 * (4 * y + x))) % 8);
+        if (index == 0) return color0;
+        if (index == 1) return color1;
+        if (intColor0 > intColor1) return (color0 * (float)(8 - index) + color1 * (float)(index - 1)) / 7.0f;
+        if (index == 6) return 0.0f;
+        if (index == 7) return 1.0f;
+        return (color0 * (float)(6 - index) + color1 * (float)(index - 1)) / 5.0f;
+    }
+
+    // Bitmap::GetPixel before the colour-space conversion, Bitmap.cpp:335-506
+    void GetRawPixel(uint32_t x, uint32_t y, float c[4]) const
+    {
+        const uint8_t* row = mData.data() + (size_t)mStride * y;
+        c[0] = c[1] = c[2] = c[3] = 0.0f;
+        switch (mFormat)
+        {
+        case Format::R8_UNorm: c[0] = c[1] = c[2] = c[3] = Unorm8(row[x]); break;                      // FromInteger(v) * (1/255): splat
+        case Format::R8G8_UNorm: { const uint8_t* s = row + 2u * (size_t)x; c[0] = Unorm8(s[0]); c[1] = Unorm8(s[1]); break; }
+        case Format::B8G8R8_UNorm: { const uint8_t* s = row + 3u * (size_t)x; c[0] = Unorm8(s[2]); c[1] = Unorm8(s[1]); c[2] = Unorm8(s[0]); break; }
+        case Format::B8G8R8A8_UNorm: { const uint8_t* s = row + 4u * (size_t)x; c[0] = Unorm8(s[2]); c[1] = Unorm8(s[1]); c[2] = Unorm8(s[0]); c[3] = Unorm8(s[3]); break; }
+        case Format::R8G8B8A8_UNorm: { const uint8_t* s = row + 4u * (size_t)x; c[0] = Unorm8(s[0]); c[1] = Unorm8(s[1]); c[2] = Unorm8(s[2]); c[3] = Unorm8(s[3]); break; }
+        case Format::B8G8R8A8_UNorm_Palette:
+        {
+            const size_t index = row[x];
+            uint8_t s[4] = { 0, 0, 0, 0 };
+            if (4u * index + 4u <= mPalette.size()) memcpy(s, mPalette.data() + 4u * index, 4);
+            c[0] = Unorm8(s[2]); c[1] = Unorm8(s[1]); c[2] = Unorm8(s[0]); c[3] = Unorm8(s[3]);
+            break;
+        }
+        case Format::B5G6R5_UNorm:
+        {
+            // Vector4_Load_B5G6R5_Norm: masked integer * (2^-k / max) = channel * (1 / max), rounded once
+            const uint32_t v = Load16(row + 2u * (size_t)x);
+            c[0] = (float)((v >> 11) & 0x1Fu) * (1.0f / 31.0f); c[1] = (float)((v >> 5) & 0x3Fu) * (1.0f / 63.0f); c[2] = (float)(v & 0x1Fu) * (1.0f / 31.0f);
+            break;
+        }
+        case Format::R16_UNorm: c[0] = c[1] = c[2] = c[3] = (float)Load16(row + 2u * (size_t)x) * (1.0f / 65535.0f); break;
+        case Format::R16G16_UNorm: { const uint8_t* s = row + 4u * (size_t)x; c[0] = (float)Load16(s) * (1.0f / 65535.0f); c[1] = (float)Load16(s + 2) * (1.0f / 65535.0f); break; }
+        case Format::R16G16B16A16_UNorm: { const uint8_t* s = row + 8u * (size_t)x; for (int k = 0; k < 4; ++k) c[k] = (float)Load16(s + 2 * k) * (1.0f / 65535.0f); break; }
+        case Format::R32_Float: c[0] = c[1] = c[2] = c[3] = LoadF32(row + 4u * (size_t)x); break;       // Vector4(float): splat
+        case Format::R32G32_Float: { const uint8_t* s = row + 8u * (size_t)x; c[0] = LoadF32(s); c[1] = LoadF32(s + 4); break; }
+        case Format::R32G32B32_Float: { const uint8_t* s = row + 12u * (size_t)x; c[0] = LoadF32(s); c[1] = LoadF32(s + 4); c[2] = LoadF32(s + 8); break; }
+        case Format::R32G32B32A32_Float: { const uint8_t* s = row + 16u * (size_t)x; for (int k = 0; k < 4; ++k) c[k] = LoadF32(s + 4 * k); break; }
+        case Format::R16_Half: c[0] = c[1] = c[2] = c[3] = HalfToFloat(Load16(row + 2u * (size_t)x)); break;
+        case Format::R16G16_Half: { const uint8_t* s = row + 4u * (size_t)x; c[0] = HalfToFloat(Load16(s)); c[1] = HalfToFloat(Load16(s + 2)); break; }
+        case Format::R16G16B16A16_Half: { const uint8_t* s = row + 8u * (size_t)x; for (int k = 0; k < 4; ++k) c[k] = HalfToFloat(Load16(s + 2 * k)); break; }
+        case Format::R9G9B9E5_SharedExp:
+        {
+            // SharedExpFloat3::ToVector, Packed.h:126-131
+            const uint32_t v = Load32(row + 4u * (size_t)x);
+            const float scale = BitsToFloat(0x33800000u + ((v >> 27) << 23));
+            c[0] = scale * (float)(v & 0x1FFu); c[1] = scale * (float)((v >> 9) & 0x1FFu); c[2] = scale * (float)((v >> 18) & 0x1FFu); c[3] = scale * 0.0f;
+            break;
+        }
+        case Format::R11G11B10_Float:
+        {
+            // PackedFloat3::ToVector, Packed.h:160-167 (bit assembly; no Inf / NaN / denormal handling, like the reference)
+            const uint32_t v = Load32(row + 4u * (size_t)x);
+            const uint32_t xm = v & 0x3Fu, xe = (v >> 6) & 0x1Fu, ym = (v >> 11) & 0x3Fu, ye = (v >> 17) & 0x1Fu, zm = (v >> 22) & 0x1Fu, ze = (v >> 27) & 0x1Fu;
+            c[0] = BitsToFloat(((xe + 112u) << 23) | (xm << 17)); c[1] = BitsToFloat(((ye + 112u) << 23) | (ym << 17)); c[2] = BitsToFloat(((ze + 112u) << 23) | (zm << 17));
+            break;
+        }
+        case Format::BC1:
+        {
+            // DecodeBC1, BlockCompression.cpp:52-70: lerp of the masked 5:6:5 integers, then the per-channel scale
+            const size_t blocksInRow = mWidth / 4u;
+            const uint8_t* block = mData.data() + 8u * (blocksInRow * (y / 4u) + (x / 4u));
+            const uint32_t v0 = Load32(block), v1 = Load32(block + 2), code = Load32(block + 4);
+            const uint32_t index = (code >> (2u * (4u * (y % 4u) + (x % 4u)))) % 4u;
+            const float weights[] = { 0.0f, 1.0f, 1.0f / 3.0f, 2.0f / 3.0f };
+            const uint32_t masks[3] = { 0x1Fu << 11, 0x3Fu << 5, 0x1Fu };
+            const float scale[3] = { 1.0f / 2048.0f / 31.0f, 1.0f / 32.0f / 63.0f, 1.0f / 31.0f };
+            for (int k = 0; k < 3; ++k)
+            {
+                const float a = (float)(int32_t)(v0 & masks[k]), b = (float)(int32_t)(v1 & masks[k]);
+                c[k] = std::fmaf(b - a, weights[index], a) * scale[k];
+            }
+            c[3] = std::fmaf(0.0f - 0.0f, weights[index], 0.0f) * 0.0f;
+            break;
+        }
+        case Format::BC4:
+        {
+            const size_t blocksInRow = mWidth / 4u;
+            const float v = DecodeBCGrayscale(mData.data() + 8u * (blocksInRow * (y / 4u) + (x / 4u)), x % 4u, y % 4u);
+            c[0] = c[1] = c[2] = v; c[3] = 1.0f;
+            break;
+        }
+        case Format::BC5:
+        {
+            const size_t blocksInRow = mWidth / 4u;
+            const uint8_t* block = mData.data() + 16u * (blocksInRow * (y / 4u) + (x / 4u));
+            const float red = DecodeBCGrayscale(block, x % 4u, y % 4u), green = DecodeBCGrayscale(block + 8, x % 4u, y % 4u);
+            c[0] = green; c[1] = red; c[2] = 0.0f; c[3] = 1.0f;          // (green, red, 0, 1), BlockCompression.cpp:141
+            break;
+        }
+        default: break;
+        }
+    }
+
+    void Decode()
+    {
+        mTexels.resize((size_t)mWidth * mHeight * 4);
+        for (uint32_t y = 0; y < mHeight; ++y)
+            for (uint32_t x = 0; x < mWidth; ++x)
+            {
+                float c[4];
+                GetRawPixel(x, y, c);
+                float* out = &mTexels[4 * ((size_t)y * mWidth + x)];
+                for (int k = 0; k < 4; ++k) out[k] = mLinearSpace ? c[k] : SrgbToLinear(c[k]);
+            }
+        mData.clear(); mData.shrink_to_fit(); mPalette.clear();
     }
 
 #pragma pack(push, 2)
@@ -88,49 +277,118 @@ private:
         BitmapInfoHeader ih;
         if (fread(&ih, sizeof(ih), 1, file) != 1) return false;
         if (ih.biPlanes != 1 || ih.biCompression != 0) return false;
-        enum { kBGR, kPalette, kGrey } format;
-        uint32_t bytesPerPixel;
-        if (ih.biBitCount == 24) { format = kBGR; bytesPerPixel = 3; }
-        else if (ih.biBitCount == 8 && ih.biClrUsed > 0) { format = kPalette; bytesPerPixel = 1; }
-        else if (ih.biBitCount == 8 && ih.biClrUsed == 0) { format = kGrey; bytesPerPixel = 1; }
+        Format format;
+        if (ih.biBitCount == 24) format = Format::B8G8R8_UNorm;
+        else if (ih.biBitCount == 8 && ih.biClrUsed > 0) format = Format::B8G8R8A8_UNorm_Palette;
+        else if (ih.biBitCount == 8 && ih.biClrUsed == 0) format = Format::R8_UNorm;
         else return false;
         if (ih.biWidth == 0 || ih.biHeight == 0) return false;
-        if (ih.biWidth > 65536u || ih.biHeight > 65536u) { mError = "bitmap larger than 65536 texels per side"; return false; }
-        const uint32_t stride = (ih.biWidth * bytesPerPixel + 3u) & ~3u;
-        std::vector<uint8_t> palette((size_t)ih.biClrUsed * 4u);
-        if (!palette.empty() && fread(palette.data(), palette.size(), 1, file) != 1) return false;
+        const uint32_t stride = (ih.biWidth * BitsPerPixel(format) / 8 + 3u) & ~3u;
+        if (!Init(ih.biWidth, ih.biHeight, format, stride, false)) return false;
+        mPalette.assign((size_t)ih.biClrUsed * 4u, 0);
+        if (!mPalette.empty() && fread(mPalette.data(), mPalette.size(), 1, file) != 1) return false;
         if (fseek(file, (long)fh.bfOffBits, SEEK_SET) != 0) return false;
-        std::vector<uint8_t> data((size_t)stride * ih.biHeight);
-        if (fread(data.data(), data.size(), 1, file) != 1) return false;
+        if (fread(mData.data(), DataSize(), 1, file) != 1) return false;
+        return true;
+    }
 
-        mWidth = ih.biWidth; mHeight = ih.biHeight;
-        mTexels.resize((size_t)mWidth * mHeight * 4);
-        for (uint32_t y = 0; y < mHeight; ++y)
+    // Bitmap::LoadDDS, BitmapDDS.cpp:228-540: only the top mip level is read, formats as listed there
+    bool LoadDDS(FILE* file, const char* path)
+    {
+        struct PixelFormat { uint32_t size, flags, fourCC, rgbBitCount, rBitMask, gBitMask, bBitMask, aBitMask; };
+        struct Header { uint32_t magic, size, flags, height, width, pitchOrLinearSize, depth, mipMapCount, reserved1[11]; PixelFormat pf; uint32_t caps[4]; uint32_t reserved2; };
+        struct HeaderDX10 { uint32_t dxgiFormat, resourceDimension, miscFlag, arraySize, miscFlags2; };
+        static_assert(sizeof(Header) == 128, "DDS header");
+        Header header;
+        if (fread(&header, sizeof(header), 1, file) != 1) return false;
+        if (header.magic != 0x20534444u) return false;
+        if (header.width < 1 || header.height < 1 || header.width >= 65535u || header.height >= 65535u) return false;
+        auto fourcc = [](char a, char b, char c, char d) { return (uint32_t)(uint8_t)a | ((uint32_t)(uint8_t)b << 8) | ((uint32_t)(uint8_t)c << 16) | ((uint32_t)(uint8_t)d << 24); };
+        Format format = Format::Unknown;
+        bool linear = true;
+        const PixelFormat& pf = header.pf;
+        if (pf.flags & 0x40u)                   // DDPF_RGB
         {
-            const uint8_t* row = data.data() + (size_t)stride * y;
-            for (uint32_t x = 0; x < mWidth; ++x)
+            if (pf.rgbBitCount == 32)
             {
-                float c[4];
-                if (format == kBGR)
-                {
-                    const uint8_t* s = row + 3u * (size_t)x;                 // Vector4_LoadBGR_UNorm: w lane = 0
-                    c[0] = Unorm8(s[2]); c[1] = Unorm8(s[1]); c[2] = Unorm8(s[0]); c[3] = 0.0f;
-                }
-                else if (format == kPalette)
-                {
-                    const size_t index = row[x];                             // B8G8R8A8_UNorm_Palette: swizzle <2,1,0,3>
-                    uint8_t s[4] = { 0, 0, 0, 0 };
-                    if (4u * index + 4u <= palette.size()) memcpy(s, palette.data() + 4u * index, 4);
-                    c[0] = Unorm8(s[2]); c[1] = Unorm8(s[1]); c[2] = Unorm8(s[0]); c[3] = Unorm8(s[3]);
-                }
-                else
-                {
-                    c[0] = c[1] = c[2] = c[3] = Unorm8(row[x]);              // R8_UNorm: splat
-                }
-                float* out = &mTexels[4 * ((size_t)y * mWidth + x)];
-                for (int k = 0; k < 4; ++k) out[k] = SrgbToLinear(c[k]);     // initData.linearSpace = false
+                if (pf.rBitMask == 0x00FF0000u && pf.gBitMask == 0x0000FF00u && pf.bBitMask == 0x000000FFu && pf.aBitMask == 0xFF000000u) { format = Format::B8G8R8A8_UNorm; linear = false; }
+                else if (pf.rBitMask == 0x000000FFu && pf.gBitMask == 0x0000FF00u && pf.bBitMask == 0x00FF0000u && pf.aBitMask == 0xFF000000u) { format = Format::R8G8B8A8_UNorm; linear = false; }
+                else if (pf.rBitMask == 0xFFFFFFFFu && pf.gBitMask == 0 && pf.bBitMask == 0 && pf.aBitMask == 0) format = Format::R32_Float;
+                else if (pf.rBitMask == 0xFFFFu && pf.gBitMask == 0xFFFF0000u && pf.bBitMask == 0 && pf.aBitMask == 0) format = Format::R16G16_UNorm;
+            }
+            else if (pf.rgbBitCount == 16)
+            {
+                if (pf.rBitMask == 0xf800u && pf.gBitMask == 0x07e0u && pf.bBitMask == 0x001fu && pf.aBitMask == 0) { format = Format::B5G6R5_UNorm; linear = false; }
             }
         }
+        else if (pf.flags & 0x4u)               // DDPF_FOURCC
+        {
+            if (pf.fourCC == 111u) format = Format::R16_Half;                  // D3DFMT_R16F
+            else if (pf.fourCC == 112u) format = Format::R16G16_Half;          // D3DFMT_G16R16F
+            else if (pf.fourCC == 113u) format = Format::R16G16B16A16_Half;    // D3DFMT_A16B16G16R16F
+            else if (pf.fourCC == 114u) format = Format::R32_Float;            // D3DFMT_R32F
+            else if (pf.fourCC == 115u) format = Format::R32G32_Float;         // D3DFMT_G32R32F
+            else if (pf.fourCC == 116u) format = Format::R32G32B32A32_Float;   // D3DFMT_A32B32G32R32F
+            else if (pf.fourCC == 36u) format = Format::R16G16B16A16_UNorm;    // D3DFMT_A16B16G16R16
+            else if (pf.fourCC == fourcc('D', 'X', 'T', '1')) format = Format::BC1;
+            else if (pf.fourCC == fourcc('A', 'T', 'I', '1') || pf.fourCC == fourcc('B', 'C', '4', 'U') || pf.fourCC == fourcc('B', 'C', '4', 'S')) format = Format::BC4;
+            else if (pf.fourCC == fourcc('A', 'T', 'I', '2') || pf.fourCC == fourcc('B', 'C', '5', 'U')) format = Format::BC5;
+            else if (pf.fourCC == fourcc('D', 'X', '1', '0'))
+            {
+                HeaderDX10 dx10;
+                if (fread(&dx10, sizeof(dx10), 1, file) != 1) return false;
+                switch (dx10.dxgiFormat)
+                {
+                case 10: format = Format::R16G16B16A16_Half; break;
+                case 34: format = Format::R16G16_Half; break;
+                case 54: format = Format::R16_Half; break;
+                default: break;
+                }
+                switch (dx10.dxgiFormat)         // (the reference's second if-chain starts here: a half format found above survives)
+                {
+                case 2: format = Format::R32G32B32A32_Float; break;
+                case 6: format = Format::R32G32B32_Float; break;
+                case 16: format = Format::R32G32_Float; break;
+                case 41: format = Format::R32_Float; break;
+                case 67: format = Format::R9G9B9E5_SharedExp; break;
+                case 26: format = Format::R11G11B10_Float; break;
+                case 87: format = Format::B8G8R8A8_UNorm; break;
+                case 91: format = Format::B8G8R8A8_UNorm; linear = false; break;
+                case 49: format = Format::R8G8_UNorm; break;
+                case 61: format = Format::R8_UNorm; break;
+                case 85: format = Format::B5G6R5_UNorm; linear = false; break;
+                case 11: format = Format::R16G16B16A16_UNorm; break;
+                case 35: format = Format::R16G16_UNorm; break;
+                case 56: format = Format::R16_UNorm; break;
+                case 71: format = Format::BC1; break;
+                case 72: format = Format::BC1; linear = false; break;
+                case 80: format = Format::BC4; break;
+                case 83: format = Format::BC5; break;
+                default: break;
+                }
+            }
+        }
+        else if (pf.flags & 0x20000u)           // DDPF_LUMINANCE
+        {
+            if (pf.rgbBitCount == 8)
+            {
+                if (pf.rBitMask == 0xFFu && pf.gBitMask == 0 && pf.bBitMask == 0 && pf.aBitMask == 0) { format = Format::R8_UNorm; linear = false; }
+                else if (pf.rBitMask == 0xFFu && pf.gBitMask == 0 && pf.bBitMask == 0 && pf.aBitMask == 0xFF00u) { format = Format::R8G8_UNorm; linear = false; }
+            }
+            else if (pf.rgbBitCount == 16)
+            {
+                if (pf.rBitMask == 0xFFFFu && pf.gBitMask == 0 && pf.bBitMask == 0 && pf.aBitMask == 0) format = Format::R16_UNorm;
+                else if (pf.rBitMask == 0xFFu && pf.gBitMask == 0 && pf.bBitMask == 0 && pf.aBitMask == 0xFF00u) { format = Format::R8G8_UNorm; linear = false; }
+            }
+        }
+        if (format == Format::Unknown) return false;     // "Unsupported DDS format"
+        if ((format == Format::BC1 || format == Format::BC4 || format == Format::BC5) && ((header.width | header.height) & 3u))
+        {
+            mError = std::string("block-compressed DDS whose size is not a multiple of 4 (the reference reads out of bounds there): '") + path + "'";
+            return false;
+        }
+        if (!Init(header.width, header.height, format, 0, linear)) return false;
+        if (fread(mData.data(), DataSize(), 1, file) != 1) return false;
         return true;
     }
 

@@ -2,6 +2,7 @@
 preprocessing) flattens a scene to EXACTLY the arrays the reference's own loader + Scene::BuildBVH produce (the
 golden .rtb files were dumped from the reference's Scene object by oracle/rtref.cpp)."""
 import ctypes as C
+import json
 import os
 
 import numpy as np
@@ -110,9 +111,11 @@ def test_loader_error_paths(built, tmp_path):
         load('{"textures": [{"name": "t", "type": "bitmap", "path": "nope.bmp"}]}')
     with pytest.raises(capi.RtbError, match="needs 'textureA'"):
         load('{"textures": [{"name": "m", "type": "mix", "textureA": "nope.bmp", "textureB": "nope.bmp", "weight": "nope.bmp"}]}')
-    (tmp_path / "x.dds").write_bytes(b"DDS " + bytes(124))
-    with pytest.raises(capi.RtbError, match="DDS bitmaps are not supported"):
-        load('{"materials": [{"name": "a", "baseColorTexture": "x.dds"}]}')
+    (tmp_path / "x.dds").write_bytes(b"DDS " + bytes(124))          # a DDS layout the reference does not know either: no texture, no error
+    load('{"materials": [{"name": "a", "baseColorTexture": "x.dds"}]}')
+    _dds(str(tmp_path / "odd.dds"), 6, 6, (0x4, _fourcc(b"DXT1"), 0, 0, 0, 0, 0), bytes(32))
+    with pytest.raises(capi.RtbError, match="not a multiple of 4"):
+        load('{"materials": [{"name": "a", "baseColorTexture": "odd.dds"}]}')
     (tmp_path / "x.exr").write_bytes(bytes([0x76, 0x2F, 0x31, 0x01]) + bytes(60))
     with pytest.raises(capi.RtbError, match="OpenEXR bitmaps are not supported"):
         load('{"lights": [{"type": "background", "color": [1.0, 1.0, 1.0], "texture": "x.exr"}]}')
@@ -166,3 +169,92 @@ def test_reference_test_scenes_load_like_the_reference(built, tmp_path):
 
 # scenes of Data/TestScenes this build refuses on purpose (DESIGN.md "Limits"): CSG shapes
 UNSUPPORTED_REFERENCE_SCENES = {"shapes_test"}
+
+
+def _dds(path, width, height, pf, payload, dx10=None):
+    """Minimal DDS container (Core/Utils/BitmapDDS.cpp:228-290): 128-byte header (+ DX10 extension) + top mip level."""
+    import struct
+    flags, fourcc, bits, r, g, b, a = pf
+    hdr = struct.pack("<II", 0x20534444, 124) + struct.pack("<IIIIII", 0x1007, height, width, 0, 0, 1) + bytes(44)
+    hdr += struct.pack("<IIIIIIII", 32, flags, fourcc, bits, r, g, b, a) + struct.pack("<IIII", 0x1000, 0, 0, 0) + struct.pack("<I", 0)
+    assert len(hdr) == 128
+    if dx10 is not None:
+        hdr += struct.pack("<IIIII", dx10, 3, 0, 1, 0)
+    with open(path, "wb") as f:
+        f.write(hdr + payload)
+
+
+def _fourcc(s):
+    return s[0] | (s[1] << 8) | (s[2] << 16) | (s[3] << 24)
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="needs oracle/_ref/exact (authoring container)")
+def test_dds_bitmaps_decode_like_the_reference(built, tmp_path):
+    """Every DDS layout the reference's loader accepts (BitmapDDS.cpp:304-523), with random payloads: the product's
+    decode must equal the reference's Bitmap::GetPixel for every texel (rtref dumps exactly that), bit for bit."""
+    rng = np.random.default_rng(11)
+    w, h = 12, 8
+    RGB, FOURCC, LUM = 0x40, 0x4, 0x20000
+    DX10 = _fourcc(b"DX10")
+
+    def rnd(nbytes):
+        return rng.integers(0, 256, nbytes, dtype=np.uint8).tobytes()
+
+    def floats(n):
+        return (rng.normal(size=n) * 3.0).astype(np.float32).tobytes()
+
+    cases = {
+        "bgra8": ((RGB, 0, 32, 0x00FF0000, 0x0000FF00, 0x000000FF, 0xFF000000), rnd(w * h * 4), None),
+        "rgba8": ((RGB, 0, 32, 0x000000FF, 0x0000FF00, 0x00FF0000, 0xFF000000), rnd(w * h * 4), None),
+        "r32f_mask": ((RGB, 0, 32, 0xFFFFFFFF, 0, 0, 0), floats(w * h), None),
+        "rg16": ((RGB, 0, 32, 0xFFFF, 0xFFFF0000, 0, 0), rnd(w * h * 4), None),
+        "b5g6r5": ((RGB, 0, 16, 0xF800, 0x07E0, 0x001F, 0), rnd(w * h * 2), None),
+        "r16f": ((FOURCC, 111, 0, 0, 0, 0, 0), rnd(w * h * 2), None),
+        "rg16f": ((FOURCC, 112, 0, 0, 0, 0, 0), rnd(w * h * 4), None),
+        "rgba16f": ((FOURCC, 113, 0, 0, 0, 0, 0), rnd(w * h * 8), None),
+        "r32f": ((FOURCC, 114, 0, 0, 0, 0, 0), floats(w * h), None),
+        "rg32f": ((FOURCC, 115, 0, 0, 0, 0, 0), floats(w * h * 2), None),
+        "rgba32f": ((FOURCC, 116, 0, 0, 0, 0, 0), floats(w * h * 4), None),
+        "rgba16": ((FOURCC, 36, 0, 0, 0, 0, 0), rnd(w * h * 8), None),
+        "dxt1": ((FOURCC, _fourcc(b"DXT1"), 0, 0, 0, 0, 0), rnd(w * h // 2), None),
+        "ati1": ((FOURCC, _fourcc(b"ATI1"), 0, 0, 0, 0, 0), rnd(w * h // 2), None),
+        "bc5u": ((FOURCC, _fourcc(b"BC5U"), 0, 0, 0, 0, 0), rnd(w * h), None),
+        "l8": ((LUM, 0, 8, 0xFF, 0, 0, 0), rnd(w * h), None),
+        "l16": ((LUM, 0, 16, 0xFFFF, 0, 0, 0), rnd(w * h * 2), None),
+        "a8l8": ((LUM, 0, 16, 0xFF, 0, 0, 0xFF00), rnd(w * h * 2), None),
+        "dx10_rgb32f": ((FOURCC, DX10, 0, 0, 0, 0, 0), floats(w * h * 3), 6),
+        "dx10_r9g9b9e5": ((FOURCC, DX10, 0, 0, 0, 0, 0), rnd(w * h * 4), 67),
+        "dx10_r11g11b10": ((FOURCC, DX10, 0, 0, 0, 0, 0), rnd(w * h * 4), 26),
+        "dx10_bgra8_srgb": ((FOURCC, DX10, 0, 0, 0, 0, 0), rnd(w * h * 4), 91),
+        "dx10_bgra8": ((FOURCC, DX10, 0, 0, 0, 0, 0), rnd(w * h * 4), 87),
+        "dx10_rg8": ((FOURCC, DX10, 0, 0, 0, 0, 0), rnd(w * h * 2), 49),
+        "dx10_r8": ((FOURCC, DX10, 0, 0, 0, 0, 0), rnd(w * h), 61),
+        "dx10_r16": ((FOURCC, DX10, 0, 0, 0, 0, 0), rnd(w * h * 2), 56),
+        "dx10_bc1_srgb": ((FOURCC, DX10, 0, 0, 0, 0, 0), rnd(w * h // 2), 72),
+        "dx10_bc4": ((FOURCC, DX10, 0, 0, 0, 0, 0), rnd(w * h // 2), 80),
+        "dx10_bc5": ((FOURCC, DX10, 0, 0, 0, 0, 0), rnd(w * h), 83),
+        "dx10_rgba16f": ((FOURCC, DX10, 0, 0, 0, 0, 0), rnd(w * h * 8), 10),
+    }
+    os.makedirs(tmp_path / "TEX")
+    mats, objs = [], []
+    for i, (name, (pf, payload, dx10)) in enumerate(sorted(cases.items())):
+        _dds(str(tmp_path / "TEX" / (name + ".dds")), w, h, pf, payload, dx10)
+        mats.append({"name": name, "bsdf": "diffuse", "baseColor": [1.0, 1.0, 1.0], "baseColorTexture": "TEX/%s.dds" % name})
+        objs.append({"type": "sphere", "radius": 0.4, "transform": {"translation": [float(i), 0.0, 0.0]}, "material": name})
+    scene = {"materials": mats, "objects": objs, "lights": [{"type": "background", "color": [1.0, 1.0, 1.0]}]}
+    sj = str(tmp_path / "dds.json")
+    json.dump(scene, open(sj, "w"))
+    ref_out, my_out = str(tmp_path / "ref.rtb"), str(tmp_path / "mine.rtb")
+    util.run_rtref(["flat", "--scene", sj, "--data", str(tmp_path) + "/", "--out", ref_out])
+    host_api.Scene(sj, str(tmp_path) + "/").save_flat(my_out, 64, 64)
+    mine, ref = capi.SceneFile(my_out), capi.SceneFile(ref_out)
+    assert len(ref.textures) == len(cases), "the reference did not load every DDS case"
+    assert len(mine.textures) == len(ref.textures)
+    assert mine.material_textures.tobytes() == ref.material_textures.tobytes()
+    names = sorted(cases)
+    for i, (a, b) in enumerate(zip(mine.textures, ref.textures)):
+        # (materials are flattened in object order = sorted case order)
+        assert (a["width"], a["height"]) == (b["width"], b["height"]) == (w, h)
+        same = a["texels"].view(np.uint32) == b["texels"].view(np.uint32)
+        assert same.all(), "%s: %d of %d texel floats differ from Bitmap::GetPixel (first: %s vs %s)" % (
+            names[i], int((~same).sum()), same.size, a["texels"].view(np.float32)[np.argmax(~same)], b["texels"].view(np.float32)[np.argmax(~same)])

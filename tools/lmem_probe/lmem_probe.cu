@@ -45,6 +45,16 @@ __global__ void __launch_bounds__(128, 6) kernelB(const unsigned* __restrict__ t
 
 __global__ void kernelC(unsigned* out, unsigned n) { const unsigned i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = i; }
 
+// short kernel that needs dynamic shared memory (forces a different L1 / shared carve-out than kernels A and B)
+__global__ void __launch_bounds__(128, 8) kernelD(unsigned* out, unsigned n)
+{
+    extern __shared__ unsigned sm[];
+    sm[threadIdx.x] = threadIdx.x * 3u;
+    __syncthreads();
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sm[(threadIdx.x * 7u) & 127u];
+}
+
 int main(int argc, char** argv)
 {
     const unsigned n = 1u << 22;
@@ -53,7 +63,8 @@ int main(int argc, char** argv)
     cudaMemset(table, 1, n * 4); cudaMemset(errors, 0, 16);
     cudaStream_t s[4];
     for (auto& x : s) cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking);
-    for (int mode = 0; mode < 2; ++mode)       // 0: kernel A alone (serial), 1: A on two streams + B and C on two more
+    cudaFuncSetAttribute(kernelD, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int mode = 0; mode < 4; ++mode)       // 0: kernel A alone (serial), 1: A on two streams + B and C on two more, 2: + hundreds of short launches, 3: + short launches with 16 KB of dynamic shared memory
     {
         cudaMemset(errors, 0, 16);
         cudaDeviceSynchronize();
@@ -65,12 +76,17 @@ int main(int argc, char** argv)
                 kernelA<<<148 * 32, 128, 0, s[1]>>>(table, n, 1500, errors, sink);
                 kernelB<<<148 * 24, 128, 0, s[2]>>>(table, n, 1200, errors, out);
                 for (int k = 0; k < 8; ++k) kernelC<<<n / 256, 256, 0, s[3]>>>(out + n / 2, n / 2);
+                if (mode >= 2) for (int k = 0; k < 200; ++k)
+                {
+                    if (mode == 3) kernelD<<<148 * 4, 128, 16 * 1024, s[3]>>>(out + n / 2, n / 2);
+                    else kernelC<<<148 * 4, 256, 0, s[3]>>>(out + n / 2, n / 2);
+                }
             }
         }
         cudaDeviceSynchronize();
         unsigned long long e[2] = {0, 0};
         cudaMemcpy(e, errors, 16, cudaMemcpyDeviceToHost);
-        printf("mode %d (%s): %llu (kernel A, 64-word stack) + %llu (kernel B, 48-word stack) corrupted local-memory words, last error: %s\n", mode, mode ? "overlapping streams" : "one stream", e[0], e[1], cudaGetErrorString(cudaGetLastError()));
+        printf("mode %d (%s): %llu (kernel A, 64-word stack) + %llu (kernel B, 48-word stack) corrupted local-memory words, last error: %s\n", mode, mode == 0 ? "one stream" : mode == 1 ? "overlapping streams" : mode == 2 ? "overlap + 200 short launches per repetition" : "overlap + 200 short launches with 16 KB dynamic shared memory", e[0], e[1], cudaGetErrorString(cudaGetLastError()));
     }
     return 0;
 }

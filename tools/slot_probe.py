@@ -5,9 +5,9 @@ from tests import util
 import json
 scene = sys.argv[1] if len(sys.argv) > 1 else "mesh_small"
 RID, DBG = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (1, 0)
-meta = json.load(open(util.golden("%s_mis.json" % scene)))
+meta = json.load(open(util.golden("%s_mis.json" % scene))) if not scene.endswith(".rtb") else {"dims": 128}
 w, h = 256, 256
-sf = capi.SceneFile(util.golden(scene + ".rtb"))
+sf = capi.SceneFile(scene if scene.endswith(".rtb") else util.golden(scene + ".rtb"))
 rng = np.random.default_rng(5)
 seeds = rng.integers(0, 2**32, (8, meta["dims"]), dtype=np.uint32); offs = (rng.normal(size=(8, 2)) * 0.5).astype(np.float32)
 def run(single):
