@@ -12,6 +12,8 @@
 //   LightSceneObject::Traverse / Traverse_Shadow, AreaLight::TestRayHit    SceneObject_Light.cpp:27-53, AreaLight.cpp:30-41
 #pragma once
 
+#include <type_traits>
+
 #include "rtb_scene.h"
 
 namespace rtb {
@@ -30,6 +32,11 @@ struct TraceCounters { uint32_t boxTests, triTests; };
 #define RTB_STACK_SIZE 64
 #ifndef RTB_LDG256
 #define RTB_LDG256 1
+#endif
+// RTB_SPLIT_FINITE = 1 compiles the node loops twice (finite-slab rays / generic test) instead of choosing the box test
+// per iteration.  Measured on the bench (ms per 8 passes): k_traverse 20.4 -> 21.6, k_shadow 32.6 -> 36.2.  Kept off.
+#ifndef RTB_SPLIT_FINITE
+#define RTB_SPLIT_FINITE 0
 #endif
 #ifndef RTB_SHADOW_NEAR_FIRST
 #define RTB_SHADOW_NEAR_FIRST 1
@@ -363,45 +370,54 @@ RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, Tr
 
     for (;;)
     {
-        // inner nodes: GenericTraverse, Traversal_Single.h:36-91
-        while (have && RTB_NUM_LEAVES(curInfo) == 0)
+        // inner nodes: GenericTraverse, Traversal_Single.h:36-91 (kMode as in ShadowWalk::node_phase)
+        auto innerNodes = [&](auto modeTag)
         {
-            DNode a, b;
-            load_node_pair(nodes, curChild, a, b);
-            float distanceA, distanceB;
-            bool hitA, hitB;
-            if (finite)
+            constexpr int kMode = decltype(modeTag)::value;
+            while (have && RTB_NUM_LEAVES(curInfo) == 0)
             {
-                hitA = box_ray_finite(ray, a.minx, a.miny, a.minz, a.maxx, a.maxy, a.maxz, distanceA);
-                hitB = box_ray_finite(ray, b.minx, b.miny, b.minz, b.maxx, b.maxy, b.maxz, distanceB);
+                DNode a, b;
+                load_node_pair(nodes, curChild, a, b);
+                float distanceA, distanceB;
+                bool hitA, hitB;
+                if (kMode == 1 || (kMode == 0 && finite))
+                {
+                    hitA = box_ray_finite(ray, a.minx, a.miny, a.minz, a.maxx, a.maxy, a.maxz, distanceA);
+                    hitB = box_ray_finite(ray, b.minx, b.miny, b.minz, b.maxx, b.maxy, b.maxz, distanceB);
+                }
+                else
+                {
+                    hitA = box_ray(ray, a.minx, a.miny, a.minz, a.maxx, a.maxy, a.maxz, distanceA);
+                    hitB = box_ray(ray, b.minx, b.miny, b.minz, b.maxx, b.maxy, b.maxz, distanceB);
+                }
+                hitA &= (distanceA < hit.distance);
+                hitB &= (distanceB < hit.distance);
+                if (kCount) cnt->boxTests += 2;
+                if (hitA && hitB)
+                {
+                    // visit the nearer child first, push the other (Traversal_Single.h:65-75)
+                    const bool bFirst = distanceB < distanceA;
+                    stk_put(stack, sstack, stackSize++, bFirst ? a.childIndex : b.childIndex, bFirst ? a.leafInfo : b.leafInfo);
+                    curChild = bFirst ? b.childIndex : a.childIndex;
+                    curInfo = bFirst ? b.leafInfo : a.leafInfo;
+                }
+                else if (hitA) { curChild = a.childIndex; curInfo = a.leafInfo; }
+                else if (hitB) { curChild = b.childIndex; curInfo = b.leafInfo; }
+                else if (stackSize > popFloor)
+                {
+                    // both children missed: take the next pending node of this mesh right here, so that the lane stays in
+                    // the inner loop with the rest of its warp instead of idling until every lane has left it
+                    const StackEntry e = stk_get(stack, sstack, --stackSize);
+                    curChild = e.a; curInfo = e.b;
+                }
+                else have = false;
             }
-            else
-            {
-                hitA = box_ray(ray, a.minx, a.miny, a.minz, a.maxx, a.maxy, a.maxz, distanceA);
-                hitB = box_ray(ray, b.minx, b.miny, b.minz, b.maxx, b.maxy, b.maxz, distanceB);
-            }
-            hitA &= (distanceA < hit.distance);
-            hitB &= (distanceB < hit.distance);
-            if (kCount) cnt->boxTests += 2;
-            if (hitA && hitB)
-            {
-                // visit the nearer child first, push the other (Traversal_Single.h:65-75)
-                const bool bFirst = distanceB < distanceA;
-                stk_put(stack, sstack, stackSize++, bFirst ? a.childIndex : b.childIndex, bFirst ? a.leafInfo : b.leafInfo);
-                curChild = bFirst ? b.childIndex : a.childIndex;
-                curInfo = bFirst ? b.leafInfo : a.leafInfo;
-            }
-            else if (hitA) { curChild = a.childIndex; curInfo = a.leafInfo; }
-            else if (hitB) { curChild = b.childIndex; curInfo = b.leafInfo; }
-            else if (stackSize > popFloor)
-            {
-                // both children missed: take the next pending node of this mesh right here, so that the lane stays in
-                // the inner loop with the rest of its warp instead of idling until every lane has left it
-                const StackEntry e = stk_get(stack, sstack, --stackSize);
-                curChild = e.a; curInfo = e.b;
-            }
-            else have = false;
-        }
+        };
+#if RTB_SPLIT_FINITE
+        if (finite) innerNodes(std::integral_constant<int, 1>()); else innerNodes(std::integral_constant<int, 2>());
+#else
+        innerNodes(std::integral_constant<int, 0>());
+#endif
 
         if (have)
         {
@@ -528,11 +544,12 @@ struct ShadowWalk
         return occluded;
     }
 
-    template <bool kCount>
-    RTB_HD int step(const SceneView& S, uint32_t* stack, TraceCounters* cnt, SharedStack sstack = 0)
+    // the node phase of step().  kMode 0: the finite / generic box test is chosen per iteration; 1 / 2: the phase is
+    // compiled once for rays with finite slabs and once for the generic (SSE NaN semantics) test and step() picks one
+    // when it enters the phase - `finite` only changes when a mesh is entered or left, never inside the phase.
+    template <bool kCount, int kMode>
+    RTB_HD void node_phase(uint32_t* stack, TraceCounters* cnt, SharedStack sstack)
     {
-        // (the form of this loop matters: `while (have) { if (leaf) break; ... }` WITHOUT the postponing measured 35 %
-        //  slower than `while (have && !leaf)`: ptxas places the reconvergence points differently)
         while (have)
         {
             if (RTB_NUM_LEAVES(curInfo) != 0)
@@ -550,7 +567,7 @@ struct ShadowWalk
             load_node_pair(nodes, curChild, a, b);
             float distanceA, distanceB;
             bool hitA, hitB;
-            if (finite)
+            if (kMode == 1 || (kMode == 0 && finite))
             {
                 hitA = box_ray_finite(ray, a.minx, a.miny, a.minz, a.maxx, a.maxy, a.maxz, distanceA);
                 hitB = box_ray_finite(ray, b.minx, b.miny, b.minz, b.maxx, b.maxy, b.maxz, distanceB);
@@ -580,6 +597,20 @@ struct ShadowWalk
             }
             else have = false;
         }
+
+    }
+
+    template <bool kCount>
+    RTB_HD int step(const SceneView& S, uint32_t* stack, TraceCounters* cnt, SharedStack sstack = 0)
+    {
+        // (the form of the node loop matters: `while (have) { if (leaf) break; ... }` WITHOUT the postponing measured 35 %
+        //  slower than `while (have && !leaf)`: ptxas places the reconvergence points differently)
+#if RTB_SPLIT_FINITE
+        if (finite) node_phase<kCount, 1>(stack, cnt, sstack);
+        else node_phase<kCount, 2>(stack, cnt, sstack);
+#else
+        node_phase<kCount, 0>(stack, cnt, sstack);
+#endif
 
         if (pendInfo != 0)
         {
