@@ -322,7 +322,8 @@ typedef struct RtbCreateDesc
     uint32_t numShards;
     uint32_t shardIndex;
     uint32_t tileSize;        /* 0 -> 32 (RenderingParams::tileSize, Context.h:76) */
-    void*    stream;          /* cudaStream_t to launch on, NULL -> a stream owned by the context */
+    void*    stream;          /* cudaStream_t to launch on; NULL -> the library's stream for that device, shared by every
+                                 context created this way, so that their kernels never overlap each other */
 } RtbCreateDesc;
 
 typedef struct RtbContext RtbContext;

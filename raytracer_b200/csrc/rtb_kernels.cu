@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <new>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -115,6 +116,27 @@ __device__ __forceinline__ void load_ray(const PathBuf& b, uint32_t i, Ray& r)
     r.originDivDir = v3(d.y, d.z, d.w);
 }
 
+// world-ray sources for the traversal kernels (rtb_trace.h RayInRegisters): load the ray again from its queue
+struct RayInPathQueue
+{
+    const PathBuf& b;
+    uint32_t i;
+    __device__ __forceinline__ Ray load() const { Ray r; load_ray(b, i, r); return r; }
+};
+
+struct RayInShadowQueue
+{
+    const Wavefront& W;
+    uint32_t j;
+    __device__ __forceinline__ Ray load() const
+    {
+        const float4 a = W.sr0[j], b = W.sr1[j], c = W.sr2[j], d = W.sr3[j];
+        Ray r;
+        r.origin = v3(a.x, a.y, a.z); r.dir = v3(b.x, b.y, b.z); r.invDir = v3(c.x, c.y, c.z); r.originDivDir = v3(d.x, d.y, d.z);
+        return r;
+    }
+};
+
 __device__ __forceinline__ void load_path(const PathBuf& b, uint32_t i, const Wavefront& W, uint32_t width, uint32_t numSeedDims, PathState& ps)
 {
     load_ray(b, i, ps.ray);
@@ -178,11 +200,10 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_traverse(const __gr
 #endif
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
     {
-        Ray ray;
-        load_ray(in, i, ray);
+        const RayInPathQueue src = { in, i };
         Hit hit;
         hit.objectId = RTB_INVALID_OBJECT; hit.subObjectId = 0; hit.distance = INFINITY; hit.u = 0.0f; hit.v = 0.0f;
-        scene_traverse<kCount>(S, ray, hit, &cnt, sstack);
+        scene_traverse_from<kCount>(S, src, hit, &cnt, sstack);
         W.hit0[i] = make_uint4(hit.objectId, hit.subObjectId, __float_as_uint(hit.distance), __float_as_uint(hit.u));
         W.hit1[i] = hit.v;
     }
@@ -343,7 +364,8 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
                     const float4 a = W.sr0[j], b = W.sr1[j], c = W.sr2[j], d = W.sr3[j];
                     Ray ray;
                     ray.origin = v3(a.x, a.y, a.z); ray.dir = v3(b.x, b.y, b.z); ray.invDir = v3(c.x, c.y, c.z); ray.originDivDir = v3(d.x, d.y, d.z);
-                    if (walk.begin(S, stack, ray, a.w, sstack)) active = true;
+                    const RayInRegisters src = { ray };
+                    if (walk.begin(S, stack, src, a.w, sstack)) active = true;
                     else visibleLocal++;
                 }
             }
@@ -355,7 +377,8 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
         }
         if (active)
         {
-            const int r = walk.step<kCount>(S, stack, &cnt, sstack);
+            const RayInShadowQueue src = { W, j };
+            const int r = walk.step<kCount>(S, stack, src, &cnt, sstack);
             if (r != ShadowWalk::kContinue)
             {
                 active = false;
@@ -370,10 +393,8 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
     {
         const uint32_t j = W.rayList[k];
-        const float4 a = W.sr0[j], b = W.sr1[j], c = W.sr2[j], d = W.sr3[j];
-        Ray ray;
-        ray.origin = v3(a.x, a.y, a.z); ray.dir = v3(b.x, b.y, b.z); ray.invDir = v3(c.x, c.y, c.z); ray.originDivDir = v3(d.x, d.y, d.z);
-        const bool occluded = scene_traverse_shadow<kCount>(S, ray, a.w, &cnt, sstack);
+        const RayInShadowQueue src = { W, j };
+        const bool occluded = scene_traverse_shadow_from<kCount>(S, src, W.sr0[j].w, &cnt, sstack);
         if (occluded)
         {
             // SampleLight returns RayColor::Zero() for an occluded light (PathTracerMIS.cpp:92-96)
@@ -851,9 +872,20 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
     if (desc->stream) { c->stream = (cudaStream_t)desc->stream; c->ownStream = false; }
     else
     {
-        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-        if (e != cudaSuccess) { delete c; return fail(RTB_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
-        c->ownStream = true;
+        // contexts that do not bring their own stream share ONE stream per device: their kernels then never overlap each
+        // other.  Overlapping kernels are not safe for this code as long as it has register spills;
+        // a caller who passes streams of its own takes over that responsibility.
+        static cudaStream_t sharedStreams[64] = {};
+        static std::mutex sharedStreamsLock;
+        std::lock_guard<std::mutex> guard(sharedStreamsLock);
+        cudaStream_t& shared = sharedStreams[desc->deviceId & 63];
+        if (!shared)
+        {
+            e = cudaStreamCreateWithFlags(&shared, cudaStreamNonBlocking);
+            if (e != cudaSuccess) { shared = nullptr; delete c; return fail(RTB_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
+        }
+        c->stream = shared;
+        c->ownStream = false;
     }
     cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, c->device);
     if (const char* t = getenv("RTB_SIMPLE_BLOCKS")) c->simpleBlocksPerSM = atoi(t) > 0 ? atoi(t) : 128;

@@ -347,8 +347,29 @@ RTB_HD void node_header(const DNode* nodes, uint32_t index, uint32_t& childIndex
 // ray.originDivDir exactly as stored: the integrator offsets ray.origin AFTER constructing the ray without
 // refreshing originDivDir (PathTracerMIS.cpp:392-393) and that stale value is part of the reference's behaviour;
 // Traverse_Object rebuilds the ray in object space.
+// Where the world-space ray comes from.  The walk needs it three times: at the start, for every object it enters
+// (Traverse_Object transforms the WORLD ray) and when it returns from a mesh to the top level.  Holding it in
+// registers across a whole mesh traversal makes ptxas spill it to local memory at 64 registers per thread; the
+// kernels therefore hand over a source that simply loads it again from the ray queue (three L1-resident 16-byte
+// loads per object, against a dozen local stores and loads), and the traversal kernels end up free of long-lived spills.
+struct RayInRegisters
+{
+    const Ray& r;
+    RTB_HD Ray load() const { return r; }
+};
+
+template <bool kCount, typename WorldRay>
+RTB_HD void scene_traverse_from(const SceneView& S, const WorldRay& worldRaySource, Hit& hit, TraceCounters* cnt, SharedStack sstack = 0);
+
 template <bool kCount>
 RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, TraceCounters* cnt, SharedStack sstack = 0)
+{
+    const RayInRegisters src = { worldRay };
+    scene_traverse_from<kCount>(S, src, hit, cnt, sstack);
+}
+
+template <bool kCount, typename WorldRay>
+RTB_HD void scene_traverse_from(const SceneView& S, const WorldRay& worldRaySource, Hit& hit, TraceCounters* cnt, SharedStack sstack)
 {
     if (S.numObjects == 0) return;
     uint32_t stack[RTB_LOCAL_STACK_SIZE];
@@ -358,8 +379,8 @@ RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, Tr
     bool inBlas = false;
     const DNode* nodes = S.tlas;
     const DTri* tris = nullptr;
-    Ray ray = worldRay;
-    const bool worldFinite = ray_is_finite(worldRay);
+    Ray ray = worldRaySource.load();
+    const bool worldFinite = ray_is_finite(ray);
     bool finite = worldFinite;
     uint32_t objectID = 0;
     bool have = false;                 // {curChild, curInfo} describe a node still to be visited
@@ -457,7 +478,7 @@ RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, Tr
         if (inBlas && stackSize == blasBase)
         {
             // mesh finished: back to the top level with the world-space ray
-            inBlas = false; popFloor = 0xFFFFFFFFu; nodes = S.tlas; ray = worldRay; finite = worldFinite;
+            inBlas = false; popFloor = 0xFFFFFFFFu; nodes = S.tlas; ray = worldRaySource.load(); finite = worldFinite;
         }
         if (stackSize == 0) break;
         const StackEntry e = stk_get(stack, sstack, --stackSize);
@@ -466,7 +487,7 @@ RTB_HD void scene_traverse(const SceneView& S, const Ray& worldRay, Hit& hit, Tr
             // Scene::Traverse_Object, Scene.cpp:128-145
             objectID = e.a;
             const DObjectTrace& obj = S.objTrace[objectID];
-            const Ray localRay = transform_ray_unsafe(obj.invTransform, worldRay);
+            const Ray localRay = transform_ray_unsafe(obj.invTransform, worldRaySource.load());
             if (obj.kind == RTB_OBJECT_SHAPE && obj.shapeType == RTB_SHAPE_MESH)
             {
                 const DMesh& mesh = S.meshes[obj.meshIndex];
@@ -507,19 +528,20 @@ struct ShadowWalk
     bool inBlas, finite, worldFinite, have;
     const DNode* nodes;
     const DTri* tris;
-    Ray ray, world;
+    Ray ray;
     float maxDistance;
     uint32_t curChild, curInfo;
     uint32_t pendChild, pendInfo;          // a mesh leaf whose triangle tests are postponed
 
     // false: nothing to traverse (the ray is unoccluded)
-    RTB_HD bool begin(const SceneView& S, uint32_t* stack, const Ray& worldRay, float tMax, SharedStack sstack = 0)
+    template <typename WorldRay>
+    RTB_HD bool begin(const SceneView& S, uint32_t* stack, const WorldRay& worldRaySource, float tMax, SharedStack sstack = 0)
     {
         if (S.numObjects == 0) return false;
         stackSize = 0; blasBase = 0; popFloor = 0xFFFFFFFFu; inBlas = false;
         nodes = S.tlas; tris = nullptr;
-        ray = worldRay; world = worldRay; maxDistance = tMax;
-        worldFinite = ray_is_finite(worldRay); finite = worldFinite;
+        ray = worldRaySource.load(); maxDistance = tMax;
+        worldFinite = ray_is_finite(ray); finite = worldFinite;
         have = false; curChild = 0; curInfo = 0; pendChild = 0; pendInfo = 0;
         if (S.numObjects == 1) { stk_put(stack, sstack, 0, 0u, RTB_ENTRY_OBJECT); stackSize = 1; }
         else if (S.numTlasNodes != 0) { node_header(S.tlas, 0, curChild, curInfo); have = true; }
@@ -600,8 +622,8 @@ struct ShadowWalk
 
     }
 
-    template <bool kCount>
-    RTB_HD int step(const SceneView& S, uint32_t* stack, TraceCounters* cnt, SharedStack sstack = 0)
+    template <bool kCount, typename WorldRay>
+    RTB_HD int step(const SceneView& S, uint32_t* stack, const WorldRay& worldRaySource, TraceCounters* cnt, SharedStack sstack = 0)
     {
         // (the form of the node loop matters: `while (have) { if (leaf) break; ... }` WITHOUT the postponing measured 35 %
         //  slower than `while (have && !leaf)`: ptxas places the reconvergence points differently)
@@ -633,7 +655,7 @@ struct ShadowWalk
 
         if (inBlas && stackSize == blasBase)
         {
-            inBlas = false; popFloor = 0xFFFFFFFFu; nodes = S.tlas; ray = world; finite = worldFinite;
+            inBlas = false; popFloor = 0xFFFFFFFFu; nodes = S.tlas; ray = worldRaySource.load(); finite = worldFinite;
         }
         if (stackSize == 0) return kVisible;
         const StackEntry e = stk_get(stack, sstack, --stackSize);
@@ -641,7 +663,7 @@ struct ShadowWalk
         {
             // Scene::Traverse_Object_Shadow, Scene.cpp:147-165
             const DObjectTrace& obj = S.objTrace[e.a];
-            const Ray localRay = transform_ray_unsafe(obj.invTransform, world);
+            const Ray localRay = transform_ray_unsafe(obj.invTransform, worldRaySource.load());
             if (obj.kind == RTB_OBJECT_SHAPE && obj.shapeType == RTB_SHAPE_MESH)
             {
                 const DMesh& mesh = S.meshes[obj.meshIndex];
@@ -665,17 +687,24 @@ struct ShadowWalk
     }
 };
 
-template <bool kCount>
-RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float maxDistance, TraceCounters* cnt, SharedStack sstack = 0)
+template <bool kCount, typename WorldRay>
+RTB_HD bool scene_traverse_shadow_from(const SceneView& S, const WorldRay& worldRaySource, float maxDistance, TraceCounters* cnt, SharedStack sstack = 0)
 {
     ShadowWalk w;
     uint32_t stack[RTB_LOCAL_STACK_SIZE];
-    if (!w.begin(S, stack, worldRay, maxDistance, sstack)) return false;
+    if (!w.begin(S, stack, worldRaySource, maxDistance, sstack)) return false;
     for (;;)
     {
-        const int r = w.step<kCount>(S, stack, cnt, sstack);
+        const int r = w.step<kCount>(S, stack, worldRaySource, cnt, sstack);
         if (r != ShadowWalk::kContinue) return r == ShadowWalk::kOccluded;
     }
+}
+
+template <bool kCount>
+RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float maxDistance, TraceCounters* cnt, SharedStack sstack = 0)
+{
+    const RayInRegisters src = { worldRay };
+    return scene_traverse_shadow_from<kCount>(S, src, maxDistance, cnt, sstack);
 }
 
 } // namespace rtb
