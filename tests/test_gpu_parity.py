@@ -229,6 +229,26 @@ def test_live_oracle_larger_ragged_sizes(ctx, tmp_path, scene, w, h, passes):
     assert (c["numRays"], c["numShadowRays"], c["numShadowRaysHit"]) == (meta["numRays"], meta["numShadowRays"], meta["numShadowRaysHit"])
 
 
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="prebuilt oracle/_ref/exact did not travel to this box")
+@pytest.mark.parametrize("mode", range(13))
+def test_every_debug_mode_against_the_live_reference(ctx, tmp_path, mode):
+    """DebugRenderer::RenderPixel, all 13 DebugRenderingMode values (camera light, triangle id, depth, position, frame
+    vectors, texture coordinates, material parameters), on the textured scene: bit-exact against the reference run here."""
+    scn = os.path.join(util.GOLDEN, "scenes")
+    w, h = 56, 40
+    sump, passp = str(tmp_path / "o.sum"), str(tmp_path / "o.passes")
+    util.run_rtref(["render", "--scene", os.path.join(scn, "textures.json"), "--data", scn + "/", "--width", w, "--height", h, "--passes", 2, "--dims", 64,
+                    "--renderer", "Debug", "--debug-mode", mode, "--dump-sum", sump, "--dump-passes", passp])
+    sf = capi.SceneFile(util.golden("textures.rtb"))
+    ps = capi.PassScript(passp)
+    ctx.upload_scene(sf)
+    ctx.resize(w, h)
+    cam = capi.camera_for(sf, w, h)
+    for p in range(2):
+        ctx.render_pass(ctx.make_pass(cam, ps.seeds[p], ps.offsets[p], p, renderer=capi.RTB_RENDERER_DEBUG, debug_mode=mode))
+    util.assert_bit_identical(ctx.read_sum(), util.load_sum(sump, w, h), "debug mode %d" % mode)
+
+
 def test_gathered_shards_unshard_to_the_full_frame(ctx):
     """What bench.py does at N > 1, emulated on one GPU: per-shard compact films concatenated (the all-gather result)
     and scattered back to raster order by rtb_unshard_film; also checks the layout against raytracer_b200.sharding."""

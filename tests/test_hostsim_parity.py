@@ -86,6 +86,23 @@ def test_hostsim_primary_rays(hostsim, tmp_path, scene):
         util.assert_bit_identical(got[f][:, :3], want[f][:, :3], f)
 
 
+DEBUG_MODES = {0: "CameraLight", 1: "TriangleID", 2: "Depth", 3: "Position", 4: "Normals", 5: "Tangents", 6: "Bitangents",
+               7: "TexCoords", 8: "BaseColor", 9: "Emission", 10: "Roughness", 11: "Metalness", 12: "IoR"}
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
+@pytest.mark.parametrize("mode", sorted(DEBUG_MODES))
+def test_hostsim_every_debug_mode_against_the_live_reference(hostsim, tmp_path, mode):
+    """DebugRenderer::RenderPixel (DebugRenderer.cpp:26-178), all 13 DebugRenderingMode values, on the textured scene."""
+    scn = os.path.join(util.GOLDEN, "scenes")
+    sump, passp = str(tmp_path / "o.sum"), str(tmp_path / "o.passes")
+    util.run_rtref(["render", "--scene", os.path.join(scn, "textures.json"), "--data", scn + "/", "--width", 48, "--height", 40, "--passes", 2, "--dims", 64,
+                    "--renderer", "Debug", "--debug-mode", mode, "--dump-sum", sump, "--dump-passes", passp])
+    out = str(tmp_path / "mine.sum")
+    subprocess.run([HOSTSIM, "render", util.golden("textures.rtb"), passp, "48", "40", out, "2", "8", str(mode), "1", hostsim], stdout=subprocess.PIPE, check=True)
+    util.assert_bit_identical(util.load_sum(out, 48, 40), util.load_sum(sump, 48, 40), "debug mode %s" % DEBUG_MODES[mode])
+
+
 @pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
 def test_golden_fixtures_reproduce_from_the_reference(tmp_path):
     """The committed fixtures are what the real reference produces today (pins the oracle: fixed seed, exact math)."""
