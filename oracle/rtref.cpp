@@ -404,6 +404,9 @@ bool LoadSceneFile(const Args& a, Scene& scene, Camera& camera, uint32 w, uint32
     if (!helpers::LoadScene(a.Str("scene"), scene, camera)) { fprintf(stderr, "rtref: scene load failed\n"); return false; }
     if (!scene.BuildBVH()) return false;
     camera.SetPerspective((float)w / (float)h, camera.mFieldOfView);
+    // camera state the JSON schema cannot express (Camera.h:43, 99): set on the reference's Camera object directly
+    if (a.Has("bokeh")) camera.mDOF.bokehShape = (BokehShape)a.Int("bokeh", 0);
+    if (a.Has("barrel")) camera.barrelDistortionConstFactor = (float)a.Dbl("barrel", 0.01);
     return true;
 }
 

@@ -249,6 +249,29 @@ def test_every_debug_mode_against_the_live_reference(ctx, tmp_path, mode):
     util.assert_bit_identical(ctx.read_sum(), util.load_sum(sump, w, h), "debug mode %d" % mode)
 
 
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="prebuilt oracle/_ref/exact did not travel to this box")
+@pytest.mark.parametrize("bokeh,barrel", [(1, 0.01), (2, 0.01), (0, 0.08)])
+def test_bokeh_shapes_and_barrel_distortion_against_the_live_reference(ctx, tmp_path, bokeh, barrel):
+    """Camera::GenerateRay with hexagon / square bokeh and another barrel distortion factor (camera state the JSON schema
+    cannot express; the harness sets it on the reference's Camera object, RtbCamera carries it to the device)."""
+    scn = os.path.join(util.GOLDEN, "scenes")
+    w, h, passes = 72, 56, 3
+    common = ["--scene", os.path.join(scn, "cornell_dof.json"), "--data", scn + "/", "--width", w, "--height", h, "--bokeh", bokeh, "--barrel", barrel]
+    sump, passp, flatp = str(tmp_path / "o.sum"), str(tmp_path / "o.passes"), str(tmp_path / "o.rtb")
+    meta = util.run_rtref(["render", *common, "--passes", passes, "--dims", 128, "--depth", 8, "--strategy", "all", "--dump-sum", sump, "--dump-passes", passp])
+    util.run_rtref(["flat", *common, "--out", flatp])
+    sf = capi.SceneFile(flatp)
+    ps = capi.PassScript(passp)
+    ctx.upload_scene(sf)
+    ctx.resize(w, h)
+    cam = capi.camera_for(sf, w, h)
+    assert cam.bokehShape == bokeh
+    for p in range(passes):
+        ctx.render_pass(ctx.make_pass(cam, ps.seeds[p], ps.offsets[p], p))
+    util.assert_bit_identical(ctx.read_sum(), util.load_sum(sump, w, h), "bokeh %d barrel %g" % (bokeh, barrel))
+    assert ctx.counters()["numRays"] == meta["numRays"]
+
+
 def test_gathered_shards_unshard_to_the_full_frame(ctx):
     """What bench.py does at N > 1, emulated on one GPU: per-shard compact films concatenated (the all-gather result)
     and scattered back to raster order by rtb_unshard_film; also checks the layout against raytracer_b200.sharding."""

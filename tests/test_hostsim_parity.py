@@ -104,6 +104,23 @@ def test_hostsim_every_debug_mode_against_the_live_reference(hostsim, tmp_path, 
 
 
 @pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
+@pytest.mark.parametrize("bokeh,barrel", [(1, 0.01), (2, 0.01), (0, 0.08), (1, 0.0)])
+def test_hostsim_bokeh_shapes_and_barrel_distortion(hostsim, tmp_path, bokeh, barrel):
+    """Camera::GenerateRay with the hexagon / square bokeh (Camera.cpp:195-217, SamplingHelpers.cpp:40-57) and other
+    barrel distortion factors (Camera.cpp:87-92): camera state the JSON schema cannot express, set on the reference's
+    Camera object by the harness and carried to the device in RtbCamera."""
+    scn = os.path.join(util.GOLDEN, "scenes")
+    common = ["--scene", os.path.join(scn, "cornell_dof.json"), "--data", scn + "/", "--width", 48, "--height", 48, "--bokeh", bokeh, "--barrel", barrel]
+    sump, passp, flatp = str(tmp_path / "o.sum"), str(tmp_path / "o.passes"), str(tmp_path / "o.rtb")
+    meta = util.run_rtref(["render", *common, "--passes", 3, "--dims", 128, "--depth", 8, "--strategy", "all", "--dump-sum", sump, "--dump-passes", passp])
+    util.run_rtref(["flat", *common, "--out", flatp])
+    out = str(tmp_path / "mine.sum")
+    r = subprocess.run([HOSTSIM, "render", flatp, passp, "48", "48", out, "1", "8", "0", "1", hostsim], stdout=subprocess.PIPE, text=True, check=True)
+    util.assert_bit_identical(util.load_sum(out, 48, 48), util.load_sum(sump, 48, 48), "bokeh %d barrel %g" % (bokeh, barrel))
+    assert json.loads(r.stdout.strip().splitlines()[-1])["numRays"] == meta["numRays"]
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
 def test_golden_fixtures_reproduce_from_the_reference(tmp_path):
     """The committed fixtures are what the real reference produces today (pins the oracle: fixed seed, exact math)."""
     scn = os.path.join(util.GOLDEN, "scenes")
