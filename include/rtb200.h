@@ -383,6 +383,8 @@ int  rtb_trace_batch(RtbContext* ctx, const RtbRay* rays, uint64_t n, RtbHit* hi
 /* device-resident variant used by bench.py for the kernel-only number; returns kernel milliseconds */
 int  rtb_trace_batch_device(RtbContext* ctx, const void* raysDevice, uint64_t n, void* hitsDevice, uint32_t mode, float* outMs);
 
+/* rgba[4i..] = ITexture::Evaluate of textures[textureIndex] at (uv[2i], uv[2i+1])   (test hook, Core/Textures/Texture.h:24) */
+int  rtb_texture_batch(RtbContext* ctx, uint32_t textureIndex, const float* uv, uint64_t n, float* rgba);
 /* out[i*numDims + d] = d-th GenericSampler::GetInt() of pixel (xy[2i], xy[2i+1]) */
 int  rtb_sample_batch(RtbContext* ctx, const RtbPassDesc* pass, const uint32_t* xy, uint64_t n, uint32_t numDims, uint32_t* out);
 /* rays[y*width + x] = primary ray of film pixel (x, y) for this pass */

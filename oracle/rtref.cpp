@@ -11,6 +11,7 @@
 //   trace    Scene::Traverse / Scene::Traverse_Shadow over a file of RtbRay -> file of RtbHit
 //   sampler  GenericSampler streams for given pixels of given passes
 //   primary  Camera::GenerateRay for every pixel exactly as Viewport::RenderTile calls it
+//   texeval  ITexture::Evaluate of every texture of the scene at a list of (u, v)
 #include "PCH.h"
 #include "Demo.h"
 #include "SceneLoader.h"
@@ -593,6 +594,36 @@ struct PassScript
     }
 };
 
+int CmdTexEval(const Args& a)
+{
+    // ITexture::Evaluate for every texture of the flattened scene (in RtbSceneDesc::textures order) at a list of (u, v)
+    Scene scene; Camera camera;
+    if (!LoadSceneFile(a, scene, camera, 64, 64)) return 1;
+    Flat flat; flat.Build(scene);
+    std::vector<const ITexture*> byIndex(flat.textures.size(), nullptr);
+    for (const auto& it : flat.textureIds) byIndex[it.second] = it.first;
+    std::vector<float> uv;
+    {
+        FILE* f = fopen(a.Str("uv").c_str(), "rb");
+        if (!f) Die("cannot open uv file");
+        float pair[2];
+        while (fread(pair, 4, 2, f) == 2) { uv.push_back(pair[0]); uv.push_back(pair[1]); }
+        fclose(f);
+    }
+    FILE* of = fopen(a.Str("out").c_str(), "wb");
+    if (!of) Die("cannot open output");
+    for (const ITexture* t : byIndex)
+        for (size_t i = 0; i + 1 < uv.size(); i += 2)
+        {
+            float c[4];
+            ToF4(t->Evaluate(Vector4(uv[i], uv[i + 1], 0.0f, 0.0f)), c);
+            WriteBytes(of, c, 16);
+        }
+    fclose(of);
+    printf("{\"textures\": %zu, \"points\": %zu}\n", byIndex.size(), uv.size() / 2);
+    return 0;
+}
+
 int CmdSampler(const Args& a)
 {
     // streams for a grid of pixels: out[pass][pixel][dim]
@@ -675,6 +706,7 @@ int main(int argc, char** argv)
     if (a.cmd == "flat") return CmdFlat(a);
     if (a.cmd == "trace") return CmdTrace(a);
     if (a.cmd == "sampler") return CmdSampler(a);
+    if (a.cmd == "texeval") return CmdTexEval(a);
     if (a.cmd == "primary") return CmdPrimary(a);
     fprintf(stderr, "usage: rtref render|flat|trace|sampler|primary --scene X.json [options]\n");
     return 2;

@@ -125,7 +125,7 @@ HIT_DTYPE = np.dtype([("objectId", np.uint32), ("subObjectId", np.uint32), ("dis
 EXPORTED_SYMBOLS = [
     "rtb_last_error", "rtb_api_version", "rtb_create", "rtb_destroy", "rtb_upload_scene", "rtb_set_blue_noise",
     "rtb_resize", "rtb_reset", "rtb_render_pass", "rtb_render_passes", "rtb_synchronize", "rtb_join", "rtb_read_sum", "rtb_film_device_buffer", "rtb_film_snapshots",
-    "rtb_unshard_film", "rtb_read_sum_async", "rtb_unshard_film_async", "rtb_host_alloc", "rtb_host_free", "rtb_get_counters", "rtb_trace_batch", "rtb_trace_batch_device", "rtb_sample_batch",
+    "rtb_unshard_film", "rtb_read_sum_async", "rtb_unshard_film_async", "rtb_host_alloc", "rtb_host_free", "rtb_get_counters", "rtb_trace_batch", "rtb_trace_batch_device", "rtb_texture_batch", "rtb_sample_batch",
     "rtb_primary_rays", "rtb_set_profiling", "rtb_get_pass_timings",
 ]
 
@@ -172,6 +172,7 @@ def load_library(path=None):
     lib.rtb_get_counters.argtypes = [C.c_void_p, C.POINTER(RtbCounters)]
     lib.rtb_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
     lib.rtb_trace_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
+    lib.rtb_texture_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
     lib.rtb_sample_batch.argtypes = [C.c_void_p, C.POINTER(RtbPassDesc), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
     lib.rtb_primary_rays.argtypes = [C.c_void_p, C.POINTER(RtbPassDesc), C.c_void_p]
     lib.rtb_set_profiling.argtypes = [C.c_void_p, C.c_int]
@@ -391,6 +392,13 @@ class Context:
         if out is None:
             out = np.empty((self.height, self.width, 3), dtype=np.float32)
         _check(self.lib, self.lib.rtb_read_sum(self.h, out.ctypes.data, which))
+        return out
+
+    def texture_batch(self, texture_index, uv):
+        """rtb_texture_batch: ITexture::Evaluate at uv (n, 2) float32 -> (n, 4) float32."""
+        uv = np.ascontiguousarray(uv, dtype=np.float32)
+        out = np.empty((len(uv), 4), dtype=np.float32)
+        _check(self.lib, self.lib.rtb_texture_batch(self.h, texture_index, uv.ctypes.data, len(uv), out.ctypes.data))
         return out
 
     def film_snapshots(self, max_passes):

@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ Wavefro
 // `snapshots` (optional): the film as of EVERY pass of the batch, snapshots[b * snapshotStride + 3 * slot], so that a
 // caller who wants each pass' frame (progressive display, the end-to-end bench) does not have to render pass by pass.
 __global__ void __launch_bounds__(256) k_film(const __grid_constant__ Wavefront W, float* __restrict__ sum, float* __restrict__ sum2,
-                                              float* __restrict__ snapshots, size_t snapshotStride)
+                                              float* __restrict__ snapshots, size_t snapshotStride, uint32_t snapshotCount)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < W.numPixels; i += stride)
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(256) k_film(const __grid_constant__ Wavefront 
             const float4 c = W.passColor[(size_t)b * W.numPixels + i];
             s0 = s0 + c.x; s1 = s1 + c.y; s2 = s2 + c.z;
             if (((W.firstPassIndex + b) & 1u) == 0u) { t0 = t0 + c.x; t1 = t1 + c.y; t2 = t2 + c.z; }
-            if (snapshots)
+            if (b < snapshotCount)
             {
                 float* q = snapshots + (size_t)b * snapshotStride + (size_t)i * 3;
                 q[0] = s0; q[1] = s1; q[2] = s2;
@@ -603,6 +603,14 @@ __global__ void __launch_bounds__(128) k_trace_batch(const __grid_constant__ Sce
         atomicAdd(mode == RTB_TRACE_SHADOW ? &tot->numShadowBoxTests : &tot->numBoxTests, (unsigned long long)cnt.boxTests);
         atomicAdd(mode == RTB_TRACE_SHADOW ? &tot->numShadowTriTests : &tot->numTriTests, (unsigned long long)cnt.triTests);
     }
+}
+
+__global__ void k_texture_batch(const __grid_constant__ SceneView S, uint32_t textureIndex, const float* __restrict__ uv, unsigned long long n, float4* __restrict__ out)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const V4 c = texture_evaluate(S, textureIndex, uv[2 * i], uv[2 * i + 1]);
+    out[i] = make_float4(c.x, c.y, c.z, c.w);
 }
 
 __global__ void k_sample_batch(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const uint32_t* __restrict__ xy, unsigned long long n, uint32_t numDims, uint32_t* __restrict__ out)
@@ -1251,9 +1259,15 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
     // stream when this wavefront was submitted (e.g. a snapshot or an all-gather still reading the film)
     if (c->lastFilm) RTB_CUDA(cudaStreamWaitEvent(s, c->lastFilm, 0));
     RTB_CUDA(cudaStreamWaitEvent(s, c->mainMark, 0));
+    // film snapshots (rtb_film_snapshots): the passes of this call whose index is below the buffer's capacity
     float* snap = nullptr;
-    if (c->snapshots.ptr && snapshotIndex + batch <= c->snapshotCapacity) snap = c->snapshots.ptr + (size_t)snapshotIndex * c->shardSlots * 3;
-    k_film<<<blocks256, 256, 0, s>>>(W, c->sum.ptr, c->sum2.ptr, snap, (size_t)c->shardSlots * 3);
+    uint32_t snapCount = 0;
+    if (c->snapshots.ptr && snapshotIndex < c->snapshotCapacity)
+    {
+        snap = c->snapshots.ptr + (size_t)snapshotIndex * c->shardSlots * 3;
+        snapCount = std::min(batch, c->snapshotCapacity - snapshotIndex);
+    }
+    k_film<<<blocks256, 256, 0, s>>>(W, c->sum.ptr, c->sum2.ptr, snap, (size_t)c->shardSlots * 3, snapCount);
     RTB_CUDA(cudaEventRecord(slot.filmDone, s));
     c->lastFilm = slot.filmDone;
     if (prof) marks.push_back(next_event(c, ev, s));
@@ -1560,6 +1574,26 @@ int rtb_trace_batch(RtbContext* c, const RtbRay* rays, uint64_t n, RtbHit* hits,
     }
     cudaFree(dRays); cudaFree(dHits);
     return rc;
+}
+
+int rtb_texture_batch(RtbContext* c, uint32_t textureIndex, const float* uv, uint64_t n, float* rgba)
+{
+    if (!c || (n && (!uv || !rgba))) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    if (!c->hasScene) return fail(RTB_ERR_NO_SCENE, "rtb_texture_batch: no scene uploaded");
+    if (textureIndex >= c->textures.count) return fail(RTB_ERR_INVALID_ARG, "texture index %u out of range (%zu textures)", textureIndex, c->textures.count);
+    RTB_CUDA(cudaSetDevice(c->device));
+    if (n == 0) return RTB_OK;
+    float* dUv = nullptr; float4* dOut = nullptr;
+    RTB_CUDA(cudaMalloc(&dUv, n * 2 * sizeof(float)));
+    cudaError_t e = cudaMalloc(&dOut, n * sizeof(float4));
+    if (e != cudaSuccess) { cudaFree(dUv); return fail(RTB_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    cudaMemcpyAsync(dUv, uv, n * 2 * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+    k_texture_batch<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->view, textureIndex, dUv, n, dOut);
+    e = cudaMemcpyAsync(rgba, dOut, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dUv); cudaFree(dOut);
+    if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "texture batch failed: %s", cudaGetErrorString(e));
+    return RTB_OK;
 }
 
 int rtb_sample_batch(RtbContext* c, const RtbPassDesc* pass, const uint32_t* xy, uint64_t n, uint32_t numDims, uint32_t* out)

@@ -145,6 +145,17 @@ def main():
             rtref("trace", "--scene", sj, "--data", scn + "/", "--rays", os.path.join(out, name + ".rays"), "--out", os.path.join(out, name + ".hits"))
             rtref("trace", "--scene", sj, "--data", scn + "/", "--rays", os.path.join(out, name + ".rays"), "--shadow", 1,
                   "--tmax", os.path.join(out, name + ".tmax"), "--out", os.path.join(out, name + ".shadow_hits"))
+        if name == "textures":
+            # ITexture::Evaluate at adversarial coordinates: negative, exactly on texel / tile boundaries, just below 1,
+            # huge (floor loses the fraction), tiny, and a dense random cloud
+            f = np.float32
+            special = [0.0, -0.0, 1.0, -1.0, 0.5, -0.5, 0.25, 0.75, 1.0 - 2.0 ** -24, 2.0 ** -24, -2.0 ** -24, 2.0 ** -149, 1.0 / 16.0, 1.0 / 8.0, 7.0 / 8.0,
+                       15.0 / 16.0, 3.0, -3.0, 17.5, -17.5, 1024.25, -1024.25, 8388608.0, 16777216.0, -16777217.0, 1.0e9, -1.0e9, 0.333333343, 12.0 / 13.0, 4.0 / 5.0]
+            grid = np.array([(a, b) for a in special for b in special[::3]], dtype=f)
+            cloud = np.concatenate([rng.uniform(-2.0, 3.0, size=(600, 2)), rng.normal(size=(200, 2)) * 40.0]).astype(f)
+            uv = np.concatenate([grid, cloud]).astype(f)
+            uv.tofile(os.path.join(out, "textures.uv"))
+            rtref("texeval", "--scene", sj, "--data", scn + "/", "--uv", os.path.join(out, "textures.uv"), "--out", os.path.join(out, "textures.texeval"))
         if name in ("cornell", "mesh_small"):
             rtref("primary", *common, "--passes", os.path.join(out, name + ".passes"), "--pass", 1, "--out", os.path.join(out, name + ".primary"))
     make_reference_scenes(out)

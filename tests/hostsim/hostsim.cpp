@@ -186,6 +186,28 @@ static int cmdRender(int argc, char** argv)
     return 0;
 }
 
+static int cmdTexEval(int argc, char** argv)
+{
+    if (argc < 5) die("usage: texeval scene uvfile out");
+    World world; world.load(argv[2]);
+    std::vector<float> uv;
+    FILE* f = fopen(argv[3], "rb");
+    if (!f) die("cannot open uv file");
+    float pair[2];
+    while (fread(pair, 4, 2, f) == 2) { uv.push_back(pair[0]); uv.push_back(pair[1]); }
+    fclose(f);
+    FILE* of = fopen(argv[4], "wb");
+    for (size_t t = 0; t < world.hs.textures.size(); ++t)
+        for (size_t i = 0; i + 1 < uv.size(); i += 2)
+        {
+            const V4 c = texture_evaluate(world.S, (uint32_t)t, uv[i], uv[i + 1]);
+            const float o[4] = { c.x, c.y, c.z, c.w };
+            fwrite(o, 4, 4, of);
+        }
+    fclose(of);
+    return 0;
+}
+
 static int cmdTrace(int argc, char** argv)
 {
     if (argc < 5) die("usage: trace scene rays out [tmax]");
@@ -302,6 +324,7 @@ int main(int argc, char** argv)
     const std::string cmd = argv[1];
     if (cmd == "render") return cmdRender(argc, argv);
     if (cmd == "trace") return cmdTrace(argc, argv);
+    if (cmd == "texeval") return cmdTexEval(argc, argv);
     if (cmd == "sampler") return cmdSampler(argc, argv);
     if (cmd == "primary") return cmdPrimary(argc, argv);
     die("unknown command");

@@ -68,6 +68,18 @@ def test_hostsim_trace_batch(hostsim, tmp_path, scene):
     assert (got["occluded"] == want["occluded"]).all()
 
 
+def test_hostsim_texture_evaluation(hostsim, tmp_path):
+    """ITexture::Evaluate of all 12 textures of the textured scene at 1 100 adversarial coordinates (negative, exactly on
+    texel / tile boundaries, huge, tiny): the device header against the reference's own Evaluate (textures.texeval)."""
+    out = str(tmp_path / "t.f32")
+    subprocess.run([HOSTSIM, "texeval", util.golden("textures.rtb"), util.golden("textures.uv"), out], check=True)
+    got = np.fromfile(out, dtype=np.uint32)
+    want = np.fromfile(util.golden("textures.texeval"), dtype=np.uint32)
+    assert got.shape == want.shape
+    bad = np.argwhere(got != want)
+    assert len(bad) == 0, "%d of %d floats differ, first at texture %d point %d" % (len(bad), got.size, bad[0][0] // (4 * 1100), (bad[0][0] // 4) % 1100)
+
+
 @pytest.mark.parametrize("blue", [True, False])
 def test_hostsim_sampler(hostsim, tmp_path, blue):
     out = str(tmp_path / "s.u32")
