@@ -9,6 +9,7 @@
  *   primary   Camera::GenerateRay for every pixel         (<scene>.primary)
  *   trace     Scene::Traverse / Traverse_Shadow           (<scene>.hits / .shadow_hits)
  *   debug     DebugRenderer TriangleID / Depth sum buffer (<scene>_dbgtri.sum / _dbgdepth.sum)
+ *   texeval   ITexture::Evaluate (bitmap / checkerboard / noise / mix) at a list of coordinates (textures.texeval)
  * The full integrator (BSDFs, lights, MIS) is NOT restated here: for it the oracle is the reference itself
  * (oracle/_ref), whose sum buffers are the committed fixtures.
  *
@@ -41,7 +42,17 @@ typedef struct
     uint32_t numTlas, numObjects, numShapes, numMeshes, numMaterials, numLights, numGlobal;
     RtbBvhNode* tlas; RtbObject* objects; RtbShape* shapes; mesh_t* meshes; RtbMaterial* materials; RtbLight* lights; uint32_t* global;
     RtbCamera camera; float fov;
+    /* RTBS version 2: textures */
+    uint32_t numTextures;
+    struct tex_s* textures;
 } scene_t;
+
+typedef struct tex_s
+{
+    uint32_t type, width, height, octaves, a, b, w;
+    float colorA[4], colorB[4];
+    float* texels;       /* width * height * 4, what Bitmap::GetPixel returns */
+} tex_t;
 
 static void die(const char* m) { fprintf(stderr, "rt_restate: %s\n", m); exit(1); }
 
@@ -57,7 +68,9 @@ static void load_scene(const char* path, scene_t* s)
 {
     FILE* f = fopen(path, "rb");
     if (!f) die("cannot open scene");
-    if (read_u32(f) != 0x53425452u || read_u32(f) != 1) die("not an RTBS v1 file");
+    if (read_u32(f) != 0x53425452u) die("not an RTBS file");
+    const uint32_t version = read_u32(f);
+    if (version != 1 && version != 2) die("not an RTBS v1 / v2 file");
     s->numTlas = read_u32(f); s->tlas = read_block(f, (size_t)s->numTlas * sizeof(RtbBvhNode));
     s->numObjects = read_u32(f); s->objects = read_block(f, (size_t)s->numObjects * sizeof(RtbObject));
     s->numShapes = read_u32(f); s->shapes = read_block(f, (size_t)s->numShapes * sizeof(RtbShape));
@@ -75,6 +88,20 @@ static void load_scene(const char* path, scene_t* s)
     s->numLights = read_u32(f); s->lights = read_block(f, (size_t)s->numLights * sizeof(RtbLight));
     s->numGlobal = read_u32(f); s->global = read_block(f, (size_t)s->numGlobal * 4);
     if (fread(&s->camera, sizeof(RtbCamera), 1, f) != 1 || fread(&s->fov, 4, 1, f) != 1) die("truncated scene file");
+    s->numTextures = 0; s->textures = NULL;
+    if (version >= 2)
+    {
+        s->numTextures = read_u32(f);
+        s->textures = calloc(s->numTextures ? s->numTextures : 1, sizeof(tex_t));
+        for (uint32_t i = 0; i < s->numTextures; ++i)
+        {
+            tex_t* t = &s->textures[i];
+            t->type = read_u32(f); t->width = read_u32(f); t->height = read_u32(f); t->octaves = read_u32(f);
+            t->a = read_u32(f); t->b = read_u32(f); t->w = read_u32(f); (void)read_u32(f);
+            if (fread(t->colorA, 4, 4, f) != 4 || fread(t->colorB, 4, 4, f) != 4) die("truncated texture");
+            if (t->type == RTB_TEXTURE_BITMAP) t->texels = read_block(f, (size_t)t->width * t->height * 16);
+        }
+    }
     fclose(f);
 }
 
@@ -432,6 +459,97 @@ static ray_t ray_from_file(const RtbRay* r)
     return o;
 }
 
+/* ---- textures (Core/Textures/*.cpp) ---------------------------------------------------------------------------- */
+
+/* Vector4::Lerp = MulAndAdd(b - a, w, a), Vector4Impl.h:58-66 (a fused multiply-add in the reference build) */
+static float lerp_fma(float a, float b, float w) { return fmaf(b - a, w, a); }
+
+/* Ken Perlin's permutation, NoiseTexture.cpp:10-27 */
+static const uint8_t perm[256] = {
+    151,160,137,91,90,15,131,13,201,95,96,53,194,233,7,225,140,36,103,30,69,142,8,99,37,240,21,10,23,190,6,148,247,120,234,75,0,26,197,62,94,252,219,203,117,35,11,32,57,177,33,
+    88,237,149,56,87,174,20,125,136,171,168,68,175,74,165,71,134,139,48,27,166,77,146,158,231,83,111,229,122,60,211,133,230,220,105,92,41,55,46,245,40,244,
+    102,143,54,65,25,63,161,1,216,80,73,209,76,132,187,208,89,18,169,200,196,135,130,116,188,159,86,164,100,109,198,173,186,3,64,52,217,226,250,124,123,
+    5,202,38,147,118,126,255,82,85,212,207,206,59,227,47,16,58,17,182,189,28,42,223,183,170,213,119,248,152,2,44,154,163,70,221,153,101,155,167,43,172,9,
+    129,22,39,253,19,98,108,110,79,113,224,232,178,185,112,104,218,246,97,228,251,34,242,193,238,210,144,12,191,179,162,241,81,51,145,235,249,14,239,107,
+    49,192,214,31,181,199,106,157,184,84,204,176,115,121,50,45,127,4,150,254,138,236,205,93,222,114,67,29,24,72,243,141,128,195,78,66,215,61,156,180 };
+
+static int floor_to_int(float v) { const int i = (int)v; return v < (float)i ? i - 1 : i; }       /* FloorInt, Math.h:100-104 */
+
+static float corner(int gi, float x, float y)            /* one simplex corner: falloff^4 * gradient, NoiseTexture.cpp:34-40, 104-135 */
+{
+    float t = 0.5f - x * x - y * y;
+    if (t < 0.0f) return 0.0f;
+    const int h = gi & 0x3F;
+    const float u = h < 4 ? x : y, v = h < 4 ? y : x;
+    const float g = ((h & 1) ? -u : u) + ((h & 2) ? -2.0f * v : 2.0f * v);
+    t *= t;
+    return t * t * g;
+}
+
+static float simplex2(float x, float y)                   /* NoiseTexture::EvaluateInternal, NoiseTexture.cpp:59-139 */
+{
+    const float F2 = 0.366025403f, G2 = 0.211324865f;
+    const float s = (x + y) * F2;
+    const int i = floor_to_int(x + s), j = floor_to_int(y + s);
+    const float t = (float)(i + j) * G2;
+    const float x0 = x - ((float)i - t), y0 = y - ((float)j - t);
+    const int i1 = x0 > y0 ? 1 : 0, j1 = 1 - i1;
+    const float x1 = x0 - (float)i1 + G2, y1 = y0 - (float)j1 + G2;
+    const float x2 = x0 - 1.0f + 2.0f * G2, y2 = y0 - 1.0f + 2.0f * G2;
+    const int gi0 = perm[(uint8_t)(i + perm[(uint8_t)j])];
+    const int gi1 = perm[(uint8_t)(i + i1 + perm[(uint8_t)(j + j1)])];
+    const int gi2 = perm[(uint8_t)(i + 1 + perm[(uint8_t)(j + 1)])];
+    const float n0 = corner(gi0, x0, y0), n1 = corner(gi1, x1, y1), n2 = corner(gi2, x2, y2);
+    const float v = 0.5f + 22.615325f * (n0 + n1 + n2);
+    return v > 1.0f ? 1.0f : (v < 0.0f ? 0.0f : v);
+}
+
+static void tex_eval(const scene_t* s, uint32_t index, float u, float v, float out[4])
+{
+    const tex_t* t = &s->textures[index];
+    if (t->type == RTB_TEXTURE_MIX)
+    {
+        /* MixTexture::Evaluate, MixTexture.cpp:24-31 */
+        float a[4], b[4], w[4];
+        tex_eval(s, t->a, u, v, a); tex_eval(s, t->b, u, v, b); tex_eval(s, t->w, u, v, w);
+        for (int k = 0; k < 4; ++k) out[k] = lerp_fma(a[k], b[k], w[k]);
+        return;
+    }
+    if (t->type == RTB_TEXTURE_CHECKERBOARD)
+    {
+        /* CheckerboardTexture::Evaluate, CheckerboardTexture.cpp:32-41 */
+        const float fu = u - floorf(u), fv = v - floorf(v);
+        const float* c = ((fu > 0.5f) ^ (fv > 0.5f)) ? t->colorA : t->colorB;
+        memcpy(out, c, 16);
+        return;
+    }
+    if (t->type == RTB_TEXTURE_NOISE)
+    {
+        /* NoiseTexture::Evaluate, NoiseTexture.cpp:141-155 */
+        float value = 0.0f, vs = 0.5f, cs = 1.0f;
+        for (uint32_t o = 0; o < t->octaves; ++o) { value += vs * simplex2(u * cs, v * cs); vs *= 0.5f; cs *= 2.0f; }
+        for (int k = 0; k < 4; ++k) out[k] = lerp_fma(t->colorA[k], t->colorB[k], value);
+        return;
+    }
+    /* BitmapTexture::Evaluate, BitmapTexture.cpp:32-93: wrap, floor, smooth-step bilinear */
+    const int w = (int)t->width, h = (int)t->height;
+    const float su = (u - floorf(u)) * (float)w, sv = (v - floorf(v)) * (float)h;
+    const int iu = (int)lrintf(floorf(su)), iv = (int)lrintf(floorf(sv));        /* _mm_cvtps_epi32 of an integral value */
+    int x0 = iu, y0 = iv;
+    if (!(iu < w)) x0 -= w;
+    if (!(iv < h)) y0 -= h;
+    if (iu < 0) x0 += w;
+    if (iv < 0) y0 += h;
+    int x1 = x0 + 1, y1 = y0 + 1;
+    if (!(x1 < w)) x1 -= w;
+    if (!(y1 < h)) y1 -= h;
+    const float* c00 = t->texels + 4 * ((size_t)y0 * w + x0), *c10 = t->texels + 4 * ((size_t)y0 * w + x1);
+    const float* c01 = t->texels + 4 * ((size_t)y1 * w + x0), *c11 = t->texels + 4 * ((size_t)y1 * w + x1);
+    float wx = su - (float)iu, wy = sv - (float)iv;
+    wx = wx * wx * (3.0f - wx * 2.0f); wy = wy * wy * (3.0f - wy * 2.0f);              /* SmoothStep, Math.h:176-179 */
+    for (int k = 0; k < 4; ++k) out[k] = lerp_fma(lerp_fma(c00[k], c01[k], wy), lerp_fma(c10[k], c11[k], wy), wx);
+}
+
 int main(int argc, char** argv)
 {
     _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);
@@ -459,6 +577,21 @@ int main(int argc, char** argv)
             hits[i].objectId = h.object; hits[i].subObjectId = h.sub; hits[i].distance = h.t; hits[i].u = h.u; hits[i].v = h.v;
         }
         FILE* o = fopen(argv[4], "wb"); fwrite(hits, sizeof(RtbHit), n, o); fclose(o);
+        return 0;
+    }
+    if (!strcmp(argv[1], "texeval") && argc >= 5)
+    {
+        /* texeval <scene.rtb> <uv pairs f32> <out f32x4 per texture per point> */
+        scene_t s; load_scene(argv[2], &s);
+        FILE* f = fopen(argv[3], "rb"); if (!f) die("cannot open uv file");
+        fseek(f, 0, SEEK_END); const size_t n = (size_t)ftell(f) / 8; fseek(f, 0, SEEK_SET);
+        float* uv = malloc(n * 8 + 8);
+        if (fread(uv, 8, n, f) != n) die("read failed");
+        fclose(f);
+        FILE* o = fopen(argv[4], "wb");
+        for (uint32_t t = 0; t < s.numTextures; ++t)
+            for (size_t i = 0; i < n; ++i) { float c[4]; tex_eval(&s, t, uv[2 * i], uv[2 * i + 1], c); fwrite(c, 4, 4, o); }
+        fclose(o);
         return 0;
     }
     if (!strcmp(argv[1], "sampler") && argc >= 8)

@@ -78,3 +78,15 @@ def test_restate_debug_renderer_sum(restate, tmp_path, scene, renderer, mode):
                     str(meta["width"]), str(meta["height"]), out], check=True)
     want = util.load_sum(util.golden("%s_%s.sum" % (scene, renderer)), meta["width"], meta["height"])
     util.assert_bit_identical(util.load_sum(out, meta["width"], meta["height"]), want, "%s/%s" % (scene, renderer))
+
+
+def test_restate_texture_evaluation(restate, tmp_path):
+    """ITexture::Evaluate (bitmap with smooth-step bilinear filtering, checkerboard, simplex noise octaves, nested mix)
+    restated in plain C, at the 1 100 adversarial coordinates of textures.uv, against the reference's own Evaluate."""
+    out = str(tmp_path / "t.f32")
+    subprocess.run([RESTATE, "texeval", util.golden("textures.rtb"), util.golden("textures.uv"), out], check=True)
+    got = np.fromfile(out, dtype=np.uint32)
+    want = np.fromfile(util.golden("textures.texeval"), dtype=np.uint32)
+    assert got.shape == want.shape and got.size > 0
+    bad = np.argwhere(got != want)
+    assert len(bad) == 0, "%d of %d floats differ (first: texture %d, point %d)" % (len(bad), got.size, bad[0][0] // 4400, (bad[0][0] // 4) % 1100)
