@@ -22,6 +22,12 @@ __global__ void __launch_bounds__(128, 12) kernelA(const unsigned* __restrict__ 
         // a chain of dependent, divergent loads with enough temporaries to keep the register allocator busy
         const unsigned a = table[idx], b = table[(idx * 31u + a) % n], c = table[(idx * 17u + b + 3u) % n], d = table[(idx + c * 5u) % n];
         acc += (a ^ b) + (c ^ d) * 3u + ((a + c) ^ (b + d));
+#ifdef PROBE_IEEE_DIV
+        // with -prec-div=true -prec-sqrt=true these compile to fast paths + CALL.REL.NOINC slow-path subroutines, as in the renderer
+        const float q = (float)(a & 1023u) / (float)((b & 1023u) | 1u), r = sqrtf((float)(c & 4095u));
+        const double qd = sqrt((double)(d & 65535u) + 0.5);
+        acc += (unsigned)(q * 7.0f) + (unsigned)r + (unsigned)qd;
+#endif
         if ((h & 15u) == 0u) { acc ^= table[(acc + it) % n]; }               // divergent side path
     }
     unsigned bad = 0;
