@@ -756,6 +756,7 @@ struct RtbContext
     cudaEvent_t mainMark = nullptr;       // position of the main stream when a wavefront was enqueued
     bool slotsNeedMain = true;            // the main stream holds work the slots must wait for (reset / resize / upload)
     bool slotsOwnStreams = false;         // false: one slot on the main stream (default), true: RTB_SLOTS > 1
+    bool serializeSlots = false, profileDepths = false;      // development aids, read from the environment at rtb_create
     DevArray<float> snapshots;            // rtb_film_snapshots: snapshotCapacity x shardSlots x 3 floats
     uint32_t snapshotCapacity = 0;
     DevArray<Totals> totals;
@@ -917,6 +918,8 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
     int numSlots = 1;
     if (const char* t = getenv("RTB_SLOTS")) numSlots = atoi(t) >= 1 && atoi(t) <= 16 ? atoi(t) : numSlots;
     c->slotsOwnStreams = numSlots > 1;
+    c->serializeSlots = getenv("RTB_SERIALIZE_SLOTS") != nullptr;
+    c->profileDepths = getenv("RTB_PROFILE_DEPTHS") != nullptr;
     c->slots.resize(numSlots);
     e = c->totals.alloc(1);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->totals.ptr, 0, sizeof(Totals), c->stream);
@@ -1036,7 +1039,7 @@ int rtb_upload_scene(RtbContext* c, const RtbSceneDesc* scene)
     v.numLights = (uint32_t)hs.lights.size(); v.numGlobalLights = (uint32_t)hs.globalLights.size();
     c->numLights = v.numLights;
     c->stackBytes = RTB_SMEM_STACK ? (size_t)hs.stackEntries * RTB_STACK_THREADS * sizeof(uint32_t) : 0;
-    if (getenv("RTB_PROFILE_DEPTHS")) fprintf(stderr, "scene: top-level BVH depth %u (largest leaf %u), deepest mesh BVH %u -> %u stack entries, %zu B shared memory per CTA\n",
+    if (c->profileDepths) fprintf(stderr, "scene: top-level BVH depth %u (largest leaf %u), deepest mesh BVH %u -> %u stack entries, %zu B shared memory per CTA\n",
                                               hs.maxTlasDepth, hs.maxTlasLeaf, hs.maxBlasDepth, hs.stackEntries, c->stackBytes);
     c->hasScene = true;
     int rc = alloc_shadow(c);
@@ -1184,7 +1187,7 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
         c->slotsNeedMain = false;
     }
 
-    if (getenv("RTB_SERIALIZE_SLOTS") && c->lastFilm) RTB_CUDA(cudaStreamWaitEvent(s, c->lastFilm, 0));     // debugging aid: no overlap between wavefronts
+    if (c->serializeSlots && c->lastFilm) RTB_CUDA(cudaStreamWaitEvent(s, c->lastFilm, 0));     // debugging aid (RTB_SERIALIZE_SLOTS): no overlap between wavefronts
     // per-pass seed vectors + AA offsets of the batch (stream ordered: the slot's previous wavefront is done with them)
     const uint32_t dims = pass->numSeedDims;
     // one upload: [batch x dims seed integers][batch x 2 AA offsets]
@@ -1296,7 +1299,7 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
         RTB_CUDA(cudaMemcpy(&h, slot.ctl.ptr, sizeof(Control), cudaMemcpyDeviceToHost));
         for (uint32_t d = 0; d <= depthLimit; ++d) t.traverseRays += h.pathCount[d];
         for (uint32_t d = 0; d <= depthLimit; ++d) t.shadowRays += h.shadowRayCount[d];
-        if (getenv("RTB_PROFILE_DEPTHS"))      // development aid: per-depth breakdown of this wavefront
+        if (c->profileDepths)      // development aid (RTB_PROFILE_DEPTHS): per-depth breakdown of this wavefront
             for (uint32_t d = 0; d <= depthLimit; ++d)
                 fprintf(stderr, "depth %u: paths %u traverse %.3f ms, shade %.3f ms, shadow rays %u shadow+resolve %.3f ms\n", d, h.pathCount[d],
                         ms(1 + 3 * d, 2 + 3 * d), ms(2 + 3 * d, 3 + 3 * d), h.shadowRayCount[d], ms(3 + 3 * d, 4 + 3 * d));
