@@ -218,6 +218,11 @@ typedef struct RtbSceneDesc
     const RtbMaterialTextures* materialTextures;   /* numMaterials entries, or NULL */
     const uint32_t*            lightTextures;      /* numLights entries (BackgroundLight::mTexture, BackgroundLight.cpp:45-61;
                                                       RTB_NO_TEXTURE = none), or NULL */
+    /* texture-shaped bokeh (Camera::mDOF.bokehTexture, Camera.cpp:208-213): the importance map of the bokeh bitmap as
+     * BitmapTexture::MakeSamplable builds it (BitmapTexture.cpp:121-152) - the normalised cumulative distribution of
+     * Distribution::Initialize (Math/Distribution.cpp:27-84), bokehWidth * bokehHeight + 1 floats; NULL = none */
+    uint32_t bokehWidth, bokehHeight;
+    const float* bokehCdf;
 } RtbSceneDesc;
 
 /* ---- per-pass description ----------------------------------------------------------------------- */
@@ -237,7 +242,9 @@ typedef enum RtbDebugMode
     RTB_DEBUG_ROUGHNESS, RTB_DEBUG_METALNESS, RTB_DEBUG_IOR
 } RtbDebugMode;
 
-typedef enum RtbBokehShape { RTB_BOKEH_CIRCLE = 0, RTB_BOKEH_HEXAGON = 1, RTB_BOKEH_SQUARE = 2 } RtbBokehShape;
+/* BokehShape, Core/Scene/Camera.h:21-28 (same numeric values).  RTB_BOKEH_TEXTURE samples the lens point from
+ * RtbSceneDesc::bokehCdf; RTB_BOKEH_NGON is refused (not implemented in the reference either, Camera.cpp:205-207) */
+typedef enum RtbBokehShape { RTB_BOKEH_CIRCLE = 0, RTB_BOKEH_HEXAGON = 1, RTB_BOKEH_SQUARE = 2, RTB_BOKEH_NGON = 3, RTB_BOKEH_TEXTURE = 4 } RtbBokehShape;
 
 /* rt::Camera state consumed by Camera::GenerateRay (Camera.cpp:81-118) */
 typedef struct RtbCamera

@@ -38,6 +38,7 @@
 #include "../Core/Textures/NoiseTexture.h"
 #include "../Core/Textures/MixTexture.h"
 #include "../Core/Utils/Bitmap.h"
+#include "../Core/Math/Distribution.h"
 #include "../Core/Traversal/TraversalContext.h"
 #include "../Core/Math/SamplingHelpers.h"
 #include "../Core/Sampling/GenericSampler.h"
@@ -349,7 +350,10 @@ struct Flat
         FILE* f = fopen(path, "wb");
         if (!f) Die("cannot open output");
         WriteU32(f, 0x53425452u); // 'RTBS'
-        WriteU32(f, anyTexture ? 2 : 1);
+        {
+            const BitmapTexture* bk = dynamic_cast<const BitmapTexture*>(camera.mDOF.bokehTexture.get());
+            WriteU32(f, (anyTexture || (bk && bk->mImportanceMap)) ? 2 : 1);
+        }
         WriteU32(f, (uint32_t)tlas.size());      WriteBytes(f, tlas.data(), tlas.size() * sizeof(RtbBvhNode));
         WriteU32(f, (uint32_t)objects.size());   WriteBytes(f, objects.data(), objects.size() * sizeof(RtbObject));
         WriteU32(f, (uint32_t)shapes.size());    WriteBytes(f, shapes.data(), shapes.size() * sizeof(RtbShape));
@@ -383,7 +387,10 @@ struct Flat
         c.barrelDistortionVariableFactor = camera.barrelDistortionVariableFactor;
         WritePod(f, c);
         WritePod(f, camera.mFieldOfView);
-        if (anyTexture)
+        // texture-shaped bokeh: the importance map BitmapTexture::MakeSamplable built (its Distribution's cumulative table)
+        const BitmapTexture* bokeh = dynamic_cast<const BitmapTexture*>(camera.mDOF.bokehTexture.get());
+        const bool hasBokeh = bokeh && bokeh->mImportanceMap;
+        if (anyTexture || hasBokeh)
         {
             WriteU32(f, (uint32_t)textures.size());
             for (const Texture& t : textures)
@@ -394,6 +401,11 @@ struct Flat
             }
             WriteU32(f, (uint32_t)materialTextures.size()); WriteBytes(f, materialTextures.data(), materialTextures.size() * sizeof(RtbMaterialTextures));
             WriteU32(f, (uint32_t)lightTextures.size()); WriteBytes(f, lightTextures.data(), lightTextures.size() * 4);
+            if (hasBokeh)
+            {
+                WriteU32(f, bokeh->mBitmap->GetWidth()); WriteU32(f, bokeh->mBitmap->GetHeight());
+                WriteBytes(f, bokeh->mImportanceMap->mCDF, ((size_t)bokeh->mImportanceMap->mSize + 1) * 4);
+            }
         }
         fclose(f);
     }

@@ -81,7 +81,8 @@ class RtbSceneDesc(C.Structure):
                 ("numLights", C.c_uint32), ("lights", C.c_void_p),
                 ("numGlobalLights", C.c_uint32), ("globalLights", C.c_void_p),
                 ("numTextures", C.c_uint32), ("textures", C.c_void_p),
-                ("materialTextures", C.c_void_p), ("lightTextures", C.c_void_p)]
+                ("materialTextures", C.c_void_p), ("lightTextures", C.c_void_p),
+                ("bokehWidth", C.c_uint32), ("bokehHeight", C.c_uint32), ("bokehCdf", C.c_void_p)]
 
 
 class RtbCamera(C.Structure):
@@ -229,6 +230,7 @@ class SceneFile:
         self.num_triangles = sum(m["numTriangles"] for m in self.meshes)
         # version 2: textures
         self.textures, self.material_textures, self.light_textures = [], None, None
+        self.bokeh_size, self.bokeh_cdf = (0, 0), None
         if version >= 2:
             for _ in range(u32()):
                 h = arr(32).view(np.uint32)
@@ -244,6 +246,10 @@ class SceneFile:
             n = u32()
             if n:
                 self.light_textures = arr(n * 4)
+            if pos + 8 <= len(data):
+                bw, bh = u32(), u32()
+                if bw and bh:
+                    self.bokeh_size, self.bokeh_cdf = (bw, bh), arr((bw * bh + 1) * 4)
 
     def desc(self):
         self._mesh_structs = (RtbMesh * max(1, len(self.meshes)))()
@@ -272,6 +278,9 @@ class SceneFile:
         d.textures = C.addressof(self._texture_structs) if self.textures else None
         d.materialTextures = self.material_textures.ctypes.data if self.material_textures is not None else None
         d.lightTextures = self.light_textures.ctypes.data if self.light_textures is not None else None
+        bokeh = getattr(self, "bokeh_cdf", None)
+        if bokeh is not None:
+            d.bokehWidth, d.bokehHeight, d.bokehCdf = self.bokeh_size[0], self.bokeh_size[1], bokeh.ctypes.data
         return d
 
 

@@ -708,6 +708,8 @@ struct RtbContext
     DevArray<DTexture> textures;
     std::vector<DevArray<float>> texels;      // one per texture (empty for procedural ones)
     DevArray<RtbMaterialTextures> materialTextures;
+    DevArray<float> bokehCdf;                 // texture-shaped bokeh (RtbSceneDesc::bokehCdf)
+    uint32_t bokehWidth = 0, bokehHeight = 0;
     SceneView view;
     uint32_t numLights = 0;
     size_t stackBytes = 0;         // dynamic shared memory of the traversal kernels: the scene's worst-case stack x 128 threads x 4 B
@@ -781,7 +783,7 @@ static void free_scene(RtbContext* c)
     for (DeviceMesh& m : c->meshes) { m.nodes.release(); m.tris.release(); m.indices.release(); m.shading.release(); m.materialIds.release(); }
     c->meshes.clear();
     c->meshViews.release(); c->materials.release(); c->lights.release(); c->globalLights.release();
-    c->textures.release(); c->materialTextures.release();
+    c->textures.release(); c->materialTextures.release(); c->bokehCdf.release(); c->bokehWidth = c->bokehHeight = 0;
     for (DevArray<float>& t : c->texels) t.release();
     c->texels.clear();
     c->hasScene = false;
@@ -1028,6 +1030,8 @@ int rtb_upload_scene(RtbContext* c, const RtbSceneDesc* scene)
     }
     RTB_CUDA(c->textures.upload(hs.textures, s));
     RTB_CUDA(c->materialTextures.upload(hs.materialTextures, s));
+    RTB_CUDA(c->bokehCdf.upload(hs.bokehCdf, s));
+    c->bokehWidth = hs.bokehWidth; c->bokehHeight = hs.bokehHeight;
     RTB_CUDA(cudaStreamSynchronize(s));   // host vectors go out of scope
 
     SceneView& v = c->view;
@@ -1139,6 +1143,11 @@ static int fill_pass_params(RtbContext* c, const RtbPassDesc* pass, PassParams& 
     P.camLocalToWorld = load_m4(pass->camera.localToWorld);
     P.aspectRatio = pass->camera.aspectRatio; P.tanHalfFoV = pass->camera.tanHalfFoV;
     P.dofEnable = pass->camera.dofEnable; P.bokehShape = pass->camera.bokehShape;
+    if (pass->camera.bokehShape > RTB_BOKEH_TEXTURE) return fail(RTB_ERR_INVALID_ARG, "unknown bokeh shape %u", pass->camera.bokehShape);
+    if (pass->camera.dofEnable && pass->camera.bokehShape == RTB_BOKEH_NGON) return fail(RTB_ERR_UNSUPPORTED, "the n-gon bokeh is not implemented (neither in the reference: Camera.cpp:205-207)");
+    if (pass->camera.dofEnable && pass->camera.bokehShape == RTB_BOKEH_TEXTURE && !c->bokehCdf.ptr)
+        return fail(RTB_ERR_INVALID_ARG, "bokehShape = texture, but the scene carries no bokeh distribution (RtbSceneDesc::bokehCdf)");
+    P.bokehCdf = c->bokehCdf.ptr; P.bokehWidth = c->bokehWidth; P.bokehHeight = c->bokehHeight;
     P.aperture = pass->camera.aperture; P.focalPlaneDistance = pass->camera.focalPlaneDistance;
     P.barrelConst = pass->camera.barrelDistortionConstFactor; P.barrelVar = 0.0f;
     P.width = c->width; P.height = c->height;

@@ -18,6 +18,8 @@ struct PassParams
     uint32_t dofEnable, bokehShape;
     float    aperture, focalPlaneDistance;
     float    barrelConst, barrelVar;
+    const float* bokehCdf;                     // RTB_BOKEH_TEXTURE: cumulative distribution over the bokeh bitmap's texels
+    uint32_t bokehWidth, bokehHeight;
     // film
     uint32_t width, height;
     float    sampleOffsetX, sampleOffsetY;     // AA offset of pass slot 0 (used when sampleOffsets is null)
@@ -114,7 +116,23 @@ RTB_HD Ray generate_primary_ray(const PassParams& P, uint32_t x, uint32_t y, flo
         const float u0 = sampler_get_float(s, P, blueNoise);
         const float u1 = sampler_get_float(s, P, blueNoise);
         float bx, by;
-        if (P.bokehShape == RTB_BOKEH_HEXAGON) sample_hexagon(u0, u1, 0.0f, bx, by);
+        if (P.bokehShape == RTB_BOKEH_TEXTURE)
+        {
+            // Camera::GenerateBokeh, BokehShape::Texture (Camera.cpp:208-213) -> BitmapTexture::Sample (BitmapTexture.cpp:95-119):
+            // a texel drawn from the importance map with the FIRST sample component only (Distribution::SampleDiscrete,
+            // Distribution.cpp:86-110), its integer coordinates divided by the bitmap size, UnipolarToBipolar
+            uint32_t low = 0u, high = P.bokehWidth * P.bokehHeight;
+            while (low < high)
+            {
+                const uint32_t mid = (low + high) / 2u;
+                if (u0 >= P.bokehCdf[mid]) low = mid + 1u; else high = mid;
+            }
+            const uint32_t pixelIndex = low - 1u;
+            const uint32_t px = pixelIndex % P.bokehWidth, py = pixelIndex / P.bokehWidth;
+            bx = fma_(fdiv((float)px, (float)P.bokehWidth), 2.0f, -1.0f);
+            by = fma_(fdiv((float)py, (float)P.bokehHeight), 2.0f, -1.0f);
+        }
+        else if (P.bokehShape == RTB_BOKEH_HEXAGON) sample_hexagon(u0, u1, 0.0f, bx, by);
         else if (P.bokehShape == RTB_BOKEH_SQUARE) { bx = fma_(u0, 2.0f, -1.0f); by = fma_(u1, 2.0f, -1.0f); }
         else sample_circle(u0, u1, bx, by);
         bx = bx * P.aperture; by = by * P.aperture;

@@ -17,6 +17,7 @@
 //                        f32 texels[width*height*4] for bitmaps }
 //   u32 n (0 or numMaterials), RtbMaterialTextures[n]
 //   u32 n (0 or numLights), u32[n]      light textures
+//   optional: u32 bokehWidth, bokehHeight, f32[bokehWidth * bokehHeight + 1]   bokeh importance map (cumulative distribution)
 #pragma once
 
 #include <cstdio>
@@ -58,8 +59,10 @@ struct SceneFile
     std::vector<RtbTexture> textureViews;
     std::vector<RtbMaterialTextures> materialTextures;   // empty or one per material
     std::vector<uint32_t> lightTextures;                 // empty or one per light
+    uint32_t bokehWidth = 0, bokehHeight = 0;
+    std::vector<float> bokehCdf;                         // empty or bokehWidth * bokehHeight + 1 entries
 
-    bool HasTextures() const { return !textures.empty() || !materialTextures.empty() || !lightTextures.empty(); }
+    bool HasTextures() const { return !textures.empty() || !materialTextures.empty() || !lightTextures.empty() || !bokehCdf.empty(); }
 
     SceneFile() { memset(&camera, 0, sizeof(camera)); }
 
@@ -95,6 +98,8 @@ struct SceneFile
         d.numTextures = (uint32_t)textureViews.size();    d.textures = textureViews.empty() ? nullptr : textureViews.data();
         d.materialTextures = materialTextures.size() == materials.size() && !materials.empty() ? materialTextures.data() : nullptr;
         d.lightTextures = lightTextures.size() == lights.size() && !lights.empty() ? lightTextures.data() : nullptr;
+        d.bokehWidth = bokehWidth; d.bokehHeight = bokehHeight;
+        d.bokehCdf = bokehCdf.empty() ? nullptr : bokehCdf.data();
         return d;
     }
 
@@ -151,6 +156,13 @@ struct SceneFile
             }
             if (!ReadU32(f, n) || !ReadVec(f, materialTextures, n)) { err = "truncated (material textures)"; return false; }
             if (!ReadU32(f, n) || !ReadVec(f, lightTextures, n)) { err = "truncated (light textures)"; return false; }
+            bokehWidth = bokehHeight = 0; bokehCdf.clear();
+            uint32_t bw = 0, bh = 0;
+            if (ReadU32(f, bw) && ReadU32(f, bh) && bw && bh)
+            {
+                if (!ReadVec(f, bokehCdf, (size_t)bw * bh + 1)) { err = "truncated (bokeh distribution)"; return false; }
+                bokehWidth = bw; bokehHeight = bh;
+            }
         }
         return true;
     }
@@ -189,6 +201,7 @@ struct SceneFile
             }
             WriteU32(f, (uint32_t)materialTextures.size()); WriteVec(f, materialTextures);
             WriteU32(f, (uint32_t)lightTextures.size()); WriteVec(f, lightTextures);
+            if (!bokehCdf.empty()) { WriteU32(f, bokehWidth); WriteU32(f, bokehHeight); WriteVec(f, bokehCdf); }
         }
         fclose(f);
         return true;

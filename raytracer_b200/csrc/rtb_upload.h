@@ -33,6 +33,8 @@ struct HostScene
     std::vector<DTexture> textures;                      // texels pointers are patched after the device upload
     std::vector<const float*> texelSources;              // host texels of every bitmap texture (caller-owned), else null
     std::vector<RtbMaterialTextures> materialTextures;   // empty = no material has a texture
+    std::vector<float> bokehCdf;                         // texture-shaped bokeh: bokehWidth * bokehHeight + 1 entries, or empty
+    uint32_t bokehWidth = 0, bokehHeight = 0;
     bool hasLightTextures = false;
     uint32_t maxTlasDepth = 0, maxBlasDepth = 0, maxTlasLeaf = 0;
     uint32_t stackEntries = 0;      // worst-case occupancy of the traversal stack (rtb_trace.h)
@@ -140,6 +142,15 @@ inline bool build_host_scene(const RtbSceneDesc& d, HostScene& out, std::string&
             }
         }
         if (any) out.materialTextures.assign(d.materialTextures, d.materialTextures + d.numMaterials);
+    }
+
+    if (d.bokehCdf)
+    {
+        if (d.bokehWidth == 0 || d.bokehHeight == 0 || d.bokehWidth > 65536u || d.bokehHeight > 65536u) { err = "bokeh distribution with an invalid size"; return false; }
+        const size_t n = (size_t)d.bokehWidth * d.bokehHeight;
+        out.bokehCdf.assign(d.bokehCdf, d.bokehCdf + n + 1);
+        for (size_t i = 0; i < n; ++i) if (!(out.bokehCdf[i] <= out.bokehCdf[i + 1])) { err = "bokeh distribution is not a cumulative distribution"; return false; }
+        out.bokehWidth = d.bokehWidth; out.bokehHeight = d.bokehHeight;
     }
 
     out.meshes.resize(d.numMeshes);

@@ -47,6 +47,7 @@ int rtbh_scene_save_flat(void* scene, const char* path, uint32_t width, uint32_t
     rt::Camera cam = h->camera;
     cam.SetPerspective((float)width / (float)height, cam.mFieldOfView);
     cam.Describe(flat.camera);
+    cam.DescribeBokeh(flat);
     flat.fieldOfView = cam.mFieldOfView;
     return flat.Save(path) ? 0 : -1;
 }
@@ -63,7 +64,7 @@ void* rtbh_viewport_create(void* scene, int deviceId, uint32_t numShards, uint32
 {
     rt::ViewportB200* vp = new rt::ViewportB200();
     if (!vp->Create(deviceId, numShards, shardIndex, flags, blueNoisePath ? blueNoisePath : "", cudaStream)) { SetErr(err, errLen, vp->GetLastError()); delete vp; return nullptr; }
-    if (scene && !vp->SetScene(static_cast<SceneHandle*>(scene)->scene)) { SetErr(err, errLen, vp->GetLastError()); delete vp; return nullptr; }
+    if (scene && !vp->SetScene(static_cast<SceneHandle*>(scene)->scene, &static_cast<SceneHandle*>(scene)->camera)) { SetErr(err, errLen, vp->GetLastError()); delete vp; return nullptr; }
     return vp;
 }
 

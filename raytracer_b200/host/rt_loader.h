@@ -589,7 +589,7 @@ inline bool ParseLight(const json::Value& v, const std::string& dataPath, Scene&
     return true;
 }
 
-inline bool ParseCamera(const json::Value& v, Camera& camera, LoadError& err)
+inline bool ParseCamera(const json::Value& v, const std::string& dataPath, const TexturesMap& textures, Camera& camera, LoadError& err)
 {
     if (!v.IsObject()) return Fail(err, "Camera description must be a structure");
     Vector4 t, q;
@@ -601,7 +601,7 @@ inline bool ParseCamera(const json::Value& v, Camera& camera, LoadError& err)
     if (!TryParseBool(v, "enableDOF", true, camera.mDOF.enable, err)) return false;
     if (!TryParseFloat(v, "aperture", true, camera.mDOF.aperture, err)) return false;
     if (!TryParseFloat(v, "focalPlaneDistance", true, camera.mDOF.focalPlaneDistance, err)) return false;
-    if (v.HasMember("bokehTexture")) return Fail(err, "'bokehTexture': texture-shaped bokeh is not supported (Camera.cpp:205-214 samples it through the importance map)");
+    if (!TryParseTextureName(v, "bokehTexture", dataPath, textures, camera.mDOF.bokehTexture, err)) return false;
     return true;
 }
 
@@ -658,7 +658,7 @@ inline bool LoadScene(const std::string& path, const std::string& dataPath, Scen
         if (!a.IsArray()) ok = Fail(err, "'lights' is expected to be an array");
         for (size_t i = 0; ok && i < a.Size(); ++i) ok = ParseLight(a[i], dataPath, scene, textures, err);
     }
-    if (ok && d.HasMember("camera")) ok = ParseCamera(d["camera"], camera, err);
+    if (ok && d.HasMember("camera")) ok = ParseCamera(d["camera"], dataPath, textures, camera, err);
     if (!ok) errorMessage = err.message;
     return ok;
 }

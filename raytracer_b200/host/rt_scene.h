@@ -341,7 +341,11 @@ class Camera
 public:
     float mAspectRatio = 1.0f;
     float mFieldOfView = math::DegToRad(20.0f);
-    struct DOF { float focalPlaneDistance = 2.0f; float aperture = 0.1f; bool enable = false; uint32_t bokehShape = RTB_BOKEH_CIRCLE; } mDOF;
+    struct DOF
+    {
+        float focalPlaneDistance = 2.0f; float aperture = 0.1f; bool enable = false; uint32_t bokehShape = RTB_BOKEH_CIRCLE;
+        TexturePtr bokehTexture;      // Camera.h:49; selects BokehShape::Texture (SceneLoader.cpp:680-687)
+    } mDOF;
     float barrelDistortionConstFactor = 0.01f;
     float barrelDistortionVariableFactor = 0.0f;
 
@@ -357,6 +361,23 @@ public:
         c.aspectRatio = mAspectRatio; c.tanHalfFoV = mTanHalfFoV;
         c.dofEnable = mDOF.enable; c.bokehShape = mDOF.bokehShape; c.aperture = mDOF.aperture; c.focalPlaneDistance = mDOF.focalPlaneDistance;
         c.barrelDistortionConstFactor = barrelDistortionConstFactor; c.barrelDistortionVariableFactor = barrelDistortionVariableFactor;
+        if (mDOF.bokehTexture)
+        {
+            // a bitmap is sampled through its importance map (DescribeBokeh); the procedural textures' Sample() returns the
+            // sample itself as coordinates (CheckerboardTexture.cpp:43-55, NoiseTexture.cpp:157-169, MixTexture.cpp:33-45), and
+            // UnipolarToBipolar of that is exactly the square bokeh (Camera.cpp:203-204)
+            c.bokehShape = mDOF.bokehTexture->GetType() == RTB_TEXTURE_BITMAP ? RTB_BOKEH_TEXTURE : RTB_BOKEH_SQUARE;
+        }
+    }
+
+    // the bokeh bitmap's importance map goes with the scene upload (RtbSceneDesc::bokehCdf)
+    void DescribeBokeh(rtb::SceneFile& out) const
+    {
+        out.bokehWidth = out.bokehHeight = 0; out.bokehCdf.clear();
+        if (!mDOF.bokehTexture || mDOF.bokehTexture->GetType() != RTB_TEXTURE_BITMAP) return;
+        Bitmap& b = *static_cast<const BitmapTexture*>(mDOF.bokehTexture.get())->GetBitmap();
+        out.bokehWidth = b.GetWidth(); out.bokehHeight = b.GetHeight();
+        out.bokehCdf = b.GetImportanceCdf();
     }
 private:
     float mTanHalfFoV = tanf(math::DegToRad(20.0f) * 0.5f);

@@ -48,6 +48,28 @@ public:
     const std::vector<float>& GetTexels() const { return mTexels; }     // width*height*4, texel (x,y) = GetPixel(x,y)
     const std::string& GetError() const { return mError; }              // non-empty: the file is valid but unsupported here
 
+    // BitmapTexture::MakeSamplable (BitmapTexture.cpp:121-152) + Distribution::Initialize (Math/Distribution.cpp:27-84):
+    // importance = Dot3(c_rgbIntensityWeights, GetPixel) per texel, accumulated in float, normalised by 1 / total.
+    // Returns the cumulative distribution (width * height + 1 entries) that Distribution::SampleDiscrete searches.
+    const std::vector<float>& GetImportanceCdf()
+    {
+        if (!mImportanceCdf.empty() || mTexels.empty()) return mImportanceCdf;
+        const size_t n = (size_t)mWidth * mHeight;
+        mImportanceCdf.resize(n + 1);
+        float accumulated = 0.0f;
+        mImportanceCdf[0] = 0.0f;
+        for (size_t i = 0; i < n; ++i)
+        {
+            const float* c = &mTexels[4 * i];
+            const float pdf = (0.21f * c[0] + 0.72f * c[1]) + (0.07f * c[2] + 0.0f);     // dpps 0x7F: (x + y) + (z + 0)
+            accumulated += pdf;
+            mImportanceCdf[i + 1] = accumulated;
+        }
+        const float cdfNormFactor = 1.0f / accumulated;
+        for (size_t i = 0; i <= n; ++i) mImportanceCdf[i] *= cdfNormFactor;
+        return mImportanceCdf;
+    }
+
     // Bitmap::Load, Bitmap.cpp:298-333 (LoadBMP, then LoadDDS, then LoadEXR)
     bool Load(const char* path)
     {
@@ -394,6 +416,7 @@ private:
 
     uint32_t mWidth = 0, mHeight = 0;
     std::vector<float> mTexels;
+    std::vector<float> mImportanceCdf;
     std::string mError;
 };
 using BitmapPtr = std::shared_ptr<Bitmap>;

@@ -216,10 +216,12 @@ public:
     }
 
     // the scene must outlive nothing here: it is flattened and copied to the device (CreateRenderer + SetRenderer)
-    bool SetScene(const Scene& scene)
+    // (`camera`: its texture-shaped bokeh, if any, is uploaded with the scene)
+    bool SetScene(const Scene& scene, const Camera* camera = nullptr)
     {
         rtb::SceneFile flat;
         scene.Flatten(flat);
+        if (camera) camera->DescribeBokeh(flat);
         const RtbSceneDesc d = flat.View();
         if (rtb_upload_scene(mCtx, &d) != RTB_OK) return Error();
         mHasScene = true;

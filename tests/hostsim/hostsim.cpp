@@ -102,6 +102,12 @@ static void fillCamera(PassParams& P, const RtbCamera& c, uint32_t w, uint32_t h
     P.width = w; P.height = h;
 }
 
+static void fillBokeh(PassParams& P, const SceneFile& file)
+{
+    P.bokehCdf = file.bokehCdf.empty() ? nullptr : file.bokehCdf.data();
+    P.bokehWidth = file.bokehWidth; P.bokehHeight = file.bokehHeight;
+}
+
 // immediate-mode sink: shadow rays are traced on the spot, in light order
 struct HostSink
 {
@@ -140,6 +146,7 @@ static int cmdRender(int argc, char** argv)
     PassParams P;
     memset(&P, 0, sizeof(P));
     fillCamera(P, world.file.camera, w, h, tanf(world.file.fieldOfView * 0.5f));
+    fillBokeh(P, world.file);
     P.renderer = renderer; P.debugMode = debugMode; P.maxRayDepth = maxDepth; P.minRussianRouletteDepth = 1;
     P.lightSamplingAll = all; P.useBlueNoise = world.S.blueNoise != nullptr; P.numSeedDims = passes.numDims;
 
@@ -293,6 +300,7 @@ static int cmdPrimary(int argc, char** argv)
     PassParams P;
     memset(&P, 0, sizeof(P));
     fillCamera(P, world.file.camera, w, h, tanf(world.file.fieldOfView * 0.5f));
+    fillBokeh(P, world.file);
     P.numSeedDims = passes.numDims;
     P.seed = &passes.seeds[(size_t)pass * passes.numDims];
     P.sampleOffsetX = passes.offsets[pass * 2]; P.sampleOffsetY = passes.offsets[pass * 2 + 1];

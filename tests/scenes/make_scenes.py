@@ -331,6 +331,9 @@ def write_texture_files(out_dir):
     palette = [((i * 53) % 256, (i * 97 + 30) % 256, (255 - i * 16) % 256, (i * 17) % 256) for i in range(16)]
     write_bmp(os.path.join(tex, "pal.bmp"), 13, 5, 8, lambda x, y: (x * 3 + y * 5) % 16, palette)
     write_bmp(os.path.join(tex, "grey.bmp"), 6, 6, 8, lambda x, y: (x * 40 + y * 9) % 256)
+    # bokeh bitmap: a ring with a few black texels (zero importance) and a bright spot
+    write_bmp(os.path.join(tex, "bokeh.bmp"), 11, 9, 24,
+              lambda x, y: (0, 0, 0) if (x - 5) ** 2 + (y - 4) ** 2 > 20 or (x - 5) ** 2 + (y - 4) ** 2 < 3 else ((255, 255, 255) if (x, y) == (7, 5) else (60 + 10 * x, 90, 40 + 15 * y)))
 
 
 def write_textured_mesh(out_dir):
@@ -404,6 +407,9 @@ def write_all(out_dir, sponza=False):
     dof = scene_cornell()
     dof["camera"].update({"enableDOF": True, "aperture": 0.15, "focalPlaneDistance": 3.5})    # circle bokeh, Camera.cpp:100-116
     dump("cornell_dof", dof)
+    bokeh = scene_cornell()
+    bokeh["camera"].update({"enableDOF": True, "aperture": 0.25, "focalPlaneDistance": 3.5, "bokehTexture": "TEXTURES/bokeh.bmp"})   # Camera.cpp:208-213
+    dump("cornell_bokeh", bokeh)
     write_texture_files(out_dir)
     write_textured_mesh(out_dir)
     dump("textures", scene_textures())

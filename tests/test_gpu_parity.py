@@ -286,6 +286,31 @@ def test_bokeh_shapes_and_barrel_distortion_against_the_live_reference(ctx, tmp_
     assert ctx.counters()["numRays"] == meta["numRays"]
 
 
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="prebuilt oracle/_ref/exact did not travel to this box")
+def test_texture_shaped_bokeh_against_the_live_reference(ctx, tmp_path):
+    """Depth of field whose lens point is drawn from a bokeh bitmap's importance map (RtbSceneDesc::bokehCdf)."""
+    scn = os.path.join(util.GOLDEN, "scenes")
+    w, h, passes = 80, 60, 3
+    common = ["--scene", os.path.join(scn, "cornell_bokeh.json"), "--data", scn + "/", "--width", w, "--height", h]
+    sump, passp, flatp = str(tmp_path / "o.sum"), str(tmp_path / "o.passes"), str(tmp_path / "o.rtb")
+    meta = util.run_rtref(["render", *common, "--passes", passes, "--dims", 128, "--depth", 8, "--strategy", "all", "--dump-sum", sump, "--dump-passes", passp])
+    util.run_rtref(["flat", *common, "--out", flatp])
+    sf = capi.SceneFile(flatp)
+    assert sf.bokeh_cdf is not None and sf.camera.bokehShape == 4
+    ps = capi.PassScript(passp)
+    ctx.upload_scene(sf)
+    ctx.resize(w, h)
+    cam = capi.camera_for(sf, w, h)
+    for p in range(passes):
+        ctx.render_pass(ctx.make_pass(cam, ps.seeds[p], ps.offsets[p], p))
+    util.assert_bit_identical(ctx.read_sum(), util.load_sum(sump, w, h), "texture-shaped bokeh")
+    assert ctx.counters()["numRays"] == meta["numRays"]
+    # the same camera on a scene without a bokeh distribution is refused
+    ctx.upload_scene(capi.SceneFile(util.golden("cornell.rtb")))
+    with pytest.raises(capi.RtbError, match="no bokeh distribution"):
+        ctx.render_pass(ctx.make_pass(cam, ps.seeds[0], ps.offsets[0], 0))
+
+
 def test_gathered_shards_unshard_to_the_full_frame(ctx):
     """What bench.py does at N > 1, emulated on one GPU: per-shard compact films concatenated (the all-gather result)
     and scattered back to raster order by rtb_unshard_film; also checks the layout against raytracer_b200.sharding."""

@@ -133,6 +133,27 @@ def test_hostsim_bokeh_shapes_and_barrel_distortion(hostsim, tmp_path, bokeh, ba
 
 
 @pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
+def test_hostsim_texture_shaped_bokeh(hostsim, tmp_path):
+    """Depth of field with a bokeh bitmap (Camera::GenerateBokeh, BokehShape::Texture -> BitmapTexture::Sample ->
+    Distribution::SampleDiscrete): the importance map the host builds equals the reference's, and so does the render."""
+    from raytracer_b200 import host_api
+    scn = os.path.join(util.GOLDEN, "scenes")
+    sj = os.path.join(scn, "cornell_bokeh.json")
+    common = ["--scene", sj, "--data", scn + "/", "--width", 48, "--height", 48]
+    sump, passp, flatp, minep = str(tmp_path / "o.sum"), str(tmp_path / "o.passes"), str(tmp_path / "o.rtb"), str(tmp_path / "mine.rtb")
+    meta = util.run_rtref(["render", *common, "--passes", 3, "--dims", 128, "--depth", 8, "--strategy", "all", "--dump-sum", sump, "--dump-passes", passp])
+    util.run_rtref(["flat", *common, "--out", flatp])
+    host_api.Scene(sj, scn + "/").save_flat(minep, 48, 48)
+    ref, mine = capi.SceneFile(flatp), capi.SceneFile(minep)
+    assert ref.bokeh_size == mine.bokeh_size == (11, 9) and ref.camera.bokehShape == mine.camera.bokehShape == 4
+    assert ref.bokeh_cdf.tobytes() == mine.bokeh_cdf.tobytes(), "importance map differs from BitmapTexture::MakeSamplable"
+    out = str(tmp_path / "mine.sum")
+    r = subprocess.run([HOSTSIM, "render", minep, passp, "48", "48", out, "1", "8", "0", "1", hostsim], stdout=subprocess.PIPE, text=True, check=True)
+    util.assert_bit_identical(util.load_sum(out, 48, 48), util.load_sum(sump, 48, 48), "texture-shaped bokeh")
+    assert json.loads(r.stdout.strip().splitlines()[-1])["numRays"] == meta["numRays"]
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
 def test_golden_fixtures_reproduce_from_the_reference(tmp_path):
     """The committed fixtures are what the real reference produces today (pins the oracle: fixed seed, exact math)."""
     scn = os.path.join(util.GOLDEN, "scenes")
