@@ -384,6 +384,35 @@ int  rtb_unshard_film_async(RtbContext* ctx, const void* gatheredDevice, float* 
 void* rtb_host_alloc(uint64_t bytes);
 void  rtb_host_free(void* p);
 
+/* Viewport::SetPostprocessParams / GetFrontBuffer (Viewport.h:43,49; PostprocessParams, Rendering/PostProcess.h:11-29):
+ * the tone-mapped 8-bit image of the film.  Tonemapper values are the reference's (Color/ColorHelpers.h:77-83). */
+typedef enum RtbTonemapper
+{
+    RTB_TONEMAP_CLAMPED  = 0,
+    RTB_TONEMAP_REINHARD = 1,
+    RTB_TONEMAP_JIM_HEJL = 2,
+    RTB_TONEMAP_ACES     = 3
+} RtbTonemapper;
+
+typedef struct RtbPostprocessDesc
+{
+    float    colorFilter[4];     /* defaults of PostprocessParams::PostprocessParams (PostProcess.cpp:6-14): 1,1,1,1 */
+    float    exposure;           /* log2 scale, 0 */
+    float    contrast;           /* 0.8 */
+    float    saturation;         /* 0.98 */
+    float    ditheringStrength;  /* 0.005; 0 = none.  The reference dithers from per-thread generators (Viewport.cpp:494,545:
+                                    not reproducible across thread counts); here the noise is a hash of (pixel, ditherSeed) */
+    float    bloomFactor;        /* 0 = off (the reference's default) */
+    uint32_t tonemapper;         /* RtbTonemapper; ACES */
+    uint32_t numPasses;          /* passes accumulated in the film: the image is sum / numPasses (Viewport.cpp:499) */
+    uint32_t ditherSeed;
+} RtbPostprocessDesc;
+
+/* Viewport::PerformPostProcess + PostProcessTile (Viewport.cpp:432-552): film (sum) -> bgra[y*width + x] = 0x00RRGGBB,
+ * row 0 = top.  `gatheredDevice` NULL: this context's own film (pixels of other shards stay 0), else the all-gathered
+ * shard films as for rtb_unshard_film.  Synchronous. */
+int  rtb_read_front(RtbContext* ctx, const RtbPostprocessDesc* post, const void* gatheredDevice, uint32_t* bgra);
+
 int  rtb_get_counters(RtbContext* ctx, RtbCounters* out);   /* counters of the passes since the last reset */
 
 int  rtb_trace_batch(RtbContext* ctx, const RtbRay* rays, uint64_t n, RtbHit* hits, uint32_t mode);

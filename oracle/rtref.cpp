@@ -452,6 +452,24 @@ int CmdRender(const Args& a)
     if (!renderer) Die("unknown renderer");
     if (rendererName == "Debug") static_cast<DebugRenderer*>(renderer.get())->mRenderingMode = (DebugRenderingMode)a.Int("debug-mode", 1);
     vp.SetRenderer(renderer);
+    if (a.Has("dump-front"))
+    {
+        // dithering draws from the per-thread generators (Viewport.cpp:494): off unless asked for
+        PostprocessParams pp;
+        pp.ditheringStrength = (float)a.Dbl("pp-dither", 0.0);
+        pp.exposure = (float)a.Dbl("pp-exposure", pp.exposure);
+        pp.contrast = (float)a.Dbl("pp-contrast", pp.contrast);
+        pp.saturation = (float)a.Dbl("pp-saturation", pp.saturation);
+        pp.bloomFactor = (float)a.Dbl("pp-bloom", pp.bloomFactor);
+        pp.tonemapper = (Tonemapper)a.Int("pp-tonemapper", (long)pp.tonemapper);
+        if (a.Has("pp-filter"))
+        {
+            float r = 1.0f, g = 1.0f, b = 1.0f;
+            if (sscanf(a.Str("pp-filter").c_str(), "%f,%f,%f", &r, &g, &b) != 3) Die("--pp-filter r,g,b");
+            pp.colorFilter = Vector4(r, g, b, 1.0f);
+        }
+        vp.SetPostprocessParams(pp);
+    }
     vp.Reset();
 
     FILE* script = a.Has("dump-passes") ? fopen(a.Str("dump-passes").c_str(), "wb") : nullptr;
@@ -491,6 +509,12 @@ int CmdRender(const Args& a)
     {
         FILE* f = fopen(a.Str("dump-sum").c_str(), "wb");
         WriteBytes(f, vp.GetSumBuffer().GetData(), (size_t)w * h * 12);
+        fclose(f);
+    }
+    if (a.Has("dump-front"))
+    {
+        FILE* f = fopen(a.Str("dump-front").c_str(), "wb");
+        WriteBytes(f, vp.GetFrontBuffer().GetData(), (size_t)w * h * 4);
         fclose(f);
     }
     if (a.Has("dump-sum2"))

@@ -100,6 +100,26 @@ class RtbPassDesc(C.Structure):
                 ("sampleOffset", C.c_float * 2)]
 
 
+RTB_TONEMAP_CLAMPED, RTB_TONEMAP_REINHARD, RTB_TONEMAP_JIM_HEJL, RTB_TONEMAP_ACES = 0, 1, 2, 3
+
+
+class RtbPostprocessDesc(C.Structure):
+    """PostprocessParams (Rendering/PostProcess.h:11-29) + the pass count the film holds."""
+    _fields_ = [("colorFilter", C.c_float * 4), ("exposure", C.c_float), ("contrast", C.c_float), ("saturation", C.c_float),
+                ("ditheringStrength", C.c_float), ("bloomFactor", C.c_float), ("tonemapper", C.c_uint32),
+                ("numPasses", C.c_uint32), ("ditherSeed", C.c_uint32)]
+
+
+def postprocess_desc(num_passes, color_filter=(1.0, 1.0, 1.0), exposure=0.0, contrast=0.8, saturation=0.98, dithering=0.005,
+                     bloom=0.0, tonemapper=RTB_TONEMAP_ACES, dither_seed=0):
+    """Defaults = PostprocessParams::PostprocessParams (Rendering/PostProcess.cpp:6-14)."""
+    d = RtbPostprocessDesc()
+    d.colorFilter[:] = [color_filter[0], color_filter[1], color_filter[2], 1.0]
+    d.exposure, d.contrast, d.saturation, d.ditheringStrength, d.bloomFactor = exposure, contrast, saturation, dithering, bloom
+    d.tonemapper, d.numPasses, d.ditherSeed = tonemapper, num_passes, dither_seed
+    return d
+
+
 class RtbCounters(C.Structure):
     _fields_ = [("numRays", C.c_uint64), ("numShadowRays", C.c_uint64), ("numShadowRaysHit", C.c_uint64),
                 ("numPrimaryRays", C.c_uint64), ("numRayBoxTests", C.c_uint64), ("numRayTriangleTests", C.c_uint64),
@@ -127,7 +147,7 @@ EXPORTED_SYMBOLS = [
     "rtb_last_error", "rtb_api_version", "rtb_create", "rtb_destroy", "rtb_upload_scene", "rtb_set_blue_noise",
     "rtb_resize", "rtb_reset", "rtb_render_pass", "rtb_render_passes", "rtb_synchronize", "rtb_join", "rtb_read_sum", "rtb_film_device_buffer", "rtb_film_snapshots",
     "rtb_unshard_film", "rtb_read_sum_async", "rtb_unshard_film_async", "rtb_host_alloc", "rtb_host_free", "rtb_get_counters", "rtb_trace_batch", "rtb_trace_batch_device", "rtb_texture_batch", "rtb_sample_batch",
-    "rtb_primary_rays", "rtb_set_profiling", "rtb_get_pass_timings",
+    "rtb_primary_rays", "rtb_set_profiling", "rtb_get_pass_timings", "rtb_read_front",
 ]
 
 _lib = None
@@ -174,6 +194,7 @@ def load_library(path=None):
     lib.rtb_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
     lib.rtb_trace_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
     lib.rtb_texture_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.rtb_read_front.argtypes = [C.c_void_p, C.POINTER(RtbPostprocessDesc), C.c_void_p, C.c_void_p]
     lib.rtb_sample_batch.argtypes = [C.c_void_p, C.POINTER(RtbPassDesc), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
     lib.rtb_primary_rays.argtypes = [C.c_void_p, C.POINTER(RtbPassDesc), C.c_void_p]
     lib.rtb_set_profiling.argtypes = [C.c_void_p, C.c_int]
@@ -401,6 +422,12 @@ class Context:
         if out is None:
             out = np.empty((self.height, self.width, 3), dtype=np.float32)
         _check(self.lib, self.lib.rtb_read_sum(self.h, out.ctypes.data, which))
+        return out
+
+    def read_front(self, post, gathered_device_ptr=None):
+        """rtb_read_front: Viewport::GetFrontBuffer - (height, width) uint32 0x00RRGGBB."""
+        out = np.empty((self.height, self.width), dtype=np.uint32)
+        _check(self.lib, self.lib.rtb_read_front(self.h, C.byref(post), gathered_device_ptr, out.ctypes.data))
         return out
 
     def texture_batch(self, texture_index, uv):

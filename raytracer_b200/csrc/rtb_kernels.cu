@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "rtb_integrator.h"
+#include "rtb_postprocess.h"
 #include "rtb_upload.h"
 
 using namespace rtb;
@@ -561,6 +562,39 @@ __global__ void __launch_bounds__(256) k_unshard(const float* __restrict__ src, 
     }
 }
 
+// front buffer (Viewport::PostProcessTile): pixel slots -> tone-mapped 0x00RRGGBB in raster order; `blurred` (the
+// RTB_BLOOM_LEVELS blurred raster images back to back) is only read when P.bloomFactor > 0
+__global__ void __launch_bounds__(256) k_front(const float* __restrict__ src, uint32_t* __restrict__ dstRaster, const uint32_t* __restrict__ pixelListAll, uint32_t total,
+                                               const float* __restrict__ blurred, size_t levelStride, const PostParams P)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+    {
+        const uint32_t pix = pixelListAll[i];
+        if (pix == 0xFFFFFFFFu) continue;     // padding slot
+        const V3 sum = v3(src[(size_t)i * 3 + 0], src[(size_t)i * 3 + 1], src[(size_t)i * 3 + 2]);
+        V3 bloom = v3s(0.0f);
+        if (P.bloomFactor > 0.0f) bloom = bloom_color(blurred, levelStride, pix);
+        dstRaster[pix] = postprocess_pixel(P, sum, bloom, pix);
+    }
+}
+
+// Bitmap::GaussianBlur, one direction: thread = (line, colour channel), lines blurred element by element in the
+// reference's order (rtb_postprocess.h).  Horizontal: line = row, elements 3 floats apart; vertical: line = column,
+// elements one row apart (neighbouring threads then read neighbouring floats).
+__global__ void __launch_bounds__(128) k_blur(const float* in, float* out, uint32_t width, uint32_t height, int vertical,
+                                              float* scratchA, float* scratchB, const BlurSchedule schedule)
+{
+    const uint32_t numLines = vertical ? width : height;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= numLines * 3u) return;
+    const uint32_t line = t / 3u, channel = t % 3u;
+    const size_t first = vertical ? (size_t)line * 3 + channel : (size_t)line * width * 3 + channel;
+    const size_t elementStride = vertical ? (size_t)width * 3 : 3;
+    blur_line(in + first, out + first, elementStride, scratchA + t, scratchB + t, (size_t)numLines * 3,
+              schedule, vertical ? RTB_BLUR_KEPT_VERTICAL : RTB_BLUR_KEPT_HORIZONTAL, vertical ? height : width);
+}
+
 // test hooks ------------------------------------------------------------------------------------------------------------
 
 template <bool kCount>
@@ -725,6 +759,8 @@ struct RtbContext
     DevArray<uint32_t> pixelListAll;  // all shards back to back, padded with 0xFFFFFFFF
     DevArray<float> sum, sum2;
     DevArray<float> raster;           // scratch for read-back
+    DevArray<uint32_t> front;         // tone-mapped front buffer (rtb_read_front), allocated on first use
+    DevArray<float> blurred, blurScratch;   // bloom: RTB_BLOOM_LEVELS raster images + two line-major scratch images
     // ring of raster snapshots for the asynchronous read-back: the render stream only waits for a copy when the ring
     // wraps, so a group of frames (rtb_film_snapshots) can be in flight on the copy stream while the next passes render
     DevArray<float> rasterAsync[RTB_SNAP_RING];
@@ -791,7 +827,7 @@ static void free_scene(RtbContext* c)
 
 static void free_film(RtbContext* c)
 {
-    c->pixelList.release(); c->pixelListAll.release(); c->sum.release(); c->sum2.release(); c->raster.release();
+    c->pixelList.release(); c->pixelListAll.release(); c->sum.release(); c->sum2.release(); c->raster.release(); c->front.release(); c->blurred.release(); c->blurScratch.release();
     for (int i = 0; i < RTB_SNAP_RING; ++i) c->rasterAsync[i].release();
     c->snapshots.release(); c->snapshotCapacity = 0;
     for (RtbContext::Slot& t : c->slots)
@@ -1519,6 +1555,79 @@ int rtb_read_sum(RtbContext* c, float* rgb, int which)
     }
     RTB_CUDA(cudaGetLastError());
     RTB_CUDA(cudaMemcpyAsync(rgb, c->raster.ptr, (size_t)c->width * c->height * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    RTB_CUDA(cudaStreamSynchronize(c->stream));
+    return RTB_OK;
+}
+
+int rtb_read_front(RtbContext* c, const RtbPostprocessDesc* post, const void* gatheredDevice, uint32_t* bgra)
+{
+    if (!c || !post || !bgra) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    if (!c->sum.ptr) return fail(RTB_ERR_INVALID_ARG, "viewport has no size");
+    if (post->tonemapper > RTB_TONEMAP_ACES) return fail(RTB_ERR_INVALID_ARG, "unknown tonemapper %u", post->tonemapper);
+    if (post->numPasses == 0) return fail(RTB_ERR_INVALID_ARG, "numPasses is 0: nothing has been accumulated");
+    const bool bloom = post->bloomFactor > 0.0f;
+    BlurSchedule schedules[RTB_BLOOM_LEVELS];
+    if (bloom)
+    {
+        if (c->numShards > 1 && !gatheredDevice) return fail(RTB_ERR_UNSUPPORTED, "bloom blurs the whole image: pass the all-gathered film");
+        // where the reference's blur leaves its image (Bitmap.cpp:981-1009 walks columns four at a time; BoxBlur_Internal
+        // reads 2 * radius + 1 elements of a line) the result would be whatever lay next to it in memory
+        if (c->width % 4u != 0u || c->width > 4096u || c->height > 4096u) return fail(RTB_ERR_UNSUPPORTED, "bloom needs a width that is a multiple of 4 and at most 4096 x 4096 pixels (Bitmap.cpp:926-931, 981)");
+        float sigma = 2.0f;                                        // Viewport.cpp:438-444
+        for (uint32_t l = 0; l < RTB_BLOOM_LEVELS; ++l, sigma *= 2.5f)
+        {
+            schedules[l] = blur_schedule(sigma);
+            for (uint32_t i = 0; i < RTB_BLUR_ITERATIONS; ++i)
+                if (2u * schedules[l].radius[i] >= (c->width < c->height ? c->width : c->height))
+                    return fail(RTB_ERR_UNSUPPORTED, "bloom needs an image larger than its widest box blur (%u pixels)", 2u * schedules[l].radius[i] + 1u);
+        }
+    }
+    RTB_CUDA(cudaSetDevice(c->device));
+    RTB_CUDA(join_slots(c));
+    const size_t n = (size_t)c->width * c->height;
+    if (c->front.count != n) RTB_CUDA(c->front.alloc(n));
+
+    PostParams P;
+    const float exposureScale = powf(2.0f, post->exposure);       // Viewport.cpp:453
+    P.colorScale = v3(post->colorFilter[0] * exposureScale, post->colorFilter[1] * exposureScale, post->colorFilter[2] * exposureScale);
+    P.pixelScaling = 1.0f / (float)post->numPasses;
+    P.contrast = post->contrast; P.saturation = post->saturation;
+    P.ditheringStrength = post->ditheringStrength; P.bloomFactor = post->bloomFactor;
+    P.tonemapper = post->tonemapper; P.ditherSeed = post->ditherSeed;
+
+    const float* src = gatheredDevice ? (const float*)gatheredDevice : c->sum.ptr;
+    const size_t levelStride = n * 3;
+    if (bloom)
+    {
+        // Viewport::PerformPostProcess (Viewport.cpp:434-445): level 0 = blur(sum), level i = blur(level i - 1)
+        if (c->blurred.count != levelStride * RTB_BLOOM_LEVELS) RTB_CUDA(c->blurred.alloc(levelStride * RTB_BLOOM_LEVELS));
+        if (c->blurScratch.count != levelStride * 2) RTB_CUDA(c->blurScratch.alloc(levelStride * 2));
+        k_unshard<<<c->numSMs * 4, 256, 0, c->stream>>>(src, c->raster.ptr, c->pixelListAll.ptr, c->numShards * c->shardSlots);
+        for (uint32_t l = 0; l < RTB_BLOOM_LEVELS; ++l)
+        {
+            const float* from = l == 0 ? c->raster.ptr : c->blurred.ptr + (l - 1) * levelStride;
+            float* level = c->blurred.ptr + l * levelStride;
+            k_blur<<<(c->height * 3 + 127) / 128, 128, 0, c->stream>>>(from, level, c->width, c->height, 0, c->blurScratch.ptr, c->blurScratch.ptr + levelStride, schedules[l]);
+            k_blur<<<(c->width * 3 + 127) / 128, 128, 0, c->stream>>>(level, level, c->width, c->height, 1, c->blurScratch.ptr, c->blurScratch.ptr + levelStride, schedules[l]);
+        }
+        c->counters.numKernelLaunches += 1 + 2 * RTB_BLOOM_LEVELS;
+    }
+    if (gatheredDevice)
+    {
+        k_front<<<c->numSMs * 4, 256, 0, c->stream>>>(src, c->front.ptr, c->pixelListAll.ptr, c->numShards * c->shardSlots, c->blurred.ptr, levelStride, P);
+    }
+    else if (c->numShards > 1)
+    {
+        RTB_CUDA(cudaMemsetAsync(c->front.ptr, 0, n * sizeof(uint32_t), c->stream));
+        k_front<<<c->numSMs * 4, 256, 0, c->stream>>>(src, c->front.ptr, c->pixelList.ptr, c->numPixels, c->blurred.ptr, levelStride, P);
+    }
+    else
+    {
+        k_front<<<c->numSMs * 4, 256, 0, c->stream>>>(src, c->front.ptr, c->pixelListAll.ptr, c->shardSlots, c->blurred.ptr, levelStride, P);
+    }
+    RTB_CUDA(cudaGetLastError());
+    c->counters.numKernelLaunches++;
+    RTB_CUDA(cudaMemcpyAsync(bgra, c->front.ptr, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     RTB_CUDA(cudaStreamSynchronize(c->stream));
     return RTB_OK;
 }

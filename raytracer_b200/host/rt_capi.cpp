@@ -104,6 +104,16 @@ int rtbh_viewport_render(void* vp, void* scene, uint32_t numPasses)
 
 int rtbh_viewport_synchronize(void* vp) { return static_cast<rt::ViewportB200*>(vp)->Synchronize() ? 0 : -1; }
 int rtbh_viewport_read_sum(void* vp, float* rgb, int which) { return static_cast<rt::ViewportB200*>(vp)->GetSumBuffer(rgb, which) ? 0 : -1; }
+// Viewport::SetPostprocessParams / GetFrontBuffer
+int rtbh_viewport_set_postprocess(void* vp, const float* colorFilter3, float exposure, float contrast, float saturation, float ditheringStrength, float bloomFactor, uint32_t tonemapper)
+{
+    rt::PostprocessParams p;
+    for (int i = 0; i < 3; ++i) p.colorFilter[i] = colorFilter3[i];
+    p.exposure = exposure; p.contrast = contrast; p.saturation = saturation; p.ditheringStrength = ditheringStrength;
+    p.bloomFactor = bloomFactor; p.tonemapper = tonemapper;
+    return static_cast<rt::ViewportB200*>(vp)->SetPostprocessParams(p) ? 0 : -1;
+}
+int rtbh_viewport_read_front(void* vp, uint32_t* bgra) { return static_cast<rt::ViewportB200*>(vp)->GetFrontBuffer(bgra) ? 0 : -1; }
 int rtbh_viewport_counters(void* vp, RtbCounters* out) { return static_cast<rt::ViewportB200*>(vp)->GetCounters(*out) ? 0 : -1; }
 
 } // extern "C"

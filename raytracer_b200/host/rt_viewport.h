@@ -189,6 +189,18 @@ struct RenderingParams
     uint32_t lightSamplingStrategy = RTB_LIGHT_SAMPLING_SINGLE;
 };
 
+// PostprocessParams, Rendering/PostProcess.h:11-29 with the defaults of PostProcess.cpp:6-14
+struct PostprocessParams
+{
+    float colorFilter[3] = { 1.0f, 1.0f, 1.0f };
+    float exposure = 0.0f;             // log2 scale
+    float contrast = 0.8f;
+    float saturation = 0.98f;
+    float ditheringStrength = 0.005f;  // applied after tonemapping
+    float bloomFactor = 0.0f;
+    uint32_t tonemapper = RTB_TONEMAP_ACES;
+};
+
 class ViewportB200
 {
 public:
@@ -248,6 +260,7 @@ public:
     }
 
     bool SetRenderingParams(const RenderingParams& p) { mParams = p; return true; }
+    bool SetPostprocessParams(const PostprocessParams& p) { mPostprocessParams = p; return true; }      // Viewport.cpp:166-177
     void SetSeed(uint64_t seed) { mSeedValue = seed; }
 
     // Viewport::Reset, Viewport.cpp:117-138
@@ -299,6 +312,20 @@ public:
 
     bool Synchronize() { return rtb_synchronize(mCtx) == RTB_OK || Error(); }
     bool GetSumBuffer(float* rgb, int which = 0) { return rtb_read_sum(mCtx, rgb, which) == RTB_OK || Error(); }
+    // Viewport::GetFrontBuffer (Viewport.h:49): the tone-mapped image of what has been rendered so far, width * height
+    // 0x00RRGGBB, row 0 = top.  The reference refreshes it inside every Render(); here it is computed when asked for.
+    bool GetFrontBuffer(uint32_t* bgra)
+    {
+        if (mPassesFinished == 0) { mError = "Viewport: nothing rendered yet"; return false; }
+        RtbPostprocessDesc d;
+        memset(&d, 0, sizeof(d));
+        for (int i = 0; i < 3; ++i) d.colorFilter[i] = mPostprocessParams.colorFilter[i];
+        d.colorFilter[3] = 1.0f;
+        d.exposure = mPostprocessParams.exposure; d.contrast = mPostprocessParams.contrast; d.saturation = mPostprocessParams.saturation;
+        d.ditheringStrength = mPostprocessParams.ditheringStrength; d.bloomFactor = mPostprocessParams.bloomFactor;
+        d.tonemapper = mPostprocessParams.tonemapper; d.numPasses = mPassesFinished; d.ditherSeed = mPassesFinished;
+        return rtb_read_front(mCtx, &d, nullptr, bgra) == RTB_OK || Error();
+    }
     bool GetCounters(RtbCounters& c) { return rtb_get_counters(mCtx, &c) == RTB_OK || Error(); }
     uint32_t GetWidth() const { return mWidth; }
     uint32_t GetHeight() const { return mHeight; }
@@ -325,6 +352,7 @@ private:
     uint32_t mRenderer = RTB_RENDERER_PATH_TRACER_MIS, mDebugMode = RTB_DEBUG_TRIANGLE_ID;
     uint32_t mWidth = 0, mHeight = 0, mPassesFinished = 0;
     RenderingParams mParams;
+    PostprocessParams mPostprocessParams;
     uint64_t mSeedValue = 12345;
     Random mRandom;
     HaltonSequence mHalton;

@@ -3,6 +3,7 @@
 //
 //   rtb200_render -s scene.json --data DIR -w 1920 -h 1080 --spp 64 --renderer "Path Tracer MIS" --depth 8
 //                 --dims 128 --strategy all --seed 12345 --device 0 --out sum.f32 [--flat scene.rtb]
+//                 [--front image.bmp --exposure E --contrast C --saturation S --dither D --bloom B --tonemapper 0..3]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -27,7 +28,8 @@ int main(int argc, char** argv)
     if (scenePath.empty())
     {
         fprintf(stderr, "usage: rtb200_render -s scene.json [--data DIR] [-w W] [-h H] [--spp N] [--renderer NAME] [--depth D] [--dims K]\n"
-                        "                     [--strategy all|single] [--seed S] [--device I] [--bluenoise FILE] [--out sum.f32] [--flat scene.rtb]\n");
+                        "                     [--strategy all|single] [--seed S] [--device I] [--bluenoise FILE] [--out sum.f32] [--flat scene.rtb]\n"
+                        "                     [--front image.bmp] [--exposure E] [--contrast C] [--saturation S] [--dither D] [--bloom B] [--tonemapper 0..3]\n");
         return 2;
     }
     const uint32_t w = atoi(get("-w", "1280").c_str()), h = atoi(get("-h", "720").c_str()), spp = atoi(get("--spp", "16").c_str());
@@ -41,13 +43,14 @@ int main(int argc, char** argv)
         rtb::SceneFile flat;
         scene.Flatten(flat);
         camera.Describe(flat.camera);
+        camera.DescribeBokeh(flat);
         flat.fieldOfView = camera.mFieldOfView;
         if (!flat.Save(a["--flat"])) { fprintf(stderr, "[ERROR] cannot write %s\n", a["--flat"].c_str()); return 1; }
         if (spp == 0) return 0;
     }
     rt::ViewportB200 vp;
     if (!vp.Create(atoi(get("--device", "0").c_str()), 1, 0, 0, get("--bluenoise", ""))) { fprintf(stderr, "[ERROR] %s\n", vp.GetLastError().c_str()); return 1; }
-    if (!vp.SetScene(scene)) { fprintf(stderr, "[ERROR] %s\n", vp.GetLastError().c_str()); return 1; }
+    if (!vp.SetScene(scene, &camera)) { fprintf(stderr, "[ERROR] %s\n", vp.GetLastError().c_str()); return 1; }
     rt::RenderingParams p;
     p.maxRayDepth = atoi(get("--depth", "8").c_str());
     p.dimensions = atoi(get("--dims", "128").c_str());
@@ -71,6 +74,28 @@ int main(int argc, char** argv)
         std::vector<float> img((size_t)w * h * 3);
         if (!vp.GetSumBuffer(img.data())) { fprintf(stderr, "[ERROR] %s\n", vp.GetLastError().c_str()); return 1; }
         FILE* f = fopen(a["--out"].c_str(), "wb");
+        fwrite(img.data(), 4, img.size(), f);
+        fclose(f);
+    }
+    if (a.count("--front"))
+    {
+        // Viewport::GetFrontBuffer as a top-down 32-bit BMP
+        rt::PostprocessParams pp;
+        pp.exposure = (float)atof(get("--exposure", "0").c_str());
+        pp.contrast = (float)atof(get("--contrast", "0.8").c_str());
+        pp.saturation = (float)atof(get("--saturation", "0.98").c_str());
+        pp.ditheringStrength = (float)atof(get("--dither", "0.005").c_str());
+        pp.bloomFactor = (float)atof(get("--bloom", "0").c_str());
+        pp.tonemapper = atoi(get("--tonemapper", "3").c_str());
+        vp.SetPostprocessParams(pp);
+        std::vector<uint32_t> img((size_t)w * h);
+        if (!vp.GetFrontBuffer(img.data())) { fprintf(stderr, "[ERROR] %s\n", vp.GetLastError().c_str()); return 1; }
+        FILE* f = fopen(a["--front"].c_str(), "wb");
+        if (!f) { fprintf(stderr, "[ERROR] cannot write %s\n", a["--front"].c_str()); return 1; }
+        const uint32_t dataBytes = w * h * 4, fileHeader[3] = { 54 + dataBytes, 0, 54 };
+        const int32_t topDown = -(int32_t)h;
+        const uint32_t info[10] = { 40, w, (uint32_t)topDown, 1u | (32u << 16), 0, dataBytes, 2835, 2835, 0, 0 };
+        fwrite("BM", 1, 2, f); fwrite(fileHeader, 4, 3, f); fwrite(info, 4, 10, f);
         fwrite(img.data(), 4, img.size(), f);
         fclose(f);
     }

@@ -45,6 +45,8 @@ def load_host_library():
     lib.rtbh_viewport_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     lib.rtbh_viewport_synchronize.argtypes = [C.c_void_p]
     lib.rtbh_viewport_read_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.rtbh_viewport_set_postprocess.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint32]
+    lib.rtbh_viewport_read_front.argtypes = [C.c_void_p, C.c_void_p]
     lib.rtbh_viewport_counters.argtypes = [C.c_void_p, C.POINTER(capi.RtbCounters)]
     _lib = lib
     return lib
@@ -129,6 +131,18 @@ class Viewport:
         if out is None:
             out = np.empty((self.height, self.width, 3), dtype=np.float32)
         self._check(self.lib.rtbh_viewport_read_sum(self.h, out.ctypes.data, which))
+        return out
+
+    def set_postprocess(self, color_filter=(1.0, 1.0, 1.0), exposure=0.0, contrast=0.8, saturation=0.98, dithering=0.005, bloom=0.0,
+                        tonemapper=capi.RTB_TONEMAP_ACES):
+        """Viewport::SetPostprocessParams; defaults = PostprocessParams::PostprocessParams (PostProcess.cpp:6-14)."""
+        f = (C.c_float * 3)(*color_filter)
+        self._check(self.lib.rtbh_viewport_set_postprocess(self.h, f, exposure, contrast, saturation, dithering, bloom, tonemapper))
+
+    def read_front(self):
+        """Viewport::GetFrontBuffer: (height, width) uint32 0x00RRGGBB."""
+        out = np.empty((self.height, self.width), dtype=np.uint32)
+        self._check(self.lib.rtbh_viewport_read_front(self.h, out.ctypes.data))
         return out
 
     def counters(self):

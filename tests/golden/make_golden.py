@@ -127,7 +127,9 @@ def main():
             extra = ["--dump-passes", os.path.join(out, name + ".passes")] if r == renderers[0] else []
             c = rtref("render", *common, "--passes", PASSES, "--dims", dims, "--renderer", rname, "--debug-mode", dbg,
                       "--depth", 8, "--strategy", "all", "--dump-sum", os.path.join(out, "%s_%s.sum" % (name, r)),
-                      "--dump-sum2", os.path.join(out, "%s_%s.sum2" % (name, r)) if r == "mis" else "/dev/null", *extra)
+                      "--dump-sum2", os.path.join(out, "%s_%s.sum2" % (name, r)) if r == "mis" else "/dev/null",
+                      # Viewport::GetFrontBuffer with the default PostprocessParams, dithering off (not reproducible)
+                      *(["--dump-front", os.path.join(out, "%s_%s.front" % (name, r))] if r == "mis" else []), *extra)
             keep = {k: c[k] for k in ("numPrimaryRays", "numRays", "numShadowRays", "numShadowRaysHit", "passes", "width", "height")}
             keep["dims"] = dims
             json.dump(keep, open(os.path.join(out, "%s_%s.json" % (name, r)), "w"))

@@ -9,6 +9,7 @@
 //   hostsim trace  <scene.rtb> <rays.bin> <out.hits> [shadow tmax.bin]
 //   hostsim sampler <passes.bin> <w> <h> <numDims> <out.u32> <bluenoise.dat|->
 //   hostsim primary <scene.rtb> <passes.bin> <pass> <w> <h> <out.rays>
+//   hostsim front  <sum.bin> <w> <h> <numPasses> <exposure> <contrast> <saturation> <dither> <tonemapper> <r,g,b filter> <out.bgra> [bloomFactor]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -18,6 +19,7 @@
 #include <pmmintrin.h>
 
 #include "../../raytracer_b200/csrc/rtb_integrator.h"
+#include "../../raytracer_b200/csrc/rtb_postprocess.h"
 #include "../../raytracer_b200/csrc/rtb_upload.h"
 #include "../../raytracer_b200/csrc/rtb_scene_file.h"
 
@@ -323,6 +325,55 @@ static int cmdPrimary(int argc, char** argv)
     return 0;
 }
 
+// the arithmetic of rtb_read_front on a raster sum buffer
+static int cmdFront(int argc, char** argv)
+{
+    if (argc < 13) die("front: arguments");
+    const uint32_t w = atoi(argv[3]), h = atoi(argv[4]);
+    std::vector<float> sum((size_t)w * h * 3);
+    FILE* f = fopen(argv[2], "rb");
+    if (!f || fread(sum.data(), 4, sum.size(), f) != sum.size()) die("cannot read sum");
+    fclose(f);
+    PostParams P;
+    float fr = 1.0f, fg = 1.0f, fb = 1.0f;
+    if (sscanf(argv[11], "%f,%f,%f", &fr, &fg, &fb) != 3) die("front: filter");
+    const float exposureScale = powf(2.0f, (float)atof(argv[6]));
+    P.colorScale = v3(fr * exposureScale, fg * exposureScale, fb * exposureScale);
+    P.pixelScaling = 1.0f / (float)(uint32_t)atoi(argv[5]);
+    P.contrast = (float)atof(argv[7]); P.saturation = (float)atof(argv[8]); P.ditheringStrength = (float)atof(argv[9]);
+    P.bloomFactor = argc > 13 ? (float)atof(argv[13]) : 0.0f; P.tonemapper = atoi(argv[10]); P.ditherSeed = 1;
+    const size_t levelStride = (size_t)w * h * 3;
+    std::vector<float> blurred;
+    if (P.bloomFactor > 0.0f)
+    {
+        // the launches of rtb_read_front, one "thread" after the other
+        blurred.resize(levelStride * RTB_BLOOM_LEVELS);
+        std::vector<float> scratch(levelStride * 2);
+        float sigma = 2.0f;
+        for (uint32_t l = 0; l < RTB_BLOOM_LEVELS; ++l, sigma *= 2.5f)
+        {
+            const BlurSchedule schedule = blur_schedule(sigma);
+            const float* from = l == 0 ? sum.data() : blurred.data() + (l - 1) * levelStride;
+            float* level = blurred.data() + l * levelStride;
+            for (uint32_t t = 0; t < h * 3; ++t)
+                blur_line(from + (size_t)(t / 3) * w * 3 + t % 3, level + (size_t)(t / 3) * w * 3 + t % 3, 3, scratch.data() + t, scratch.data() + levelStride + t,
+                          (size_t)h * 3, schedule, RTB_BLUR_KEPT_HORIZONTAL, w);
+            for (uint32_t t = 0; t < w * 3; ++t)
+                blur_line(level + t, level + t, (size_t)w * 3, scratch.data() + t, scratch.data() + levelStride + t, (size_t)w * 3, schedule, RTB_BLUR_KEPT_VERTICAL, h);
+        }
+    }
+    std::vector<uint32_t> out((size_t)w * h);
+    for (uint32_t i = 0; i < w * h; ++i)
+    {
+        const V3 bloom = P.bloomFactor > 0.0f ? bloom_color(blurred.data(), levelStride, i) : v3s(0.0f);
+        out[i] = postprocess_pixel(P, v3(sum[3 * i], sum[3 * i + 1], sum[3 * i + 2]), bloom, i);
+    }
+    FILE* of = fopen(argv[12], "wb");
+    fwrite(out.data(), 4, out.size(), of);
+    fclose(of);
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     // the reference runs with FTZ + DAZ (Core/Math/Math.cpp:27-34); the CUDA build uses -ftz=true
@@ -335,6 +386,7 @@ int main(int argc, char** argv)
     if (cmd == "texeval") return cmdTexEval(argc, argv);
     if (cmd == "sampler") return cmdSampler(argc, argv);
     if (cmd == "primary") return cmdPrimary(argc, argv);
+    if (cmd == "front") return cmdFront(argc, argv);
     die("unknown command");
     return 2;
 }

@@ -455,3 +455,132 @@ def test_async_read_back_snapshots_every_pass(ctx):
     finally:
         for im in pinned:
             im.close()
+
+
+# ---- front buffer: Viewport::SetPostprocessParams / GetFrontBuffer (rtb_read_front) ---------------------------------------
+
+@pytest.mark.parametrize("scene", ["c1_sphere_area", "cornell", "cornell_dof", "materials", "mesh_small", "textures"])
+def test_front_buffer_golden(ctx, scene):
+    """The reference's front buffer (default PostprocessParams, dithering off) of the golden renders, bit for bit."""
+    meta, _, _ = render_golden_case(ctx, scene, "mis")
+    got = ctx.read_front(capi.postprocess_desc(meta["passes"], dithering=0.0))
+    want = np.fromfile(util.golden(scene + "_mis.front"), dtype=np.uint32).reshape(meta["height"], meta["width"])
+    assert np.array_equal(got, want), "%d of %d front-buffer pixels differ" % ((got != want).sum(), want.size)
+
+
+POSTPROCESS_CASES = [
+    # scene, w, h, passes, exposure, contrast, saturation, tonemapper, filter, bloom
+    ("cornell", 64, 48, 3, 0.0, 0.8, 0.98, 0, (1, 1, 1), 0.0),
+    ("cornell", 64, 48, 3, 0.0, 0.8, 0.98, 1, (1, 1, 1), 0.0),
+    ("cornell", 64, 48, 3, 0.0, 0.8, 0.98, 2, (1, 1, 1), 0.0),
+    ("materials", 64, 48, 3, 1.5, 1.2, 0.3, 3, (0.9, 0.5, 1.25), 0.0),
+    ("mesh_small", 40, 30, 2, 9.0, 0.8, 1.0, 1, (3, 0, 1e-30), 0.0),
+    ("cornell", 33, 17, 1, 30.0, 40.0, 5.0, 2, (1, 1, 1), 0.0),       # overflowing curve: inf / nan lanes through ToBGR
+    ("cornell", 33, 17, 1, -20.0, 3.0, 1.0, 0, (1, 1, 1), 0.0),
+    ("cornell", 200, 196, 2, 0.0, 0.8, 0.98, 3, (1, 1, 1), 0.3),      # bloom: smallest image its widest box blur fits in
+    ("materials", 256, 200, 1, 1.0, 0.8, 0.98, 3, (1, 1, 1), 0.8),
+]
+
+
+def reference_front_buffer(tmp_path, scene, w, h, passes, exposure, contrast, saturation, tonemapper, filt, bloom):
+    """sum buffer, front buffer, pass script and flat scene of one live run of the reference."""
+    sj = os.path.join(util.GOLDEN, "scenes", scene + ".json")
+    data = os.path.join(util.GOLDEN, "scenes") + "/"
+    dims = 256 if scene == "materials" else 128
+    sump, frontp, passp, flatp = str(tmp_path / "o.sum"), str(tmp_path / "o.front"), str(tmp_path / "o.passes"), str(tmp_path / "o.rtb")
+    util.run_rtref(["render", "--scene", sj, "--data", data, "--width", w, "--height", h, "--passes", passes, "--dims", dims, "--depth", 8,
+                    "--strategy", "all", "--dump-sum", sump, "--dump-passes", passp, "--dump-front", frontp, "--pp-exposure", exposure,
+                    "--pp-contrast", contrast, "--pp-saturation", saturation, "--pp-tonemapper", tonemapper,
+                    "--pp-filter", "%g,%g,%g" % filt, "--pp-bloom", bloom])
+    util.run_rtref(["flat", "--scene", sj, "--data", data, "--width", w, "--height", h, "--out", flatp])
+    return sump, np.fromfile(frontp, dtype=np.uint32).reshape(h, w), passp, flatp
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="prebuilt oracle/_ref/exact did not travel to this box")
+@pytest.mark.parametrize("case", POSTPROCESS_CASES, ids=lambda c: "%s-%dx%d-tm%d-bloom%g-exp%g" % (c[0], c[1], c[2], c[7], c[9], c[4]))
+def test_front_buffer_against_the_live_reference(ctx, tmp_path, case):
+    """Every tone-mapping curve, colour filter / exposure / contrast / saturation extremes and bloom: the 8-bit image
+    equals the reference's Viewport::GetFrontBuffer bit for bit."""
+    scene, w, h, passes, exposure, contrast, saturation, tonemapper, filt, bloom = case
+    sump, want, passp, flatp = reference_front_buffer(tmp_path, *case)
+    sf = capi.SceneFile(flatp)
+    ps = capi.PassScript(passp)
+    ctx.upload_scene(sf)
+    ctx.resize(w, h)
+    cam = capi.camera_for(sf, w, h)
+    for p in range(passes):
+        ctx.render_pass(ctx.make_pass(cam, ps.seeds[p], ps.offsets[p], p))
+    util.assert_bit_identical(ctx.read_sum(), util.load_sum(sump, w, h), "sum buffer")
+    post = capi.postprocess_desc(passes, color_filter=filt, exposure=exposure, contrast=contrast, saturation=saturation, dithering=0.0,
+                                 bloom=bloom, tonemapper=tonemapper)
+    got = ctx.read_front(post)
+    assert np.array_equal(got, want), "%d of %d front-buffer pixels differ" % ((got != want).sum(), want.size)
+    if bloom > 0.0:
+        post.bloomFactor = 0.0
+        assert not np.array_equal(ctx.read_front(post), want), "bloom left the image unchanged"
+
+
+def test_front_buffer_of_gathered_shards_with_bloom(ctx):
+    """The all-gathered film of 4 shards through rtb_read_front equals the single-context front buffer, bloom included
+    (bloom needs the whole image: one shard alone is refused)."""
+    import torch
+    from bench import CudaArray
+
+    sf = capi.SceneFile(util.golden("cornell.rtb"))
+    ps = capi.PassScript(util.golden("cornell.passes"))
+    w, h, passes = 208, 200, 2
+    cam = capi.camera_for(sf, w, h)
+
+    def render(c):
+        c.upload_scene(sf)
+        c.resize(w, h)
+        for p in range(passes):
+            c.render_pass(c.make_pass(cam, ps.seeds[p], ps.offsets[p], p))
+
+    render(ctx)
+    post = capi.postprocess_desc(passes, dithering=0.0, bloom=0.4, exposure=0.5)
+    plain = capi.postprocess_desc(passes, dithering=0.0)
+    want, want_plain = ctx.read_front(post), ctx.read_front(plain)
+    n, parts, ctxs = 4, [], []
+    for s in range(n):
+        c = capi.Context(device=0, num_shards=n, shard_index=s)
+        render(c)
+        c.synchronize()
+        ptr, cnt = c.film_device_buffer(0)
+        parts.append(torch.as_tensor(CudaArray(ptr, cnt), device="cuda").clone())
+        ctxs.append(c)
+    gathered = torch.cat(parts)
+    torch.cuda.synchronize()
+    assert np.array_equal(ctxs[1].read_front(post, gathered.data_ptr()), want)
+    assert np.array_equal(ctxs[2].read_front(plain, gathered.data_ptr()), want_plain)
+    # one shard on its own: its pixels tone-mapped, the others 0
+    own = ctxs[3].read_front(plain)
+    mask = own != 0
+    assert mask.any() and not mask.all() and np.array_equal(own[mask], want_plain[mask])
+    with pytest.raises(capi.RtbError, match="all-gathered"):
+        ctxs[3].read_front(post)
+    for c in ctxs:
+        c.close()
+
+
+def test_front_buffer_dithering_and_errors(ctx):
+    meta, _, _ = render_golden_case(ctx, "cornell", "mis")
+    clean = ctx.read_front(capi.postprocess_desc(meta["passes"], dithering=0.0))
+    noisy = ctx.read_front(capi.postprocess_desc(meta["passes"], dithering=0.005, dither_seed=3))
+    again = ctx.read_front(capi.postprocess_desc(meta["passes"], dithering=0.005, dither_seed=3))
+    other = ctx.read_front(capi.postprocess_desc(meta["passes"], dithering=0.005, dither_seed=4))
+    assert np.array_equal(noisy, again) and not np.array_equal(noisy, other) and not np.array_equal(noisy, clean)
+    for shift in (0, 8, 16):
+        d = ((noisy >> shift) & 255).astype(np.int32) - ((clean >> shift) & 255).astype(np.int32)
+        assert np.abs(d).max() <= 2            # 0.005 * 255 = 1.3 levels either way
+        assert abs(d.mean()) < 0.1             # zero-mean noise
+    assert (noisy >> 24).max() == 0
+    with pytest.raises(capi.RtbError, match="tonemapper"):
+        ctx.read_front(capi.postprocess_desc(4, tonemapper=7))
+    with pytest.raises(capi.RtbError, match="numPasses"):
+        ctx.read_front(capi.postprocess_desc(0))
+    with pytest.raises(capi.RtbError, match="widest box blur"):
+        ctx.read_front(capi.postprocess_desc(4, bloom=0.5))          # 64 x 64 image
+    ctx.resize(202, 200)
+    with pytest.raises(capi.RtbError, match="multiple of 4"):
+        ctx.read_front(capi.postprocess_desc(4, bloom=0.5))

@@ -153,6 +153,55 @@ def test_hostsim_texture_shaped_bokeh(hostsim, tmp_path):
     assert json.loads(r.stdout.strip().splitlines()[-1])["numRays"] == meta["numRays"]
 
 
+def hostsim_front(sump, w, h, passes, out, exposure=0.0, contrast=0.8, saturation=0.98, dither=0.0, tonemapper=3, filt=(1, 1, 1), bloom=0.0):
+    subprocess.run([HOSTSIM, "front", sump, str(w), str(h), str(passes), repr(float(exposure)), repr(float(contrast)), repr(float(saturation)), repr(float(dither)),
+                    str(tonemapper), "%r,%r,%r" % tuple(float(f) for f in filt), out, repr(float(bloom))], check=True)
+    return np.fromfile(out, dtype=np.uint32).reshape(h, w)
+
+
+@pytest.mark.parametrize("scene", ["c1_sphere_area", "cornell", "cornell_dof", "materials", "mesh_small", "textures"])
+def test_hostsim_front_buffer_golden(hostsim, tmp_path, scene):
+    """Viewport::PostProcessTile (Viewport.cpp:492-552) with the default PostprocessParams on the golden sum buffers:
+    the device header's arithmetic gives the reference's 8-bit front buffer."""
+    meta = json.load(open(util.golden(scene + "_mis.json")))
+    w, h = meta["width"], meta["height"]
+    got = hostsim_front(util.golden(scene + "_mis.sum"), w, h, meta["passes"], str(tmp_path / "mine.front"))
+    want = np.fromfile(util.golden(scene + "_mis.front"), dtype=np.uint32).reshape(h, w)
+    assert np.array_equal(got, want), "%d of %d front-buffer pixels differ" % ((got != want).sum(), want.size)
+    assert len(np.unique(want)) > 50 and (want >> 24).max() == 0
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
+@pytest.mark.parametrize("case", [
+    # scene, w, h, passes, exposure, contrast, saturation, tonemapper, filter, bloom
+    ("cornell", 64, 48, 3, 0.0, 0.8, 0.98, 0, (1, 1, 1), 0.0),
+    ("cornell", 64, 48, 3, 0.0, 0.8, 0.98, 1, (1, 1, 1), 0.0),
+    ("cornell", 64, 48, 3, 0.0, 0.8, 0.98, 2, (1, 1, 1), 0.0),
+    ("materials", 64, 48, 3, 1.5, 1.2, 0.3, 3, (0.9, 0.5, 1.25), 0.0),
+    ("textures", 50, 37, 2, -2.0, 0.5, 1.6, 2, (1, 1, 1), 0.0),
+    ("mesh_small", 40, 30, 2, 9.0, 0.8, 1.0, 1, (3, 0, 1e-30), 0.0),
+    ("cornell", 33, 17, 1, 30.0, 40.0, 5.0, 2, (1, 1, 1), 0.0),
+    ("cornell", 33, 17, 1, 30.0, 40.0, 5.0, 3, (1, 1, 1), 0.0),
+    ("cornell", 33, 17, 1, -20.0, 3.0, 1.0, 0, (1, 1, 1), 0.0),
+    ("cornell", 200, 196, 2, 0.0, 0.8, 0.98, 3, (1, 1, 1), 0.3),
+    ("materials", 256, 200, 1, 1.0, 0.8, 0.98, 3, (1, 1, 1), 0.8),
+], ids=lambda c: "%s-%dx%d-tm%d-bloom%g-exp%g" % (c[0], c[1], c[2], c[7], c[9], c[4]))
+def test_hostsim_front_buffer_against_the_live_reference(hostsim, tmp_path, case):
+    """Tone-mapping curves, exposure / contrast / saturation / colour-filter extremes (overflowing lanes included) and
+    bloom (Bitmap::GaussianBlur's running sums, five levels): bit-identical to Viewport::GetFrontBuffer."""
+    scene, w, h, passes, exposure, contrast, saturation, tonemapper, filt, bloom = case
+    scn = os.path.join(util.GOLDEN, "scenes")
+    sump, frontp = str(tmp_path / "o.sum"), str(tmp_path / "o.front")
+    util.run_rtref(["render", "--scene", os.path.join(scn, scene + ".json"), "--data", scn + "/", "--width", w, "--height", h, "--passes", passes,
+                    "--dims", 256, "--depth", 8, "--dump-sum", sump, "--dump-front", frontp, "--pp-exposure", exposure, "--pp-contrast", contrast,
+                    "--pp-saturation", saturation, "--pp-tonemapper", tonemapper, "--pp-filter", "%g,%g,%g" % filt, "--pp-bloom", bloom])
+    want = np.fromfile(frontp, dtype=np.uint32).reshape(h, w)
+    got = hostsim_front(sump, w, h, passes, str(tmp_path / "mine.front"), exposure, contrast, saturation, 0.0, tonemapper, filt, bloom)
+    assert np.array_equal(got, want), "%d of %d front-buffer pixels differ" % ((got != want).sum(), want.size)
+    if bloom > 0.0:
+        assert not np.array_equal(hostsim_front(sump, w, h, passes, str(tmp_path / "nobloom.front"), exposure, contrast, saturation, 0.0, tonemapper, filt), want)
+
+
 @pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
 def test_golden_fixtures_reproduce_from_the_reference(tmp_path):
     """The committed fixtures are what the real reference produces today (pins the oracle: fixed seed, exact math)."""
