@@ -413,6 +413,22 @@ typedef struct RtbPostprocessDesc
  * shard films as for rtb_unshard_film.  Synchronous. */
 int  rtb_read_front(RtbContext* ctx, const RtbPostprocessDesc* post, const void* gatheredDevice, uint32_t* bgra);
 
+/* Adaptive rendering (AdaptiveRenderingSettings, Rendering/Context.h:35-43; Viewport.cpp:552-732).  The block list and its
+ * subdivision policy stay with the caller (host/rt_viewport.h mirrors Viewport::UpdateBlocksList); the device side is the
+ * error estimate of a list of blocks and the restriction of the following passes to a list of tiles. */
+typedef struct RtbBlock { uint32_t minX, maxX, minY, maxY; } RtbBlock;     /* math::Rectangle<uint32>, Viewport.h:64 */
+
+/* errors[i] = Viewport::ComputeBlockError(blocks[i]) (Viewport.cpp:552-582) from sum and secondarySum after `numPasses`
+ * (even) passes; blocks may overlap (ComputeError passes the whole image, Viewport.cpp:179-183).  `gatheredSum` /
+ * `gatheredSum2` NULL: this context's film (numShards must be 1: an estimate sums whole rows of a block), else the
+ * all-gathered films as for rtb_unshard_film.  Synchronous. */
+int  rtb_block_errors(RtbContext* ctx, const void* gatheredSum, const void* gatheredSum2, uint32_t numPasses,
+                      const RtbBlock* blocks, uint32_t numBlocks, float* errors);
+/* The following passes sample only the pixels inside `tiles` (Viewport::GenerateRenderingTiles, Viewport.cpp:584-616 -
+ * the reference renders exactly its tile list, Viewport.cpp:261); the other pixels keep their sums.  tiles == NULL: the
+ * whole image again (also after rtb_resize).  numTiles == 0 with tiles != NULL: nothing is left to render. */
+int  rtb_set_active_tiles(RtbContext* ctx, const RtbBlock* tiles, uint32_t numTiles);
+
 int  rtb_get_counters(RtbContext* ctx, RtbCounters* out);   /* counters of the passes since the last reset */
 
 int  rtb_trace_batch(RtbContext* ctx, const RtbRay* rays, uint64_t n, RtbHit* hits, uint32_t mode);

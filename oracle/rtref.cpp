@@ -434,6 +434,12 @@ RenderingParams MakeParams(const Args& a)
     p.samplingParams.useBlueNoiseDithering = a.Int("blue-noise", 1) != 0;
     p.lightSamplingStrategy = a.Str("strategy", "all") == "single" ? LightSamplingStrategy::Single : LightSamplingStrategy::All;
     p.antiAliasingSpread = (float)a.Dbl("aa-spread", 0.5);
+    p.adaptiveSettings.enable = a.Int("adaptive", 0) != 0;
+    p.adaptiveSettings.numInitialPasses = (uint32)a.Int("adaptive-initial", p.adaptiveSettings.numInitialPasses);
+    p.adaptiveSettings.minBlockSize = (uint32)a.Int("adaptive-min-block", p.adaptiveSettings.minBlockSize);
+    p.adaptiveSettings.maxBlockSize = (uint32)a.Int("adaptive-max-block", p.adaptiveSettings.maxBlockSize);
+    p.adaptiveSettings.subdivisionTreshold = (float)a.Dbl("adaptive-subdivision", p.adaptiveSettings.subdivisionTreshold);
+    p.adaptiveSettings.convergenceTreshold = (float)a.Dbl("adaptive-convergence", p.adaptiveSettings.convergenceTreshold);
     return p;
 }
 
@@ -472,6 +478,9 @@ int CmdRender(const Args& a)
     }
     vp.Reset();
 
+    // --dump-progress: after every Render(): RenderingProgress (Viewport.h:25-32) + the block list (Viewport.h:126)
+    std::vector<math::Rectangle<uint32>> previousBlocks(vp.mBlocks.begin(), vp.mBlocks.end());
+    FILE* progress = a.Has("dump-progress") ? fopen(a.Str("dump-progress").c_str(), "wb") : nullptr;
     FILE* script = a.Has("dump-passes") ? fopen(a.Str("dump-passes").c_str(), "wb") : nullptr;
     if (script) { WriteU32(script, passes); WriteU32(script, params.samplingParams.dimensions); }
 
@@ -496,6 +505,20 @@ int CmdRender(const Args& a)
             WritePod(script, sampleOffset.x);
             WritePod(script, sampleOffset.y);
         }
+        if (progress)
+        {
+            const RenderingProgress& pr = vp.GetProgress();
+            WriteU32(progress, pr.passesFinished); WriteU32(progress, pr.activePixels); WriteU32(progress, pr.activeBlocks);
+            WritePod(progress, pr.converged); WritePod(progress, pr.averageError);
+            WriteU32(progress, vp.mBlocks.Size());
+            for (const auto& b : vp.mBlocks) { WriteU32(progress, b.minX); WriteU32(progress, b.maxX); WriteU32(progress, b.minY); WriteU32(progress, b.maxY); }
+            // what Viewport::UpdateBlocksList saw inside this Render(): the film is as it was then, the blocks are those
+            // of the previous pass -> their ComputeBlockError values (only defined after an even number of passes)
+            const bool even = pr.passesFinished > 0 && pr.passesFinished % 2 == 0;
+            WriteU32(progress, even ? (uint32)previousBlocks.size() : 0u);
+            if (even) for (const auto& b : previousBlocks) WritePod(progress, vp.ComputeBlockError(b));
+            previousBlocks.assign(vp.mBlocks.begin(), vp.mBlocks.end());
+        }
         if (i >= warmup)
         {
             seconds += dt;
@@ -504,11 +527,26 @@ int CmdRender(const Args& a)
         }
     }
     if (script) fclose(script);
+    if (progress) fclose(progress);
 
     if (a.Has("dump-sum"))
     {
         FILE* f = fopen(a.Str("dump-sum").c_str(), "wb");
         WriteBytes(f, vp.GetSumBuffer().GetData(), (size_t)w * h * 12);
+        fclose(f);
+    }
+    if (a.Has("block-errors"))
+    {
+        // --block-errors blocks.bin (u32 minX, maxX, minY, maxY each) --dump-block-errors out.f32: Viewport::ComputeBlockError
+        FILE* f = fopen(a.Str("block-errors").c_str(), "rb");
+        if (!f) Die("cannot open --block-errors");
+        uint32 r[4];
+        std::vector<float> errors;
+        while (fread(r, 4, 4, f) == 4) errors.push_back(vp.ComputeBlockError(math::Rectangle<uint32>(r[0], r[1], r[2], r[3])));
+        fclose(f);
+        f = fopen(a.Str("dump-block-errors").c_str(), "wb");
+        if (!f) Die("cannot open --dump-block-errors");
+        WriteBytes(f, errors.data(), errors.size() * 4);
         fclose(f);
     }
     if (a.Has("dump-front"))

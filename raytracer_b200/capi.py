@@ -147,7 +147,7 @@ EXPORTED_SYMBOLS = [
     "rtb_last_error", "rtb_api_version", "rtb_create", "rtb_destroy", "rtb_upload_scene", "rtb_set_blue_noise",
     "rtb_resize", "rtb_reset", "rtb_render_pass", "rtb_render_passes", "rtb_synchronize", "rtb_join", "rtb_read_sum", "rtb_film_device_buffer", "rtb_film_snapshots",
     "rtb_unshard_film", "rtb_read_sum_async", "rtb_unshard_film_async", "rtb_host_alloc", "rtb_host_free", "rtb_get_counters", "rtb_trace_batch", "rtb_trace_batch_device", "rtb_texture_batch", "rtb_sample_batch",
-    "rtb_primary_rays", "rtb_set_profiling", "rtb_get_pass_timings", "rtb_read_front",
+    "rtb_primary_rays", "rtb_set_profiling", "rtb_get_pass_timings", "rtb_read_front", "rtb_block_errors", "rtb_set_active_tiles",
 ]
 
 _lib = None
@@ -194,6 +194,8 @@ def load_library(path=None):
     lib.rtb_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
     lib.rtb_trace_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
     lib.rtb_texture_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.rtb_block_errors.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+    lib.rtb_set_active_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     lib.rtb_read_front.argtypes = [C.c_void_p, C.POINTER(RtbPostprocessDesc), C.c_void_p, C.c_void_p]
     lib.rtb_sample_batch.argtypes = [C.c_void_p, C.POINTER(RtbPassDesc), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
     lib.rtb_primary_rays.argtypes = [C.c_void_p, C.POINTER(RtbPassDesc), C.c_void_p]
@@ -423,6 +425,22 @@ class Context:
             out = np.empty((self.height, self.width, 3), dtype=np.float32)
         _check(self.lib, self.lib.rtb_read_sum(self.h, out.ctypes.data, which))
         return out
+
+    def block_errors(self, num_passes, blocks, gathered_sum=None, gathered_sum2=None):
+        """rtb_block_errors: Viewport::ComputeBlockError of each (minX, maxX, minY, maxY) row -> float32 array."""
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint32).reshape(-1, 4)
+        out = np.zeros(len(blocks), dtype=np.float32)
+        _check(self.lib, self.lib.rtb_block_errors(self.h, gathered_sum, gathered_sum2, num_passes, blocks.ctypes.data, len(blocks), out.ctypes.data))
+        return out
+
+    def set_active_tiles(self, tiles):
+        """rtb_set_active_tiles: None = whole image; else (n, 4) uint32 rows minX, maxX, minY, maxY (n may be 0)."""
+        if tiles is None:
+            _check(self.lib, self.lib.rtb_set_active_tiles(self.h, None, 0))
+            return
+        tiles = np.ascontiguousarray(tiles, dtype=np.uint32).reshape(-1, 4)
+        keep = tiles if len(tiles) else np.zeros((1, 4), dtype=np.uint32)       # a non-null pointer even for an empty list
+        _check(self.lib, self.lib.rtb_set_active_tiles(self.h, keep.ctypes.data, len(tiles)))
 
     def read_front(self, post, gathered_device_ptr=None):
         """rtb_read_front: Viewport::GetFrontBuffer - (height, width) uint32 0x00RRGGBB."""

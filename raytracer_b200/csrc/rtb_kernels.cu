@@ -74,6 +74,8 @@ struct Totals
     unsigned long long numRays, numShadowRays, numShadowRaysHit, numBoxTests, numTriTests, numShadowBoxTests, numShadowTriTests;
 };
 
+#define RTB_ALL_ACTIVE 0xFFFFFFFFu
+
 struct Wavefront
 {
     PathBuf  buf[2];
@@ -97,6 +99,9 @@ struct Wavefront
     uint32_t tailThreshold;      // k_tail takes over when at most this many paths are left (0 = never)
     uint32_t batch;              // passes in flight in this wavefront (pass slot b uses passColor[b * numPixels + pixel])
     uint32_t firstPassIndex;     // Viewport pass index of pass slot 0
+    // adaptive rendering (rtb_set_active_tiles): only these pixel slots get a sample in this wavefront
+    const uint32_t* activeList;
+    uint32_t numActive;          // RTB_ALL_ACTIVE: every slot, activeList unused
 };
 
 __device__ __forceinline__ void store_path(const PathBuf& b, uint32_t i, const PathState& ps)
@@ -165,7 +170,9 @@ __device__ __forceinline__ void load_path(const PathBuf& b, uint32_t i, const Wa
 __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const __grid_constant__ Wavefront W)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t total = W.numPixels * W.batch;
+    const bool allActive = W.numActive == RTB_ALL_ACTIVE;
+    const uint32_t perPass = allActive ? W.numPixels : W.numActive;
+    const uint32_t total = perPass * W.batch;
     if (blockIdx.x == 0)
     {
         // queue counters of this wavefront (the kernels that read them are launched after this one on the same stream)
@@ -175,13 +182,14 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ SceneVie
     }
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
     {
-        const uint32_t passSlot = i / W.numPixels, slot = i - passSlot * W.numPixels;
+        const uint32_t passSlot = i / perPass, a = i - passSlot * perPass;
+        const uint32_t slot = allActive ? a : W.activeList[a];
         const uint32_t pix = W.pixelList[slot];
         PathState ps;
         init_path(P, S.blueNoise, pix % P.width, pix / P.width, passSlot, ps);
         ps.pixel = slot;
         store_path(W.buf[0], i, ps);
-        W.passColor[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        W.passColor[passSlot * W.numPixels + slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);      // (inactive slots: zeroed by the host's memset)
     }
 }
 
@@ -563,9 +571,10 @@ __global__ void __launch_bounds__(256) k_unshard(const float* __restrict__ src, 
 }
 
 // front buffer (Viewport::PostProcessTile): pixel slots -> tone-mapped 0x00RRGGBB in raster order; `blurred` (the
-// RTB_BLOOM_LEVELS blurred raster images back to back) is only read when P.bloomFactor > 0
+// RTB_BLOOM_LEVELS blurred raster images back to back) is only read when P.bloomFactor > 0; `frozenRaster` (optional):
+// per raster pixel, the pass count at which adaptive rendering dropped it (0 = still sampled)
 __global__ void __launch_bounds__(256) k_front(const float* __restrict__ src, uint32_t* __restrict__ dstRaster, const uint32_t* __restrict__ pixelListAll, uint32_t total,
-                                               const float* __restrict__ blurred, size_t levelStride, const PostParams P)
+                                               const float* __restrict__ blurred, size_t levelStride, const uint32_t* __restrict__ frozenRaster, const PostParams P)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
@@ -575,7 +584,10 @@ __global__ void __launch_bounds__(256) k_front(const float* __restrict__ src, ui
         const V3 sum = v3(src[(size_t)i * 3 + 0], src[(size_t)i * 3 + 1], src[(size_t)i * 3 + 2]);
         V3 bloom = v3s(0.0f);
         if (P.bloomFactor > 0.0f) bloom = bloom_color(blurred, levelStride, pix);
-        dstRaster[pix] = postprocess_pixel(P, sum, bloom, pix);
+        // a pixel adaptive rendering stopped sampling after n passes holds the sum of n passes (the reference keeps the
+        // front-buffer value it had then: Viewport.cpp:474-485 post-processes the active tiles only)
+        const uint32_t frozen = frozenRaster ? frozenRaster[pix] : 0u;
+        dstRaster[pix] = postprocess_pixel(P, sum, bloom, pix, frozen ? fdiv(1.0f, (float)frozen) : P.pixelScaling);
     }
 }
 
@@ -593,6 +605,38 @@ __global__ void __launch_bounds__(128) k_blur(const float* in, float* out, uint3
     const size_t elementStride = vertical ? (size_t)width * 3 : 3;
     blur_line(in + first, out + first, elementStride, scratchA + t, scratchB + t, (size_t)numLines * 3,
               schedule, vertical ? RTB_BLUR_KEPT_VERTICAL : RTB_BLUR_KEPT_HORIZONTAL, vertical ? height : width);
+}
+
+// Viewport::ComputeBlockError in three steps (rtb_postprocess.h): per-pixel estimates (parallel), row sums of every
+// block (one thread per block row, left to right), block sums (one thread per block, top to bottom)
+__global__ void __launch_bounds__(256) k_pixel_error(const float* __restrict__ sumRaster, const float* __restrict__ sum2Raster, uint32_t numPixels, float scale, float* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numPixels) return;
+    out[i] = pixel_error(v3(sumRaster[3 * (size_t)i], sumRaster[3 * (size_t)i + 1], sumRaster[3 * (size_t)i + 2]),
+                         v3(sum2Raster[3 * (size_t)i], sum2Raster[3 * (size_t)i + 1], sum2Raster[3 * (size_t)i + 2]), scale);
+}
+
+// rowStart[b] = index of block b's first row in rowErrors (rowStart[numBlocks] = total)
+__global__ void __launch_bounds__(128) k_row_error(const float* __restrict__ pixelErrors, uint32_t width, const RtbBlock* __restrict__ blocks, const uint32_t* __restrict__ rowStart,
+                                                   uint32_t numBlocks, float* __restrict__ rowErrors)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rowStart[numBlocks]) return;
+    uint32_t lo = 0, hi = numBlocks;                 // last block whose first row is <= t
+    while (hi - lo > 1u) { const uint32_t mid = (lo + hi) / 2u; if (rowStart[mid] <= t) lo = mid; else hi = mid; }
+    const RtbBlock b = blocks[lo];
+    const uint32_t y = b.minY + (t - rowStart[lo]);
+    rowErrors[t] = row_error(pixelErrors + (size_t)y * width, b.minX, b.maxX);
+}
+
+__global__ void __launch_bounds__(128) k_block_error(const float* __restrict__ rowErrors, const RtbBlock* __restrict__ blocks, const uint32_t* __restrict__ rowStart,
+                                                     uint32_t numBlocks, uint32_t totalArea, float* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numBlocks) return;
+    const RtbBlock b = blocks[i];
+    out[i] = block_error(rowErrors + rowStart[i], b.maxY - b.minY, b.maxX - b.minX, totalArea);
 }
 
 // test hooks ------------------------------------------------------------------------------------------------------------
@@ -757,6 +801,15 @@ struct RtbContext
     uint32_t maxBatch = 1;         // passes per wavefront (sized at resize so that a wavefront has a few million paths)
     DevArray<uint32_t> pixelList;     // this shard
     DevArray<uint32_t> pixelListAll;  // all shards back to back, padded with 0xFFFFFFFF
+    std::vector<uint32_t> hostPixelList;   // this shard's list, kept for rtb_set_active_tiles
+    DevArray<uint32_t> activeList;    // adaptive rendering: the pixel slots that still get samples ...
+    uint32_t numActive = 0;
+    bool hasActiveList = false;       // ... when set (rtb_set_active_tiles); otherwise every pixel
+    std::vector<uint32_t> hostFrozen; // per raster pixel: passesSinceReset when it left the active set (0 = active); the same on every shard
+    DevArray<uint32_t> frozen;
+    bool frozenDirty = false;
+    DevArray<float> raster2, pixelError, rowError;   // rtb_block_errors scratch
+    DevArray<uint32_t> blockRows;
     DevArray<float> sum, sum2;
     DevArray<float> raster;           // scratch for read-back
     DevArray<uint32_t> front;         // tone-mapped front buffer (rtb_read_front), allocated on first use
@@ -827,7 +880,7 @@ static void free_scene(RtbContext* c)
 
 static void free_film(RtbContext* c)
 {
-    c->pixelList.release(); c->pixelListAll.release(); c->sum.release(); c->sum2.release(); c->raster.release(); c->front.release(); c->blurred.release(); c->blurScratch.release();
+    c->pixelList.release(); c->pixelListAll.release(); c->sum.release(); c->sum2.release(); c->raster.release(); c->activeList.release(); c->hasActiveList = false; c->frozen.release(); c->hostFrozen.clear(); c->raster2.release(); c->pixelError.release(); c->rowError.release(); c->blockRows.release(); c->front.release(); c->blurred.release(); c->blurScratch.release();
     for (int i = 0; i < RTB_SNAP_RING; ++i) c->rasterAsync[i].release();
     c->snapshots.release(); c->snapshotCapacity = 0;
     for (RtbContext::Slot& t : c->slots)
@@ -889,6 +942,7 @@ static void fill_wavefront(RtbContext* c)
         w.pixelList = c->pixelList.ptr;
         w.numPixels = c->numPixels;
         w.raysPerPath = c->raysPerPath;
+        w.activeList = nullptr; w.numActive = RTB_ALL_ACTIVE;
     }
 }
 
@@ -1118,6 +1172,7 @@ int rtb_resize(RtbContext* c, uint32_t width, uint32_t height)
     c->numPixels = (uint32_t)lists[c->shardIndex].size();
     std::vector<uint32_t> all((size_t)c->numShards * maxSlots, 0xFFFFFFFFu);
     for (uint32_t s = 0; s < c->numShards; ++s) memcpy(&all[(size_t)s * maxSlots], lists[s].data(), lists[s].size() * 4);
+    c->hostPixelList = lists[c->shardIndex];
     RTB_CUDA(c->pixelList.upload(lists[c->shardIndex], c->stream));
     RTB_CUDA(c->pixelListAll.upload(all, c->stream));
     RTB_CUDA(cudaStreamSynchronize(c->stream));
@@ -1165,6 +1220,7 @@ int rtb_reset(RtbContext* c)
     c->slotsNeedMain = true;
     memset(&c->counters, 0, sizeof(c->counters));
     c->passesSinceReset = 0;
+    c->hasActiveList = false; c->numActive = 0; c->hostFrozen.clear();      // Viewport::Reset -> BuildInitialBlocksList: everything active again
     return RTB_OK;
 }
 
@@ -1255,7 +1311,14 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
     Wavefront W = slot.wf;
     W.batch = batch;
     W.firstPassIndex = pass->passIndex;
-    const uint32_t numPaths = c->numPixels * batch;
+    const uint32_t perPass = c->hasActiveList ? c->numActive : c->numPixels;
+    const uint32_t numPaths = perPass * batch;
+    if (c->hasActiveList)
+    {
+        // the pixels outside the active tiles receive nothing from these passes (Viewport::RenderTile is not called for them)
+        W.activeList = c->activeList.ptr; W.numActive = c->numActive;
+        RTB_CUDA(cudaMemsetAsync(W.passColor, 0, (size_t)c->numPixels * batch * sizeof(float4), s));
+    }
 
     const bool count = (c->flags & RTB_FLAG_COUNT_TESTS) != 0;
     // (k_raygen initialises the queue counters of this wavefront)
@@ -1275,7 +1338,7 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
     if (prof) marks.push_back(next_event(c, ev, s));
     k_raygen<<<blocks256, 256, 0, s>>>(c->view, P, W);
     if (prof) marks.push_back(next_event(c, ev, s));
-    const uint32_t depthLimit = pass->renderer == RTB_RENDERER_DEBUG ? 0u : pass->maxRayDepth;
+    const uint32_t depthLimit = pass->renderer == RTB_RENDERER_DEBUG ? 0u : (numPaths ? pass->maxRayDepth : 0u);
     const bool shadows = pass->renderer == RTB_RENDERER_PATH_TRACER_MIS && c->numLights > 0;
     const bool textured = c->textures.count > 0;     // scenes without textures run the k_shade that has no texture calls compiled in
     for (uint32_t d = 0; d <= depthLimit; ++d)
@@ -1320,7 +1383,7 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
     c->lastFilm = slot.filmDone;
     if (prof) marks.push_back(next_event(c, ev, s));
     RTB_CUDA(cudaGetLastError());
-    c->counters.numPrimaryRays += (uint64_t)c->numPixels * batch;     // Viewport.cpp:429
+    c->counters.numPrimaryRays += (uint64_t)perPass * batch;          // Viewport.cpp:429
     c->counters.numKernelLaunches += 2u + (depthLimit + 1u) * (shadows ? 4u : 2u);
     c->passesSinceReset += batch;
 
@@ -1597,6 +1660,16 @@ int rtb_read_front(RtbContext* c, const RtbPostprocessDesc* post, const void* ga
 
     const float* src = gatheredDevice ? (const float*)gatheredDevice : c->sum.ptr;
     const size_t levelStride = n * 3;
+    const uint32_t* frozen = nullptr;
+    if (c->hasActiveList)
+    {
+        if (c->frozenDirty)
+        {
+            RTB_CUDA(c->frozen.upload(c->hostFrozen, c->stream));
+            c->frozenDirty = false;
+        }
+        frozen = c->frozen.ptr;
+    }
     if (bloom)
     {
         // Viewport::PerformPostProcess (Viewport.cpp:434-445): level 0 = blur(sum), level i = blur(level i - 1)
@@ -1614,21 +1687,113 @@ int rtb_read_front(RtbContext* c, const RtbPostprocessDesc* post, const void* ga
     }
     if (gatheredDevice)
     {
-        k_front<<<c->numSMs * 4, 256, 0, c->stream>>>(src, c->front.ptr, c->pixelListAll.ptr, c->numShards * c->shardSlots, c->blurred.ptr, levelStride, P);
+        k_front<<<c->numSMs * 4, 256, 0, c->stream>>>(src, c->front.ptr, c->pixelListAll.ptr, c->numShards * c->shardSlots, c->blurred.ptr, levelStride, frozen, P);
     }
     else if (c->numShards > 1)
     {
         RTB_CUDA(cudaMemsetAsync(c->front.ptr, 0, n * sizeof(uint32_t), c->stream));
-        k_front<<<c->numSMs * 4, 256, 0, c->stream>>>(src, c->front.ptr, c->pixelList.ptr, c->numPixels, c->blurred.ptr, levelStride, P);
+        k_front<<<c->numSMs * 4, 256, 0, c->stream>>>(src, c->front.ptr, c->pixelList.ptr, c->numPixels, c->blurred.ptr, levelStride, frozen, P);
     }
     else
     {
-        k_front<<<c->numSMs * 4, 256, 0, c->stream>>>(src, c->front.ptr, c->pixelListAll.ptr, c->shardSlots, c->blurred.ptr, levelStride, P);
+        k_front<<<c->numSMs * 4, 256, 0, c->stream>>>(src, c->front.ptr, c->pixelListAll.ptr, c->shardSlots, c->blurred.ptr, levelStride, frozen, P);
     }
     RTB_CUDA(cudaGetLastError());
     c->counters.numKernelLaunches++;
     RTB_CUDA(cudaMemcpyAsync(bgra, c->front.ptr, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     RTB_CUDA(cudaStreamSynchronize(c->stream));
+    return RTB_OK;
+}
+
+int rtb_block_errors(RtbContext* c, const void* gatheredSum, const void* gatheredSum2, uint32_t numPasses, const RtbBlock* blocks, uint32_t numBlocks, float* errors)
+{
+    if (!c || (numBlocks && (!blocks || !errors))) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    if (!c->sum.ptr) return fail(RTB_ERR_INVALID_ARG, "viewport has no size");
+    if ((gatheredSum == nullptr) != (gatheredSum2 == nullptr)) return fail(RTB_ERR_INVALID_ARG, "pass both gathered films or neither");
+    if (c->numShards > 1 && !gatheredSum) return fail(RTB_ERR_UNSUPPORTED, "a block error sums whole rows of the image: pass the all-gathered films");
+    if (numPasses == 0 || (numPasses & 1u)) return fail(RTB_ERR_INVALID_ARG, "block errors compare all passes with the even ones: numPasses must be even and > 0 (Viewport.cpp:559)");
+    if (numBlocks == 0) return RTB_OK;
+    std::vector<uint32_t> rowStart(numBlocks + 1, 0u);
+    for (uint32_t i = 0; i < numBlocks; ++i)
+    {
+        const RtbBlock& b = blocks[i];
+        if (b.minX >= b.maxX || b.minY >= b.maxY || b.maxX > c->width || b.maxY > c->height)
+            return fail(RTB_ERR_INVALID_ARG, "block %u [%u, %u) x [%u, %u) is empty or outside the %u x %u image", i, b.minX, b.maxX, b.minY, b.maxY, c->width, c->height);
+        const uint64_t next = (uint64_t)rowStart[i] + (b.maxY - b.minY);
+        if (next > 0xFFFFFFFFull) return fail(RTB_ERR_INVALID_ARG, "too many block rows");
+        rowStart[i + 1] = (uint32_t)next;
+    }
+    RTB_CUDA(cudaSetDevice(c->device));
+    RTB_CUDA(join_slots(c));
+    const size_t n = (size_t)c->width * c->height;
+    if (c->raster2.count != n * 3) RTB_CUDA(c->raster2.alloc(n * 3));
+    if (c->pixelError.count != n) RTB_CUDA(c->pixelError.alloc(n));
+    if (c->rowError.count < rowStart[numBlocks] + (size_t)numBlocks) RTB_CUDA(c->rowError.alloc(rowStart[numBlocks] + (size_t)numBlocks));
+    // blocks and row offsets in one upload: [numBlocks x RtbBlock][numBlocks + 1 offsets]
+    std::vector<uint32_t> staging((size_t)numBlocks * 4 + numBlocks + 1);
+    memcpy(staging.data(), blocks, (size_t)numBlocks * sizeof(RtbBlock));
+    memcpy(staging.data() + (size_t)numBlocks * 4, rowStart.data(), rowStart.size() * sizeof(uint32_t));
+    if (c->blockRows.count < staging.size()) RTB_CUDA(c->blockRows.alloc(staging.size()));
+    RTB_CUDA(cudaMemcpyAsync(c->blockRows.ptr, staging.data(), staging.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    const RtbBlock* dBlocks = reinterpret_cast<const RtbBlock*>(c->blockRows.ptr);
+    const uint32_t* dRowStart = c->blockRows.ptr + (size_t)numBlocks * 4;
+
+    const uint32_t slots = c->numShards * c->shardSlots;
+    k_unshard<<<c->numSMs * 4, 256, 0, c->stream>>>(gatheredSum ? (const float*)gatheredSum : c->sum.ptr, c->raster.ptr, c->pixelListAll.ptr, slots);
+    k_unshard<<<c->numSMs * 4, 256, 0, c->stream>>>(gatheredSum2 ? (const float*)gatheredSum2 : c->sum2.ptr, c->raster2.ptr, c->pixelListAll.ptr, slots);
+    k_pixel_error<<<(uint32_t)((n + 255) / 256), 256, 0, c->stream>>>(c->raster.ptr, c->raster2.ptr, (uint32_t)n, 1.0f / (float)numPasses, c->pixelError.ptr);
+    k_row_error<<<(rowStart[numBlocks] + 127) / 128, 128, 0, c->stream>>>(c->pixelError.ptr, c->width, dBlocks, dRowStart, numBlocks, c->rowError.ptr);
+    float* dErrors = c->rowError.ptr + rowStart[numBlocks];
+    k_block_error<<<(numBlocks + 127) / 128, 128, 0, c->stream>>>(c->rowError.ptr, dBlocks, dRowStart, numBlocks, c->width * c->height, dErrors);
+    RTB_CUDA(cudaGetLastError());
+    c->counters.numKernelLaunches += 5;
+    RTB_CUDA(cudaMemcpyAsync(errors, dErrors, (size_t)numBlocks * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    RTB_CUDA(cudaStreamSynchronize(c->stream));
+    return RTB_OK;
+}
+
+int rtb_set_active_tiles(RtbContext* c, const RtbBlock* tiles, uint32_t numTiles)
+{
+    if (!c) return fail(RTB_ERR_INVALID_ARG, "null context");
+    if (!c->sum.ptr) return fail(RTB_ERR_INVALID_ARG, "viewport has no size");
+    RTB_CUDA(cudaSetDevice(c->device));
+    if (!tiles)
+    {
+        c->hasActiveList = false; c->numActive = 0; c->hostFrozen.clear();
+        return RTB_OK;
+    }
+    std::vector<uint8_t> mask((size_t)c->width * c->height, 0);
+    for (uint32_t i = 0; i < numTiles; ++i)
+    {
+        const RtbBlock& b = tiles[i];
+        if (b.minX >= b.maxX || b.minY >= b.maxY || b.maxX > c->width || b.maxY > c->height)
+            return fail(RTB_ERR_INVALID_ARG, "tile %u [%u, %u) x [%u, %u) is empty or outside the %u x %u image", i, b.minX, b.maxX, b.minY, b.maxY, c->width, c->height);
+        for (uint32_t y = b.minY; y < b.maxY; ++y)
+            for (uint32_t x = b.minX; x < b.maxX; ++x)
+            {
+                // a pixel in two tiles would get two samples per pass from the reference; its block lists never overlap
+                if (mask[(size_t)y * c->width + x]) return fail(RTB_ERR_INVALID_ARG, "tile %u overlaps an earlier tile at pixel (%u, %u)", i, x, y);
+                mask[(size_t)y * c->width + x] = 1;
+            }
+    }
+    // pixels that leave the active set now hold the sum of the passes rendered so far (every shard records the same)
+    if (c->hostFrozen.size() != mask.size()) c->hostFrozen.assign(mask.size(), 0u);
+    for (size_t p = 0; p < mask.size(); ++p)
+    {
+        if (mask[p]) c->hostFrozen[p] = 0u;
+        else if (c->hostFrozen[p] == 0u) c->hostFrozen[p] = c->passesSinceReset;
+    }
+    c->frozenDirty = true;
+    // this shard's active pixel slots, in slot order (neighbouring paths stay neighbouring pixels)
+    std::vector<uint32_t> active;
+    active.reserve(c->hostPixelList.size());
+    for (uint32_t slot = 0; slot < (uint32_t)c->hostPixelList.size(); ++slot) if (mask[c->hostPixelList[slot]]) active.push_back(slot);
+    RTB_CUDA(sync_all(c));        // wavefronts in flight still read the previous list
+    if (!active.empty()) RTB_CUDA(c->activeList.upload(active, c->stream));
+    RTB_CUDA(cudaStreamSynchronize(c->stream));
+    c->numActive = (uint32_t)active.size();
+    c->hasActiveList = true;
+    c->slotsNeedMain = true;
     return RTB_OK;
 }
 

@@ -207,9 +207,37 @@ RTB_HD V3 bloom_color(const float* blurred, const size_t levelStride, const size
     return b;
 }
 
+// ---- adaptive rendering: Viewport::ComputeBlockError (Viewport.cpp:552-582) ----------------------------------------
+
+// the error estimate of one pixel: |image - image of the even passes| weighted (1, 2, 1), relative to the brightness
+RTB_HD float pixel_error(const V3& sum, const V3& secondarySum, const float imageScalingFactor)
+{
+    const V3 a = sum * imageScalingFactor;
+    const V3 b = secondarySum * (2.0f * imageScalingFactor);
+    const V3 diff = v3(bit_abs(a.x - b.x), bit_abs(a.y - b.y), bit_abs(a.z - b.z));
+    return fdiv(diff.x + 2.0f * diff.y + diff.z, sqrtf(0.000001f + a.x + 2.0f * a.y + a.z));
+}
+
+// the reference adds the pixel errors of a block row from left to right, then the row sums from top to bottom
+RTB_HD float row_error(const float* pixelErrors, const uint32_t minX, const uint32_t maxX)
+{
+    float rowError = 0.0f;
+    for (uint32_t x = minX; x < maxX; ++x) rowError += pixelErrors[x];
+    return rowError;
+}
+
+RTB_HD float block_error(const float* rowErrors, const uint32_t numRows, const uint32_t blockWidth, const uint32_t totalArea)
+{
+    float totalError = 0.0f;
+    for (uint32_t y = 0; y < numRows; ++y) totalError += rowErrors[y];
+    const uint32_t blockArea = blockWidth * numRows;
+    return fdiv(totalError * sqrtf(fdiv((float)blockArea, (float)totalArea)), (float)blockArea);
+}
+
 // `sum` = the film's accumulated colour; `bloom` = sum of the weighted blurred images (Viewport.cpp:517-523), unused
-// when bloomFactor == 0.  Returns 0x00RRGGBB.
-RTB_HD uint32_t postprocess_pixel(const PostParams& P, V3 sum, const V3& bloom, uint32_t pixel)
+// when bloomFactor == 0; `pixelScaling` = 1 / the passes this pixel has received (P.pixelScaling unless adaptive
+// rendering stopped sampling it earlier).  Returns 0x00RRGGBB.
+RTB_HD uint32_t postprocess_pixel(const PostParams& P, V3 sum, const V3& bloom, uint32_t pixel, float pixelScaling)
 {
     V3 c = sum;
     if (P.bloomFactor > 0.0f)
@@ -217,7 +245,7 @@ RTB_HD uint32_t postprocess_pixel(const PostParams& P, V3 sum, const V3& bloom, 
         c = c * (1.0f - P.bloomFactor);
         c = mul_add(bloom, P.bloomFactor, c);
     }
-    c = c * P.pixelScaling;
+    c = c * pixelScaling;
 
     const float gray = dot3(c, v3(0.2126f, 0.7152f, 0.0722f));
     c = v3(sse_max(0.0f, fma_(c.x - gray, P.saturation, gray)),

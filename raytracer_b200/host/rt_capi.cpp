@@ -82,12 +82,54 @@ int rtbh_viewport_set_renderer(void* vp, const char* name, uint32_t debugMode)
 int rtbh_viewport_set_params(void* vp, uint32_t dimensions, uint32_t useBlueNoise, float aaSpread, uint32_t maxRayDepth, uint32_t minRRDepth, uint32_t strategy, uint64_t seed)
 {
     rt::ViewportB200* v = static_cast<rt::ViewportB200*>(vp);
-    rt::RenderingParams p;
+    rt::RenderingParams p = v->GetRenderingParams();
     p.dimensions = dimensions; p.useBlueNoiseDithering = useBlueNoise != 0; p.antiAliasingSpread = aaSpread;
     p.maxRayDepth = maxRayDepth; p.minRussianRouletteDepth = minRRDepth; p.lightSamplingStrategy = strategy;
     v->SetRenderingParams(p);
     v->SetSeed(seed);
     return 0;
+}
+
+// AdaptiveRenderingSettings (Context.h:35-43); takes effect at the next Reset / Resize like the reference's
+int rtbh_viewport_set_adaptive(void* vp, uint32_t enable, uint32_t numInitialPasses, uint32_t minBlockSize, uint32_t maxBlockSize, float subdivisionTreshold, float convergenceTreshold)
+{
+    rt::ViewportB200* v = static_cast<rt::ViewportB200*>(vp);
+    rt::RenderingParams p = v->GetRenderingParams();
+    p.adaptiveSettings.enable = enable != 0; p.adaptiveSettings.numInitialPasses = numInitialPasses;
+    p.adaptiveSettings.minBlockSize = minBlockSize; p.adaptiveSettings.maxBlockSize = maxBlockSize;
+    p.adaptiveSettings.subdivisionTreshold = subdivisionTreshold; p.adaptiveSettings.convergenceTreshold = convergenceTreshold;
+    v->SetRenderingParams(p);
+    return 0;
+}
+
+// Viewport::GetProgress; out5 = passesFinished, activePixels, activeBlocks, converged (float bits), averageError (float bits)
+int rtbh_viewport_progress(void* vp, uint32_t* out5)
+{
+    rt::RenderingProgress pr;
+    if (!static_cast<rt::ViewportB200*>(vp)->GetProgress(pr)) return -1;
+    out5[0] = pr.passesFinished; out5[1] = pr.activePixels; out5[2] = pr.activeBlocks;
+    memcpy(&out5[3], &pr.converged, 4); memcpy(&out5[4], &pr.averageError, 4);
+    return 0;
+}
+
+// the block list (Viewport::mBlocks): returns the number of blocks, copies at most `capacity`
+uint32_t rtbh_viewport_blocks(void* vp, RtbBlock* out, uint32_t capacity)
+{
+    const std::vector<RtbBlock>& b = static_cast<rt::ViewportB200*>(vp)->GetBlocks();
+    for (uint32_t i = 0; i < b.size() && i < capacity; ++i) out[i] = b[i];
+    return (uint32_t)b.size();
+}
+
+// ViewportB200::ReviseBlocks on caller data (no device): blocks[0..n) + errors[0..n) in, the revised list out (at most
+// `capacity` entries are written; a revision at most doubles the list); returns its length
+uint32_t rtbh_revise_blocks(RtbBlock* blocks, uint32_t n, uint32_t capacity, const float* errors, uint32_t minBlockSize, float subdivisionTreshold, float convergenceTreshold)
+{
+    rt::AdaptiveRenderingSettings settings;
+    settings.minBlockSize = minBlockSize; settings.subdivisionTreshold = subdivisionTreshold; settings.convergenceTreshold = convergenceTreshold;
+    std::vector<RtbBlock> list(blocks, blocks + n);
+    rt::ViewportB200::ReviseBlocks(list, std::vector<float>(errors, errors + n), settings);
+    for (uint32_t i = 0; i < list.size() && i < capacity; ++i) blocks[i] = list[i];
+    return (uint32_t)list.size();
 }
 
 int rtbh_viewport_resize(void* vp, uint32_t w, uint32_t h) { return static_cast<rt::ViewportB200*>(vp)->Resize(w, h) ? 0 : -1; }

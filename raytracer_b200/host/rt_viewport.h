@@ -10,6 +10,8 @@
 
 #include <cmath>
 #include <cstdio>
+#include <limits>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -178,9 +180,31 @@ inline float FastLog(float x)
     return r;
 }
 
+// AdaptiveRenderingSettings, Context.h:35-43
+struct AdaptiveRenderingSettings
+{
+    bool enable = false;
+    uint32_t numInitialPasses = 10;
+    uint32_t minBlockSize = 4;
+    uint32_t maxBlockSize = 256;
+    float subdivisionTreshold = 0.005f;
+    float convergenceTreshold = 0.0001f;
+};
+
+// RenderingProgress, Viewport.h:25-32
+struct RenderingProgress
+{
+    uint32_t passesFinished = 0;
+    uint32_t activePixels = 0;
+    uint32_t activeBlocks = 0;
+    float converged = 0.0f;
+    float averageError = std::numeric_limits<float>::infinity();
+};
+
 // LightSamplingStrategy / SamplingParams / RenderingParams subset, Context.h:28-90
 struct RenderingParams
 {
+    AdaptiveRenderingSettings adaptiveSettings;
     uint32_t dimensions = 64;
     bool useBlueNoiseDithering = true;
     float antiAliasingSpread = 0.5f;
@@ -217,6 +241,7 @@ public:
         RtbCreateDesc d;
         memset(&d, 0, sizeof(d));
         d.deviceId = deviceId; d.numShards = numShards; d.shardIndex = shardIndex; d.flags = flags; d.stream = cudaStream;
+        mNumShards = numShards ? numShards : 1;
         if (rtb_create(&d, &mCtx) != RTB_OK) return Error();
         if (!blueNoisePath.empty())
         {
@@ -260,6 +285,7 @@ public:
     }
 
     bool SetRenderingParams(const RenderingParams& p) { mParams = p; return true; }
+    const RenderingParams& GetRenderingParams() const { return mParams; }
     bool SetPostprocessParams(const PostprocessParams& p) { mPostprocessParams = p; return true; }      // Viewport.cpp:166-177
     void SetSeed(uint64_t seed) { mSeedValue = seed; }
 
@@ -269,7 +295,9 @@ public:
         mRandom.Reset(mSeedValue);
         mHalton.Initialize(mParams.dimensions, mRandom);
         mPassesFinished = 0;
-        if (mCtx) rtb_reset(mCtx);
+        mProgress = RenderingProgress();
+        BuildInitialBlocksList();
+        if (mCtx) rtb_reset(mCtx);      // (also makes every pixel active again)
     }
 
     // Viewport::Render, Viewport.cpp:185-289 (asynchronous: call Synchronize / GetSumBuffer to wait)
@@ -279,6 +307,111 @@ public:
     // pass in the reference's order, the device traces the passes in shared wavefronts and adds them to the film in
     // pass order, so the image is the one `count` Render() calls produce.
     bool RenderPasses(const Camera& camera, uint32_t count)
+    {
+        if (!mParams.adaptiveSettings.enable) return RenderPassesNow(camera, count);
+        // adaptive rendering: the block list is revised after every second pass (Viewport.cpp:267-274), so the device
+        // gets the passes two at a time
+        if (mNumShards > 1) { mError = "adaptive rendering estimates errors over whole image rows: with several shards, all-gather the films and use rtb_block_errors / rtb_set_active_tiles directly"; return false; }
+        while (count > 0)
+        {
+            const uint32_t n = (mPassesFinished & 1u) ? 1u : (count < 2u ? count : 2u);
+            if (!RenderPassesNow(camera, n)) return false;
+            count -= n;
+            if (mPassesFinished > 0 && (mPassesFinished & 1u) == 0u && !UpdateBlocksList()) return false;
+        }
+        return true;
+    }
+
+    // RenderingProgress (Viewport::GetProgress, Viewport.h:55).  averageError (Viewport::ComputeError, Viewport.cpp:179-183)
+    // is evaluated here, when asked for, if an even number of passes is in the film - the reference evaluates it
+    // after every second pass, which would put a device round trip between the passes; like the reference's it stays
+    // at its previous value otherwise, and is not maintained while adaptive rendering is on (Viewport.cpp:269-278).
+    bool GetProgress(RenderingProgress& out)
+    {
+        mProgress.passesFinished = mPassesFinished;
+        if (!mParams.adaptiveSettings.enable && mNumShards == 1 && mPassesFinished > 0 && (mPassesFinished & 1u) == 0u && mErrorPasses != mPassesFinished)
+        {
+            const RtbBlock whole = { 0, mWidth, 0, mHeight };
+            if (rtb_block_errors(mCtx, nullptr, nullptr, mPassesFinished, &whole, 1, &mProgress.averageError) != RTB_OK) return Error();
+            mErrorPasses = mPassesFinished;
+        }
+        out = mProgress;
+        return true;
+    }
+    const std::vector<RtbBlock>& GetBlocks() const { return mBlocks; }
+
+private:
+    // Viewport::BuildInitialBlocksList, Viewport.cpp:618-645
+    void BuildInitialBlocksList()
+    {
+        mBlocks.clear();
+        mErrorPasses = 0;
+        if (mWidth == 0 || mHeight == 0) return;
+        const uint32_t blockSize = mParams.adaptiveSettings.maxBlockSize;
+        const uint32_t rows = 1 + (mHeight - 1) / blockSize, columns = 1 + (mWidth - 1) / blockSize;
+        for (uint32_t j = 0; j < rows; ++j)
+            for (uint32_t i = 0; i < columns; ++i)
+                mBlocks.push_back(RtbBlock{ i * blockSize, std::min(mWidth, (i + 1) * blockSize), j * blockSize, std::min(mHeight, (j + 1) * blockSize) });
+        mProgress.activeBlocks = (uint32_t)mBlocks.size();
+    }
+
+public:
+    // The list revision of Viewport::UpdateBlocksList (Viewport.cpp:659-716) given each block's error: converged blocks
+    // are dropped, somewhat converged ones split in two along their longer side.  A dropped or split block is replaced
+    // by the last one of the list, which - as in the reference - is therefore not looked at in this round.  Returns
+    // whether a block was dropped (the set of active pixels changed).
+    static bool ReviseBlocks(std::vector<RtbBlock>& blocks, std::vector<float> errors, const AdaptiveRenderingSettings& settings)
+    {
+        std::vector<RtbBlock> newBlocks;
+        bool removed = false;
+        for (size_t i = 0; i < blocks.size(); ++i)
+        {
+            const RtbBlock block = blocks[i];
+            const float blockError = errors[i];
+            const uint32_t width = block.maxX - block.minX, height = block.maxY - block.minY;
+            if (blockError < settings.convergenceTreshold)
+            {
+                blocks[i] = blocks.back(); blocks.pop_back();
+                errors[i] = errors.back(); errors.pop_back();
+                removed = true;
+                continue;
+            }
+            if (blockError < settings.subdivisionTreshold && (width > settings.minBlockSize || height > settings.minBlockSize))
+            {
+                blocks[i] = blocks.back(); blocks.pop_back();
+                errors[i] = errors.back(); errors.pop_back();
+                RtbBlock childA = block, childB = block;
+                if (width > height) { const uint32_t halfPoint = (block.minX + block.maxX) / 2u; childA.maxX = halfPoint; childB.minX = halfPoint; }
+                else { const uint32_t halfPoint = (block.minY + block.maxY) / 2u; childA.maxY = halfPoint; childB.minY = halfPoint; }
+                newBlocks.push_back(childA);
+                newBlocks.push_back(childB);
+            }
+        }
+        blocks.insert(blocks.end(), newBlocks.begin(), newBlocks.end());
+        return removed;
+    }
+
+private:
+    // Viewport::UpdateBlocksList, Viewport.cpp:647-732.  The error of a block depends on the film only, so the errors of
+    // the whole list come from one device call; the list is then revised exactly as the reference revises it: a removed
+    // block is replaced by the last one, which is therefore not looked at in this round.
+    bool UpdateBlocksList()
+    {
+        const AdaptiveRenderingSettings& settings = mParams.adaptiveSettings;
+        if (mPassesFinished < settings.numInitialPasses) return true;
+        std::vector<float> errors(mBlocks.size());
+        if (!mBlocks.empty() && rtb_block_errors(mCtx, nullptr, nullptr, mPassesFinished, mBlocks.data(), (uint32_t)mBlocks.size(), errors.data()) != RTB_OK) return Error();
+        const bool removed = ReviseBlocks(mBlocks, errors, settings);
+        mProgress.activePixels = 0;
+        for (const RtbBlock& b : mBlocks) mProgress.activePixels += (b.maxX - b.minX) * (b.maxY - b.minY);
+        mProgress.converged = 1.0f - (float)mProgress.activePixels / (float)(mWidth * mHeight);
+        mProgress.activeBlocks = (uint32_t)mBlocks.size();
+        // Viewport::GenerateRenderingTiles cuts the blocks into tiles for its thread pool; the pixels are the same
+        if (removed && rtb_set_active_tiles(mCtx, mBlocks.data(), (uint32_t)mBlocks.size()) != RTB_OK) return Error();
+        return true;
+    }
+
+    bool RenderPassesNow(const Camera& camera, uint32_t count)
     {
         if (mWidth == 0 || mHeight == 0) return false;
         if (!mHasScene) { mError = "Viewport: Missing renderer"; return false; }
@@ -310,6 +443,7 @@ public:
         return true;
     }
 
+public:
     bool Synchronize() { return rtb_synchronize(mCtx) == RTB_OK || Error(); }
     bool GetSumBuffer(float* rgb, int which = 0) { return rtb_read_sum(mCtx, rgb, which) == RTB_OK || Error(); }
     // Viewport::GetFrontBuffer (Viewport.h:49): the tone-mapped image of what has been rendered so far, width * height
@@ -353,6 +487,9 @@ private:
     uint32_t mWidth = 0, mHeight = 0, mPassesFinished = 0;
     RenderingParams mParams;
     PostprocessParams mPostprocessParams;
+    RenderingProgress mProgress;
+    std::vector<RtbBlock> mBlocks;        // regions of the image still being rendered (Viewport.h:126)
+    uint32_t mNumShards = 1, mErrorPasses = 0;
     uint64_t mSeedValue = 12345;
     Random mRandom;
     HaltonSequence mHalton;

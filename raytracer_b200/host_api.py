@@ -45,11 +45,29 @@ def load_host_library():
     lib.rtbh_viewport_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     lib.rtbh_viewport_synchronize.argtypes = [C.c_void_p]
     lib.rtbh_viewport_read_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.rtbh_viewport_set_adaptive.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float]
+    lib.rtbh_viewport_progress.argtypes = [C.c_void_p, C.c_void_p]
+    lib.rtbh_viewport_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.rtbh_viewport_blocks.restype = C.c_uint32
+    lib.rtbh_revise_blocks.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_float, C.c_float]
+    lib.rtbh_revise_blocks.restype = C.c_uint32
     lib.rtbh_viewport_set_postprocess.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint32]
     lib.rtbh_viewport_read_front.argtypes = [C.c_void_p, C.c_void_p]
     lib.rtbh_viewport_counters.argtypes = [C.c_void_p, C.POINTER(capi.RtbCounters)]
     _lib = lib
     return lib
+
+
+def revise_blocks(blocks, errors, min_block_size=4, subdivision_treshold=0.005, convergence_treshold=0.0001):
+    """The block-list revision of Viewport::UpdateBlocksList (host logic only, no device): (n, 4) blocks + n errors -> (m, 4)."""
+    lib = load_host_library()
+    blocks = np.ascontiguousarray(blocks, dtype=np.uint32).reshape(-1, 4)
+    errors = np.ascontiguousarray(errors, dtype=np.float32)
+    assert len(errors) == len(blocks)
+    buf = np.zeros((2 * len(blocks) + 1, 4), dtype=np.uint32)
+    buf[:len(blocks)] = blocks
+    m = lib.rtbh_revise_blocks(buf.ctypes.data, len(blocks), len(buf), errors.ctypes.data, min_block_size, subdivision_treshold, convergence_treshold)
+    return buf[:m].copy()
 
 
 class Scene:
@@ -131,6 +149,25 @@ class Viewport:
         if out is None:
             out = np.empty((self.height, self.width, 3), dtype=np.float32)
         self._check(self.lib.rtbh_viewport_read_sum(self.h, out.ctypes.data, which))
+        return out
+
+    def set_adaptive(self, enable=True, num_initial_passes=10, min_block_size=4, max_block_size=256, subdivision_treshold=0.005, convergence_treshold=0.0001):
+        """AdaptiveRenderingSettings (Context.h:35-43); applies from the next reset() / resize()."""
+        self._check(self.lib.rtbh_viewport_set_adaptive(self.h, 1 if enable else 0, num_initial_passes, min_block_size, max_block_size, subdivision_treshold, convergence_treshold))
+
+    def progress(self):
+        """Viewport::GetProgress (Viewport.h:25-32, 55)."""
+        out = np.zeros(5, dtype=np.uint32)
+        self._check(self.lib.rtbh_viewport_progress(self.h, out.ctypes.data))
+        return {"passesFinished": int(out[0]), "activePixels": int(out[1]), "activeBlocks": int(out[2]),
+                "converged": out[3:4].view(np.float32)[0], "averageError": out[4:5].view(np.float32)[0]}
+
+    def blocks(self):
+        """The block list of adaptive rendering: (n, 4) uint32 rows minX, maxX, minY, maxY."""
+        n = self.lib.rtbh_viewport_blocks(self.h, None, 0)
+        out = np.zeros((n, 4), dtype=np.uint32)
+        if n:
+            self.lib.rtbh_viewport_blocks(self.h, out.ctypes.data, n)
         return out
 
     def set_postprocess(self, color_filter=(1.0, 1.0, 1.0), exposure=0.0, contrast=0.8, saturation=0.98, dithering=0.005, bloom=0.0,

@@ -9,6 +9,7 @@
 //   hostsim trace  <scene.rtb> <rays.bin> <out.hits> [shadow tmax.bin]
 //   hostsim sampler <passes.bin> <w> <h> <numDims> <out.u32> <bluenoise.dat|->
 //   hostsim primary <scene.rtb> <passes.bin> <pass> <w> <h> <out.rays>
+//   hostsim blockerrors <sum.bin> <sum2.bin> <w> <h> <numPasses> <blocks.bin> <out.f32>
 //   hostsim front  <sum.bin> <w> <h> <numPasses> <exposure> <contrast> <saturation> <dither> <tonemapper> <r,g,b filter> <out.bgra> [bloomFactor]
 #include <cstdio>
 #include <cstdlib>
@@ -325,6 +326,36 @@ static int cmdPrimary(int argc, char** argv)
     return 0;
 }
 
+// the arithmetic of rtb_block_errors on raster sum buffers (the three kernels, one thread after the other)
+static int cmdBlockErrors(int argc, char** argv)
+{
+    if (argc < 9) die("blockerrors: arguments");
+    const uint32_t w = atoi(argv[4]), h = atoi(argv[5]), passes = atoi(argv[6]);
+    std::vector<float> sum((size_t)w * h * 3), sum2((size_t)w * h * 3);
+    FILE* f = fopen(argv[2], "rb");
+    if (!f || fread(sum.data(), 4, sum.size(), f) != sum.size()) die("cannot read sum");
+    fclose(f);
+    f = fopen(argv[3], "rb");
+    if (!f || fread(sum2.data(), 4, sum2.size(), f) != sum2.size()) die("cannot read sum2");
+    fclose(f);
+    std::vector<float> pixelErrors((size_t)w * h);
+    for (size_t i = 0; i < pixelErrors.size(); ++i)
+        pixelErrors[i] = pixel_error(v3(sum[3 * i], sum[3 * i + 1], sum[3 * i + 2]), v3(sum2[3 * i], sum2[3 * i + 1], sum2[3 * i + 2]), 1.0f / (float)passes);
+    f = fopen(argv[7], "rb");
+    if (!f) die("cannot read blocks");
+    FILE* of = fopen(argv[8], "wb");
+    RtbBlock b;
+    while (fread(&b, sizeof(b), 1, f) == 1)
+    {
+        std::vector<float> rows;
+        for (uint32_t y = b.minY; y < b.maxY; ++y) rows.push_back(row_error(pixelErrors.data() + (size_t)y * w, b.minX, b.maxX));
+        const float e = block_error(rows.data(), (uint32_t)rows.size(), b.maxX - b.minX, w * h);
+        fwrite(&e, 4, 1, of);
+    }
+    fclose(f); fclose(of);
+    return 0;
+}
+
 // the arithmetic of rtb_read_front on a raster sum buffer
 static int cmdFront(int argc, char** argv)
 {
@@ -366,7 +397,7 @@ static int cmdFront(int argc, char** argv)
     for (uint32_t i = 0; i < w * h; ++i)
     {
         const V3 bloom = P.bloomFactor > 0.0f ? bloom_color(blurred.data(), levelStride, i) : v3s(0.0f);
-        out[i] = postprocess_pixel(P, v3(sum[3 * i], sum[3 * i + 1], sum[3 * i + 2]), bloom, i);
+        out[i] = postprocess_pixel(P, v3(sum[3 * i], sum[3 * i + 1], sum[3 * i + 2]), bloom, i, P.pixelScaling);
     }
     FILE* of = fopen(argv[12], "wb");
     fwrite(out.data(), 4, out.size(), of);
@@ -387,6 +418,7 @@ int main(int argc, char** argv)
     if (cmd == "sampler") return cmdSampler(argc, argv);
     if (cmd == "primary") return cmdPrimary(argc, argv);
     if (cmd == "front") return cmdFront(argc, argv);
+    if (cmd == "blockerrors") return cmdBlockErrors(argc, argv);
     die("unknown command");
     return 2;
 }

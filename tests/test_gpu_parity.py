@@ -584,3 +584,149 @@ def test_front_buffer_dithering_and_errors(ctx):
     ctx.resize(202, 200)
     with pytest.raises(capi.RtbError, match="multiple of 4"):
         ctx.read_front(capi.postprocess_desc(4, bloom=0.5))
+
+
+# ---- adaptive rendering: block errors, active tiles, the host's block list (Viewport.cpp:552-732) ------------------------
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="prebuilt oracle/_ref/exact did not travel to this box")
+@pytest.mark.parametrize("scene", ["cornell", "mesh_small"])
+def test_block_errors_against_the_live_reference(ctx, tmp_path, scene):
+    """rtb_block_errors == Viewport::ComputeBlockError for the whole image, single pixels / rows / columns and random
+    rectangles, from this context's film and from the all-gathered films of 3 shards."""
+    import torch
+    from bench import CudaArray
+    from tests.test_hostsim_parity import error_test_blocks
+
+    w, h, passes = 100, 76, 4
+    sj = os.path.join(util.GOLDEN, "scenes", scene + ".json")
+    data = os.path.join(util.GOLDEN, "scenes") + "/"
+    blocks = error_test_blocks(w, h)
+    bp, refp, passp, flatp = (str(tmp_path / n) for n in ("blocks.bin", "o.err", "o.passes", "o.rtb"))
+    blocks.tofile(bp)
+    util.run_rtref(["render", "--scene", sj, "--data", data, "--width", w, "--height", h, "--passes", passes, "--dims", 128, "--depth", 8,
+                    "--strategy", "all", "--dump-passes", passp, "--block-errors", bp, "--dump-block-errors", refp])
+    util.run_rtref(["flat", "--scene", sj, "--data", data, "--width", w, "--height", h, "--out", flatp])
+    want = np.fromfile(refp, dtype=np.float32)
+    sf, ps = capi.SceneFile(flatp), capi.PassScript(passp)
+    cam = capi.camera_for(sf, w, h)
+
+    def render(c):
+        c.upload_scene(sf)
+        c.resize(w, h)
+        c.render_passes(cam, ps.seeds[:passes], ps.offsets[:passes])
+
+    render(ctx)
+    assert ctx.block_errors(passes, blocks).tobytes() == want.tobytes()
+    n, parts, parts2, ctxs = 3, [], [], []
+    for s in range(n):
+        c = capi.Context(device=0, num_shards=n, shard_index=s, tile_size=16)
+        render(c)
+        c.synchronize()
+        for which, dst in ((0, parts), (1, parts2)):
+            ptr, cnt = c.film_device_buffer(which)
+            dst.append(torch.as_tensor(CudaArray(ptr, cnt), device="cuda").clone())
+        ctxs.append(c)
+    g, g2 = torch.cat(parts), torch.cat(parts2)
+    torch.cuda.synchronize()
+    assert ctxs[1].block_errors(passes, blocks, g.data_ptr(), g2.data_ptr()).tobytes() == want.tobytes()
+    with pytest.raises(capi.RtbError, match="all-gathered"):
+        ctxs[0].block_errors(passes, blocks)
+    with pytest.raises(capi.RtbError, match="even"):
+        ctx.block_errors(3, blocks)
+    with pytest.raises(capi.RtbError, match="outside"):
+        ctx.block_errors(4, [(0, w + 1, 0, h)])
+    for c in ctxs:
+        c.close()
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="prebuilt oracle/_ref/exact did not travel to this box")
+@pytest.mark.parametrize("subdivision,convergence,per_call", [(0.05, 0.01, 1), (0.3, 0.08, 1), (0.3, 0.08, 5)])
+def test_adaptive_rendering_against_the_live_reference(tmp_path, subdivision, convergence, per_call):
+    """AdaptiveRenderingSettings through the host viewport: after every pass the progress and the block list are the
+    reference's; at the end so are the sums (converged blocks stop receiving samples), the ray counters and the front
+    buffer (a converged pixel keeps the value it had when it was last rendered).  The second parameter set converges
+    the whole image: the last passes render nothing."""
+    from raytracer_b200 import host_api
+
+    w, h, passes, init, minb, maxb = 96, 80, 16, 2, 4, 32
+    scn = os.path.join(util.GOLDEN, "scenes")
+    sj = os.path.join(scn, "cornell.json")
+    sump, sum2p, frontp, progp = (str(tmp_path / n) for n in ("o.sum", "o.sum2", "o.front", "o.progress"))
+    meta = util.run_rtref(["render", "--scene", sj, "--data", scn + "/", "--width", w, "--height", h, "--passes", passes, "--dims", 256, "--depth", 8,
+                           "--strategy", "all", "--adaptive", 1, "--adaptive-initial", init, "--adaptive-min-block", minb, "--adaptive-max-block", maxb,
+                           "--adaptive-subdivision", subdivision, "--adaptive-convergence", convergence,
+                           "--dump-progress", progp, "--dump-sum", sump, "--dump-sum2", sum2p, "--dump-front", frontp])
+    records = util.read_progress(progp)
+    scene = host_api.Scene(sj, scn + "/")
+    vp = host_api.Viewport(scene, device=0)
+    try:
+        vp.set_renderer("Path Tracer MIS")
+        vp.set_params(dimensions=256, max_ray_depth=8, strategy="all", seed=12345)
+        vp.set_adaptive(True, init, minb, maxb, subdivision, convergence)
+        vp.set_postprocess(dithering=0.0)
+        vp.resize(w, h)
+        done = 0
+        while done < passes:
+            n = min(per_call, passes - done)
+            vp.render(n)
+            done += n
+            r, mine = records[done - 1], vp.progress()
+            assert mine["passesFinished"] == r["passesFinished"] == done
+            assert (mine["activeBlocks"], mine["activePixels"]) == (r["activeBlocks"], r["activePixels"]), "pass %d" % done
+            assert mine["converged"] == r["converged"] and np.isinf(mine["averageError"])
+            assert np.array_equal(vp.blocks(), r["blocks"]), "block list after pass %d" % done
+        util.assert_bit_identical(vp.read_sum(), util.load_sum(sump, w, h), "adaptive sum")
+        util.assert_bit_identical(vp.read_sum(1), util.load_sum(sum2p, w, h), "adaptive secondary sum")
+        c = vp.counters()
+        assert (c["numPrimaryRays"], c["numRays"], c["numShadowRays"], c["numShadowRaysHit"]) == \
+               (meta["numPrimaryRays"], meta["numRays"], meta["numShadowRays"], meta["numShadowRaysHit"])
+        assert c["numPrimaryRays"] < w * h * passes
+        got, want = vp.read_front(), np.fromfile(frontp, dtype=np.uint32).reshape(h, w)
+        assert np.array_equal(got, want), "%d of %d front-buffer pixels differ" % ((got != want).sum(), want.size)
+        # Viewport::Reset: every block is back
+        vp.reset()
+        assert len(vp.blocks()) == 9
+        vp.render(2)
+        assert vp.counters()["numPrimaryRays"] == 2 * w * h
+    finally:
+        vp.close()
+        scene.close()
+
+
+def test_active_tiles(ctx):
+    """rtb_set_active_tiles: the passes that follow touch only the pixels inside the tiles."""
+    sf = capi.SceneFile(util.golden("cornell.rtb"))
+    ps = capi.PassScript(util.golden("cornell.passes"))
+    w = h = 64
+    cam = capi.camera_for(sf, w, h)
+    ctx.upload_scene(sf)
+    ctx.resize(w, h)
+    first_two = lambda: ctx.render_passes(cam, ps.seeds[0:2], ps.offsets[0:2], first_pass=0)
+    last_two = lambda: ctx.render_passes(cam, ps.seeds[2:4], ps.offsets[2:4], first_pass=2)
+    first_two()
+    two = ctx.read_sum().copy()
+    last_two()
+    four = ctx.read_sum().copy()
+    ctx.reset()
+    first_two()
+    ctx.set_active_tiles([(8, 40, 0, 17), (40, 64, 3, 4), (0, 1, 63, 64)])
+    last_two()
+    mask = np.zeros((h, w), dtype=bool)
+    mask[0:17, 8:40] = True; mask[3:4, 40:64] = True; mask[63:64, 0:1] = True
+    got = ctx.read_sum()
+    util.assert_bit_identical(got[mask], four[mask], "active pixels")
+    util.assert_bit_identical(got[~mask], two[~mask], "inactive pixels")
+    assert ctx.counters()["numPrimaryRays"] == 2 * w * h + 2 * int(mask.sum())
+    # nothing active: passes are counted, nothing is rendered
+    ctx.set_active_tiles(np.zeros((0, 4), dtype=np.uint32))
+    last_two()
+    util.assert_bit_identical(ctx.read_sum(), got, "no active pixels")
+    with pytest.raises(capi.RtbError, match="overlaps"):
+        ctx.set_active_tiles([(0, 10, 0, 10), (9, 12, 9, 12)])
+    with pytest.raises(capi.RtbError, match="outside"):
+        ctx.set_active_tiles([(0, 65, 0, 10)])
+    # the whole image again
+    ctx.set_active_tiles(None)
+    ctx.reset()
+    ctx.render_passes(cam, ps.seeds[0:4], ps.offsets[0:4])
+    util.assert_bit_identical(ctx.read_sum(), four, "all pixels active again")

@@ -202,6 +202,67 @@ def test_hostsim_front_buffer_against_the_live_reference(hostsim, tmp_path, case
         assert not np.array_equal(hostsim_front(sump, w, h, passes, str(tmp_path / "nobloom.front"), exposure, contrast, saturation, 0.0, tonemapper, filt), want)
 
 
+def error_test_blocks(w, h, seed=3):
+    """The whole image (Viewport::ComputeError), single pixels, single rows / columns and random rectangles."""
+    rng = np.random.default_rng(seed)
+    blocks = [(0, w, 0, h), (0, 1, 0, 1), (w - 1, w, h - 1, h), (0, w, 5, 6), (7, 8, 0, h)]
+    while len(blocks) < 48:
+        x0, x1 = sorted(int(v) for v in rng.integers(0, w + 1, 2))
+        y0, y1 = sorted(int(v) for v in rng.integers(0, h + 1, 2))
+        if x0 < x1 and y0 < y1:
+            blocks.append((x0, x1, y0, y1))
+    return np.array(blocks, dtype=np.uint32)
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
+@pytest.mark.parametrize("scene", ["cornell", "mesh_small", "materials"])
+def test_hostsim_block_errors_against_the_live_reference(hostsim, tmp_path, scene):
+    """Viewport::ComputeBlockError (Viewport.cpp:552-582): per-pixel estimate, row sums left to right, block sum top to
+    bottom - the float sums are order dependent, so the device code adds in the reference's order."""
+    w, h, passes = 100, 76, 4
+    scn = os.path.join(util.GOLDEN, "scenes")
+    blocks = error_test_blocks(w, h)
+    bp, sump, sum2p, refp, minep, progp = (str(tmp_path / n) for n in ("blocks.bin", "o.sum", "o.sum2", "o.err", "mine.err", "o.progress"))
+    blocks.tofile(bp)
+    util.run_rtref(["render", "--scene", os.path.join(scn, scene + ".json"), "--data", scn + "/", "--width", w, "--height", h, "--passes", passes, "--dims", 256,
+                    "--dump-sum", sump, "--dump-sum2", sum2p, "--block-errors", bp, "--dump-block-errors", refp, "--dump-progress", progp])
+    subprocess.run([HOSTSIM, "blockerrors", sump, sum2p, str(w), str(h), str(passes), bp, minep], check=True)
+    want, got = np.fromfile(refp, dtype=np.float32), np.fromfile(minep, dtype=np.float32)
+    assert len(want) == len(blocks) and want.tobytes() == got.tobytes()
+    assert np.isfinite(want).all() and want[0] > 0
+    # RenderingProgress::averageError after the last (even) pass is the whole image's error (Viewport.cpp:179-183)
+    assert util.read_progress(progp)[-1]["averageError"] == want[0]
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
+@pytest.mark.parametrize("subdivision,convergence", [(0.05, 0.01), (0.3, 0.08)])
+def test_block_list_revision_against_the_live_reference(tmp_path, subdivision, convergence):
+    """Viewport::UpdateBlocksList (Viewport.cpp:647-732), host logic only: fed the reference's own block lists and block
+    errors pass after pass, ViewportB200::ReviseBlocks produces the reference's next list (order included)."""
+    from raytracer_b200 import host_api
+    w, h, passes, init, minb, maxb = 96, 80, 16, 2, 4, 32
+    scn = os.path.join(util.GOLDEN, "scenes")
+    progp = str(tmp_path / "o.progress")
+    util.run_rtref(["render", "--scene", os.path.join(scn, "cornell.json"), "--data", scn + "/", "--width", w, "--height", h, "--passes", passes, "--dims", 256,
+                    "--adaptive", 1, "--adaptive-initial", init, "--adaptive-min-block", minb, "--adaptive-max-block", maxb,
+                    "--adaptive-subdivision", subdivision, "--adaptive-convergence", convergence, "--dump-progress", progp])
+    records = util.read_progress(progp)
+    assert len(records) == passes and len(records[0]["blocks"]) == 9
+    previous, revisions, dropped = records[0]["blocks"], 0, False
+    for r in records[1:]:
+        if len(r["previousErrors"]) and r["passesFinished"] >= init:
+            mine = host_api.revise_blocks(previous, r["previousErrors"], minb, subdivision, convergence)
+            assert np.array_equal(mine, r["blocks"]), "block list after pass %d" % r["passesFinished"]
+            area = int(((mine[:, 1] - mine[:, 0]) * (mine[:, 3] - mine[:, 2])).sum())
+            assert area == r["activePixels"] and len(mine) == r["activeBlocks"]
+            revisions += 1
+            dropped = dropped or area < w * h
+        else:
+            assert np.array_equal(previous, r["blocks"])
+        previous = r["blocks"]
+    assert revisions >= 5 and dropped
+
+
 @pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
 def test_golden_fixtures_reproduce_from_the_reference(tmp_path):
     """The committed fixtures are what the real reference produces today (pins the oracle: fixed seed, exact math)."""

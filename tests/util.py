@@ -71,3 +71,20 @@ def reference_scene_manifest():
 
 
 REFERENCE_SCENE_RENDERS = [(n, r) for n, e in sorted(reference_scene_manifest().items()) if e.get("loads") for r in ("mis", "pt")]
+
+
+def read_progress(path):
+    """rtref --dump-progress: one record per Render(): RenderingProgress, the block list after the pass and, after even
+    passes, ComputeBlockError of each block of the PREVIOUS list (what UpdateBlocksList compared with its thresholds)."""
+    import numpy as np
+    raw = np.fromfile(path, dtype=np.uint32)
+    out, i = [], 0
+    while i < len(raw):
+        rec = {"passesFinished": int(raw[i]), "activePixels": int(raw[i + 1]), "activeBlocks": int(raw[i + 2]),
+               "converged": raw[i + 3:i + 4].view(np.float32)[0], "averageError": raw[i + 4:i + 5].view(np.float32)[0]}
+        n = int(raw[i + 5]); i += 6
+        rec["blocks"] = raw[i:i + 4 * n].reshape(n, 4).copy(); i += 4 * n
+        m = int(raw[i]); i += 1
+        rec["previousErrors"] = raw[i:i + m].view(np.float32).copy(); i += m
+        out.append(rec)
+    return out
