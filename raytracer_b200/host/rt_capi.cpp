@@ -120,6 +120,12 @@ uint32_t rtbh_viewport_blocks(void* vp, RtbBlock* out, uint32_t capacity)
     return (uint32_t)b.size();
 }
 
+// ViewportB200::PassScript: seeds[numPasses * dimensions], sampleOffsets[numPasses * 2] (host prologue only, no device)
+void rtbh_pass_script(uint64_t seed, uint32_t dimensions, float antiAliasingSpread, uint32_t width, uint32_t height, uint32_t extraResets, uint32_t numPasses, uint32_t* seeds, float* sampleOffsets)
+{
+    rt::ViewportB200::PassScript(seed, dimensions, antiAliasingSpread, width, height, extraResets, numPasses, seeds, sampleOffsets);
+}
+
 // ViewportB200::ReviseBlocks on caller data (no device): blocks[0..n) + errors[0..n) in, the revised list out (at most
 // `capacity` entries are written; a revision at most doubles the list); returns its length
 uint32_t rtbh_revise_blocks(RtbBlock* blocks, uint32_t n, uint32_t capacity, const float* errors, uint32_t minBlockSize, float subdivisionTreshold, float convergenceTreshold)

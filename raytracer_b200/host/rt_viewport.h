@@ -20,15 +20,67 @@
 
 namespace rt {
 
+// The seed source of every generator: Entropy::GetInt (Utils/Entropy.cpp:65-85).  The reference reads /dev/urandom; its
+// fixed-seed oracle build (oracle/patch_ref.py P8, RT_FIXED_SEED) hands out the upper halves of a splitmix64 stream
+// instead, and so does this class, so that a seed reproduces the oracle's renders.
+class EntropyStream
+{
+public:
+    explicit EntropyStream(uint64_t seed) : mState(seed) {}
+    uint32_t GetInt()
+    {
+        mState += 0x9E3779B97F4A7C15ULL;
+        uint64_t z = mState;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        z = z ^ (z >> 31);
+        return (uint32_t)(z >> 32);
+    }
+private:
+    uint64_t mState;
+};
+
 class Random
 {
 public:
-    explicit Random(uint64_t seed = 0x853c49e6748fea9bULL) { Reset(seed); }
-    void Reset(uint64_t seed)
+    Random() { mSeed[0] = 0x853c49e6748fea9bULL; mSeed[1] = 0xda3e39cb94b95bdbULL; }
+    // Random::Reset (Math/Random.cpp:19-32): per half of the state, 2 integers for the scalar generator, then 4 + 8
+    // for the SIMD generators (which the hot path's host side never uses - drawn and dropped to stay in step)
+    void Reset(EntropyStream& entropy)
     {
-        mState = seed;
-        mSeed[0] = Next(); mSeed[1] = Next();
-        if (mSeed[0] == 0 && mSeed[1] == 0) mSeed[0] = 1;
+        for (int i = 0; i < 2; ++i)
+        {
+            const uint64_t hi = entropy.GetInt();
+            const uint64_t lo = entropy.GetInt();
+            mSeed[i] = (hi << 32) | lo;
+            // mSeedSimd4[i] = VectorInt4(x, y, z, w): GCC evaluates the four GetInt() arguments right to left
+            uint32_t lane[4];
+            for (int k = 3; k >= 0; --k) lane[k] = entropy.GetInt();
+            mSeedSimd4[i][0] = ((uint64_t)lane[1] << 32) | lane[0];
+            mSeedSimd4[i][1] = ((uint64_t)lane[3] << 32) | lane[2];
+            for (int k = 0; k < 8; ++k) entropy.GetInt();      // mSeedSimd8[i]
+        }
+    }
+    // `count` GetVector4() draws whose values nobody reads (Viewport::Resize draws one per pixel, Viewport.cpp:99-102)
+    void SkipVector4(uint64_t count)
+    {
+        float x, y;
+        for (uint64_t i = 0; i < count; ++i) GetFloat2(x, y);
+    }
+    // Random::GetFloat2 (Random.cpp:65-68, 83-126): lanes x, y of the 4-wide xorshift128+ generator, as floats in [0, 1)
+    void GetFloat2(float& x, float& y)
+    {
+        const uint64_t s0 = mSeedSimd4[1][0], s0b = mSeedSimd4[1][1];
+        uint64_t s1 = mSeedSimd4[0][0], s1b = mSeedSimd4[0][1];
+        const uint64_t v = s0 + s1;
+        s1 <<= 23; s1b <<= 23;
+        mSeedSimd4[0][0] = s0; mSeedSimd4[0][1] = s0b;
+        mSeedSimd4[1][0] = (s0 ^ s1) ^ ((s0 >> 5) ^ (s1 >> 18));
+        mSeedSimd4[1][1] = (s0b ^ s1b) ^ ((s0b >> 5) ^ (s1b >> 18));
+        union { uint32_t u; float f; } a, b;
+        a.u = ((uint32_t)v & 0x007fffffu) | 0x3f800000u;
+        b.u = ((uint32_t)(v >> 32) & 0x007fffffu) | 0x3f800000u;
+        x = a.f - 1.0f; y = b.f - 1.0f;
     }
     // xoroshiro128+, Random.cpp:33-47
     uint64_t GetLong()
@@ -46,16 +98,8 @@ public:
     float GetFloat() { union { uint32_t u; float f; } r; r.u = (GetInt() & 0x007fffffu) | 0x3f800000u; return r.f - 1.0f; }
     double GetDouble() { return static_cast<double>(GetLong()) / static_cast<double>(UINT64_MAX); }
 private:
-    uint64_t Next()   // splitmix64
-    {
-        mState += 0x9E3779B97F4A7C15ULL;
-        uint64_t z = mState;
-        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-        return z ^ (z >> 31);
-    }
-    uint64_t mState = 0;
     uint64_t mSeed[2];
+    uint64_t mSeedSimd4[2][2] = {};      // two 64-bit lanes per half
 };
 
 // scrambled Halton sequence with random start (HaltonSampler.cpp): digit expansion per dimension in base p_d, digits
@@ -65,8 +109,13 @@ class HaltonSequence
 public:
     static constexpr uint32_t Width = 64;
 
-    void Initialize(uint32_t dims, Random& rng)
+    // HaltonSequence::mRandom (HaltonSampler.h:45) is seeded once, when the sequence is constructed; Initialize keeps
+    // drawing from it, so a second Initialize gives a different scramble (as in the reference)
+    void Seed(EntropyStream& entropy) { mRandom.Reset(entropy); }
+
+    void Initialize(uint32_t dims)
     {
+        Random& rng = mRandom;
         mDims = dims;
         mBase.assign(dims, 0); mStarts.assign(dims, 0);
         mRnd.assign(dims, std::vector<double>(Width + 1, 0.0));
@@ -155,6 +204,7 @@ public:
     uint32_t GetInt(uint32_t dimension) const { return uint32_t(mRnd[dimension][0] * (double)UINT32_MAX); }
 
 private:
+    Random mRandom;
     uint32_t mDims = 0;
     std::vector<uint64_t> mStarts;
     std::vector<uint32_t> mBase;
@@ -228,7 +278,7 @@ struct PostprocessParams
 class ViewportB200
 {
 public:
-    ViewportB200() = default;
+    ViewportB200() { SetSeed(12345); }
     ~ViewportB200() { if (mCtx) rtb_destroy(mCtx); }
     ViewportB200(const ViewportB200&) = delete;
     ViewportB200& operator=(const ViewportB200&) = delete;
@@ -280,6 +330,9 @@ public:
     {
         if (rtb_resize(mCtx, width, height) != RTB_OK) return Error();
         mWidth = width; mHeight = height;
+        // the reference fills a per-pixel salt table from the viewport's generator here (Viewport.cpp:99-102; the table
+        // is not used on this path): the generator moves on by one draw per pixel, and with it every later AA offset
+        mRandom.SkipVector4((uint64_t)width * height);
         Reset();
         return true;
     }
@@ -287,13 +340,21 @@ public:
     bool SetRenderingParams(const RenderingParams& p) { mParams = p; return true; }
     const RenderingParams& GetRenderingParams() const { return mParams; }
     bool SetPostprocessParams(const PostprocessParams& p) { mPostprocessParams = p; return true; }      // Viewport.cpp:166-177
-    void SetSeed(uint64_t seed) { mSeedValue = seed; }
+    // Seeds the generators the way the reference's constructor does (Viewport.h:106-107: mRandomGenerator, then the
+    // Halton sequence's own generator, each taking its integers from the entropy source in turn).  With the oracle's
+    // RT_FIXED_SEED = seed, a Viewport that is the process's first consumer of entropy draws the same integers, so
+    // the same calls (Resize, Reset, Render ...) give the same pass scripts.  Default seed: 12345.
+    void SetSeed(uint64_t seed)
+    {
+        EntropyStream entropy(seed);
+        mRandom.Reset(entropy);
+        mHalton.Seed(entropy);
+    }
 
     // Viewport::Reset, Viewport.cpp:117-138
     void Reset()
     {
-        mRandom.Reset(mSeedValue);
-        mHalton.Initialize(mParams.dimensions, mRandom);
+        mHalton.Initialize(mParams.dimensions);      // (continues the sequence's generator: no re-seeding, Viewport.cpp:120-138)
         mPassesFinished = 0;
         mProgress = RenderingProgress();
         BuildInitialBlocksList();
@@ -356,6 +417,37 @@ private:
     }
 
 public:
+    // The host prologue of one Viewport::Render: the pass's Halton seed vector (Viewport.cpp:200-205) and its
+    // anti-aliasing offset GetFloatNormal2(rng.GetFloat2()) * antiAliasingSpread (Viewport.cpp:235-242), drawn in the
+    // reference's order.  `seeds` receives halton.GetNumDimensions() integers.
+    static void NextPass(HaltonSequence& halton, Random& random, float antiAliasingSpread, uint32_t* seeds, float sampleOffset[2])
+    {
+        halton.NextSample();
+        for (uint32_t i = 0; i < halton.GetNumDimensions(); ++i) seeds[i] = halton.GetInt(i);
+        float u0, u1;
+        random.GetFloat2(u0, u1);
+        float s, c;
+        rtb::sin_cos(2.0f * RTB_PI * u1, s, c);
+        const float radius = sqrtf(-2.0f * FastLog(u0));
+        sampleOffset[0] = radius * s * antiAliasingSpread;
+        sampleOffset[1] = radius * c * antiAliasingSpread;
+    }
+
+    // the pass script of `numPasses` Render() calls of a viewport that was seeded with `seed`, resized once to
+    // width x height (which resets it) and reset `extraResets` more times - no device involved
+    static void PassScript(uint64_t seed, uint32_t dimensions, float antiAliasingSpread, uint32_t width, uint32_t height, uint32_t extraResets,
+                           uint32_t numPasses, uint32_t* seeds, float* sampleOffsets)
+    {
+        EntropyStream entropy(seed);
+        Random random;
+        HaltonSequence halton;
+        random.Reset(entropy);
+        halton.Seed(entropy);
+        random.SkipVector4((uint64_t)width * height);
+        for (uint32_t i = 0; i < 1 + extraResets; ++i) halton.Initialize(dimensions);
+        for (uint32_t p = 0; p < numPasses; ++p) NextPass(halton, random, antiAliasingSpread, seeds + (size_t)p * dimensions, sampleOffsets + 2 * (size_t)p);
+    }
+
     // The list revision of Viewport::UpdateBlocksList (Viewport.cpp:659-716) given each block's error: converged blocks
     // are dropped, somewhat converged ones split in two along their longer side.  A dropped or split block is replaced
     // by the last one of the list, which - as in the reference - is therefore not looked at in this round.  Returns
@@ -421,13 +513,8 @@ private:
         std::vector<RtbPassDesc> passes(count);
         for (uint32_t p = 0; p < count; ++p)
         {
-            mHalton.NextSample();                                                   // Viewport.cpp:200-205
-            for (uint32_t i = 0; i < dims; ++i) seeds[(size_t)p * dims + i] = mHalton.GetInt(i);
-            // GetFloatNormal2(rng.GetFloat2()) * antiAliasingSpread                // Viewport.cpp:235-242
-            const float u0 = mRandom.GetFloat(), u1 = mRandom.GetFloat();
-            float s, c;
-            rtb::sin_cos(2.0f * RTB_PI * u1, s, c);
-            const float radius = sqrtf(-2.0f * FastLog(u0));
+            float sampleOffset[2];
+            NextPass(mHalton, mRandom, mParams.antiAliasingSpread, &seeds[(size_t)p * dims], sampleOffset);
             RtbPassDesc& pass = passes[p];
             memset(&pass, 0, sizeof(pass));
             pass.renderer = mRenderer; pass.debugMode = mDebugMode;
@@ -435,8 +522,8 @@ private:
             pass.maxRayDepth = mParams.maxRayDepth; pass.minRussianRouletteDepth = mParams.minRussianRouletteDepth;
             pass.lightSamplingStrategy = mParams.lightSamplingStrategy; pass.useBlueNoise = mParams.useBlueNoiseDithering;
             pass.passIndex = mPassesFinished + p; pass.numSeedDims = dims; pass.seed = dims ? &seeds[(size_t)p * dims] : nullptr;
-            pass.sampleOffset[0] = radius * s * mParams.antiAliasingSpread;
-            pass.sampleOffset[1] = radius * c * mParams.antiAliasingSpread;
+            pass.sampleOffset[0] = sampleOffset[0];
+            pass.sampleOffset[1] = sampleOffset[1];
         }
         if (rtb_render_passes(mCtx, passes.data(), count) != RTB_OK) return Error();
         mPassesFinished += count;
@@ -490,7 +577,6 @@ private:
     RenderingProgress mProgress;
     std::vector<RtbBlock> mBlocks;        // regions of the image still being rendered (Viewport.h:126)
     uint32_t mNumShards = 1, mErrorPasses = 0;
-    uint64_t mSeedValue = 12345;
     Random mRandom;
     HaltonSequence mHalton;
     std::string mError;

@@ -49,6 +49,8 @@ def load_host_library():
     lib.rtbh_viewport_progress.argtypes = [C.c_void_p, C.c_void_p]
     lib.rtbh_viewport_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     lib.rtbh_viewport_blocks.restype = C.c_uint32
+    lib.rtbh_pass_script.argtypes = [C.c_uint64, C.c_uint32, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.rtbh_pass_script.restype = None
     lib.rtbh_revise_blocks.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_float, C.c_float]
     lib.rtbh_revise_blocks.restype = C.c_uint32
     lib.rtbh_viewport_set_postprocess.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint32]
@@ -56,6 +58,17 @@ def load_host_library():
     lib.rtbh_viewport_counters.argtypes = [C.c_void_p, C.POINTER(capi.RtbCounters)]
     _lib = lib
     return lib
+
+
+def pass_script(num_passes, width, height, dimensions=128, seed=12345, aa_spread=0.5, extra_resets=1):
+    """The host prologue of `num_passes` Viewport::Render calls (Halton seed vectors + AA offsets) of a viewport seeded
+    with `seed`, resized to width x height and reset `extra_resets` more times (the oracle harness resets once after
+    Resize): what ViewportB200 hands to rtb_render_passes.  No device involved."""
+    lib = load_host_library()
+    seeds = np.zeros((num_passes, dimensions), dtype=np.uint32)
+    offsets = np.zeros((num_passes, 2), dtype=np.float32)
+    lib.rtbh_pass_script(seed, dimensions, aa_spread, width, height, extra_resets, num_passes, seeds.ctypes.data, offsets.ctypes.data)
+    return seeds, offsets
 
 
 def revise_blocks(blocks, errors, min_block_size=4, subdivision_treshold=0.005, convergence_treshold=0.0001):

@@ -642,7 +642,8 @@ def test_block_errors_against_the_live_reference(ctx, tmp_path, scene):
 @pytest.mark.skipif(not util.oracle_available("exact"), reason="prebuilt oracle/_ref/exact did not travel to this box")
 @pytest.mark.parametrize("subdivision,convergence,per_call", [(0.05, 0.01, 1), (0.3, 0.08, 1), (0.3, 0.08, 5)])
 def test_adaptive_rendering_against_the_live_reference(tmp_path, subdivision, convergence, per_call):
-    """AdaptiveRenderingSettings through the host viewport: after every pass the progress and the block list are the
+    """AdaptiveRenderingSettings through the host viewport, which draws its own pass script (seeded like the oracle's
+    fixed-seed build, so the two renders see the same random numbers): after every pass the progress and the block list are the
     reference's; at the end so are the sums (converged blocks stop receiving samples), the ray counters and the front
     buffer (a converged pixel keeps the value it had when it was last rendered).  The second parameter set converges
     the whole image: the last passes render nothing."""
@@ -665,6 +666,7 @@ def test_adaptive_rendering_against_the_live_reference(tmp_path, subdivision, co
         vp.set_adaptive(True, init, minb, maxb, subdivision, convergence)
         vp.set_postprocess(dithering=0.0)
         vp.resize(w, h)
+        vp.reset()              # the harness resets once more after Resize: the Halton scramble moves on (see test_host_scene)
         done = 0
         while done < passes:
             n = min(per_call, passes - done)

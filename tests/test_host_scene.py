@@ -257,3 +257,39 @@ def test_dds_bitmaps_decode_like_the_reference(built, tmp_path):
         same = a["texels"].view(np.uint32) == b["texels"].view(np.uint32)
         assert same.all(), "%s: %d of %d texel floats differ from Bitmap::GetPixel (first: %s vs %s)" % (
             names[i], int((~same).sum()), same.size, a["texels"].view(np.float32)[np.argmax(~same)], b["texels"].view(np.float32)[np.argmax(~same)])
+
+
+# ---- the host prologue of Viewport::Render: Halton seed vectors and anti-aliasing offsets -----------------------------------
+
+@pytest.mark.parametrize("scene,dims", [("c1_sphere_area", 128), ("cornell", 128), ("materials", 256), ("mesh_small", 128), ("textures", 192)])
+def test_pass_script_reproduces_the_golden_fixtures(scene, dims):
+    """ViewportB200's own generators (EntropyStream -> Random -> HaltonSequence; the 4-wide xorshift128+ generator behind
+    GetFloat2; FastLog / SinCos Box-Muller), seeded like the oracle's fixed-seed build, reproduce the reference's pass
+    scripts committed with the fixtures: every Halton seed integer (HaltonSampler.cpp:84-106, .h:26) and both floats
+    of every anti-aliasing offset (Viewport.cpp:235-242), bit for bit."""
+    from raytracer_b200 import capi, host_api
+    ps = capi.PassScript(util.golden(scene + ".passes"))
+    n = len(ps.seeds)
+    assert n == 4 and ps.seeds.shape[1] == dims
+    seeds, offsets = host_api.pass_script(n, 64, 64, dimensions=dims, seed=12345)      # make_golden.py: 64 x 64, RT_FIXED_SEED=12345
+    assert np.array_equal(seeds, ps.seeds)
+    assert offsets.tobytes() == np.ascontiguousarray(ps.offsets, dtype=np.float32).tobytes()
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
+@pytest.mark.parametrize("seed,w,h,dims,passes", [(12345, 8, 8, 256, 48), (777, 33, 17, 64, 9), (4242, 100, 76, 128, 16), (1, 1, 1, 1, 3)])
+def test_pass_script_against_the_live_reference(tmp_path, seed, w, h, dims, passes):
+    """Other seeds, image sizes (Viewport::Resize draws one number per pixel from the generator the AA offsets come
+    from, Viewport.cpp:99-102), dimension counts and more passes (the Halton digit counters carry)."""
+    from raytracer_b200 import capi, host_api
+    scn = os.path.join(util.GOLDEN, "scenes")
+    passp = str(tmp_path / "o.passes")
+    util.run_rtref(["render", "--scene", os.path.join(scn, "c1_sphere_area.json"), "--data", scn + "/", "--width", w, "--height", h, "--passes", passes,
+                    "--dims", dims, "--renderer", "Debug", "--dump-passes", passp], seed=str(seed))
+    ps = capi.PassScript(passp)
+    seeds, offsets = host_api.pass_script(passes, w, h, dimensions=dims, seed=seed)
+    assert np.array_equal(seeds, ps.seeds)
+    assert offsets.tobytes() == np.ascontiguousarray(ps.offsets, dtype=np.float32).tobytes()
+    # a different reset count is a different scramble (the sequence's generator is not re-seeded by Reset)
+    other, _ = host_api.pass_script(passes, w, h, dimensions=dims, seed=seed, extra_resets=0)
+    assert not np.array_equal(other, ps.seeds)
