@@ -80,12 +80,64 @@ def write_random_mesh(rng, path):
         f.write("newmtl a\nKd 0.8 0.4 0.3\nKe 0 0 0\n\nnewmtl b\nKd 0.3 0.5 0.8\nKe 0 0 0\n\n")
 
 
+def write_random_bitmaps(rng, out_dir):
+    """24-bit colour, 8-bit palette and 8-bit grey BMPs of odd sizes (the three layouts the BMP reader accepts)."""
+    from tests.scenes.make_scenes import write_bmp
+    tex = os.path.join(out_dir, "TEXTURES")
+    os.makedirs(tex, exist_ok=True)
+    a, b, c = (rng.randint(1, 97) for _ in range(3))
+    w, h = rng.randint(1, 19), rng.randint(1, 13)
+    write_bmp(os.path.join(tex, "color.bmp"), w, h, 24, lambda x, y: ((x * a + y * 7) % 256, (y * b + x * 3) % 256, (x * y * c + 11) % 256))
+    write_bmp(os.path.join(tex, "normal.bmp"), rng.randint(2, 9), rng.randint(2, 9), 24,
+              lambda x, y: (255, int(128 + 90 * math.cos(y * 0.9 + x * 0.3 + a)), int(128 + 90 * math.sin(x * 0.8 + b))))
+    write_bmp(os.path.join(tex, "env.bmp"), rng.randint(4, 24), rng.randint(2, 12), 24,
+              lambda x, y: (min(255, 40 + (x * a) % 60 + 10 * y), min(255, 60 + 8 * y), min(255, 30 + (y * b) % 90 + 4 * x)))
+    palette = [((i * 53 + a) % 256, (i * 97 + 30) % 256, (255 - i * 16) % 256, (i * 17) % 256) for i in range(16)]
+    write_bmp(os.path.join(tex, "pal.bmp"), rng.randint(1, 15), rng.randint(1, 9), 8, lambda x, y: (x * 3 + y * 5 + c) % 16, palette)
+    write_bmp(os.path.join(tex, "grey.bmp"), rng.randint(1, 9), rng.randint(1, 9), 8, lambda x, y: (x * 40 + y * 9 + a) % 256)
+
+
+def write_random_textured_mesh(rng, path):
+    """A folded strip with texture coordinates and (sometimes) vertex normals; the .mtl binds textures by file name."""
+    n = rng.randint(2, 8)
+    with_normals = rng.random() < 0.5
+    lines = ["mtllib %s.mtl" % os.path.basename(path)[:-4]]
+    for i in range(n + 1):
+        x = -1.5 + 3.0 * i / n
+        for j, z in enumerate((-0.6, 0.6)):
+            lines.append("v %.6f %.6f %.6f" % (x, 0.3 * math.sin(i * 1.3 + rng.random()) + 0.1 * j, z))
+    for i in range(n + 1):
+        for j in range(2):
+            lines.append("vt %.6f %.6f" % (rng.uniform(-1.5, 2.5), rng.uniform(-1.5, 2.5)))
+    if with_normals:
+        for i in range(2 * (n + 1)):
+            nx, ny, nz = rng.uniform(-0.4, 0.4), 1.0, rng.uniform(-0.4, 0.4)
+            l = math.sqrt(nx * nx + ny * ny + nz * nz)
+            lines.append("vn %.6f %.6f %.6f" % (nx / l, ny / l, nz / l))
+    lines.append("usemtl cloth")
+    fmt = "%d/%d/%d" if with_normals else "%d/%d"
+    for i in range(n):
+        quad = (2 * i + 1, 2 * i + 2, 2 * i + 4, 2 * i + 3)
+        for tri in ((0, 1, 2), (0, 2, 3)):
+            lines.append("f " + " ".join(fmt % ((quad[k],) * (3 if with_normals else 2)) for k in tri))
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    with open(path[:-4] + ".mtl", "w") as f:
+        f.write("newmtl cloth\nKd 0.9 0.8 0.7\nKe 0 0 0\nmap_Kd ../TEXTURES/%s\n" % rng.choice(["color.bmp", "pal.bmp"]))
+        if rng.random() < 0.6:
+            f.write("norm ../TEXTURES/normal.bmp\n")
+        f.write("\n")
+
+
 def random_scene(seed, out_dir):
     rng = random.Random(seed)
+    write_random_bitmaps(rng, out_dir)
     textures = [
         {"name": "checker", "type": "checkerboard", "colorA": _color(rng), "colorB": _color(rng)},
         {"name": "clouds", "type": "noise", "colorA": _color(rng, 0.0, 0.3), "colorB": _color(rng, 0.6, 1.0), "octaves": rng.randint(1, 5)},
         {"name": "blend", "type": "mix", "textureA": "checker", "textureB": "clouds", "weight": "clouds"},
+        {"name": "photo", "type": "bitmap", "path": "TEXTURES/color.bmp"},
+        {"name": "blend2", "type": "mix", "textureA": "blend", "textureB": "photo", "weight": "TEXTURES/grey.bmp"},
     ]
     materials = [{"name": "ground", "bsdf": "diffuse", "baseColor": _color(rng, 0.4, 0.9)}]
     for i in range(rng.randint(3, 7)):
@@ -101,11 +153,18 @@ def random_scene(seed, out_dir):
         if rng.random() < 0.2:
             m["emissionColor"] = _color(rng, 0.2, 3.0)
         if rng.random() < 0.3:
-            m["baseColorTexture"] = rng.choice(["checker", "clouds", "blend"])
+            m["baseColorTexture"] = rng.choice(["checker", "clouds", "blend", "photo", "blend2", "TEXTURES/pal.bmp"])
         if rng.random() < 0.15 and "roughness" in m:
             m["roughnessTexture"] = "clouds"
         if rng.random() < 0.15:
             m["metalness"] = round(rng.random(), 3)
+            if rng.random() < 0.5:
+                m["metalnessTexture"] = "TEXTURES/grey.bmp"
+        if rng.random() < 0.25:
+            m["normalMap"] = "TEXTURES/normal.bmp"
+            m["normalMapStrength"] = round(rng.uniform(0.1, 1.0), 3)
+        if "emissionColor" in m and rng.random() < 0.4:
+            m["emissionTexture"] = rng.choice(["checker", "photo"])
         materials.append(m)
     names = [m["name"] for m in materials[1:]]
     objects = [{"type": "box", "size": [6.0, 0.2, 6.0], "transform": {"translation": [0.0, -1.6, 0.0]}, "material": "ground"}]
@@ -120,6 +179,10 @@ def random_scene(seed, out_dir):
         os.makedirs(os.path.join(out_dir, "MODELS"), exist_ok=True)
         write_random_mesh(rng, os.path.join(out_dir, "MODELS", "fuzz%d.obj" % seed))
         objects.append({"type": "mesh", "path": "MODELS/fuzz%d.obj" % seed, "transform": _xform(rng, 1.5, (-1.0, 0.5)), "material": rng.choice(names)})
+    if rng.random() < 0.4:
+        os.makedirs(os.path.join(out_dir, "MODELS"), exist_ok=True)
+        write_random_textured_mesh(rng, os.path.join(out_dir, "MODELS", "cloth%d.obj" % seed))
+        objects.append({"type": "mesh", "path": "MODELS/cloth%d.obj" % seed, "transform": _xform(rng, 1.5, (-0.5, 1.5)), "material": rng.choice(names)})
     lights = []
     for _ in range(rng.randint(1, 4)):
         kind = rng.choice(["area", "area", "point", "spot", "directional", "background"])
@@ -136,6 +199,8 @@ def random_scene(seed, out_dir):
                            "transform": {"orientation": [round(rng.uniform(20.0, 160.0), 2), round(rng.uniform(-180.0, 180.0), 2), 0.0]}})
         else:
             lights.append({"type": "background", "color": _color(rng, 0.05, 1.5)})
+            if rng.random() < 0.5:
+                lights[-1]["texture"] = "TEXTURES/env.bmp"
     camera = {"transform": {"translation": [round(rng.uniform(-1.0, 1.0), 3), round(rng.uniform(0.0, 2.0), 3), round(rng.uniform(-8.0, -5.0), 3)],
                             "orientation": [round(rng.uniform(0.0, 20.0), 2), round(rng.uniform(-10.0, 10.0), 2), 0.0]},
               "fieldOfView": round(rng.uniform(35.0, 80.0), 2)}
@@ -169,6 +234,19 @@ def assert_same_flat(mine, ref):
         for k in ("triangles", "indices", "shading", "materialIds"):
             assert a[k].tobytes() == b[k].tobytes(), "mesh %s differ" % k
     assert bytes(mine.camera) == bytes(ref.camera), "camera differs"
+    assert len(mine.textures) == len(ref.textures)
+    for i, (a, b) in enumerate(zip(mine.textures, ref.textures)):
+        for k in ("type", "width", "height", "numOctaves", "texA", "texB", "texWeight"):
+            assert a[k] == b[k], "texture %d: %s" % (i, k)
+        assert a["colorA"].tobytes() == b["colorA"].tobytes() and a["colorB"].tobytes() == b["colorB"].tobytes(), "texture %d colours" % i
+        assert (a["texels"] is None) == (b["texels"] is None)
+        if a["texels"] is not None:
+            assert a["texels"].tobytes() == b["texels"].tobytes(), "texture %d: decoded texels differ" % i
+    for what in ("material_textures", "light_textures"):
+        a, b = getattr(mine, what), getattr(ref, what)
+        assert (a is None) == (b is None), what
+        if a is not None:
+            assert a.tobytes() == b.tobytes(), "%s differ" % what
 
 
 @pytest.fixture(scope="module")
@@ -206,6 +284,13 @@ def test_random_scene_on_the_device_headers(hostsim, tmp_path, seed):
         util.assert_bit_identical(util.load_sum(out, W, H), util.load_sum(sump, W, H), "seed %d %s" % (seed, renderer))
         mine = json.loads(r.stdout.strip().splitlines()[-1])
         assert (mine["numRays"], mine["numShadowRays"], mine["numShadowRaysHit"]) == (meta["numRays"], meta["numShadowRays"], meta["numShadowRaysHit"])
+    # DebugRenderer: one mode per scene (normals / tangents / texture coordinates / material parameters ...)
+    mode = 1 + seed % 12
+    sump, passp, out = str(tmp_path / "dbg.sum"), str(tmp_path / "dbg.passes"), str(tmp_path / "dbg_mine.sum")
+    util.run_rtref(["render", "--scene", sj, "--data", data, "--width", W, "--height", H, "--passes", 1, "--dims", DIMS, "--renderer", "Debug",
+                    "--debug-mode", mode, "--dump-sum", sump, "--dump-passes", passp])
+    subprocess.run([HOSTSIM, "render", flat, passp, str(W), str(H), out, "2", "8", str(mode), "1", hostsim], stdout=subprocess.PIPE, check=True)
+    util.assert_bit_identical(util.load_sum(out, W, H), util.load_sum(sump, W, H), "seed %d debug mode %d" % (seed, mode))
 
 
 @pytest.mark.gpu
