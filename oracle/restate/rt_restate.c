@@ -10,6 +10,10 @@
  *   trace     Scene::Traverse / Traverse_Shadow           (<scene>.hits / .shadow_hits)
  *   debug     DebugRenderer TriangleID / Depth sum buffer (<scene>_dbgtri.sum / _dbgdepth.sum)
  *   texeval   ITexture::Evaluate (bitmap / checkerboard / noise / mix) at a list of coordinates (textures.texeval)
+ *   front     Viewport::PostProcessTile with the default PostprocessParams, no dithering   (<scene>_mis.front)
+ *   blockerr  Viewport::ComputeBlockError for a list of blocks                             (<scene>_mis.blockerr)
+ *   passes    the host prologue of Viewport::Render under the oracle's fixed seed: Halton seed vectors and
+ *             anti-aliasing offsets                                                        (<scene>.passes)
  * The full integrator (BSDFs, lights, MIS) is NOT restated here: for it the oracle is the reference itself
  * (oracle/_ref), whose sum buffers are the committed fixtures.
  *
@@ -550,11 +554,279 @@ static void tex_eval(const scene_t* s, uint32_t index, float u, float v, float o
     for (int k = 0; k < 4; ++k) out[k] = lerp_fma(lerp_fma(c00[k], c01[k], wy), lerp_fma(c10[k], c11[k], wy), wx);
 }
 
+/* ---- front buffer: Viewport::PostProcessTile, Rendering/Viewport.cpp:492-552 (bloom off) ---------------------------- */
+
+static uint32_t as_u32(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static float as_f32(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+/* FastLog(Vector4), Math/Transcendental.cpp:216-232: exponent split off with integer arithmetic, log1p polynomial */
+static float fast_log(float a)
+{
+    const uint32_t bits = as_u32(a);
+    const uint32_t e = (bits - 0x3f2aaaabu) & 0xff800000u;
+    const float m = as_f32(bits - e);
+    const float i = (float)(int32_t)e * 1.19209290e-7f;
+    const float f = m - 1.0f, s = f * f;
+    float r = fmaf(f, 0.230836749f, -0.279208571f);
+    const float t = fmaf(f, 0.331826031f, -0.498910338f);
+    r = fmaf(r, s, t);
+    r = fmaf(r, s, f);
+    return fmaf(i, 0.693147182f, r);
+}
+
+/* _mm_cvtps_epi32 / _mm_cvttps_epi32: "integer indefinite" outside the int32 range */
+static int32_t cvt_nearest(float v) { return (v >= -2147483648.0f && v < 2147483648.0f) ? (int32_t)lrintf(v) : INT32_MIN; }
+static int32_t cvt_truncate(float v) { return (v >= -2147483648.0f && v < 2147483648.0f) ? (int32_t)v : INT32_MIN; }
+
+/* FastExp(Vector4), Math/Transcendental.cpp:147-165 */
+static float fast_exp(float a)
+{
+    const float t = a * 1.442695041f, fi = floorf(t), f = t - fi;
+    const int32_t i = cvt_nearest(fi);
+    float y = fmaf(f, 0.3371894346f, 0.657636276f);
+    y = fmaf(f, y, 1.00172476f);
+    y = as_f32(as_u32(y) + ((uint32_t)i << 23));
+    if (-a >= 87.0f) y = 0.0f;
+    if (a >= 87.0f) y = INFINITY;
+    return y;
+}
+
+/* Convert_Linear_To_sRGB, Color/ColorHelpers.h:30-45 */
+static float to_srgb(float c)
+{
+    const float s1 = sqrtf(c), s2 = sqrtf(s1), s3 = sqrtf(s2);
+    float r = 0.585122381f * s1;
+    r = fmaf(s2, 0.783140355f, r);
+    r = fmaf(s3, -0.368262736f, r);
+    return minps(1.0f, maxps(0.0f, r));
+}
+
+/* ToneMap, Tonemapper::ACES (the default), Color/ColorHelpers.h:111-122 */
+static float aces(float c)
+{
+    const float t0 = c * fmaf(c, 2.51f, 0.03f);
+    const float t1 = fmaf(c, 2.43f, 0.59f);
+    const float t2 = fmaf(c, t1, 0.14f);
+    return to_srgb(t0 * (1.0f / t2));
+}
+
+/* one pixel with PostprocessParams' defaults (PostProcess.cpp:6-14): colorFilter 1, exposure 0, contrast 0.8,
+ * saturation 0.98, no bloom; dithering strength 0 (MulAndAdd(random, 0, x) == x); Vector4::ToBGR, Vector4ImplSSE.h:89-110 */
+static uint32_t front_pixel(const float* sum, float pixelScaling)
+{
+    const float contrast = 0.8f, saturation = 0.98f, colorScale = 1.0f * powf(2.0f, 0.0f);
+    float c[3];
+    for (int k = 0; k < 3; ++k) c[k] = sum[k] * pixelScaling;
+    const float gray = (c[0] * 0.2126f + c[1] * 0.7152f) + (c[2] * 0.0722f + 0.0f);            /* Dot3 = dpps */
+    uint32_t out = 0;
+    for (int k = 0; k < 3; ++k)
+    {
+        float v = maxps(0.0f, fmaf(c[k] - gray, saturation, gray));                               /* Max(0, Lerp(gray, rgb, saturation)) */
+        v = fast_exp(fast_log(v) * contrast);
+        v = aces(v * colorScale);
+        int32_t q = cvt_truncate(v * 255.0f);
+        q = q < 0 ? 0 : (q > 255 ? 255 : q);
+        out |= (uint32_t)q << (16 - 8 * k);                                                       /* x -> R (bits 16..23), z -> B */
+    }
+    return out;
+}
+
+/* ---- Viewport::ComputeBlockError, Rendering/Viewport.cpp:552-582 ----------------------------------------------------- */
+
+static float block_error(const float* sum, const float* sum2, uint32_t w, uint32_t h, uint32_t passes, const uint32_t* b /* minX maxX minY maxY */)
+{
+    const float scale = 1.0f / (float)passes;
+    float total = 0.0f;
+    for (uint32_t y = b[2]; y < b[3]; ++y)
+    {
+        float row = 0.0f;
+        for (uint32_t x = b[0]; x < b[1]; ++x)
+        {
+            const float* p = sum + ((size_t)y * w + x) * 3;
+            const float* q = sum2 + ((size_t)y * w + x) * 3;
+            float a[3], d[3];
+            for (int k = 0; k < 3; ++k) { a[k] = scale * p[k]; d[k] = absbits(a[k] - (2.0f * scale) * q[k]); }
+            row += (d[0] + 2.0f * d[1] + d[2]) / sqrtf(0.000001f + a[0] + 2.0f * a[1] + a[2]);
+        }
+        total += row;
+    }
+    const uint32_t area = (b[1] - b[0]) * (b[3] - b[2]);
+    return total * sqrtf((float)area / (float)(w * h)) / (float)area;
+}
+
+/* ---- the host prologue of Viewport::Render under RT_FIXED_SEED --------------------------------------------------------- */
+
+/* oracle/patch_ref.py P8: Entropy::GetInt = upper half of a splitmix64 step */
+static uint64_t entropyState;
+static uint32_t entropy_int(void)
+{
+    entropyState += 0x9E3779B97F4A7C15ULL;
+    uint64_t z = entropyState;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return (uint32_t)((z ^ (z >> 31)) >> 32);
+}
+
+/* math::Random, Math/Random.cpp:19-126: xoroshiro128+ (scalar) and a 2 x 64-bit xorshift128+ (the "SIMD4" generator) */
+typedef struct { uint64_t s[2]; uint64_t v4[2][2]; } rng_t;
+
+static void rng_seed(rng_t* r)                      /* Random::Reset: 2 + 4 + 8 integers per half; GCC evaluates the */
+{                                                   /* VectorInt4(x, y, z, w) arguments right to left                */
+    for (int i = 0; i < 2; ++i)
+    {
+        const uint64_t hi = entropy_int(), lo = entropy_int();
+        r->s[i] = (hi << 32) | lo;
+        uint32_t lane[4];
+        for (int k = 3; k >= 0; --k) lane[k] = entropy_int();
+        r->v4[i][0] = ((uint64_t)lane[1] << 32) | lane[0];
+        r->v4[i][1] = ((uint64_t)lane[3] << 32) | lane[2];
+        for (int k = 0; k < 8; ++k) entropy_int();   /* mSeedSimd8 */
+    }
+}
+
+static uint64_t rng_long(rng_t* r)                  /* Random::GetLong, :33-47 */
+{
+    const uint64_t s0 = r->s[0];
+    uint64_t s1 = r->s[1];
+    const uint64_t result = s0 + s1;
+    s1 ^= s0;
+    r->s[0] = ((s0 << 24) | (s0 >> 40)) ^ s1 ^ (s1 << 16);
+    r->s[1] = (s1 << 37) | (s1 >> 27);
+    return result;
+}
+
+static double rng_double(rng_t* r) { return (double)rng_long(r) / (double)UINT64_MAX; }           /* :60-63 */
+
+static void rng_float2(rng_t* r, float* x, float* y)   /* GetFloat2 = lanes 0, 1 of GetVector4, :65-68, 83-126 */
+{
+    uint64_t out = 0;
+    for (int l = 0; l < 2; ++l)
+    {
+        const uint64_t s0 = r->v4[1][l];
+        uint64_t s1 = r->v4[0][l];
+        if (l == 0) out = s0 + s1;
+        s1 <<= 23;
+        r->v4[0][l] = s0;
+        r->v4[1][l] = (s0 ^ s1) ^ ((s0 >> 5) ^ (s1 >> 18));
+    }
+    *x = as_f32(((uint32_t)out & 0x007fffffu) | 0x3f800000u) - 1.0f;
+    *y = as_f32(((uint32_t)(out >> 32) & 0x007fffffu) | 0x3f800000u) - 1.0f;
+}
+
+/* HaltonSequence, Sampling/HaltonSampler.cpp:37-230 (scrambled Halton with a random start, double precision) */
+#define HALTON_WIDTH 64
+typedef struct
+{
+    uint32_t dims;
+    uint32_t* base; uint64_t* start; uint64_t** perm;
+    uint64_t (*digit)[HALTON_WIDTH + 1]; uint64_t (*power)[HALTON_WIDTH]; double (*rnd)[HALTON_WIDTH + 1];
+    rng_t rng;
+} halton_t;
+
+static void halton_init(halton_t* h, uint32_t dims)
+{
+    h->dims = dims;
+    h->base = calloc(dims + 1, sizeof(uint32_t)); h->start = calloc(dims + 1, sizeof(uint64_t)); h->perm = calloc(dims + 1, sizeof(uint64_t*));
+    h->digit = calloc(dims + 1, sizeof(*h->digit)); h->power = calloc(dims + 1, sizeof(*h->power)); h->rnd = calloc(dims + 1, sizeof(*h->rnd));
+    /* InitPrimes, :135-154: the first `dims` primes by trial division */
+    for (uint32_t m = 0, candidate = 2; m < dims; ++candidate)
+    {
+        int isPrime = 1;
+        for (uint64_t i = 2; (double)i <= sqrt((double)candidate); ++i) if (candidate % i == 0) { isPrime = 0; break; }
+        if (isPrime) h->base[m++] = candidate;
+    }
+    /* InitStart, :156-183: a random start index, built digit by digit from one uniform double */
+    for (uint32_t i = 0; i < dims; ++i)
+    {
+        double r = rng_double(&h->rng);
+        const uint64_t base = h->base[i];
+        uint64_t z = 0, b = base;
+        while (r > 1.0e-16)
+        {
+            if (r >= 1.0 / b)
+            {
+                const uint64_t cnt = (uint64_t)floor(r * b);
+                r = r - cnt * 1.0 / b;
+                z += cnt * b / base;
+            }
+            b *= base;
+        }
+        h->start[i] = z;
+    }
+    for (uint32_t i = 0; i < dims; ++i)              /* InitPowerBuffer */
+        for (uint32_t j = 0; j < HALTON_WIDTH; ++j) h->power[i][j] = j ? h->power[i][j - 1] * h->base[i] : h->base[i];
+    /* InitPermutation, :113-133: random transpositions of the digits */
+    for (uint32_t i = 0; i < dims; ++i)
+    {
+        h->perm[i] = malloc(h->base[i] * sizeof(uint64_t));
+        for (uint64_t j = 0; j < h->base[i]; ++j) h->perm[i][j] = j;
+        for (uint64_t j = 1; j < h->base[i]; ++j)
+        {
+            const uint64_t other = (uint64_t)floor(rng_double(&h->rng) * h->base[i]);
+            if (other != 0 && other < h->base[i]) { const uint64_t k = h->perm[i][j]; h->perm[i][j] = h->perm[i][other]; h->perm[i][other] = k; }
+        }
+    }
+    /* InitExpansion: digits of start - 1, radical inverse accumulated from the most significant digit down */
+    for (uint32_t i = 0; i < dims; ++i)
+    {
+        uint64_t n = h->start[i] - 1;
+        int j = 0;
+        while (n > 0 && j < HALTON_WIDTH) { h->digit[i][j] = n % h->base[i]; n /= h->base[i]; ++j; }
+        for (--j; j >= 0; --j) h->rnd[i][j] = h->rnd[i][j + 1] + h->perm[i][h->digit[i][j]] * 1.0 / h->power[i][j];
+    }
+}
+
+static void halton_next(halton_t* h)                 /* NextSample, :84-106: increment with carry, refresh the sums */
+{
+    for (uint32_t i = 0; i < h->dims; ++i)
+    {
+        int j = 0;
+        while (h->digit[i][j] + 1 >= h->base[i] && j + 1 < HALTON_WIDTH) ++j;
+        h->digit[i][j]++;
+        h->rnd[i][j] = h->rnd[i][j + 1] + h->perm[i][h->digit[i][j]] * 1.0 / h->power[i][j];
+        for (--j; j >= 0; --j)
+        {
+            h->digit[i][j] = 0;
+            h->rnd[i][j] = h->rnd[i][j + 1] + h->perm[i][0] * 1.0 / h->power[i][j];
+        }
+    }
+}
+
+/* Sin(Vector4) lane, Math/Transcendental.cpp:54-76 (coefficients :26-34); SinCos(x) = Sin((x, x + pi/2)), TranscendentalImpl.h:22-26 */
+static float sin_lane(float a)
+{
+    const int32_t i = cvt_nearest(a * (1.0f / 3.14159265359f));
+    const float x = fmaf(-(float)i, 3.14159265359f, a);            /* NegMulAndAdd = fnmadd */
+    const float x2 = x * x;
+    float y = fmaf(-2.0532988642e-08f, x2, 2.7040521217e-06f);
+    y = fmaf(y, x2, -1.9812576647e-04f);
+    y = fmaf(y, x2, 8.3325579762e-03f);
+    y = fmaf(y, x2, -1.6666577756e-01f);
+    y = fmaf(y, x2, 9.9999970197e-01f);
+    y *= x;
+    return as_f32(as_u32(y) ^ ((uint32_t)i << 31));
+}
+
+/* scalar FastLog, Math/Transcendental.cpp:194-214: the same polynomial as the vector one, without fused operations */
+static float fast_log_scalar(float x)
+{
+    const uint32_t bits = as_u32(x);
+    const uint32_t e = (bits - 0x3f2aaaabu) & 0xff800000u;
+    const float m = as_f32(bits - e);
+    const float i = 1.19209290e-7f * (float)(int32_t)e;
+    const float f = m - 1.0f, s = f * f;
+    float r = 0.230836749f * f - 0.279208571f;
+    const float t = 0.331826031f * f - 0.498910338f;
+    r = r * s + t;
+    r = r * s + f;
+    return i * 0.693147182f + r;
+}
+
 int main(int argc, char** argv)
 {
     _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);
     _MM_SET_DENORMALS_ZERO_MODE(_MM_DENORMALS_ZERO_ON);
-    if (argc < 2) die("usage: rt_restate trace|sampler|primary|debug ...");
+    if (argc < 2) die("usage: rt_restate trace|sampler|primary|debug|texeval|front|blockerr|passes ...");
 
     if (!strcmp(argv[1], "trace") && argc >= 5)
     {
@@ -647,6 +919,63 @@ int main(int argc, char** argv)
                     px[0] = px[0] + rgb[0]; px[1] = px[1] + rgb[1]; px[2] = px[2] + rgb[2];
                 }
             fwrite(sum, 4, (size_t)w * h * 3, o);
+        }
+        fclose(o);
+        return 0;
+    }
+    if (!strcmp(argv[1], "front") && argc >= 7)
+    {
+        /* front <sum raster> <w> <h> <passes> <out.bgra> */
+        const uint32_t w = (uint32_t)atoi(argv[3]), h = (uint32_t)atoi(argv[4]), passes = (uint32_t)atoi(argv[5]);
+        float* sum = malloc((size_t)w * h * 12 + 4);
+        FILE* f = fopen(argv[2], "rb"); if (!f || fread(sum, 12, (size_t)w * h, f) != (size_t)w * h) die("cannot read sum");
+        fclose(f);
+        FILE* o = fopen(argv[6], "wb");
+        const float pixelScaling = 1.0f / (float)passes;                /* 1 / (1 + passesFinished), Viewport.cpp:499 */
+        for (size_t i = 0; i < (size_t)w * h; ++i) { const uint32_t px = front_pixel(sum + 3 * i, pixelScaling); fwrite(&px, 4, 1, o); }
+        fclose(o);
+        return 0;
+    }
+    if (!strcmp(argv[1], "blockerr") && argc >= 9)
+    {
+        /* blockerr <sum> <sum2> <w> <h> <passes> <blocks u32x4> <out f32> */
+        const uint32_t w = (uint32_t)atoi(argv[4]), h = (uint32_t)atoi(argv[5]), passes = (uint32_t)atoi(argv[6]);
+        float* sum = malloc((size_t)w * h * 12 + 4); float* sum2 = malloc((size_t)w * h * 12 + 4);
+        FILE* f = fopen(argv[2], "rb"); if (!f || fread(sum, 12, (size_t)w * h, f) != (size_t)w * h) die("cannot read sum");
+        fclose(f);
+        f = fopen(argv[3], "rb"); if (!f || fread(sum2, 12, (size_t)w * h, f) != (size_t)w * h) die("cannot read sum2");
+        fclose(f);
+        f = fopen(argv[7], "rb"); if (!f) die("cannot read blocks");
+        FILE* o = fopen(argv[8], "wb");
+        uint32_t b[4];
+        while (fread(b, 4, 4, f) == 4) { const float e = block_error(sum, sum2, w, h, passes, b); fwrite(&e, 4, 1, o); }
+        fclose(f); fclose(o);
+        return 0;
+    }
+    if (!strcmp(argv[1], "passes") && argc >= 8)
+    {
+        /* passes <seed> <dims> <w> <h> <numPasses> <out.passes>: what the oracle harness' Viewport draws under RT_FIXED_SEED=seed.
+         * Construction order (Viewport.h:106-107): mRandomGenerator, then the Halton sequence's generator.  Resize draws one
+         * Vector4 per pixel from mRandomGenerator (Viewport.cpp:99-102) and resets; the harness resets once more. */
+        entropyState = strtoull(argv[2], NULL, 10);
+        const uint32_t dims = (uint32_t)atoi(argv[3]), w = (uint32_t)atoi(argv[4]), h = (uint32_t)atoi(argv[5]), n = (uint32_t)atoi(argv[6]);
+        rng_t viewport; halton_t halton;
+        rng_seed(&viewport); rng_seed(&halton.rng);
+        float x, y;
+        for (uint64_t i = 0; i < (uint64_t)w * h; ++i) rng_float2(&viewport, &x, &y);
+        halton_init(&halton, dims);
+        halton_init(&halton, dims);                  /* (the first initialisation is leaked: this is a one-shot tool) */
+        FILE* o = fopen(argv[7], "wb");
+        fwrite(&n, 4, 1, o); fwrite(&dims, 4, 1, o);
+        for (uint32_t p = 0; p < n; ++p)
+        {
+            halton_next(&halton);
+            for (uint32_t d = 0; d < dims; ++d) { const uint32_t v = (uint32_t)(halton.rnd[d][0] * (double)UINT32_MAX); fwrite(&v, 4, 1, o); }   /* GetInt, HaltonSampler.h:26 */
+            /* GetFloatNormal2(GetFloat2()) * antiAliasingSpread (0.5), SamplingHelpers.cpp:145-149, Viewport.cpp:235-242 */
+            rng_float2(&viewport, &x, &y);
+            const float radius = sqrtf(-2.0f * fast_log_scalar(x)), angle = 2.0f * 3.14159265359f * y;
+            const float off[2] = { radius * sin_lane(angle + 0.0f) * 0.5f, radius * sin_lane(angle + 3.14159265359f / 2.0f) * 0.5f };
+            fwrite(off, 4, 2, o);
         }
         fclose(o);
         return 0;

@@ -125,6 +125,17 @@ def main():
         for r in renderers:
             rname, dbg = RENDERERS[r]
             extra = ["--dump-passes", os.path.join(out, name + ".passes")] if r == renderers[0] else []
+            if name in ("cornell", "mesh_small") and r == "mis":
+                # Viewport::ComputeBlockError of the whole image, single pixels / rows / columns and random rectangles
+                brng = np.random.default_rng(11)
+                blocks = [(0, W, 0, H), (0, 1, 0, 1), (W - 1, W, H - 1, H), (0, W, 5, 6), (7, 8, 0, H)]
+                while len(blocks) < 40:
+                    x0, x1 = sorted(int(v) for v in brng.integers(0, W + 1, 2))
+                    y0, y1 = sorted(int(v) for v in brng.integers(0, H + 1, 2))
+                    if x0 < x1 and y0 < y1:
+                        blocks.append((x0, x1, y0, y1))
+                np.array(blocks, dtype=np.uint32).tofile(os.path.join(out, name + ".blocks"))
+                extra += ["--block-errors", os.path.join(out, name + ".blocks"), "--dump-block-errors", os.path.join(out, name + "_mis.blockerr")]
             c = rtref("render", *common, "--passes", PASSES, "--dims", dims, "--renderer", rname, "--debug-mode", dbg,
                       "--depth", 8, "--strategy", "all", "--dump-sum", os.path.join(out, "%s_%s.sum" % (name, r)),
                       "--dump-sum2", os.path.join(out, "%s_%s.sum2" % (name, r)) if r == "mis" else "/dev/null",

@@ -272,3 +272,13 @@ def test_golden_fixtures_reproduce_from_the_reference(tmp_path):
                            "--passes", 4, "--dims", 128, "--depth", 8, "--strategy", "all", "--dump-sum", out])
     util.assert_bit_identical(util.load_sum(out, 64, 64), util.load_sum(util.golden("cornell_mis.sum"), 64, 64), "cornell golden")
     assert meta["numRays"] == json.load(open(util.golden("cornell_mis.json")))["numRays"]
+
+
+@pytest.mark.parametrize("scene", ["cornell", "mesh_small"])
+def test_hostsim_block_errors_golden(hostsim, tmp_path, scene):
+    """The device header's block-error arithmetic on the golden sum / secondary-sum buffers (no live oracle needed)."""
+    meta = json.load(open(util.golden(scene + "_mis.json")))
+    out = str(tmp_path / "mine.err")
+    subprocess.run([HOSTSIM, "blockerrors", util.golden(scene + "_mis.sum"), util.golden(scene + "_mis.sum2"), str(meta["width"]), str(meta["height"]),
+                    str(meta["passes"]), util.golden(scene + ".blocks"), out], check=True)
+    assert open(out, "rb").read() == open(util.golden(scene + "_mis.blockerr"), "rb").read()

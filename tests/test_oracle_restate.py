@@ -90,3 +90,35 @@ def test_restate_texture_evaluation(restate, tmp_path):
     assert got.shape == want.shape and got.size > 0
     bad = np.argwhere(got != want)
     assert len(bad) == 0, "%d of %d floats differ (first: texture %d, point %d)" % (len(bad), got.size, bad[0][0] // 4400, (bad[0][0] // 4) % 1100)
+
+
+@pytest.mark.parametrize("scene", ["c1_sphere_area", "cornell", "cornell_dof", "materials", "mesh_small", "textures"])
+def test_restate_front_buffer(restate, tmp_path, scene):
+    """Viewport::PostProcessTile with the default PostprocessParams (saturation, FastLog / FastExp contrast, ACES curve,
+    sRGB approximation, ToBGR) restated in plain C: the reference's 8-bit front buffer of the golden renders."""
+    meta = json.load(open(util.golden(scene + "_mis.json")))
+    out = str(tmp_path / "front.bgra")
+    subprocess.run([RESTATE, "front", util.golden(scene + "_mis.sum"), str(meta["width"]), str(meta["height"]), str(meta["passes"]), out], check=True)
+    assert open(out, "rb").read() == open(util.golden(scene + "_mis.front"), "rb").read()
+
+
+@pytest.mark.parametrize("scene", ["cornell", "mesh_small"])
+def test_restate_block_errors(restate, tmp_path, scene):
+    """Viewport::ComputeBlockError (row sums left to right, rows top to bottom) for the whole image, single pixels,
+    rows, columns and random rectangles."""
+    meta = json.load(open(util.golden(scene + "_mis.json")))
+    out = str(tmp_path / "block.err")
+    subprocess.run([RESTATE, "blockerr", util.golden(scene + "_mis.sum"), util.golden(scene + "_mis.sum2"), str(meta["width"]), str(meta["height"]),
+                    str(meta["passes"]), util.golden(scene + ".blocks"), out], check=True)
+    want = np.fromfile(util.golden(scene + "_mis.blockerr"), dtype=np.float32)
+    assert len(want) == 40 and np.isfinite(want).all() and (want[:1] > 0).all()
+    assert open(out, "rb").read() == want.tobytes()
+
+
+@pytest.mark.parametrize("scene,dims", [("c1_sphere_area", 128), ("cornell", 128), ("materials", 256), ("mesh_small", 128), ("textures", 192)])
+def test_restate_pass_script(restate, tmp_path, scene, dims):
+    """The host prologue of Viewport::Render (entropy stream -> Random -> scrambled Halton; the 4-wide generator, FastLog
+    and Sin behind the Box-Muller anti-aliasing offset) restated in plain C: the committed pass scripts, byte for byte."""
+    out = str(tmp_path / "script.passes")
+    subprocess.run([RESTATE, "passes", "12345", str(dims), "64", "64", "4", out], check=True)
+    assert open(out, "rb").read() == open(util.golden(scene + ".passes"), "rb").read()
