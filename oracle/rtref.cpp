@@ -12,6 +12,7 @@
 //   sampler  GenericSampler streams for given pixels of given passes
 //   primary  Camera::GenerateRay for every pixel exactly as Viewport::RenderTile calls it
 //   texeval  ITexture::Evaluate of every texture of the scene at a list of (u, v)
+//   writeexr a seeded random HDR image written by the reference's own EXR writer (tinyexr) - test input for EXR readers
 #include "PCH.h"
 #include "Demo.h"
 #include "SceneLoader.h"
@@ -44,6 +45,7 @@
 #include "../Core/Sampling/GenericSampler.h"
 #include "../Core/Utils/Timer.h"
 #include "../Core/Utils/Memory.h"
+#include "../External/tinyexr/tinyexr.h"
 
 #include "rtb200.h"
 
@@ -769,6 +771,50 @@ static void CrashHandler(int sig)
     _exit(128 + sig);
 }
 
+// writeexr --out F.exr --width W --height H --channels 3|4 --type half|float --compression 0..4 [--seed S]
+// (channel names A, B, G, R as tinyexr's own SaveEXR orders them; values: HDR-ish noise with zeros, smooth regions and
+// large peaks so that every compressor sees runs, gradients and outliers)
+int CmdWriteExr(const Args& a)
+{
+    const int w = (int)a.Int("width", 16), h = (int)a.Int("height", 16), channels = (int)a.Int("channels", 3);
+    const bool half = a.Str("type", "half") == "half";
+    uint64_t state = (uint64_t)a.Int("seed", 1) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    auto next = [&state]() { state ^= state << 13; state ^= state >> 7; state ^= state << 17; return (uint32_t)(state >> 11); };
+    std::vector<std::vector<float>> planes(channels, std::vector<float>((size_t)w * h));
+    for (int c = 0; c < channels; ++c)
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x)
+            {
+                const uint32_t r = next();
+                float v = 0.25f * (float)((x / 3 + y / 2 + c) % 7);                  // plateaus
+                if (r % 5u == 0u) v += (float)(r >> 8) * (1.0f / 16777216.0f);      // noise
+                if (r % 97u == 0u) v *= 1000.0f;                                    // highlights
+                if (r % 11u == 0u) v = 0.0f;
+                planes[c][(size_t)y * w + x] = v;
+            }
+    EXRHeader header; InitEXRHeader(&header);
+    EXRImage image; InitEXRImage(&image);
+    image.num_channels = channels;
+    std::vector<float*> ptrs(channels);
+    for (int c = 0; c < channels; ++c) ptrs[c] = planes[c].data();
+    image.images = (unsigned char**)ptrs.data();
+    image.width = w; image.height = h;
+    header.num_channels = channels;
+    std::vector<EXRChannelInfo> infos(channels);
+    const char* names3[] = { "B", "G", "R" };
+    const char* names4[] = { "A", "B", "G", "R" };
+    std::vector<int> pixelTypes(channels, TINYEXR_PIXELTYPE_FLOAT), requested(channels, half ? TINYEXR_PIXELTYPE_HALF : TINYEXR_PIXELTYPE_FLOAT);
+    for (int c = 0; c < channels; ++c) { memset(&infos[c], 0, sizeof(EXRChannelInfo)); strncpy(infos[c].name, channels == 3 ? names3[c] : names4[c], 255); }
+    header.channels = infos.data();
+    header.pixel_types = pixelTypes.data();
+    header.requested_pixel_types = requested.data();
+    header.compression_type = (int)a.Int("compression", 0);
+    const char* err = nullptr;
+    const int ret = SaveEXRImageToFile(&image, &header, a.Str("out").c_str(), &err);
+    if (ret != TINYEXR_SUCCESS) { fprintf(stderr, "rtref: SaveEXRImageToFile: %s\n", err ? err : "?"); return 1; }
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     signal(SIGSEGV, CrashHandler);
@@ -781,6 +827,7 @@ int main(int argc, char** argv)
     if (a.cmd == "trace") return CmdTrace(a);
     if (a.cmd == "sampler") return CmdSampler(a);
     if (a.cmd == "texeval") return CmdTexEval(a);
+    if (a.cmd == "writeexr") return CmdWriteExr(a);
     if (a.cmd == "primary") return CmdPrimary(a);
     fprintf(stderr, "usage: rtref render|flat|trace|sampler|primary --scene X.json [options]\n");
     return 2;

@@ -12,8 +12,8 @@
 // Bitmap decodes into the float quadruples the reference's Bitmap::GetPixel returns for every texel (format decode +
 // sRGB -> linear for gamma-space files), which is what the device samples.  BMP and DDS (Core/Utils/BitmapDDS.cpp:
 // uncompressed 8 / 16 / 32-bit integer, half and float layouts, R11G11B10, R9G9B9E5, BC1 / BC4 / BC5 blocks) are read;
-// OpenEXR containers are recognised and REFUSED with an error (the reference reads them through the third-party
-// tinyexr; silently dropping the texture would render a different image); any other unreadable file yields "no
+// OpenEXR files (which the reference reads through the third-party tinyexr) go through rt_exr.h: scan-line images with
+// 3 or 4 half / float channels, uncompressed or RLE / ZIP / ZIPS / PIZ compressed; any unreadable file yields "no
 // texture" exactly like the reference (Bitmap::Load fails, helpers::LoadTexture returns nullptr, MeshLoader.cpp:31-76).
 #pragma once
 
@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "rt_math.h"
+#include "rt_exr.h"
 #include "../../include/rtb200.h"
 
 namespace rt {
@@ -40,7 +41,7 @@ public:
     {
         Unknown = 0, R8_UNorm, R8G8_UNorm, B8G8R8_UNorm, B8G8R8A8_UNorm, R8G8B8A8_UNorm, B8G8R8A8_UNorm_Palette, B5G6R5_UNorm,
         R16_UNorm, R16G16_UNorm, R16G16B16A16_UNorm, R32_Float, R32G32_Float, R32G32B32_Float, R32G32B32A32_Float,
-        R11G11B10_Float, R16_Half, R16G16_Half, R16G16B16A16_Half, R9G9B9E5_SharedExp, BC1, BC4, BC5,
+        R11G11B10_Float, R16_Half, R16G16_Half, R16G16B16_Half, R16G16B16A16_Half, R9G9B9E5_SharedExp, BC1, BC4, BC5,
     };
 
     uint32_t GetWidth() const { return mWidth; }
@@ -81,14 +82,7 @@ public:
             fseek(file, 0, SEEK_SET);
             ok = LoadDDS(file, path);
         }
-        if (!ok && mError.empty())
-        {
-            // the reference would now try its OpenEXR reader (Bitmap::LoadEXR, third-party tinyexr)
-            uint8_t magic[4] = { 0, 0, 0, 0 };
-            fseek(file, 0, SEEK_SET);
-            if (fread(magic, 1, 4, file) == 4 && magic[0] == 0x76 && magic[1] == 0x2F && magic[2] == 0x31 && magic[3] == 0x01)
-                mError = std::string("OpenEXR bitmaps are not supported by this build: '") + path + "'";
-        }
+        if (!ok && mError.empty()) ok = LoadEXR(path);
         fclose(file);
         if (ok) Decode();
         return ok;
@@ -110,6 +104,7 @@ private:
         case Format::B8G8R8_UNorm: return 24;
         case Format::B8G8R8A8_UNorm: case Format::R8G8B8A8_UNorm: case Format::R16G16_UNorm: case Format::R32_Float:
         case Format::R11G11B10_Float: case Format::R16G16_Half: case Format::R9G9B9E5_SharedExp: return 32;
+        case Format::R16G16B16_Half: return 48;
         case Format::R16G16B16A16_UNorm: case Format::R32G32_Float: case Format::R16G16B16A16_Half: return 64;
         case Format::R32G32B32_Float: return 96;
         case Format::R32G32B32A32_Float: return 128;
@@ -213,6 +208,7 @@ private:
         case Format::R32G32B32A32_Float: { const uint8_t* s = row + 16u * (size_t)x; for (int k = 0; k < 4; ++k) c[k] = LoadF32(s + 4 * k); break; }
         case Format::R16_Half: c[0] = c[1] = c[2] = c[3] = HalfToFloat(Load16(row + 2u * (size_t)x)); break;
         case Format::R16G16_Half: { const uint8_t* s = row + 4u * (size_t)x; c[0] = HalfToFloat(Load16(s)); c[1] = HalfToFloat(Load16(s + 2)); break; }
+        case Format::R16G16B16_Half: { const uint8_t* s = row + 6u * (size_t)x; for (int k = 0; k < 3; ++k) c[k] = HalfToFloat(Load16(s + 2 * k)); break; }      // Load_Half4 & mask<1,1,1,0>
         case Format::R16G16B16A16_Half: { const uint8_t* s = row + 8u * (size_t)x; for (int k = 0; k < 4; ++k) c[k] = HalfToFloat(Load16(s + 2 * k)); break; }
         case Format::R9G9B9E5_SharedExp:
         {
@@ -279,6 +275,29 @@ private:
                 for (int k = 0; k < 4; ++k) out[k] = mLinearSpace ? c[k] : SrgbToLinear(c[k]);
             }
         mData.clear(); mData.shrink_to_fit(); mPalette.clear();
+    }
+
+    // Bitmap::LoadEXR, BitmapEXR.cpp:11-190: single-part scan-line files with 3 or 4 channels of one type (half or
+    // float); the planes arrive in the file's channel order (B, G, R or A, B, G, R) and are stored reversed; linear space
+    bool LoadEXR(const char* path)
+    {
+        exr::Image image;
+        std::string error;
+        if (!exr::Load(path, image, error)) { mError = error; return false; }
+        const size_t n = image.channels.size();
+        if (n != 3 && n != 4) return false;                                        // "Unsupported EXR format."
+        const int32_t type = image.channels[0].pixelType;
+        for (const exr::Channel& c : image.channels) if (c.pixelType != type) return false;      // "All channels must be of the same type"
+        if (type != exr::FLOAT && type != exr::HALF) return false;                 // "Unsupported EXR format: %i"
+        const Format format = type == exr::FLOAT ? (n == 3 ? Format::R32G32B32_Float : Format::R32G32B32A32_Float)
+                                                 : (n == 3 ? Format::R16G16B16_Half : Format::R16G16B16A16_Half);
+        if (!Init((uint32_t)image.width, (uint32_t)image.height, format, 0, true)) return false;
+        const size_t elem = type == exr::FLOAT ? 4 : 2;
+        for (size_t y = 0; y < (size_t)image.height; ++y)
+            for (size_t x = 0; x < (size_t)image.width; ++x)
+                for (size_t k = 0; k < n; ++k)
+                    memcpy(&mData[(size_t)mStride * y + (x * n + k) * elem], &image.planes[n - 1 - k][(y * image.width + x) * elem], elem);
+        return true;
     }
 
 #pragma pack(push, 2)

@@ -116,9 +116,8 @@ def test_loader_error_paths(built, tmp_path):
     _dds(str(tmp_path / "odd.dds"), 6, 6, (0x4, _fourcc(b"DXT1"), 0, 0, 0, 0, 0), bytes(32))
     with pytest.raises(capi.RtbError, match="not a multiple of 4"):
         load('{"materials": [{"name": "a", "baseColorTexture": "odd.dds"}]}')
-    (tmp_path / "x.exr").write_bytes(bytes([0x76, 0x2F, 0x31, 0x01]) + bytes(60))
-    with pytest.raises(capi.RtbError, match="OpenEXR bitmaps are not supported"):
-        load('{"lights": [{"type": "background", "color": [1.0, 1.0, 1.0], "texture": "x.exr"}]}')
+    (tmp_path / "x.exr").write_bytes(bytes([0x76, 0x2F, 0x31, 0x01]) + bytes(60))     # a truncated EXR: no texture, no error (tinyexr fails, Bitmap::Load fails)
+    load('{"lights": [{"type": "background", "color": [1.0, 1.0, 1.0], "texture": "x.exr"}]}')
     load('{"camera": {"bokehTexture": "missing.bmp"}}')              # unreadable bokeh bitmap: plain circular bokeh, as in the reference
     s = load('{}')                     # empty scene loads (RenderingTest.EmptyScene)
     assert s.stats() == dict(objects=0, lights=0, tlas_nodes=0)
@@ -257,6 +256,72 @@ def test_dds_bitmaps_decode_like_the_reference(built, tmp_path):
         same = a["texels"].view(np.uint32) == b["texels"].view(np.uint32)
         assert same.all(), "%s: %d of %d texel floats differ from Bitmap::GetPixel (first: %s vs %s)" % (
             names[i], int((~same).sum()), same.size, a["texels"].view(np.float32)[np.argmax(~same)], b["texels"].view(np.float32)[np.argmax(~same)])
+
+
+def _write_plain_exr(path, w, h, chans, line_order, ymin=0, xmin=0, seed=0):
+    """Uncompressed scan-line EXR written by hand: `chans` = [(name, pixel type 1 = half / 2 = float)], rows stored in
+    `line_order` (0 increasing, 1 decreasing), data window offset by (xmin, ymin)."""
+    import struct
+    rng = np.random.default_rng(seed)
+    planes = {c: (rng.normal(size=(h, w)) * 3).astype(np.float16 if t == 1 else np.float32) for c, t in chans}
+    attr = lambda name, typ, data: name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<I", len(data)) + data
+    chl = b"".join(c.encode() + b"\0" + struct.pack("<iBBBBii", t, 0, 0, 0, 0, 1, 1) for c, t in chans) + b"\0"
+    head = b"\x76\x2f\x31\x01" + struct.pack("<I", 2) + b"".join([
+        attr("channels", "chlist", chl), attr("compression", "compression", b"\0"),
+        attr("dataWindow", "box2i", struct.pack("<4i", xmin, ymin, xmin + w - 1, ymin + h - 1)),
+        attr("displayWindow", "box2i", struct.pack("<4i", 0, 0, w - 1, h - 1)), attr("lineOrder", "lineOrder", bytes([line_order])),
+        attr("pixelAspectRatio", "float", struct.pack("<f", 1.0)), attr("screenWindowCenter", "v2f", struct.pack("<2f", 0, 0)),
+        attr("screenWindowWidth", "float", struct.pack("<f", 1.0))]) + b"\0"
+    rows = list(range(h)) if line_order == 0 else list(range(h - 1, -1, -1))
+    blocks = []
+    for y in rows:
+        data = b"".join(planes[c][y].tobytes() for c, _ in chans)
+        blocks.append(struct.pack("<ii", ymin + y, len(data)) + data)
+    off, table = len(head) + 8 * h, b""
+    for b in blocks:
+        table += struct.pack("<Q", off)
+        off += len(b)
+    open(path, "wb").write(head + table + b"".join(blocks))
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="needs oracle/_ref/exact (authoring container)")
+def test_exr_bitmaps_decode_like_the_reference(built, tmp_path):
+    """OpenEXR through the product's own reader (host/rt_exr.h) vs the reference's Bitmap::LoadEXR (tinyexr): files
+    written by tinyexr itself in every compression it has (none, RLE, ZIPS, ZIP, PIZ) x half / float x 3 / 4 channels
+    at sizes with partial blocks, plus hand-written files with decreasing line order and offset data windows; every
+    texel equal to the reference's Bitmap::GetPixel.  Layouts the reference refuses (2 channels, mixed or integer
+    channel types) bind no texture in either."""
+    os.makedirs(tmp_path / "TEX")
+    cases = []
+    for comp in range(5):
+        for typ in ("half", "float"):
+            for ch, (w, h) in ((3, (21, 37)), (4, (64, 33)), (3, (300, 70)), (3, (1, 1))):
+                name = "c%d_%s_%d_%dx%d" % (comp, typ, ch, w, h)
+                util.run_rtref(["writeexr", "--out", str(tmp_path / "TEX" / (name + ".exr")), "--width", w, "--height", h, "--channels", ch,
+                                "--type", typ, "--compression", comp, "--seed", len(cases) + 1])
+                cases.append(name)
+    half3, float4 = [("B", 1), ("G", 1), ("R", 1)], [("A", 2), ("B", 2), ("G", 2), ("R", 2)]
+    for name, args in (("inc", (9, 7, half3, 0)), ("dec", (9, 7, half3, 1)), ("win", (5, 6, float4, 0, -3, 4)), ("decwin", (5, 6, [("B", 2), ("G", 2), ("R", 2)], 1, 10, -2))):
+        _write_plain_exr(str(tmp_path / "TEX" / (name + ".exr")), *args, seed=len(cases))
+        cases.append(name)
+    refused = {"mixed": [("B", 1), ("G", 2), ("R", 1)], "two": [("G", 1), ("R", 1)], "uint": [("B", 0), ("G", 0), ("R", 0)]}
+    for name, chans in refused.items():
+        _write_plain_exr(str(tmp_path / "TEX" / (name + ".exr")), 5, 6, chans, 0)
+    names = cases + sorted(refused)
+    mats = [{"name": n, "bsdf": "diffuse", "baseColor": [1.0, 1.0, 1.0], "baseColorTexture": "TEX/%s.exr" % n} for n in names]
+    objs = [{"type": "sphere", "radius": 0.4, "transform": {"translation": [float(i), 0.0, 0.0]}, "material": n} for i, n in enumerate(names)]
+    sj = str(tmp_path / "exr.json")
+    json.dump({"materials": mats, "objects": objs, "lights": [{"type": "background", "color": [1.0, 1.0, 1.0]}]}, open(sj, "w"))
+    ref_out, my_out = str(tmp_path / "ref.rtb"), str(tmp_path / "mine.rtb")
+    util.run_rtref(["flat", "--scene", sj, "--data", str(tmp_path) + "/", "--out", ref_out])
+    host_api.Scene(sj, str(tmp_path) + "/").save_flat(my_out, 64, 64)
+    mine, ref = capi.SceneFile(my_out), capi.SceneFile(ref_out)
+    assert len(ref.textures) == len(cases), "the reference did not load every EXR case (or loaded a refused one)"
+    assert len(mine.textures) == len(ref.textures)
+    assert mine.material_textures.tobytes() == ref.material_textures.tobytes()
+    for i, (a, b) in enumerate(zip(mine.textures, ref.textures)):
+        assert (a["width"], a["height"]) == (b["width"], b["height"]), cases[i]
+        assert a["texels"].tobytes() == b["texels"].tobytes(), "%s: texels differ from Bitmap::GetPixel" % cases[i]
 
 
 # ---- the host prologue of Viewport::Render: Halton seed vectors and anti-aliasing offsets -----------------------------------
