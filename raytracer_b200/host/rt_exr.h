@@ -463,6 +463,8 @@ inline bool Load(const char* path, Image& image, std::string& error)
     const int linesPerBlock = compression == ZIP ? 16 : (compression == PIZ ? 32 : 1);
     const size_t numBlocks = (size_t)((height + linesPerBlock - 1) / linesPerBlock);
     if (pos + numBlocks * 8 > f.size()) return false;
+    // a corrupt data window must not turn into a multi-gigabyte allocation: no compressor here gets beyond ~1000 : 1
+    if ((uint64_t)lineBytes * (uint64_t)height / 4096u > f.size()) return false;
     image.planes.resize(image.channels.size());
     for (size_t c = 0; c < image.channels.size(); ++c) image.planes[c].assign((size_t)width * height * PixelSize(image.channels[c].pixelType), 0);
 

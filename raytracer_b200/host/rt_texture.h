@@ -22,6 +22,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -283,7 +284,8 @@ private:
     {
         exr::Image image;
         std::string error;
-        if (!exr::Load(path, image, error)) { mError = error; return false; }
+        try { if (!exr::Load(path, image, error)) { mError = error; return false; } }
+        catch (const std::bad_alloc&) { return false; }
         const size_t n = image.channels.size();
         if (n != 3 && n != 4) return false;                                        // "Unsupported EXR format."
         const int32_t type = image.channels[0].pixelType;
