@@ -551,6 +551,19 @@ int CmdRender(const Args& a)
         WriteBytes(f, errors.data(), errors.size() * 4);
         fclose(f);
     }
+    if (a.Has("dump-overlay"))
+    {
+        // Viewport::VisualizeActiveBlocks on a copy of the front buffer
+        Bitmap overlay;
+        Bitmap::InitData init;
+        init.width = w; init.height = h; init.format = Bitmap::Format::B8G8R8A8_UNorm; init.linearSpace = false;
+        if (!overlay.Init(init)) Die("overlay bitmap");
+        memcpy(overlay.GetData(), vp.GetFrontBuffer().GetData(), (size_t)w * h * 4);
+        vp.VisualizeActiveBlocks(overlay);
+        FILE* f = fopen(a.Str("dump-overlay").c_str(), "wb");
+        WriteBytes(f, overlay.GetData(), (size_t)w * h * 4);
+        fclose(f);
+    }
     if (a.Has("dump-front"))
     {
         FILE* f = fopen(a.Str("dump-front").c_str(), "wb");

@@ -120,6 +120,12 @@ uint32_t rtbh_viewport_blocks(void* vp, RtbBlock* out, uint32_t capacity)
     return (uint32_t)b.size();
 }
 
+// ViewportB200::VisualizeBlocks on caller data (Viewport::VisualizeActiveBlocks; host only)
+void rtbh_visualize_blocks(uint32_t* bgra, uint32_t width, const RtbBlock* blocks, uint32_t numBlocks)
+{
+    rt::ViewportB200::VisualizeBlocks(bgra, width, blocks, numBlocks);
+}
+
 // ViewportB200::PassScript: seeds[numPasses * dimensions], sampleOffsets[numPasses * 2] (host prologue only, no device)
 void rtbh_pass_script(uint64_t seed, uint32_t dimensions, float antiAliasingSpread, uint32_t width, uint32_t height, uint32_t extraResets, uint32_t numPasses, uint32_t* seeds, float* sampleOffsets)
 {

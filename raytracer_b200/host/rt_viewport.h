@@ -401,6 +401,34 @@ public:
     }
     const std::vector<RtbBlock>& GetBlocks() const { return mBlocks; }
 
+    // Viewport::VisualizeActiveBlocks (Viewport.cpp:734-771) on a front-buffer image in host memory (width * height
+    // 0x00RRGGBB as GetFrontBuffer delivers it): the blocks still being rendered tinted red (LdrColor Lerp with
+    // alpha 64, LdrColor.h:18-26) with solid red borders
+    static void VisualizeBlocks(uint32_t* bgra, uint32_t width, const RtbBlock* blocks, size_t numBlocks)
+    {
+        const uint8_t color[4] = { 0, 0, 255, 255 };        // b, g, r, a
+        const uint32_t solid = 0xFFFF0000u, alpha = 64;
+        for (size_t i = 0; i < numBlocks; ++i)
+        {
+            const RtbBlock& b = blocks[i];
+            for (uint32_t y = b.minY; y < b.maxY; ++y)
+                for (uint32_t x = b.minX; x < b.maxX; ++x)
+                {
+                    uint32_t& pixel = bgra[(size_t)y * width + x];
+                    uint32_t out = 0;
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const uint32_t a = (pixel >> (8 * k)) & 0xFFu;
+                        out |= (((a * (255u - alpha) + color[k] * alpha) / 256u) & 0xFFu) << (8 * k);
+                    }
+                    pixel = out;
+                }
+            for (uint32_t y = b.minY; y < b.maxY; ++y) { bgra[(size_t)y * width + b.minX] = solid; bgra[(size_t)y * width + b.maxX - 1] = solid; }
+            for (uint32_t x = b.minX; x < b.maxX; ++x) { bgra[(size_t)b.minY * width + x] = solid; bgra[(size_t)(b.maxY - 1) * width + x] = solid; }
+        }
+    }
+    void VisualizeActiveBlocks(uint32_t* bgra) const { VisualizeBlocks(bgra, mWidth, mBlocks.data(), mBlocks.size()); }
+
 private:
     // Viewport::BuildInitialBlocksList, Viewport.cpp:618-645
     void BuildInitialBlocksList()

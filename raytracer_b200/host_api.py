@@ -49,6 +49,8 @@ def load_host_library():
     lib.rtbh_viewport_progress.argtypes = [C.c_void_p, C.c_void_p]
     lib.rtbh_viewport_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     lib.rtbh_viewport_blocks.restype = C.c_uint32
+    lib.rtbh_visualize_blocks.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    lib.rtbh_visualize_blocks.restype = None
     lib.rtbh_pass_script.argtypes = [C.c_uint64, C.c_uint32, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
     lib.rtbh_pass_script.restype = None
     lib.rtbh_revise_blocks.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_float, C.c_float]
@@ -69,6 +71,15 @@ def pass_script(num_passes, width, height, dimensions=128, seed=12345, aa_spread
     offsets = np.zeros((num_passes, 2), dtype=np.float32)
     lib.rtbh_pass_script(seed, dimensions, aa_spread, width, height, extra_resets, num_passes, seeds.ctypes.data, offsets.ctypes.data)
     return seeds, offsets
+
+
+def visualize_blocks(front, blocks):
+    """Viewport::VisualizeActiveBlocks on a (height, width) uint32 front-buffer image: returns the tinted copy."""
+    lib = load_host_library()
+    out = np.ascontiguousarray(front, dtype=np.uint32).copy()
+    blocks = np.ascontiguousarray(blocks, dtype=np.uint32).reshape(-1, 4)
+    lib.rtbh_visualize_blocks(out.ctypes.data, out.shape[1], blocks.ctypes.data, len(blocks))
+    return out
 
 
 def revise_blocks(blocks, errors, min_block_size=4, subdivision_treshold=0.005, convergence_treshold=0.0001):

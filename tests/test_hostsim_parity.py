@@ -264,6 +264,24 @@ def test_block_list_revision_against_the_live_reference(tmp_path, subdivision, c
 
 
 @pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
+def test_active_block_overlay_against_the_live_reference(tmp_path):
+    """Viewport::VisualizeActiveBlocks (Viewport.cpp:734-771): the reference's front buffer + its final block list through
+    ViewportB200::VisualizeBlocks gives the reference's overlay image (8-bit blend, borders, overlapping order)."""
+    from raytracer_b200 import host_api
+    w, h, passes = 96, 80, 12
+    scn = os.path.join(util.GOLDEN, "scenes")
+    progp, frontp, overp = str(tmp_path / "o.progress"), str(tmp_path / "o.front"), str(tmp_path / "o.overlay")
+    util.run_rtref(["render", "--scene", os.path.join(scn, "cornell.json"), "--data", scn + "/", "--width", w, "--height", h, "--passes", passes, "--dims", 256,
+                    "--adaptive", 1, "--adaptive-initial", 2, "--adaptive-min-block", 4, "--adaptive-max-block", 32, "--adaptive-subdivision", 0.05,
+                    "--adaptive-convergence", 0.01, "--dump-progress", progp, "--dump-front", frontp, "--dump-overlay", overp])
+    blocks = util.read_progress(progp)[-1]["blocks"]
+    front = np.fromfile(frontp, dtype=np.uint32).reshape(h, w)
+    want = np.fromfile(overp, dtype=np.uint32).reshape(h, w)
+    assert 9 < len(blocks) and not np.array_equal(front, want)
+    assert np.array_equal(host_api.visualize_blocks(front, blocks), want)
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
 def test_golden_fixtures_reproduce_from_the_reference(tmp_path):
     """The committed fixtures are what the real reference produces today (pins the oracle: fixed seed, exact math)."""
     scn = os.path.join(util.GOLDEN, "scenes")
