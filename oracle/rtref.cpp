@@ -12,6 +12,7 @@
 //   sampler  GenericSampler streams for given pixels of given passes
 //   primary  Camera::GenerateRay for every pixel exactly as Viewport::RenderTile calls it
 //   texeval  ITexture::Evaluate of every texture of the scene at a list of (u, v)
+//   emit     ILight::Emit of every light of the scene for a list of (position sample x3, direction sample x2)
 //   writeexr a seeded random HDR image written by the reference's own EXR writer (tinyexr) - test input for EXR readers
 #include "PCH.h"
 #include "Demo.h"
@@ -784,6 +785,40 @@ static void CrashHandler(int sig)
     _exit(128 + sig);
 }
 
+// emit --scene X.json --samples F (5 floats each) --out F: per light (Scene::GetLights order), per sample, 12 floats:
+// position xyz, direction xyz, directPdfA, emissionPdfW, cosAtLight, radiance rgb
+int CmdEmit(const Args& a)
+{
+    Scene scene; Camera camera;
+    if (!LoadSceneFile(a, scene, camera, 64, 64)) return 1;
+    FILE* f = fopen(a.Str("samples").c_str(), "rb");
+    if (!f) Die("cannot open --samples");
+    std::vector<float> samples;
+    float v[5];
+    while (fread(v, 4, 5, f) == 5) samples.insert(samples.end(), v, v + 5);
+    fclose(f);
+    FILE* o = fopen(a.Str("out").c_str(), "wb");
+    if (!o) Die("cannot open --out");
+    Wavelength wavelength;
+    for (const LightSceneObject* lightObject : scene.GetLights())
+    {
+        const ILight& light = lightObject->GetLight();
+        for (size_t i = 0; i + 5 <= samples.size(); i += 5)
+        {
+            const ILight::EmitParam param = { lightObject->GetTransform(0.0f), wavelength, Float3(samples[i], samples[i + 1], samples[i + 2]), Float2(samples[i + 3], samples[i + 4]) };
+            ILight::EmitResult r;
+            r.position = Vector4::Zero(); r.direction = Vector4::Zero(); r.directPdfA = r.emissionPdfW = r.cosAtLight = 0.0f;
+            const RayColor color = light.Emit(param, r);
+            const Vector4 rgb = color.ConvertToTristimulus(wavelength);
+            const float out[12] = { r.position.x, r.position.y, r.position.z, r.direction.x, r.direction.y, r.direction.z,
+                                    r.directPdfA, r.emissionPdfW, r.cosAtLight, rgb.x, rgb.y, rgb.z };
+            WriteBytes(o, out, sizeof(out));
+        }
+    }
+    fclose(o);
+    return 0;
+}
+
 // writeexr --out F.exr --width W --height H --channels 3|4 --type half|float --compression 0..4 [--seed S]
 // (channel names A, B, G, R as tinyexr's own SaveEXR orders them; values: HDR-ish noise with zeros, smooth regions and
 // large peaks so that every compressor sees runs, gradients and outliers)
@@ -841,6 +876,7 @@ int main(int argc, char** argv)
     if (a.cmd == "sampler") return CmdSampler(a);
     if (a.cmd == "texeval") return CmdTexEval(a);
     if (a.cmd == "writeexr") return CmdWriteExr(a);
+    if (a.cmd == "emit") return CmdEmit(a);
     if (a.cmd == "primary") return CmdPrimary(a);
     fprintf(stderr, "usage: rtref render|flat|trace|sampler|primary --scene X.json [options]\n");
     return 2;

@@ -9,6 +9,7 @@
 //   hostsim trace  <scene.rtb> <rays.bin> <out.hits> [shadow tmax.bin]
 //   hostsim sampler <passes.bin> <w> <h> <numDims> <out.u32> <bluenoise.dat|->
 //   hostsim primary <scene.rtb> <passes.bin> <pass> <w> <h> <out.rays>
+//   hostsim emit <scene.rtb> <samples.f32 (5 per sample)> <out.f32 (12 per light and sample)>
 //   hostsim blockerrors <sum.bin> <sum2.bin> <w> <h> <numPasses> <blocks.bin> <out.f32>
 //   hostsim front  <sum.bin> <w> <h> <numPasses> <exposure> <contrast> <saturation> <dither> <tonemapper> <r,g,b filter> <out.bgra> [bloomFactor]
 #include <cstdio>
@@ -21,6 +22,7 @@
 
 #include "../../raytracer_b200/csrc/rtb_integrator.h"
 #include "../../raytracer_b200/csrc/rtb_postprocess.h"
+#include "../../raytracer_b200/csrc/rtb_emit.h"
 #include "../../raytracer_b200/csrc/rtb_upload.h"
 #include "../../raytracer_b200/csrc/rtb_scene_file.h"
 
@@ -326,6 +328,31 @@ static int cmdPrimary(int argc, char** argv)
     return 0;
 }
 
+// ILight::Emit for every light (in Scene::GetLights order = the order of the flattened light array) and every sample
+static int cmdEmit(int argc, char** argv)
+{
+    if (argc < 5) die("emit: arguments");
+    World world; world.load(argv[2]);
+    FILE* f = fopen(argv[3], "rb");
+    if (!f) die("cannot open samples");
+    std::vector<float> samples;
+    float v[5];
+    while (fread(v, 4, 5, f) == 5) samples.insert(samples.end(), v, v + 5);
+    fclose(f);
+    FILE* of = fopen(argv[4], "wb");
+    for (uint32_t l = 0; l < world.S.numLights; ++l)
+        for (size_t i = 0; i + 5 <= samples.size(); i += 5)
+        {
+            EmitResult r;
+            memset(&r, 0, sizeof(r));
+            const V4 c = light_emit<true>(world.S, world.S.lights[l], samples[i], samples[i + 1], samples[i + 2], samples[i + 3], samples[i + 4], r);
+            const float out[12] = { r.position.x, r.position.y, r.position.z, r.direction.x, r.direction.y, r.direction.z, r.directPdfA, r.emissionPdfW, r.cosAtLight, c.x, c.y, c.z };
+            fwrite(out, 4, 12, of);
+        }
+    fclose(of);
+    return 0;
+}
+
 // the arithmetic of rtb_block_errors on raster sum buffers (the three kernels, one thread after the other)
 static int cmdBlockErrors(int argc, char** argv)
 {
@@ -418,6 +445,7 @@ int main(int argc, char** argv)
     if (cmd == "sampler") return cmdSampler(argc, argv);
     if (cmd == "primary") return cmdPrimary(argc, argv);
     if (cmd == "front") return cmdFront(argc, argv);
+    if (cmd == "emit") return cmdEmit(argc, argv);
     if (cmd == "blockerrors") return cmdBlockErrors(argc, argv);
     die("unknown command");
     return 2;

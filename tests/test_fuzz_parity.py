@@ -284,6 +284,13 @@ def test_random_scene_on_the_device_headers(hostsim, tmp_path, seed):
         util.assert_bit_identical(util.load_sum(out, W, H), util.load_sum(sump, W, H), "seed %d %s" % (seed, renderer))
         mine = json.loads(r.stdout.strip().splitlines()[-1])
         assert (mine["numRays"], mine["numShadowRays"], mine["numShadowRaysHit"]) == (meta["numRays"], meta["numShadowRays"], meta["numShadowRaysHit"])
+    # ILight::Emit of every light (csrc/rtb_emit.h)
+    from tests.test_hostsim_parity import emission_samples
+    sp, refp, minep = str(tmp_path / "samples.f32"), str(tmp_path / "emit_ref.f32"), str(tmp_path / "emit_mine.f32")
+    emission_samples(64, seed).tofile(sp)
+    util.run_rtref(["emit", "--scene", sj, "--data", data, "--samples", sp, "--out", refp])
+    subprocess.run([HOSTSIM, "emit", flat, sp, minep], check=True)
+    assert open(refp, "rb").read() == open(minep, "rb").read(), "seed %d: ILight::Emit differs" % seed
     # DebugRenderer: one mode per scene (normals / tangents / texture coordinates / material parameters ...)
     mode = 1 + seed % 12
     sump, passp, out = str(tmp_path / "dbg.sum"), str(tmp_path / "dbg.passes"), str(tmp_path / "dbg_mine.sum")

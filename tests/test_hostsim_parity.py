@@ -300,3 +300,30 @@ def test_hostsim_block_errors_golden(hostsim, tmp_path, scene):
     subprocess.run([HOSTSIM, "blockerrors", util.golden(scene + "_mis.sum"), util.golden(scene + "_mis.sum2"), str(meta["width"]), str(meta["height"]),
                     str(meta["passes"]), util.golden(scene + ".blocks"), out], check=True)
     assert open(out, "rb").read() == open(util.golden(scene + "_mis.blockerr"), "rb").read()
+
+
+def emission_samples(n=400, seed=2):
+    """(position sample x3, direction sample x2) rows: corners of the unit cube first, then random."""
+    rng = np.random.default_rng(seed)
+    samples = rng.random((n, 5), dtype=np.float32)
+    samples[:8] = [[0, 0, 0, 0, 0], [1, 1, 1, 1, 1], [0.5] * 5, [0, 1, 0, 1, 0], [0.25, 0.75, 0.1, 0, 0.5], [0.3, 0.3, 0.34, 0.999, 0.001],
+                   [0.1, 0.2, 0.67, 0.5, 0.25], [0.9, 0.8, 0.99, 0.75, 0.5]]
+    return np.minimum(samples, np.float32(0.99999994))          # what GenericSampler::GetFloat can return
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
+@pytest.mark.parametrize("scene", ["c1_sphere_area", "cornell", "materials", "mesh_small", "textures"])
+def test_hostsim_light_emission_against_the_live_reference(hostsim, tmp_path, scene):
+    """ILight::Emit of every light of the fixture scenes (sphere / rect / box area lights, point, spot, directional,
+    constant and environment-mapped background): position, direction, both pdfs, cosAtLight and radiance, bit for bit.
+    Building block of the light sub-paths; see csrc/rtb_emit.h."""
+    scn = os.path.join(util.GOLDEN, "scenes")
+    sp, refp, minep = str(tmp_path / "samples.f32"), str(tmp_path / "ref.f32"), str(tmp_path / "mine.f32")
+    emission_samples().tofile(sp)
+    util.run_rtref(["emit", "--scene", os.path.join(scn, scene + ".json"), "--data", scn + "/", "--samples", sp, "--out", refp])
+    subprocess.run([HOSTSIM, "emit", util.golden(scene + ".rtb"), sp, minep], check=True)
+    want, got = np.fromfile(refp, dtype=np.uint32).reshape(-1, 12), np.fromfile(minep, dtype=np.uint32).reshape(-1, 12)
+    assert want.shape == got.shape and len(want) % 400 == 0 and len(want) > 0
+    bad = np.argwhere((want != got).any(axis=1)).ravel()
+    assert len(bad) == 0, "light %d sample %d: %s vs %s" % (bad[0] // 400, bad[0] % 400, got[bad[0]].view(np.float32), want[bad[0]].view(np.float32))
+    assert np.isfinite(want.view(np.float32)).all()
