@@ -13,6 +13,7 @@
 //   primary  Camera::GenerateRay for every pixel exactly as Viewport::RenderTile calls it
 //   texeval  ITexture::Evaluate of every texture of the scene at a list of (u, v)
 //   emit     ILight::Emit of every light of the scene for a list of (position sample x3, direction sample x2)
+//   camera   Camera::WorldToFilm and Camera::PdfW for a list of world-space points
 //   writeexr a seeded random HDR image written by the reference's own EXR writer (tinyexr) - test input for EXR readers
 #include "PCH.h"
 #include "Demo.h"
@@ -819,6 +820,34 @@ int CmdEmit(const Args& a)
     return 0;
 }
 
+// camera --scene X.json --width W --height H --points F (3 floats each) --out F: per point 7 words: WorldToFilm's
+// return value, film x, film y (0 when behind the camera), the unit direction camera -> point, Camera::PdfW(direction)
+int CmdCamera(const Args& a)
+{
+    const uint32 w = (uint32)a.Int("width", 64), h = (uint32)a.Int("height", 64);
+    Scene scene; Camera camera;
+    if (!LoadSceneFile(a, scene, camera, w, h)) return 1;
+    FILE* f = fopen(a.Str("points").c_str(), "rb");
+    if (!f) Die("cannot open --points");
+    FILE* o = fopen(a.Str("out").c_str(), "wb");
+    if (!o) Die("cannot open --out");
+    float p[3];
+    while (fread(p, 4, 3, f) == 3)
+    {
+        const Vector4 point(p[0], p[1], p[2], 0.0f);
+        Vector4 film = Vector4::Zero();
+        const uint32 ok = camera.WorldToFilm(point, film) ? 1u : 0u;
+        Vector4 dir = point - camera.GetTransform().GetTranslation();
+        dir /= sqrtf(dir.SqrLength3());
+        const float pdf = camera.PdfW(dir);
+        WriteU32(o, ok);
+        const float out[6] = { ok ? film.x : 0.0f, ok ? film.y : 0.0f, dir.x, dir.y, dir.z, pdf };
+        WriteBytes(o, out, sizeof(out));
+    }
+    fclose(f); fclose(o);
+    return 0;
+}
+
 // writeexr --out F.exr --width W --height H --channels 3|4 --type half|float --compression 0..4 [--seed S]
 // (channel names A, B, G, R as tinyexr's own SaveEXR orders them; values: HDR-ish noise with zeros, smooth regions and
 // large peaks so that every compressor sees runs, gradients and outliers)
@@ -877,6 +906,7 @@ int main(int argc, char** argv)
     if (a.cmd == "texeval") return CmdTexEval(a);
     if (a.cmd == "writeexr") return CmdWriteExr(a);
     if (a.cmd == "emit") return CmdEmit(a);
+    if (a.cmd == "camera") return CmdCamera(a);
     if (a.cmd == "primary") return CmdPrimary(a);
     fprintf(stderr, "usage: rtref render|flat|trace|sampler|primary --scene X.json [options]\n");
     return 2;

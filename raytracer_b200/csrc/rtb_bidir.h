@@ -1,9 +1,9 @@
-// rtb_emit.h — ILight::Emit for the five light types (the first step of every light sub-path of the
+// rtb_bidir.h — ILight::Emit for the five light types (the first step of every light sub-path of the
 // reference's Light Tracer and VCM renderers, Rendering/LightTracer.cpp:44-66, VertexConnectionAndMerging.cpp:320-360).
 //
 // STATUS: building block.  No kernel launches this yet (the bidirectional renderers are not built); the
 // functions are restated here in the device headers' arithmetic and pinned bit for bit against the reference's own
-// ILight::Emit through tests/hostsim (`emit` command, tests/test_hostsim_parity.py::test_hostsim_light_emission_*), so
+// ILight::Emit / Camera through tests/hostsim (`emit` and `camera` commands, tests/test_hostsim_parity.py), so
 // that the renderers can be built on checked parts.  rtb_kernels.cu does not include this file.
 #pragma once
 
@@ -156,6 +156,69 @@ RTB_HD V4 light_emit(const SceneView& S, const DLight& light, float p0, float p1
         return background_color<kTex>(S, light, v3(-out.direction.x, -out.direction.y, -out.direction.z));
     }
     }
+}
+
+// ---- camera connection -------------------------------------------------------------------------------------------------
+
+RTB_HD V4 row_times_matrix(const V4& a, const M4& b)          // one row of Matrix4::operator*, Matrix4.cpp:35-75: a mul, then three FMAs
+{
+    V4 c = v4(a.x * b.r0.x, a.x * b.r0.y, a.x * b.r0.z, a.x * b.r0.w);
+    c = v4(fma_(a.y, b.r1.x, c.x), fma_(a.y, b.r1.y, c.y), fma_(a.y, b.r1.z, c.z), fma_(a.y, b.r1.w, c.w));
+    c = v4(fma_(a.z, b.r2.x, c.x), fma_(a.z, b.r2.y, c.y), fma_(a.z, b.r2.z, c.z), fma_(a.z, b.r2.w, c.w));
+    c = v4(fma_(a.w, b.r3.x, c.x), fma_(a.w, b.r3.y, c.y), fma_(a.w, b.r3.z, c.z), fma_(a.w, b.r3.w, c.w));
+    return c;
+}
+
+// Camera::mWorldToScreen as Camera::SetPerspective builds it (Camera.cpp:30-47): FastInverseNoScale() * MakePerspective.
+// All four lanes are carried the way the reference's SSE code carries them: Vector4::Transpose3 (Vector4ImplSSE.h:578-585)
+// leaves lanes of the third row in the w lanes of the transposed rows, and the inverse that is multiplied is the one
+// WITHOUT the w clean-up of Camera.cpp:38-42 (that clean-up is applied to a copy nobody uses) - both only reach the
+// z lane of the product, which Camera::WorldToFilm uses for its "in front of the camera" test.
+RTB_HD M4 camera_world_to_screen(const M4& localToWorld, float aspectRatio, float tanHalfFoV)
+{
+    const V4 a = localToWorld.r0, b = localToWorld.r1, c = localToWorld.r2, t = localToWorld.r3;
+    M4 inv;
+    inv.r0 = v4(a.x, b.x, c.x, c.y);
+    inv.r1 = v4(a.y, b.y, c.y, c.w);
+    inv.r2 = v4(a.z, b.z, c.z, c.w);
+    // rows[3] = TransformVectorNeg(original row 3): x * r0, then NegMulAndSub(y, r1, .), then NegMulAndAdd(z, r2, .)
+    V4 r = v4(t.x * inv.r0.x, t.x * inv.r0.y, t.x * inv.r0.z, t.x * inv.r0.w);
+    r = v4(fma_(-t.y, inv.r1.x, -r.x), fma_(-t.y, inv.r1.y, -r.y), fma_(-t.y, inv.r1.z, -r.z), fma_(-t.y, inv.r1.w, -r.w));
+    r = v4(fma_(-t.z, inv.r2.x, r.x), fma_(-t.z, inv.r2.y, r.y), fma_(-t.z, inv.r2.z, r.z), fma_(-t.z, inv.r2.w, r.w));
+    inv.r3 = r;
+    // Matrix4::MakePerspective(aspect, fov, 0.01, 1000), Matrix4.cpp:15-24
+    const float nearZ = 0.01f, farZ = 1000.0f;
+    const float yScale = fdiv(1.0f, tanHalfFoV), xScale = fdiv(yScale, aspectRatio);
+    M4 proj;
+    proj.r0 = v4(xScale, 0.0f, 0.0f, 0.0f);
+    proj.r1 = v4(0.0f, yScale, 0.0f, 0.0f);
+    proj.r2 = v4(0.0f, 0.0f, fdiv(farZ, farZ - nearZ), 1.0f);
+    proj.r3 = v4(0.0f, 0.0f, fdiv(-nearZ * farZ, farZ - nearZ), 0.0f);
+    M4 out;
+    out.r0 = row_times_matrix(inv.r0, proj); out.r1 = row_times_matrix(inv.r1, proj);
+    out.r2 = row_times_matrix(inv.r2, proj); out.r3 = row_times_matrix(inv.r3, proj);
+    return out;
+}
+
+// Camera::WorldToFilm, Camera.cpp:120-134: false behind the camera; film coordinates in [0, 1]^2 when inside the frame
+RTB_HD bool camera_world_to_film(const M4& worldToScreen, const V3& p, float& filmX, float& filmY)
+{
+    const M4& m = worldToScreen;
+    V4 t = v4(fma_(p.x, m.r0.x, m.r3.x), fma_(p.x, m.r0.y, m.r3.y), fma_(p.x, m.r0.z, m.r3.z), fma_(p.x, m.r0.w, m.r3.w));
+    t = v4(fma_(p.y, m.r1.x, t.x), fma_(p.y, m.r1.y, t.y), fma_(p.y, m.r1.z, t.z), fma_(p.y, m.r1.w, t.w));
+    t = v4(fma_(p.z, m.r2.x, t.x), fma_(p.z, m.r2.y, t.y), fma_(p.z, m.r2.z, t.z), fma_(p.z, m.r2.w, t.w));
+    if (!(t.z > 0.0f)) return false;
+    filmX = fma_(fdiv(t.x, t.w), 0.5f, 0.5f);          // BipolarToUnipolar(cameraSpacePosition / w)
+    filmY = fma_(fdiv(t.y, t.w), 0.5f, 0.5f);
+    return true;
+}
+
+// Camera::PdfW, Camera.cpp:136-148
+RTB_HD float camera_pdf_w(const M4& localToWorld, float tanHalfFoV, float aspectRatio, const V3& direction)
+{
+    const float cosAtCamera = dot3(xyz(localToWorld.r2), direction);
+    const float pdf = fdiv(0.25f, (tanHalfFoV * tanHalfFoV) * ((cosAtCamera * cosAtCamera) * cosAtCamera) * aspectRatio);
+    return s_max(0.0f, pdf);
 }
 
 } // namespace rtb

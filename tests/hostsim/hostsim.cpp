@@ -10,6 +10,7 @@
 //   hostsim sampler <passes.bin> <w> <h> <numDims> <out.u32> <bluenoise.dat|->
 //   hostsim primary <scene.rtb> <passes.bin> <pass> <w> <h> <out.rays>
 //   hostsim emit <scene.rtb> <samples.f32 (5 per sample)> <out.f32 (12 per light and sample)>
+//   hostsim camera <scene.rtb> <w> <h> <points.f32 (3 per point)> <ref.bin (for the directions)> <out.bin (7 words per point)>
 //   hostsim blockerrors <sum.bin> <sum2.bin> <w> <h> <numPasses> <blocks.bin> <out.f32>
 //   hostsim front  <sum.bin> <w> <h> <numPasses> <exposure> <contrast> <saturation> <dither> <tonemapper> <r,g,b filter> <out.bgra> [bloomFactor]
 #include <cstdio>
@@ -22,7 +23,7 @@
 
 #include "../../raytracer_b200/csrc/rtb_integrator.h"
 #include "../../raytracer_b200/csrc/rtb_postprocess.h"
-#include "../../raytracer_b200/csrc/rtb_emit.h"
+#include "../../raytracer_b200/csrc/rtb_bidir.h"
 #include "../../raytracer_b200/csrc/rtb_upload.h"
 #include "../../raytracer_b200/csrc/rtb_scene_file.h"
 
@@ -353,6 +354,35 @@ static int cmdEmit(int argc, char** argv)
     return 0;
 }
 
+// Camera::WorldToFilm / PdfW; the direction handed to PdfW is read from the reference's record (word 3..5) so that both
+// sides evaluate the same input
+static int cmdCamera(int argc, char** argv)
+{
+    if (argc < 8) die("camera: arguments");
+    World world; world.load(argv[2]);
+    const uint32_t w = atoi(argv[3]), h = atoi(argv[4]);
+    PassParams P;
+    memset(&P, 0, sizeof(P));
+    fillCamera(P, world.file.camera, w, h, tanf(world.file.fieldOfView * 0.5f));
+    const M4 worldToScreen = camera_world_to_screen(P.camLocalToWorld, P.aspectRatio, P.tanHalfFoV);
+    FILE* f = fopen(argv[5], "rb");
+    FILE* rf = fopen(argv[6], "rb");
+    if (!f || !rf) die("cannot open points / reference records");
+    FILE* of = fopen(argv[7], "wb");
+    float p[3], ref[7];
+    while (fread(p, 4, 3, f) == 3 && fread(ref, 4, 7, rf) == 7)
+    {
+        float fx = 0.0f, fy = 0.0f;
+        const uint32_t ok = camera_world_to_film(worldToScreen, v3(p[0], p[1], p[2]), fx, fy) ? 1u : 0u;
+        const float pdf = camera_pdf_w(P.camLocalToWorld, P.tanHalfFoV, P.aspectRatio, v3(ref[3], ref[4], ref[5]));
+        fwrite(&ok, 4, 1, of);
+        const float out[6] = { ok ? fx : 0.0f, ok ? fy : 0.0f, ref[3], ref[4], ref[5], pdf };
+        fwrite(out, 4, 6, of);
+    }
+    fclose(f); fclose(rf); fclose(of);
+    return 0;
+}
+
 // the arithmetic of rtb_block_errors on raster sum buffers (the three kernels, one thread after the other)
 static int cmdBlockErrors(int argc, char** argv)
 {
@@ -446,6 +476,7 @@ int main(int argc, char** argv)
     if (cmd == "primary") return cmdPrimary(argc, argv);
     if (cmd == "front") return cmdFront(argc, argv);
     if (cmd == "emit") return cmdEmit(argc, argv);
+    if (cmd == "camera") return cmdCamera(argc, argv);
     if (cmd == "blockerrors") return cmdBlockErrors(argc, argv);
     die("unknown command");
     return 2;

@@ -284,7 +284,7 @@ def test_random_scene_on_the_device_headers(hostsim, tmp_path, seed):
         util.assert_bit_identical(util.load_sum(out, W, H), util.load_sum(sump, W, H), "seed %d %s" % (seed, renderer))
         mine = json.loads(r.stdout.strip().splitlines()[-1])
         assert (mine["numRays"], mine["numShadowRays"], mine["numShadowRaysHit"]) == (meta["numRays"], meta["numShadowRays"], meta["numShadowRaysHit"])
-    # ILight::Emit of every light (csrc/rtb_emit.h)
+    # ILight::Emit of every light (csrc/rtb_bidir.h)
     from tests.test_hostsim_parity import emission_samples
     sp, refp, minep = str(tmp_path / "samples.f32"), str(tmp_path / "emit_ref.f32"), str(tmp_path / "emit_mine.f32")
     emission_samples(64, seed).tofile(sp)

@@ -316,7 +316,7 @@ def emission_samples(n=400, seed=2):
 def test_hostsim_light_emission_against_the_live_reference(hostsim, tmp_path, scene):
     """ILight::Emit of every light of the fixture scenes (sphere / rect / box area lights, point, spot, directional,
     constant and environment-mapped background): position, direction, both pdfs, cosAtLight and radiance, bit for bit.
-    Building block of the light sub-paths; see csrc/rtb_emit.h."""
+    Building block of the light sub-paths; see csrc/rtb_bidir.h."""
     scn = os.path.join(util.GOLDEN, "scenes")
     sp, refp, minep = str(tmp_path / "samples.f32"), str(tmp_path / "ref.f32"), str(tmp_path / "mine.f32")
     emission_samples().tofile(sp)
@@ -327,3 +327,25 @@ def test_hostsim_light_emission_against_the_live_reference(hostsim, tmp_path, sc
     bad = np.argwhere((want != got).any(axis=1)).ravel()
     assert len(bad) == 0, "light %d sample %d: %s vs %s" % (bad[0] // 400, bad[0] % 400, got[bad[0]].view(np.float32), want[bad[0]].view(np.float32))
     assert np.isfinite(want.view(np.float32)).all()
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
+@pytest.mark.parametrize("scene,w,h", [("cornell", 64, 64), ("materials", 40, 30), ("mesh_small", 1920, 1080), ("cornell_dof", 33, 77)])
+def test_hostsim_camera_connection_against_the_live_reference(hostsim, tmp_path, scene, w, h):
+    """Camera::WorldToFilm (through the world-to-screen matrix Camera::SetPerspective builds, SSE lane quirks included)
+    and Camera::PdfW for points all around the camera: in-front flag, film coordinates and pdf, bit for bit.
+    Building block of the camera connection of the light sub-paths (csrc/rtb_bidir.h)."""
+    scn = os.path.join(util.GOLDEN, "scenes")
+    pp, refp, flatp, minep = (str(tmp_path / n) for n in ("points.f32", "ref.bin", "scene.rtb", "mine.bin"))
+    rng = np.random.default_rng(4)
+    (rng.normal(size=(600, 3)) * 6).astype(np.float32).tofile(pp)
+    common = ["--scene", os.path.join(scn, scene + ".json"), "--data", scn + "/", "--width", w, "--height", h]
+    util.run_rtref(["camera", *common, "--points", pp, "--out", refp])
+    util.run_rtref(["flat", *common, "--out", flatp])
+    subprocess.run([HOSTSIM, "camera", flatp, str(w), str(h), pp, refp, minep], check=True)
+    want, got = np.fromfile(refp, dtype=np.uint32).reshape(-1, 7), np.fromfile(minep, dtype=np.uint32).reshape(-1, 7)
+    assert want.shape == got.shape == (600, 7)
+    assert 0 < want[:, 0].sum() < 600, "points on both sides of the camera expected"
+    assert np.array_equal(want, got), "%d of 600 records differ" % (want != got).any(axis=1).sum()
+    inside = want[want[:, 0] == 1][:, 1:3].view(np.float32)
+    assert ((inside >= 0) & (inside <= 1)).all(axis=1).any(), "no point inside the frame"
