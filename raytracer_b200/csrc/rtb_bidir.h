@@ -8,6 +8,7 @@
 #pragma once
 
 #include "rtb_shading.h"
+#include "rtb_trace.h"
 
 namespace rtb {
 
@@ -219,6 +220,85 @@ RTB_HD float camera_pdf_w(const M4& localToWorld, float tanHalfFoV, float aspect
     const float cosAtCamera = dot3(xyz(localToWorld.r2), direction);
     const float pdf = fdiv(0.25f, (tanHalfFoV * tanHalfFoV) * ((cosAtCamera * cosAtCamera) * cosAtCamera) * aspectRatio);
     return s_max(0.0f, pdf);
+}
+
+// ---- LightTracer::RenderPixel, Rendering/LightTracer.cpp:27-183 ---------------------------------------------------------
+//
+// One light sub-path: pick a light, emit, and at every surface vertex connect to the camera and splat onto the film.
+// The reference draws ALL its random numbers here from the per-thread generator (ctx.randomGenerator), so its image is
+// reproducible only statistically; `Rng` supplies uniform floats in [0, 1) / integers, `Splat` receives
+// (filmX, filmY, rgb) for Film::AccumulateColor(pos, value, rng) (Film.cpp:41-77).  Returns the number of rays traced.
+struct CameraConnection { M4 localToWorld, worldToScreen; float tanHalfFoV, aspectRatio; };
+
+template <bool kTex = true, typename Rng, typename Splat>
+RTB_HD uint32_t light_trace_path(const SceneView& S, const CameraConnection& camera, uint32_t maxRayDepth, Rng& rng, Splat& splat)
+{
+    if (S.numLights == 0) return 0;
+    const float lightPickingProbability = 1.0f / (float)S.numLights;
+    const uint32_t lightIndex = rng.next_uint() % S.numLights;
+    const DLight& light = S.lights[lightIndex];
+
+    const float p0 = rng.next_float(), p1 = rng.next_float(), p2 = rng.next_float();
+    const float d0 = rng.next_float(), d1 = rng.next_float();
+    EmitResult emit;
+    V4 throughput = light_emit<kTex>(S, light, p0, p1, p2, d0, d1, emit);
+    if (almost_zero(throughput)) return 0;
+    emit.emissionPdfW *= lightPickingProbability;
+    emit.position = emit.position + emit.direction * 0.0005f;
+    Ray ray = make_ray(emit.position, emit.direction);
+    throughput = throughput * (1.0f / emit.emissionPdfW);
+
+    uint32_t depth = 0;
+    Vertex vx;
+    for (;;)
+    {
+        Hit hit;
+        hit.objectId = RTB_INVALID_OBJECT; hit.subObjectId = 0; hit.distance = INFINITY; hit.u = 0.0f; hit.v = 0.0f;
+        scene_traverse<false>(S, ray, hit, nullptr);
+        if (hit.distance == INFINITY) break;                       // ray missed
+        if (hit.subObjectId == RTB_LIGHT_OBJECT) break;         // we hit a light directly
+        evaluate_intersection<kTex>(S, ray, hit, vx, RTB_NO_MATERIAL);
+        vx.outgoingDirWorld = neg(ray.dir);
+        evaluate_shading_data<kTex>(S, vx);
+        if (depth >= maxRayDepth) break;
+
+        // connect to camera                                       LightTracer.cpp:117-151
+        {
+            const V3 cameraPos = xyz(camera.localToWorld.r3);
+            V3 dirToCamera = cameraPos - vx.position;
+            const float cameraDistanceSqr = sqr_length3(dirToCamera);
+            const float cameraDistance = sqrtf(cameraDistanceSqr);
+            dirToCamera = dirToCamera / cameraDistance;
+            float bsdfPdfW = 0.0f;
+            const V3 outLocal = world_to_local(vx, vx.outgoingDirWorld);
+            const V4 cameraFactor = bsdf_evaluate(vx, outLocal, world_to_local(vx, neg(dirToCamera)), bsdfPdfW);
+            if (!almost_zero(cameraFactor))
+            {
+                float filmX, filmY;
+                if (camera_world_to_film(camera.worldToScreen, vx.position, filmX, filmY))
+                {
+                    const Ray shadowRay = make_ray(vx.position + vx.normal * 0.0001f, dirToCamera);
+                    if (!scene_traverse_shadow<false>(S, shadowRay, cameraDistance * 0.999f, nullptr))
+                    {
+                        const float cameraPdfA = camera_pdf_w(camera.localToWorld, camera.tanHalfFoV, camera.aspectRatio, neg(dirToCamera)) / cameraDistanceSqr;
+                        const V4 contribution = (cameraFactor * throughput) * cameraPdfA;
+                        splat(filmX, filmY, xyz(contribution));
+                    }
+                }
+            }
+        }
+
+        // sample BSDF                                             LightTracer.cpp:154-172
+        const float s0 = rng.next_float(), s1 = rng.next_float(), s2 = rng.next_float();
+        BsdfSample bs;
+        if (!bsdf_sample(vx, world_to_local(vx, vx.outgoingDirWorld), s0, s1, s2, bs)) break;
+        throughput = throughput * bs.color;
+        if (almost_zero(throughput)) break;
+        ray = make_ray(vx.position, local_to_world(vx, bs.incomingDir));
+        ray.origin = ray.origin + ray.dir * 0.001f;
+        depth++;
+    }
+    return depth + 1u;
 }
 
 } // namespace rtb

@@ -11,6 +11,7 @@
 //   hostsim primary <scene.rtb> <passes.bin> <pass> <w> <h> <out.rays>
 //   hostsim emit <scene.rtb> <samples.f32 (5 per sample)> <out.f32 (12 per light and sample)>
 //   hostsim camera <scene.rtb> <w> <h> <points.f32 (3 per point)> <ref.bin (for the directions)> <out.bin (7 words per point)>
+//   hostsim lighttrace <scene.rtb> <w> <h> <passes> <maxDepth> <seed> <out.sum>     (LightTracer: statistical parity only)
 //   hostsim blockerrors <sum.bin> <sum2.bin> <w> <h> <numPasses> <blocks.bin> <out.f32>
 //   hostsim front  <sum.bin> <w> <h> <numPasses> <exposure> <contrast> <saturation> <dither> <tonemapper> <r,g,b filter> <out.bgra> [bloomFactor]
 #include <cstdio>
@@ -383,6 +384,57 @@ static int cmdCamera(int argc, char** argv)
     return 0;
 }
 
+// LightTracer (Rendering/LightTracer.cpp): one light sub-path per pixel and pass, camera connections splatted onto the
+// film.  The reference draws from per-thread generators, so only the statistics of the image can be compared.
+struct HostRng
+{
+    uint64_t state;
+    uint64_t next() { state ^= state >> 12; state ^= state << 25; state ^= state >> 27; return state * 0x2545F4914F6CDD1DULL; }
+    uint32_t next_uint() { return (uint32_t)(next() >> 32); }
+    float next_float() { return bits2f(((uint32_t)(next() >> 41)) | 0x3f800000u) - 1.0f; }
+};
+
+static int cmdLightTrace(int argc, char** argv)
+{
+    if (argc < 9) die("lighttrace: arguments");
+    World world; world.load(argv[2]);
+    const uint32_t w = atoi(argv[3]), h = atoi(argv[4]), passes = atoi(argv[5]), maxDepth = atoi(argv[6]);
+    HostRng rng{ strtoull(argv[7], nullptr, 10) * 0x9E3779B97F4A7C15ULL + 1u };
+    PassParams P;
+    memset(&P, 0, sizeof(P));
+    fillCamera(P, world.file.camera, w, h, tanf(world.file.fieldOfView * 0.5f));
+    CameraConnection camera;
+    camera.localToWorld = P.camLocalToWorld; camera.tanHalfFoV = P.tanHalfFoV; camera.aspectRatio = P.aspectRatio;
+    camera.worldToScreen = camera_world_to_screen(P.camLocalToWorld, P.aspectRatio, P.tanHalfFoV);
+    std::vector<float> sum((size_t)w * h * 3, 0.0f);
+    uint64_t numRays = 0, numSplats = 0;
+    // Film::AccumulateColor(pos, value, rng), Film.cpp:41-77: nearest pixel with a random +1 step in x by the fractional
+    // part (the y step is computed but the row comes from the unjittered coordinate, as in the reference)
+    auto splat = [&](float filmX, float filmY, const V3& value)
+    {
+        const float cx = filmX * (float)w + 0.0f, cy = filmY * (float)h + 0.5f;
+        int32_t ix = cvt_rn(cx);
+        const float fractionX = cx - (float)ix;
+        const float ux = rng.next_float();
+        rng.next_float(); rng.next_float(); rng.next_float();       // GetVector4: four lanes drawn
+        if (ux < fractionX) ix++;
+        const int32_t x = ix, y = (int32_t)(h - 1) - (int32_t)cy;
+        if ((uint32_t)x < w && (uint32_t)y < h)
+        {
+            float* px = &sum[((size_t)y * w + x) * 3];
+            px[0] += value.x; px[1] += value.y; px[2] += value.z;
+            numSplats++;
+        }
+    };
+    for (uint32_t p = 0; p < passes; ++p)
+        for (uint32_t i = 0; i < w * h; ++i) numRays += light_trace_path<true>(world.S, camera, maxDepth, rng, splat);
+    FILE* f = fopen(argv[8], "wb");
+    fwrite(sum.data(), 4, sum.size(), f);
+    fclose(f);
+    printf("{\"numRays\": %llu, \"numSplats\": %llu}\n", (unsigned long long)numRays, (unsigned long long)numSplats);
+    return 0;
+}
+
 // the arithmetic of rtb_block_errors on raster sum buffers (the three kernels, one thread after the other)
 static int cmdBlockErrors(int argc, char** argv)
 {
@@ -476,6 +528,7 @@ int main(int argc, char** argv)
     if (cmd == "primary") return cmdPrimary(argc, argv);
     if (cmd == "front") return cmdFront(argc, argv);
     if (cmd == "emit") return cmdEmit(argc, argv);
+    if (cmd == "lighttrace") return cmdLightTrace(argc, argv);
     if (cmd == "camera") return cmdCamera(argc, argv);
     if (cmd == "blockerrors") return cmdBlockErrors(argc, argv);
     die("unknown command");

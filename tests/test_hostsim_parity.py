@@ -349,3 +349,27 @@ def test_hostsim_camera_connection_against_the_live_reference(hostsim, tmp_path,
     assert np.array_equal(want, got), "%d of 600 records differ" % (want != got).any(axis=1).sum()
     inside = want[want[:, 0] == 1][:, 1:3].view(np.float32)
     assert ((inside >= 0) & (inside <= 1)).all(axis=1).any(), "no point inside the frame"
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
+@pytest.mark.parametrize("scene,passes,mean_tolerance,min_correlation", [("cornell", 200, 0.02, 0.995), ("c1_sphere_area", 200, 0.03, 0.99), ("textures", 300, 0.12, 0.90)])
+def test_hostsim_light_tracer_statistics(hostsim, tmp_path, scene, passes, mean_tolerance, min_correlation):
+    """LightTracer::RenderPixel (LightTracer.cpp:27-183) assembled from the checked parts in csrc/rtb_bidir.h (emission,
+    camera connection, film splat) and the path tracer's BSDF / traversal code.  The reference draws every number of
+    this renderer from per-thread generators, so - like its own renderer tests - the comparison is statistical: ray
+    count, mean colour and the image at 8 x 8-pixel blocks."""
+    w = h = 48
+    depth = 6
+    scn = os.path.join(util.GOLDEN, "scenes")
+    common = ["--scene", os.path.join(scn, scene + ".json"), "--data", scn + "/", "--width", w, "--height", h]
+    refp, flatp, minep = str(tmp_path / "ref.sum"), str(tmp_path / "scene.rtb"), str(tmp_path / "mine.sum")
+    meta = util.run_rtref(["render", *common, "--passes", passes, "--dims", 256, "--depth", depth, "--renderer", "Light Tracer", "--dump-sum", refp])
+    util.run_rtref(["flat", *common, "--out", flatp])
+    r = subprocess.run([HOSTSIM, "lighttrace", flatp, str(w), str(h), str(passes), str(depth), "7", minep], stdout=subprocess.PIPE, text=True, check=True)
+    mine = json.loads(r.stdout.strip().splitlines()[-1])
+    assert abs(mine["numRays"] - meta["numRays"]) <= 0.003 * meta["numRays"], (mine["numRays"], meta["numRays"])
+    a, b = util.load_sum(refp, w, h) / passes, util.load_sum(minep, w, h) / passes
+    ma, mb = a.mean(axis=(0, 1)), b.mean(axis=(0, 1))
+    assert (np.abs(ma - mb) <= mean_tolerance * ma).all(), (ma, mb)
+    blocks = lambda x: x.reshape(6, 8, 6, 8, 3).mean(axis=(1, 3)).ravel()
+    assert np.corrcoef(blocks(a), blocks(b))[0, 1] >= min_correlation
