@@ -13,6 +13,7 @@
 //   primary  Camera::GenerateRay for every pixel exactly as Viewport::RenderTile calls it
 //   texeval  ITexture::Evaluate of every texture of the scene at a list of (u, v)
 //   emit     ILight::Emit of every light of the scene for a list of (position sample x3, direction sample x2)
+//   bsdfpdf  BSDF::Pdf (forward and reverse) of every material of the scene for a list of direction pairs
 //   camera   Camera::WorldToFilm and Camera::PdfW for a list of world-space points
 //   writeexr a seeded random HDR image written by the reference's own EXR writer (tinyexr) - test input for EXR readers
 #include "PCH.h"
@@ -820,6 +821,45 @@ int CmdEmit(const Args& a)
     return 0;
 }
 
+// bsdfpdf --scene X.json --dirs F (6 floats each: local outgoing xyz, local incoming xyz, both unit) --out F:
+// per material (Scene flatten order = first use by an object), per pair: forward pdf, reverse pdf.  Material parameters
+// are the constants of the material (no texture lookups).
+int CmdBsdfPdf(const Args& a)
+{
+    Scene scene; Camera camera;
+    if (!LoadSceneFile(a, scene, camera, 64, 64)) return 1;
+    Flat flat;
+    flat.Build(scene);
+    FILE* f = fopen(a.Str("dirs").c_str(), "rb");
+    if (!f) Die("cannot open --dirs");
+    std::vector<float> dirs;
+    float v[6];
+    while (fread(v, 4, 6, f) == 6) dirs.insert(dirs.end(), v, v + 6);
+    fclose(f);
+    FILE* o = fopen(a.Str("out").c_str(), "wb");
+    if (!o) Die("cannot open --out");
+    Wavelength wavelength;
+    std::vector<const Material*> materialPtrs(flat.materials.size(), nullptr);
+    for (const auto& it : flat.materialIds) materialPtrs[it.second] = it.first;
+    for (const Material* material : materialPtrs)
+    {
+        SampledMaterialParameters params;
+        params.baseColor = RayColor::Resolve(wavelength, Spectrum(material->baseColor.baseValue));
+        params.emissionColor = RayColor::Zero();
+        params.roughness = material->roughness.baseValue;
+        params.metalness = material->metalness.baseValue;
+        params.IoR = material->IoR;
+        for (size_t i = 0; i + 6 <= dirs.size(); i += 6)
+        {
+            const BSDF::EvaluationContext ctx = { *material, params, wavelength, Vector4(dirs[i], dirs[i + 1], dirs[i + 2], 0.0f), Vector4(dirs[i + 3], dirs[i + 4], dirs[i + 5], 0.0f) };
+            const float out[2] = { material->GetBSDF()->Pdf(ctx, BSDF::ForwardPdf), material->GetBSDF()->Pdf(ctx, BSDF::ReversePdf) };
+            WriteBytes(o, out, sizeof(out));
+        }
+    }
+    fclose(o);
+    return 0;
+}
+
 // camera --scene X.json --width W --height H --points F (3 floats each) --out F: per point 7 words: WorldToFilm's
 // return value, film x, film y (0 when behind the camera), the unit direction camera -> point, Camera::PdfW(direction)
 int CmdCamera(const Args& a)
@@ -907,6 +947,7 @@ int main(int argc, char** argv)
     if (a.cmd == "writeexr") return CmdWriteExr(a);
     if (a.cmd == "emit") return CmdEmit(a);
     if (a.cmd == "camera") return CmdCamera(a);
+    if (a.cmd == "bsdfpdf") return CmdBsdfPdf(a);
     if (a.cmd == "primary") return CmdPrimary(a);
     fprintf(stderr, "usage: rtref render|flat|trace|sampler|primary --scene X.json [options]\n");
     return 2;

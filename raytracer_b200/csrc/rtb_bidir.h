@@ -159,6 +159,81 @@ RTB_HD V4 light_emit(const SceneView& S, const DLight& light, float p0, float p1
     }
 }
 
+// ---- BSDF::Pdf(ctx, ForwardPdf | ReversePdf) for the nine BSDFs ------------------------------------------------------------
+// (what VCM's vertex connection asks for, VertexConnectionAndMerging.cpp:553-563).  `out` / `in` are the local-space
+// outgoing and incoming directions of BSDF::EvaluationContext (incoming points towards the surface).
+RTB_HD float bsdf_pdf(const Vertex& vx, const V3& out, const V3& in, bool reverse)
+{
+    const float NdotV = out.z, NdotL = -in.z;
+    switch (vx.bsdf)
+    {
+    case RTB_BSDF_DIFFUSE:            // DiffuseBSDF.cpp:56-74
+    case RTB_BSDF_ROUGH_DIFFUSE:      // RoughDiffuseBSDF.cpp:75-93
+        if (NdotV > RTB_COS_EPSILON && NdotL > RTB_COS_EPSILON) return (reverse ? NdotV : NdotL) * RTB_INV_PI;
+        return 0.0f;
+    case RTB_BSDF_ROUGH_METAL:
+    {
+        // RoughMetalBSDF::Pdf, RoughMetalBSDF.cpp:109-137 (the same value in both directions)
+        const float roughness = vx.roughness;
+        if (roughness < RTB_SPECULAR_ROUGHNESS_THRESHOLD) return 0.0f;
+        const V3 m = normalize3(out - in);
+        const float VdotH = dot3(m, out);
+        if (NdotV < RTB_COS_EPSILON || NdotL < RTB_COS_EPSILON || VdotH < RTB_COS_EPSILON) return 0.0f;
+        const Microfacet microfacet(roughness * roughness);
+        return microfacet.Pdf(m) / (4.0f * VdotH);
+    }
+    case RTB_BSDF_ROUGH_DIELECTRIC:
+    {
+        // RoughDielectricBSDF::Pdf, RoughDielectricBSDF.cpp:195-253 ("TODO is this correct for reverse direction?")
+        if (s_abs(NdotV) < RTB_COS_EPSILON || s_abs(NdotL) < RTB_COS_EPSILON) return 0.0f;
+        const float roughness = vx.roughness;
+        if (roughness < RTB_SPECULAR_ROUGHNESS_THRESHOLD) return 0.0f;
+        const float ior = vx.IoR;
+        const float eta = NdotV < 0.0f ? ior : 1.0f / ior;
+        const bool reflection = NdotV * NdotL >= 0.0f;
+        V3 m;
+        if (reflection) m = out - in;
+        else m = eta * out - in;
+        const float sg = m.z > 0.0f ? 1.0f : (m.z < 0.0f ? -1.0f : 0.0f);
+        m = m * sg;
+        m = normalize3(m);
+        if (s_abs(m.z) < RTB_COS_EPSILON) return 0.0f;
+        const float VdotH = dot3(m, out);
+        const float LdotH = dot3(m, neg(in));
+        const Microfacet microfacet(roughness * roughness);
+        const float F = fresnel_dielectric(VdotH, ior);
+        if (reflection) return F * microfacet.Pdf(m) / (4.0f * s_abs(VdotH));
+        const float denom = s_sqr(eta * VdotH + LdotH);
+        return (1.0f - F) * microfacet.Pdf(m) * s_abs(LdotH) / denom;
+    }
+    case RTB_BSDF_PLASTIC:
+    case RTB_BSDF_ROUGH_PLASTIC:
+    {
+        // PlasticBSDF::Pdf, PlasticBSDF.cpp:101-127; RoughPlasticBSDF::Pdf, RoughPlasticBSDF.cpp:160-212
+        if (NdotV < RTB_COS_EPSILON || NdotL < RTB_COS_EPSILON) return 0.0f;
+        const float Fi = fresnel_dielectric(NdotV, vx.IoR);
+        const float specularWeight = Fi;
+        const float diffuseWeight = (1.0f - Fi) * color_max(vx.baseColor);
+        const float specularProbability = specularWeight / (specularWeight + diffuseWeight);
+        const float diffuseProbability = 1.0f - specularProbability;
+        if (vx.bsdf == RTB_BSDF_PLASTIC || vx.roughness < RTB_SPECULAR_ROUGHNESS_THRESHOLD)
+            return (reverse ? NdotV : NdotL) * RTB_INV_PI * diffuseProbability;
+        const float diffusePdf = (reverse ? NdotV : NdotL) * RTB_INV_PI;
+        float specularPdf = 0.0f;
+        const V3 m = normalize3(out - in);
+        const float VdotH = dot3(m, out);
+        if (VdotH >= RTB_COS_EPSILON)
+        {
+            const Microfacet microfacet(vx.roughness * vx.roughness);
+            specularPdf = microfacet.Pdf(m) / (4.0f * VdotH);
+        }
+        return diffusePdf * diffuseProbability + specularPdf * specularProbability;
+    }
+    default:
+        return 0.0f;      // Metal, Dielectric (Dirac deltas) and Null: MetalBSDF.cpp:56-63, DielectricBSDF.cpp:124-131, NullBSDF.cpp:27-33
+    }
+}
+
 // ---- camera connection -------------------------------------------------------------------------------------------------
 
 RTB_HD V4 row_times_matrix(const V4& a, const M4& b)          // one row of Matrix4::operator*, Matrix4.cpp:35-75: a mul, then three FMAs

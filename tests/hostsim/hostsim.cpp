@@ -12,6 +12,7 @@
 //   hostsim emit <scene.rtb> <samples.f32 (5 per sample)> <out.f32 (12 per light and sample)>
 //   hostsim camera <scene.rtb> <w> <h> <points.f32 (3 per point)> <ref.bin (for the directions)> <out.bin (7 words per point)>
 //   hostsim lighttrace <scene.rtb> <w> <h> <passes> <maxDepth> <seed> <out.sum>     (LightTracer: statistical parity only)
+//   hostsim bsdfpdf <scene.rtb> <dirs.f32 (6 per pair)> <out.f32 (forward, reverse per material and pair)>
 //   hostsim blockerrors <sum.bin> <sum2.bin> <w> <h> <numPasses> <blocks.bin> <out.f32>
 //   hostsim front  <sum.bin> <w> <h> <numPasses> <exposure> <contrast> <saturation> <dither> <tonemapper> <r,g,b filter> <out.bgra> [bloomFactor]
 #include <cstdio>
@@ -435,6 +436,36 @@ static int cmdLightTrace(int argc, char** argv)
     return 0;
 }
 
+// BSDF::Pdf, forward and reverse, of every material (constant parameters) for a list of local direction pairs
+static int cmdBsdfPdf(int argc, char** argv)
+{
+    if (argc < 5) die("bsdfpdf: arguments");
+    World world; world.load(argv[2]);
+    FILE* f = fopen(argv[3], "rb");
+    if (!f) die("cannot open dirs");
+    std::vector<float> dirs;
+    float v[6];
+    while (fread(v, 4, 6, f) == 6) dirs.insert(dirs.end(), v, v + 6);
+    fclose(f);
+    FILE* of = fopen(argv[4], "wb");
+    for (size_t m = 0; m < world.file.materials.size(); ++m)
+    {
+        const RtbMaterial& mat = world.file.materials[m];
+        Vertex vx;
+        memset(&vx, 0, sizeof(vx));
+        vx.bsdf = mat.bsdf; vx.baseColor = v4(mat.baseColor[0], mat.baseColor[1], mat.baseColor[2], mat.baseColor[3]);
+        vx.roughness = mat.roughness; vx.metalness = mat.metalness; vx.IoR = mat.IoR; vx.K = mat.K;
+        for (size_t i = 0; i + 6 <= dirs.size(); i += 6)
+        {
+            const V3 out = v3(dirs[i], dirs[i + 1], dirs[i + 2]), in = v3(dirs[i + 3], dirs[i + 4], dirs[i + 5]);
+            const float r[2] = { bsdf_pdf(vx, out, in, false), bsdf_pdf(vx, out, in, true) };
+            fwrite(r, 4, 2, of);
+        }
+    }
+    fclose(of);
+    return 0;
+}
+
 // the arithmetic of rtb_block_errors on raster sum buffers (the three kernels, one thread after the other)
 static int cmdBlockErrors(int argc, char** argv)
 {
@@ -528,6 +559,7 @@ int main(int argc, char** argv)
     if (cmd == "primary") return cmdPrimary(argc, argv);
     if (cmd == "front") return cmdFront(argc, argv);
     if (cmd == "emit") return cmdEmit(argc, argv);
+    if (cmd == "bsdfpdf") return cmdBsdfPdf(argc, argv);
     if (cmd == "lighttrace") return cmdLightTrace(argc, argv);
     if (cmd == "camera") return cmdCamera(argc, argv);
     if (cmd == "blockerrors") return cmdBlockErrors(argc, argv);

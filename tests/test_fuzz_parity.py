@@ -291,6 +291,13 @@ def test_random_scene_on_the_device_headers(hostsim, tmp_path, seed):
     util.run_rtref(["emit", "--scene", sj, "--data", data, "--samples", sp, "--out", refp])
     subprocess.run([HOSTSIM, "emit", flat, sp, minep], check=True)
     assert open(refp, "rb").read() == open(minep, "rb").read(), "seed %d: ILight::Emit differs" % seed
+    # BSDF::Pdf, forward and reverse, of every material
+    from tests.test_hostsim_parity import bsdf_direction_pairs
+    dp, refp, minep = str(tmp_path / "dirs.f32"), str(tmp_path / "pdf_ref.f32"), str(tmp_path / "pdf_mine.f32")
+    bsdf_direction_pairs(300, seed).tofile(dp)
+    util.run_rtref(["bsdfpdf", "--scene", sj, "--data", data, "--dirs", dp, "--out", refp])
+    subprocess.run([HOSTSIM, "bsdfpdf", flat, dp, minep], check=True)
+    assert open(refp, "rb").read() == open(minep, "rb").read(), "seed %d: BSDF::Pdf differs" % seed
     # DebugRenderer: one mode per scene (normals / tangents / texture coordinates / material parameters ...)
     mode = 1 + seed % 12
     sump, passp, out = str(tmp_path / "dbg.sum"), str(tmp_path / "dbg.passes"), str(tmp_path / "dbg_mine.sum")

@@ -373,3 +373,37 @@ def test_hostsim_light_tracer_statistics(hostsim, tmp_path, scene, passes, mean_
     assert (np.abs(ma - mb) <= mean_tolerance * ma).all(), (ma, mb)
     blocks = lambda x: x.reshape(6, 8, 6, 8, 3).mean(axis=(1, 3)).ravel()
     assert np.corrcoef(blocks(a), blocks(b))[0, 1] >= min_correlation
+
+
+def bsdf_direction_pairs(n=1500, seed=6):
+    """(local outgoing, local incoming) unit vector pairs: reflection and transmission configurations, arbitrary ones
+    (mostly clipped to 0), and a few axis-aligned cases."""
+    rng = np.random.default_rng(seed)
+
+    def unit(k):
+        d = rng.normal(size=(k, 3))
+        return (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+
+    out, inn = unit(n), unit(n)
+    out[:n // 3, 2] = np.abs(out[:n // 3, 2]); inn[:n // 3, 2] = -np.abs(inn[:n // 3, 2])
+    a, b = n // 3, n // 3 + n // 8
+    out[a:b, 2] = np.abs(out[a:b, 2]); inn[a:b, 2] = np.abs(inn[a:b, 2])
+    out[0], inn[0] = [0, 0, 1], [0, 0, -1]
+    out[1], inn[1] = [1, 0, 0], [0, 0, -1]
+    out[2], inn[2] = [0, 0, 1], [0.6, 0, -0.8]
+    return np.hstack([out, inn]).astype(np.float32)
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
+@pytest.mark.parametrize("scene", ["materials", "cornell", "textures", "mesh_small"])
+def test_hostsim_bsdf_pdfs_against_the_live_reference(hostsim, tmp_path, scene):
+    """BSDF::Pdf(ctx, ForwardPdf / ReversePdf) of every material (all nine BSDFs, incl. the specular fallback of the rough
+    ones) for 1 500 direction pairs: what VCM's vertex connection evaluates (csrc/rtb_bidir.h bsdf_pdf), bit for bit."""
+    scn = os.path.join(util.GOLDEN, "scenes")
+    dp, refp, minep = str(tmp_path / "dirs.f32"), str(tmp_path / "ref.f32"), str(tmp_path / "mine.f32")
+    bsdf_direction_pairs().tofile(dp)
+    util.run_rtref(["bsdfpdf", "--scene", os.path.join(scn, scene + ".json"), "--data", scn + "/", "--dirs", dp, "--out", refp])
+    subprocess.run([HOSTSIM, "bsdfpdf", util.golden(scene + ".rtb"), dp, minep], check=True)
+    want = np.fromfile(refp, dtype=np.float32)
+    assert len(want) % 3000 == 0 and (want > 0).sum() > 1000 and np.isfinite(want).all()
+    assert want.tobytes() == open(minep, "rb").read()
