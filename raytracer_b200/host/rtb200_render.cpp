@@ -4,6 +4,8 @@
 //   rtb200_render -s scene.json --data DIR -w 1920 -h 1080 --spp 64 --renderer "Path Tracer MIS" --depth 8
 //                 --dims 128 --strategy all --seed 12345 --device 0 --out sum.f32 [--flat scene.rtb]
 //                 [--front image.bmp --exposure E --contrast C --saturation S --dither D --bloom B --tonemapper 0..3]
+//                 [--adaptive 1 --adaptive-initial 10 --adaptive-min-block 4 --adaptive-max-block 256
+//                  --adaptive-subdivision 0.005 --adaptive-convergence 0.0001]      AdaptiveRenderingSettings, Context.h:35-43
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -29,6 +31,7 @@ int main(int argc, char** argv)
     {
         fprintf(stderr, "usage: rtb200_render -s scene.json [--data DIR] [-w W] [-h H] [--spp N] [--renderer NAME] [--depth D] [--dims K]\n"
                         "                     [--strategy all|single] [--seed S] [--device I] [--bluenoise FILE] [--out sum.f32] [--flat scene.rtb]\n"
+                        "                     [--adaptive 1] [--adaptive-initial N] [--adaptive-min-block N] [--adaptive-max-block N] [--adaptive-subdivision T] [--adaptive-convergence T]\n"
                         "                     [--front image.bmp] [--exposure E] [--contrast C] [--saturation S] [--dither D] [--bloom B] [--tonemapper 0..3]\n");
         return 2;
     }
@@ -55,16 +58,27 @@ int main(int argc, char** argv)
     p.maxRayDepth = atoi(get("--depth", "8").c_str());
     p.dimensions = atoi(get("--dims", "128").c_str());
     p.lightSamplingStrategy = get("--strategy", "all") == "single" ? RTB_LIGHT_SAMPLING_SINGLE : RTB_LIGHT_SAMPLING_ALL;
+    p.adaptiveSettings.enable = atoi(get("--adaptive", "0").c_str()) != 0;
+    p.adaptiveSettings.numInitialPasses = atoi(get("--adaptive-initial", "10").c_str());
+    p.adaptiveSettings.minBlockSize = atoi(get("--adaptive-min-block", "4").c_str());
+    p.adaptiveSettings.maxBlockSize = atoi(get("--adaptive-max-block", "256").c_str());
+    p.adaptiveSettings.subdivisionTreshold = (float)atof(get("--adaptive-subdivision", "0.005").c_str());
+    p.adaptiveSettings.convergenceTreshold = (float)atof(get("--adaptive-convergence", "0.0001").c_str());
     vp.SetRenderingParams(p);
     vp.SetSeed(strtoull(get("--seed", "12345").c_str(), nullptr, 10));
     if (!vp.SetRenderer(get("--renderer", "Path Tracer MIS"))) { fprintf(stderr, "[ERROR] %s\n", vp.GetLastError().c_str()); return 1; }
     if (!vp.Resize(w, h)) { fprintf(stderr, "[ERROR] %s\n", vp.GetLastError().c_str()); return 1; }
     const auto t0 = std::chrono::steady_clock::now();
-    for (uint32_t i = 0; i < spp; ++i) if (!vp.Render(camera)) { fprintf(stderr, "[ERROR] %s\n", vp.GetLastError().c_str()); return 1; }
+    // all passes in one call: the device traces them in shared wavefronts, the image is the one `spp` Render() calls give
+    if (!vp.RenderPasses(camera, spp)) { fprintf(stderr, "[ERROR] %s\n", vp.GetLastError().c_str()); return 1; }
     vp.Synchronize();
     const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     RtbCounters c;
     vp.GetCounters(c);
+    rt::RenderingProgress progress;
+    if (vp.GetProgress(progress))
+        fprintf(stderr, "progress: %u passes, %u active blocks, %u active pixels, converged %.4f, average error %g\n", progress.passesFinished,
+                progress.activeBlocks, progress.activePixels, progress.converged, progress.averageError);
     printf("{\"width\": %u, \"height\": %u, \"passes\": %u, \"seconds\": %.6f, \"numPrimaryRays\": %llu, \"numRays\": %llu, \"numShadowRays\": %llu, "
            "\"numShadowRaysHit\": %llu, \"mrays_per_s\": %.3f, \"msamples_per_s\": %.3f}\n", w, h, spp, s,
            (unsigned long long)c.numPrimaryRays, (unsigned long long)c.numRays, (unsigned long long)c.numShadowRays, (unsigned long long)c.numShadowRaysHit,
