@@ -13,6 +13,7 @@
 //   primary  Camera::GenerateRay for every pixel exactly as Viewport::RenderTile calls it
 //   texeval  ITexture::Evaluate of every texture of the scene at a list of (u, v)
 //   emit     ILight::Emit of every light of the scene for a list of (position sample x3, direction sample x2)
+//   illuminate ILight::Illuminate without solid-angle sampling (as VCM calls it) for a list of shading points
 //   bsdfpdf  BSDF::Pdf (forward and reverse) of every material of the scene for a list of direction pairs
 //   camera   Camera::WorldToFilm and Camera::PdfW for a list of world-space points
 //   writeexr a seeded random HDR image written by the reference's own EXR writer (tinyexr) - test input for EXR readers
@@ -821,6 +822,47 @@ int CmdEmit(const Args& a)
     return 0;
 }
 
+// illuminate --scene X.json --points F (15 floats each: position, tangent, bitangent, normal, sample) --out F: per light,
+// per point 10 floats: direction to the light, distance, directPdfW, emissionPdfW, cosAtLight, radiance rgb
+int CmdIlluminate(const Args& a)
+{
+    Scene scene; Camera camera;
+    if (!LoadSceneFile(a, scene, camera, 64, 64)) return 1;
+    FILE* f = fopen(a.Str("points").c_str(), "rb");
+    if (!f) Die("cannot open --points");
+    std::vector<float> pts;
+    float v[15];
+    while (fread(v, 4, 15, f) == 15) pts.insert(pts.end(), v, v + 15);
+    fclose(f);
+    FILE* o = fopen(a.Str("out").c_str(), "wb");
+    if (!o) Die("cannot open --out");
+    Wavelength wavelength;
+    for (const LightSceneObject* lightObject : scene.GetLights())
+    {
+        const ILight& light = lightObject->GetLight();
+        const Matrix4 lightToWorld = lightObject->GetTransform(0.0f);
+        const Matrix4 worldToLight = lightObject->GetInverseTransform(0.0f);
+        for (size_t i = 0; i + 15 <= pts.size(); i += 15)
+        {
+            const float* p = &pts[i];
+            IntersectionData intersection;
+            intersection.frame[0] = Vector4(p[3], p[4], p[5], 0.0f);
+            intersection.frame[1] = Vector4(p[6], p[7], p[8], 0.0f);
+            intersection.frame[2] = Vector4(p[9], p[10], p[11], 0.0f);
+            intersection.frame[3] = Vector4(p[0], p[1], p[2], 1.0f);
+            intersection.texCoord = Vector4::Zero();
+            const ILight::IlluminateParam param = { worldToLight, lightToWorld, intersection, wavelength, Float3(p[12], p[13], p[14]), false };
+            ILight::IlluminateResult r;
+            const RayColor color = light.Illuminate(param, r);
+            const Vector4 rgb = color.ConvertToTristimulus(wavelength);
+            const float out[10] = { r.directionToLight.x, r.directionToLight.y, r.directionToLight.z, r.distance, r.directPdfW, r.emissionPdfW, r.cosAtLight, rgb.x, rgb.y, rgb.z };
+            WriteBytes(o, out, sizeof(out));
+        }
+    }
+    fclose(o);
+    return 0;
+}
+
 // bsdfpdf --scene X.json --dirs F (6 floats each: local outgoing xyz, local incoming xyz, both unit) --out F:
 // per material (Scene flatten order = first use by an object), per pair: forward pdf, reverse pdf.  Material parameters
 // are the constants of the material (no texture lookups).
@@ -948,6 +990,7 @@ int main(int argc, char** argv)
     if (a.cmd == "emit") return CmdEmit(a);
     if (a.cmd == "camera") return CmdCamera(a);
     if (a.cmd == "bsdfpdf") return CmdBsdfPdf(a);
+    if (a.cmd == "illuminate") return CmdIlluminate(a);
     if (a.cmd == "primary") return CmdPrimary(a);
     fprintf(stderr, "usage: rtref render|flat|trace|sampler|primary --scene X.json [options]\n");
     return 2;

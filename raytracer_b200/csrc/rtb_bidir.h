@@ -159,6 +159,49 @@ RTB_HD V4 light_emit(const SceneView& S, const DLight& light, float p0, float p1
     }
 }
 
+// ---- ILight::Illuminate as the bidirectional renderers call it --------------------------------------------------------------
+// VCM passes rendererSupportsSolidAngleSampling = false (VertexConnectionAndMerging.cpp:649) and reads emissionPdfW as
+// well: area lights then take the area-sampling branch of AreaLight::Illuminate (AreaLight.cpp:78-102), the other light
+// types behave as for the path tracers (light_illuminate, rtb_shading.h) and add their emission pdf.
+struct IlluminateResultBidir { V3 directionToLight; float distance, directPdfW, emissionPdfW, cosAtLight; };
+
+template <bool kTex = true>
+RTB_HD V4 light_illuminate_bidir(const SceneView& S, const DLight& light, const Vertex& vx, float u0, float u1, float u2, IlluminateResultBidir& out)
+{
+    if (light.type == RTB_LIGHT_AREA)
+    {
+        out.directionToLight = v3s(0.0f); out.distance = -1.0f; out.directPdfW = -1.0f; out.emissionPdfW = -1.0f; out.cosAtLight = -1.0f;
+        V3 positionLocal, normalLocal;
+        shape_sample_point(S.shapes[light.shapeIndex], u0, u1, u2, positionLocal, normalLocal);
+        const V3 lightPointWorld = transform_point(light.transform, positionLocal);
+        const V3 normalWorld = transform_point(light.transform, normalLocal);          // TransformPoint on the normal, as in the reference
+        out.directionToLight = lightPointWorld - vx.position;
+        const float sqrDistance = sqr_length3(out.directionToLight);
+        out.distance = sqrtf(sqrDistance);
+        out.directionToLight = out.directionToLight / out.distance;
+        const float cosNormalDir = dot3(v3(-normalWorld.x, -normalWorld.y, -normalWorld.z), out.directionToLight);
+        if (cosNormalDir < RTB_EPSILON) return v4s(0.0f);
+        const float invArea = 1.0f / shape_surface_area(S.shapes[light.shapeIndex]);
+        out.cosAtLight = cosNormalDir;
+        out.directPdfW = invArea * sqrDistance / cosNormalDir;
+        out.emissionPdfW = cosNormalDir * invArea * RTB_INV_PI;
+        return light.color;
+    }
+    IlluminateResult r;
+    r.directionToLight = v3s(0.0f); r.distance = -1.0f; r.directPdfW = -1.0f; r.cosAtLight = -1.0f;
+    const V4 color = light_illuminate<kTex>(S, light, vx, u0, u1, u2, r);
+    out.directionToLight = r.directionToLight; out.distance = r.distance; out.directPdfW = r.directPdfW; out.cosAtLight = r.cosAtLight;
+    const float circlePdf = 1.0f / (RTB_PI * s_sqr(RTB_SCENE_RADIUS));
+    switch (light.type)
+    {
+    case RTB_LIGHT_POINT: out.emissionPdfW = RTB_INV_PI / 4.0f; break;                                   // PointLight.cpp:34-49
+    case RTB_LIGHT_SPOT: out.emissionPdfW = light.isDelta ? 1.0f : sphere_cap_pdf(light.cosAngle); break;  // SpotLight.cpp:41-61
+    case RTB_LIGHT_DIRECTIONAL: out.emissionPdfW = r.directPdfW * circlePdf; break;                        // DirectionalLight.cpp:80-91
+    default: out.emissionPdfW = (RTB_INV_PI / 4.0f) * circlePdf; break;                                    // BackgroundLight.cpp:63-76
+    }
+    return color;
+}
+
 // ---- BSDF::Pdf(ctx, ForwardPdf | ReversePdf) for the nine BSDFs ------------------------------------------------------------
 // (what VCM's vertex connection asks for, VertexConnectionAndMerging.cpp:553-563).  `out` / `in` are the local-space
 // outgoing and incoming directions of BSDF::EvaluationContext (incoming points towards the surface).

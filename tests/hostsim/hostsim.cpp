@@ -13,6 +13,7 @@
 //   hostsim camera <scene.rtb> <w> <h> <points.f32 (3 per point)> <ref.bin (for the directions)> <out.bin (7 words per point)>
 //   hostsim lighttrace <scene.rtb> <w> <h> <passes> <maxDepth> <seed> <out.sum>     (LightTracer: statistical parity only)
 //   hostsim bsdfpdf <scene.rtb> <dirs.f32 (6 per pair)> <out.f32 (forward, reverse per material and pair)>
+//   hostsim illuminate <scene.rtb> <points.f32 (15 per point)> <out.f32 (10 per light and point)>
 //   hostsim blockerrors <sum.bin> <sum2.bin> <w> <h> <numPasses> <blocks.bin> <out.f32>
 //   hostsim front  <sum.bin> <w> <h> <numPasses> <exposure> <contrast> <saturation> <dither> <tonemapper> <r,g,b filter> <out.bgra> [bloomFactor]
 #include <cstdio>
@@ -466,6 +467,34 @@ static int cmdBsdfPdf(int argc, char** argv)
     return 0;
 }
 
+// ILight::Illuminate without solid-angle sampling (the bidirectional renderers' call) for every light and shading point
+static int cmdIlluminate(int argc, char** argv)
+{
+    if (argc < 5) die("illuminate: arguments");
+    World world; world.load(argv[2]);
+    FILE* f = fopen(argv[3], "rb");
+    if (!f) die("cannot open points");
+    std::vector<float> pts;
+    float v[15];
+    while (fread(v, 4, 15, f) == 15) pts.insert(pts.end(), v, v + 15);
+    fclose(f);
+    FILE* of = fopen(argv[4], "wb");
+    for (uint32_t l = 0; l < world.S.numLights; ++l)
+        for (size_t i = 0; i + 15 <= pts.size(); i += 15)
+        {
+            const float* p = &pts[i];
+            Vertex vx;
+            memset(&vx, 0, sizeof(vx));
+            vx.position = v3(p[0], p[1], p[2]); vx.tangent = v3(p[3], p[4], p[5]); vx.bitangent = v3(p[6], p[7], p[8]); vx.normal = v3(p[9], p[10], p[11]);
+            IlluminateResultBidir r;
+            const V4 c = light_illuminate_bidir<true>(world.S, world.S.lights[l], vx, p[12], p[13], p[14], r);
+            const float out[10] = { r.directionToLight.x, r.directionToLight.y, r.directionToLight.z, r.distance, r.directPdfW, r.emissionPdfW, r.cosAtLight, c.x, c.y, c.z };
+            fwrite(out, 4, 10, of);
+        }
+    fclose(of);
+    return 0;
+}
+
 // the arithmetic of rtb_block_errors on raster sum buffers (the three kernels, one thread after the other)
 static int cmdBlockErrors(int argc, char** argv)
 {
@@ -559,6 +588,7 @@ int main(int argc, char** argv)
     if (cmd == "primary") return cmdPrimary(argc, argv);
     if (cmd == "front") return cmdFront(argc, argv);
     if (cmd == "emit") return cmdEmit(argc, argv);
+    if (cmd == "illuminate") return cmdIlluminate(argc, argv);
     if (cmd == "bsdfpdf") return cmdBsdfPdf(argc, argv);
     if (cmd == "lighttrace") return cmdLightTrace(argc, argv);
     if (cmd == "camera") return cmdCamera(argc, argv);

@@ -291,6 +291,13 @@ def test_random_scene_on_the_device_headers(hostsim, tmp_path, seed):
     util.run_rtref(["emit", "--scene", sj, "--data", data, "--samples", sp, "--out", refp])
     subprocess.run([HOSTSIM, "emit", flat, sp, minep], check=True)
     assert open(refp, "rb").read() == open(minep, "rb").read(), "seed %d: ILight::Emit differs" % seed
+    # ILight::Illuminate as the bidirectional renderers call it
+    from tests.test_hostsim_parity import shading_points
+    pp, refp, minep = str(tmp_path / "points.f32"), str(tmp_path / "ill_ref.f32"), str(tmp_path / "ill_mine.f32")
+    shading_points(100, seed).tofile(pp)
+    util.run_rtref(["illuminate", "--scene", sj, "--data", data, "--points", pp, "--out", refp])
+    subprocess.run([HOSTSIM, "illuminate", flat, pp, minep], check=True)
+    assert open(refp, "rb").read() == open(minep, "rb").read(), "seed %d: ILight::Illuminate (area sampling) differs" % seed
     # BSDF::Pdf, forward and reverse, of every material
     from tests.test_hostsim_parity import bsdf_direction_pairs
     dp, refp, minep = str(tmp_path / "dirs.f32"), str(tmp_path / "pdf_ref.f32"), str(tmp_path / "pdf_mine.f32")

@@ -407,3 +407,28 @@ def test_hostsim_bsdf_pdfs_against_the_live_reference(hostsim, tmp_path, scene):
     want = np.fromfile(refp, dtype=np.float32)
     assert len(want) % 3000 == 0 and (want > 0).sum() > 1000 and np.isfinite(want).all()
     assert want.tobytes() == open(minep, "rb").read()
+
+
+def shading_points(n=500, seed=8):
+    """(position, orthonormal frame, 3 samples) rows for ILight::Illuminate."""
+    rng = np.random.default_rng(seed)
+    pos = rng.normal(size=(n, 3)) * 3
+    nrm = rng.normal(size=(n, 3)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    t = np.cross(nrm, rng.normal(size=(n, 3))); t /= np.linalg.norm(t, axis=1, keepdims=True)
+    return np.hstack([pos, t, np.cross(nrm, t), nrm, np.minimum(rng.random((n, 3)), 0.99999994)]).astype(np.float32)
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
+@pytest.mark.parametrize("scene", ["materials", "cornell", "textures", "mesh_small", "c1_sphere_area"])
+def test_hostsim_bidirectional_illuminate_against_the_live_reference(hostsim, tmp_path, scene):
+    """ILight::Illuminate with rendererSupportsSolidAngleSampling = false (how VCM calls it: area lights are sampled by
+    area, every light reports its emission pdf) for 500 shading points x every light: direction, distance, both pdfs,
+    cosAtLight and radiance, incl. the early-out cases, bit for bit (csrc/rtb_bidir.h light_illuminate_bidir)."""
+    scn = os.path.join(util.GOLDEN, "scenes")
+    pp, refp, minep = str(tmp_path / "points.f32"), str(tmp_path / "ref.f32"), str(tmp_path / "mine.f32")
+    shading_points().tofile(pp)
+    util.run_rtref(["illuminate", "--scene", os.path.join(scn, scene + ".json"), "--data", scn + "/", "--points", pp, "--out", refp])
+    subprocess.run([HOSTSIM, "illuminate", util.golden(scene + ".rtb"), pp, minep], check=True)
+    want = np.fromfile(refp, dtype=np.float32).reshape(-1, 10)
+    assert len(want) % 500 == 0 and (want[:, 7:].sum(axis=1) > 0).sum() > 20
+    assert want.tobytes() == open(minep, "rb").read()
