@@ -14,6 +14,7 @@
 //   texeval  ITexture::Evaluate of every texture of the scene at a list of (u, v)
 //   emit     ILight::Emit of every light of the scene for a list of (position sample x3, direction sample x2)
 //   illuminate ILight::Illuminate without solid-angle sampling (as VCM calls it) for a list of shading points
+//   radiance ILight::GetRadiance without solid-angle sampling, with both pdf outputs, for a list of light-space rays
 //   bsdfpdf  BSDF::Pdf (forward and reverse) of every material of the scene for a list of direction pairs
 //   camera   Camera::WorldToFilm and Camera::PdfW for a list of world-space points
 //   writeexr a seeded random HDR image written by the reference's own EXR writer (tinyexr) - test input for EXR readers
@@ -863,6 +864,43 @@ int CmdIlluminate(const Args& a)
     return 0;
 }
 
+// radiance --scene X.json --rays F (4 floats each: unit direction in light space, cosAtLight) --out F: per light that can be
+// hit (everything but point / spot lights), per ray 5 floats: radiance rgb, directPdfA, emissionPdfW (-1 where not written)
+int CmdRadiance(const Args& a)
+{
+    Scene scene; Camera camera;
+    if (!LoadSceneFile(a, scene, camera, 64, 64)) return 1;
+    FILE* f = fopen(a.Str("rays").c_str(), "rb");
+    if (!f) Die("cannot open --rays");
+    std::vector<float> rays;
+    float v[4];
+    while (fread(v, 4, 4, f) == 4) rays.insert(rays.end(), v, v + 4);
+    fclose(f);
+    FILE* o = fopen(a.Str("out").c_str(), "wb");
+    if (!o) Die("cannot open --out");
+    RenderingContext ctx;
+    for (const LightSceneObject* lightObject : scene.GetLights())
+    {
+        const ILight& light = lightObject->GetLight();
+        if (dynamic_cast<const PointLight*>(&light) || dynamic_cast<const SpotLight*>(&light)) continue;
+        for (size_t i = 0; i + 4 <= rays.size(); i += 4)
+        {
+            Ray ray;
+            ray.origin = Vector4::Zero();
+            ray.dir = Vector4(rays[i], rays[i + 1], rays[i + 2], 0.0f);
+            ray.invDir = Vector4::Zero(); ray.originDivDir = Vector4::Zero();
+            const ILight::RadianceParam param = { ctx, ray, Vector4::Zero(), rays[i + 3], false };
+            float directPdfA = -1.0f, emissionPdfW = -1.0f;
+            const RayColor color = light.GetRadiance(param, &directPdfA, &emissionPdfW);
+            const Vector4 rgb = color.ConvertToTristimulus(ctx.wavelength);
+            const float out[5] = { rgb.x, rgb.y, rgb.z, directPdfA, emissionPdfW };
+            WriteBytes(o, out, sizeof(out));
+        }
+    }
+    fclose(o);
+    return 0;
+}
+
 // bsdfpdf --scene X.json --dirs F (6 floats each: local outgoing xyz, local incoming xyz, both unit) --out F:
 // per material (Scene flatten order = first use by an object), per pair: forward pdf, reverse pdf.  Material parameters
 // are the constants of the material (no texture lookups).
@@ -991,6 +1029,7 @@ int main(int argc, char** argv)
     if (a.cmd == "camera") return CmdCamera(a);
     if (a.cmd == "bsdfpdf") return CmdBsdfPdf(a);
     if (a.cmd == "illuminate") return CmdIlluminate(a);
+    if (a.cmd == "radiance") return CmdRadiance(a);
     if (a.cmd == "primary") return CmdPrimary(a);
     fprintf(stderr, "usage: rtref render|flat|trace|sampler|primary --scene X.json [options]\n");
     return 2;

@@ -202,6 +202,44 @@ RTB_HD V4 light_illuminate_bidir(const SceneView& S, const DLight& light, const 
     return color;
 }
 
+// ILight::GetRadiance with rendererSupportsSolidAngleSampling = false and both pdf outputs (VCM's EvaluateLight,
+// VertexConnectionAndMerging.cpp:576-626): `lightRayDir` is the direction of the ray in light space.  Point / spot lights
+// cannot be hit.  Returns the radiance; the pdfs keep the caller's values where the reference does not write them.
+template <bool kTex = true>
+RTB_HD V4 light_radiance_bidir(const SceneView& S, const DLight& light, const V3& lightRayDir, float cosAtLight, float& directPdfA, float& emissionPdfW)
+{
+    const float circlePdf = 1.0f / (RTB_PI * s_sqr(RTB_SCENE_RADIUS));
+    switch (light.type)
+    {
+    case RTB_LIGHT_AREA:
+    {
+        // AreaLight::GetRadiance, AreaLight.cpp:107-147
+        if (cosAtLight < RTB_EPSILON) return v4s(0.0f);
+        const float invArea = 1.0f / shape_surface_area(S.shapes[light.shapeIndex]);
+        directPdfA = invArea;
+        emissionPdfW = cosAtLight * invArea * RTB_INV_PI;
+        return light.color;
+    }
+    case RTB_LIGHT_BACKGROUND:
+        // BackgroundLight::GetRadiance, BackgroundLight.cpp:78-90
+        directPdfA = uniform_hemisphere_pdf();
+        emissionPdfW = (RTB_INV_PI / 4.0f) * circlePdf;
+        return background_color<kTex>(S, light, lightRayDir);
+    case RTB_LIGHT_DIRECTIONAL:
+    {
+        // DirectionalLight::GetRadiance, DirectionalLight.cpp:92-118
+        if (light.isDelta) return v4s(0.0f);
+        if (dot3(lightRayDir, v3(0.0f, 0.0f, 1.0f)) > -light.cosAngle) return v4s(0.0f);
+        const float directPdf = sphere_cap_pdf(light.cosAngle);
+        directPdfA = directPdf;
+        emissionPdfW = directPdf * circlePdf;
+        return light.color;
+    }
+    default:
+        return v4s(0.0f);
+    }
+}
+
 // ---- BSDF::Pdf(ctx, ForwardPdf | ReversePdf) for the nine BSDFs ------------------------------------------------------------
 // (what VCM's vertex connection asks for, VertexConnectionAndMerging.cpp:553-563).  `out` / `in` are the local-space
 // outgoing and incoming directions of BSDF::EvaluationContext (incoming points towards the surface).

@@ -14,6 +14,7 @@
 //   hostsim lighttrace <scene.rtb> <w> <h> <passes> <maxDepth> <seed> <out.sum>     (LightTracer: statistical parity only)
 //   hostsim bsdfpdf <scene.rtb> <dirs.f32 (6 per pair)> <out.f32 (forward, reverse per material and pair)>
 //   hostsim illuminate <scene.rtb> <points.f32 (15 per point)> <out.f32 (10 per light and point)>
+//   hostsim radiance <scene.rtb> <rays.f32 (4 per ray)> <out.f32 (5 per hittable light and ray)>
 //   hostsim blockerrors <sum.bin> <sum2.bin> <w> <h> <numPasses> <blocks.bin> <out.f32>
 //   hostsim front  <sum.bin> <w> <h> <numPasses> <exposure> <contrast> <saturation> <dither> <tonemapper> <r,g,b filter> <out.bgra> [bloomFactor]
 #include <cstdio>
@@ -495,6 +496,34 @@ static int cmdIlluminate(int argc, char** argv)
     return 0;
 }
 
+// ILight::GetRadiance with both pdf outputs for every light a ray can hit
+static int cmdRadiance(int argc, char** argv)
+{
+    if (argc < 5) die("radiance: arguments");
+    World world; world.load(argv[2]);
+    FILE* f = fopen(argv[3], "rb");
+    if (!f) die("cannot open rays");
+    std::vector<float> rays;
+    float v[4];
+    while (fread(v, 4, 4, f) == 4) rays.insert(rays.end(), v, v + 4);
+    fclose(f);
+    FILE* of = fopen(argv[4], "wb");
+    for (uint32_t l = 0; l < world.S.numLights; ++l)
+    {
+        const DLight& light = world.S.lights[l];
+        if (light.type == RTB_LIGHT_POINT || light.type == RTB_LIGHT_SPOT) continue;
+        for (size_t i = 0; i + 4 <= rays.size(); i += 4)
+        {
+            float directPdfA = -1.0f, emissionPdfW = -1.0f;
+            const V4 c = light_radiance_bidir<true>(world.S, light, v3(rays[i], rays[i + 1], rays[i + 2]), rays[i + 3], directPdfA, emissionPdfW);
+            const float out[5] = { c.x, c.y, c.z, directPdfA, emissionPdfW };
+            fwrite(out, 4, 5, of);
+        }
+    }
+    fclose(of);
+    return 0;
+}
+
 // the arithmetic of rtb_block_errors on raster sum buffers (the three kernels, one thread after the other)
 static int cmdBlockErrors(int argc, char** argv)
 {
@@ -588,6 +617,7 @@ int main(int argc, char** argv)
     if (cmd == "primary") return cmdPrimary(argc, argv);
     if (cmd == "front") return cmdFront(argc, argv);
     if (cmd == "emit") return cmdEmit(argc, argv);
+    if (cmd == "radiance") return cmdRadiance(argc, argv);
     if (cmd == "illuminate") return cmdIlluminate(argc, argv);
     if (cmd == "bsdfpdf") return cmdBsdfPdf(argc, argv);
     if (cmd == "lighttrace") return cmdLightTrace(argc, argv);

@@ -432,3 +432,23 @@ def test_hostsim_bidirectional_illuminate_against_the_live_reference(hostsim, tm
     want = np.fromfile(refp, dtype=np.float32).reshape(-1, 10)
     assert len(want) % 500 == 0 and (want[:, 7:].sum(axis=1) > 0).sum() > 20
     assert want.tobytes() == open(minep, "rb").read()
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
+@pytest.mark.parametrize("scene", ["materials", "cornell", "textures", "mesh_small"])
+def test_hostsim_bidirectional_radiance_against_the_live_reference(hostsim, tmp_path, scene):
+    """ILight::GetRadiance with rendererSupportsSolidAngleSampling = false and both pdf outputs (VCM's EvaluateLight) for
+    every light a ray can hit (area, directional, constant / environment-mapped background) x 600 light-space rays with
+    cosAtLight on both sides of the cut-off: radiance, directPdfA, emissionPdfW, bit for bit."""
+    scn = os.path.join(util.GOLDEN, "scenes")
+    rp, refp, minep = str(tmp_path / "rays.f32"), str(tmp_path / "ref.f32"), str(tmp_path / "mine.f32")
+    rng = np.random.default_rng(9)
+    d = rng.normal(size=(600, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[:200, 2] = -np.abs(d[:200, 2]) * 50; d[:200] /= np.linalg.norm(d[:200], axis=1, keepdims=True)     # inside small directional cones too
+    cos = rng.uniform(-0.2, 1.0, size=(600, 1)); cos[:5, 0] = [0.0, 1e-6, 9e-7, 1.0, -1.0]
+    np.hstack([d, cos]).astype(np.float32).tofile(rp)
+    util.run_rtref(["radiance", "--scene", os.path.join(scn, scene + ".json"), "--data", scn + "/", "--rays", rp, "--out", refp])
+    subprocess.run([HOSTSIM, "radiance", util.golden(scene + ".rtb"), rp, minep], check=True)
+    want = np.fromfile(refp, dtype=np.float32).reshape(-1, 5)
+    assert len(want) % 600 == 0 and len(want) > 0 and (want[:, :3].sum(axis=1) > 0).any()
+    assert want.tobytes() == open(minep, "rb").read()
