@@ -23,6 +23,7 @@
 #include "SceneLoader.h"
 #include "../Core/Rendering/Renderer.h"
 #include "../Core/Rendering/DebugRenderer.h"
+#include "../Core/Rendering/VertexConnectionAndMerging.h"
 #include "../Core/Rendering/Viewport.h"
 #include "../Core/Rendering/Context.h"
 #include "../Core/Scene/Scene.h"
@@ -464,6 +465,13 @@ int CmdRender(const Args& a)
     RendererPtr renderer = CreateRenderer(rendererName, scene);
     if (!renderer) Die("unknown renderer");
     if (rendererName == "Debug") static_cast<DebugRenderer*>(renderer.get())->mRenderingMode = (DebugRenderingMode)a.Int("debug-mode", 1);
+    if (rendererName == "VCM")
+    {
+        // --vcm-connection 0|1 --vcm-merging 0|1: the renderer's own switches (VertexConnectionAndMerging.h)
+        VertexConnectionAndMerging* vcm = static_cast<VertexConnectionAndMerging*>(renderer.get());
+        vcm->mUseVertexConnection = a.Int("vcm-connection", 1) != 0;
+        vcm->mUseVertexMerging = a.Int("vcm-merging", 1) != 0;
+    }
     vp.SetRenderer(renderer);
     if (a.Has("dump-front"))
     {

@@ -15,6 +15,7 @@
 //   hostsim bsdfpdf <scene.rtb> <dirs.f32 (6 per pair)> <out.f32 (forward, reverse per material and pair)>
 //   hostsim illuminate <scene.rtb> <points.f32 (15 per point)> <out.f32 (10 per light and point)>
 //   hostsim radiance <scene.rtb> <rays.f32 (4 per ray)> <out.f32 (5 per hittable light and ray)>
+//   hostsim vcm <scene.rtb> <passes.bin> <w> <h> <seed> <connection 0|1> <merging 0|1> <out.sum> [bluenoise]     (statistical parity only)
 //   hostsim blockerrors <sum.bin> <sum2.bin> <w> <h> <numPasses> <blocks.bin> <out.f32>
 //   hostsim front  <sum.bin> <w> <h> <numPasses> <exposure> <contrast> <saturation> <dither> <tonemapper> <r,g,b filter> <out.bgra> [bloomFactor]
 #include <cstdio>
@@ -28,6 +29,7 @@
 #include "../../raytracer_b200/csrc/rtb_integrator.h"
 #include "../../raytracer_b200/csrc/rtb_postprocess.h"
 #include "../../raytracer_b200/csrc/rtb_bidir.h"
+#include "hostsim_vcm.h"
 #include "../../raytracer_b200/csrc/rtb_upload.h"
 #include "../../raytracer_b200/csrc/rtb_scene_file.h"
 
@@ -524,6 +526,59 @@ static int cmdRadiance(int argc, char** argv)
     return 0;
 }
 
+// VCM (hostsim_vcm.h): camera rays from the pass script, everything else from the host generator
+static int cmdVcm(int argc, char** argv)
+{
+    if (argc < 10) die("vcm: arguments");
+    World world; world.load(argv[2]);
+    Passes passes; passes.load(argv[3]);
+    const uint32_t w = atoi(argv[4]), h = atoi(argv[5]);
+    HostRng rng{ strtoull(argv[6], nullptr, 10) * 0x9E3779B97F4A7C15ULL + 1u };
+    VcmSettings settings;
+    settings.useVertexConnection = atoi(argv[7]) != 0; settings.useVertexMerging = atoi(argv[8]) != 0;
+    if (argc > 10 && strcmp(argv[10], "-") != 0) world.loadBlueNoise(argv[10]);
+    PassParams P;
+    memset(&P, 0, sizeof(P));
+    fillCamera(P, world.file.camera, w, h, tanf(world.file.fieldOfView * 0.5f));
+    fillBokeh(P, world.file);
+    P.useBlueNoise = world.S.blueNoise != nullptr; P.numSeedDims = passes.numDims;
+    CameraConnection camera;
+    camera.localToWorld = P.camLocalToWorld; camera.tanHalfFoV = P.tanHalfFoV; camera.aspectRatio = P.aspectRatio;
+    camera.worldToScreen = camera_world_to_screen(P.camLocalToWorld, P.aspectRatio, P.tanHalfFoV);
+    std::vector<float> sum((size_t)w * h * 3, 0.0f);
+    auto splat = [&](float filmX, float filmY, const V3& value)
+    {
+        const float cx = filmX * (float)w + 0.0f, cy = filmY * (float)h + 0.5f;
+        int32_t ix = cvt_rn(cx);
+        const float ux = rng.next_float();
+        rng.next_float(); rng.next_float(); rng.next_float();
+        if (ux < cx - (float)ix) ix++;
+        const int32_t x = ix, y = (int32_t)(h - 1) - (int32_t)cy;
+        if ((uint32_t)x < w && (uint32_t)y < h) { float* px = &sum[((size_t)y * w + x) * 3]; px[0] += value.x; px[1] += value.y; px[2] += value.z; }
+    };
+    auto sampler3 = [&]() { return rng.next_float(); };
+    VcmModel<HostRng> vcm(world.S, camera, settings, rng, w, h);
+    for (uint32_t p = 0; p < passes.numPasses; ++p)
+    {
+        P.passIndex = p;
+        P.seed = &passes.seeds[(size_t)p * passes.numDims];
+        P.sampleOffsetX = passes.offsets[p * 2]; P.sampleOffsetY = passes.offsets[p * 2 + 1];
+        vcm.BeginPass(p);
+        for (uint32_t y = 0; y < h; ++y) for (uint32_t x = 0; x < w; ++x)
+        {
+            PathState ps;
+            init_path(P, world.S.blueNoise, x, y, 0, ps);
+            const V4 c = vcm.RenderPixel(ps.ray, sampler3, splat);
+            float* px = &sum[((size_t)y * w + x) * 3];
+            px[0] += c.x; px[1] += c.y; px[2] += c.z;
+        }
+    }
+    FILE* f = fopen(argv[9], "wb");
+    fwrite(sum.data(), 4, sum.size(), f);
+    fclose(f);
+    return 0;
+}
+
 // the arithmetic of rtb_block_errors on raster sum buffers (the three kernels, one thread after the other)
 static int cmdBlockErrors(int argc, char** argv)
 {
@@ -617,6 +672,7 @@ int main(int argc, char** argv)
     if (cmd == "primary") return cmdPrimary(argc, argv);
     if (cmd == "front") return cmdFront(argc, argv);
     if (cmd == "emit") return cmdEmit(argc, argv);
+    if (cmd == "vcm") return cmdVcm(argc, argv);
     if (cmd == "radiance") return cmdRadiance(argc, argv);
     if (cmd == "illuminate") return cmdIlluminate(argc, argv);
     if (cmd == "bsdfpdf") return cmdBsdfPdf(argc, argv);

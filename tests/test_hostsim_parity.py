@@ -452,3 +452,32 @@ def test_hostsim_bidirectional_radiance_against_the_live_reference(hostsim, tmp_
     want = np.fromfile(refp, dtype=np.float32).reshape(-1, 5)
     assert len(want) % 600 == 0 and len(want) > 0 and (want[:, :3].sum(axis=1) > 0).any()
     assert want.tobytes() == open(minep, "rb").read()
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="oracle/_ref/exact not built")
+@pytest.mark.parametrize("scene,passes,connection,merging,mean_tolerance,min_correlation", [
+    ("cornell", 30, 1, 1, 0.02, 0.999),          # VCM as the reference configures it
+    ("materials", 30, 1, 1, 0.02, 0.999),        # all nine BSDFs, six lights of five types
+    ("textures", 40, 1, 1, 0.03, 0.995),         # textured materials, environment map
+    ("cornell", 30, 1, 0, 0.02, 0.999),          # vertex connection only (bidirectional path tracing)
+    ("cornell", 150, 0, 1, 0.06, 0.99),          # vertex merging only (photon mapping; noisy at this photon density)
+])
+def test_hostsim_vcm_statistics(hostsim, tmp_path, scene, passes, connection, merging, mean_tolerance, min_correlation):
+    """The reference's VCM renderer (VertexConnectionAndMerging.cpp) against the CPU model assembled from the checked
+    parts (tests/hostsim/hostsim_vcm.h): light sub-paths with dVCM / dVC / dVM bookkeeping, camera connection, next-event
+    estimation, vertex connection and vertex merging with the one-pass delay, in the reference's three modes.  The
+    reference draws its light paths from per-thread generators, so the comparison is statistical (mean colour and the
+    image at 8 x 8-pixel blocks)."""
+    w = h = 48
+    scn = os.path.join(util.GOLDEN, "scenes")
+    common = ["--scene", os.path.join(scn, scene + ".json"), "--data", scn + "/", "--width", w, "--height", h]
+    refp, passp, flatp, minep = (str(tmp_path / n) for n in ("ref.sum", "ref.passes", "scene.rtb", "mine.sum"))
+    util.run_rtref(["render", *common, "--passes", passes, "--dims", 256, "--renderer", "VCM", "--vcm-connection", connection, "--vcm-merging", merging,
+                    "--dump-sum", refp, "--dump-passes", passp])
+    util.run_rtref(["flat", *common, "--out", flatp])
+    subprocess.run([HOSTSIM, "vcm", flatp, passp, str(w), str(h), "7", str(connection), str(merging), minep, hostsim], check=True)
+    a, b = util.load_sum(refp, w, h) / passes, util.load_sum(minep, w, h) / passes
+    ma, mb = a.mean(axis=(0, 1)), b.mean(axis=(0, 1))
+    assert np.isfinite(b).all() and (np.abs(ma - mb) <= mean_tolerance * ma).all(), (ma, mb)
+    blocks = lambda x: x.reshape(6, 8, 6, 8, 3).mean(axis=(1, 3)).ravel()
+    assert np.corrcoef(blocks(a), blocks(b))[0, 1] >= min_correlation
