@@ -526,7 +526,7 @@ static int cmdRadiance(int argc, char** argv)
     return 0;
 }
 
-// VCM (hostsim_vcm.h): camera rays from the pass script, everything else from the host generator
+// VCM (hostsim_vcm.h): camera rays and camera-path samples from the pass script, light paths from the host generator
 static int cmdVcm(int argc, char** argv)
 {
     if (argc < 10) die("vcm: arguments");
@@ -556,7 +556,10 @@ static int cmdVcm(int argc, char** argv)
         const int32_t x = ix, y = (int32_t)(h - 1) - (int32_t)cy;
         if ((uint32_t)x < w && (uint32_t)y < h) { float* px = &sum[((size_t)y * w + x) * 3]; px[0] += value.x; px[1] += value.y; px[2] += value.z; }
     };
-    auto sampler3 = [&]() { return rng.next_float(); };
+    // the camera path draws from the pixel's sampler like the reference's (ctx.sampler: Halton + blue noise - its low
+    // discrepancy is what keeps the reference inside its own furnace-test tolerances); the light path from the generator
+    PathState* current = nullptr;
+    auto sampler3 = [&]() { return sampler_get_float(current->sampler, P, world.S.blueNoise); };
     VcmModel<HostRng> vcm(world.S, camera, settings, rng, w, h);
     for (uint32_t p = 0; p < passes.numPasses; ++p)
     {
@@ -568,6 +571,7 @@ static int cmdVcm(int argc, char** argv)
         {
             PathState ps;
             init_path(P, world.S.blueNoise, x, y, 0, ps);
+            current = &ps;
             const V4 c = vcm.RenderPixel(ps.ray, sampler3, splat);
             float* px = &sum[((size_t)y * w + x) * 3];
             px[0] += c.x; px[1] += c.y; px[2] += c.z;

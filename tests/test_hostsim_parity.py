@@ -481,3 +481,36 @@ def test_hostsim_vcm_statistics(hostsim, tmp_path, scene, passes, connection, me
     assert np.isfinite(b).all() and (np.abs(ma - mb) <= mean_tolerance * ma).all(), (ma, mb)
     blocks = lambda x: x.reshape(6, 8, 6, 8, 3).mean(axis=(1, 3)).ravel()
     assert np.corrcoef(blocks(a), blocks(b))[0, 1] >= min_correlation
+
+
+def write_pass_script(path, seeds, offsets):
+    with open(path, "wb") as f:
+        np.array([len(seeds), seeds.shape[1]], dtype=np.uint32).tofile(f)
+        for s, o in zip(seeds, offsets):
+            s.astype(np.uint32).tofile(f)
+            o.astype(np.float32).tofile(f)
+
+
+@pytest.mark.parametrize("name,material,fov,sphere,passes,expected,tolerance", [
+    # RaytracingTests.cpp:287-516 with its third renderer, "VCM": scene, pass count, expected colour, tolerance
+    ("background", None, 90.0, False, 1, [1.0, 2.0, 3.0], 0.01),
+    ("diffuse", {"bsdf": "diffuse", "baseColor": [0.4, 0.6, 0.8]}, 10.0, True, 100, [0.4, 1.2, 2.4], 0.05),
+    ("emissive", {"bsdf": "null", "baseColor": [0.0, 0.0, 0.0], "emissionColor": [3.0, 2.0, 1.0]}, 10.0, True, 1, [3.0, 2.0, 1.0], 0.0),
+    ("metal", {"bsdf": "metal", "baseColor": [0.4, 0.6, 0.8], "IoR": 0.0, "K": 100.0}, 10.0, True, 20, [0.4, 1.2, 2.4], 0.05),
+    ("dielectric", {"bsdf": "dielectric", "baseColor": [1.0, 1.0, 1.0]}, 10.0, True, 1000, [1.0, 2.0, 3.0], 0.075),
+])
+def test_hostsim_vcm_passes_the_reference_renderer_tests(hostsim, tmp_path, name, material, fov, sphere, passes, expected, tolerance):
+    """The reference's own renderer tests (furnace, background light) run on "VCM" too (RaytracingTests.cpp:17-22): the
+    CPU model of VCM passes them with the reference's scenes, pass counts and per-pixel tolerances."""
+    from raytracer_b200 import host_api
+    from tests.test_furnace import furnace_scene, validate, SIZE
+    sj = furnace_scene(tmp_path, material, fov=fov, sphere=sphere)
+    flatp, passp, outp = str(tmp_path / "scene.rtb"), str(tmp_path / "script.passes"), str(tmp_path / "mine.sum")
+    scene = host_api.Scene(sj, "")
+    try:
+        scene.save_flat(flatp, SIZE, SIZE)
+    finally:
+        scene.close()
+    write_pass_script(passp, *host_api.pass_script(passes, SIZE, SIZE, dimensions=64))
+    subprocess.run([HOSTSIM, "vcm", flatp, passp, str(SIZE), str(SIZE), "11", "1", "1", outp, hostsim], check=True)
+    validate(util.load_sum(outp, SIZE, SIZE) / np.float32(passes), expected, tolerance)
