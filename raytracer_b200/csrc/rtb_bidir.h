@@ -457,4 +457,257 @@ RTB_HD uint32_t light_trace_path(const SceneView& S, const CameraConnection& cam
     return depth + 1u;
 }
 
+// ---- VCM: VertexConnectionAndMerging.cpp -------------------------------------------------------------------------------
+//
+// The per-vertex arithmetic of the reference's VCM renderer as free functions on plain structs, so that the CPU model
+// (tests/hostsim/hostsim_vcm.h, which pins them statistically against the reference) and a future device version call
+// the same code.  `Occluded(ray, tMax)` is the visibility test (Scene::Traverse_Shadow); Mis() is the identity there.
+
+struct BidirPath
+{
+    Ray      ray;
+    V4       throughput;
+    float    dVC, dVM, dVCM;          // MIS quantities (VertexConnectionAndMerging.h:98-112)
+    uint32_t length;
+    uint32_t lastSpecular, isFiniteLight;
+};
+struct BidirLightVertex { Vertex vx; V4 throughput; float dVC, dVM, dVCM; uint32_t pathLength; };
+struct BidirPhoton { V3 position, direction, throughput; float dVM, dVCM; };
+
+struct BidirPass
+{
+    uint32_t useVertexConnection, useVertexMerging, maxPathLength, iteration;
+    float    radiusVC, radiusVM, mergingNormalization;
+    float    vmWeightVC, vcWeightVC, vmWeightVM, vcWeightVM;     // mMisVertex{Merging,Connection}WeightFactor{VC,VM}
+};
+
+// PreRender(passNumber, film), :80-125.  `pass` carries radiusVC from the previous call (any value for pass 0).
+RTB_HD void bidir_begin_pass(BidirPass& pass, uint32_t passNumber, float lightPathsCount, float initialRadius, float minRadius, float radiusMultiplier)
+{
+    pass.iteration = passNumber;
+    if (passNumber == 0) pass.radiusVC = pass.radiusVM = initialRadius;
+    else
+    {
+        pass.radiusVM = pass.radiusVC;
+        pass.radiusVC *= radiusMultiplier;
+        pass.radiusVC = s_max(pass.radiusVC, minRadius);
+    }
+    pass.mergingNormalization = 1.0f / (s_sqr(pass.radiusVM) * RTB_PI * lightPathsCount);
+    {
+        const float etaVCM = RTB_PI * s_sqr(pass.radiusVC) * lightPathsCount;
+        pass.vmWeightVC = (pass.useVertexMerging && passNumber > 0) ? etaVCM : 0.0f;
+        pass.vcWeightVC = pass.useVertexConnection ? 1.0f / etaVCM : 0.0f;
+    }
+    {
+        const float etaVCM = RTB_PI * s_sqr(pass.radiusVM) * lightPathsCount;
+        pass.vmWeightVM = pass.useVertexMerging ? etaVCM : 0.0f;
+        pass.vcWeightVM = pass.useVertexConnection ? 1.0f / etaVCM : 0.0f;
+    }
+}
+
+RTB_HD bool bidir_is_delta_bsdf(const Vertex& vx) { return vx.bsdf == RTB_BSDF_METAL || vx.bsdf == RTB_BSDF_DIELECTRIC; }      // BSDF::IsDelta
+
+// Material::Evaluate with both pdfs
+RTB_HD V4 bidir_evaluate(const Vertex& vx, const V3& incomingDirWorld, float& pdfW, float& revPdfW)
+{
+    const V3 out = world_to_local(vx, vx.outgoingDirWorld), in = world_to_local(vx, incomingDirWorld);
+    pdfW = 0.0f;
+    const V4 value = bsdf_evaluate(vx, out, in, pdfW);
+    revPdfW = bsdf_pdf(vx, out, in, true);
+    return value;
+}
+
+// the camera path's start, RenderPixel :176-184
+RTB_HD void bidir_begin_camera_path(BidirPath& path, const Ray& primaryRay, const CameraConnection& camera)
+{
+    path.ray = primaryRay;
+    path.throughput = v4(1.0f, 1.0f, 1.0f, 1.0f);
+    path.dVC = 0.0f; path.dVM = 0.0f;
+    path.dVCM = 1.0f / camera_pdf_w(camera.localToWorld, camera.tanHalfFoV, camera.aspectRatio, primaryRay.dir);
+    path.length = 1; path.lastSpecular = 1; path.isFiniteLight = 0;
+}
+
+// GenerateLightSample, :430-485: `pick` chooses the light, (p0, p1, p2, d0, d1) are the emission samples
+template <bool kTex = true>
+RTB_HD bool bidir_generate_light_sample(const SceneView& S, const BidirPass& pass, uint32_t pick, float p0, float p1, float p2, float d0, float d1, BidirPath& outPath)
+{
+    if (S.numLights == 0) return false;
+    const float lightPickProbability = 1.0f / (float)S.numLights;
+    const DLight& light = S.lights[pick % S.numLights];
+    EmitResult emit;
+    const V4 throughput = light_emit<kTex>(S, light, p0, p1, p2, d0, d1, emit);
+    if (almost_zero(throughput)) return false;
+    emit.directPdfA *= lightPickProbability;
+    emit.emissionPdfW *= lightPickProbability;
+    const float emissionInvPdfW = 1.0f / emit.emissionPdfW;
+    emit.position = emit.position + emit.direction * 0.0005f;
+    outPath.ray = make_ray(emit.position, emit.direction);
+    outPath.throughput = throughput * emissionInvPdfW;
+    outPath.length = 1; outPath.lastSpecular = 1;
+    outPath.isFiniteLight = (light.flags & RTB_LIGHT_FLAG_FINITE) != 0 ? 1u : 0u;
+    outPath.dVCM = emit.directPdfA * emissionInvPdfW;
+    if ((light.flags & RTB_LIGHT_FLAG_DELTA) == 0) outPath.dVC = (outPath.isFiniteLight ? emit.cosAtLight : 1.0f) * emissionInvPdfW;
+    else outPath.dVC = 0.0f;
+    outPath.dVM = outPath.dVC * pass.vcWeightVC;
+    return true;
+}
+
+// the MIS update when a path arrives at a surface: camera paths :203-211, light paths :352-364
+RTB_HD void bidir_arrive(BidirPath& path, const Vertex& vx, float hitDistance, bool lightPath)
+{
+    if (!lightPath || path.length > 1 || path.isFiniteLight) path.dVCM *= s_sqr(hitDistance);
+    const float cosTheta = dot3(path.ray.dir, vx.normal);
+    const float invMis = 1.0f / s_abs(cosTheta);
+    path.dVCM *= invMis; path.dVC *= invMis; path.dVM *= invMis;
+}
+
+// AdvancePath, :487-575
+RTB_HD bool bidir_advance_path(const BidirPass& pass, BidirPath& path, const Vertex& vx, float s0, float s1, float s2)
+{
+    BsdfSample bs;
+    const V3 outLocal = world_to_local(vx, vx.outgoingDirWorld);
+    if (!bsdf_sample(vx, outLocal, s0, s1, s2, bs)) return false;
+    const V3 incomingDirWorld = local_to_world(vx, bs.incomingDir);
+    const float cosThetaOut = s_abs(dot3(incomingDirWorld, vx.normal));
+    path.throughput = path.throughput * bs.color;
+    if (almost_zero(path.throughput)) return false;
+    path.ray = make_ray(vx.position, incomingDirWorld);
+    path.ray.origin = path.ray.origin + path.ray.dir * 0.001f;
+    path.length++;
+    if (bs.event & EV_SPECULAR)
+    {
+        path.dVC *= cosThetaOut; path.dVM *= cosThetaOut; path.dVCM = 0.0f;
+        path.lastSpecular = 1;
+    }
+    else
+    {
+        const float bsdfRevPdf = bsdf_pdf(vx, outLocal, neg(world_to_local(vx, incomingDirWorld)), true);
+        const float invBsdfDirPdf = 1.0f / bs.pdf;
+        path.dVC = (cosThetaOut * invBsdfDirPdf) * (path.dVC * bsdfRevPdf + path.dVCM + pass.vmWeightVC);
+        path.dVM = (cosThetaOut * invBsdfDirPdf) * (path.dVM * bsdfRevPdf + path.dVCM * pass.vcWeightVC + 1.0f);
+        path.dVCM = invBsdfDirPdf;
+        path.lastSpecular = 0;
+    }
+    return true;
+}
+
+// EvaluateLight, :577-626 (`hitVertex` null: a global light seen by a ray that left the scene)
+template <bool kTex = true>
+RTB_HD V4 bidir_evaluate_light(const SceneView& S, const BidirPass& pass, const DLight& light, const Vertex* hitVertex, const BidirPath& path)
+{
+    const Ray lightSpaceRay = transform_ray_unsafe(light.invTransform, path.ray);
+    const float cosAtLight = hitVertex ? -dot3(hitVertex->normal, path.ray.dir) : 1.0f;
+    float directPdfA = 0.0f, emissionPdfW = 0.0f;
+    V4 contribution = light_radiance_bidir<kTex>(S, light, lightSpaceRay.dir, cosAtLight, directPdfA, emissionPdfW);
+    if (almost_zero(contribution)) return v4s(0.0f);
+    if (path.length > 1)
+    {
+        const bool useVertexMerging = pass.useVertexMerging && pass.iteration > 0;
+        if (useVertexMerging && !pass.useVertexConnection)
+        {
+            if (!path.lastSpecular) return v4s(0.0f);
+        }
+        else
+        {
+            const float wCamera = directPdfA * path.dVCM + emissionPdfW * path.dVC;
+            contribution = contribution * (1.0f / (1.0f + wCamera));
+        }
+    }
+    return contribution;
+}
+
+// SampleLight, :628-716
+template <bool kTex = true, typename Occluded>
+RTB_HD V4 bidir_sample_light(const SceneView& S, const BidirPass& pass, const DLight& light, const Vertex& vx, const BidirPath& path, float u0, float u1, float u2,
+                             const Occluded& occluded)
+{
+    IlluminateResultBidir ir;
+    const V4 radiance = light_illuminate_bidir<kTex>(S, light, vx, u0, u1, u2, ir);
+    if (almost_zero(radiance)) return v4s(0.0f);
+    float bsdfPdfW, bsdfRevPdfW;
+    const V4 bsdfFactor = bidir_evaluate(vx, neg(ir.directionToLight), bsdfPdfW, bsdfRevPdfW);
+    if (almost_zero(bsdfFactor)) return v4s(0.0f);
+    Ray shadowRay = make_ray(vx.position, ir.directionToLight);
+    shadowRay.origin = shadowRay.origin + shadowRay.dir * 0.0001f;
+    if (occluded(shadowRay, ir.distance * 0.999f)) return v4s(0.0f);
+    const bool isDeltaLight = (light.flags & RTB_LIGHT_FLAG_DELTA) != 0;
+    bsdfPdfW *= isDeltaLight ? 0.0f : 1.0f;
+    const float cosToLight = dot3(vx.normal, ir.directionToLight);
+    if (cosToLight <= FLT_EPSILON) return v4s(0.0f);
+    const float wLight = bsdfPdfW / ir.directPdfW;
+    const float wCamera = (ir.emissionPdfW * cosToLight / (ir.directPdfW * ir.cosAtLight)) * (pass.vmWeightVC + path.dVCM + path.dVC * bsdfRevPdfW);
+    const float misWeight = 1.0f / (wLight + 1.0f + wCamera);
+    return (radiance * bsdfFactor) * (misWeight / ir.directPdfW);
+}
+
+// ConnectVertices, :738-806
+template <typename Occluded>
+RTB_HD V4 bidir_connect_vertices(const BidirPass& pass, const BidirPath& cameraPath, const Vertex& vx, const BidirLightVertex& lv, const Occluded& occluded)
+{
+    V3 lightDir = lv.vx.position - vx.position;
+    const float distanceSqr = sqr_length3(lightDir);
+    const float distance = sqrtf(distanceSqr);
+    lightDir = lightDir / distance;
+    const float cosCameraVertex = dot3(vx.normal, lightDir);
+    const float cosLightVertex = dot3(lv.vx.normal, neg(lightDir));
+    if (cosCameraVertex <= 0.0f || cosLightVertex <= 0.0f) return v4s(0.0f);
+    const float geometryTerm = 1.0f / distanceSqr;
+    float cameraBsdfPdfW, cameraBsdfRevPdfW, lightBsdfPdfW, lightBsdfRevPdfW;
+    const V4 cameraFactor = bidir_evaluate(vx, neg(lightDir), cameraBsdfPdfW, cameraBsdfRevPdfW);
+    if (almost_zero(cameraFactor)) return v4s(0.0f);
+    const V4 lightFactor = bidir_evaluate(lv.vx, lightDir, lightBsdfPdfW, lightBsdfRevPdfW);
+    if (almost_zero(lightFactor)) return v4s(0.0f);
+    Ray shadowRay = make_ray(vx.position, lightDir);
+    shadowRay.origin = shadowRay.origin + shadowRay.dir * 0.0001f;
+    if (occluded(shadowRay, distance * 0.999f)) return v4s(0.0f);
+    const float cameraBsdfPdfA = cameraBsdfPdfW * s_abs(cosLightVertex) / s_sqr(distance);        // PdfWtoA, :23-26
+    const float lightBsdfPdfA = lightBsdfPdfW * s_abs(cosCameraVertex) / s_sqr(distance);
+    const float wLight = cameraBsdfPdfA * (pass.vmWeightVC + lv.dVCM + lv.dVC * lightBsdfRevPdfW);
+    const float wCamera = lightBsdfPdfA * (pass.vmWeightVC + cameraPath.dVCM + cameraPath.dVC * cameraBsdfRevPdfW);
+    const float misWeight = 1.0f / (wLight + 1.0f + wCamera);
+    return (cameraFactor * lightFactor) * (geometryTerm * misWeight);
+}
+
+// one photon of MergeVertices' range query, :822-851 (the caller has checked the distance); adds to `contribution`
+RTB_HD void bidir_merge_photon(const BidirPass& pass, const BidirPath& cameraPath, const Vertex& vx, const BidirPhoton& photon, V4& contribution)
+{
+    const float cosToLight = dot3(vx.normal, photon.direction);
+    if (cosToLight < FLT_EPSILON) return;
+    float cameraBsdfDirPdfW, cameraBsdfRevPdfW;
+    const V4 cameraBsdfFactor = bidir_evaluate(vx, neg(photon.direction), cameraBsdfDirPdfW, cameraBsdfRevPdfW);
+    if (almost_zero(cameraBsdfFactor)) return;
+    const float wLight = photon.dVCM * pass.vcWeightVM + photon.dVM * cameraBsdfDirPdfW;
+    const float wCamera = cameraPath.dVCM * pass.vcWeightVM + cameraPath.dVM * cameraBsdfRevPdfW;
+    const float weight = (1.0f / (wLight + 1.0f + wCamera)) / cosToLight;
+    const V4 t = cameraBsdfFactor * v4(photon.throughput.x, photon.throughput.y, photon.throughput.z, 0.0f);
+    contribution = v4(fma_(t.x, weight, contribution.x), fma_(t.y, weight, contribution.y), fma_(t.z, weight, contribution.z), fma_(t.w, weight, contribution.w));
+}
+
+// ConnectToCamera, :908-970: true with the film position and the value to splat
+template <typename Occluded>
+RTB_HD bool bidir_connect_to_camera(const BidirPass& pass, const CameraConnection& camera, const BidirLightVertex& lv, const Occluded& occluded,
+                                    float& filmX, float& filmY, V3& value)
+{
+    const V3 cameraPos = xyz(camera.localToWorld.r3);
+    V3 dirToCamera = cameraPos - lv.vx.position;
+    const float cameraDistanceSqr = sqr_length3(dirToCamera);
+    const float cameraDistance = sqrtf(cameraDistanceSqr);
+    dirToCamera = dirToCamera / cameraDistance;
+    float bsdfPdfW, bsdfRevPdfW;
+    const V4 cameraFactor = bidir_evaluate(lv.vx, neg(dirToCamera), bsdfPdfW, bsdfRevPdfW);
+    if (almost_zero(cameraFactor)) return false;
+    if (!camera_world_to_film(camera.worldToScreen, lv.vx.position, filmX, filmY)) return false;
+    Ray shadowRay = make_ray(lv.vx.position, dirToCamera);
+    shadowRay.origin = shadowRay.origin + shadowRay.dir * 0.0001f;
+    if (occluded(shadowRay, cameraDistance * 0.999f)) return false;
+    const float cosToCamera = dot3(dirToCamera, lv.vx.normal);
+    if (cosToCamera <= FLT_EPSILON) return false;
+    const float cameraPdfW = camera_pdf_w(camera.localToWorld, camera.tanHalfFoV, camera.aspectRatio, neg(dirToCamera));
+    const float cameraPdfA = cameraPdfW * cosToCamera / cameraDistanceSqr;
+    const float wLight = cameraPdfA * (pass.vmWeightVC + lv.dVCM + lv.dVC * bsdfRevPdfW);
+    const float misWeight = 1.0f / (wLight + 1.0f);
+    value = xyz((cameraFactor * lv.throughput) * (misWeight * cameraPdfA / cosToCamera));
+    return true;
+}
+
 } // namespace rtb

@@ -514,3 +514,15 @@ def test_hostsim_vcm_passes_the_reference_renderer_tests(hostsim, tmp_path, name
     write_pass_script(passp, *host_api.pass_script(passes, SIZE, SIZE, dimensions=64))
     subprocess.run([HOSTSIM, "vcm", flatp, passp, str(SIZE), str(SIZE), "11", "1", "1", outp, hostsim], check=True)
     validate(util.load_sum(outp, SIZE, SIZE) / np.float32(passes), expected, tolerance)
+
+
+def test_bidirectional_functions_compile_for_the_device(tmp_path):
+    """csrc/rtb_bidir.h is written for host and device; the CPU model exercises the host instantiation, this compiles the
+    device one (nvcc, sm_100a, the product's arithmetic flags) inside a kernel that is never launched."""
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "--fmad=false", "-ftz=true", "-prec-div=true", "-prec-sqrt=true",
+                        "-c", os.path.join(HOSTSIM_DIR, "bidir_device_check.cu"), "-o", str(tmp_path / "check.o")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
