@@ -11,6 +11,7 @@ Scenes:
     c1_sphere_area   BASELINE config 1: diffuse sphere + rect area light
     cornell          BASELINE config 2: Cornell box (boxes, 2 spheres, rect area light) - same geometry values as
                      the reference's Data/TestScenes/cornell_box.json so the CPU baseline is comparable
+    caustics         BASELINE config 5 in miniature: rough-glass sphere + glass block under a small area light (VCM tests)
     materials        all nine BSDFs on spheres/boxes, area(sphere) + point + spot + background lights
     mesh_small       ~2.3k-triangle OBJ (two materials from a .mtl) + analytic metal/glass spheres, background +
                      directional light (the two-light pattern of Data/TestScenes/sponza.json:19-31)
@@ -393,6 +394,30 @@ def scene_textures():
     }
 
 
+def scene_caustics():
+    """BASELINE config 5 in miniature: a rough-glass sphere and a glass block between a small area light and a diffuse
+    floor (caustics: the paths the bidirectional renderer exists for), plus a metal sphere."""
+    return {
+        "materials": [
+            mat("floor", "diffuse", (0.8, 0.8, 0.8)),
+            mat("wall", "diffuse", (0.7, 0.3, 0.3)),
+            mat("roughGlass", "roughDielectric", (1.0, 1.0, 1.0), roughness=0.08, IoR=1.5),
+            mat("glass", "dielectric", (0.95, 1.0, 0.95), IoR=1.45),
+            mat("steel", "roughMetal", (0.9, 0.9, 0.9), roughness=0.2),
+        ],
+        "objects": [
+            {"type": "box", "size": [4.0, 0.1, 4.0], "transform": xform((0.0, -1.1, 0.0)), "material": "floor"},
+            {"type": "box", "size": [4.0, 2.0, 0.1], "transform": xform((0.0, 0.9, 3.0)), "material": "wall"},
+            {"type": "sphere", "radius": 0.6, "transform": xform((-0.9, -0.4, 0.2)), "material": "roughGlass"},
+            {"type": "box", "size": [0.35, 0.5, 0.35], "transform": xform((0.9, -0.5, 0.0), (0.0, 35.0, 0.0)), "material": "glass"},
+            {"type": "sphere", "radius": 0.35, "transform": xform((0.1, -0.65, -1.0)), "material": "steel"},
+        ],
+        "lights": [{"type": "area", "color": [60.0, 55.0, 50.0], "transform": xform((0.0, 2.6, 0.0), (90.0, 0.0, 0.0)),
+                    "shape": {"type": "plane", "size": [0.25, 0.25]}}],
+        "camera": {"transform": xform((0.0, 0.9, -5.0), (14.0, 0.0, 0.0)), "fieldOfView": 48.0},
+    }
+
+
 def write_all(out_dir, sponza=False):
     os.makedirs(out_dir, exist_ok=True)
     os.makedirs(os.path.join(out_dir, "MODELS"), exist_ok=True)
@@ -404,6 +429,7 @@ def write_all(out_dir, sponza=False):
     dump("c1_sphere_area", scene_c1())
     dump("cornell", scene_cornell())
     dump("materials", scene_materials())
+    dump("caustics", scene_caustics())
     dof = scene_cornell()
     dof["camera"].update({"enableDOF": True, "aperture": 0.15, "focalPlaneDistance": 3.5})    # circle bokeh, Camera.cpp:100-116
     dump("cornell_dof", dof)

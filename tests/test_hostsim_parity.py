@@ -459,6 +459,7 @@ def test_hostsim_bidirectional_radiance_against_the_live_reference(hostsim, tmp_
     ("cornell", 30, 1, 1, 0.02, 0.999),          # VCM as the reference configures it
     ("materials", 30, 1, 1, 0.02, 0.999),        # all nine BSDFs, six lights of five types
     ("textures", 40, 1, 1, 0.03, 0.995),         # textured materials, environment map
+    ("caustics", 120, 1, 1, 0.04, 0.99),         # BASELINE config 5 in miniature: rough glass + glass block, caustics
     ("cornell", 30, 1, 0, 0.02, 0.999),          # vertex connection only (bidirectional path tracing)
     ("cornell", 150, 0, 1, 0.06, 0.99),          # vertex merging only (photon mapping; noisy at this photon density)
 ])
