@@ -81,6 +81,14 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples), "reasons": reasons}
 
 
+def config_for(world):
+    """`config` of the JSON line: the SAME dict for the product arm and for --impl reference (same workload, same step)."""
+    return {"workload": WORKLOAD,
+            "step": "one pass (1 sample per pixel) of the 1920x1080 frame",
+            "parallelism": "tiles32x32-interleaved x%d" % world,
+            "l2": "per-pass path/ray/shadow queues (>400 MB) exceed L2; the 20 MB BVH+triangles stay L2-resident by design"}
+
+
 def cpu_reference_run(steps, warmup, width, height, threads=0):
     """The reference's own CPU implementation (oracle/_ref/avx: as-shipped -O2 -mavx2 -mfma build, asserts off)."""
     from tests import util
@@ -100,17 +108,17 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    w, h = WIDTH // 2, HEIGHT // 2
+    w, h = WIDTH, HEIGHT          # the product arm's configuration: full 1920x1080 passes of the same scene and camera
     meta = cpu_reference_run(args.steps, args.warmup, w, h)
     if meta is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/avx (the reference built from /root/reference) is not present on this box"}))
         return
     value = meta["mrays_per_s"]
-    sample = "%d passes of %dx%d (quarter-resolution frames of the same scene/camera), %d threads" % (args.steps, w, h, meta["threads"])
+    sample = "%d passes of %dx%d (full frames of the same scene/camera), %d threads" % (args.steps, w, h, meta["threads"])
     print(json.dumps({
         "impl": "reference", "metric": "Mray/s", "value": value, "unit": "Mray/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * meta["seconds"] / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "step": sample},
+        "dtype": "f32", "data": "synthetic", "config": config_for(max(1, args.gpus)),
         "msamples_per_s": meta["msamples_per_s"],
         "cpu_baseline": {"value": value, "unit": "Mray/s", "cores": meta["threads"], "kind": "reference", "sample": sample, "host_cores": cores},
         "e2e": {"value": value, "unit": "Mray/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -312,10 +320,10 @@ def run_gpu(args):
         roofline[other["kernel"].split(" ")[0]] = other
         roofline["k_shade_share_of_pass"] = tm["shadeMs"] / tm["totalMs"] if tm["totalMs"] > 0 else 0.0
         if world == 1 and not args.no_cpu_baseline:
-            meta = cpu_reference_run(2, 1, WIDTH // 2, HEIGHT // 2)
+            meta = cpu_reference_run(4, 1, WIDTH, HEIGHT)
             if meta is not None:
                 cpu_baseline = {"value": meta["mrays_per_s"], "unit": "Mray/s", "cores": meta["threads"], "kind": "reference",
-                                "sample": "2 timed + 1 warm-up passes of %dx%d of the same scene with the reference's AVX2 build on all host threads" % (WIDTH // 2, HEIGHT // 2),
+                                "sample": "4 timed + 1 warm-up passes of %dx%d (full frames) of the same scene with the reference's AVX2 build on all host threads" % (WIDTH, HEIGHT),
                                 "msamples_per_s": meta["msamples_per_s"], "host_cores": os.cpu_count()}
 
     if rank == 0:      # the frames are gathered on rank 0 only
@@ -329,9 +337,8 @@ def run_gpu(args):
             "metric": "Mray/s", "value": value, "unit": "Mray/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * seconds / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "step": "one pass (1 sample per pixel) of the 1920x1080 frame; consecutive passes share wavefronts (rtb_render_passes)", "parallelism": "tiles32x32-interleaved x%d" % world,
-                       "l2": "per-pass path/ray/shadow queues (>400 MB) exceed L2; the 20 MB BVH+triangles stay L2-resident by design",
-                       "scene_load_s": load_s},
+            "config": config_for(world),
+            "scene_load_s": load_s, "batching": "consecutive passes share wavefronts (rtb_render_passes)",
             "msamples_per_s": samples / seconds * 1e-6, "rays_per_sample": rays / max(1.0, samples),
             "gpu_launches": gpu_launches,
             "e2e": {"value": e2e_rays / e2e_s * 1e-6, "unit": "Mray/s", "steps": e2e_steps,

@@ -24,7 +24,8 @@ struct PathState
     Ray      ray;
     V4       throughput;
     Sampler  sampler;
-    uint32_t pixel;
+    uint32_t pixel;         // pixel slot of this shard (the wavefront's film / pass-colour index)
+    uint32_t rasterPixel;   // y * width + x: what shard-invariant decisions (LightSamplingStrategy::Single) key on
     uint32_t passSlot;      // which pass of the batch in flight (0 when passes are rendered one at a time)
     uint32_t depth;
     float    lastPdfW;
@@ -50,6 +51,7 @@ RTB_HD void init_path(const PassParams& P, const uint16_t* blueNoise, uint32_t x
     ps.ray = generate_primary_ray(P, x, y, offX, offY, ps.sampler, blueNoise);
     ps.throughput = v4s(1.0f);      // RayColor::One() = (1, 1, 1, 1)
     ps.pixel = y * P.width + x;
+    ps.rasterPixel = y * P.width + x;
     ps.depth = 0;
     ps.lastPdfW = 1.0f;
     ps.lastSpecular = 1u;
@@ -135,8 +137,9 @@ RTB_HD bool shade_vertex_mis(const SceneView& S, const PassParams& P, PathState&
         if (!P.lightSamplingAll)
         {
             // the reference picks with a per-thread RNG (PathTracerMIS.cpp:136); here: a counter-based hash of the
-            // sampler state, which is reproducible but only statistically equivalent
-            first = (uint32_t)(hash64(((uint64_t)ps.pixel << 32) ^ ((uint64_t)(P.passIndex + ps.passSlot) << 8) ^ ps.depth ^ 0x9E3779B97F4A7C15ULL) % S.numLights);
+            // raster pixel, pass and depth: reproducible, independent of how the frame is sharded, but only statistically
+            // equivalent to the reference
+            first = (uint32_t)(hash64(((uint64_t)ps.rasterPixel << 32) ^ ((uint64_t)(P.passIndex + ps.passSlot) << 8) ^ ps.depth ^ 0x9E3779B97F4A7C15ULL) % S.numLights);
             last = first + 1;
         }
         const bool isLastPathSegment = ps.depth >= P.maxRayDepth;

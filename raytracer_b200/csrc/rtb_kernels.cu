@@ -158,6 +158,7 @@ __device__ __forceinline__ void load_path(const PathBuf& b, uint32_t i, const Wa
     ps.lastMaterial = (m.z >> 20) == 0xFFFu ? RTB_NO_MATERIAL : (m.z >> 20);
     ps.lastPdfW = __uint_as_float(m.w);
     const uint32_t pix = W.pixelList[ps.pixel];
+    ps.rasterPixel = pix;
     const uint32_t x = pix % width, y = pix / width;
     ps.sampler.bnOffset = 4u * (128u * (y & 127u) + (x & 127u));
     ps.sampler.seedBase = ps.passSlot * numSeedDims;
@@ -799,6 +800,7 @@ struct RtbContext
     uint32_t shardSlots = 0;       // padded slot count (equal on every shard)
     uint32_t raysPerPath = 0;
     uint32_t maxBatch = 1;         // passes per wavefront (sized at resize so that a wavefront has a few million paths)
+    uint32_t maxBatchFilm = 1;     // ... as the film size alone would have it (alloc_shadow lowers maxBatch for scenes with many lights)
     DevArray<uint32_t> pixelList;     // this shard
     DevArray<uint32_t> pixelListAll;  // all shards back to back, padded with 0xFFFFFFFF
     std::vector<uint32_t> hostPixelList;   // this shard's list, kept for rtb_set_active_tiles
@@ -913,6 +915,21 @@ static int alloc_shadow(RtbContext* c)
     // shadow-ray storage depends on both the film size and the number of lights sampled per vertex
     const uint32_t rpp = c->numLights > 0 ? c->numLights : 1;
     if (c->numPixels == 0) return RTB_OK;
+    // passes per wavefront: what the film size allows (rtb_resize), cut down when the scene's light count would make the
+    // shadow-ray queues (68 B per path and light) outgrow half of the free device memory
+    c->maxBatch = c->maxBatchFilm;
+    {
+        size_t freeB = 0, totalB = 0;
+        if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess)
+        {
+            size_t held = 0;
+            for (RtbContext::Slot& t : c->slots) held += (t.sr0.count * 4 * sizeof(float4)) + t.rayList.count * sizeof(uint32_t);
+            const size_t budget = (freeB + held) / 2 / c->slots.size();
+            const size_t perPass = (size_t)c->numPixels * rpp * (4 * sizeof(float4) + sizeof(uint32_t));
+            const size_t cap = perPass ? budget / perPass : c->maxBatch;
+            if (cap < c->maxBatch) c->maxBatch = cap < 1 ? 1u : (uint32_t)cap;
+        }
+    }
     const size_t n = (size_t)c->numPixels * c->maxBatch * rpp;
     if (rpp == c->raysPerPath && !c->slots.empty() && c->slots[0].sr0.count == n) return RTB_OK;
     c->raysPerPath = rpp;
@@ -1168,6 +1185,9 @@ int rtb_resize(RtbContext* c, uint32_t width, uint32_t height)
     }
     size_t maxSlots = 0;
     for (const auto& l : lists) if (l.size() > maxSlots) maxSlots = l.size();
+    // the packed path state holds the pixel slot in 26 bits (store_path / load_path)
+    if (maxSlots >= ((size_t)1 << 26)) { c->width = c->height = 0; c->numPixels = 0; }
+    if (maxSlots >= ((size_t)1 << 26)) return fail(RTB_ERR_UNSUPPORTED, "rtb_resize: %zu pixels in one shard; the limit is 2^26 - 1 (use more shards)", maxSlots);
     c->shardSlots = (uint32_t)maxSlots;
     c->numPixels = (uint32_t)lists[c->shardIndex].size();
     std::vector<uint32_t> all((size_t)c->numShards * maxSlots, 0xFFFFFFFFu);
@@ -1184,10 +1204,9 @@ int rtb_resize(RtbContext* c, uint32_t width, uint32_t height)
         uint32_t b = c->numPixels ? (target + c->numPixels - 1) / c->numPixels : 1u;
         if (b < 1u) b = 1u;
         if (b > 16u) b = 16u;
-        if (c->numPixels >= (1u << 26)) b = 1u;
         if (const char* t = getenv("RTB_MAX_BATCH")) b = (uint32_t)atoi(t) > 0 ? (uint32_t)atoi(t) : b;
         if (b > 63u) b = 63u;
-        c->maxBatch = b;
+        c->maxBatch = b; c->maxBatchFilm = b;
     }
     const size_t n = (size_t)c->numPixels * c->maxBatch;
     RTB_CUDA(c->sum.alloc(maxSlots * 3)); RTB_CUDA(c->sum2.alloc(maxSlots * 3));

@@ -105,8 +105,17 @@ struct SceneFile
 
     template <typename T> static bool ReadVec(FILE* f, std::vector<T>& v, size_t n)
     {
+        if (n == 0) { v.clear(); return true; }
+        // a count read from the file must not size an allocation beyond what the file can still deliver
+        const long here = ftell(f);
+        if (here >= 0 && fseek(f, 0, SEEK_END) == 0)
+        {
+            const long size = ftell(f);
+            fseek(f, here, SEEK_SET);
+            if (size >= here && n > (size_t)(size - here) / sizeof(T)) return false;
+        }
         v.resize(n);
-        return n == 0 || fread(v.data(), sizeof(T), n, f) == n;
+        return fread(v.data(), sizeof(T), n, f) == n;
     }
     static bool ReadU32(FILE* f, uint32_t& v) { return fread(&v, 4, 1, f) == 1; }
 

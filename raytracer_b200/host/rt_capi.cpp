@@ -2,6 +2,7 @@
 // users.  Thin: every function forwards to the C++ classes in rt_scene.h / rt_loader.h / rt_viewport.h, which in turn
 // call the extern "C" rtb_* boundary of librtb200.so.
 #include <cstring>
+#include <exception>
 #include <string>
 
 #include "rt_loader.h"
@@ -29,11 +30,18 @@ extern "C" {
 // helpers::LoadScene + Scene::BuildBVH (Demo/Demo.cpp:156-198 SwitchScene)
 void* rtbh_scene_load(const char* jsonPath, const char* dataPath, char* err, size_t errLen)
 {
-    SceneHandle* h = new SceneHandle();
-    std::string msg;
-    if (!rt::helpers::LoadScene(jsonPath, dataPath ? dataPath : "", h->scene, h->camera, msg)) { SetErr(err, errLen, msg); delete h; return nullptr; }
-    if (!h->scene.BuildBVH()) { SetErr(err, errLen, "Scene::BuildBVH failed"); delete h; return nullptr; }
-    return h;
+    // no C++ exception may cross the C boundary (std::bad_alloc / std::length_error from a hostile file)
+    SceneHandle* h = nullptr;
+    try
+    {
+        h = new SceneHandle();
+        std::string msg;
+        if (!rt::helpers::LoadScene(jsonPath, dataPath ? dataPath : "", h->scene, h->camera, msg)) { SetErr(err, errLen, msg); delete h; return nullptr; }
+        if (!h->scene.BuildBVH()) { SetErr(err, errLen, "Scene::BuildBVH failed"); delete h; return nullptr; }
+        return h;
+    }
+    catch (const std::exception& e) { SetErr(err, errLen, std::string("scene load failed: ") + e.what()); delete h; return nullptr; }
+    catch (...) { SetErr(err, errLen, "scene load failed: unknown exception"); delete h; return nullptr; }
 }
 
 void rtbh_scene_free(void* scene) { delete static_cast<SceneHandle*>(scene); }
@@ -41,15 +49,19 @@ void rtbh_scene_free(void* scene) { delete static_cast<SceneHandle*>(scene); }
 // flat RTBS file of the scene + camera at the given aspect (what rtb_upload_scene receives)
 int rtbh_scene_save_flat(void* scene, const char* path, uint32_t width, uint32_t height)
 {
-    SceneHandle* h = static_cast<SceneHandle*>(scene);
-    rtb::SceneFile flat;
-    h->scene.Flatten(flat);
-    rt::Camera cam = h->camera;
-    cam.SetPerspective((float)width / (float)height, cam.mFieldOfView);
-    cam.Describe(flat.camera);
-    cam.DescribeBokeh(flat);
-    flat.fieldOfView = cam.mFieldOfView;
-    return flat.Save(path) ? 0 : -1;
+    try
+    {
+        SceneHandle* h = static_cast<SceneHandle*>(scene);
+        rtb::SceneFile flat;
+        h->scene.Flatten(flat);
+        rt::Camera cam = h->camera;
+        cam.SetPerspective((float)width / (float)height, cam.mFieldOfView);
+        cam.Describe(flat.camera);
+        cam.DescribeBokeh(flat);
+        flat.fieldOfView = cam.mFieldOfView;
+        return flat.Save(path) ? 0 : -1;
+    }
+    catch (...) { return -1; }
 }
 
 void rtbh_scene_stats(void* scene, uint32_t* numObjects, uint32_t* numLights, uint32_t* numTlasNodes)
@@ -62,10 +74,16 @@ void rtbh_scene_stats(void* scene, uint32_t* numObjects, uint32_t* numLights, ui
 
 void* rtbh_viewport_create(void* scene, int deviceId, uint32_t numShards, uint32_t shardIndex, uint32_t flags, const char* blueNoisePath, void* cudaStream, char* err, size_t errLen)
 {
-    rt::ViewportB200* vp = new rt::ViewportB200();
-    if (!vp->Create(deviceId, numShards, shardIndex, flags, blueNoisePath ? blueNoisePath : "", cudaStream)) { SetErr(err, errLen, vp->GetLastError()); delete vp; return nullptr; }
-    if (scene && !vp->SetScene(static_cast<SceneHandle*>(scene)->scene, &static_cast<SceneHandle*>(scene)->camera)) { SetErr(err, errLen, vp->GetLastError()); delete vp; return nullptr; }
-    return vp;
+    rt::ViewportB200* vp = nullptr;
+    try
+    {
+        vp = new rt::ViewportB200();
+        if (!vp->Create(deviceId, numShards, shardIndex, flags, blueNoisePath ? blueNoisePath : "", cudaStream)) { SetErr(err, errLen, vp->GetLastError()); delete vp; return nullptr; }
+        if (scene && !vp->SetScene(static_cast<SceneHandle*>(scene)->scene, &static_cast<SceneHandle*>(scene)->camera)) { SetErr(err, errLen, vp->GetLastError()); delete vp; return nullptr; }
+        return vp;
+    }
+    catch (const std::exception& e) { SetErr(err, errLen, std::string("viewport creation failed: ") + e.what()); delete vp; return nullptr; }
+    catch (...) { SetErr(err, errLen, "viewport creation failed: unknown exception"); delete vp; return nullptr; }
 }
 
 void rtbh_viewport_free(void* vp) { delete static_cast<rt::ViewportB200*>(vp); }

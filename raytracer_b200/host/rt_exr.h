@@ -473,10 +473,10 @@ inline bool Load(const char* path, Image& image, std::string& error)
     {
         uint64_t offset;
         memcpy(&offset, &f[pos + b * 8], 8);
-        if (offset + 8 > f.size()) return false;
+        if (f.size() < 8 || offset > f.size() - 8) return false;          // (subtraction form: offset + 8 would wrap for offsets near 2^64)
         int32_t lineNo, dataLen;
         memcpy(&lineNo, &f[offset], 4); memcpy(&dataLen, &f[offset + 4], 4);
-        if (dataLen < 0 || offset + 8 + (uint64_t)dataLen > f.size()) return false;
+        if (dataLen < 0 || (uint64_t)dataLen > f.size() - 8 - offset) return false;
         const int64_t endLine = std::min<int64_t>((int64_t)lineNo + linesPerBlock, (int64_t)dataWindow[3] + 1);
         const int64_t numLines = endLine - lineNo;
         const int64_t firstLine = (int64_t)lineNo - dataWindow[1];

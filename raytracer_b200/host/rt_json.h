@@ -63,8 +63,13 @@ private:
     void SkipWs() { while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p; }
     bool Fail(const char* m) { if (error.empty()) error = m; return false; }
 
+    int depth = 0;
+    struct DepthGuard { int& d; explicit DepthGuard(int& x) : d(x) { ++d; } ~DepthGuard() { --d; } };
+
     bool ParseValue(Value& v)
     {
+        const DepthGuard guard(depth);
+        if (depth > 256) return Fail("nesting deeper than 256 levels");     // recursion bound for hostile input
         SkipWs();
         if (p >= end) return Fail("unexpected end of input");
         switch (*p)

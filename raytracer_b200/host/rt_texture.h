@@ -325,7 +325,8 @@ private:
         else if (ih.biBitCount == 8 && ih.biClrUsed > 0) format = Format::B8G8R8A8_UNorm_Palette;
         else if (ih.biBitCount == 8 && ih.biClrUsed == 0) format = Format::R8_UNorm;
         else return false;
-        if (ih.biWidth == 0 || ih.biHeight == 0) return false;
+        if (ih.biWidth == 0 || ih.biHeight == 0 || ih.biWidth > 65536u || ih.biHeight > 65536u) return false;
+        if (ih.biClrUsed > 256u) return false;      // an 8-bit index cannot address more; a crafted header must not size the allocation
         const uint32_t stride = (ih.biWidth * BitsPerPixel(format) / 8 + 3u) & ~3u;
         if (!Init(ih.biWidth, ih.biHeight, format, stride, false)) return false;
         mPalette.assign((size_t)ih.biClrUsed * 4u, 0);

@@ -1,6 +1,8 @@
 """BASELINE.json's full-size configuration (sponza-class scene, 1920x1080, PathTracerMIS depth 8, All lights) on the GPU,
-checked through size-independent properties: determinism, batched == pass-by-pass, sharded == unsharded, and the
-live reference on a crop-free lower resolution of the same scene (the CPU oracle needs minutes at 1080p)."""
+checked through size-independent properties (determinism, batched == pass-by-pass, sharded == unsharded) AND bit for
+bit against the live reference at the sizes BASELINE.json states: config 1 (sphere + area light, 256x256 x 16 spp),
+config 2 (Cornell box, 512x512 x 256 spp, depth 8) and config 3 (the bench scene at 1920x1080; two passes, the CPU
+reference needs well under a second per 1080p pass per 16 cores)."""
 import os
 
 import numpy as np
@@ -98,3 +100,56 @@ def test_full_size_scene_against_the_live_reference(scene, tmp_path):
         util.assert_bit_identical(ctx.read_sum(), util.load_sum(sump, w, h), "bench scene vs live reference")
         c = ctx.counters()
     assert (c["numRays"], c["numShadowRays"], c["numShadowRaysHit"]) == (meta["numRays"], meta["numShadowRays"], meta["numShadowRaysHit"])
+
+
+def live_reference_case(tmp_path, scene_json, data_dir, w, h, passes, dims, host_scene=None, seed="12345", timeout=3000):
+    """Render `passes` passes with the real reference (exact-math build) on this box's CPU and with the CUDA path from the
+    reference's own pass script (Halton seed vectors + AA offsets); return both films and counter sets."""
+    sump, sum2p, passp = str(tmp_path / "o.sum"), str(tmp_path / "o.sum2"), str(tmp_path / "o.passes")
+    meta = util.run_rtref(["render", "--scene", scene_json, "--data", data_dir, "--width", w, "--height", h, "--passes", passes, "--dims", dims,
+                           "--depth", bench.MAX_DEPTH, "--strategy", "all", "--dump-sum", sump, "--dump-sum2", sum2p, "--dump-passes", passp],
+                          seed=seed, timeout=timeout)
+    flat = str(tmp_path / "host.rtb")
+    own = host_scene is None
+    if own:
+        host_scene = host_api.Scene(scene_json, data_dir)
+    try:
+        host_scene.save_flat(flat, w, h)                  # the HOST model's flattening, not the oracle's
+    finally:
+        if own:
+            host_scene.close()
+    sf = capi.SceneFile(flat)
+    ps = capi.PassScript(passp)
+    with capi.Context(device=0) as ctx:
+        ctx.upload_scene(sf)
+        ctx.resize(w, h)
+        ctx.render_passes(capi.camera_for(sf, w, h), ps.seeds[:passes], ps.offsets[:passes], 0)
+        got, got2, c = ctx.read_sum(), ctx.read_sum(1), ctx.counters()
+    util.assert_bit_identical(got, util.load_sum(sump, w, h), "sum vs live reference")
+    util.assert_bit_identical(got2, util.load_sum(sum2p, w, h), "secondary sum vs live reference")
+    for k in ("numRays", "numShadowRays", "numShadowRaysHit", "numPrimaryRays"):
+        assert c[k] == meta[k], "%s: %d vs reference %d" % (k, c[k], meta[k])
+    assert c["numPrimaryRays"] == w * h * passes
+    return meta
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="prebuilt oracle/_ref/exact did not travel to this box")
+def test_config1_sphere_area_light_256x256_16spp_against_the_live_reference(tmp_path):
+    """BASELINE config 1 at its stated size: single sphere + area light, 256x256, 16 spp, PathTracerMIS, fixed seed."""
+    scn = os.path.join(util.GOLDEN, "scenes")
+    live_reference_case(tmp_path, os.path.join(scn, "c1_sphere_area.json"), scn + "/", 256, 256, 16, 128)
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="prebuilt oracle/_ref/exact did not travel to this box")
+def test_config2_cornell_box_512x512_256spp_against_the_live_reference(tmp_path):
+    """BASELINE config 2 at its stated size: Cornell box, 512x512, 256 spp, max depth 8 (67 M samples; the film after
+    256 passes accumulated in pass order must equal the reference's bit for bit)."""
+    scn = os.path.join(util.GOLDEN, "scenes")
+    live_reference_case(tmp_path, os.path.join(scn, "cornell.json"), scn + "/", 512, 512, 256, 128)
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="prebuilt oracle/_ref/exact did not travel to this box")
+def test_config3_bench_scene_1920x1080_against_the_live_reference(scene, tmp_path):
+    """BASELINE config 3 at its stated resolution: the 256 768-triangle bench scene, 1920x1080, depth 8, both lights
+    sampled per vertex; two passes (4.1 M samples, ~33 M rays) against the reference on this box's CPU."""
+    live_reference_case(tmp_path, bench.ensure_scene(), bench.SCENE_DIR + "/", bench.WIDTH, bench.HEIGHT, 2, bench.DIMS, host_scene=scene, seed="4242")
