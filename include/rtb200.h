@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RTB_API_VERSION 2   /* 2: textures (RtbTexture, RtbMaterialTextures, RtbSceneDesc::textures ...) */
+#define RTB_API_VERSION 3   /* 2: textures (RtbTexture, RtbMaterialTextures, RtbSceneDesc::textures ...)  3: RTB_RENDERER_VCM, rtb_set_vcm_params, rtb_vcm_* */
 
 typedef enum RtbStatus
 {
@@ -231,7 +231,8 @@ typedef enum RtbRenderer
 {
     RTB_RENDERER_PATH_TRACER     = 0,  /* "Path Tracer"     Core/Rendering/PathTracer.cpp    */
     RTB_RENDERER_PATH_TRACER_MIS = 1,  /* "Path Tracer MIS" Core/Rendering/PathTracerMIS.cpp */
-    RTB_RENDERER_DEBUG           = 2   /* "Debug"           Core/Rendering/DebugRenderer.cpp */
+    RTB_RENDERER_DEBUG           = 2,  /* "Debug"           Core/Rendering/DebugRenderer.cpp */
+    RTB_RENDERER_VCM             = 3   /* "VCM"             Core/Rendering/VertexConnectionAndMerging.cpp (rtb_set_vcm_params) */
 } RtbRenderer;
 
 /* DebugRenderingMode, Core/Rendering/DebugRenderer.h:7-33 (same numeric values) */
@@ -450,6 +451,34 @@ typedef struct RtbPassTimings
     uint64_t traverseRays, shadowRays;
 } RtbPassTimings;
 int  rtb_set_profiling(RtbContext* ctx, int enable);
+
+/* ---- "VCM": vertex connection and merging (Core/Rendering/VertexConnectionAndMerging.h:31-58) -------------------------
+ * The public members of the reference's renderer object; defaults as its constructor sets them
+ * (VertexConnectionAndMerging.cpp:47-62).  Passes with renderer = RTB_RENDERER_VCM are rendered one at a time: a pass traces
+ * one light sub-path and one camera path per pixel, merges with the photons of the PREVIOUS pass (passIndex - 1 of the
+ * same frame) and splats the light paths' camera connections onto the film with float atomics.  The camera path draws
+ * from the pass' Halton seed like the path tracers; the light path draws from a generator seeded with lightPathSeed, the
+ * pixel and the pass (the reference uses its per-thread generators there): the image is reproducible here, comparable
+ * with the reference statistically.  maxRayDepth / minRussianRouletteDepth / lightSamplingStrategy of the pass are not
+ * used by this renderer (nor by the reference's). */
+typedef struct RtbVcmParams
+{
+    uint32_t useVertexConnection;      /* mUseVertexConnection */
+    uint32_t useVertexMerging;         /* mUseVertexMerging */
+    uint32_t maxPathLength;            /* mMaxPathLength (1 .. 32) */
+    float    initialMergingRadius;     /* mInitialMergingRadius */
+    float    minMergingRadius;         /* mMinMergingRadius */
+    float    mergingRadiusMultiplier;  /* mMergingRadiusMultiplier (0 < m <= 1) */
+    uint64_t lightPathSeed;
+} RtbVcmParams;
+int  rtb_set_vcm_params(RtbContext* ctx, const RtbVcmParams* params);
+/* Sharded contexts (numShards > 1): a light path's camera connection can land on any pixel, so every shard collects the
+ * splats of ITS light paths in two raster buffers (width * height * 3 floats each: sum, secondary sum) until the frame is
+ * read.  The caller sums them over the shards (one all-reduce per frame) in place and calls rtb_vcm_fold_splats, which adds
+ * this shard's pixels to its film and clears the buffers.  Single-shard contexts fold after every pass by themselves.
+ * Vertex merging needs every shard's photons: not built - a sharded context refuses useVertexMerging. */
+int  rtb_vcm_splat_buffers(RtbContext* ctx, void** outSplat, void** outSplat2, uint64_t* outNumFloats);
+int  rtb_vcm_fold_splats(RtbContext* ctx);
 int  rtb_get_pass_timings(RtbContext* ctx, RtbPassTimings* out);
 
 #ifdef __cplusplus

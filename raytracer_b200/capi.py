@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("RTB200_LIB", os.path.join(_HERE, "librtb200.so"))   #
 
 RTB_INVALID_OBJECT = 0xFFFFFFFF
 RTB_LIGHT_OBJECT = 0xFFFFFFFE
-RTB_RENDERER_PATH_TRACER, RTB_RENDERER_PATH_TRACER_MIS, RTB_RENDERER_DEBUG = 0, 1, 2
+RTB_RENDERER_PATH_TRACER, RTB_RENDERER_PATH_TRACER_MIS, RTB_RENDERER_DEBUG, RTB_RENDERER_VCM = 0, 1, 2, 3
 RTB_TRACE_CLOSEST, RTB_TRACE_SHADOW = 0, 1
 RTB_LIGHT_SAMPLING_SINGLE, RTB_LIGHT_SAMPLING_ALL = 0, 1
 RTB_FLAG_COUNT_TESTS = 1
@@ -120,6 +120,12 @@ def postprocess_desc(num_passes, color_filter=(1.0, 1.0, 1.0), exposure=0.0, con
     return d
 
 
+class RtbVcmParams(C.Structure):
+    _fields_ = [("useVertexConnection", C.c_uint32), ("useVertexMerging", C.c_uint32), ("maxPathLength", C.c_uint32),
+                ("initialMergingRadius", C.c_float), ("minMergingRadius", C.c_float), ("mergingRadiusMultiplier", C.c_float),
+                ("lightPathSeed", C.c_uint64)]
+
+
 class RtbCounters(C.Structure):
     _fields_ = [("numRays", C.c_uint64), ("numShadowRays", C.c_uint64), ("numShadowRaysHit", C.c_uint64),
                 ("numPrimaryRays", C.c_uint64), ("numRayBoxTests", C.c_uint64), ("numRayTriangleTests", C.c_uint64),
@@ -147,6 +153,7 @@ EXPORTED_SYMBOLS = [
     "rtb_last_error", "rtb_api_version", "rtb_create", "rtb_destroy", "rtb_upload_scene", "rtb_set_blue_noise",
     "rtb_resize", "rtb_reset", "rtb_render_pass", "rtb_render_passes", "rtb_synchronize", "rtb_join", "rtb_read_sum", "rtb_film_device_buffer", "rtb_film_snapshots",
     "rtb_unshard_film", "rtb_read_sum_async", "rtb_unshard_film_async", "rtb_host_alloc", "rtb_host_free", "rtb_get_counters", "rtb_trace_batch", "rtb_trace_batch_device", "rtb_texture_batch", "rtb_sample_batch",
+    "rtb_set_vcm_params", "rtb_vcm_splat_buffers", "rtb_vcm_fold_splats",
     "rtb_primary_rays", "rtb_set_profiling", "rtb_get_pass_timings", "rtb_read_front", "rtb_block_errors", "rtb_set_active_tiles",
 ]
 
@@ -200,6 +207,9 @@ def load_library(path=None):
     lib.rtb_sample_batch.argtypes = [C.c_void_p, C.POINTER(RtbPassDesc), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
     lib.rtb_primary_rays.argtypes = [C.c_void_p, C.POINTER(RtbPassDesc), C.c_void_p]
     lib.rtb_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    lib.rtb_set_vcm_params.argtypes = [C.c_void_p, C.POINTER(RtbVcmParams)]
+    lib.rtb_vcm_splat_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.rtb_vcm_fold_splats.argtypes = [C.c_void_p]
     lib.rtb_get_pass_timings.argtypes = [C.c_void_p, C.POINTER(RtbPassTimings)]
     if path is None:
         _lib = lib
@@ -354,6 +364,11 @@ def load_blue_noise(path=None):
 class Context:
     """Thin RAII wrapper around RtbContext*."""
 
+    def set_vcm_params(self, connection=True, merging=True, max_path_length=10, initial_radius=0.02, min_radius=0.02, radius_multiplier=1.0, seed=0x5EED):
+        """VertexConnectionAndMerging's public members (defaults: its constructor's)."""
+        p = RtbVcmParams(1 if connection else 0, 1 if merging else 0, max_path_length, initial_radius, min_radius, radius_multiplier, seed)
+        _check(self.lib, self.lib.rtb_set_vcm_params(self.h, C.byref(p)))
+
     def __init__(self, device=0, flags=0, num_shards=1, shard_index=0, tile_size=0, stream=None, blue_noise=True):
         self.lib = load_library()
         d = RtbCreateDesc(device, flags, num_shards, shard_index, tile_size, stream)
@@ -474,6 +489,20 @@ class Context:
         out = np.empty((self.height, self.width, 3), dtype=np.float32)
         _check(self.lib, self.lib.rtb_unshard_film(self.h, gathered_device_ptr, out.ctypes.data))
         return out
+
+    def vcm_splat_buffers(self):
+        """rtb_vcm_splat_buffers as two torch tensors (views of the device buffers) for the caller's all-reduce."""
+        import torch
+        a, b, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        _check(self.lib, self.lib.rtb_vcm_splat_buffers(self.h, C.byref(a), C.byref(b), C.byref(n)))
+
+        class _View:
+            def __init__(self, ptr, count):
+                self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+        return torch.as_tensor(_View(a.value, n.value), device="cuda"), torch.as_tensor(_View(b.value, n.value), device="cuda")
+
+    def vcm_fold_splats(self):
+        _check(self.lib, self.lib.rtb_vcm_fold_splats(self.h))
 
     def counters(self):
         c = RtbCounters()

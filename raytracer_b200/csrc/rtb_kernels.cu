@@ -74,6 +74,8 @@ struct Totals
     unsigned long long numRays, numShadowRays, numShadowRaysHit, numBoxTests, numTriTests, numShadowBoxTests, numShadowTriTests;
 };
 
+#include "rtb_vcm.cuh"
+
 #define RTB_ALL_ACTIVE 0xFFFFFFFFu
 
 struct Wavefront
@@ -422,6 +424,178 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
     }
 }
 
+
+// ---- any-hit rays on the 8-wide tree: persistent warps, top of the tree staged in shared memory ---------------------------
+// k_shadow above gives every ray a thread and lets it run the two-level walk on its own.  k_shadow_wide is the kernel
+// built around rtb_wide.h:
+//   * persistent CTAs (RTB_SW_MINBLOCKS per SM); a warp draws 32 rays at a time from the ray list with one atomic
+//     (W.ctl->shadowCursor) until the list is empty;
+//   * the first `hotCount` nodes of the scene's largest 8-wide tree (breadth-first order = the top levels every ray
+//     goes through) are copied into shared memory once per CTA with ONE bulk copy (cp.async.bulk, completion on an
+//     mbarrier) that overlaps the first top-level steps; nodes below come from L1 / L2 with 256-bit loads;
+//   * the walk of a warp's 32 rays alternates between two phases.  Top phase: every lane advances its exact top-level
+//     walk (rtb_trace.h ShadowWalk: top-level BVH, analytic shapes, meshes without a wide tree) until it is finished or
+//     stands in front of a mesh that has a wide tree.  Wide phase: all lanes that stand in front of a mesh walk it
+//     TOGETHER - eight child tests per node with no branch in between - until each has its answer.  With one
+//     dominant mesh (the bench) that is one wide phase per ray batch.
+#ifndef RTB_SW_THREADS
+#define RTB_SW_THREADS 384
+#endif
+#ifndef RTB_SW_MINBLOCKS
+#define RTB_SW_MINBLOCKS 2
+#endif
+#ifndef RTB_SW_REFILL
+#define RTB_SW_REFILL 0     // the wide phase is left for a refill when fewer than this many lanes of the warp are still inside a mesh
+#endif
+
+struct WideFetchHot
+{
+    const WNode* hotNodes;     // the tree whose first hotCount nodes are staged
+    uint32_t hotCount;
+    uint32_t hotShared;        // shared-space byte address of the staged copy
+    __device__ __forceinline__ void operator()(const WNode* nodes, uint32_t index, uint32_t* n) const
+    {
+        if (nodes == hotNodes && index < hotCount)
+        {
+            const uint32_t a = hotShared + index * 96u;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(n[0]), "=r"(n[1]), "=r"(n[2]), "=r"(n[3]) : "r"(a));
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(n[4]), "=r"(n[5]), "=r"(n[6]), "=r"(n[7]) : "r"(a));
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+32];" : "=r"(n[8]), "=r"(n[9]), "=r"(n[10]), "=r"(n[11]) : "r"(a));
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+48];" : "=r"(n[12]), "=r"(n[13]), "=r"(n[14]), "=r"(n[15]) : "r"(a));
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+64];" : "=r"(n[16]), "=r"(n[17]), "=r"(n[18]), "=r"(n[19]) : "r"(a));
+        }
+        else WideFetchGlobal()(nodes, index, n);
+    }
+};
+
+template <bool kCount>
+__global__ void __launch_bounds__(RTB_SW_THREADS, RTB_SW_MINBLOCKS) k_shadow_wide(const __grid_constant__ SceneView S, const __grid_constant__ Wavefront W, uint32_t depth,
+                                                                                  const WNode* __restrict__ hotNodes, uint32_t hotCount, uint32_t panelBytes)
+{
+    extern __shared__ __align__(128) uint8_t smemRaw[];
+    // [0, 8): mbarrier   [128, 128 + hotCount * 96): staged nodes   then one stack panel (rtb_trace.h layout) per 128 threads
+    const uint32_t smemBase = (uint32_t)__cvta_generic_to_shared(smemRaw);
+    const uint32_t hotShared = smemBase + 128u;
+    const uint32_t hotBytes = hotCount * (uint32_t)sizeof(WNode);
+    const uint32_t stackBase = hotShared + ((hotBytes + 127u) & ~127u);
+    const uint32_t count = W.ctl->tailTaken ? 0u : W.ctl->shadowRayCount[depth];
+    if (hotCount)
+    {
+        if (threadIdx.x == 0)
+        {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smemBase));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smemBase), "r"(hotBytes) : "memory");
+            const char* src = reinterpret_cast<const char*>(hotNodes);
+            for (uint32_t off = 0; off < hotBytes; off += 32768u)
+            {
+                const uint32_t chunk = hotBytes - off < 32768u ? hotBytes - off : 32768u;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(hotShared + off), "l"(src + off), "r"(chunk), "r"(smemBase) : "memory");
+            }
+        }
+        __syncthreads();       // the barrier is initialised before anyone waits on it
+    }
+    bool hotReady = hotCount == 0u;
+    WideFetchHot fetch; fetch.hotNodes = hotNodes; fetch.hotCount = hotCount; fetch.hotShared = hotShared;
+
+    const uint32_t lane = threadIdx.x & 31u;
+    SharedStack sstack = stackBase + (threadIdx.x >> 7) * panelBytes + (threadIdx.x & 127u) * 4u;
+    asm volatile("" : "+r"(sstack));
+    unsigned long long visibleLocal = 0;
+    TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
+    uint32_t stack[1];
+    enum { kIdle = 0, kTop = 1, kWide = 2 };
+    int state = kIdle;
+    bool exhausted = false;
+    uint32_t j = 0, wideTop = 0;
+    ShadowWalk walk;
+    WideWalk wide;
+    WideView wv; wv.nodes = nullptr; wv.tris = nullptr; wv.refNodes = nullptr; wv.maxAbs = 0.0f;
+    for (;;)
+    {
+        // ---- idle lanes draw new rays (one atomic per warp) ------------------------------------------------------------
+        const uint32_t idle = __ballot_sync(0xFFFFFFFFu, state == kIdle);
+        if (idle != 0u && !exhausted)
+        {
+            const uint32_t want = __popc(idle);
+            uint32_t k0 = 0;
+            if (lane == 0) k0 = atomicAdd(&W.ctl->shadowCursor[depth], want);
+            k0 = __shfl_sync(0xFFFFFFFFu, k0, 0);
+            exhausted = k0 + want >= count;
+            const uint32_t k = k0 + __popc(idle & ((1u << lane) - 1u));
+            if (state == kIdle && k < count)
+            {
+                j = W.rayList[k];
+                const RayInShadowQueue src = { W, j };
+                if (walk.begin(S, stack, src, W.sr0[j].w, sstack)) state = kTop;
+                else visibleLocal++;
+            }
+        }
+        if (__ballot_sync(0xFFFFFFFFu, state != kIdle) == 0u)
+        {
+            if (exhausted) break;
+            continue;
+        }
+        const RayInShadowQueue src = { W, j };
+        // ---- top phase: the exact two-level walk up to the next mesh that has a wide tree ---------------------------------------
+        while (state == kTop)
+        {
+            const int r = walk.template step<kCount, RayInShadowQueue, true>(S, stack, src, &cnt, sstack);
+            if (r == ShadowWalk::kEnterWide)
+            {
+                state = kWide;
+                const DMesh& mesh = S.meshes[walk.wideMesh];
+                wv.nodes = mesh.wideNodes; wv.tris = mesh.wideTris; wv.refNodes = mesh.nodes;
+                wide.begin(walk.ray, mesh.wideMaxAbs);
+                wideTop = walk.stackSize;
+            }
+            else if (r != ShadowWalk::kContinue)
+            {
+                state = kIdle;
+                // SampleLight returns RayColor::Zero() for an occluded light (PathTracerMIS.cpp:92-96)
+                if (r == ShadowWalk::kOccluded) { W.sr1[j].w = 0.0f; W.sr2[j].w = 0.0f; W.sr3[j].w = 0.0f; }
+                else visibleLocal++;
+            }
+        }
+        if (!hotReady)
+        {
+            // the staged nodes have landed (phase 0 of the barrier completes when all bytes arrived)
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smemBase) : "memory");
+            hotReady = true;
+        }
+        // ---- wide phase: one node visit per iteration for every lane that is inside a mesh; it ends when those lanes are
+        //      done, or - while there are rays left to draw - when so few are left inside that a refill pays ---------------------------
+        for (;;)
+        {
+            if (state == kWide)
+            {
+                WideStackAbove ws; ws.stack = stack; ws.sstack = sstack; ws.floor = walk.stackSize; ws.top = wideTop;
+                const int r = wide.template step<kCount>(wv, walk.ray, walk.maxDistance, ws, &cnt, fetch);
+                wideTop = ws.top;
+                if (r == WideWalk::kOccluded)
+                {
+                    state = kIdle;
+                    W.sr1[j].w = 0.0f; W.sr2[j].w = 0.0f; W.sr3[j].w = 0.0f;
+                }
+                else if (r == WideWalk::kMissed) { walk.leave_wide(S, src); state = kTop; }
+            }
+            const uint32_t inside = __ballot_sync(0xFFFFFFFFu, state == kWide);
+            if (inside == 0u) break;
+            if (!exhausted && __popc(inside) < RTB_SW_REFILL) break;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) visibleLocal += __shfl_down_sync(0xFFFFFFFFu, visibleLocal, o);
+    if (lane == 0 && visibleLocal) atomicAdd(&W.tot->numShadowRaysHit, visibleLocal);
+    if (kCount)
+    {
+        atomicAdd(&W.tot->numShadowBoxTests, (unsigned long long)cnt.boxTests);
+        atomicAdd(&W.tot->numShadowTriTests, (unsigned long long)cnt.triTests);
+    }
+}
+
 // ---- the tail of a wavefront ---------------------------------------------------------------------------------------------
 // Once only a few ten thousand paths are left, every further bounce costs four launches whose run time is one warp's
 // latency, not throughput (a 1/8 shard rendered pass by pass spends more than half of its 2.2 ms there).  k_tail is
@@ -452,8 +626,11 @@ struct TailSink
     }
 };
 
+#ifndef RTB_TAIL_MINBLOCKS
+#define RTB_TAIL_MINBLOCKS 4       // 2 compiles it free of spills (255 registers)
+#endif
 template <bool kTex>
-__global__ void __launch_bounds__(128, 4) k_tail(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const __grid_constant__ Wavefront W, uint32_t depth)
+__global__ void __launch_bounds__(128, RTB_TAIL_MINBLOCKS) k_tail(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const __grid_constant__ Wavefront W, uint32_t depth)
 {
     // tailTaken = 1 + the depth at which the tail took over.  CTAs of THIS launch may already see the value written by
     // its first CTA (a grid larger than what is resident starts late CTAs after early ones have finished): they must
@@ -761,6 +938,8 @@ struct DeviceMesh
     DevArray<DVertexIndices> indices;
     DevArray<DVertexShading> shading;
     DevArray<uint32_t> materialIds;
+    DevArray<WNode> wideNodes;     // any-hit tree (rtb_wide.h), empty if the mesh keeps the binary walk
+    DevArray<DTri> wideTris;
 };
 
 struct RtbContext
@@ -850,6 +1029,12 @@ struct RtbContext
     bool slotsNeedMain = true;            // the main stream holds work the slots must wait for (reset / resize / upload)
     bool slotsOwnStreams = false;         // false: one slot on the main stream (default), true: RTB_SLOTS > 1
     bool serializeSlots = false, profileDepths = false;      // development aids, read from the environment at rtb_create
+    bool noWide = false;                  // RTB_NO_WIDE: any-hit rays walk the binary tree (A/B against rtb_wide.h)
+    bool wideKernel = true;               // k_shadow_wide (persistent warps, staged tree top) when the scene has an 8-wide tree; RTB_SHADOW_KERNEL=simple: k_shadow
+    const WNode* hotNodes = nullptr;      // the scene's largest 8-wide tree ...
+    uint32_t hotTotal = 0;                // ... and its node count
+    int hotOverride = 0;                  // RTB_HOT_NODES: nodes of the tree top staged in shared memory (-1: as many as fit).  Measured on the bench
+                                          // (k_shadow_wide per 8 passes): none 40.1 ms, 256 nodes 43.1, as many as fit (~1000) 43.2 - the copy costs L1
     DevArray<float> snapshots;            // rtb_film_snapshots: snapshotCapacity x shardSlots x 3 floats
     uint32_t snapshotCapacity = 0;
     DevArray<Totals> totals;
@@ -857,6 +1042,20 @@ struct RtbContext
 
     RtbCounters counters;
     uint32_t passesSinceReset = 0;
+
+    // "VCM" renderer (rtb_vcm.cuh): buffers are allocated by the first VCM pass after a resize / parameter change
+    struct Vcm
+    {
+        RtbVcmParams params = { 1u, 1u, 10u, 0.02f, 0.02f, 1.0f, 0x5EEDull };      // VertexConnectionAndMerging.cpp:47-62
+        DevArray<float4> lightVertices, photons[2];
+        DevArray<uint32_t> lightVertexCount, photonCount, cellStart, cellCursor, gridIndices, tileTotals;
+        DevArray<float> splat, splat2;
+        uint32_t hashSize = 0, photonCapacity = 0, vertexStride = 0;
+        uint32_t current = 0;             // photons[current] holds the previous pass' photons
+        uint32_t lastPassIndex = 0xFFFFFFFFu;   // passIndex of the pass that wrote them
+        bool allocated = false;
+        bool splatsPending = false;
+    } vcm;
 
     // CTAs per SM of the grid-stride kernels.  8 are resident; launching 16x as many lets the hardware scheduler
     // even out the very uneven per-warp traversal times (measured: 8 -> 71.1, 32 -> 69.3, 128 -> 67.8, 1024 -> 70.0 ms / 8 passes)
@@ -871,7 +1070,7 @@ struct RtbContext
 static void free_scene(RtbContext* c)
 {
     c->tlas.release(); c->objTrace.release(); c->objShade.release(); c->shapes.release();
-    for (DeviceMesh& m : c->meshes) { m.nodes.release(); m.tris.release(); m.indices.release(); m.shading.release(); m.materialIds.release(); }
+    for (DeviceMesh& m : c->meshes) { m.nodes.release(); m.tris.release(); m.indices.release(); m.shading.release(); m.materialIds.release(); m.wideNodes.release(); m.wideTris.release(); }
     c->meshes.clear();
     c->meshViews.release(); c->materials.release(); c->lights.release(); c->globalLights.release();
     c->textures.release(); c->materialTextures.release(); c->bokehCdf.release(); c->bokehWidth = c->bokehHeight = 0;
@@ -880,8 +1079,17 @@ static void free_scene(RtbContext* c)
     c->hasScene = false;
 }
 
+static void free_vcm(RtbContext* c)
+{
+    RtbContext::Vcm& v = c->vcm;
+    v.lightVertices.release(); v.photons[0].release(); v.photons[1].release(); v.lightVertexCount.release(); v.photonCount.release();
+    v.cellStart.release(); v.cellCursor.release(); v.gridIndices.release(); v.tileTotals.release(); v.splat.release(); v.splat2.release();
+    v.allocated = false; v.splatsPending = false; v.lastPassIndex = 0xFFFFFFFFu;
+}
+
 static void free_film(RtbContext* c)
 {
+    free_vcm(c);
     c->pixelList.release(); c->pixelListAll.release(); c->sum.release(); c->sum2.release(); c->raster.release(); c->activeList.release(); c->hasActiveList = false; c->frozen.release(); c->hostFrozen.clear(); c->raster2.release(); c->pixelError.release(); c->rowError.release(); c->blockRows.release(); c->front.release(); c->blurred.release(); c->blurScratch.release();
     for (int i = 0; i < RTB_SNAP_RING; ++i) c->rasterAsync[i].release();
     c->snapshots.release(); c->snapshotCapacity = 0;
@@ -1018,7 +1226,19 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
         cudaFuncSetAttribute(k_trace_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
         cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
         cudaFuncSetAttribute(k_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+        cudaFuncSetAttribute(k_shadow_wide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        cudaFuncSetAttribute(k_shadow_wide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (const char* t = getenv("RTB_TAIL_PATHS")) c->tailThreshold = (uint32_t)strtoul(t, nullptr, 10);
+    }
+    // RTB_CARVEOUT=n (development aid): pin the L1 / shared-memory split of EVERY kernel of this library to n percent
+    // shared memory, so that kernels of different streams never ask the SM for different splits
+    if (const char* t = getenv("RTB_CARVEOUT"))
+    {
+        const int pct = atoi(t);
+        const void* all[] = { (const void*)k_raygen, (const void*)k_traverse<false>, (const void*)k_traverse<true>, (const void*)k_shade<false>, (const void*)k_shade<true>,
+                              (const void*)k_shadow<false>, (const void*)k_shadow<true>, (const void*)k_tail<false>, (const void*)k_tail<true>, (const void*)k_resolve,
+                              (const void*)k_film, (const void*)k_unshard, (const void*)k_front };
+        for (const void* f : all) cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     }
     // wavefront slots (see RtbContext::Slot).  The default is ONE slot that runs on the main stream, i.e. strictly one
     // kernel at a time: with several slots (RTB_SLOTS=4: +3 % device-resident, +9-12 % end to end on the bench) the
@@ -1027,8 +1247,17 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
     int numSlots = 1;
     if (const char* t = getenv("RTB_SLOTS")) numSlots = atoi(t) >= 1 && atoi(t) <= 16 ? atoi(t) : numSlots;
     c->slotsOwnStreams = numSlots > 1;
+    // Round-2 bisect of the overlap problem (gpurun_out/r2b): with k_tail out of the picture every
+    // renderer is bit-identical under overlapping wavefronts (MIS, PT, debug; RTB_SLOTS=2 and 4); with it, a few hundred
+    // paths per frame differ.  k_tail is the one kernel that keeps spilled state (the world-space ray) alive across
+    // whole traversals while launches of other streams come and go on its SM.  Slots and the tail kernel solve the same
+    // problem (small wavefronts), so several slots simply run without it.
+    if (c->slotsOwnStreams && !getenv("RTB_TAIL_WITH_SLOTS")) c->tailThreshold = 0;
     c->serializeSlots = getenv("RTB_SERIALIZE_SLOTS") != nullptr;
     c->profileDepths = getenv("RTB_PROFILE_DEPTHS") != nullptr;
+    c->noWide = getenv("RTB_NO_WIDE") != nullptr;
+    if (const char* t = getenv("RTB_SHADOW_KERNEL")) c->wideKernel = strcmp(t, "simple") != 0;
+    if (const char* t = getenv("RTB_HOT_NODES")) c->hotOverride = atoi(t);
     c->slots.resize(numSlots);
     e = c->totals.alloc(1);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->totals.ptr, 0, sizeof(Totals), c->stream);
@@ -1119,12 +1348,18 @@ int rtb_upload_scene(RtbContext* c, const RtbSceneDesc* scene)
         RTB_CUDA(dm.indices.upload(hm.indices, s));
         RTB_CUDA(dm.shading.upload(hm.shading, s));
         RTB_CUDA(dm.materialIds.upload(hm.materialIds, s));
+        const bool wide = !hm.wide.nodes.empty() && !c->noWide;
+        if (wide) { RTB_CUDA(dm.wideNodes.upload(hm.wide.nodes, s)); RTB_CUDA(dm.wideTris.upload(hm.wide.tris, s)); }
         DMesh& v = views[i];
+        v.wideNodes = wide ? dm.wideNodes.ptr : nullptr; v.wideTris = wide ? dm.wideTris.ptr : nullptr;
+        v.wideMaxAbs = hm.wide.maxAbs; v.numWideNodes = wide ? (uint32_t)hm.wide.nodes.size() : 0u;
         v.nodes = dm.nodes.ptr; v.tris = dm.tris.ptr; v.indices = dm.indices.ptr; v.shading = dm.shading.ptr; v.materialIds = dm.materialIds.ptr;
         v.numNodes = (uint32_t)hm.nodes.size(); v.numTriangles = (uint32_t)hm.tris.size();
         v.numVertices = (uint32_t)hm.shading.size(); v.numMaterials = (uint32_t)hm.materialIds.size();
     }
     RTB_CUDA(c->meshViews.upload(views, s));
+    c->hotNodes = nullptr; c->hotTotal = 0;
+    for (size_t i = 0; i < views.size(); ++i) if (views[i].numWideNodes > c->hotTotal) { c->hotTotal = views[i].numWideNodes; c->hotNodes = views[i].wideNodes; }
     // textures: bitmap texels stay float4 in HBM (rtb_texture.h); the descriptors get the device pointers
     c->texels.resize(hs.textures.size());
     for (size_t i = 0; i < hs.textures.size(); ++i)
@@ -1240,12 +1475,19 @@ int rtb_reset(RtbContext* c)
     memset(&c->counters, 0, sizeof(c->counters));
     c->passesSinceReset = 0;
     c->hasActiveList = false; c->numActive = 0; c->hostFrozen.clear();      // Viewport::Reset -> BuildInitialBlocksList: everything active again
+    c->vcm.lastPassIndex = 0xFFFFFFFFu;
+    if (c->vcm.allocated)
+    {
+        RTB_CUDA(cudaMemsetAsync(c->vcm.splat.ptr, 0, c->vcm.splat.count * sizeof(float), c->stream));
+        RTB_CUDA(cudaMemsetAsync(c->vcm.splat2.ptr, 0, c->vcm.splat2.count * sizeof(float), c->stream));
+        c->vcm.splatsPending = false;
+    }
     return RTB_OK;
 }
 
 static int fill_pass_params(RtbContext* c, const RtbPassDesc* pass, PassParams& P, bool uploadSeed)
 {
-    if (pass->renderer > RTB_RENDERER_DEBUG) return fail(RTB_ERR_INVALID_ARG, "unknown renderer id %u", pass->renderer);   // CreateRenderer, Renderer.cpp:45-69
+    if (pass->renderer > RTB_RENDERER_VCM) return fail(RTB_ERR_INVALID_ARG, "unknown renderer id %u", pass->renderer);   // CreateRenderer, Renderer.cpp:45-69
     if (pass->maxRayDepth >= 255u || pass->maxRayDepth >= RTB_MAX_DEPTH_SLOTS) return fail(RTB_ERR_INVALID_ARG, "maxRayDepth %u too large (limit %u)", pass->maxRayDepth, RTB_MAX_DEPTH_SLOTS - 1);
     if (pass->camera.barrelDistortionVariableFactor != 0.0f) return fail(RTB_ERR_UNSUPPORTED, "variable barrel distortion draws from a per-thread RNG in the reference and is not supported");
     if (pass->numSeedDims > 0 && !pass->seed) return fail(RTB_ERR_INVALID_ARG, "seed pointer is null");
@@ -1372,7 +1614,20 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
         {
             // resident warps only: they fetch rays dynamically until the list is empty
             const int shadowBlocks = RTB_SHADOW_REFILL ? c->numSMs * RTB_TRAV_MINBLOCKS : blocksShadow;
-            if (count) k_shadow<true><<<shadowBlocks, 128, c->stackBytes, s>>>(c->view, W, d);
+            if (c->wideKernel && c->hotTotal > 0)
+            {
+                // persistent CTAs; shared memory: barrier + staged tree top + one stack panel per 128 threads
+                const size_t perCta = (233472u - 1024u * RTB_SW_MINBLOCKS) / RTB_SW_MINBLOCKS;
+                const size_t stacks = (size_t)(RTB_SW_THREADS / 128) * c->stackBytes;
+                size_t hot = perCta > stacks + 256u ? (perCta - stacks - 256u) / sizeof(WNode) : 0u;
+                if (hot > c->hotTotal) hot = c->hotTotal;
+                if (c->hotOverride >= 0 && (size_t)c->hotOverride < hot) hot = (size_t)c->hotOverride;      // (-1: all that fit)
+                const size_t smem = 128u + ((hot * sizeof(WNode) + 127u) & ~(size_t)127u) + stacks;
+                const int wideBlocks = (int)std::min<size_t>((size_t)c->numSMs * RTB_SW_MINBLOCKS, std::max<size_t>(1, ((size_t)numPaths * std::max<uint32_t>(1u, W.raysPerPath) + RTB_SW_THREADS - 1) / RTB_SW_THREADS));
+                if (count) k_shadow_wide<true><<<wideBlocks, RTB_SW_THREADS, smem, s>>>(c->view, W, d, c->hotNodes, (uint32_t)hot, (uint32_t)c->stackBytes);
+                else k_shadow_wide<false><<<wideBlocks, RTB_SW_THREADS, smem, s>>>(c->view, W, d, c->hotNodes, (uint32_t)hot, (uint32_t)c->stackBytes);
+            }
+            else if (count) k_shadow<true><<<shadowBlocks, 128, c->stackBytes, s>>>(c->view, W, d);
             else k_shadow<false><<<shadowBlocks, 128, c->stackBytes, s>>>(c->view, W, d);
             k_resolve<<<blocks256, 256, 0, s>>>(W, d);
         }
@@ -1434,7 +1689,151 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
     return RTB_OK;
 }
 
-int rtb_render_passes(RtbContext* c, const RtbPassDesc* passes, uint32_t count)
+
+// ---- "VCM" passes (rtb_vcm.cuh) --------------------------------------------------------------------------------------------
+static int vcm_allocate(RtbContext* c)
+{
+    RtbContext::Vcm& v = c->vcm;
+    const uint32_t stride = v.params.maxPathLength;
+    if (v.allocated && v.vertexStride == stride && v.lightVertexCount.count == c->numPixels) return RTB_OK;
+    RTB_CUDA(sync_all(c));
+    free_vcm(c);
+    v.vertexStride = stride;
+    const size_t capacity = (size_t)c->numPixels * stride;
+    if (capacity >= (1ull << 31)) return fail(RTB_ERR_UNSUPPORTED, "VCM: %zu light vertices per pass exceed 2^31", capacity);
+    v.photonCapacity = (uint32_t)capacity;
+    RTB_CUDA(v.lightVertices.alloc(capacity * (RTB_VCM_VERTEX_WORDS / 4u)));
+    RTB_CUDA(v.lightVertexCount.alloc(c->numPixels));
+    RTB_CUDA(v.photons[0].alloc(capacity * 3u)); RTB_CUDA(v.photons[1].alloc(capacity * 3u));
+    RTB_CUDA(v.photonCount.alloc(2));
+    uint32_t hashSize = 1u;                                   // HashGrid::Build: NextPowerOfTwo(particles.Size()) (HashGrid.h:40), here of the capacity
+    while (hashSize < capacity) hashSize <<= 1;
+    v.hashSize = hashSize;
+    RTB_CUDA(v.cellStart.alloc((size_t)hashSize + 1u)); RTB_CUDA(v.cellCursor.alloc((size_t)hashSize + 1u));
+    RTB_CUDA(v.gridIndices.alloc(capacity));
+    RTB_CUDA(v.tileTotals.alloc(((size_t)hashSize + 1u + 1023u) / 1024u + 1u));
+    const size_t raster = (size_t)c->width * c->height * 3u;
+    RTB_CUDA(v.splat.alloc(raster)); RTB_CUDA(v.splat2.alloc(raster));
+    RTB_CUDA(cudaMemsetAsync(v.splat.ptr, 0, raster * sizeof(float), c->stream));
+    RTB_CUDA(cudaMemsetAsync(v.splat2.ptr, 0, raster * sizeof(float), c->stream));
+    RTB_CUDA(cudaMemsetAsync(v.photonCount.ptr, 0, 2 * sizeof(uint32_t), c->stream));
+    RTB_CUDA(cudaMemsetAsync(v.cellStart.ptr, 0, ((size_t)hashSize + 1u) * sizeof(uint32_t), c->stream));
+    v.allocated = true; v.current = 0; v.lastPassIndex = 0xFFFFFFFFu; v.splatsPending = false;
+    {
+        const int maxStack = (int)((size_t)RTB_MAX_SMEM_STACK_ENTRIES * RTB_STACK_THREADS * sizeof(uint32_t));
+        cudaFuncSetAttribute(k_vcm_light<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+        cudaFuncSetAttribute(k_vcm_light<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+        cudaFuncSetAttribute(k_vcm_camera<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+        cudaFuncSetAttribute(k_vcm_camera<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+    }
+    return RTB_OK;
+}
+
+static int vcm_fold(RtbContext* c)
+{
+    RtbContext::Vcm& v = c->vcm;
+    if (!v.allocated || !v.splatsPending) return RTB_OK;
+    cudaStream_t s = c->stream;
+    k_vcm_fold<<<c->numSMs * 4, 256, 0, s>>>(v.splat.ptr, c->sum.ptr, c->pixelList.ptr, c->numPixels);
+    k_vcm_fold<<<c->numSMs * 4, 256, 0, s>>>(v.splat2.ptr, c->sum2.ptr, c->pixelList.ptr, c->numPixels);
+    RTB_CUDA(cudaGetLastError());
+    RTB_CUDA(cudaMemsetAsync(v.splat.ptr, 0, v.splat.count * sizeof(float), s));
+    RTB_CUDA(cudaMemsetAsync(v.splat2.ptr, 0, v.splat2.count * sizeof(float), s));
+    c->counters.numKernelLaunches += 2;
+    v.splatsPending = false;
+    return RTB_OK;
+}
+
+static int render_vcm_pass(RtbContext* c, const RtbPassDesc* pass)
+{
+    RtbContext::Vcm& v = c->vcm;
+    if (c->hasActiveList) return fail(RTB_ERR_UNSUPPORTED, "VCM: adaptive rendering (rtb_set_active_tiles) is not supported");
+    if (c->numShards > 1 && v.params.useVertexMerging) return fail(RTB_ERR_UNSUPPORTED, "VCM: vertex merging needs the photons of every shard; sharded contexts support vertex connection only");
+    PassParams P;
+    int rc = fill_pass_params(c, pass, P, false);
+    if (rc != RTB_OK) return rc;
+    rc = vcm_allocate(c);
+    if (rc != RTB_OK) return rc;
+    RTB_CUDA(join_slots(c));
+    RtbContext::Slot& slot = c->slots[0];
+    cudaStream_t s = c->stream;
+    if (c->slotsOwnStreams) RTB_CUDA(cudaStreamSynchronize(slot.stream));
+    // seed vector + AA offset of this pass
+    const uint32_t dims = pass->numSeedDims;
+    if (slot.seed.count < (size_t)c->maxBatch * (dims + 2u) || !slot.seed.ptr)
+    {
+        RTB_CUDA(cudaStreamSynchronize(s));
+        RTB_CUDA(slot.seed.alloc((size_t)c->maxBatch * ((dims > 64 ? dims : 64) + 2u)));
+    }
+    slot.stagingSeeds.resize(dims + 2u);
+    if (dims) memcpy(slot.stagingSeeds.data(), pass->seed, dims * sizeof(uint32_t));
+    memcpy(&slot.stagingSeeds[dims], pass->sampleOffset, 2 * sizeof(float));
+    RTB_CUDA(cudaMemcpyAsync(slot.seed.ptr, slot.stagingSeeds.data(), (dims + 2u) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    P.seed = slot.seed.ptr;
+    P.sampleOffsets = reinterpret_cast<const float*>(slot.seed.ptr + dims);
+
+    VcmDevice V;
+    memset(&V, 0, sizeof(V));
+    // PreRender (VertexConnectionAndMerging.cpp:80-125): the radii follow from the pass number alone
+    V.pass.useVertexConnection = v.params.useVertexConnection ? 1u : 0u; V.pass.useVertexMerging = v.params.useVertexMerging ? 1u : 0u;
+    V.pass.maxPathLength = v.params.maxPathLength;
+    for (uint32_t p = 0; p <= pass->passIndex; ++p)
+        bidir_begin_pass(V.pass, p, (float)(c->width * c->height), v.params.initialMergingRadius, v.params.minMergingRadius, v.params.mergingRadiusMultiplier);
+    // photons of the previous pass of this frame, if that is what the buffer holds
+    const bool havePhotons = v.params.useVertexMerging && pass->passIndex > 0 && v.lastPassIndex + 1u == pass->passIndex;
+    if (v.params.useVertexMerging && pass->passIndex > 0 && !havePhotons)
+        return fail(RTB_ERR_INVALID_ARG, "VCM: pass %u merges with the photons of pass %u, which was not the previous pass rendered", pass->passIndex, pass->passIndex - 1u);
+    V.camera.localToWorld = P.camLocalToWorld; V.camera.tanHalfFoV = P.tanHalfFoV; V.camera.aspectRatio = P.aspectRatio;
+    V.camera.worldToScreen = camera_world_to_screen(P.camLocalToWorld, P.aspectRatio, P.tanHalfFoV);
+    const uint32_t prev = v.current, next = v.current ^ 1u;
+    V.lightVertices = v.lightVertices.ptr; V.lightVertexCount = v.lightVertexCount.ptr;
+    V.newPhotons = v.photons[next].ptr; V.newPhotonCount = v.photonCount.ptr + next;
+    V.photons = v.photons[prev].ptr; V.photonCount = v.photonCount.ptr + prev;
+    V.cellStart = v.cellStart.ptr; V.gridIndices = v.gridIndices.ptr;
+    V.hashMask = v.hashSize - 1u; V.photonCapacity = v.photonCapacity;
+    V.splat = v.splat.ptr; V.splat2 = (pass->passIndex & 1u) == 0u ? v.splat2.ptr : nullptr;      // Film: the secondary sum takes the even passes (Viewport.cpp:283)
+    V.vertexStride = v.vertexStride;
+    V.seedLo = (uint32_t)v.params.lightPathSeed; V.seedHi = (uint32_t)(v.params.lightPathSeed >> 32);
+
+    const int blocks256 = c->numSMs * 4;
+    uint32_t launches = 0;
+    if (!havePhotons) RTB_CUDA(cudaMemsetAsync(v.photonCount.ptr + prev, 0, sizeof(uint32_t), s));
+    if (havePhotons)
+    {
+        // HashGrid::Build (HashGrid.h:17-82): count per cell, exclusive prefix sum, fill
+        const uint32_t cells = v.hashSize + 1u, tiles = (cells + 1023u) / 1024u;
+        const float invCell = 1.0f / (V.pass.radiusVM * 2.0f);
+        RTB_CUDA(cudaMemsetAsync(v.cellStart.ptr, 0, (size_t)cells * sizeof(uint32_t), s));
+        k_vcm_grid_count<<<blocks256, 256, 0, s>>>(V.photons, V.photonCount, v.photonCapacity, invCell, V.hashMask, v.cellStart.ptr);
+        k_vcm_scan_tiles<<<tiles, 256, 0, s>>>(v.cellStart.ptr, cells, v.tileTotals.ptr);
+        k_vcm_scan_totals<<<1, 1024, 0, s>>>(v.tileTotals.ptr, tiles, v.tileTotals.ptr + tiles);
+        k_vcm_scan_offsets<<<(cells + 255u) / 256u, 256, 0, s>>>(v.cellStart.ptr, cells, v.tileTotals.ptr);
+        RTB_CUDA(cudaMemcpyAsync(v.cellCursor.ptr, v.cellStart.ptr, (size_t)cells * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        k_vcm_grid_fill<<<blocks256, 256, 0, s>>>(V.photons, V.photonCount, v.photonCapacity, invCell, V.hashMask, v.cellCursor.ptr, v.gridIndices.ptr);
+        launches += 5;
+    }
+    RTB_CUDA(cudaMemsetAsync(v.photonCount.ptr + next, 0, sizeof(uint32_t), s));
+    const bool textured = c->textures.count > 0;
+    const int blocks128 = (int)std::min<size_t>((size_t)c->numSMs * 16, std::max<size_t>(1, ((size_t)c->numPixels + 127) / 128));
+    Wavefront W = slot.wf;
+    W.batch = 1; W.firstPassIndex = pass->passIndex;
+    if (textured) k_vcm_light<true><<<blocks128, 128, c->stackBytes, s>>>(c->view, P, V, c->pixelList.ptr, c->numPixels, c->totals.ptr);
+    else k_vcm_light<false><<<blocks128, 128, c->stackBytes, s>>>(c->view, P, V, c->pixelList.ptr, c->numPixels, c->totals.ptr);
+    if (textured) k_vcm_camera<true><<<blocks128, 128, c->stackBytes, s>>>(c->view, P, V, c->pixelList.ptr, c->numPixels, W.passColor, c->totals.ptr);
+    else k_vcm_camera<false><<<blocks128, 128, c->stackBytes, s>>>(c->view, P, V, c->pixelList.ptr, c->numPixels, W.passColor, c->totals.ptr);
+    k_film<<<blocks256, 256, 0, s>>>(W, c->sum.ptr, c->sum2.ptr, nullptr, 0, 0);
+    RTB_CUDA(cudaGetLastError());
+    launches += 3;
+    v.splatsPending = true;
+    v.current = next; v.lastPassIndex = pass->passIndex;
+    c->counters.numPrimaryRays += c->numPixels;
+    c->counters.numKernelLaunches += launches;
+    c->passesSinceReset += 1;
+    if (c->numShards == 1) return vcm_fold(c);
+    return RTB_OK;
+}
+
+extern "C" int rtb_render_passes(RtbContext* c, const RtbPassDesc* passes, uint32_t count)
 {
     if (!c || (count && !passes)) return fail(RTB_ERR_INVALID_ARG, "rtb_render_passes: null argument");
     if (!c->hasScene) return fail(RTB_ERR_NO_SCENE, "rtb_render_passes: no scene uploaded");       // Viewport.cpp:194-198 ("Missing renderer")
@@ -1446,7 +1845,14 @@ int rtb_render_passes(RtbContext* c, const RtbPassDesc* passes, uint32_t count)
         const RtbPassDesc* pass = &passes[i];
         // the reference silently switches to a per-thread RNG beyond SamplingParams::dimensions (GenericSampler.cpp:106-109);
         // that is irreproducible, so refuse it up front.  Worst case per path: SURVEY appendix B.
-        if (pass->renderer != RTB_RENDERER_DEBUG)
+        if (pass->renderer == RTB_RENDERER_VCM)
+        {
+            // camera path: per vertex three numbers per light (SampleLights) and three for the BSDF sample (AdvancePath)
+            const uint32_t needed = (pass->camera.dofEnable ? 2u : 0u) + (3u * c->numLights + 3u) * c->vcm.params.maxPathLength;
+            if (needed > pass->numSeedDims)
+                return fail(RTB_ERR_INVALID_ARG, "rtb_render_pass: VCM needs %u sample dimensions (lights=%u, maxPathLength=%u) but only %u are seeded", needed, c->numLights, c->vcm.params.maxPathLength, pass->numSeedDims);
+        }
+        else if (pass->renderer != RTB_RENDERER_DEBUG)
         {
             const uint32_t L = pass->renderer == RTB_RENDERER_PATH_TRACER_MIS ? (pass->lightSamplingStrategy == RTB_LIGHT_SAMPLING_ALL ? c->numLights : (c->numLights ? 1u : 0u)) : 0u;
             const uint32_t D = pass->maxRayDepth;
@@ -1471,6 +1877,13 @@ int rtb_render_passes(RtbContext* c, const RtbPassDesc* passes, uint32_t count)
     uint32_t i = 0;
     while (i < count)
     {
+        if (passes[i].renderer == RTB_RENDERER_VCM)
+        {
+            int rc = render_vcm_pass(c, passes + i);
+            if (rc != RTB_OK) return rc;
+            i++;
+            continue;
+        }
         // run of compatible passes, then cut into equal wavefronts (64 passes with maxBatch 9 -> 8 x 8, not 7 x 9 + 1)
         uint32_t run = 1;
         while (i + run < count && same(passes[i], passes[i + run]) && passes[i + run].passIndex == passes[i].passIndex + run) run++;
@@ -1940,6 +2353,38 @@ int rtb_primary_rays(RtbContext* c, const RtbPassDesc* pass, RtbRay* rays)
     cudaFree(d);
     if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "primary rays failed: %s", cudaGetErrorString(e));
     return RTB_OK;
+}
+
+int rtb_set_vcm_params(RtbContext* c, const RtbVcmParams* params)
+{
+    if (!c || !params) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    // the asserts of VertexConnectionAndMerging::PreRender, VertexConnectionAndMerging.cpp:82-85
+    if (params->maxPathLength == 0 || params->maxPathLength > RTB_VCM_MAX_PATH_LENGTH) return fail(RTB_ERR_INVALID_ARG, "maxPathLength %u out of range (1 .. %u)", params->maxPathLength, RTB_VCM_MAX_PATH_LENGTH);
+    if (!(params->initialMergingRadius >= params->minMergingRadius) || !(params->minMergingRadius > 0.0f)) return fail(RTB_ERR_INVALID_ARG, "merging radii: initial >= min > 0 required");
+    if (!(params->mergingRadiusMultiplier > 0.0f) || !(params->mergingRadiusMultiplier <= 1.0f)) return fail(RTB_ERR_INVALID_ARG, "mergingRadiusMultiplier must be in (0, 1]");
+    c->vcm.params = *params;
+    c->vcm.lastPassIndex = 0xFFFFFFFFu;
+    return RTB_OK;
+}
+
+int rtb_vcm_splat_buffers(RtbContext* c, void** outSplat, void** outSplat2, uint64_t* outNumFloats)
+{
+    if (!c || !outSplat || !outSplat2 || !outNumFloats) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    if (!c->sum.ptr) return fail(RTB_ERR_INVALID_ARG, "viewport has no size");
+    RTB_CUDA(cudaSetDevice(c->device));
+    int rc = vcm_allocate(c);
+    if (rc != RTB_OK) return rc;
+    RTB_CUDA(join_slots(c));
+    *outSplat = c->vcm.splat.ptr; *outSplat2 = c->vcm.splat2.ptr; *outNumFloats = (uint64_t)c->width * c->height * 3u;
+    return RTB_OK;
+}
+
+int rtb_vcm_fold_splats(RtbContext* c)
+{
+    if (!c) return fail(RTB_ERR_INVALID_ARG, "null context");
+    RTB_CUDA(cudaSetDevice(c->device));
+    RTB_CUDA(join_slots(c));
+    return vcm_fold(c);
 }
 
 int rtb_set_profiling(RtbContext* c, int enable)

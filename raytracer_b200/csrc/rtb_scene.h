@@ -49,10 +49,17 @@ struct __attribute__((aligned(16))) DObjectShade
 struct __attribute__((aligned(16))) DVertexIndices { uint32_t i0, i1, i2, materialIndex; };      // VertexBuffer.h:18-24
 struct __attribute__((aligned(16))) DVertexShading { float nx, ny, nz, tx, ty, tz, u, v; };      // VertexBuffer.h:26-31
 
+struct WNode;      // rtb_wide.h
+
 struct DMesh
 {
     const DNode*          nodes;
     const DTri*           tris;
+    // any-hit acceleration structure (rtb_wide.h); wideNodes == nullptr: the mesh only has the reference's binary tree
+    const WNode*          wideNodes;
+    const DTri*           wideTris;
+    float                 wideMaxAbs;
+    uint32_t              numWideNodes;
     const DVertexIndices* indices;
     const DVertexShading* shading;
     const uint32_t*       materialIds;

@@ -120,6 +120,32 @@ RTB_HD bool triangle_ray(const Ray& ray, const V3& v0, const V3& e1, const V3& e
     return !(upv > 1.0f) && (outV > 0.0f) && (outT > 0.0f) && (outU > 0.0f);
 }
 
+// The same test as "triangle_ray(...) && outT < tLimit" with the four IEEE divisions (a subroutine each on the device)
+// taken only by candidates: the numerators are the reference's, and a quotient can only be positive if numerator and
+// determinant agree in sign, can only stay <= 1 if |u + v| <= |det| up to its rounding, can only stay below tLimit if
+// |t| < tLimit * |det| up to its rounding.  Everything that survives this division-free screen takes the reference's
+// divisions and comparisons, so the result is the reference's bit for bit; what the screen rejects the reference rejects.
+RTB_HD bool triangle_ray_below(const Ray& ray, const V3& v0, const V3& e1, const V3& e2, float tLimit, float& outU, float& outV, float& outT)
+{
+    const V3 tvec = ray.origin - v0;
+    const V3 pvec = cross3(ray.dir, e2);
+    const V3 qvec = cross3(tvec, e1);
+    const float det = dot3(e1, pvec);
+    const float u = dot3(tvec, pvec);
+    const float v = dot3(ray.dir, qvec);
+    const float t = dot3(e2, qvec);
+    const uint32_t sign = f2bits(det) & 0x80000000u;
+    const float ad = bits2f(f2bits(det) ^ sign);                          // |det|
+    const float su = bits2f(f2bits(u) ^ sign), sv = bits2f(f2bits(v) ^ sign), st = bits2f(f2bits(t) ^ sign);
+    const float slack = 1.00000095367431640625f;                          // 1 + 2^-20
+    if (!(su > 0.0f && sv > 0.0f && st > 0.0f && bit_abs(u + v) <= ad * slack && st < (tLimit * ad) * slack)) return false;
+    const float upv = (u + v) / det;
+    outU = u / det;
+    outV = v / det;
+    outT = t / det;
+    return !(upv > 1.0f) && (outV > 0.0f) && (outT > 0.0f) && (outU > 0.0f) && (outT < tLimit);
+}
+
 struct ShapeIntersection { float nearDist, farDist; uint32_t subObjectId; };
 
 // SphereShape::Intersect (double precision quadratic), SphereShape.cpp:29-46
@@ -222,6 +248,10 @@ RTB_HD void load_node_pair(const DNode* nodes, uint32_t index, DNode& a, DNode& 
     b = load_node(nodes, index + 1);
 #endif
 }
+
+} // namespace rtb
+#include "rtb_wide.h"
+namespace rtb {
 
 #define RTB_NUM_LEAVES(info) ((info) & 0x3FFFFFFFu)
 #define RTB_ENTRY_OBJECT 0xFFFFFFFFu    // stack entry {k, RTB_ENTRY_OBJECT}: "traverse object k" (otherwise {childIndex, leafInfo} of a node)
@@ -453,16 +483,13 @@ RTB_HD void scene_traverse_from(const SceneView& S, const WorldRay& worldRaySour
                     V3 v0, e1, e2;
                     load_tri(tris, triangleIndex, v0, e1, e2);
                     float u, v, distance;
-                    if (triangle_ray(ray, v0, e1, e2, u, v, distance))
+                    if (triangle_ray_below(ray, v0, e1, e2, hit.distance, u, v, distance))       // Intersect_TriangleRay && distance < hitPoint.distance
                     {
-                        if (distance < hit.distance)
-                        {
-                            hit.distance = distance;
-                            hit.subObjectId = triangleIndex;
-                            hit.objectId = objectID;
-                            hit.u = u;
-                            hit.v = v;
-                        }
+                        hit.distance = distance;
+                        hit.subObjectId = triangleIndex;
+                        hit.objectId = objectID;
+                        hit.u = u;
+                        hit.v = v;
                     }
                 }
             }
@@ -510,6 +537,38 @@ RTB_HD void scene_traverse_from(const SceneView& S, const WorldRay& worldRaySour
     }
 }
 
+// stack of the wide any-hit walk (rtb_wide.h) on top of the entries the two-level walk already holds: a group is two
+// consecutive 4-byte entries
+struct WideStackAbove
+{
+    uint32_t* stack; SharedStack sstack; uint32_t floor, top;
+    RTB_HD bool empty() const { return top == floor; }
+    RTB_HD void push(uint32_t a, uint32_t b)
+    {
+#if RTB_SSTACK
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(sstack + top * (RTB_STACK_THREADS * 4u)), "r"(a));
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(sstack + (top + 1u) * (RTB_STACK_THREADS * 4u)), "r"(b));
+#else
+        stack[top] = a; stack[top + 1u] = b;
+#endif
+        top += 2u;
+    }
+    RTB_HD void pop(uint32_t& a, uint32_t& b)
+    {
+        top -= 2u;
+#if RTB_SSTACK
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a) : "r"(sstack + top * (RTB_STACK_THREADS * 4u)));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(b) : "r"(sstack + (top + 1u) * (RTB_STACK_THREADS * 4u)));
+#else
+        a = stack[top]; b = stack[top + 1u];
+#endif
+    }
+};
+
+#ifndef RTB_WIDE_SHADOW
+#define RTB_WIDE_SHADOW 1      // 0: any-hit rays walk the reference's binary tree like closest-hit rays do
+#endif
+
 // Scene::Traverse_Shadow (Scene.cpp:245-261), same flattening, as a resumable walk: begin() + step() until done.
 // The result is a boolean "any triangle / shape closer than maxDistance among the leaves whose ancestors pass the box
 // test".  It does not depend on the visiting order, so this any-hit walk is free to (a) descend into the NEARER child
@@ -519,7 +578,7 @@ RTB_HD void scene_traverse_from(const SceneView& S, const WorldRay& worldRaySour
 // between steps.
 struct ShadowWalk
 {
-    enum { kContinue = 0, kOccluded = 1, kVisible = 2 };
+    enum { kContinue = 0, kOccluded = 1, kVisible = 2, kEnterWide = 3 };
 
     // (the stack itself is a separate local array handed to begin()/step(): with the array inside, the whole struct
     //  would live in local memory instead of registers)
@@ -532,6 +591,7 @@ struct ShadowWalk
     float maxDistance;
     uint32_t curChild, curInfo;
     uint32_t pendChild, pendInfo;          // a mesh leaf whose triangle tests are postponed
+    uint32_t wideMesh;                     // kEnterWide: the mesh whose 8-wide tree the caller walks with `ray` (mesh-local), then leave_wide()
 
     // false: nothing to traverse (the ray is unoccluded)
     template <typename WorldRay>
@@ -561,7 +621,7 @@ struct ShadowWalk
             V3 v0, e1, e2;
             load_tri(tris, first + i, v0, e1, e2);
             float u, v, distance;
-            if (triangle_ray(ray, v0, e1, e2, u, v, distance) && distance < maxDistance) occluded = true;
+            if (triangle_ray_below(ray, v0, e1, e2, maxDistance, u, v, distance)) occluded = true;
         }
         return occluded;
     }
@@ -622,7 +682,18 @@ struct ShadowWalk
 
     }
 
-    template <bool kCount, typename WorldRay>
+    // after the caller has walked the wide tree of `wideMesh` without finding an occluder
+    template <typename WorldRay>
+    RTB_HD void leave_wide(const SceneView& S, const WorldRay& worldRaySource)
+    {
+        nodes = S.tlas; ray = worldRaySource.load(); finite = worldFinite;
+        // (what step() left behind when it returned kEnterWide, restated so that none of it has to live through the wide walk)
+        have = false; inBlas = false; pendInfo = 0; pendChild = 0; popFloor = 0xFFFFFFFFu; blasBase = 0; curChild = 0; curInfo = 0; tris = nullptr;
+    }
+
+    // kSuspendWide: a mesh that has an 8-wide tree is not walked here; step() returns kEnterWide with the mesh-local ray
+    // in `ray` and the caller walks it (k_shadow_wide does that for all lanes of a warp together)
+    template <bool kCount, typename WorldRay, bool kSuspendWide = false>
     RTB_HD int step(const SceneView& S, uint32_t* stack, const WorldRay& worldRaySource, TraceCounters* cnt, SharedStack sstack = 0)
     {
         // (the form of the node loop matters: `while (have) { if (leaf) break; ... }` WITHOUT the postponing measured 35 %
@@ -667,6 +738,17 @@ struct ShadowWalk
             if (obj.kind == RTB_OBJECT_SHAPE && obj.shapeType == RTB_SHAPE_MESH)
             {
                 const DMesh& mesh = S.meshes[obj.meshIndex];
+#if RTB_WIDE_SHADOW
+                if (mesh.numNodes != 0 && mesh.wideNodes != nullptr && wide_ray_ok(localRay))
+                {
+                    if (kSuspendWide) { wideMesh = obj.meshIndex; ray = localRay; return kEnterWide; }
+                    // the whole mesh in one go on its 8-wide tree: same boolean as the binary walk (rtb_wide.h)
+                    WideView wv; wv.nodes = mesh.wideNodes; wv.tris = mesh.wideTris; wv.refNodes = mesh.nodes; wv.maxAbs = mesh.wideMaxAbs;
+                    WideStackAbove ws; ws.stack = stack; ws.sstack = sstack; ws.floor = stackSize; ws.top = stackSize;
+                    if (wide_any_hit<kCount>(wv, localRay, maxDistance, ws, cnt)) return kOccluded;
+                }
+                else
+#endif
                 if (mesh.numNodes != 0)
                 {
                     inBlas = true; blasBase = stackSize; popFloor = stackSize; nodes = mesh.nodes; tris = mesh.tris; ray = localRay; finite = ray_is_finite(localRay);

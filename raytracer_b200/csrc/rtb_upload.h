@@ -6,8 +6,10 @@
 #include <string>
 #include <cstring>
 #include <algorithm>
+#include <cstdlib>
 
 #include "rtb_trace.h"
+#include "rtb_wide_build.h"
 
 namespace rtb {
 
@@ -18,6 +20,7 @@ struct HostMesh
     std::vector<DVertexIndices> indices;
     std::vector<DVertexShading> shading;
     std::vector<uint32_t> materialIds;
+    HostWide wide;                 // any-hit tree (rtb_wide.h); wide.nodes empty: not built, the binary walk is used
 };
 
 struct HostScene
@@ -184,6 +187,12 @@ inline bool build_host_scene(const RtbSceneDesc& d, HostScene& out, std::string&
         const uint32_t depth = bvh_depth(src.nodes, src.numNodes, src.numTriangles, err);
         if (src.numNodes && depth == 0) return false;
         if (depth > out.maxBlasDepth) out.maxBlasDepth = depth;
+        // any-hit tree; a mesh it cannot be built for keeps the binary walk.  Its stack: two entries per level
+#if RTB_WIDE_SHADOW
+        const char* leafEnv = getenv("RTB_WIDE_LEAF_TRIS");      // development knob: triangles per leaf child (1..4)
+        if (!build_wide_bvh(dst.nodes, dst.tris, dst.wide, leafEnv ? (uint32_t)atoi(leafEnv) : RTB_WIDE_LEAF_TRIS)) dst.wide = HostWide();
+        if (2u * dst.wide.depth > out.maxBlasDepth) out.maxBlasDepth = 2u * dst.wide.depth;
+#endif
     }
 
     out.lights.resize(d.numLights);

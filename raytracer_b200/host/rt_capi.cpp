@@ -162,6 +162,14 @@ uint32_t rtbh_revise_blocks(RtbBlock* blocks, uint32_t n, uint32_t capacity, con
     return (uint32_t)list.size();
 }
 
+int rtbh_viewport_set_vcm(void* vp, uint32_t connection, uint32_t merging, uint32_t maxPathLength, float initialRadius, float minRadius, float radiusMultiplier, uint64_t seed)
+{
+    RtbVcmParams p;
+    p.useVertexConnection = connection; p.useVertexMerging = merging; p.maxPathLength = maxPathLength;
+    p.initialMergingRadius = initialRadius; p.minMergingRadius = minRadius; p.mergingRadiusMultiplier = radiusMultiplier; p.lightPathSeed = seed;
+    return static_cast<rt::ViewportB200*>(vp)->SetVcmParams(p) ? 0 : -1;
+}
+
 int rtbh_viewport_resize(void* vp, uint32_t w, uint32_t h) { return static_cast<rt::ViewportB200*>(vp)->Resize(w, h) ? 0 : -1; }
 void rtbh_viewport_reset(void* vp) { static_cast<rt::ViewportB200*>(vp)->Reset(); }
 

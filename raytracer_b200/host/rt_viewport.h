@@ -321,7 +321,14 @@ public:
         if (name == "Path Tracer") mRenderer = RTB_RENDERER_PATH_TRACER;
         else if (name == "Path Tracer MIS") mRenderer = RTB_RENDERER_PATH_TRACER_MIS;
         else if (name == "Debug") mRenderer = RTB_RENDERER_DEBUG;
-        else { mError = "Unknown renderer name: '" + name + "' (supported: 'Path Tracer', 'Path Tracer MIS', 'Debug')"; return false; }
+        else if (name == "VCM") mRenderer = RTB_RENDERER_VCM;          // VertexConnectionAndMerging; its public members: SetVcmParams
+        else { mError = "Unknown renderer name: '" + name + "' (supported: 'Path Tracer', 'Path Tracer MIS', 'Debug', 'VCM')"; return false; }
+        return true;
+    }
+    // VertexConnectionAndMerging::mUseVertexConnection ... mMergingRadiusMultiplier (VertexConnectionAndMerging.h:48-56)
+    bool SetVcmParams(const RtbVcmParams& params)
+    {
+        if (rtb_set_vcm_params(mCtx, &params) != RTB_OK) return Error();
         return true;
     }
     void SetDebugMode(uint32_t mode) { mDebugMode = mode; }

@@ -46,6 +46,7 @@ def load_host_library():
     lib.rtbh_viewport_synchronize.argtypes = [C.c_void_p]
     lib.rtbh_viewport_read_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.rtbh_viewport_set_adaptive.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float]
+    lib.rtbh_viewport_set_vcm.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_uint64]
     lib.rtbh_viewport_progress.argtypes = [C.c_void_p, C.c_void_p]
     lib.rtbh_viewport_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     lib.rtbh_viewport_blocks.restype = C.c_uint32
@@ -178,6 +179,10 @@ class Viewport:
     def set_adaptive(self, enable=True, num_initial_passes=10, min_block_size=4, max_block_size=256, subdivision_treshold=0.005, convergence_treshold=0.0001):
         """AdaptiveRenderingSettings (Context.h:35-43); applies from the next reset() / resize()."""
         self._check(self.lib.rtbh_viewport_set_adaptive(self.h, 1 if enable else 0, num_initial_passes, min_block_size, max_block_size, subdivision_treshold, convergence_treshold))
+
+    def set_vcm(self, connection=True, merging=True, max_path_length=10, initial_radius=0.02, min_radius=0.02, radius_multiplier=1.0, seed=0x5EED):
+        """The public members of the reference's VCM renderer (VertexConnectionAndMerging.h:48-56), its defaults."""
+        self._check(self.lib.rtbh_viewport_set_vcm(self.h, 1 if connection else 0, 1 if merging else 0, max_path_length, initial_radius, min_radius, radius_multiplier, seed))
 
     def progress(self):
         """Viewport::GetProgress (Viewport.h:25-32, 55)."""

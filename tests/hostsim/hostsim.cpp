@@ -80,6 +80,9 @@ struct World
             v.materialIds = m.materialIds.data();
             v.numNodes = (uint32_t)m.nodes.size(); v.numTriangles = (uint32_t)m.tris.size();
             v.numVertices = (uint32_t)m.shading.size(); v.numMaterials = (uint32_t)m.materialIds.size();
+            const bool wide = !m.wide.nodes.empty() && !getenv("HOSTSIM_NO_WIDE");
+            v.wideNodes = wide ? m.wide.nodes.data() : nullptr; v.wideTris = wide ? m.wide.tris.data() : nullptr;
+            v.wideMaxAbs = m.wide.maxAbs; v.numWideNodes = wide ? (uint32_t)m.wide.nodes.size() : 0u;
         }
         memset(&S, 0, sizeof(S));
         S.tlas = hs.tlas.data(); S.objTrace = hs.objTrace.data(); S.objShade = hs.objShade.data();
@@ -246,6 +249,9 @@ static int cmdTrace(int argc, char** argv)
         fclose(tf);
     }
     std::vector<RtbHit> hits(n);
+    TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
+    unsigned long long boxTests = 0, triTests = 0;
+    const bool countTests = getenv("HOSTSIM_COUNT") != nullptr;
     for (size_t i = 0; i < n; ++i)
     {
         Ray r;
@@ -257,13 +263,21 @@ static int cmdTrace(int argc, char** argv)
         hit.objectId = RTB_INVALID_OBJECT; hit.subObjectId = 0; hit.distance = INFINITY; hit.u = 0.0f; hit.v = 0.0f;
         RtbHit& o = hits[i];
         memset(&o, 0, sizeof(o));
-        if (shadow) { hit.distance = tmax[i]; o.occluded = scene_traverse_shadow<false>(world.S, r, tmax[i], nullptr) ? 1u : 0u; }
+        if (shadow) { hit.distance = tmax[i]; o.occluded = (countTests ? scene_traverse_shadow<true>(world.S, r, tmax[i], &cnt) : scene_traverse_shadow<false>(world.S, r, tmax[i], nullptr)) ? 1u : 0u; }
+        else if (countTests) scene_traverse<true>(world.S, r, hit, &cnt);
         else scene_traverse<false>(world.S, r, hit, nullptr);
+        boxTests += cnt.boxTests; triTests += cnt.triTests; cnt.boxTests = 0; cnt.triTests = 0;
         o.objectId = hit.objectId; o.subObjectId = hit.subObjectId; o.distance = hit.distance; o.u = hit.u; o.v = hit.v;
     }
     FILE* of = fopen(argv[4], "wb");
     fwrite(hits.data(), sizeof(RtbHit), n, of);
     fclose(of);
+    if (countTests)
+    {
+        size_t wideNodes = 0, wideTris = 0; uint32_t depth = 0;
+        for (const HostMesh& m : world.hs.meshes) { wideNodes += m.wide.nodes.size(); wideTris += m.wide.tris.size(); depth = std::max(depth, m.wide.depth); }
+        printf("{\"rays\": %zu, \"boxTests\": %llu, \"triTests\": %llu, \"wideNodes\": %zu, \"wideTris\": %zu, \"wideDepth\": %u}\n", n, boxTests, triTests, wideNodes, wideTris, depth);
+    }
     return 0;
 }
 

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 SIZE = 32                                   # RenderingTest::ViewportSize
 LIGHT = [1.0, 2.0, 3.0]
-RENDERERS = ["Path Tracer", "Path Tracer MIS"]      # the reference's third entry, "VCM", is out of scope
+RENDERERS = ["Path Tracer", "Path Tracer MIS", "VCM"]     # RaytracingTests.cpp:17-22: the reference runs every test on all three
 
 
 def furnace_scene(tmp_path, material=None, fov=10.0, sphere=True):

@@ -732,3 +732,18 @@ def test_active_tiles(ctx):
     ctx.reset()
     ctx.render_passes(cam, ps.seeds[0:4], ps.offsets[0:4])
     util.assert_bit_identical(ctx.read_sum(), four, "all pixels active again")
+
+
+@pytest.mark.parametrize("env", [{"RTB_SHADOW_KERNEL": "simple", "RTB_NO_WIDE": "1"}, {"RTB_SHADOW_KERNEL": "simple"}, {"RTB_HOT_NODES": "0"}, {"RTB_HOT_NODES": "64"}, {"RTB_HOT_NODES": "-1"}])
+def test_any_hit_walks_agree(env, monkeypatch):
+    """The three any-hit walks - the reference's binary tree in k_shadow, the 8-wide quantised tree (rtb_wide.h) inside
+    k_shadow, and the persistent k_shadow_wide with 0 / 64 / all-that-fit nodes of the tree top staged in shared memory by
+    a bulk copy - give the reference's film and shadow-ray counters on the mesh scenes, bit for bit."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for scene in ("mesh_small", "textures"):
+        with capi.Context(device=0) as c:
+            meta, img, counters = render_golden_case(c, scene, "mis")
+        want = util.load_sum(util.golden("%s_mis.sum" % scene), meta["width"], meta["height"])
+        util.assert_bit_identical(img, want, "%s/mis with %s" % (scene, env))
+        assert counters["numShadowRays"] == meta["numShadowRays"] and counters["numShadowRaysHit"] == meta["numShadowRaysHit"]
