@@ -182,10 +182,21 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput: K passes enqueued back to back, film gathered once per frame ----------------------
-    film_ptr, film_n = C.c_void_p(), C.c_uint64()
-    lib.rtb_film_device_buffer(ctx, 0, C.byref(film_ptr), C.byref(film_n))
-    film = torch.as_tensor(CudaArray(film_ptr.value, film_n.value), device="cuda")
-    gathered = torch.empty(world * film_n.value, dtype=torch.float32, device="cuda") if world > 1 else None
+    # multi-GPU: the communicator lives in the library (rtb_comm_init: NCCL loaded there); torch.distributed only carries
+    # the 128-byte id, the barriers and the timing reductions
+    if world > 1:
+        ident = torch.zeros(capi.RTB_COMM_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_ubyte * capi.RTB_COMM_ID_BYTES)()
+            rc = lib.rtb_comm_unique_id(buf)
+            assert rc == 0, lib.rtb_last_error()
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        ident = ident.cuda()
+        dist.broadcast(ident, 0)
+        raw = bytes(ident.cpu().tolist())
+        rc = lib.rtb_comm_init(ctx, raw)
+        assert rc == 0, lib.rtb_last_error()
+    gathered_ptr = C.c_void_p()
 
     vp.render(args.warmup)
     sync_all()
@@ -200,7 +211,8 @@ def run_gpu(args):
     vp.render(args.steps)
     lib.rtb_join(ctx)                                    # the torch stream waits (on the device) for the wavefront streams
     if world > 1:
-        dist.all_gather_into_tensor(gathered, film)      # ONE collective per frame
+        rc = lib.rtb_finish_frame(ctx, 0, C.byref(gathered_ptr))      # ONE collective per frame: ncclAllGather of the shard films, inside the library
+        assert rc == 0, lib.rtb_last_error()
     ev1.record()
     sync_all()
     wall_s = time.perf_counter() - t0
@@ -219,8 +231,8 @@ def run_gpu(args):
         seconds = dev_s
     if world > 1 and rank == 0:
         img = np.empty((HEIGHT, WIDTH, 3), dtype=np.float32)
-        lib.rtb_unshard_film(ctx, C.c_void_p(gathered.data_ptr()), img.ctypes.data)
-        assert np.isfinite(img).all() and img.mean() > 0
+        lib.rtb_unshard_film(ctx, gathered_ptr, img.ctypes.data)
+        assert np.isfinite(img).all() and img.mean() > 0 and (img.sum(axis=2) > 0).mean() > 0.99      # every shard's pixels are there
 
     # ---- end to end through the public API with host buffers: EVERY step's frame is read back to the host ---------------
     # A step is still one pass, and the frame as of every pass lands in page-locked host memory; the passes are
@@ -228,28 +240,56 @@ def run_gpu(args):
     # rtb_film_snapshots leaves the film as of each of them on the device, from where each frame is (all-gathered when
     # sharded,) un-permuted to raster order and copied out asynchronously.
     vp.reset()
-    pinned = [capi.PinnedImage(WIDTH, HEIGHT), capi.PinnedImage(WIDTH, HEIGHT)]   # page-locked host frames (rtb_host_alloc)
     E2E_GROUP = 8
     e2e_steps = max(E2E_GROUP, (min(args.steps, 32) // E2E_GROUP) * E2E_GROUP)
     snap_ptr, snap_stride = C.c_void_p(), C.c_uint64()
     rc = lib.rtb_film_snapshots(ctx, E2E_GROUP, C.byref(snap_ptr), C.byref(snap_stride))
     assert rc == 0, lib.rtb_last_error()
-    snaps = [torch.as_tensor(CudaArray(snap_ptr.value + 4 * snap_stride.value * i, snap_stride.value), device="cuda") for i in range(E2E_GROUP)]
+    snap_addr = [snap_ptr.value + 4 * snap_stride.value * i for i in range(E2E_GROUP)]
+    frame_bytes = WIDTH * HEIGHT * 12
     e2e_count = [0]
+    shm = None
+    if world == 1:
+        pinned = [capi.PinnedImage(WIDTH, HEIGHT), capi.PinnedImage(WIDTH, HEIGHT)]   # page-locked host frames (rtb_host_alloc)
+        frames = [im.array for im in pinned]
 
-    def e2e_group():
-        vp.render(E2E_GROUP)              # H2D: the seed vectors + pass descriptors of these steps
-        lib.rtb_join(ctx)
-        for i in range(E2E_GROUP):
-            dst = pinned[e2e_count[0] & 1]
-            e2e_count[0] += 1
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, snaps[i])
-                if rank == 0:
-                    rc = lib.rtb_unshard_film_async(ctx, C.c_void_p(gathered.data_ptr()), C.c_void_p(dst.ptr))
-                    assert rc == 0, lib.rtb_last_error()
-            else:
-                rc = lib.rtb_unshard_film_async(ctx, C.c_void_p(snaps[i].data_ptr()), C.c_void_p(dst.ptr))
+        def e2e_group():
+            vp.render(E2E_GROUP)              # H2D: the seed vectors + pass descriptors of these steps
+            lib.rtb_join(ctx)
+            for i in range(E2E_GROUP):
+                dst = pinned[e2e_count[0] & 1]
+                e2e_count[0] += 1
+                rc = lib.rtb_unshard_film_async(ctx, C.c_void_p(snap_addr[i]), C.c_void_p(dst.ptr))
+                assert rc == 0, lib.rtb_last_error()
+    else:
+        # ONE host frame pair in shared memory, attached and page-locked by every rank process: each rank writes ITS pixels of
+        # every frame straight into it (rtb_scatter_shard) over its own PCIe link - no all-gather, no funnel through rank 0
+        from multiprocessing import shared_memory
+        names = [None]
+        if rank == 0:
+            shm = shared_memory.SharedMemory(create=True, size=2 * frame_bytes)
+            names = [shm.name]
+        dist.broadcast_object_list(names, 0)
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=names[0])
+        host = np.ndarray((2, HEIGHT, WIDTH, 3), dtype=np.float32, buffer=shm.buf)
+        if rank == 0:
+            host[:] = 0
+        dist.barrier()
+        base = host.ctypes.data
+        rc = lib.rtb_host_register(C.c_void_p(base), 2 * frame_bytes)
+        assert rc == 0, lib.rtb_last_error()
+        dev_base = lib.rtb_host_device_pointer(C.c_void_p(base))
+        assert dev_base, lib.rtb_last_error()
+        frames = [host[0], host[1]]
+
+        def e2e_group():
+            vp.render(E2E_GROUP)
+            lib.rtb_join(ctx)
+            for i in range(E2E_GROUP):
+                k = e2e_count[0] & 1
+                e2e_count[0] += 1
+                rc = lib.rtb_scatter_shard(ctx, C.c_void_p(snap_addr[i]), 0, C.c_void_p(dev_base + k * frame_bytes))
                 assert rc == 0, lib.rtb_last_error()
 
     e2e_group()
@@ -268,6 +308,9 @@ def run_gpu(args):
         a = te.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
         b = te.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
         e2e_s, e2e_rays = float(a[0]), float(b[1])
+    if rank == 0:      # the host frame holds every shard's pixels
+        last = frames[(e2e_count[0] - 1) & 1]
+        assert np.isfinite(last).all() and last.mean() > 0 and (last.sum(axis=2) > 0).mean() > 0.99
 
     # ---- roofline of the dominant kernel (closest-hit traversal), measured live with CUDA events on its stream ---------
     roofline = None
@@ -282,7 +325,9 @@ def run_gpu(args):
             for k in tm:
                 tm[k] += getattr(pt, k)
         lib.rtb_set_profiling(ctx, 0)
-        # per-ray traversal work from an instrumented (counting) context on the same inputs
+        # per-ray traversal work from an instrumented (counting) context on the same inputs.  SURVEY section 8(d) defines the
+        # algorithmic bytes per ray "in the reference layout": 32 B per box test and 48 B per (padded) triangle test of the
+        # reference's walk over ITS binary tree - a counting context therefore walks that tree for shadow rays as well.
         vpc = make_viewport(flags=capi.RTB_FLAG_COUNT_TESTS)
         vpc.render(1)
         cc = vpc.counters()
@@ -293,6 +338,16 @@ def run_gpu(args):
         nts = cc["numShadowTriangleTests"] / max(1, cc["numShadowRays"])
         bytes_per_ray = 32 + 24 + 32 * nb + 48 * nt              # ray in + hit out + 32 B per box test + 48 B per (padded) triangle
         bytes_per_shadow_ray = 32 + 4 + 32 * nbs + 48 * nts
+        # what the shipped any-hit kernel itself fetches: 96-byte nodes of the 8-wide tree (rtb_wide.h), 48-byte triangles
+        os.environ["RTB_COUNT_WIDE"] = "1"
+        vpw = make_viewport(flags=capi.RTB_FLAG_COUNT_TESTS)
+        vpw.render(1)
+        cw = vpw.counters()
+        vpw.close()
+        del os.environ["RTB_COUNT_WIDE"]
+        wide_nodes = cw["numShadowBoxTests"] / 8.0 / max(1, cw["numShadowRays"])
+        wide_tris = cw["numShadowTriangleTests"] / max(1, cw["numShadowRays"])
+        own_bytes_per_shadow_ray = 32 + 4 + 96 * wide_nodes + 48 * wide_tris
         peak, peak_src = measured_peak()
         traffic = {}
         prof = os.path.join(ROOT, "profiles", "traverse_dram_bytes.json")
@@ -305,16 +360,22 @@ def run_gpu(args):
         def kernel_roofline(name, what, rays_n, ms, n_launches, bpr, box, tri):
             ach = rays_n * bpr / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             n_launches = max(1, n_launches)
+            per_ray = traffic.get(name + "_dram_bytes_per_ray")
             return {"bound": "hbm", "kernel": "%s (%s)" % (name, what), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic.get(name + "_dram_bytes_per_launch"), "peak_source": peak_src,
+                    # ncu dram__bytes per ray of the committed N=1 capture x the rays THIS run's launches carry
+                    "traffic": per_ray * rays_n / n_launches if per_ray is not None else None,
+                    "traffic_source": traffic.get("source"), "peak_source": peak_src,
                     "algorithmic_bytes_per_ray": bpr, "box_tests_per_ray": box, "tri_tests_per_ray": tri,
                     "rays_per_launch": rays_n / n_launches, "algorithmic_bytes_per_launch": rays_n * bpr / n_launches,
                     "ms_per_launch": ms / n_launches, "gray_per_s": rays_n / (ms * 1e-3) / 1e9 if ms > 0 else 0.0,
                     "share_of_pass": ms / tm["totalMs"] if tm["totalMs"] > 0 else 0.0}
 
-        # one k_shadow launch per k_traverse launch (one per depth and wavefront)
+        # one any-hit launch per k_traverse launch (one per depth and wavefront)
         r_trav = kernel_roofline("k_traverse", "closest-hit two-level BVH traversal", tm["traverseRays"], tm["traverseMs"], tm["traverseLaunches"], bytes_per_ray, nb, nt)
-        r_shad = kernel_roofline("k_shadow", "any-hit two-level BVH traversal of the light-sample rays", tm["shadowRays"], tm["shadowMs"], tm["traverseLaunches"], bytes_per_shadow_ray, nbs, nts)
+        r_shad = kernel_roofline("k_shadow", "any-hit traversal of the light-sample rays: k_shadow_wide on the 8-wide quantised tree; bytes per ray in the reference layout, SURVEY 8(d)",
+                                 tm["shadowRays"], tm["shadowMs"], tm["traverseLaunches"], bytes_per_shadow_ray, nbs, nts)
+        r_shad["own_layout"] = {"nodes_per_ray": wide_nodes, "tri_tests_per_ray": wide_tris, "bytes_per_ray": own_bytes_per_shadow_ray,
+                                "achieved": tm["shadowRays"] * own_bytes_per_shadow_ray / (tm["shadowMs"] * 1e-3) / 1e9 if tm["shadowMs"] > 0 else 0.0}
         # the dominant kernel is the one with the larger share of the pass; the other one rides along under its name
         roofline, other = (r_shad, r_trav) if r_shad["share_of_pass"] >= r_trav["share_of_pass"] else (r_trav, r_shad)
         roofline[other["kernel"].split(" ")[0]] = other
@@ -326,11 +387,18 @@ def run_gpu(args):
                                 "sample": "4 timed + 1 warm-up passes of %dx%d (full frames) of the same scene with the reference's AVX2 build on all host threads" % (WIDTH, HEIGHT),
                                 "msamples_per_s": meta["msamples_per_s"], "host_cores": os.cpu_count()}
 
-    if rank == 0:      # the frames are gathered on rank 0 only
-        assert np.isfinite(pinned[0].array).all() and pinned[0].array.mean() > 0
+    if world > 1:
+        lib.rtb_host_unregister(C.c_void_p(base))
+        del host, frames, last
     vp.close()
-    for im in pinned:
-        im.close()
+    if world == 1:
+        for im in pinned:
+            im.close()
+    else:
+        dist.barrier()
+        shm.close()
+        if rank == 0:
+            shm.unlink()
     if rank == 0:
         value = rays / seconds * 1e-6
         line = {
@@ -345,7 +413,7 @@ def run_gpu(args):
                     "h2d_bytes_per_step": DIMS * 4 + C.sizeof(capi.RtbPassDesc), "d2h_bytes_per_step": WIDTH * HEIGHT * 12,
                     "group": E2E_GROUP,
                     "api": ("raytracer_b200.host_api.Viewport.render(8) (ViewportB200::Render x 8, one call) with rtb_film_snapshots; the frame as of EVERY pass is copied into a page-locked host frame (rtb_unshard_film_async), synchronize at the end" if world == 1 else
-                            "Viewport.render(8) on every rank with rtb_film_snapshots; for EVERY pass: NCCL all-gather of the shard snapshots, rtb_unshard_film_async into rank 0's page-locked host frame; synchronize at the end")},
+                            "Viewport.render(8) on every rank with rtb_film_snapshots; for EVERY pass every rank writes its own pixels into ONE page-locked host frame in shared memory (rtb_scatter_shard, one PCIe link per rank, no collective); synchronize + barrier at the end")},
             "wall_s_timed_region": wall_s,
             "clocks": sampler.summary(),
             "roofline": roofline,
@@ -357,6 +425,132 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+
+# ---- BASELINE config 5: rough glass + caustics, 1024x1024, bidirectional path tracing (the reference's "VCM" renderer with
+#      vertex connection; merging needs every shard's photons and is a single-GPU feature here) ------------------------------
+C5_W = C5_H = 1024
+C5_PATH_LENGTH, C5_DIMS = 16, 256
+C5_WORKLOAD = ("rough-glass + caustics scene (tests/golden/scenes/caustics.json: glass block, rough-glass sphere, rough metal, area light), "
+               "1024x1024, VCM renderer: vertex connection (bidirectional path tracing) + vertex merging on one GPU, vertex connection only when sharded, "
+               "maxPathLength 16, 256 sampler dims")
+
+
+def run_c5(args):
+    import torch
+    from raytracer_b200 import capi, host_api
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+    lib = capi.load_library()
+    scn = os.path.join(ROOT, "tests", "golden", "scenes")
+    scene = host_api.Scene(os.path.join(scn, "caustics.json"), scn + "/")
+    merging = world == 1
+    vp = host_api.Viewport(scene, device=local_rank, num_shards=world, shard_index=rank, stream=stream.cuda_stream)
+    vp.set_renderer("VCM")
+    vp.set_params(dimensions=C5_DIMS, max_ray_depth=C5_PATH_LENGTH, strategy="all", seed=12345)
+    vp.set_vcm(connection=True, merging=merging, max_path_length=C5_PATH_LENGTH)
+    vp.resize(C5_W, C5_H)
+    ctx = vp.context()
+    if world > 1:
+        ident = torch.zeros(capi.RTB_COMM_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_ubyte * capi.RTB_COMM_ID_BYTES)(); assert lib.rtb_comm_unique_id(buf) == 0, lib.rtb_last_error()
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        ident = ident.cuda(); dist.broadcast(ident, 0)
+        assert lib.rtb_comm_init(ctx, bytes(ident.cpu().tolist())) == 0, lib.rtb_last_error()
+
+    def sync_all():
+        vp.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gathered = C.c_void_p()
+    vp.render(args.warmup); sync_all(); vp.reset()
+    c0 = vp.counters()
+    sampler = ClockSampler(local_rank); sampler.start(); sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    vp.render(args.steps)
+    lib.rtb_join(ctx)
+    assert lib.rtb_finish_frame(ctx, 0, C.byref(gathered)) == 0, lib.rtb_last_error()     # splat all-reduce + film all-gather when sharded
+    ev1.record()
+    sync_all()
+    sampler.stop_flag = True
+    c1 = vp.counters()
+    rays = (c1["numRays"] - c0["numRays"]) + (c1["numShadowRays"] - c0["numShadowRays"])
+    launches = c1["numKernelLaunches"] - c0["numKernelLaunches"]
+    dev_s = ev0.elapsed_time(ev1) * 1e-3
+    t = torch.tensor([dev_s, float(rays)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        a = t.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX); b = t.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        dev_s, rays = float(a[0]), float(b[1])
+    img = np.empty((C5_H, C5_W, 3), dtype=np.float32)
+    if rank == 0:
+        assert lib.rtb_unshard_film(ctx, gathered, img.ctypes.data) == 0, lib.rtb_last_error()
+        assert np.isfinite(img).all() and img.mean() > 0
+    # end to end: every 4 passes the frame goes to a page-locked host frame (single GPU: Viewport::GetSumBuffer; sharded:
+    # finish_frame + un-permute on rank 0)
+    vp.reset(); sync_all()
+    e2e_steps = max(4, (min(args.steps, 16) // 4) * 4)
+    pinned = capi.PinnedImage(C5_W, C5_H)
+    c0 = vp.counters()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps // 4):
+        vp.render(4)
+        lib.rtb_join(ctx)
+        if world > 1:
+            assert lib.rtb_finish_frame(ctx, 0, C.byref(gathered)) == 0, lib.rtb_last_error()
+            if rank == 0:
+                assert lib.rtb_unshard_film_async(ctx, gathered, C.c_void_p(pinned.ptr)) == 0, lib.rtb_last_error()
+        else:
+            assert lib.rtb_read_sum_async(ctx, C.c_void_p(pinned.ptr), 0) == 0, lib.rtb_last_error()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    c1 = vp.counters()
+    e2e_rays = (c1["numRays"] - c0["numRays"]) + (c1["numShadowRays"] - c0["numShadowRays"])
+    te = torch.tensor([e2e_s, float(e2e_rays)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        a = te.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX); b = te.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        e2e_s, e2e_rays = float(a[0]), float(b[1])
+    # algorithmic bytes of a VCM pass (stated in DESIGN.md): per path segment one ray in (32 B) + hit out (24 B) + the boxes and
+    # triangles of the reference's walk (this scene: analytic shapes, a handful of top-level nodes), per light vertex 160 B
+    # written and read once, per photon 48 B written, counted and gathered, per pixel 16 B pass colour + 24 B film
+    roofline = None
+    if rank == 0:
+        vpc = host_api.Viewport(scene, device=local_rank, flags=capi.RTB_FLAG_COUNT_TESTS)
+        vpc.set_renderer("Path Tracer MIS"); vpc.set_params(dimensions=C5_DIMS, max_ray_depth=8, strategy="all", seed=12345); vpc.resize(256, 256); vpc.render(1)
+        cc = vpc.counters(); vpc.close()
+        nb = (cc["numRayBoxTests"] + cc["numShadowBoxTests"]) / max(1, cc["numRays"] + cc["numShadowRays"])
+        b_ray = 32 + 24 + 32 * nb + 64
+        per_pass_rays = rays / max(1, args.steps)
+        per_pass_bytes = per_pass_rays * b_ray + C5_W * C5_H * (40 + 2 * 160 * 3 + 48 * 3)
+        peak, peak_src = measured_peak()
+        ach = per_pass_bytes * args.steps / dev_s / 1e9
+        roofline = {"bound": "hbm", "kernel": "VCM pass (k_vcm_light + k_vcm_camera + hash grid), timed as a whole", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_ray": b_ray, "box_tests_per_ray": nb,
+                    "note": "one thread per sub-path: latency / divergence bound, not HBM bound; analytic-shape scene with ~%.0f box tests per ray" % nb}
+    vp.close(); pinned.close()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "Mray/s", "value": rays / dev_s * 1e-6, "unit": "Mray/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * dev_s / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": C5_WORKLOAD, "step": "one VCM pass (one light sub-path + one camera path per pixel) of the 1024x1024 frame", "parallelism": "tiles32x32-interleaved x%d" % world,
+                       "l2": "light vertices (1.7 GB) and photons round-trip through HBM every pass; the scene itself is a few KB"},
+            "msamples_per_s": C5_W * C5_H * args.steps / dev_s * 1e-6, "gpu_launches": launches,
+            "e2e": {"value": e2e_rays / e2e_s * 1e-6, "unit": "Mray/s", "steps": e2e_steps, "h2d_bytes_per_step": C5_DIMS * 4 + C.sizeof(capi.RtbPassDesc), "d2h_bytes_per_step": C5_W * C5_H * 12 // 4,
+                    "api": "Viewport.render(4) then the frame into a page-locked host frame (rtb_read_sum_async / rtb_finish_frame + rtb_unshard_film_async)"},
+            "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": None}))
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -364,11 +558,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c3", choices=["c3", "c5"], help="c3: the headline 1080p sponza-class MIS benchmark (default); c5: BASELINE config 5, bidirectional / VCM on the caustics scene")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "c5":
+        run_c5(args)
     else:
         run_gpu(args)
 

@@ -379,6 +379,32 @@ int  rtb_unshard_film(RtbContext* ctx, const void* gatheredDevice, float* hostRg
  * read-backs are in flight (the thirteenth waits for the first).  The host buffer should be page-locked (rtb_host_alloc). */
 int  rtb_read_sum_async(RtbContext* ctx, float* rgb, int which);
 int  rtb_unshard_film_async(RtbContext* ctx, const void* gatheredDevice, float* hostRgb);
+/* ---- multi-GPU frames (the reference renders its tiles on a thread pool, Viewport.cpp:216-268) -------
+ * Every shard context owns tile t % numShards of the frame.  Two ways to put a frame together:
+ *
+ * (1) host-destined frames: rtb_scatter_shard writes THIS shard's pixels of the film (or of a film snapshot / any buffer in
+ *     the layout of rtb_film_device_buffer) into a raster frame `rasterDst` - device memory, or page-locked host memory that
+ *     is mapped into this device (rtb_host_alloc / rtb_host_register; pass the pointer rtb_host_device_pointer returns).
+ *     All shards write into the same frame, each over its own PCIe link, no collective and no funnel through one GPU.
+ *     Stream ordered; complete after rtb_synchronize.
+ * (2) device-resident frames: rtb_comm_init gives the context an NCCL communicator (the library loads libnccl.so.2 at that
+ *     point; one rank per shard, rank = shardIndex), rtb_finish_frame all-gathers the shard films once per frame on the
+ *     context's stream and returns the gathered buffer (numShards * shardFloats) that rtb_unshard_film / rtb_read_front /
+ *     rtb_block_errors accept.  For VCM it first all-reduces the splat buffers and folds them into the film.
+ *     rtb_comm_init_all is the single-process flavour (ncclCommInitAll over the contexts' devices). */
+int  rtb_scatter_shard(RtbContext* ctx, const void* shardFilmDevice /* NULL: own film */, int which, void* rasterDst);
+#define RTB_COMM_ID_BYTES 128
+int  rtb_comm_unique_id(void* outId /* RTB_COMM_ID_BYTES */);                                   /* ncclGetUniqueId: rank 0 calls it and hands the bytes to the others */
+int  rtb_comm_init(RtbContext* ctx, const void* id /* RTB_COMM_ID_BYTES */);                  /* ncclCommInitRank(numShards, id, shardIndex) */
+int  rtb_comm_init_all(RtbContext** ctxs, uint32_t count);                                    /* one process, `count` = numShards contexts on different devices */
+int  rtb_finish_frame(RtbContext* ctx, int which, void** outGatheredDevice);
+int  rtb_finish_frame_all(RtbContext** ctxs, uint32_t count, int which, void** outGatheredDevice);   /* after rtb_comm_init_all: all contexts' collectives in one NCCL group */
+/* host memory the devices can write into directly: rtb_host_alloc'ed memory is mapped already; rtb_host_register pins and
+ * maps memory the caller owns (e.g. a shared-memory segment several rank processes attach to) */
+int  rtb_host_register(void* p, uint64_t bytes);
+int  rtb_host_unregister(void* p);
+void* rtb_host_device_pointer(void* p);
+
 /* page-locked host memory for the rgb / hostRgb arguments above (the reference's Viewport owns its sum Bitmap,
  * Viewport.h:121; an adapter that wants full-speed read-back allocates that bitmap here).  Any host pointer works,
  * pinned ones copy at PCIe rate.  NULL on failure (rtb_last_error). */

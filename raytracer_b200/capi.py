@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("RTB200_LIB", os.path.join(_HERE, "librtb200.so"))   #
 RTB_INVALID_OBJECT = 0xFFFFFFFF
 RTB_LIGHT_OBJECT = 0xFFFFFFFE
 RTB_RENDERER_PATH_TRACER, RTB_RENDERER_PATH_TRACER_MIS, RTB_RENDERER_DEBUG, RTB_RENDERER_VCM = 0, 1, 2, 3
+RTB_COMM_ID_BYTES = 128
 RTB_TRACE_CLOSEST, RTB_TRACE_SHADOW = 0, 1
 RTB_LIGHT_SAMPLING_SINGLE, RTB_LIGHT_SAMPLING_ALL = 0, 1
 RTB_FLAG_COUNT_TESTS = 1
@@ -154,6 +155,8 @@ EXPORTED_SYMBOLS = [
     "rtb_resize", "rtb_reset", "rtb_render_pass", "rtb_render_passes", "rtb_synchronize", "rtb_join", "rtb_read_sum", "rtb_film_device_buffer", "rtb_film_snapshots",
     "rtb_unshard_film", "rtb_read_sum_async", "rtb_unshard_film_async", "rtb_host_alloc", "rtb_host_free", "rtb_get_counters", "rtb_trace_batch", "rtb_trace_batch_device", "rtb_texture_batch", "rtb_sample_batch",
     "rtb_set_vcm_params", "rtb_vcm_splat_buffers", "rtb_vcm_fold_splats",
+    "rtb_scatter_shard", "rtb_comm_unique_id", "rtb_comm_init", "rtb_comm_init_all", "rtb_finish_frame", "rtb_finish_frame_all",
+    "rtb_host_register", "rtb_host_unregister", "rtb_host_device_pointer",
     "rtb_primary_rays", "rtb_set_profiling", "rtb_get_pass_timings", "rtb_read_front", "rtb_block_errors", "rtb_set_active_tiles",
 ]
 
@@ -210,6 +213,16 @@ def load_library(path=None):
     lib.rtb_set_vcm_params.argtypes = [C.c_void_p, C.POINTER(RtbVcmParams)]
     lib.rtb_vcm_splat_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.rtb_vcm_fold_splats.argtypes = [C.c_void_p]
+    lib.rtb_scatter_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.rtb_comm_unique_id.argtypes = [C.c_void_p]
+    lib.rtb_comm_init.argtypes = [C.c_void_p, C.c_char_p]
+    lib.rtb_comm_init_all.argtypes = [C.POINTER(C.c_void_p), C.c_uint32]
+    lib.rtb_finish_frame.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.rtb_finish_frame_all.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
+    lib.rtb_host_register.argtypes = [C.c_void_p, C.c_uint64]
+    lib.rtb_host_unregister.argtypes = [C.c_void_p]
+    lib.rtb_host_device_pointer.argtypes = [C.c_void_p]
+    lib.rtb_host_device_pointer.restype = C.c_void_p
     lib.rtb_get_pass_timings.argtypes = [C.c_void_p, C.POINTER(RtbPassTimings)]
     if path is None:
         _lib = lib

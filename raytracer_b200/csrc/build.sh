@@ -7,5 +7,5 @@ OUT="${RTB_OUT:-$HERE/../librtb200.so}"
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
      --fmad=false -ftz=true -prec-div=true -prec-sqrt=true \
      -Xptxas -v -shared -Xcompiler -fPIC -Xcompiler -O2 \
-     -o "$OUT" "$HERE/rtb_kernels.cu" "$@"
+     -o "$OUT" "$HERE/rtb_kernels.cu" -ldl "$@"
 echo "built $OUT"

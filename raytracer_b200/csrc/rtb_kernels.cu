@@ -17,6 +17,8 @@
 // that vertex, then the next vertex ...) because shade(d) -> shadow(d) -> shade(d+1) are ordered and every pixel
 // has exactly one path per pass.
 #include <cuda_runtime.h>
+#include <nccl.h>          // types only: the library is loaded with dlopen when a context asks for a communicator
+#include <dlfcn.h>
 #include <cstdio>
 #include <cstdarg>
 #include <new>
@@ -445,7 +447,8 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
 #define RTB_SW_MINBLOCKS 2
 #endif
 #ifndef RTB_SW_REFILL
-#define RTB_SW_REFILL 0     // the wide phase is left for a refill when fewer than this many lanes of the warp are still inside a mesh
+#define RTB_SW_REFILL 20    // the wide phase is left for a refill when fewer than this many lanes of the warp are still inside a mesh
+                            // (k_shadow_wide per 8 bench passes, 384 x 2: never 35.4 / 36.4 / 34.1 / 36.3 ms, 20: 34.1 / 34.1 / 34.3 / 35.6)
 #endif
 
 struct WideFetchHot
@@ -748,6 +751,18 @@ __global__ void __launch_bounds__(256) k_unshard(const float* __restrict__ src, 
     }
 }
 
+// one shard's pixel slots -> their places in a raster frame the caller owns (device memory or mapped host memory: the 8 x 4
+// pixel blocks of the slot order make every warp write four runs of 96 contiguous bytes)
+__global__ void __launch_bounds__(256) k_scatter_shard(const float* __restrict__ src, float* dstRaster, const uint32_t* __restrict__ pixelList, uint32_t numPixels)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < numPixels; i += stride)
+    {
+        const size_t o = (size_t)pixelList[i] * 3;
+        dstRaster[o] = src[(size_t)i * 3]; dstRaster[o + 1] = src[(size_t)i * 3 + 1]; dstRaster[o + 2] = src[(size_t)i * 3 + 2];
+    }
+}
+
 // front buffer (Viewport::PostProcessTile): pixel slots -> tone-mapped 0x00RRGGBB in raster order; `blurred` (the
 // RTB_BLOOM_LEVELS blurred raster images back to back) is only read when P.bloomFactor > 0; `frozenRaster` (optional):
 // per raster pixel, the pass count at which adaptive rendering dropped it (0 = still sampled)
@@ -1043,6 +1058,10 @@ struct RtbContext
     RtbCounters counters;
     uint32_t passesSinceReset = 0;
 
+    // multi-GPU frames (rtb_comm_init / rtb_finish_frame)
+    ncclComm_t comm = nullptr;
+    DevArray<float> gathered;             // numShards x shardSlots x 3: the all-gathered films
+
     // "VCM" renderer (rtb_vcm.cuh): buffers are allocated by the first VCM pass after a resize / parameter change
     struct Vcm
     {
@@ -1256,6 +1275,9 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
     c->serializeSlots = getenv("RTB_SERIALIZE_SLOTS") != nullptr;
     c->profileDepths = getenv("RTB_PROFILE_DEPTHS") != nullptr;
     c->noWide = getenv("RTB_NO_WIDE") != nullptr;
+    // an instrumented context counts the REFERENCE's work per ray (box / triangle tests of its binary tree: the algorithmic
+    // bytes of SURVEY 8(d)); RTB_COUNT_WIDE makes it count what the 8-wide walk does instead (8 "box tests" per node visited)
+    if ((c->flags & RTB_FLAG_COUNT_TESTS) != 0 && !getenv("RTB_COUNT_WIDE")) c->noWide = true;
     if (const char* t = getenv("RTB_SHADOW_KERNEL")) c->wideKernel = strcmp(t, "simple") != 0;
     if (const char* t = getenv("RTB_HOT_NODES")) c->hotOverride = atoi(t);
     c->slots.resize(numSlots);
@@ -1278,6 +1300,8 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
     return RTB_OK;
 }
 
+static void release_comm(RtbContext* c);
+
 void rtb_destroy(RtbContext* c)
 {
     if (!c) return;
@@ -1286,7 +1310,8 @@ void rtb_destroy(RtbContext* c)
     for (RtbContext::Slot& t : c->slots) if (t.stream) cudaStreamSynchronize(t.stream);
     free_scene(c);
     free_film(c);
-    c->blueNoise.release(); c->totals.release(); c->seed.release();
+    c->blueNoise.release(); c->totals.release(); c->seed.release(); c->gathered.release();
+    release_comm(c);
     for (RtbContext::Slot& t : c->slots)
     {
         t.ctl.release(); t.seed.release();
@@ -2022,7 +2047,7 @@ int rtb_unshard_film_async(RtbContext* c, const void* gatheredDevice, float* hos
 void* rtb_host_alloc(uint64_t bytes)
 {
     void* p = nullptr;
-    const cudaError_t e = cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable);
+    const cudaError_t e = cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable | cudaHostAllocMapped);
     if (e != cudaSuccess) { fail(RTB_ERR_CUDA, "rtb_host_alloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e)); return nullptr; }
     return p;
 }
@@ -2353,6 +2378,217 @@ int rtb_primary_rays(RtbContext* c, const RtbPassDesc* pass, RtbRay* rays)
     cudaFree(d);
     if (e != cudaSuccess) return fail(RTB_ERR_CUDA, "primary rays failed: %s", cudaGetErrorString(e));
     return RTB_OK;
+}
+
+// ---- NCCL, loaded on demand (a single-GPU user of this library never needs it) ------------------------------------------------
+struct NcclApi
+{
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+};
+
+static NcclApi* nccl_api()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, []()
+    {
+        // a process that already has an NCCL (e.g. the one PyTorch ships) gets that one back
+        api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.lib) { api.error = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+        bool ok = true;
+        auto sym = [&](const char* name) { void* p = dlsym(api.lib, name); if (!p) { ok = false; api.error = std::string("libnccl has no ") + name; } return p; };
+        api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+        api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
+        api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+        api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+        api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+        api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+        api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+        if (!ok) { dlclose(api.lib); api.lib = nullptr; }
+    });
+    return api.lib ? &api : nullptr;
+}
+
+static void release_comm(RtbContext* c)
+{
+    if (!c->comm) return;
+    if (NcclApi* n = nccl_api()) n->CommDestroy(c->comm);
+    c->comm = nullptr;
+}
+
+#define RTB_NCCL(api, call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(RTB_ERR_CUDA, "%s failed: %s", #call, (api)->GetErrorString(r_)); } while (0)
+
+int rtb_comm_unique_id(void* outId)
+{
+    if (!outId) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    NcclApi* n = nccl_api();
+    if (!n) return fail(RTB_ERR_UNSUPPORTED, "NCCL is not available: %s", nccl_api() ? "" : "libnccl.so.2 could not be loaded");
+    static_assert(sizeof(ncclUniqueId) == RTB_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    RTB_NCCL(n, n->GetUniqueId(&id));
+    memcpy(outId, &id, sizeof(id));
+    return RTB_OK;
+}
+
+int rtb_comm_init(RtbContext* c, const void* idBytes)
+{
+    if (!c || !idBytes) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    NcclApi* n = nccl_api();
+    if (!n) return fail(RTB_ERR_UNSUPPORTED, "NCCL is not available (libnccl.so.2 could not be loaded)");
+    if (c->comm) return fail(RTB_ERR_INVALID_ARG, "the context already has a communicator");
+    RTB_CUDA(cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(&id, idBytes, sizeof(id));
+    RTB_NCCL(n, n->CommInitRank(&c->comm, (int)c->numShards, id, (int)c->shardIndex));
+    return RTB_OK;
+}
+
+int rtb_comm_init_all(RtbContext** ctxs, uint32_t count)
+{
+    if (!ctxs || count == 0) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    NcclApi* n = nccl_api();
+    if (!n) return fail(RTB_ERR_UNSUPPORTED, "NCCL is not available (libnccl.so.2 could not be loaded)");
+    std::vector<int> devices(count);
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        if (!ctxs[i] || ctxs[i]->numShards != count || ctxs[i]->shardIndex != i) return fail(RTB_ERR_INVALID_ARG, "rtb_comm_init_all: context %u must be shard %u of %u", i, i, count);
+        if (ctxs[i]->comm) return fail(RTB_ERR_INVALID_ARG, "context %u already has a communicator", i);
+        devices[i] = ctxs[i]->device;
+        for (uint32_t k = 0; k < i; ++k) if (devices[k] == devices[i]) return fail(RTB_ERR_INVALID_ARG, "rtb_comm_init_all: contexts %u and %u share device %d", k, i, devices[i]);
+    }
+    std::vector<ncclComm_t> comms(count);
+    RTB_NCCL(n, n->CommInitAll(comms.data(), (int)count, devices.data()));
+    for (uint32_t i = 0; i < count; ++i) ctxs[i]->comm = comms[i];
+    return RTB_OK;
+}
+
+int rtb_finish_frame(RtbContext* c, int which, void** outGatheredDevice)
+{
+    if (!c || !outGatheredDevice) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    if (!c->sum.ptr) return fail(RTB_ERR_INVALID_ARG, "viewport has no size");
+    RTB_CUDA(cudaSetDevice(c->device));
+    RTB_CUDA(join_slots(c));
+    const size_t shardFloats = (size_t)c->shardSlots * 3;
+    if (c->numShards == 1)
+    {
+        int rc = vcm_fold(c);
+        if (rc != RTB_OK) return rc;
+        *outGatheredDevice = which == 0 ? c->sum.ptr : c->sum2.ptr;
+        return RTB_OK;
+    }
+    if (!c->comm) return fail(RTB_ERR_INVALID_ARG, "rtb_finish_frame: the context has no communicator (rtb_comm_init)");
+    NcclApi* n = nccl_api();
+    if (c->vcm.allocated && c->vcm.splatsPending)
+    {
+        // the camera connections of every shard's light paths, summed once per frame, then this shard's pixels into its film
+        RTB_NCCL(n, n->GroupStart());
+        RTB_NCCL(n, n->AllReduce(c->vcm.splat.ptr, c->vcm.splat.ptr, c->vcm.splat.count, ncclFloat, ncclSum, c->comm, c->stream));
+        RTB_NCCL(n, n->AllReduce(c->vcm.splat2.ptr, c->vcm.splat2.ptr, c->vcm.splat2.count, ncclFloat, ncclSum, c->comm, c->stream));
+        RTB_NCCL(n, n->GroupEnd());
+        int rc = vcm_fold(c);
+        if (rc != RTB_OK) return rc;
+    }
+    if (c->gathered.count != shardFloats * c->numShards) RTB_CUDA(c->gathered.alloc(shardFloats * c->numShards));
+    RTB_NCCL(n, n->AllGather(which == 0 ? c->sum.ptr : c->sum2.ptr, c->gathered.ptr, shardFloats, ncclFloat, c->comm, c->stream));
+    *outGatheredDevice = c->gathered.ptr;
+    return RTB_OK;
+}
+
+// single process, one thread driving every device: the collectives of all contexts inside ONE NCCL group
+int rtb_finish_frame_all(RtbContext** ctxs, uint32_t count, int which, void** outGatheredDevice)
+{
+    if (!ctxs || !outGatheredDevice || count == 0) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    if (count == 1) return rtb_finish_frame(ctxs[0], which, outGatheredDevice);
+    NcclApi* n = nccl_api();
+    if (!n) return fail(RTB_ERR_UNSUPPORTED, "NCCL is not available (libnccl.so.2 could not be loaded)");
+    bool splats = false;
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        RtbContext* c = ctxs[i];
+        if (!c || !c->comm || c->numShards != count || !c->sum.ptr) return fail(RTB_ERR_INVALID_ARG, "rtb_finish_frame_all: context %u is not a sized shard with a communicator", i);
+        RTB_CUDA(cudaSetDevice(c->device));
+        RTB_CUDA(join_slots(c));
+        splats = splats || (c->vcm.allocated && c->vcm.splatsPending);
+        const size_t total = (size_t)c->shardSlots * 3 * c->numShards;
+        if (c->gathered.count != total) RTB_CUDA(c->gathered.alloc(total));
+    }
+    if (splats)
+    {
+        RTB_NCCL(n, n->GroupStart());
+        for (uint32_t i = 0; i < count; ++i)
+        {
+            RtbContext* c = ctxs[i];
+            if (!c->vcm.allocated) { n->GroupEnd(); return fail(RTB_ERR_INVALID_ARG, "rtb_finish_frame_all: context %u has rendered no VCM pass while others have", i); }
+            RTB_NCCL(n, n->AllReduce(c->vcm.splat.ptr, c->vcm.splat.ptr, c->vcm.splat.count, ncclFloat, ncclSum, c->comm, c->stream));
+            RTB_NCCL(n, n->AllReduce(c->vcm.splat2.ptr, c->vcm.splat2.ptr, c->vcm.splat2.count, ncclFloat, ncclSum, c->comm, c->stream));
+        }
+        RTB_NCCL(n, n->GroupEnd());
+        for (uint32_t i = 0; i < count; ++i)
+        {
+            RTB_CUDA(cudaSetDevice(ctxs[i]->device));
+            ctxs[i]->vcm.splatsPending = true;
+            int rc = vcm_fold(ctxs[i]);
+            if (rc != RTB_OK) return rc;
+        }
+    }
+    RTB_NCCL(n, n->GroupStart());
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        RtbContext* c = ctxs[i];
+        RTB_NCCL(n, n->AllGather(which == 0 ? c->sum.ptr : c->sum2.ptr, c->gathered.ptr, (size_t)c->shardSlots * 3, ncclFloat, c->comm, c->stream));
+        outGatheredDevice[i] = c->gathered.ptr;
+    }
+    RTB_NCCL(n, n->GroupEnd());
+    return RTB_OK;
+}
+
+int rtb_scatter_shard(RtbContext* c, const void* shardFilmDevice, int which, void* rasterDst)
+{
+    if (!c || !rasterDst) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    if (!c->sum.ptr) return fail(RTB_ERR_INVALID_ARG, "viewport has no size");
+    RTB_CUDA(cudaSetDevice(c->device));
+    RTB_CUDA(join_slots(c));
+    if (!shardFilmDevice && c->numShards == 1) { int rc = vcm_fold(c); if (rc != RTB_OK) return rc; }
+    const float* src = shardFilmDevice ? (const float*)shardFilmDevice : (which == 0 ? c->sum.ptr : c->sum2.ptr);
+    k_scatter_shard<<<c->numSMs * 4, 256, 0, c->stream>>>(src, (float*)rasterDst, c->pixelList.ptr, c->numPixels);
+    RTB_CUDA(cudaGetLastError());
+    c->counters.numKernelLaunches++;
+    return RTB_OK;
+}
+
+int rtb_host_register(void* p, uint64_t bytes)
+{
+    if (!p || !bytes) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    RTB_CUDA(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return RTB_OK;
+}
+
+int rtb_host_unregister(void* p)
+{
+    if (!p) return fail(RTB_ERR_INVALID_ARG, "null argument");
+    RTB_CUDA(cudaHostUnregister(p));
+    return RTB_OK;
+}
+
+void* rtb_host_device_pointer(void* p)
+{
+    void* d = nullptr;
+    const cudaError_t e = cudaHostGetDevicePointer(&d, p, 0);
+    if (e != cudaSuccess) { fail(RTB_ERR_CUDA, "cudaHostGetDevicePointer: %s", cudaGetErrorString(e)); return nullptr; }
+    return d;
 }
 
 int rtb_set_vcm_params(RtbContext* c, const RtbVcmParams* params)

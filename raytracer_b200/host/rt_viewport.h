@@ -617,4 +617,118 @@ private:
     std::string mError;
 };
 
+// One frame on several GPUs of one box from ONE process (the reference spreads its tiles over a thread pool,
+// Viewport.cpp:216-268; here tile t goes to device t % N): N ViewportB200 objects, one per device, each rendering its
+// shard of every pass.  Every member viewport draws the same pass script from the same seed, so the N-GPU film is the
+// one-GPU film bit for bit.  Frames for the host are assembled by every device writing its own pixels straight into one
+// page-locked frame (rtb_scatter_shard: N PCIe links, no collective); device-resident frames (FinishFrame) by one NCCL
+// all-gather per frame inside the library (rtb_comm_init_all / rtb_finish_frame).
+class ViewportGroupB200
+{
+public:
+    ~ViewportGroupB200() { Release(); }
+    const std::string& GetLastError() const { return mError; }
+    uint32_t GetNumDevices() const { return (uint32_t)mViewports.size(); }
+    ViewportB200& GetViewport(uint32_t i) { return *mViewports[i]; }
+
+    bool Create(const std::vector<int>& deviceIds, uint32_t flags, const std::string& blueNoisePath)
+    {
+        Release();
+        if (deviceIds.empty()) { mError = "no devices"; return false; }
+        for (size_t i = 0; i < deviceIds.size(); ++i)
+        {
+            mViewports.push_back(new ViewportB200());
+            if (!mViewports.back()->Create(deviceIds[i], (uint32_t)deviceIds.size(), (uint32_t)i, flags, blueNoisePath)) return Fail(i);
+        }
+        return true;
+    }
+    bool SetScene(const Scene& scene, const Camera* camera = nullptr) { return All([&](ViewportB200& v) { return v.SetScene(scene, camera); }); }
+    bool SetRenderer(const std::string& name) { return All([&](ViewportB200& v) { return v.SetRenderer(name); }); }
+    bool SetRenderingParams(const RenderingParams& p) { return All([&](ViewportB200& v) { return v.SetRenderingParams(p); }); }
+    void SetSeed(uint64_t seed) { for (ViewportB200* v : mViewports) v->SetSeed(seed); }
+    bool Resize(uint32_t width, uint32_t height)
+    {
+        FreeFrame();
+        mWidth = width; mHeight = height;
+        return All([&](ViewportB200& v) { return v.Resize(width, height); });
+    }
+    void Reset() { for (ViewportB200* v : mViewports) v->Reset(); }
+    // every device gets its passes enqueued before any is waited for: the launches are asynchronous
+    bool RenderPasses(const Camera& camera, uint32_t count) { return All([&](ViewportB200& v) { return v.RenderPasses(camera, count); }); }
+    bool Synchronize() { return All([&](ViewportB200& v) { return v.Synchronize(); }); }
+
+    // Viewport::GetSumBuffer for the whole frame
+    bool GetSumBuffer(float* rgb, int which = 0)
+    {
+        const size_t bytes = (size_t)mWidth * mHeight * 3 * sizeof(float);
+        if (!mFrame)
+        {
+            mFrame = static_cast<float*>(rtb_host_alloc(bytes));
+            if (!mFrame) { mError = rtb_last_error(); return false; }
+        }
+        void* deviceView = rtb_host_device_pointer(mFrame);
+        if (!deviceView) { mError = rtb_last_error(); return false; }
+        for (size_t i = 0; i < mViewports.size(); ++i)
+            if (rtb_scatter_shard(mViewports[i]->GetContext(), nullptr, which, deviceView) != RTB_OK) { mError = rtb_last_error(); return false; }
+        if (!Synchronize()) return false;
+        memcpy(rgb, mFrame, bytes);
+        return true;
+    }
+
+    // the all-gathered film on every device (NCCL inside the library); `outGathered[i]` is device i's copy
+    bool FinishFrame(std::vector<void*>& outGathered, int which = 0)
+    {
+        if (!mHaveComm && mViewports.size() > 1)
+        {
+            std::vector<RtbContext*> ctxs;
+            for (ViewportB200* v : mViewports) ctxs.push_back(v->GetContext());
+            if (rtb_comm_init_all(ctxs.data(), (uint32_t)ctxs.size()) != RTB_OK) { mError = rtb_last_error(); return false; }
+            mHaveComm = true;
+        }
+        outGathered.assign(mViewports.size(), nullptr);
+        // (one thread drives all devices: their collectives go into one NCCL group inside rtb_finish_frame_all)
+        std::vector<RtbContext*> ctxs;
+        for (ViewportB200* v : mViewports) ctxs.push_back(v->GetContext());
+        if (rtb_finish_frame_all(ctxs.data(), (uint32_t)ctxs.size(), which, outGathered.data()) != RTB_OK) { mError = rtb_last_error(); return false; }
+        return true;
+    }
+
+    bool GetCounters(RtbCounters& total)
+    {
+        memset(&total, 0, sizeof(total));
+        for (ViewportB200* v : mViewports)
+        {
+            RtbCounters c;
+            if (!v->GetCounters(c)) { mError = v->GetLastError(); return false; }
+            total.numRays += c.numRays; total.numShadowRays += c.numShadowRays; total.numShadowRaysHit += c.numShadowRaysHit;
+            total.numPrimaryRays += c.numPrimaryRays; total.numKernelLaunches += c.numKernelLaunches;
+            total.numRayBoxTests += c.numRayBoxTests; total.numRayTriangleTests += c.numRayTriangleTests;
+            total.numShadowBoxTests += c.numShadowBoxTests; total.numShadowTriangleTests += c.numShadowTriangleTests;
+        }
+        return true;
+    }
+
+private:
+    template <typename F> bool All(F f)
+    {
+        for (size_t i = 0; i < mViewports.size(); ++i) if (!f(*mViewports[i])) return Fail(i);
+        return true;
+    }
+    bool Fail(size_t i) { mError = "device " + std::to_string(i) + ": " + mViewports[i]->GetLastError(); return false; }
+    void FreeFrame() { if (mFrame) rtb_host_free(mFrame); mFrame = nullptr; }
+    void Release()
+    {
+        FreeFrame();
+        for (ViewportB200* v : mViewports) delete v;
+        mViewports.clear();
+        mHaveComm = false;
+    }
+
+    std::vector<ViewportB200*> mViewports;
+    std::string mError;
+    uint32_t mWidth = 0, mHeight = 0;
+    float* mFrame = nullptr;
+    bool mHaveComm = false;
+};
+
 } // namespace rt

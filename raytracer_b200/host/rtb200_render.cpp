@@ -3,6 +3,7 @@
 //
 //   rtb200_render -s scene.json --data DIR -w 1920 -h 1080 --spp 64 --renderer "Path Tracer MIS" --depth 8
 //                 --dims 128 --strategy all --seed 12345 --device 0 --out sum.f32 [--flat scene.rtb]
+//                 [--gpus N [--check-gather 1]]      tiles over N devices of this box from this one process
 //                 [--front image.bmp --exposure E --contrast C --saturation S --dither D --bloom B --tonemapper 0..3]
 //                 [--adaptive 1 --adaptive-initial 10 --adaptive-min-block 4 --adaptive-max-block 256
 //                  --adaptive-subdivision 0.005 --adaptive-convergence 0.0001]      AdaptiveRenderingSettings, Context.h:35-43
@@ -50,6 +51,58 @@ int main(int argc, char** argv)
         flat.fieldOfView = camera.mFieldOfView;
         if (!flat.Save(a["--flat"])) { fprintf(stderr, "[ERROR] cannot write %s\n", a["--flat"].c_str()); return 1; }
         if (spp == 0) return 0;
+    }
+    const int numGpus = atoi(get("--gpus", "1").c_str());
+    if (numGpus > 1)
+    {
+        // the frame's tiles over several devices of this box (tile t -> device t % N), one process
+        std::vector<int> devices;
+        for (int i = 0; i < numGpus; ++i) devices.push_back(atoi(get("--device", "0").c_str()) + i);
+        rt::ViewportGroupB200 group;
+        rt::RenderingParams p;
+        p.maxRayDepth = atoi(get("--depth", "8").c_str());
+        p.dimensions = atoi(get("--dims", "128").c_str());
+        p.lightSamplingStrategy = get("--strategy", "all") == "single" ? RTB_LIGHT_SAMPLING_SINGLE : RTB_LIGHT_SAMPLING_ALL;
+        auto bail = [&]() { fprintf(stderr, "[ERROR] %s\n", group.GetLastError().c_str()); return 1; };
+        if (!group.Create(devices, 0, get("--bluenoise", ""))) return bail();
+        if (!group.SetScene(scene, &camera)) return bail();
+        group.SetRenderingParams(p);
+        group.SetSeed(strtoull(get("--seed", "12345").c_str(), nullptr, 10));
+        if (!group.SetRenderer(get("--renderer", "Path Tracer MIS"))) return bail();
+        if (!group.Resize(w, h)) return bail();
+        const auto t0 = std::chrono::steady_clock::now();
+        if (!group.RenderPasses(camera, spp)) return bail();
+        if (!group.Synchronize()) return bail();
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        RtbCounters c;
+        if (!group.GetCounters(c)) return bail();
+        std::vector<float> img((size_t)w * h * 3);
+        if (!group.GetSumBuffer(img.data())) return bail();
+        if (atoi(get("--check-gather", "0").c_str()))
+        {
+            // the same frame through the library's NCCL all-gather: every device ends up with the whole film
+            std::vector<void*> gathered;
+            if (!group.FinishFrame(gathered)) return bail();
+            for (int i = 0; i < numGpus; ++i)
+            {
+                std::vector<float> viaNccl((size_t)w * h * 3);
+                if (rtb_unshard_film(group.GetViewport(i).GetContext(), gathered[i], viaNccl.data()) != RTB_OK) { fprintf(stderr, "[ERROR] %s\n", rtb_last_error()); return 1; }
+                if (memcmp(viaNccl.data(), img.data(), img.size() * sizeof(float)) != 0) { fprintf(stderr, "[ERROR] device %d: the all-gathered film differs from the scattered frame\n", i); return 1; }
+            }
+            fprintf(stderr, "all-gathered film on %d devices == scattered host frame\n", numGpus);
+        }
+        printf("{\"width\": %u, \"height\": %u, \"passes\": %u, \"gpus\": %d, \"seconds\": %.6f, \"numPrimaryRays\": %llu, \"numRays\": %llu, \"numShadowRays\": %llu, "
+               "\"numShadowRaysHit\": %llu, \"mrays_per_s\": %.3f, \"msamples_per_s\": %.3f}\n", w, h, spp, numGpus, s,
+               (unsigned long long)c.numPrimaryRays, (unsigned long long)c.numRays, (unsigned long long)c.numShadowRays, (unsigned long long)c.numShadowRaysHit,
+               (c.numRays + c.numShadowRays) / s * 1e-6, c.numPrimaryRays / s * 1e-6);
+        if (a.count("--out"))
+        {
+            FILE* f = fopen(a["--out"].c_str(), "wb");
+            if (!f) { fprintf(stderr, "[ERROR] cannot write %s\n", a["--out"].c_str()); return 1; }
+            fwrite(img.data(), 4, img.size(), f);
+            fclose(f);
+        }
+        return 0;
     }
     rt::ViewportB200 vp;
     if (!vp.Create(atoi(get("--device", "0").c_str()), 1, 0, 0, get("--bluenoise", ""))) { fprintf(stderr, "[ERROR] %s\n", vp.GetLastError().c_str()); return 1; }

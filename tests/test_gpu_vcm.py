@@ -60,9 +60,10 @@ def test_vcm_statistics_against_the_live_reference(tmp_path, scene, passes, conn
     m2a, m2b = ref2.mean(axis=(0, 1)), got2.mean(axis=(0, 1))
     assert (np.abs(m2a - m2b) <= 2.0 * mean_tolerance * m2a).all(), (m2a, m2b)
     assert counters["numPrimaryRays"] == w * h * passes
-    # ray counts: light + camera sub-paths; the reference counts the same events (statistical: different random numbers)
-    assert abs(counters["numRays"] - meta["numRays"]) <= 0.02 * meta["numRays"], (counters["numRays"], meta["numRays"])
-    assert abs(counters["numShadowRays"] - meta["numShadowRays"]) <= 0.03 * meta["numShadowRays"], (counters["numShadowRays"], meta["numShadowRays"])
+    # (the reference's VCM renderer does not touch the ray counters - its meta reports 0 - so only sanity here: at least one
+    #  light and one camera segment per pixel and pass, shadow rays only with vertex connection)
+    assert counters["numRays"] >= w * h * passes
+    assert (counters["numShadowRays"] > 0) == bool(connection) and counters["numShadowRaysHit"] <= counters["numShadowRays"]
 
 
 def test_vcm_is_reproducible_and_needs_the_previous_pass(tmp_path):
