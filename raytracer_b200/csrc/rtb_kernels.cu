@@ -1036,6 +1036,10 @@ struct RtbContext
         cudaStream_t stream = nullptr;
         cudaEvent_t filmDone = nullptr;   // recorded after this slot's last k_film
         Wavefront wf;
+        // the launch chain of a wavefront (raygen + up to five kernels per depth) as a CUDA graph, re-used while its
+        // parameters stay the same: one graph launch instead of ~47 dependent kernel launches
+        cudaGraphExec_t graphExec = nullptr;
+        std::vector<unsigned char> graphKey;
     };
     std::vector<Slot> slots;
     uint32_t nextSlot = 0;
@@ -1044,6 +1048,8 @@ struct RtbContext
     bool slotsNeedMain = true;            // the main stream holds work the slots must wait for (reset / resize / upload)
     bool slotsOwnStreams = false;         // false: one slot on the main stream (default), true: RTB_SLOTS > 1
     bool serializeSlots = false, profileDepths = false;      // development aids, read from the environment at rtb_create
+    bool useGraphs = true;                // RTB_GRAPH=0: plain launches
+    bool exclusiveStream = false;         // the wavefront streams belong to this context alone (RtbCreateDesc::stream given, or RTB_SLOTS > 1)
     bool noWide = false;                  // RTB_NO_WIDE: any-hit rays walk the binary tree (A/B against rtb_wide.h)
     bool wideKernel = true;               // k_shadow_wide (persistent warps, staged tree top) when the scene has an 8-wide tree; RTB_SHADOW_KERNEL=simple: k_shadow
     const WNode* hotNodes = nullptr;      // the scene's largest 8-wide tree ...
@@ -1214,7 +1220,7 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
     c->numShards = numShards;
     c->shardIndex = desc->shardIndex;
     c->tileSize = desc->tileSize ? desc->tileSize : 32;
-    if (desc->stream) { c->stream = (cudaStream_t)desc->stream; c->ownStream = false; }
+    if (desc->stream) { c->stream = (cudaStream_t)desc->stream; c->ownStream = false; c->exclusiveStream = true; }
     else
     {
         // contexts that do not bring their own stream share ONE stream per device: their kernels then never overlap each
@@ -1266,6 +1272,7 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
     int numSlots = 1;
     if (const char* t = getenv("RTB_SLOTS")) numSlots = atoi(t) >= 1 && atoi(t) <= 16 ? atoi(t) : numSlots;
     c->slotsOwnStreams = numSlots > 1;
+    if (c->slotsOwnStreams) c->exclusiveStream = true;
     // Round-2 bisect of the overlap problem (gpurun_out/r2b): with k_tail out of the picture every
     // renderer is bit-identical under overlapping wavefronts (MIS, PT, debug; RTB_SLOTS=2 and 4); with it, a few hundred
     // paths per frame differ.  k_tail is the one kernel that keeps spilled state (the world-space ray) alive across
@@ -1275,6 +1282,7 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
     c->serializeSlots = getenv("RTB_SERIALIZE_SLOTS") != nullptr;
     c->profileDepths = getenv("RTB_PROFILE_DEPTHS") != nullptr;
     c->noWide = getenv("RTB_NO_WIDE") != nullptr;
+    if (const char* t = getenv("RTB_GRAPH")) c->useGraphs = atoi(t) != 0;
     // an instrumented context counts the REFERENCE's work per ray (box / triangle tests of its binary tree: the algorithmic
     // bytes of SURVEY 8(d)); RTB_COUNT_WIDE makes it count what the 8-wide walk does instead (8 "box tests" per node visited)
     if ((c->flags & RTB_FLAG_COUNT_TESTS) != 0 && !getenv("RTB_COUNT_WIDE")) c->noWide = true;
@@ -1315,6 +1323,7 @@ void rtb_destroy(RtbContext* c)
     for (RtbContext::Slot& t : c->slots)
     {
         t.ctl.release(); t.seed.release();
+        if (t.graphExec) { cudaGraphExecDestroy(t.graphExec); t.graphExec = nullptr; }
         if (t.filmDone) cudaEventDestroy(t.filmDone);
         if (t.stream && c->slotsOwnStreams) cudaStreamDestroy(t.stream);
     }
@@ -1463,7 +1472,7 @@ int rtb_resize(RtbContext* c, uint32_t width, uint32_t height)
         if (const char* t = getenv("RTB_BATCH_PATHS")) target = (uint32_t)strtoul(t, nullptr, 10);
         uint32_t b = c->numPixels ? (target + c->numPixels - 1) / c->numPixels : 1u;
         if (b < 1u) b = 1u;
-        if (b > 16u) b = 16u;
+        if (b > 32u) b = 32u;          // (a 1/8 shard of 1080p: 20 passes share one 5 M-path wavefront instead of two 2.6 M-path ones)
         if (const char* t = getenv("RTB_MAX_BATCH")) b = (uint32_t)atoi(t) > 0 ? (uint32_t)atoi(t) : b;
         if (b > 63u) b = 63u;
         c->maxBatch = b; c->maxBatchFilm = b;
@@ -1621,12 +1630,14 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
     W.tailThreshold = tailThreshold;
     size_t ev = 0;
     std::vector<cudaEvent_t> marks;
-    if (prof) marks.push_back(next_event(c, ev, s));
-    k_raygen<<<blocks256, 256, 0, s>>>(c->view, P, W);
-    if (prof) marks.push_back(next_event(c, ev, s));
     const uint32_t depthLimit = pass->renderer == RTB_RENDERER_DEBUG ? 0u : (numPaths ? pass->maxRayDepth : 0u);
     const bool shadows = pass->renderer == RTB_RENDERER_PATH_TRACER_MIS && c->numLights > 0;
     const bool textured = c->textures.count > 0;     // scenes without textures run the k_shade that has no texture calls compiled in
+    auto enqueue = [&]()
+    {
+    if (prof) marks.push_back(next_event(c, ev, s));
+    k_raygen<<<blocks256, 256, 0, s>>>(c->view, P, W);
+    if (prof) marks.push_back(next_event(c, ev, s));
     for (uint32_t d = 0; d <= depthLimit; ++d)
     {
         if (count) k_traverse<true><<<blocks128, 128, c->stackBytes, s>>>(c->view, W, d);
@@ -1661,9 +1672,47 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
             // does nothing unless at most tailThreshold paths are left, then finishes them all (see k_tail)
             if (textured) k_tail<true><<<tailBlocks, 128, c->stackBytes, s>>>(c->view, P, W, d + 1);
             else k_tail<false><<<tailBlocks, 128, c->stackBytes, s>>>(c->view, P, W, d + 1);
-            c->counters.numKernelLaunches++;
         }
         if (prof) marks.push_back(next_event(c, ev, s));
+    }
+    };
+    if (tailBlocks > 0) c->counters.numKernelLaunches += depthLimit;
+    // The chain as a CUDA graph.  Everything a kernel of the chain reads from its arguments goes into the key; what changes
+    // from wavefront to wavefront without the kernels looking at it is blanked first: the pass index (only the `Single`
+    // light pick hashes it - such passes keep plain launches), pass slot 0's AA offset (the batched path reads the
+    // offsets from the seed upload) and the film parity (k_film is launched outside the graph).
+    // (only on a stream this context has to itself - the caller's, or a slot's: contexts without one share a stream per
+    //  device, and another thread's launches on it would end up inside the capture)
+    const bool graphable = c->useGraphs && c->exclusiveStream && !prof && !count && (P.lightSamplingAll || pass->renderer != RTB_RENDERER_PATH_TRACER_MIS);
+    if (!graphable) enqueue();
+    else
+    {
+        struct Key { PassParams P; Wavefront W; SceneView S; uint32_t numPaths, depthLimit, tailBlocks, flags; size_t stackBytes; const void* hot; int hotOverride, wide; };
+        std::vector<unsigned char> key(sizeof(Key), 0);
+        {
+            Key k;
+            memset(&k, 0, sizeof(k));
+            memcpy(&k.P, &P, sizeof(P)); memcpy(&k.W, &W, sizeof(W)); memcpy(&k.S, &c->view, sizeof(SceneView));
+            k.P.passIndex = 0; k.P.sampleOffsetX = 0.0f; k.P.sampleOffsetY = 0.0f; k.W.firstPassIndex = 0;
+            k.numPaths = numPaths; k.depthLimit = depthLimit; k.tailBlocks = (uint32_t)tailBlocks; k.flags = (shadows ? 1u : 0u) | (textured ? 2u : 0u);
+            k.stackBytes = c->stackBytes; k.hot = c->hotNodes; k.hotOverride = c->hotOverride; k.wide = c->wideKernel ? 1 : 0;
+            memcpy(key.data(), &k, sizeof(k));
+        }
+        if (!slot.graphExec || slot.graphKey != key)
+        {
+            if (slot.graphExec) { cudaGraphExecDestroy(slot.graphExec); slot.graphExec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            RTB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            enqueue();
+            const cudaError_t launchError = cudaGetLastError();
+            RTB_CUDA(cudaStreamEndCapture(s, &graph));
+            if (launchError != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail(RTB_ERR_CUDA, "kernel launch failed during graph capture: %s", cudaGetErrorString(launchError)); }
+            const cudaError_t ie = cudaGraphInstantiate(&slot.graphExec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) { slot.graphExec = nullptr; return fail(RTB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+            slot.graphKey = key;
+        }
+        RTB_CUDA(cudaGraphLaunch(slot.graphExec, s));
     }
     // the film: after the previous wavefront's k_film (pass order) and after whatever the caller had enqueued on the main
     // stream when this wavefront was submitted (e.g. a snapshot or an all-gather still reading the film)
