@@ -351,16 +351,19 @@ def run_gpu(args):
         nts = cc["numShadowTriangleTests"] / max(1, cc["numShadowRays"])
         bytes_per_ray = 32 + 24 + 32 * nb + 48 * nt              # ray in + hit out + 32 B per box test + 48 B per (padded) triangle
         bytes_per_shadow_ray = 32 + 4 + 32 * nbs + 48 * nts
-        # what the shipped any-hit kernel itself fetches: 96-byte nodes of the 8-wide tree (rtb_wide.h), 48-byte triangles
-        os.environ["RTB_COUNT_WIDE"] = "1"
-        vpw = make_viewport(flags=capi.RTB_FLAG_COUNT_TESTS)
-        vpw.render(1)
-        cw = vpw.counters()
-        vpw.close()
-        del os.environ["RTB_COUNT_WIDE"]
-        wide_nodes = cw["numShadowBoxTests"] / 8.0 / max(1, cw["numShadowRays"])
-        wide_tris = cw["numShadowTriangleTests"] / max(1, cw["numShadowRays"])
-        own_bytes_per_shadow_ray = 32 + 4 + 96 * wide_nodes + 48 * wide_tris
+        # RTB_SHADOW_KERNEL=wide: what k_shadow_wide itself fetches - 96-byte nodes of the 8-wide tree (rtb_wide.h), 48-byte triangles
+        wide = os.environ.get("RTB_SHADOW_KERNEL") == "wide"
+        own_bytes_per_shadow_ray = wide_nodes = wide_tris = None
+        if wide:
+            os.environ["RTB_COUNT_WIDE"] = "1"
+            vpw = make_viewport(flags=capi.RTB_FLAG_COUNT_TESTS)
+            vpw.render(1)
+            cw = vpw.counters()
+            vpw.close()
+            del os.environ["RTB_COUNT_WIDE"]
+            wide_nodes = cw["numShadowBoxTests"] / 8.0 / max(1, cw["numShadowRays"])
+            wide_tris = cw["numShadowTriangleTests"] / max(1, cw["numShadowRays"])
+            own_bytes_per_shadow_ray = 32 + 4 + 96 * wide_nodes + 48 * wide_tris
         peak, peak_src = measured_peak()
         traffic = {}
         prof = os.path.join(ROOT, "profiles", "traverse_dram_bytes.json")
@@ -385,10 +388,12 @@ def run_gpu(args):
 
         # one any-hit launch per k_traverse launch (one per depth and wavefront)
         r_trav = kernel_roofline("k_traverse", "closest-hit two-level BVH traversal", tm["traverseRays"], tm["traverseMs"], tm["traverseLaunches"], bytes_per_ray, nb, nt)
-        r_shad = kernel_roofline("k_shadow", "any-hit traversal of the light-sample rays: k_shadow_wide on the 8-wide quantised tree; bytes per ray in the reference layout, SURVEY 8(d)",
+        r_shad = kernel_roofline("k_shadow", ("any-hit traversal of the light-sample rays: k_shadow_wide on the 8-wide quantised tree; bytes per ray in the reference layout, SURVEY 8(d)" if wide else
+                                              "any-hit two-level BVH traversal of the light-sample rays"),
                                  tm["shadowRays"], tm["shadowMs"], tm["traverseLaunches"], bytes_per_shadow_ray, nbs, nts)
-        r_shad["own_layout"] = {"nodes_per_ray": wide_nodes, "tri_tests_per_ray": wide_tris, "bytes_per_ray": own_bytes_per_shadow_ray,
-                                "achieved": tm["shadowRays"] * own_bytes_per_shadow_ray / (tm["shadowMs"] * 1e-3) / 1e9 if tm["shadowMs"] > 0 else 0.0}
+        if wide:
+            r_shad["own_layout"] = {"nodes_per_ray": wide_nodes, "tri_tests_per_ray": wide_tris, "bytes_per_ray": own_bytes_per_shadow_ray,
+                                    "achieved": tm["shadowRays"] * own_bytes_per_shadow_ray / (tm["shadowMs"] * 1e-3) / 1e9 if tm["shadowMs"] > 0 else 0.0}
         # the dominant kernel is the one with the larger share of the pass; the other one rides along under its name
         roofline, other = (r_shad, r_trav) if r_shad["share_of_pass"] >= r_trav["share_of_pass"] else (r_trav, r_shad)
         roofline[other["kernel"].split(" ")[0]] = other

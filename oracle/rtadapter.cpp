@@ -127,7 +127,9 @@ public:
         mWidth = width; mHeight = height;
         // Viewport::Resize draws one Vector4 per pixel from its generator for a salt table (Viewport.cpp:99-102)
         for (uint32 i = 0; i < width * height; ++i) mRandomGenerator.GetVector4();
-        return rtb_resize(mCtx, width, height) == RTB_OK;
+        if (rtb_resize(mCtx, width, height) != RTB_OK) return false;
+        Reset();                                                                // Viewport::Resize ends with Reset() (Viewport.cpp:104)
+        return true;
     }
     bool SetRenderingParams(const RenderingParams& params)
     {
@@ -231,10 +233,16 @@ int main(int argc, char** argv)
     vp.SetRenderer(renderer);
     vp.Reset();
     Timer cpuTimer;
-    for (uint32 i = 0; i < passes; ++i) vp.Render(camera);
+    RayTracingCounters rc;      // Viewport::GetCounters holds the LAST pass' counters (Viewport.cpp:423-430): add them up like the adapter's
+    rc.numRays = rc.numShadowRays = rc.numShadowRaysHit = rc.numPrimaryRays = 0;
+    for (uint32 i = 0; i < passes; ++i)
+    {
+        vp.Render(camera);
+        const RayTracingCounters& c = vp.GetCounters();
+        rc.numRays += c.numRays; rc.numShadowRays += c.numShadowRays; rc.numShadowRaysHit += c.numShadowRaysHit; rc.numPrimaryRays += c.numPrimaryRays;
+    }
     const double cpuSeconds = cpuTimer.Stop();
     const Bitmap& sum = vp.GetSumBuffer();
-    const RayTracingCounters& rc = vp.GetCounters();
 
     // ---- the same calls on the adapter ---------------------------------------------------------------------------------------
     if (!vpb.SetRenderingParams(params)) Die("SetRenderingParams");

@@ -1,10 +1,13 @@
-// rtb_bidir.h — ILight::Emit for the five light types (the first step of every light sub-path of the
-// reference's Light Tracer and VCM renderers, Rendering/LightTracer.cpp:44-66, VertexConnectionAndMerging.cpp:320-360).
+// rtb_bidir.h — the per-vertex arithmetic of the reference's bidirectional renderers, written once for host and device:
+// ILight::Emit for the five light types, ILight::Illuminate / GetRadiance as VCM calls them, BSDF::Pdf, the camera
+// connection (Camera::WorldToFilm / PdfW), LightTracer::RenderPixel, and VertexConnectionAndMerging's building blocks
+// (bidir_*: pass weights, light sample generation, the dVCM / dVC / dVM updates, AdvancePath, EvaluateLight, SampleLight,
+// ConnectVertices, the per-photon merge, ConnectToCamera).  (Rendering/LightTracer.cpp:27-183,
+// Rendering/VertexConnectionAndMerging.cpp:80-125, 292-970.)
 //
-// STATUS: building block.  No kernel launches this yet (the bidirectional renderers are not built); the
-// functions are restated here in the device headers' arithmetic and pinned bit for bit against the reference's own
-// ILight::Emit / Camera through tests/hostsim (`emit` and `camera` commands, tests/test_hostsim_parity.py), so
-// that the renderers can be built on checked parts.  rtb_kernels.cu does not include this file.
+// Used by the VCM kernels of rtb_vcm.cuh (the product, included from rtb_kernels.cu) and by the CPU model of the same
+// renderer (tests/hostsim/hostsim_vcm.h), which pinned every function here against the reference's own
+// ILight / Camera / BSDF bit for bit and the assembled renderer statistically (tests/test_hostsim_parity.py).
 #pragma once
 
 #include "rtb_shading.h"

@@ -66,6 +66,8 @@ struct Control
     uint32_t shadowPathCount[RTB_MAX_DEPTH_SLOTS + 2];
     uint32_t shadowRayCount[RTB_MAX_DEPTH_SLOTS + 2];
     uint32_t shadowCursor[RTB_MAX_DEPTH_SLOTS + 2];   // next unfetched entry of rayList (k_shadow's dynamic fetch)
+    uint32_t meshItemCount[RTB_MAX_DEPTH_SLOTS + 2];  // k_shadow_top -> k_shadow_mesh: (ray, mesh) visits queued at this depth
+    uint32_t meshCursor[RTB_MAX_DEPTH_SLOTS + 2];     // next unfetched item
     uint32_t tailTaken;                               // != 0: k_tail finished every remaining path (1 + the depth it started at): later kernels have nothing to do
     uint32_t pad[3];
 };
@@ -95,6 +97,12 @@ struct Wavefront
     uint32_t* shCount;    // per input index: number of shadow rays
     uint32_t* shList;     // compacted input indices that own >= 1 shadow ray
     uint32_t* rayList;    // compacted shadow-ray slots (i * raysPerPath + r) of the current depth
+    // split any-hit walk (k_shadow_top / k_shadow_mesh): one item per (ray, mesh) visit = the mesh-local ray
+    float4*  mi0;         // origin.xyz, tMax
+    float4*  mi1;         // dir.xyz, ray slot bits
+    float4*  mi2;         // invDir.xyz, mesh index bits
+    uint32_t* shFlag;     // per ray slot: 1 = found occluded (set once)
+    uint32_t miCapacity;
     Control* ctl;
     Totals*  tot;
     const uint32_t* pixelList;   // pixel slot -> y * width + x
@@ -392,7 +400,7 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
         if (active)
         {
             const RayInShadowQueue src = { W, j };
-            const int r = walk.step<kCount>(S, stack, src, &cnt, sstack);
+            const int r = walk.template step<kCount, RayInShadowQueue, false, false>(S, stack, src, &cnt, sstack);
             if (r != ShadowWalk::kContinue)
             {
                 active = false;
@@ -408,7 +416,7 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
     {
         const uint32_t j = W.rayList[k];
         const RayInShadowQueue src = { W, j };
-        const bool occluded = scene_traverse_shadow_from<kCount>(S, src, W.sr0[j].w, &cnt, sstack);
+        const bool occluded = scene_traverse_shadow_from<kCount, RayInShadowQueue, false>(S, src, W.sr0[j].w, &cnt, sstack);      // the binary tree
         if (occluded)
         {
             // SampleLight returns RayColor::Zero() for an occluded light (PathTracerMIS.cpp:92-96)
@@ -599,6 +607,158 @@ __global__ void __launch_bounds__(RTB_SW_THREADS, RTB_SW_MINBLOCKS) k_shadow_wid
     }
 }
 
+// ---- any-hit rays, split walk ------------------------------------------------------------------------------------------------
+// "Occluded" is an OR over everything a ray meets, so the top level and the meshes need not be walked by the same thread
+// in the same kernel.  k_shadow_top walks the exact top level for every ray (all lanes start together: converged), tests
+// the analytic shapes on the spot and QUEUES every visit of a mesh that has an 8-wide tree as an item (the mesh-local
+// ray).  k_shadow_mesh then does nothing but wide walks: persistent warps whose lanes fetch a new item the moment they
+// finish one (an item is 48 bytes, there is no other per-ray state to set up), so the eight-child node visits run at
+// nearly full warps.  A ray found occluded has its contribution zeroed and its flag set exactly once (the counter of
+// visible rays is corrected through it).
+#ifndef RTB_SM_THREADS
+#define RTB_SM_THREADS 256
+#endif
+#ifndef RTB_SM_MINBLOCKS
+#define RTB_SM_MINBLOCKS 4
+#endif
+#ifndef RTB_SM_REFILL
+#define RTB_SM_REFILL 1      // idle lanes needed before the warp draws new items
+#endif
+
+template <bool kCount>
+__global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow_top(const __grid_constant__ SceneView S, const __grid_constant__ Wavefront W, uint32_t depth)
+{
+    const uint32_t count = W.ctl->tailTaken ? 0u : W.ctl->shadowRayCount[depth];
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long visibleLocal = 0;
+    TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
+    extern __shared__ uint32_t smemStack[];
+    SharedStack sstack = (SharedStack)__cvta_generic_to_shared(smemStack) + threadIdx.x * 4u;
+    asm volatile("" : "+r"(sstack));
+    uint32_t stack[1];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+    {
+        const uint32_t j = W.rayList[k];
+        const RayInShadowQueue src = { W, j };
+        ShadowWalk walk;
+        bool occluded = false;
+        if (walk.begin(S, stack, src, W.sr0[j].w, sstack))
+        {
+            for (;;)
+            {
+                const int r = walk.template step<kCount, RayInShadowQueue, true>(S, stack, src, &cnt, sstack);
+                if (r == ShadowWalk::kContinue) continue;
+                if (r == ShadowWalk::kEnterWide)
+                {
+                    const uint32_t slot = atomicAdd(&W.ctl->meshItemCount[depth], 1u);
+                    if (slot < W.miCapacity)
+                    {
+                        W.mi0[slot] = make_float4(walk.ray.origin.x, walk.ray.origin.y, walk.ray.origin.z, walk.maxDistance);
+                        W.mi1[slot] = make_float4(walk.ray.dir.x, walk.ray.dir.y, walk.ray.dir.z, __uint_as_float(j));
+                        W.mi2[slot] = make_float4(walk.ray.invDir.x, walk.ray.invDir.y, walk.ray.invDir.z, __uint_as_float(walk.wideMesh));
+                    }
+                    else
+                    {
+                        // queue full (a ray visits more meshes than the queue was sized for): walk it here
+                        const DMesh& mesh = S.meshes[walk.wideMesh];
+                        WideView wv; wv.nodes = mesh.wideNodes; wv.tris = mesh.wideTris; wv.refNodes = mesh.nodes; wv.maxAbs = mesh.wideMaxAbs;
+                        WideStackAbove ws; ws.stack = stack; ws.sstack = sstack; ws.floor = walk.stackSize; ws.top = walk.stackSize;
+                        if (wide_any_hit<kCount>(wv, walk.ray, walk.maxDistance, ws, &cnt)) { occluded = true; break; }
+                    }
+                    walk.leave_wide(S, src);
+                    continue;
+                }
+                occluded = r == ShadowWalk::kOccluded;
+                break;
+            }
+        }
+        if (occluded) { W.sr1[j].w = 0.0f; W.sr2[j].w = 0.0f; W.sr3[j].w = 0.0f; W.shFlag[j] = 1u; }      // SampleLight returns RayColor::Zero() (PathTracerMIS.cpp:92-96)
+        else { W.shFlag[j] = 0u; visibleLocal++; }
+    }
+    for (int o = 16; o > 0; o >>= 1) visibleLocal += __shfl_down_sync(0xFFFFFFFFu, visibleLocal, o);
+    if (lane == 0 && visibleLocal) atomicAdd(&W.tot->numShadowRaysHit, visibleLocal);
+    if (kCount)
+    {
+        atomicAdd(&W.tot->numShadowBoxTests, (unsigned long long)cnt.boxTests);
+        atomicAdd(&W.tot->numShadowTriTests, (unsigned long long)cnt.triTests);
+    }
+}
+
+template <bool kCount>
+__global__ void __launch_bounds__(RTB_SM_THREADS, RTB_SM_MINBLOCKS) k_shadow_mesh(const __grid_constant__ SceneView S, const __grid_constant__ Wavefront W, uint32_t depth, uint32_t panelBytes)
+{
+    extern __shared__ uint32_t smemStack[];
+    const uint32_t numItems = W.ctl->tailTaken ? 0u : min(W.ctl->meshItemCount[depth], W.miCapacity);
+    const uint32_t lane = threadIdx.x & 31u;
+    SharedStack sstack = (SharedStack)__cvta_generic_to_shared(smemStack) + (threadIdx.x >> 7) * panelBytes + (threadIdx.x & 127u) * 4u;
+    asm volatile("" : "+r"(sstack));
+    uint32_t stack[1];
+    unsigned long long newlyOccluded = 0;
+    TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
+    bool active = false, exhausted = false;
+    uint32_t j = 0, top = 0;
+    Ray ray;
+    float tMax = 0.0f;
+    WideWalk wide;
+    WideView wv; wv.nodes = nullptr; wv.tris = nullptr; wv.refNodes = nullptr; wv.maxAbs = 0.0f;
+    const WideFetchGlobal fetch;
+    for (;;)
+    {
+        const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
+        if (!exhausted && __popc(idle) >= RTB_SM_REFILL)
+        {
+            const uint32_t want = __popc(idle);
+            uint32_t k0 = 0;
+            if (lane == 0) k0 = atomicAdd(&W.ctl->meshCursor[depth], want);
+            k0 = __shfl_sync(0xFFFFFFFFu, k0, 0);
+            exhausted = k0 + want >= numItems;
+            const uint32_t k = k0 + __popc(idle & ((1u << lane) - 1u));
+            if (!active && k < numItems)
+            {
+                const float4 a = W.mi0[k], b = W.mi1[k], c = W.mi2[k];
+                j = __float_as_uint(b.w);
+                ray.origin = v3(a.x, a.y, a.z); ray.dir = v3(b.x, b.y, b.z); ray.invDir = v3(c.x, c.y, c.z);
+                ray.originDivDir = ray.origin * ray.invDir;                    // make_ray_unsafe (Ray.h:31-39): the same product
+                tMax = a.w;
+                const DMesh& mesh = S.meshes[__float_as_uint(c.w)];
+                wv.nodes = mesh.wideNodes; wv.tris = mesh.wideTris; wv.refNodes = mesh.nodes;
+                wide.begin(ray, mesh.wideMaxAbs);
+                top = 0;
+                active = true;
+            }
+        }
+        if (__ballot_sync(0xFFFFFFFFu, active) == 0u)
+        {
+            if (exhausted) break;
+            continue;
+        }
+        if (active)
+        {
+            WideStackAbove ws; ws.stack = stack; ws.sstack = sstack; ws.floor = 0; ws.top = top;
+            const int r = wide.template step<kCount>(wv, ray, tMax, ws, &cnt, fetch);
+            top = ws.top;
+            if (r == WideWalk::kOccluded)
+            {
+                active = false;
+                if (atomicExch(&W.shFlag[j], 1u) == 0u)
+                {
+                    newlyOccluded++;
+                    W.sr1[j].w = 0.0f; W.sr2[j].w = 0.0f; W.sr3[j].w = 0.0f;
+                }
+            }
+            else if (r == WideWalk::kMissed) active = false;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) newlyOccluded += __shfl_down_sync(0xFFFFFFFFu, newlyOccluded, o);
+    if (lane == 0 && newlyOccluded) atomicAdd(&W.tot->numShadowRaysHit, 0ull - newlyOccluded);       // k_shadow_top counted them as visible
+    if (kCount)
+    {
+        atomicAdd(&W.tot->numShadowBoxTests, (unsigned long long)cnt.boxTests);
+        atomicAdd(&W.tot->numShadowTriTests, (unsigned long long)cnt.triTests);
+    }
+}
+
 // ---- the tail of a wavefront ---------------------------------------------------------------------------------------------
 // Once only a few ten thousand paths are left, every further bounce costs four launches whose run time is one warp's
 // latency, not throughput (a 1/8 shard rendered pass by pass spends more than half of its 2.2 ms there).  k_tail is
@@ -618,7 +778,7 @@ struct TailSink
     __device__ void shadow(const Ray& ray, float tMax, const V4& c, uint32_t)
     {
         raysThisVertex++; shadowRays++;
-        const bool occluded = scene_traverse_shadow<false>(S, ray, tMax, nullptr, sstack);
+        const bool occluded = scene_traverse_shadow<false, false>(S, ray, tMax, nullptr, sstack);
         if (!occluded) { visible++; lightSum = lightSum + xyz(c); }
         else lightSum = lightSum + v3s(0.0f);           // k_shadow zeroes the contribution, k_resolve still adds it
     }
@@ -1029,7 +1189,8 @@ struct RtbContext
         DevArray<uint4> hit0;
         DevArray<float> hit1;
         DevArray<float4> passColor, sr0, sr1, sr2, sr3, shThr;
-        DevArray<uint32_t> shCount, shList, rayList;
+        DevArray<uint32_t> shCount, shList, rayList, shFlag;
+        DevArray<float4> mi0, mi1, mi2;
         DevArray<Control> ctl;
         DevArray<uint32_t> seed;       // maxBatch x numSeedDims seed integers, then maxBatch x 2 AA offsets
         std::vector<uint32_t> stagingSeeds;
@@ -1051,9 +1212,12 @@ struct RtbContext
     bool useGraphs = true;                // RTB_GRAPH=0: plain launches
     bool exclusiveStream = false;         // the wavefront streams belong to this context alone (RtbCreateDesc::stream given, or RTB_SLOTS > 1)
     bool noWide = false;                  // RTB_NO_WIDE: any-hit rays walk the binary tree (A/B against rtb_wide.h)
-    bool wideKernel = true;               // k_shadow_wide (persistent warps, staged tree top) when the scene has an 8-wide tree; RTB_SHADOW_KERNEL=simple: k_shadow
+    int shadowKernel = 0;                 // RTB_SHADOW_KERNEL: 0 simple = k_shadow, 1 wide = k_shadow_wide, 2 split = k_shadow_top + k_shadow_mesh
+    bool wideKernel = false;              // RTB_SHADOW_KERNEL=wide: k_shadow_wide (8-wide tree, persistent warps) for any-hit rays instead of k_shadow
+                                          // (binary tree).  Same results; measured on the bench it does not beat the binary walk
     const WNode* hotNodes = nullptr;      // the scene's largest 8-wide tree ...
     uint32_t hotTotal = 0;                // ... and its node count
+    uint32_t wideDepth = 0;               // deepest 8-wide tree of the scene (levels)
     int hotOverride = 0;                  // RTB_HOT_NODES: nodes of the tree top staged in shared memory (-1: as many as fit).  Measured on the bench
                                           // (k_shadow_wide per 8 passes): none 40.1 ms, 256 nodes 43.1, as many as fit (~1000) 43.2 - the copy costs L1
     DevArray<float> snapshots;            // rtb_film_snapshots: snapshotCapacity x shardSlots x 3 floats
@@ -1123,6 +1287,7 @@ static void free_film(RtbContext* c)
         for (int b = 0; b < 2; ++b) { for (int k = 0; k < 4; ++k) t.p[b][k].release(); t.p4[b].release(); }
         t.hit0.release(); t.hit1.release(); t.passColor.release();
         t.sr0.release(); t.sr1.release(); t.sr2.release(); t.sr3.release(); t.shThr.release(); t.shCount.release(); t.shList.release(); t.rayList.release();
+        t.shFlag.release(); t.mi0.release(); t.mi1.release(); t.mi2.release();
     }
 }
 
@@ -1170,6 +1335,7 @@ static int alloc_shadow(RtbContext* c)
     {
         RTB_CUDA(t.sr0.alloc(n)); RTB_CUDA(t.sr1.alloc(n)); RTB_CUDA(t.sr2.alloc(n)); RTB_CUDA(t.sr3.alloc(n));
         RTB_CUDA(t.rayList.alloc(n));
+        if (c->shadowKernel == 2) { RTB_CUDA(t.shFlag.alloc(n)); RTB_CUDA(t.mi0.alloc(n)); RTB_CUDA(t.mi1.alloc(n)); RTB_CUDA(t.mi2.alloc(n)); }
     }
     return RTB_OK;
 }
@@ -1187,6 +1353,7 @@ static void fill_wavefront(RtbContext* c)
         w.hit0 = t.hit0.ptr; w.hit1 = t.hit1.ptr; w.passColor = t.passColor.ptr;
         w.sr0 = t.sr0.ptr; w.sr1 = t.sr1.ptr; w.sr2 = t.sr2.ptr; w.sr3 = t.sr3.ptr;
         w.shThr = t.shThr.ptr; w.shCount = t.shCount.ptr; w.shList = t.shList.ptr; w.rayList = t.rayList.ptr;
+        w.mi0 = t.mi0.ptr; w.mi1 = t.mi1.ptr; w.mi2 = t.mi2.ptr; w.shFlag = t.shFlag.ptr; w.miCapacity = (uint32_t)std::min<size_t>(t.mi0.count, 0xFFFFFFFFu);
         w.ctl = t.ctl.ptr;
         w.tot = c->totals.ptr;
         w.pixelList = c->pixelList.ptr;
@@ -1253,6 +1420,8 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
         cudaFuncSetAttribute(k_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
         cudaFuncSetAttribute(k_shadow_wide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         cudaFuncSetAttribute(k_shadow_wide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        cudaFuncSetAttribute(k_shadow_top<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+        cudaFuncSetAttribute(k_shadow_top<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
         if (const char* t = getenv("RTB_TAIL_PATHS")) c->tailThreshold = (uint32_t)strtoul(t, nullptr, 10);
     }
     // RTB_CARVEOUT=n (development aid): pin the L1 / shared-memory split of EVERY kernel of this library to n percent
@@ -1286,7 +1455,7 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
     // an instrumented context counts the REFERENCE's work per ray (box / triangle tests of its binary tree: the algorithmic
     // bytes of SURVEY 8(d)); RTB_COUNT_WIDE makes it count what the 8-wide walk does instead (8 "box tests" per node visited)
     if ((c->flags & RTB_FLAG_COUNT_TESTS) != 0 && !getenv("RTB_COUNT_WIDE")) c->noWide = true;
-    if (const char* t = getenv("RTB_SHADOW_KERNEL")) c->wideKernel = strcmp(t, "simple") != 0;
+    if (const char* t = getenv("RTB_SHADOW_KERNEL")) { c->shadowKernel = !strcmp(t, "wide") ? 1 : !strcmp(t, "split") ? 2 : 0; c->wideKernel = c->shadowKernel != 0; }
     if (const char* t = getenv("RTB_HOT_NODES")) c->hotOverride = atoi(t);
     c->slots.resize(numSlots);
     e = c->totals.alloc(1);
@@ -1392,7 +1561,8 @@ int rtb_upload_scene(RtbContext* c, const RtbSceneDesc* scene)
         v.numVertices = (uint32_t)hm.shading.size(); v.numMaterials = (uint32_t)hm.materialIds.size();
     }
     RTB_CUDA(c->meshViews.upload(views, s));
-    c->hotNodes = nullptr; c->hotTotal = 0;
+    c->hotNodes = nullptr; c->hotTotal = 0; c->wideDepth = 1;
+    for (const HostMesh& hm : hs.meshes) c->wideDepth = std::max(c->wideDepth, hm.wide.depth);
     for (size_t i = 0; i < views.size(); ++i) if (views[i].numWideNodes > c->hotTotal) { c->hotTotal = views[i].numWideNodes; c->hotNodes = views[i].wideNodes; }
     // textures: bitmap texels stay float4 in HBM (rtb_texture.h); the descriptors get the device pointers
     c->texels.resize(hs.textures.size());
@@ -1650,7 +1820,24 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
         {
             // resident warps only: they fetch rays dynamically until the list is empty
             const int shadowBlocks = RTB_SHADOW_REFILL ? c->numSMs * RTB_TRAV_MINBLOCKS : blocksShadow;
-            if (c->wideKernel && c->hotTotal > 0)
+            if (c->shadowKernel == 2 && c->hotTotal > 0)
+            {
+                // top level for every ray, then the queued mesh visits on persistent warps (16 stack words per thread: 8 levels)
+                const size_t meshPanel = (size_t)2 * c->wideDepth * RTB_STACK_THREADS * sizeof(uint32_t);
+                const int meshBlocks = c->numSMs * RTB_SM_MINBLOCKS;
+                if (count)
+                {
+                    k_shadow_top<true><<<shadowBlocks, 128, c->stackBytes, s>>>(c->view, W, d);
+                    k_shadow_mesh<true><<<meshBlocks, RTB_SM_THREADS, (RTB_SM_THREADS / 128) * meshPanel, s>>>(c->view, W, d, (uint32_t)meshPanel);
+                }
+                else
+                {
+                    k_shadow_top<false><<<shadowBlocks, 128, c->stackBytes, s>>>(c->view, W, d);
+                    k_shadow_mesh<false><<<meshBlocks, RTB_SM_THREADS, (RTB_SM_THREADS / 128) * meshPanel, s>>>(c->view, W, d, (uint32_t)meshPanel);
+                }
+                c->counters.numKernelLaunches++;
+            }
+            else if (c->wideKernel && c->hotTotal > 0)
             {
                 // persistent CTAs; shared memory: barrier + staged tree top + one stack panel per 128 threads
                 const size_t perCta = (233472u - 1024u * RTB_SW_MINBLOCKS) / RTB_SW_MINBLOCKS;
@@ -1695,7 +1882,7 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
             memcpy(&k.P, &P, sizeof(P)); memcpy(&k.W, &W, sizeof(W)); memcpy(&k.S, &c->view, sizeof(SceneView));
             k.P.passIndex = 0; k.P.sampleOffsetX = 0.0f; k.P.sampleOffsetY = 0.0f; k.W.firstPassIndex = 0;
             k.numPaths = numPaths; k.depthLimit = depthLimit; k.tailBlocks = (uint32_t)tailBlocks; k.flags = (shadows ? 1u : 0u) | (textured ? 2u : 0u);
-            k.stackBytes = c->stackBytes; k.hot = c->hotNodes; k.hotOverride = c->hotOverride; k.wide = c->wideKernel ? 1 : 0;
+            k.stackBytes = c->stackBytes; k.hot = c->hotNodes; k.hotOverride = c->hotOverride; k.wide = c->shadowKernel;
             memcpy(key.data(), &k, sizeof(k));
         }
         if (!slot.graphExec || slot.graphKey != key)

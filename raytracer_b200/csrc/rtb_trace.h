@@ -693,7 +693,9 @@ struct ShadowWalk
 
     // kSuspendWide: a mesh that has an 8-wide tree is not walked here; step() returns kEnterWide with the mesh-local ray
     // in `ray` and the caller walks it (k_shadow_wide does that for all lanes of a warp together)
-    template <bool kCount, typename WorldRay, bool kSuspendWide = false>
+    // kAllowWide = false: meshes are walked on the reference's binary tree whether they have a wide one or not (k_shadow and
+    // k_tail: the round-1 kernels, whose register budget has no room for both walks)
+    template <bool kCount, typename WorldRay, bool kSuspendWide = false, bool kAllowWide = true>
     RTB_HD int step(const SceneView& S, uint32_t* stack, const WorldRay& worldRaySource, TraceCounters* cnt, SharedStack sstack = 0)
     {
         // (the form of the node loop matters: `while (have) { if (leaf) break; ... }` WITHOUT the postponing measured 35 %
@@ -739,7 +741,7 @@ struct ShadowWalk
             {
                 const DMesh& mesh = S.meshes[obj.meshIndex];
 #if RTB_WIDE_SHADOW
-                if (mesh.numNodes != 0 && mesh.wideNodes != nullptr && wide_ray_ok(localRay))
+                if (kAllowWide && mesh.numNodes != 0 && mesh.wideNodes != nullptr && wide_ray_ok(localRay))
                 {
                     if (kSuspendWide) { wideMesh = obj.meshIndex; ray = localRay; return kEnterWide; }
                     // the whole mesh in one go on its 8-wide tree: same boolean as the binary walk (rtb_wide.h)
@@ -769,7 +771,7 @@ struct ShadowWalk
     }
 };
 
-template <bool kCount, typename WorldRay>
+template <bool kCount, typename WorldRay, bool kAllowWide = true>
 RTB_HD bool scene_traverse_shadow_from(const SceneView& S, const WorldRay& worldRaySource, float maxDistance, TraceCounters* cnt, SharedStack sstack = 0)
 {
     ShadowWalk w;
@@ -777,16 +779,16 @@ RTB_HD bool scene_traverse_shadow_from(const SceneView& S, const WorldRay& world
     if (!w.begin(S, stack, worldRaySource, maxDistance, sstack)) return false;
     for (;;)
     {
-        const int r = w.step<kCount>(S, stack, worldRaySource, cnt, sstack);
+        const int r = w.template step<kCount, WorldRay, false, kAllowWide>(S, stack, worldRaySource, cnt, sstack);
         if (r != ShadowWalk::kContinue) return r == ShadowWalk::kOccluded;
     }
 }
 
-template <bool kCount>
+template <bool kCount, bool kAllowWide = true>
 RTB_HD bool scene_traverse_shadow(const SceneView& S, const Ray& worldRay, float maxDistance, TraceCounters* cnt, SharedStack sstack = 0)
 {
     const RayInRegisters src = { worldRay };
-    return scene_traverse_shadow_from<kCount>(S, src, maxDistance, cnt, sstack);
+    return scene_traverse_shadow_from<kCount, RayInRegisters, kAllowWide>(S, src, maxDistance, cnt, sstack);
 }
 
 } // namespace rtb

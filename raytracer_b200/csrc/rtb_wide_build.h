@@ -28,7 +28,11 @@ inline bool build_wide_bvh(const std::vector<DNode>& n2, const std::vector<DTri>
     out = HostWide();
     const uint32_t numNodes = (uint32_t)n2.size();
     if (numNodes == 0 || tris2.empty() || tris2.size() >= (1u << 24)) return false;
-    if (leafTris < 1u) leafTris = 1u;
+    // leafTris = 0: every leaf child is ONE triangle with its own (inflated, quantised) box - a leaf of the reference's tree
+    // with two triangles takes two child slots.  Triangle tests run at a few lanes per warp, child tests at nearly full
+    // warps, so trading the former for the latter pays (k_shadow_mesh).
+    const bool perTriangle = leafTris == 0u;
+    if (perTriangle) leafTris = 1u;
     if (leafTris > 4u) leafTris = 4u;
     auto leafCount = [&](uint32_t i) { return n2[i].leafInfo & 0x3FFFFFFFu; };
 
@@ -131,7 +135,11 @@ inline bool build_wide_bvh(const std::vector<DNode>& n2, const std::vector<DTri>
             const double leafCost = count[n] <= leafTris ? a * count[n] * kTriCost : 1e300;
             if (leafCount(n) != 0)
             {
-                for (int i = 0; i < 7; ++i) { d.cost[i] = (float)leafCost; d.split[i] = 0; }
+                // per-triangle mode: a leaf of c triangles needs c slots (its cost: c boxes tested where the parent is visited)
+                const uint32_t need = perTriangle ? count[n] : 1u;
+                const double cst = perTriangle ? a * count[n] * kTriCost : (count[n] <= leafTris ? leafCost : a * count[n] * kTriCost);
+                if (need > 7u) return false;
+                for (int i = 0; i < 7; ++i) { d.cost[i] = (uint32_t)(i + 1) >= need ? (float)cst : INFINITY; d.split[i] = 0; }
                 d.leaf = 1; d.innerSplit = 0;
                 continue;
             }
@@ -162,7 +170,34 @@ inline bool build_wide_bvh(const std::vector<DNode>& n2, const std::vector<DTri>
         }
     }
     // the children that stand for subtree n when it may use `slots` slots
-    auto gather = [&](uint32_t root, int rootSlots, std::vector<uint32_t>& kids)
+    struct Kid { uint32_t node; int tri; double box[6]; };      // tri >= 0: triangle `tri` (reference order) of leaf `node`, alone
+    const double margin = 1.0e-4 * (double)out.maxAbs;        // a float triangle hit lies inside the triangle's box inflated by this (MT's error is a few ulps of maxAbs)
+    auto makeKid = [&](uint32_t node, int tri)
+    {
+        Kid k; k.node = node; k.tri = tri;
+        if (tri < 0)
+        {
+            const DNode& c = n2[node];
+            k.box[0] = c.minx; k.box[1] = c.miny; k.box[2] = c.minz; k.box[3] = c.maxx; k.box[4] = c.maxy; k.box[5] = c.maxz;
+        }
+        else
+        {
+            const DTri& t = tris2[(size_t)tri];
+            const double v[3][3] = { { t.v0x, t.v0y, t.v0z }, { (double)t.v0x + t.e1x, (double)t.v0y + t.e1y, (double)t.v0z + t.e1z }, { (double)t.v0x + t.e2x, (double)t.v0y + t.e2y, (double)t.v0z + t.e2z } };
+            for (int a = 0; a < 3; ++a)
+            {
+                k.box[a] = std::min(v[0][a], std::min(v[1][a], v[2][a])) - margin;
+                k.box[3 + a] = std::max(v[0][a], std::max(v[1][a], v[2][a])) + margin;
+            }
+        }
+        return k;
+    };
+    auto pushLeaf = [&](uint32_t node, std::vector<Kid>& kids)
+    {
+        if (!perTriangle) { kids.push_back(makeKid(node, -1)); return; }
+        for (uint32_t t = 0; t < count[node]; ++t) kids.push_back(makeKid(node, (int)(first[node] + t)));
+    };
+    auto gather = [&](uint32_t root, int rootSlots, std::vector<Kid>& kids)
     {
         struct G { uint32_t node; int slots; };
         std::vector<G> st(1, { root, rootSlots });
@@ -170,8 +205,9 @@ inline bool build_wide_bvh(const std::vector<DNode>& n2, const std::vector<DTri>
         {
             G g = st.back(); st.pop_back();
             const Dp& d = dp[g.node];
+            if (leafCount(g.node) != 0) { pushLeaf(g.node, kids); continue; }
             while (g.slots > 1 && d.split[g.slots - 1] == 0) g.slots--;
-            if (g.slots <= 1 || leafCount(g.node) != 0) { kids.push_back(g.node); continue; }
+            if (g.slots <= 1) { kids.push_back(makeKid(g.node, -1)); continue; }
             const int kk = d.split[g.slots - 1];
             st.push_back({ n2[g.node].childIndex + 1, g.slots - kk });
             st.push_back({ n2[g.node].childIndex, kk });
@@ -186,33 +222,32 @@ inline bool build_wide_bvh(const std::vector<DNode>& n2, const std::vector<DTri>
     {
         const Work w = queue[head];
         out.depth = std::max(out.depth, w.level);
-        std::vector<uint32_t> kids;
+        std::vector<Kid> kids;
         if (leafCount(w.node) != 0)
         {
-            // (only the root can arrive here as a leaf) one node whose only child is that leaf
-            if (count[w.node] > leafTris) return false;
-            kids.push_back(w.node);
+            // (only the root can arrive here as a leaf) one node whose children are that leaf / its triangles
+            if (!perTriangle && count[w.node] > leafTris) return false;
+            pushLeaf(w.node, kids);
         }
         else
         {
             const int kk = dp[w.node].innerSplit;
             gather(n2[w.node].childIndex, kk, kids);
             gather(n2[w.node].childIndex + 1, 8 - kk, kids);
-            if (kids.empty() || kids.size() > 8) return false;
         }
+        if (kids.empty() || kids.size() > 8) return false;
         // slot order: largest surface first (an any-hit ray is most likely to be stopped there)
-        std::stable_sort(kids.begin(), kids.end(), [&](uint32_t a, uint32_t b) { return area(a) > area(b); });
+        auto kidArea = [](const Kid& k) { const double dx = k.box[3] - k.box[0], dy = k.box[4] - k.box[1], dz = k.box[5] - k.box[2]; return dx * dy + dy * dz + dz * dx; };
+        std::stable_sort(kids.begin(), kids.end(), [&](const Kid& a, const Kid& b) { return kidArea(a) > kidArea(b); });
 
         WNode node;
         memset(&node, 0, sizeof(node));
         double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
-        for (uint32_t k : kids)
-        {
-            const DNode& c = n2[k];
-            lo[0] = std::min(lo[0], (double)c.minx); lo[1] = std::min(lo[1], (double)c.miny); lo[2] = std::min(lo[2], (double)c.minz);
-            hi[0] = std::max(hi[0], (double)c.maxx); hi[1] = std::max(hi[1], (double)c.maxy); hi[2] = std::max(hi[2], (double)c.maxz);
-        }
-        node.px = (float)lo[0]; node.py = (float)lo[1]; node.pz = (float)lo[2];     // exact: they are floats
+        for (const Kid& k : kids)
+            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], k.box[a]); hi[a] = std::max(hi[a], k.box[3 + a]); }
+        // the grid origin must be a float at or below the smallest coordinate (inflated triangle boxes are doubles)
+        for (int a = 0; a < 3; ++a) { float f = (float)lo[a]; if ((double)f > lo[a]) f = std::nextafterf(f, -INFINITY); lo[a] = (double)f; }
+        node.px = (float)lo[0]; node.py = (float)lo[1]; node.pz = (float)lo[2];
         int e[3];
         for (int a = 0; a < 3; ++a)
         {
@@ -230,19 +265,30 @@ inline bool build_wide_bvh(const std::vector<DNode>& n2, const std::vector<DTri>
         memset(qlo, 255, sizeof(qlo)); memset(qhi, 0, sizeof(qhi));               // empty children: inverted boxes
         for (size_t s = 0; s < kids.size(); ++s)
         {
-            const uint32_t k = kids[s];
-            const DNode& c = n2[k];
-            const double cmin[3] = { c.minx, c.miny, c.minz }, cmax[3] = { c.maxx, c.maxy, c.maxz };
+            const Kid& kid = kids[s];
+            const uint32_t k = kid.node;
             for (int a = 0; a < 3; ++a)
             {
                 const double step = std::ldexp(1.0, e[a]);
-                double l = std::floor((cmin[a] - lo[a]) / step), h = std::ceil((cmax[a] - lo[a]) / step);
+                double l = std::floor((kid.box[a] - lo[a]) / step), h = std::ceil((kid.box[3 + a] - lo[a]) / step);
                 l = std::min(std::max(l, 0.0), 255.0); h = std::min(std::max(h, 0.0), 255.0);
-                if (lo[a] + l * step > cmin[a] || lo[a] + h * step < cmax[a]) return false;     // (cannot happen: doubles hold these exactly)
+                if (lo[a] + l * step > kid.box[a] || lo[a] + h * step < kid.box[3 + a]) return false;     // (cannot happen)
                 qlo[a][s] = (uint8_t)l; qhi[a][s] = (uint8_t)h;
             }
             valid |= 1u << s;
-            if (dp[k].leaf || leafCount(k) != 0)
+            if (kid.tri >= 0)
+            {
+                // one triangle of a reference leaf
+                if (triOffset + 1u > 32u) return false;
+                meta[s] = (uint8_t)(0x80u | triOffset);
+                triOffset += 1u;
+                out.maxLeafTris = std::max(out.maxLeafTris, 1u);
+                DTri tri = tris2[(size_t)kid.tri];
+                const uint32_t tag = k == 0u ? RTB_WIDE_NO_LEAF : k, index = (uint32_t)kid.tri;
+                memcpy(&tri.pad0, &tag, 4); memcpy(&tri.pad1, &index, 4);
+                out.tris.push_back(tri);
+            }
+            else if (dp[k].leaf || leafCount(k) != 0)
             {
                 if (count[k] > 4u || triOffset + count[k] > 32u) return false;
                 meta[s] = (uint8_t)(0x80u | ((count[k] - 1u) << 5) | triOffset);
@@ -260,7 +306,7 @@ inline bool build_wide_bvh(const std::vector<DNode>& n2, const std::vector<DTri>
         for (int a = 0; a < 3; ++a) { memcpy(node.qlo[a], qlo[a], 8); memcpy(node.qhi[a], qhi[a], 8); }
         out.nodes.resize(out.nodes.size() + numInner);
         uint32_t rank = 0;
-        for (size_t s = 0; s < kids.size(); ++s) if (imask & (1u << s)) queue.push_back({ kids[s], node.childBase + rank++, w.level + 1u });
+        for (size_t s = 0; s < kids.size(); ++s) if (imask & (1u << s)) queue.push_back({ kids[s].node, node.childBase + rank++, w.level + 1u });
         out.nodes[w.wide] = node;
     }
     return true;

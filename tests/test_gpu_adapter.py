@@ -15,18 +15,18 @@ ADAPTER = os.path.join(util.ORACLE_EXACT, "rtadapter")
 
 
 @pytest.mark.skipif(not os.path.exists(ADAPTER), reason="oracle/_ref/exact/rtadapter did not travel to this box")
-@pytest.mark.parametrize("scene,renderer,w,h,passes", [
-    ("cornell", "Path Tracer MIS", 96, 80, 4),
-    ("mesh_small", "Path Tracer MIS", 80, 64, 3),
-    ("materials", "Path Tracer MIS", 72, 56, 3),
-    ("textures", "Path Tracer", 64, 48, 2),
+@pytest.mark.parametrize("scene,renderer,w,h,passes,dims", [
+    ("cornell", "Path Tracer MIS", 96, 80, 4, 128),
+    ("mesh_small", "Path Tracer MIS", 80, 64, 3, 128),
+    ("materials", "Path Tracer MIS", 72, 56, 3, 256),      # six lights: 194 sample dimensions at depth 8
+    ("textures", "Path Tracer", 64, 48, 2, 128),
 ])
-def test_reference_scene_through_the_compiled_adapter(scene, renderer, w, h, passes):
+def test_reference_scene_through_the_compiled_adapter(scene, renderer, w, h, passes, dims):
     scn = os.path.join(util.GOLDEN, "scenes")
     run_dir = os.path.join(util.ORACLE_EXACT, "run")
     os.makedirs(run_dir, exist_ok=True)
     r = subprocess.run([ADAPTER, "--scene", os.path.join(scn, scene + ".json"), "--data", scn + "/", "--width", str(w), "--height", str(h), "--passes", str(passes),
-                        "--renderer", renderer, "--dims", "128", "--depth", "8"],
+                        "--renderer", renderer, "--dims", str(dims), "--depth", "8"],
                        cwd=run_dir, env=dict(os.environ, RT_FIXED_SEED="777"), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert lines, r.stderr[-2000:]

@@ -149,7 +149,10 @@ def test_config2_cornell_box_512x512_256spp_against_the_live_reference(tmp_path)
 
 
 @pytest.mark.skipif(not util.oracle_available("exact"), reason="prebuilt oracle/_ref/exact did not travel to this box")
-def test_config3_bench_scene_1920x1080_against_the_live_reference(scene, tmp_path):
+@pytest.mark.parametrize("shadow_kernel", ["simple", "wide", "split"])
+def test_config3_bench_scene_1920x1080_against_the_live_reference(scene, tmp_path, shadow_kernel, monkeypatch):
     """BASELINE config 3 at its stated resolution: the 256 768-triangle bench scene, 1920x1080, depth 8, both lights
-    sampled per vertex; two passes (4.1 M samples, ~33 M rays) against the reference on this box's CPU."""
+    sampled per vertex; two passes (4.1 M samples, ~33 M rays) against the reference on this box's CPU - with the default
+    any-hit kernel (binary tree) and with k_shadow_wide on the 8-wide quantised tree (18 M shadow rays, same booleans)."""
+    monkeypatch.setenv("RTB_SHADOW_KERNEL", shadow_kernel)
     live_reference_case(tmp_path, bench.ensure_scene(), bench.SCENE_DIR + "/", bench.WIDTH, bench.HEIGHT, 2, bench.DIMS, host_scene=scene, seed="4242")

@@ -737,11 +737,14 @@ def test_active_tiles(ctx):
     util.assert_bit_identical(ctx.read_sum(), four, "all pixels active again")
 
 
-@pytest.mark.parametrize("env", [{"RTB_SHADOW_KERNEL": "simple", "RTB_NO_WIDE": "1"}, {"RTB_SHADOW_KERNEL": "simple"}, {"RTB_HOT_NODES": "0"}, {"RTB_HOT_NODES": "64"}, {"RTB_HOT_NODES": "-1"}])
+@pytest.mark.parametrize("env", [{"RTB_SHADOW_KERNEL": "simple"}, {"RTB_SHADOW_KERNEL": "wide", "RTB_HOT_NODES": "0"}, {"RTB_SHADOW_KERNEL": "wide", "RTB_HOT_NODES": "64"},
+                                 {"RTB_SHADOW_KERNEL": "wide", "RTB_HOT_NODES": "-1"}, {"RTB_SHADOW_KERNEL": "wide", "RTB_NO_WIDE": "1"},
+                                 {"RTB_SHADOW_KERNEL": "split"}])
 def test_any_hit_walks_agree(env, monkeypatch):
-    """The three any-hit walks - the reference's binary tree in k_shadow, the 8-wide quantised tree (rtb_wide.h) inside
-    k_shadow, and the persistent k_shadow_wide with 0 / 64 / all-that-fit nodes of the tree top staged in shared memory by
-    a bulk copy - give the reference's film and shadow-ray counters on the mesh scenes, bit for bit."""
+    """The any-hit walks - the reference's binary tree in k_shadow (the default) and the 8-wide quantised tree (rtb_wide.h)
+    in the persistent k_shadow_wide with 0 / 64 / all-that-fit nodes of the tree top staged in shared memory by a bulk
+    copy - give the reference's film and shadow-ray counters on the mesh scenes, bit for bit.  (rtb_trace_batch and the
+    CPU build of the headers exercise the wide walk inline as well.)"""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     for scene in ("mesh_small", "textures"):
