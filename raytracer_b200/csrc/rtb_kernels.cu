@@ -454,6 +454,12 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
 #ifndef RTB_SW_MINBLOCKS
 #define RTB_SW_MINBLOCKS 2
 #endif
+#ifndef RTB_SW_DEFER
+#define RTB_SW_DEFER 1      // leaf confirmations as a warp-wide phase of their own (WideWalkDeferred) instead of inside the node visit
+#endif
+#ifndef RTB_SW_LEAF_BIAS
+#define RTB_SW_LEAF_BIAS 4  // the confirmation phase runs when (lanes with a queued leaf) * bias >= (lanes with a node to visit) * 2
+#endif
 #ifndef RTB_SW_REFILL
 #define RTB_SW_REFILL 20    // the wide phase is left for a refill when fewer than this many lanes of the warp are still inside a mesh
                             // (k_shadow_wide per 8 bench passes, 384 x 2: never 35.4 / 36.4 / 34.1 / 36.3 ms, 20: 34.1 / 34.1 / 34.3 / 35.6)
@@ -521,7 +527,12 @@ __global__ void __launch_bounds__(RTB_SW_THREADS, RTB_SW_MINBLOCKS) k_shadow_wid
     bool exhausted = false;
     uint32_t j = 0, wideTop = 0;
     ShadowWalk walk;
+#if RTB_SW_DEFER
+    WideWalkDeferred wide;
+    const uint32_t leafTop = panelBytes / (RTB_STACK_THREADS * 4u);      // the leaf queue hangs from the top of the lane's column
+#else
     WideWalk wide;
+#endif
     WideView wv; wv.nodes = nullptr; wv.tris = nullptr; wv.refNodes = nullptr; wv.maxAbs = 0.0f;
     for (;;)
     {
@@ -579,6 +590,35 @@ __global__ void __launch_bounds__(RTB_SW_THREADS, RTB_SW_MINBLOCKS) k_shadow_wid
         }
         // ---- wide phase: one node visit per iteration for every lane that is inside a mesh; it ends when those lanes are
         //      done, or - while there are rays left to draw - when so few are left inside that a refill pays ---------------------------
+#if RTB_SW_DEFER
+        // a node visit only queues the leaves it touches; the confirmations (triangle + leaf box) run as a phase of their
+        // own once enough lanes have one queued, so that both halves of the walk run at many lanes (rtb_wide.h)
+        for (;;)
+        {
+            WideStackAbove ws; ws.stack = stack; ws.sstack = sstack; ws.floor = walk.stackSize; ws.top = wideTop;
+            const bool visit = state == kWide && wide.has_nodes(ws) && wide.can_visit();
+            const bool confirm = state == kWide && wide.leafCount != 0u;
+            const uint32_t numVisit = __popc(__ballot_sync(0xFFFFFFFFu, visit));
+            const uint32_t numConfirm = __popc(__ballot_sync(0xFFFFFFFFu, confirm));
+            if (numConfirm != 0u && (numVisit == 0u || numConfirm * RTB_SW_LEAF_BIAS >= numVisit * 2u))
+            {
+                if (confirm && wide.template leaf_step<kCount>(wv, walk.ray, walk.maxDistance, ws, sstack, leafTop, &cnt))
+                {
+                    state = kIdle;
+                    W.sr1[j].w = 0.0f; W.sr2[j].w = 0.0f; W.sr3[j].w = 0.0f;
+                }
+            }
+            else if (visit)
+            {
+                wide.template node_step<kCount>(wv, walk.ray, walk.maxDistance, ws, sstack, leafTop, &cnt, fetch);
+                wideTop = ws.top;
+            }
+            if (state == kWide && wide.leafCount == 0u && !wide.has_nodes(ws)) { walk.leave_wide(S, src); state = kTop; }
+            const uint32_t inside = __ballot_sync(0xFFFFFFFFu, state == kWide);
+            if (inside == 0u) break;
+            if (!exhausted && __popc(inside) < RTB_SW_REFILL) break;
+        }
+#else
         for (;;)
         {
             if (state == kWide)
@@ -597,6 +637,7 @@ __global__ void __launch_bounds__(RTB_SW_THREADS, RTB_SW_MINBLOCKS) k_shadow_wid
             if (inside == 0u) break;
             if (!exhausted && __popc(inside) < RTB_SW_REFILL) break;
         }
+#endif
     }
     for (int o = 16; o > 0; o >>= 1) visibleLocal += __shfl_down_sync(0xFFFFFFFFu, visibleLocal, o);
     if (lane == 0 && visibleLocal) atomicAdd(&W.tot->numShadowRaysHit, visibleLocal);
@@ -1146,6 +1187,7 @@ struct RtbContext
     SceneView view;
     uint32_t numLights = 0;
     size_t stackBytes = 0;         // dynamic shared memory of the traversal kernels: the scene's worst-case stack x 128 threads x 4 B
+    size_t widePanelBytes = 0;     // k_shadow_wide's column: top-level entries + the wide tree's groups + the queue of leaves to confirm
     uint32_t tailThreshold = 65536;   // k_tail finishes a wavefront once at most this many paths are alive (RTB_TAIL_PATHS, 0 = off)
 
     // film + wavefront
@@ -1589,6 +1631,11 @@ int rtb_upload_scene(RtbContext* c, const RtbSceneDesc* scene)
     v.numLights = (uint32_t)hs.lights.size(); v.numGlobalLights = (uint32_t)hs.globalLights.size();
     c->numLights = v.numLights;
     c->stackBytes = RTB_SMEM_STACK ? (size_t)hs.stackEntries * RTB_STACK_THREADS * sizeof(uint32_t) : 0;
+    {
+        const uint32_t topEntries = hs.maxTlasDepth + hs.maxTlasLeaf + 2u;
+        const uint32_t wideEntries = std::max<uint32_t>(hs.stackEntries, topEntries + 2u * c->wideDepth + (RTB_SW_DEFER ? RTB_WIDE_LEAF_QUEUE : 0u));
+        c->widePanelBytes = (size_t)wideEntries * RTB_STACK_THREADS * sizeof(uint32_t);
+    }
     if (c->profileDepths) fprintf(stderr, "scene: top-level BVH depth %u (largest leaf %u), deepest mesh BVH %u -> %u stack entries, %zu B shared memory per CTA\n",
                                               hs.maxTlasDepth, hs.maxTlasLeaf, hs.maxBlasDepth, hs.stackEntries, c->stackBytes);
     c->hasScene = true;
@@ -1841,14 +1888,14 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
             {
                 // persistent CTAs; shared memory: barrier + staged tree top + one stack panel per 128 threads
                 const size_t perCta = (233472u - 1024u * RTB_SW_MINBLOCKS) / RTB_SW_MINBLOCKS;
-                const size_t stacks = (size_t)(RTB_SW_THREADS / 128) * c->stackBytes;
+                const size_t stacks = (size_t)(RTB_SW_THREADS / 128) * c->widePanelBytes;
                 size_t hot = perCta > stacks + 256u ? (perCta - stacks - 256u) / sizeof(WNode) : 0u;
                 if (hot > c->hotTotal) hot = c->hotTotal;
                 if (c->hotOverride >= 0 && (size_t)c->hotOverride < hot) hot = (size_t)c->hotOverride;      // (-1: all that fit)
                 const size_t smem = 128u + ((hot * sizeof(WNode) + 127u) & ~(size_t)127u) + stacks;
                 const int wideBlocks = (int)std::min<size_t>((size_t)c->numSMs * RTB_SW_MINBLOCKS, std::max<size_t>(1, ((size_t)numPaths * std::max<uint32_t>(1u, W.raysPerPath) + RTB_SW_THREADS - 1) / RTB_SW_THREADS));
-                if (count) k_shadow_wide<true><<<wideBlocks, RTB_SW_THREADS, smem, s>>>(c->view, W, d, c->hotNodes, (uint32_t)hot, (uint32_t)c->stackBytes);
-                else k_shadow_wide<false><<<wideBlocks, RTB_SW_THREADS, smem, s>>>(c->view, W, d, c->hotNodes, (uint32_t)hot, (uint32_t)c->stackBytes);
+                if (count) k_shadow_wide<true><<<wideBlocks, RTB_SW_THREADS, smem, s>>>(c->view, W, d, c->hotNodes, (uint32_t)hot, (uint32_t)c->widePanelBytes);
+                else k_shadow_wide<false><<<wideBlocks, RTB_SW_THREADS, smem, s>>>(c->view, W, d, c->hotNodes, (uint32_t)hot, (uint32_t)c->widePanelBytes);
             }
             else if (count) k_shadow<true><<<shadowBlocks, 128, c->stackBytes, s>>>(c->view, W, d);
             else k_shadow<false><<<shadowBlocks, 128, c->stackBytes, s>>>(c->view, W, d);

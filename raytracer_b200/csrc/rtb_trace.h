@@ -38,6 +38,12 @@ struct TraceCounters { uint32_t boxTests, triTests; };
 #ifndef RTB_SPLIT_FINITE
 #define RTB_SPLIT_FINITE 0
 #endif
+#ifndef RTB_TRAV_VOTE
+#define RTB_TRAV_VOTE 0        // > 0: the closest-hit node loop is left once fewer than this many lanes of the warp are still in it
+#endif
+#ifndef RTB_SHADOW_VOTE
+#define RTB_SHADOW_VOTE 0      // the same for the binary any-hit walk
+#endif
 #ifndef RTB_SHADOW_NEAR_FIRST
 #define RTB_SHADOW_NEAR_FIRST 1
 #endif      // BVH::MaxDepth is 128 (BVH.h:20); upload verifies the real depth of every tree fits
@@ -249,10 +255,6 @@ RTB_HD void load_node_pair(const DNode* nodes, uint32_t index, DNode& a, DNode& 
 #endif
 }
 
-} // namespace rtb
-#include "rtb_wide.h"
-namespace rtb {
-
 #define RTB_NUM_LEAVES(info) ((info) & 0x3FFFFFFFu)
 #define RTB_ENTRY_OBJECT 0xFFFFFFFFu    // stack entry {k, RTB_ENTRY_OBJECT}: "traverse object k" (otherwise {childIndex, leafInfo} of a node)
 
@@ -462,6 +464,11 @@ RTB_HD void scene_traverse_from(const SceneView& S, const WorldRay& worldRaySour
                     curChild = e.a; curInfo = e.b;
                 }
                 else have = false;
+#if defined(__CUDA_ARCH__) && RTB_TRAV_VOTE > 0
+                // the lanes that have reached a leaf wait for this loop to end: leave it once only a few are still
+                // walking nodes (each lane's own sequence of visits is unchanged, only the interleaving between lanes)
+                if (__popc(__activemask()) < RTB_TRAV_VOTE) break;
+#endif
             }
         };
 #if RTB_SPLIT_FINITE
@@ -470,6 +477,9 @@ RTB_HD void scene_traverse_from(const SceneView& S, const WorldRay& worldRaySour
         innerNodes(std::integral_constant<int, 0>());
 #endif
 
+#if RTB_TRAV_VOTE > 0
+        if (have && RTB_NUM_LEAVES(curInfo) == 0) continue;       // left the node loop by vote: carry on with the same node
+#endif
         if (have)
         {
             const uint32_t numLeaves = RTB_NUM_LEAVES(curInfo);
@@ -564,6 +574,10 @@ struct WideStackAbove
 #endif
     }
 };
+
+} // namespace rtb
+#include "rtb_wide.h"      // (after the stack definitions it builds on)
+namespace rtb {
 
 #ifndef RTB_WIDE_SHADOW
 #define RTB_WIDE_SHADOW 1      // 0: any-hit rays walk the reference's binary tree like closest-hit rays do
@@ -678,6 +692,9 @@ struct ShadowWalk
                 curChild = e.a; curInfo = e.b;
             }
             else have = false;
+#if defined(__CUDA_ARCH__) && RTB_SHADOW_VOTE > 0
+            if (__popc(__activemask()) < RTB_SHADOW_VOTE) break;      // (see scene_traverse_from)
+#endif
         }
 
     }
@@ -712,6 +729,9 @@ struct ShadowWalk
             if (leaf_occludes<kCount>(pendChild, pendInfo, cnt)) return kOccluded;
             pendInfo = 0;
         }
+#if RTB_SHADOW_VOTE > 0
+        if (have && RTB_NUM_LEAVES(curInfo) == 0) return kContinue;       // left the node loop by vote: carry on with the same node
+#endif
         if (have)
         {
             if (inBlas)

@@ -62,12 +62,16 @@ RTB_HD bool wide_ray_ok(const Ray& r)
 // fma(x, invDir, -(o * invDir)), this one as fma(f, step * invDir, (p - o) * invDir - step' * invDir).  Each rounding is
 // relative (2^-24) to a term bounded by (|o| + maxAbs) * |invDir|, there are fewer than eight of them, so 2^-19 of that
 // bound covers the difference with a factor of four to spare.  (The grid-step term is added per node, see wide_node_test.)
-RTB_HD float wide_ray_eps(const Ray& r, float maxAbs)
+// The bound holds axis by axis, and the slack must be per axis as well: one shared slack (the largest of the three) makes
+// a ray with one tiny direction component - invDir 10^5 on that axis, a slack of several scene lengths - pass EVERY box
+// on the other two axes too and walk the whole tree.  A few thousand such rays per launch kept a handful of warps busy
+// for 3 M cycles after all others had finished (ncu: sm__cycles_active 12.8 M min / 16.1 M max, profiles/r2j_*).
+RTB_HD V3 wide_ray_eps(const Ray& r, float maxAbs)
 {
     const float ex = (bit_abs(r.origin.x) + maxAbs) * bit_abs(r.invDir.x);
     const float ey = (bit_abs(r.origin.y) + maxAbs) * bit_abs(r.invDir.y);
     const float ez = (bit_abs(r.origin.z) + maxAbs) * bit_abs(r.invDir.z);
-    return fmaxf(ex, fmaxf(ey, ez)) * 1.9073486328125e-06f;     // 2^-19
+    return v3(ex * 1.9073486328125e-06f, ey * 1.9073486328125e-06f, ez * 1.9073486328125e-06f);     // 2^-19
 }
 
 // byte k (0..3) of w as the float 1 + byte * 2^-15 (exact): one PRMT on the device
@@ -86,7 +90,7 @@ RTB_HD float wide_byte_float(uint32_t w)
 // The 8 child tests of one node.  Returns the mask of children whose (outward-rounded, slack-widened) box the ray
 // segment [0, tMax] touches.  n1 = words 8..15 of the node (qlo x, y, z, qhi x), n2 = words 16..19 (qhi y, z).
 RTB_HD uint32_t wide_node_test(float px, float py, float pz, uint32_t eimask, const uint32_t* q /* 12 words: qlo[3][2], qhi[3][2] */,
-                               const Ray& ray, float tMax, float eps)
+                               const Ray& ray, float tMax, const V3& eps)
 {
     // grid step 2^e per axis, pre-multiplied by 2^15 (the child coordinate arrives as 1 + q * 2^-15)
     const float sx = bits2f(((eimask & 0xFFu) + 15u) << 23);
@@ -96,7 +100,7 @@ RTB_HD uint32_t wide_node_test(float px, float py, float pz, uint32_t eimask, co
     // t(q) = (p + q * 2^e - o) * invDir = f * a + (b - a),  f = 1 + q * 2^-15,  b = (p - o) * invDir
     const float bx = (px - ray.origin.x) * ray.invDir.x, by = (py - ray.origin.y) * ray.invDir.y, bz = (pz - ray.origin.z) * ray.invDir.z;
     // slack: the ray's (see wide_ray_eps) + 2^-22 of |a| for the rounding of (b - a) (= 1/128 of a grid step)
-    const float kx = fma_(bit_abs(ax), 2.384185791015625e-07f, eps), ky = fma_(bit_abs(ay), 2.384185791015625e-07f, eps), kz = fma_(bit_abs(az), 2.384185791015625e-07f, eps);
+    const float kx = fma_(bit_abs(ax), 2.384185791015625e-07f, eps.x), ky = fma_(bit_abs(ay), 2.384185791015625e-07f, eps.y), kz = fma_(bit_abs(az), 2.384185791015625e-07f, eps.z);
     const float cx = bx - ax, cy = by - ay, cz = bz - az;
     const float clx = cx - kx, chx = cx + kx, cly = cy - ky, chy = cy + ky, clz = cz - kz, chz = cz + kz;
     // entry planes: qlo for a positive direction, qhi for a negative one
@@ -180,7 +184,7 @@ struct WideWalk
 {
     enum { kContinue = 0, kOccluded = 1, kMissed = 2 };
     uint32_t base, bits;
-    float eps;
+    V3 eps;
 
     RTB_HD void begin(const Ray& ray, float maxAbs)
     {
@@ -233,6 +237,114 @@ struct WideWalk
         base = n[4];
         bits = (hit & imask) | (imask << 8);
         return kContinue;
+    }
+};
+
+// The same walk with the leaf confirmations taken OUT of the node visit (k_shadow_wide, RTB_SW_DEFER).  ncu on WideWalk
+// showed why the 8-wide tree bought so little: the eight child tests ran at 26 of 32 lanes, but the triangle / leaf-box
+// confirmations inside step() ran at 2-4 lanes (each lane meets its leaves at a different visit) and took 37 % of the
+// kernel's warp instructions.  Here a node visit only QUEUES the leaves it touches (one word per visit: node index | mask
+// of the touched leaf children << 24) and leaf_step() confirms one queued leaf; the kernel runs either as a warp-wide
+// phase, chosen by vote, so that both run at many lanes.  Any-hit: the order in which leaves are confirmed cannot
+// change the boolean.  The queue grows downwards from entry `leafTop` of the lane's shared-memory column (the node
+// groups grow upwards from the floor); the caller keeps RTB_WIDE_LEAF_QUEUE entries free for it and lets a lane visit
+// a node only while can_visit() holds (one more entry fits).
+#define RTB_WIDE_LEAF_QUEUE 8u
+struct WideWalkDeferred
+{
+    uint32_t base, bits, leafCount;
+    V3 eps;
+
+    RTB_HD void begin(const Ray& ray, float maxAbs)
+    {
+        eps = wide_ray_eps(ray, maxAbs);
+        base = 0u; bits = 0x0101u; leafCount = 0u;
+    }
+    template <typename Stack> RTB_HD bool has_nodes(const Stack& stk) const { return (bits & 0xFFu) != 0u || !stk.empty(); }
+    RTB_HD bool can_visit() const { return leafCount < RTB_WIDE_LEAF_QUEUE; }
+
+    // one node visit; the lane has_nodes() and can_visit()
+    template <bool kCount, typename Stack, typename Fetch>
+    RTB_HD void node_step(const WideView& W, const Ray& ray, float tMax, Stack& stk, SharedStack sstack, uint32_t leafTop, TraceCounters* cnt, const Fetch& fetch)
+    {
+        if ((bits & 0xFFu) == 0u) stk.pop(base, bits);
+        const uint32_t pending = bits & 0xFFu;
+#if defined(__CUDA_ARCH__)
+        const uint32_t slot = 31u - (uint32_t)__clz(pending & (0u - pending));
+#else
+        const uint32_t slot = 31u - (uint32_t)__builtin_clz(pending & (0u - pending));
+#endif
+        bits &= ~(1u << slot);
+        const uint32_t below = (bits >> 8) & ((1u << slot) - 1u);
+#if defined(__CUDA_ARCH__)
+        const uint32_t index = base + __popc(below);
+#else
+        const uint32_t index = base + (uint32_t)__builtin_popcount(below);
+#endif
+        if (bits & 0xFFu) stk.push(base, bits);
+
+        uint32_t n[20];
+        fetch(W.nodes, index, n);
+        const uint32_t imask = n[3] >> 24;
+        const uint32_t hit = wide_node_test(bits2f(n[0]), bits2f(n[1]), bits2f(n[2]), n[3], n + 8, ray, tMax, eps) & (n[5] >> 24);
+        if (kCount) cnt->boxTests += 8;
+        // ONE queue entry per visit whatever the number of leaves touched (node index | mask of the touched leaf children << 24);
+        // leaf_step() decodes a child from the node's meta words when its turn comes.  (A loop that pushed one entry per
+        // leaf ran at 3.8 lanes and took 5 % of the kernel's warp instructions.)
+        const uint32_t leaves = hit & ~imask;
+        if (leaves)
+        {
+            leafCount++;
+            const uint32_t entry = index | (leaves << 24);
+#if RTB_SSTACK
+            asm volatile("st.shared.u32 [%0], %1;" :: "r"(sstack + (leafTop - leafCount) * (RTB_STACK_THREADS * 4u)), "r"(entry));
+#else
+            (void)sstack; stk.stack[leafTop - leafCount] = entry;
+#endif
+        }
+        base = n[4];
+        bits = (hit & imask) | (imask << 8);
+    }
+
+    // confirm one queued leaf (leafCount != 0); true: the ray is occluded
+    template <bool kCount, typename Stack>
+    RTB_HD bool leaf_step(const WideView& W, const Ray& ray, float tMax, const Stack& stk, SharedStack sstack, uint32_t leafTop, TraceCounters* cnt)
+    {
+        uint32_t entry;
+#if RTB_SSTACK
+        (void)stk;
+        const uint32_t slotAddr = sstack + (leafTop - leafCount) * (RTB_STACK_THREADS * 4u);
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(entry) : "r"(slotAddr));
+#else
+        (void)sstack; entry = stk.stack[leafTop - leafCount];
+#endif
+        const uint32_t index = entry & 0x00FFFFFFu;
+        uint32_t mask = entry >> 24;
+#if defined(__CUDA_ARCH__)
+        const uint32_t s = 31u - (uint32_t)__clz(mask & (0u - mask));
+        const uint4 w = RTB_LDG(reinterpret_cast<const uint4*>(W.nodes + index) + 1);       // childBase, triBaseValid, meta[0], meta[1]
+#else
+        const uint32_t s = 31u - (uint32_t)__builtin_clz(mask & (0u - mask));
+        const WNode& nd = W.nodes[index];
+        struct { uint32_t x, y, z, w; } w = { nd.childBase, nd.triBaseValid, nd.meta[0], nd.meta[1] };
+#endif
+        mask &= mask - 1u;
+        if (mask)
+        {
+            // more touched leaves in this node: the entry stays, without the child taken now
+#if RTB_SSTACK
+            asm volatile("st.shared.u32 [%0], %1;" :: "r"(slotAddr), "r"(index | (mask << 24)));
+#else
+            stk.stack[leafTop - leafCount] = index | (mask << 24);
+#endif
+        }
+        else leafCount--;
+        const uint32_t m = (((s & 4u) ? w.w : w.z) >> (8u * (s & 3u))) & 0xFFu;
+        const uint32_t firstTri = (w.y & 0x00FFFFFFu) + (m & 31u), numTris = ((m >> 5) & 3u) + 1u;
+        if (kCount) cnt->triTests += numTris;
+        bool occluded = false;
+        for (uint32_t i = 0; i < numTris; ++i) if (wide_confirm(W, ray, tMax, firstTri + i)) occluded = true;
+        return occluded;
     }
 };
 

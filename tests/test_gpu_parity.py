@@ -783,3 +783,40 @@ def test_wavefront_launch_chain_as_a_cuda_graph(graph, monkeypatch):
                 util.assert_bit_identical(c.read_sum(), want, "%s/%s graph=%s batched=%s" % (scene, renderer, graph, batched))
                 counters = c.counters()
             assert counters["numRays"] == meta["numRays"] and counters["numShadowRays"] == meta["numShadowRays"]
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="prebuilt oracle/_ref/exact did not travel to this box")
+@pytest.mark.parametrize("scene,passes", [("materials", 400), ("mesh_small", 300)])
+def test_single_light_sampling_statistics_against_the_live_reference(tmp_path, scene, passes):
+    """LightSamplingStrategy::Single (the reference's default, Context.h:82, PathTracerMIS.cpp:128-146): one light per
+    vertex, picked uniformly, contribution scaled by the number of lights.  The reference picks with its per-thread
+    generator, so the bar is statistical: the converged mean per channel and the image at 8 x 8-pixel blocks agree with
+    the reference's `single` render, both agree with the `all` estimator (same expectation), and the shadow-ray count is
+    the reference's to within the sampling noise (one shadow ray per vertex at most, instead of one per light)."""
+    w = h = 48
+    scn = os.path.join(util.GOLDEN, "scenes")
+    common = ["--scene", os.path.join(scn, scene + ".json"), "--data", scn + "/", "--width", w, "--height", h]
+    refp, passp, flatp = (str(tmp_path / n) for n in ("ref.sum", "ref.passes", "scene.rtb"))
+    meta = util.run_rtref(["render", *common, "--passes", passes, "--dims", 256, "--depth", 8, "--strategy", "single", "--dump-sum", refp, "--dump-passes", passp])
+    util.run_rtref(["flat", *common, "--out", flatp])
+    ref = util.load_sum(refp, w, h) / passes
+    sf = capi.SceneFile(flatp)
+    ps = capi.PassScript(passp)
+    imgs, counters = {}, {}
+    for name, strategy in (("single", capi.RTB_LIGHT_SAMPLING_SINGLE), ("all", capi.RTB_LIGHT_SAMPLING_ALL)):
+        with capi.Context(device=0) as c:
+            c.upload_scene(sf)
+            c.resize(w, h)
+            c.render_passes(capi.camera_for(sf, w, h), ps.seeds[:passes], ps.offsets[:passes], 0, max_depth=8, strategy=strategy)
+            imgs[name], counters[name] = c.read_sum() / passes, c.counters()
+    blocks = lambda x: x.reshape(6, 8, 6, 8, 3).mean(axis=(1, 3)).ravel()
+    for name in ("single", "all"):
+        got = imgs[name]
+        assert np.isfinite(got).all() and (got >= 0).all()
+        ma, mb = ref.mean(axis=(0, 1)), got.mean(axis=(0, 1))
+        assert (np.abs(ma - mb) <= 0.03 * ma).all(), (name, ma, mb)
+        assert np.corrcoef(blocks(ref), blocks(got))[0, 1] >= 0.995, name
+    # the camera paths are the reference's (same sampler), so the path-ray count is close; shadow rays: at most one per vertex
+    assert counters["single"]["numPrimaryRays"] == meta["numPrimaryRays"] == w * h * passes
+    assert abs(counters["single"]["numShadowRays"] - meta["numShadowRays"]) <= 0.02 * meta["numShadowRays"]
+    assert counters["single"]["numShadowRays"] < counters["all"]["numShadowRays"]

@@ -18,6 +18,14 @@ o[:, :3] = rng.uniform([-14, 0.05, -6], [14, 11, 6], (n, 3))
 v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
 # half of the rays point to the upper hemisphere (sky / sun samples), like the bench's shadow rays
 v[: n // 2, 1] = np.abs(v[: n // 2, 1])
+# WIDE_STATS_NEAR_AXIS=f: that fraction of the rays gets one direction component shrunk to ~1e-5 (|invDir| ~ 1e5 on that axis:
+# the case that made a shared per-ray slack pass every box, see rtb_wide.h wide_ray_eps)
+frac = float(os.environ.get("WIDE_STATS_NEAR_AXIS", "0"))
+if frac > 0:
+    k = int(n * frac)
+    ax = rng.integers(0, 3, k)
+    v[np.arange(k), ax] *= 1e-5
+    v[:k] /= np.linalg.norm(v[:k], axis=1, keepdims=True)
 d[:, :3] = v
 with np.errstate(divide="ignore"):
     inv = np.zeros((n, 4), np.float32); inv[:, :3] = (np.float32(1.0) / d[:, :3]).astype(np.float32)
