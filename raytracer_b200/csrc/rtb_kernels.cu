@@ -259,23 +259,92 @@ struct DeviceSink
     __device__ void end_lights(const V4& thr) { lightThr = thr; }
 };
 
-template <bool kTex>
+// ---- material binning before shading (north_star: "material sorting before shade") ---------------------------------------
+// shade_vertex_* is one large switch: miss / light hit / surface hit, then nine BSDFs (sample + evaluate per light), and
+// a warp executes every branch any of its lanes takes.  Each CTA therefore takes a TILE of RTB_SHADE_TILE consecutive paths,
+// computes a key per path (miss, light, or BSDF of the material at the hit x mesh / analytic shape) and counting-sorts the
+// tile's indices by key in shared memory (histogram with shared atomics, 32-bin scan by one warp, scatter); its threads then
+// shade the tile in key order, so all but the warps that straddle a bin boundary run ONE branch.  The sort is local to a
+// CTA: no extra kernel, no extra pass over HBM (the 16-byte hit records the keys need are read again from L1 by the
+// shading itself), the path state of a tile is gathered from a 1024-path window that the CTA consumes entirely.
+// A path owns its pixel's pass colour and its own shadow-ray slots, so the order in which paths are shaded cannot change
+// the film (the compacted output order is not deterministic to begin with: one atomic per warp).
+#ifndef RTB_SHADE_TILE
+#define RTB_SHADE_TILE 1024u
+#endif
+#define RTB_SHADE_BINS 32u
+
+__device__ __forceinline__ uint32_t shade_key(const SceneView& S, uint32_t objectId, uint32_t subObjectId)
+{
+    if (objectId == RTB_INVALID_OBJECT) return 0u;                       // miss: background lights
+    if (subObjectId == RTB_LIGHT_OBJECT) return 1u;                      // a light hit directly
+    const DObjectShade& obj = S.objShade[objectId];
+    uint32_t material = obj.materialIndex;
+    const RtbShape& shape = S.shapes[obj.shapeIndex];
+    const bool mesh = shape.type == RTB_SHAPE_MESH;
+    if (mesh)
+    {
+        const DMesh& m = S.meshes[shape.meshIndex];
+        const uint32_t slot = m.indices[subObjectId].materialIndex;
+        if (slot != 0xFFFFFFFFu) material = m.materialIds[slot];
+    }
+    const uint32_t bsdf = material != RTB_NO_MATERIAL ? S.materials[material].bsdf : 14u;
+    return 2u + (bsdf < 14u ? bsdf : 14u) + (mesh ? 0u : 15u);       // 2..16 mesh, 17..31 analytic shapes
+}
+
+template <bool kTex, bool kSort>
 __global__ void __launch_bounds__(128, RTB_SHADE_MINBLOCKS) k_shade(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const __grid_constant__ Wavefront W, uint32_t depth)
 {
     const uint32_t count = W.ctl->tailTaken ? 0u : W.ctl->pathCount[depth];
     const PathBuf& in = W.buf[depth & 1];
     const PathBuf& out = W.buf[(depth + 1) & 1];
-    const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
-    // loop bound rounded up to a whole warp so that every lane takes part in the ballots
-    const uint32_t countUp = (count + 31u) & ~31u;
     unsigned long long shadowRaysLocal = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < countUp; i += stride)
+    __shared__ uint16_t tileOrder[kSort ? RTB_SHADE_TILE : 1u];
+    __shared__ uint8_t tileKeys[kSort ? RTB_SHADE_TILE : 1u];
+    __shared__ uint32_t binCursor[RTB_SHADE_BINS];
+#pragma unroll 1
+    for (uint32_t tileBase = blockIdx.x * RTB_SHADE_TILE; tileBase < count; tileBase += gridDim.x * RTB_SHADE_TILE)
     {
+    const uint32_t tileCount = min(RTB_SHADE_TILE, count - tileBase);
+    if (kSort)
+    {
+        __syncthreads();                                   // the previous tile's order is no longer read
+        if (threadIdx.x < RTB_SHADE_BINS) binCursor[threadIdx.x] = 0u;
+        __syncthreads();
+        for (uint32_t j = threadIdx.x; j < tileCount; j += 128u)
+        {
+            const uint4 h0 = W.hit0[tileBase + j];
+            const uint32_t key = shade_key(S, h0.x, h0.y);
+            tileKeys[j] = (uint8_t)key;
+            atomicAdd(&binCursor[key], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32u)
+        {
+            const uint32_t v = binCursor[lane];
+            uint32_t incl = v;
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= (uint32_t)o) incl += up;
+            }
+            binCursor[lane] = incl - v;
+        }
+        __syncthreads();
+        for (uint32_t j = threadIdx.x; j < tileCount; j += 128u) tileOrder[atomicAdd(&binCursor[tileKeys[j]], 1u)] = (uint16_t)j;
+        __syncthreads();
+    }
+    // (loop bound rounded up to a whole warp so that every lane takes part in the ballots)
+#pragma unroll 1
+    for (uint32_t j = threadIdx.x; j < ((tileCount + 31u) & ~31u); j += 128u)
+    {
+        const bool valid = j < tileCount;
+        const uint32_t i = tileBase + (kSort ? (valid ? (uint32_t)tileOrder[j] : 0u) : j);
         bool alive = false;
         uint32_t numShadow = 0;
         PathState ps;
-        if (i < count)
+        if (valid)
         {
             load_path(in, i, W, P.width, P.numSeedDims, ps);
             const uint4 h0 = W.hit0[i];
@@ -333,6 +402,7 @@ __global__ void __launch_bounds__(128, RTB_SHADE_MINBLOCKS) k_shade(const __grid
                 for (uint32_t r = 0; r < numShadow; ++r) W.rayList[first + r] = i * W.raysPerPath + r;
             }
         }
+    }
     }
     // counters: one atomic per warp
     for (int o = 16; o > 0; o >>= 1) shadowRaysLocal += __shfl_down_sync(0xFFFFFFFFu, shadowRaysLocal, o);
@@ -458,10 +528,10 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
 #define RTB_SW_DEFER 1      // leaf confirmations as a warp-wide phase of their own (WideWalkDeferred) instead of inside the node visit
 #endif
 #ifndef RTB_SW_LEAF_BIAS
-#define RTB_SW_LEAF_BIAS 4  // the confirmation phase runs when (lanes with a queued leaf) * bias >= (lanes with a node to visit) * 2
+#define RTB_SW_LEAF_BIAS 2  // the confirmation phase runs when (lanes with a queued leaf) * bias >= (lanes with a node to visit) * 2
 #endif
 #ifndef RTB_SW_REFILL
-#define RTB_SW_REFILL 20    // the wide phase is left for a refill when fewer than this many lanes of the warp are still inside a mesh
+#define RTB_SW_REFILL 16    // the wide phase is left for a refill when fewer than this many lanes of the warp are still inside a mesh
                             // (k_shadow_wide per 8 bench passes, 384 x 2: never 35.4 / 36.4 / 34.1 / 36.3 ms, 20: 34.1 / 34.1 / 34.3 / 35.6)
 #endif
 
@@ -485,7 +555,7 @@ struct WideFetchHot
     }
 };
 
-template <bool kCount>
+template <bool kCount, bool kHot>
 __global__ void __launch_bounds__(RTB_SW_THREADS, RTB_SW_MINBLOCKS) k_shadow_wide(const __grid_constant__ SceneView S, const __grid_constant__ Wavefront W, uint32_t depth,
                                                                                   const WNode* __restrict__ hotNodes, uint32_t hotCount, uint32_t panelBytes)
 {
@@ -496,7 +566,7 @@ __global__ void __launch_bounds__(RTB_SW_THREADS, RTB_SW_MINBLOCKS) k_shadow_wid
     const uint32_t hotBytes = hotCount * (uint32_t)sizeof(WNode);
     const uint32_t stackBase = hotShared + ((hotBytes + 127u) & ~127u);
     const uint32_t count = W.ctl->tailTaken ? 0u : W.ctl->shadowRayCount[depth];
-    if (hotCount)
+    if (kHot && hotCount)
     {
         if (threadIdx.x == 0)
         {
@@ -513,8 +583,10 @@ __global__ void __launch_bounds__(RTB_SW_THREADS, RTB_SW_MINBLOCKS) k_shadow_wid
         }
         __syncthreads();       // the barrier is initialised before anyone waits on it
     }
-    bool hotReady = hotCount == 0u;
-    WideFetchHot fetch; fetch.hotNodes = hotNodes; fetch.hotCount = hotCount; fetch.hotShared = hotShared;
+    // (the instantiation without staged nodes has none of this in its node visit: the staging is an option that did not pay, §4a)
+    bool hotReady = !kHot || hotCount == 0u;
+    typename std::conditional<kHot, WideFetchHot, WideFetchGlobal>::type fetch;
+    if constexpr (kHot) { fetch.hotNodes = hotNodes; fetch.hotCount = hotCount; fetch.hotShared = hotShared; }
 
     const uint32_t lane = threadIdx.x & 31u;
     SharedStack sstack = stackBase + (threadIdx.x >> 7) * panelBytes + (threadIdx.x & 127u) * 4u;
@@ -1254,8 +1326,9 @@ struct RtbContext
     bool useGraphs = true;                // RTB_GRAPH=0: plain launches
     bool exclusiveStream = false;         // the wavefront streams belong to this context alone (RtbCreateDesc::stream given, or RTB_SLOTS > 1)
     bool noWide = false;                  // RTB_NO_WIDE: any-hit rays walk the binary tree (A/B against rtb_wide.h)
-    int shadowKernel = 0;                 // RTB_SHADOW_KERNEL: 0 simple = k_shadow, 1 wide = k_shadow_wide, 2 split = k_shadow_top + k_shadow_mesh
-    bool wideKernel = false;              // RTB_SHADOW_KERNEL=wide: k_shadow_wide (8-wide tree, persistent warps) for any-hit rays instead of k_shadow
+    bool sortShade = true;                // RTB_SORT_SHADE=0: k_shade takes its tile of paths in queue order instead of binned by material
+    int shadowKernel = 1;                 // RTB_SHADOW_KERNEL: 0 simple = k_shadow (binary tree), 1 wide = k_shadow_wide (the default), 2 split = k_shadow_top + k_shadow_mesh
+    bool wideKernel = true;               // k_shadow_wide (8-wide tree, persistent warps, deferred leaf confirmations) for any-hit rays
                                           // (binary tree).  Same results; measured on the bench it does not beat the binary walk
     const WNode* hotNodes = nullptr;      // the scene's largest 8-wide tree ...
     uint32_t hotTotal = 0;                // ... and its node count
@@ -1460,8 +1533,10 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
         cudaFuncSetAttribute(k_trace_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
         cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
         cudaFuncSetAttribute(k_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
-        cudaFuncSetAttribute(k_shadow_wide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-        cudaFuncSetAttribute(k_shadow_wide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        cudaFuncSetAttribute(k_shadow_wide<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        cudaFuncSetAttribute(k_shadow_wide<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        cudaFuncSetAttribute(k_shadow_wide<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        cudaFuncSetAttribute(k_shadow_wide<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         cudaFuncSetAttribute(k_shadow_top<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
         cudaFuncSetAttribute(k_shadow_top<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
         if (const char* t = getenv("RTB_TAIL_PATHS")) c->tailThreshold = (uint32_t)strtoul(t, nullptr, 10);
@@ -1471,7 +1546,7 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
     if (const char* t = getenv("RTB_CARVEOUT"))
     {
         const int pct = atoi(t);
-        const void* all[] = { (const void*)k_raygen, (const void*)k_traverse<false>, (const void*)k_traverse<true>, (const void*)k_shade<false>, (const void*)k_shade<true>,
+        const void* all[] = { (const void*)k_raygen, (const void*)k_traverse<false>, (const void*)k_traverse<true>, (const void*)k_shade<false, false>, (const void*)k_shade<true, false>, (const void*)k_shade<false, true>, (const void*)k_shade<true, true>,
                               (const void*)k_shadow<false>, (const void*)k_shadow<true>, (const void*)k_tail<false>, (const void*)k_tail<true>, (const void*)k_resolve,
                               (const void*)k_film, (const void*)k_unshard, (const void*)k_front };
         for (const void* f : all) cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
@@ -1497,7 +1572,8 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
     // an instrumented context counts the REFERENCE's work per ray (box / triangle tests of its binary tree: the algorithmic
     // bytes of SURVEY 8(d)); RTB_COUNT_WIDE makes it count what the 8-wide walk does instead (8 "box tests" per node visited)
     if ((c->flags & RTB_FLAG_COUNT_TESTS) != 0 && !getenv("RTB_COUNT_WIDE")) c->noWide = true;
-    if (const char* t = getenv("RTB_SHADOW_KERNEL")) { c->shadowKernel = !strcmp(t, "wide") ? 1 : !strcmp(t, "split") ? 2 : 0; c->wideKernel = c->shadowKernel != 0; }
+    if (const char* t = getenv("RTB_SORT_SHADE")) c->sortShade = atoi(t) != 0;
+    if (const char* t = getenv("RTB_SHADOW_KERNEL")) { c->shadowKernel = !strcmp(t, "simple") ? 0 : !strcmp(t, "split") ? 2 : 1; c->wideKernel = c->shadowKernel != 0; }
     if (const char* t = getenv("RTB_HOT_NODES")) c->hotOverride = atoi(t);
     c->slots.resize(numSlots);
     e = c->totals.alloc(1);
@@ -1841,6 +1917,7 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
     const int blocks128 = (int)std::min<size_t>((size_t)blocksCap, std::max<size_t>(1, ((size_t)numPaths + 127) / 128));
     const int blocksShadow = (int)std::min<size_t>((size_t)blocksCap, std::max<size_t>(1, ((size_t)numPaths * std::max<uint32_t>(1u, W.raysPerPath) + 127) / 128));
     const int blocks256 = c->numSMs * 4;
+    const int blocksShade = (int)std::min<size_t>((size_t)blocks128, std::max<size_t>(1, ((size_t)numPaths + RTB_SHADE_TILE - 1) / RTB_SHADE_TILE));
     // the instrumented (counting) context keeps the plain wavefront so that its per-ray test counters stay per kernel
     const uint32_t tailThreshold = (count || pass->renderer == RTB_RENDERER_DEBUG) ? 0u : c->tailThreshold;
     const int tailBlocks = tailThreshold ? (int)std::min<size_t>((size_t)blocks128, ((size_t)tailThreshold + 127) / 128) : 0;
@@ -1860,8 +1937,14 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
         if (count) k_traverse<true><<<blocks128, 128, c->stackBytes, s>>>(c->view, W, d);
         else k_traverse<false><<<blocks128, 128, c->stackBytes, s>>>(c->view, W, d);
         if (prof) marks.push_back(next_event(c, ev, s));
-        if (textured) k_shade<true><<<blocks128, 128, 0, s>>>(c->view, P, W, d);
-        else k_shade<false><<<blocks128, 128, 0, s>>>(c->view, P, W, d);
+        // (a tile of RTB_SHADE_TILE paths per CTA and loop iteration)
+        if (c->sortShade)
+        {
+            if (textured) k_shade<true, true><<<blocksShade, 128, 0, s>>>(c->view, P, W, d);
+            else k_shade<false, true><<<blocksShade, 128, 0, s>>>(c->view, P, W, d);
+        }
+        else if (textured) k_shade<true, false><<<blocksShade, 128, 0, s>>>(c->view, P, W, d);
+        else k_shade<false, false><<<blocksShade, 128, 0, s>>>(c->view, P, W, d);
         if (prof) marks.push_back(next_event(c, ev, s));
         if (shadows)
         {
@@ -1894,8 +1977,13 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
                 if (c->hotOverride >= 0 && (size_t)c->hotOverride < hot) hot = (size_t)c->hotOverride;      // (-1: all that fit)
                 const size_t smem = 128u + ((hot * sizeof(WNode) + 127u) & ~(size_t)127u) + stacks;
                 const int wideBlocks = (int)std::min<size_t>((size_t)c->numSMs * RTB_SW_MINBLOCKS, std::max<size_t>(1, ((size_t)numPaths * std::max<uint32_t>(1u, W.raysPerPath) + RTB_SW_THREADS - 1) / RTB_SW_THREADS));
-                if (count) k_shadow_wide<true><<<wideBlocks, RTB_SW_THREADS, smem, s>>>(c->view, W, d, c->hotNodes, (uint32_t)hot, (uint32_t)c->widePanelBytes);
-                else k_shadow_wide<false><<<wideBlocks, RTB_SW_THREADS, smem, s>>>(c->view, W, d, c->hotNodes, (uint32_t)hot, (uint32_t)c->widePanelBytes);
+                if (hot)
+                {
+                    if (count) k_shadow_wide<true, true><<<wideBlocks, RTB_SW_THREADS, smem, s>>>(c->view, W, d, c->hotNodes, (uint32_t)hot, (uint32_t)c->widePanelBytes);
+                    else k_shadow_wide<false, true><<<wideBlocks, RTB_SW_THREADS, smem, s>>>(c->view, W, d, c->hotNodes, (uint32_t)hot, (uint32_t)c->widePanelBytes);
+                }
+                else if (count) k_shadow_wide<true, false><<<wideBlocks, RTB_SW_THREADS, smem, s>>>(c->view, W, d, c->hotNodes, 0u, (uint32_t)c->widePanelBytes);
+                else k_shadow_wide<false, false><<<wideBlocks, RTB_SW_THREADS, smem, s>>>(c->view, W, d, c->hotNodes, 0u, (uint32_t)c->widePanelBytes);
             }
             else if (count) k_shadow<true><<<shadowBlocks, 128, c->stackBytes, s>>>(c->view, W, d);
             else k_shadow<false><<<shadowBlocks, 128, c->stackBytes, s>>>(c->view, W, d);
@@ -1928,7 +2016,7 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
             memset(&k, 0, sizeof(k));
             memcpy(&k.P, &P, sizeof(P)); memcpy(&k.W, &W, sizeof(W)); memcpy(&k.S, &c->view, sizeof(SceneView));
             k.P.passIndex = 0; k.P.sampleOffsetX = 0.0f; k.P.sampleOffsetY = 0.0f; k.W.firstPassIndex = 0;
-            k.numPaths = numPaths; k.depthLimit = depthLimit; k.tailBlocks = (uint32_t)tailBlocks; k.flags = (shadows ? 1u : 0u) | (textured ? 2u : 0u);
+            k.numPaths = numPaths; k.depthLimit = depthLimit; k.tailBlocks = (uint32_t)tailBlocks; k.flags = (shadows ? 1u : 0u) | (textured ? 2u : 0u) | (c->sortShade ? 4u : 0u);
             k.stackBytes = c->stackBytes; k.hot = c->hotNodes; k.hotOverride = c->hotOverride; k.wide = c->shadowKernel;
             memcpy(key.data(), &k, sizeof(k));
         }

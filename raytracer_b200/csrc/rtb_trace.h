@@ -39,10 +39,10 @@ struct TraceCounters { uint32_t boxTests, triTests; };
 #define RTB_SPLIT_FINITE 0
 #endif
 #ifndef RTB_TRAV_VOTE
-#define RTB_TRAV_VOTE 0        // > 0: the closest-hit node loop is left once fewer than this many lanes of the warp are still in it
+#define RTB_TRAV_VOTE 6        // > 0: the closest-hit node loop is left once fewer than this many lanes of the warp are still in it
 #endif
 #ifndef RTB_SHADOW_VOTE
-#define RTB_SHADOW_VOTE 0      // the same for the binary any-hit walk
+#define RTB_SHADOW_VOTE 6      // the same for the binary any-hit walk
 #endif
 #ifndef RTB_SHADOW_NEAR_FIRST
 #define RTB_SHADOW_NEAR_FIRST 1
@@ -149,6 +149,36 @@ RTB_HD bool triangle_ray_below(const Ray& ray, const V3& v0, const V3& e1, const
     outU = u / det;
     outV = v / det;
     outT = t / det;
+    return !(upv > 1.0f) && (outV > 0.0f) && (outT > 0.0f) && (outU > 0.0f) && (outT < tLimit);
+}
+
+// "triangle_ray(...) && outT < tLimit" as a boolean only (any-hit rays).  On top of the screen above: when every one of the
+// reference's comparisons is decided with room to spare the quotients need not be formed at all -
+//   u / det > 0 (FTZ division): numerator and determinant agree in sign and the quotient cannot underflow (>= 2^-100);
+//   !((u + v) / det > 1):       |fl(u + v)| <= |det| * (1 - 2^-20): the quotient is below 1 before and after rounding;
+//   t / det < tLimit:           |t| <= fl(fl(tLimit * |det|) * (1 - 2^-20)) with a finite product: the real quotient is
+//                               below tLimit * (1 - 2^-21), so its rounding is below tLimit.
+// Candidates inside those margins (hits within 2^-20 of an edge or of tLimit) take the reference's divisions.
+RTB_HD bool triangle_ray_occludes(const Ray& ray, const V3& v0, const V3& e1, const V3& e2, float tLimit)
+{
+    const V3 tvec = ray.origin - v0;
+    const V3 pvec = cross3(ray.dir, e2);
+    const V3 qvec = cross3(tvec, e1);
+    const float det = dot3(e1, pvec);
+    const float u = dot3(tvec, pvec);
+    const float v = dot3(ray.dir, qvec);
+    const float t = dot3(e2, qvec);
+    const uint32_t sign = f2bits(det) & 0x80000000u;
+    const float ad = bits2f(f2bits(det) ^ sign);                          // |det|
+    const float su = bits2f(f2bits(u) ^ sign), sv = bits2f(f2bits(v) ^ sign), st = bits2f(f2bits(t) ^ sign);
+    const float slack = 1.00000095367431640625f;                          // 1 + 2^-20
+    const float sum = bit_abs(u + v), lim = tLimit * ad;
+    if (!(su > 0.0f && sv > 0.0f && st > 0.0f && sum <= ad * slack && st < lim * slack)) return false;
+    const float tight = 0.99999904632568359375f;                          // 1 - 2^-20
+    const float tiny = ad * 7.8886090522101181e-31f;                      // 2^-100 (flushes to 0 for |det| < 2^-26: then any normal numerator is far enough)
+    if (su >= tiny && sv >= tiny && st >= tiny && sum <= ad * tight && is_finite_bits(lim) && st <= lim * tight) return true;
+    const float upv = (u + v) / det;
+    const float outU = u / det, outV = v / det, outT = t / det;
     return !(upv > 1.0f) && (outV > 0.0f) && (outT > 0.0f) && (outU > 0.0f) && (outT < tLimit);
 }
 
@@ -634,8 +664,7 @@ struct ShadowWalk
         {
             V3 v0, e1, e2;
             load_tri(tris, first + i, v0, e1, e2);
-            float u, v, distance;
-            if (triangle_ray_below(ray, v0, e1, e2, maxDistance, u, v, distance)) occluded = true;
+            if (triangle_ray_occludes(ray, v0, e1, e2, maxDistance)) occluded = true;
         }
         return occluded;
     }

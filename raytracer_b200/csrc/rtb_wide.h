@@ -75,15 +75,21 @@ RTB_HD V3 wide_ray_eps(const Ray& r, float maxAbs)
 }
 
 // byte k (0..3) of w as the float 1 + byte * 2^-15 (exact): one PRMT on the device
+#if defined(__CUDACC__)
+__constant__ uint32_t g_wideOne = 0x3F800000u;      // bits of 1.0f, see wide_byte_float
+#endif
+// (`one` = 0x3F800000 held in a register the compiler cannot see through: PRMT takes one immediate, and with both the
+//  constant and the selector known ptxas kept the constant as the immediate and rebuilt the SELECTOR in a register
+//  before every one of the 48 PRMTs of a node visit - 47 extra IMAD.U32 of 297 instructions)
 template <int k>
-RTB_HD float wide_byte_float(uint32_t w)
+RTB_HD float wide_byte_float(uint32_t w, uint32_t one)
 {
 #if defined(__CUDA_ARCH__)
     uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x3F800000u), "n"(0x7604 | (k << 4)));
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(one), "n"(0x7604 | (k << 4)));
     return __uint_as_float(r);
 #else
-    return bits2f(0x3F800000u | (((w >> (8 * k)) & 0xFFu) << 8));
+    return bits2f(one | (((w >> (8 * k)) & 0xFFu) << 8));
 #endif
 }
 
@@ -109,10 +115,15 @@ RTB_HD uint32_t wide_node_test(float px, float py, float pz, uint32_t eimask, co
     const uint32_t nearY0 = ny ? q[8] : q[2], nearY1 = ny ? q[9] : q[3], farY0 = ny ? q[2] : q[8], farY1 = ny ? q[3] : q[9];
     const uint32_t nearZ0 = nz ? q[10] : q[4], nearZ1 = nz ? q[11] : q[5], farZ0 = nz ? q[4] : q[10], farZ1 = nz ? q[5] : q[11];
     uint32_t mask = 0;
+#if defined(__CUDA_ARCH__)
+    const uint32_t one = g_wideOne;          // (from constant memory: a value ptxas cannot fold back into an immediate)
+#else
+    const uint32_t one = 0x3F800000u;
+#endif
 #define RTB_WIDE_CHILD(i, k, NX, NY, NZ, FX, FY, FZ)                                                          \
     {                                                                                                           \
-        const float tlx = fma_(wide_byte_float<k>(NX), ax, clx), tly = fma_(wide_byte_float<k>(NY), ay, cly), tlz = fma_(wide_byte_float<k>(NZ), az, clz); \
-        const float thx = fma_(wide_byte_float<k>(FX), ax, chx), thy = fma_(wide_byte_float<k>(FY), ay, chy), thz = fma_(wide_byte_float<k>(FZ), az, chz); \
+        const float tlx = fma_(wide_byte_float<k>(NX, one), ax, clx), tly = fma_(wide_byte_float<k>(NY, one), ay, cly), tlz = fma_(wide_byte_float<k>(NZ, one), az, clz); \
+        const float thx = fma_(wide_byte_float<k>(FX, one), ax, chx), thy = fma_(wide_byte_float<k>(FY, one), ay, chy), thz = fma_(wide_byte_float<k>(FZ, one), az, chz); \
         const float tmin = fmaxf(fmaxf(tlx, tly), fmaxf(tlz, 0.0f));                                            \
         const float tmax = fminf(fminf(thx, thy), fminf(thz, tMax));                                            \
         if (tmin <= tmax) mask |= 1u << (i);                                                                    \
@@ -151,8 +162,7 @@ RTB_HD bool wide_confirm(const WideView& W, const Ray& ray, float tMax, uint32_t
     const V3 v0 = v3(tr.v0x, tr.v0y, tr.v0z), e1 = v3(tr.e1x, tr.e1y, tr.e1z), e2 = v3(tr.e2x, tr.e2y, tr.e2z);
     const uint32_t leaf = f2bits(tr.pad0);
 #endif
-    float u, v, t;
-    if (!triangle_ray_below(ray, v0, e1, e2, tMax, u, v, t)) return false;
+    if (!triangle_ray_occludes(ray, v0, e1, e2, tMax)) return false;
     if (leaf == RTB_WIDE_NO_LEAF) return true;
     const DNode n = load_node(W.refNodes, leaf);
     float d;
