@@ -68,6 +68,7 @@ struct Control
     uint32_t shadowCursor[RTB_MAX_DEPTH_SLOTS + 2];   // next unfetched entry of rayList (k_shadow's dynamic fetch)
     uint32_t meshItemCount[RTB_MAX_DEPTH_SLOTS + 2];  // k_shadow_top -> k_shadow_mesh: (ray, mesh) visits queued at this depth
     uint32_t meshCursor[RTB_MAX_DEPTH_SLOTS + 2];     // next unfetched item
+    uint32_t pathCursor[RTB_MAX_DEPTH_SLOTS + 2];     // next unfetched path of depth d (k_traverse_p's dynamic fetch)
     uint32_t tailTaken;                               // != 0: k_tail finished every remaining path (1 + the depth it started at): later kernels have nothing to do
     uint32_t pad[3];
 };
@@ -102,6 +103,8 @@ struct Wavefront
     float4*  mi1;         // dir.xyz, ray slot bits
     float4*  mi2;         // invDir.xyz, mesh index bits
     uint32_t* shFlag;     // per ray slot: 1 = found occluded (set once)
+    uint8_t*  shOcc;      // per ray slot: cleared by k_shade when it emits the ray, set by the any-hit kernel when the ray is occluded: ONE byte
+                          // per occluded ray instead of zeroing the three contribution words in place (three 32-byte sectors dirtied per ray)
     uint32_t miCapacity;
     Control* ctl;
     Totals*  tot;
@@ -237,6 +240,76 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_traverse(const __gr
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&W.tot->numRays, (unsigned long long)count);
 }
 
+// Closest-hit rays on persistent warps (RTB_TRAV_KERNEL=persistent): RTB_TRAV_MINBLOCKS CTAs per SM stay resident, a warp
+// draws paths from the queue with one atomic whenever at least RTB_TP_REFILL of its lanes are idle, and every lane runs
+// the resumable TraverseWalk.  Same visits per ray as k_traverse, fuller warps.
+#ifndef RTB_TP_REFILL
+#define RTB_TP_REFILL 24      // (k_traverse_p per launch on the bench: 4: 1.387, 8: 1.338, 12: 1.285, 20: 1.197, 24: 1.174, 28: 1.175 ms; k_traverse 1.246)
+#endif
+template <bool kCount>
+__global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_traverse_p(const __grid_constant__ SceneView S, const __grid_constant__ Wavefront W, uint32_t depth)
+{
+    const uint32_t count = W.ctl->tailTaken ? 0u : W.ctl->pathCount[depth];
+    const PathBuf& in = W.buf[depth & 1];
+    const uint32_t lane = threadIdx.x & 31u;
+    TraceCounters cnt; cnt.boxTests = 0; cnt.triTests = 0;
+    extern __shared__ uint32_t smemStack[];
+    SharedStack sstack = (SharedStack)__cvta_generic_to_shared(smemStack) + threadIdx.x * 4u;
+    asm volatile("" : "+r"(sstack));
+    uint32_t stack[1];
+    TraverseWalk walk;
+    bool active = false, exhausted = false;
+    uint32_t i = 0;
+    for (;;)
+    {
+        const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
+        if (!exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= RTB_TP_REFILL))
+        {
+            const uint32_t want = __popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&W.ctl->pathCursor[depth], want);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            exhausted = base + want >= count;
+            if (!active)
+            {
+                const uint32_t k = base + __popc(idle & ((1u << lane) - 1u));
+                if (k < count)
+                {
+                    i = k;
+                    const RayInPathQueue src = { in, i };
+                    if (walk.begin(S, stack, src, sstack)) active = true;
+                    else
+                    {
+                        W.hit0[i] = make_uint4(walk.hit.objectId, walk.hit.subObjectId, __float_as_uint(walk.hit.distance), __float_as_uint(walk.hit.u));
+                        W.hit1[i] = walk.hit.v;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(0xFFFFFFFFu, active) == 0u)
+        {
+            if (exhausted) break;
+            continue;
+        }
+        if (active)
+        {
+            const RayInPathQueue src = { in, i };
+            if (!walk.template step<kCount>(S, stack, src, &cnt, sstack))
+            {
+                active = false;
+                W.hit0[i] = make_uint4(walk.hit.objectId, walk.hit.subObjectId, __float_as_uint(walk.hit.distance), __float_as_uint(walk.hit.u));
+                W.hit1[i] = walk.hit.v;
+            }
+        }
+    }
+    if (kCount)
+    {
+        atomicAdd(&W.tot->numBoxTests, (unsigned long long)cnt.boxTests);
+        atomicAdd(&W.tot->numTriTests, (unsigned long long)cnt.triTests);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&W.tot->numRays, (unsigned long long)count);
+}
+
 struct DeviceSink
 {
     V3 result;
@@ -255,6 +328,7 @@ struct DeviceSink
         W.sr1[j] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, c.x);
         W.sr2[j] = make_float4(ray.invDir.x, ray.invDir.y, ray.invDir.z, c.y);
         W.sr3[j] = make_float4(ray.originDivDir.x, ray.originDivDir.y, ray.originDivDir.z, c.z);
+        W.shOcc[j] = 0u;
     }
     __device__ void end_lights(const V4& thr) { lightThr = thr; }
 };
@@ -475,7 +549,7 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
             {
                 active = false;
                 // SampleLight returns RayColor::Zero() for an occluded light (PathTracerMIS.cpp:92-96)
-                if (r == ShadowWalk::kOccluded) { W.sr1[j].w = 0.0f; W.sr2[j].w = 0.0f; W.sr3[j].w = 0.0f; }
+                if (r == ShadowWalk::kOccluded) { W.shOcc[j] = 1u; }
                 else visibleLocal++;
             }
         }
@@ -490,7 +564,7 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow(const __grid
         if (occluded)
         {
             // SampleLight returns RayColor::Zero() for an occluded light (PathTracerMIS.cpp:92-96)
-            W.sr1[j].w = 0.0f; W.sr2[j].w = 0.0f; W.sr3[j].w = 0.0f;
+            W.shOcc[j] = 1u;
         }
         else visibleLocal++;
     }
@@ -648,7 +722,7 @@ __global__ void __launch_bounds__(RTB_SW_THREADS, RTB_SW_MINBLOCKS) k_shadow_wid
             {
                 state = kIdle;
                 // SampleLight returns RayColor::Zero() for an occluded light (PathTracerMIS.cpp:92-96)
-                if (r == ShadowWalk::kOccluded) { W.sr1[j].w = 0.0f; W.sr2[j].w = 0.0f; W.sr3[j].w = 0.0f; }
+                if (r == ShadowWalk::kOccluded) { W.shOcc[j] = 1u; }
                 else visibleLocal++;
             }
         }
@@ -677,7 +751,7 @@ __global__ void __launch_bounds__(RTB_SW_THREADS, RTB_SW_MINBLOCKS) k_shadow_wid
                 if (confirm && wide.template leaf_step<kCount>(wv, walk.ray, walk.maxDistance, ws, sstack, leafTop, &cnt))
                 {
                     state = kIdle;
-                    W.sr1[j].w = 0.0f; W.sr2[j].w = 0.0f; W.sr3[j].w = 0.0f;
+                    W.shOcc[j] = 1u;
                 }
             }
             else if (visit)
@@ -701,7 +775,7 @@ __global__ void __launch_bounds__(RTB_SW_THREADS, RTB_SW_MINBLOCKS) k_shadow_wid
                 if (r == WideWalk::kOccluded)
                 {
                     state = kIdle;
-                    W.sr1[j].w = 0.0f; W.sr2[j].w = 0.0f; W.sr3[j].w = 0.0f;
+                    W.shOcc[j] = 1u;
                 }
                 else if (r == WideWalk::kMissed) { walk.leave_wide(S, src); state = kTop; }
             }
@@ -786,7 +860,7 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_shadow_top(const __
                 break;
             }
         }
-        if (occluded) { W.sr1[j].w = 0.0f; W.sr2[j].w = 0.0f; W.sr3[j].w = 0.0f; W.shFlag[j] = 1u; }      // SampleLight returns RayColor::Zero() (PathTracerMIS.cpp:92-96)
+        if (occluded) { W.shOcc[j] = 1u; W.shFlag[j] = 1u; }      // SampleLight returns RayColor::Zero() (PathTracerMIS.cpp:92-96)
         else { W.shFlag[j] = 0u; visibleLocal++; }
     }
     for (int o = 16; o > 0; o >>= 1) visibleLocal += __shfl_down_sync(0xFFFFFFFFu, visibleLocal, o);
@@ -857,7 +931,7 @@ __global__ void __launch_bounds__(RTB_SM_THREADS, RTB_SM_MINBLOCKS) k_shadow_mes
                 if (atomicExch(&W.shFlag[j], 1u) == 0u)
                 {
                     newlyOccluded++;
-                    W.sr1[j].w = 0.0f; W.sr2[j].w = 0.0f; W.sr3[j].w = 0.0f;
+                    W.shOcc[j] = 1u;
                 }
             }
             else if (r == WideWalk::kMissed) active = false;
@@ -972,7 +1046,8 @@ __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ Wavefro
         const uint32_t n = W.shCount[i];
         const uint32_t base = i * W.raysPerPath;
         V3 sum = v3s(0.0f);
-        for (uint32_t r = 0; r < n; ++r) sum = sum + v3(W.sr1[base + r].w, W.sr2[base + r].w, W.sr3[base + r].w);
+        // SampleLight returns RayColor::Zero() for an occluded light (PathTracerMIS.cpp:92-96) and the zero is still added
+        for (uint32_t r = 0; r < n; ++r) sum = sum + (W.shOcc[base + r] ? v3s(0.0f) : v3(W.sr1[base + r].w, W.sr2[base + r].w, W.sr3[base + r].w));
         const float4 t = W.shThr[i];
         const uint32_t pixel = __float_as_uint(t.w);
         const float4 pc = W.passColor[pixel];
@@ -1304,6 +1379,7 @@ struct RtbContext
         DevArray<float> hit1;
         DevArray<float4> passColor, sr0, sr1, sr2, sr3, shThr;
         DevArray<uint32_t> shCount, shList, rayList, shFlag;
+        DevArray<uint8_t> shOcc;
         DevArray<float4> mi0, mi1, mi2;
         DevArray<Control> ctl;
         DevArray<uint32_t> seed;       // maxBatch x numSeedDims seed integers, then maxBatch x 2 AA offsets
@@ -1326,6 +1402,7 @@ struct RtbContext
     bool useGraphs = true;                // RTB_GRAPH=0: plain launches
     bool exclusiveStream = false;         // the wavefront streams belong to this context alone (RtbCreateDesc::stream given, or RTB_SLOTS > 1)
     bool noWide = false;                  // RTB_NO_WIDE: any-hit rays walk the binary tree (A/B against rtb_wide.h)
+    bool persistentTraverse = true;       // k_traverse_p (persistent warps with ray refill); RTB_TRAV_KERNEL=simple: k_traverse (one ray per thread, grid-stride)
     bool sortShade = true;                // RTB_SORT_SHADE=0: k_shade takes its tile of paths in queue order instead of binned by material
     int shadowKernel = 1;                 // RTB_SHADOW_KERNEL: 0 simple = k_shadow (binary tree), 1 wide = k_shadow_wide (the default), 2 split = k_shadow_top + k_shadow_mesh
     bool wideKernel = true;               // k_shadow_wide (8-wide tree, persistent warps, deferred leaf confirmations) for any-hit rays
@@ -1402,7 +1479,7 @@ static void free_film(RtbContext* c)
         for (int b = 0; b < 2; ++b) { for (int k = 0; k < 4; ++k) t.p[b][k].release(); t.p4[b].release(); }
         t.hit0.release(); t.hit1.release(); t.passColor.release();
         t.sr0.release(); t.sr1.release(); t.sr2.release(); t.sr3.release(); t.shThr.release(); t.shCount.release(); t.shList.release(); t.rayList.release();
-        t.shFlag.release(); t.mi0.release(); t.mi1.release(); t.mi2.release();
+        t.shOcc.release(); t.shFlag.release(); t.mi0.release(); t.mi1.release(); t.mi2.release();
     }
 }
 
@@ -1438,7 +1515,7 @@ static int alloc_shadow(RtbContext* c)
             size_t held = 0;
             for (RtbContext::Slot& t : c->slots) held += (t.sr0.count * 4 * sizeof(float4)) + t.rayList.count * sizeof(uint32_t);
             const size_t budget = (freeB + held) / 2 / c->slots.size();
-            const size_t perPass = (size_t)c->numPixels * rpp * (4 * sizeof(float4) + sizeof(uint32_t));
+            const size_t perPass = (size_t)c->numPixels * rpp * (4 * sizeof(float4) + sizeof(uint32_t) + 1);
             const size_t cap = perPass ? budget / perPass : c->maxBatch;
             if (cap < c->maxBatch) c->maxBatch = cap < 1 ? 1u : (uint32_t)cap;
         }
@@ -1449,7 +1526,7 @@ static int alloc_shadow(RtbContext* c)
     for (RtbContext::Slot& t : c->slots)
     {
         RTB_CUDA(t.sr0.alloc(n)); RTB_CUDA(t.sr1.alloc(n)); RTB_CUDA(t.sr2.alloc(n)); RTB_CUDA(t.sr3.alloc(n));
-        RTB_CUDA(t.rayList.alloc(n));
+        RTB_CUDA(t.rayList.alloc(n)); RTB_CUDA(t.shOcc.alloc(n));
         if (c->shadowKernel == 2) { RTB_CUDA(t.shFlag.alloc(n)); RTB_CUDA(t.mi0.alloc(n)); RTB_CUDA(t.mi1.alloc(n)); RTB_CUDA(t.mi2.alloc(n)); }
     }
     return RTB_OK;
@@ -1468,7 +1545,7 @@ static void fill_wavefront(RtbContext* c)
         w.hit0 = t.hit0.ptr; w.hit1 = t.hit1.ptr; w.passColor = t.passColor.ptr;
         w.sr0 = t.sr0.ptr; w.sr1 = t.sr1.ptr; w.sr2 = t.sr2.ptr; w.sr3 = t.sr3.ptr;
         w.shThr = t.shThr.ptr; w.shCount = t.shCount.ptr; w.shList = t.shList.ptr; w.rayList = t.rayList.ptr;
-        w.mi0 = t.mi0.ptr; w.mi1 = t.mi1.ptr; w.mi2 = t.mi2.ptr; w.shFlag = t.shFlag.ptr; w.miCapacity = (uint32_t)std::min<size_t>(t.mi0.count, 0xFFFFFFFFu);
+        w.mi0 = t.mi0.ptr; w.mi1 = t.mi1.ptr; w.mi2 = t.mi2.ptr; w.shFlag = t.shFlag.ptr; w.shOcc = t.shOcc.ptr; w.miCapacity = (uint32_t)std::min<size_t>(t.mi0.count, 0xFFFFFFFFu);
         w.ctl = t.ctl.ptr;
         w.tot = c->totals.ptr;
         w.pixelList = c->pixelList.ptr;
@@ -1527,6 +1604,8 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
         const int maxStack = (int)((size_t)RTB_MAX_SMEM_STACK_ENTRIES * RTB_STACK_THREADS * sizeof(uint32_t));
         cudaFuncSetAttribute(k_traverse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
         cudaFuncSetAttribute(k_traverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+        cudaFuncSetAttribute(k_traverse_p<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+        cudaFuncSetAttribute(k_traverse_p<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
         cudaFuncSetAttribute(k_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
         cudaFuncSetAttribute(k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
         cudaFuncSetAttribute(k_trace_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
@@ -1573,6 +1652,7 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
     // bytes of SURVEY 8(d)); RTB_COUNT_WIDE makes it count what the 8-wide walk does instead (8 "box tests" per node visited)
     if ((c->flags & RTB_FLAG_COUNT_TESTS) != 0 && !getenv("RTB_COUNT_WIDE")) c->noWide = true;
     if (const char* t = getenv("RTB_SORT_SHADE")) c->sortShade = atoi(t) != 0;
+    if (const char* t = getenv("RTB_TRAV_KERNEL")) c->persistentTraverse = strcmp(t, "simple") != 0;
     if (const char* t = getenv("RTB_SHADOW_KERNEL")) { c->shadowKernel = !strcmp(t, "simple") ? 0 : !strcmp(t, "split") ? 2 : 1; c->wideKernel = c->shadowKernel != 0; }
     if (const char* t = getenv("RTB_HOT_NODES")) c->hotOverride = atoi(t);
     c->slots.resize(numSlots);
@@ -1934,7 +2014,13 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
     if (prof) marks.push_back(next_event(c, ev, s));
     for (uint32_t d = 0; d <= depthLimit; ++d)
     {
-        if (count) k_traverse<true><<<blocks128, 128, c->stackBytes, s>>>(c->view, W, d);
+        if (c->persistentTraverse)
+        {
+            const int persistentBlocks = std::min(blocks128, c->numSMs * RTB_TRAV_MINBLOCKS);
+            if (count) k_traverse_p<true><<<persistentBlocks, 128, c->stackBytes, s>>>(c->view, W, d);
+            else k_traverse_p<false><<<persistentBlocks, 128, c->stackBytes, s>>>(c->view, W, d);
+        }
+        else if (count) k_traverse<true><<<blocks128, 128, c->stackBytes, s>>>(c->view, W, d);
         else k_traverse<false><<<blocks128, 128, c->stackBytes, s>>>(c->view, W, d);
         if (prof) marks.push_back(next_event(c, ev, s));
         // (a tile of RTB_SHADE_TILE paths per CTA and loop iteration)
@@ -2016,7 +2102,7 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
             memset(&k, 0, sizeof(k));
             memcpy(&k.P, &P, sizeof(P)); memcpy(&k.W, &W, sizeof(W)); memcpy(&k.S, &c->view, sizeof(SceneView));
             k.P.passIndex = 0; k.P.sampleOffsetX = 0.0f; k.P.sampleOffsetY = 0.0f; k.W.firstPassIndex = 0;
-            k.numPaths = numPaths; k.depthLimit = depthLimit; k.tailBlocks = (uint32_t)tailBlocks; k.flags = (shadows ? 1u : 0u) | (textured ? 2u : 0u) | (c->sortShade ? 4u : 0u);
+            k.numPaths = numPaths; k.depthLimit = depthLimit; k.tailBlocks = (uint32_t)tailBlocks; k.flags = (shadows ? 1u : 0u) | (textured ? 2u : 0u) | (c->sortShade ? 4u : 0u) | (c->persistentTraverse ? 8u : 0u);
             k.stackBytes = c->stackBytes; k.hot = c->hotNodes; k.hotOverride = c->hotOverride; k.wide = c->shadowKernel;
             memcpy(key.data(), &k, sizeof(k));
         }

@@ -577,6 +577,137 @@ RTB_HD void scene_traverse_from(const SceneView& S, const WorldRay& worldRaySour
     }
 }
 
+// scene_traverse_from as a resumable walk (begin() + step() until it returns false) for the persistent closest-hit kernel
+// (k_traverse_p), whose warps give a finished lane a new ray instead of letting it idle until the slowest ray of the
+// warp is done.  One step() = what one iteration of scene_traverse_from's outer loop does, in the same order: node
+// phase, leaf (triangle tests / top-level leaf), pop.  A lane's own sequence of box and triangle tests is exactly the
+// one above - hit records are bit-identical - only the interleaving between lanes differs.
+struct TraverseWalk
+{
+    uint32_t stackSize, blasBase, popFloor, objectID, curChild, curInfo;
+    bool inBlas, finite, worldFinite, have;
+    const DNode* nodes;
+    const DTri* tris;
+    Ray ray;
+    Hit hit;
+
+    // false: nothing to traverse
+    template <typename WorldRay>
+    RTB_HD bool begin(const SceneView& S, uint32_t* stack, const WorldRay& worldRaySource, SharedStack sstack = 0)
+    {
+        hit.objectId = RTB_INVALID_OBJECT; hit.subObjectId = 0; hit.distance = INFINITY; hit.u = 0.0f; hit.v = 0.0f;
+        if (S.numObjects == 0) return false;
+        stackSize = 0; blasBase = 0; popFloor = 0xFFFFFFFFu; inBlas = false; nodes = S.tlas; tris = nullptr;
+        ray = worldRaySource.load();
+        worldFinite = ray_is_finite(ray); finite = worldFinite;
+        objectID = 0; have = false; curChild = 0; curInfo = 0;
+        if (S.numObjects == 1) { stk_put(stack, sstack, 0, 0u, RTB_ENTRY_OBJECT); stackSize = 1; }
+        else if (S.numTlasNodes != 0) { node_header(S.tlas, 0, curChild, curInfo); have = true; }
+        else return false;
+        return true;
+    }
+
+    // false: the walk is finished (hit holds the result)
+    template <bool kCount, typename WorldRay>
+    RTB_HD bool step(const SceneView& S, uint32_t* stack, const WorldRay& worldRaySource, TraceCounters* cnt, SharedStack sstack = 0)
+    {
+        while (have && RTB_NUM_LEAVES(curInfo) == 0)
+        {
+            DNode a, b;
+            load_node_pair(nodes, curChild, a, b);
+            float distanceA, distanceB;
+            bool hitA, hitB;
+            if (finite)
+            {
+                hitA = box_ray_finite(ray, a.minx, a.miny, a.minz, a.maxx, a.maxy, a.maxz, distanceA);
+                hitB = box_ray_finite(ray, b.minx, b.miny, b.minz, b.maxx, b.maxy, b.maxz, distanceB);
+            }
+            else
+            {
+                hitA = box_ray(ray, a.minx, a.miny, a.minz, a.maxx, a.maxy, a.maxz, distanceA);
+                hitB = box_ray(ray, b.minx, b.miny, b.minz, b.maxx, b.maxy, b.maxz, distanceB);
+            }
+            hitA &= (distanceA < hit.distance);
+            hitB &= (distanceB < hit.distance);
+            if (kCount) cnt->boxTests += 2;
+            if (hitA && hitB)
+            {
+                const bool bFirst = distanceB < distanceA;
+                stk_put(stack, sstack, stackSize++, bFirst ? a.childIndex : b.childIndex, bFirst ? a.leafInfo : b.leafInfo);
+                curChild = bFirst ? b.childIndex : a.childIndex;
+                curInfo = bFirst ? b.leafInfo : a.leafInfo;
+            }
+            else if (hitA) { curChild = a.childIndex; curInfo = a.leafInfo; }
+            else if (hitB) { curChild = b.childIndex; curInfo = b.leafInfo; }
+            else if (stackSize > popFloor)
+            {
+                const StackEntry e = stk_get(stack, sstack, --stackSize);
+                curChild = e.a; curInfo = e.b;
+            }
+            else have = false;
+#if defined(__CUDA_ARCH__) && RTB_TRAV_VOTE > 0
+            if (__popc(__activemask()) < RTB_TRAV_VOTE) break;
+#endif
+        }
+        if (have && RTB_NUM_LEAVES(curInfo) == 0) return true;         // left the node loop by vote
+        if (have)
+        {
+            const uint32_t numLeaves = RTB_NUM_LEAVES(curInfo);
+            if (inBlas)
+            {
+                if (kCount) cnt->triTests += numLeaves;
+                for (uint32_t i = 0; i < numLeaves; ++i)
+                {
+                    const uint32_t triangleIndex = curChild + i;
+                    V3 v0, e1, e2;
+                    load_tri(tris, triangleIndex, v0, e1, e2);
+                    float u, v, distance;
+                    if (triangle_ray_below(ray, v0, e1, e2, hit.distance, u, v, distance))
+                    {
+                        hit.distance = distance; hit.subObjectId = triangleIndex; hit.objectId = objectID; hit.u = u; hit.v = v;
+                    }
+                }
+            }
+            else
+            {
+                for (uint32_t i = numLeaves; i-- > 0;) { stk_put(stack, sstack, stackSize, curChild + i, RTB_ENTRY_OBJECT); stackSize++; }
+            }
+            have = false;
+        }
+        if (inBlas && stackSize == blasBase)
+        {
+            inBlas = false; popFloor = 0xFFFFFFFFu; nodes = S.tlas; ray = worldRaySource.load(); finite = worldFinite;
+        }
+        if (stackSize == 0) return false;
+        const StackEntry e = stk_get(stack, sstack, --stackSize);
+        if (e.b == RTB_ENTRY_OBJECT)
+        {
+            objectID = e.a;
+            const DObjectTrace& obj = S.objTrace[objectID];
+            const Ray localRay = transform_ray_unsafe(obj.invTransform, worldRaySource.load());
+            if (obj.kind == RTB_OBJECT_SHAPE && obj.shapeType == RTB_SHAPE_MESH)
+            {
+                const DMesh& mesh = S.meshes[obj.meshIndex];
+                if (mesh.numNodes != 0)
+                {
+                    inBlas = true; blasBase = stackSize; popFloor = stackSize; nodes = mesh.nodes; tris = mesh.tris; ray = localRay; finite = ray_is_finite(localRay);
+                    node_header(nodes, 0, curChild, curInfo);
+                    have = true;
+                }
+            }
+            else
+            {
+                analytic_closest(obj, localRay, objectID, hit);
+            }
+        }
+        else
+        {
+            curChild = e.a; curInfo = e.b; have = true;
+        }
+        return true;
+    }
+};
+
 // stack of the wide any-hit walk (rtb_wide.h) on top of the entries the two-level walk already holds: a group is two
 // consecutive 4-byte entries
 struct WideStackAbove

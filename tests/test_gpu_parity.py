@@ -739,20 +739,22 @@ def test_active_tiles(ctx):
 
 @pytest.mark.parametrize("env", [{"RTB_SHADOW_KERNEL": "simple"}, {"RTB_SHADOW_KERNEL": "wide", "RTB_HOT_NODES": "0"}, {"RTB_SHADOW_KERNEL": "wide", "RTB_HOT_NODES": "64"},
                                  {"RTB_SHADOW_KERNEL": "wide", "RTB_HOT_NODES": "-1"}, {"RTB_SHADOW_KERNEL": "wide", "RTB_NO_WIDE": "1"},
-                                 {"RTB_SHADOW_KERNEL": "split"}])
+                                 {"RTB_SHADOW_KERNEL": "split"}, {"RTB_TRAV_KERNEL": "simple"}, {"RTB_SORT_SHADE": "0"}])
 def test_any_hit_walks_agree(env, monkeypatch):
-    """The any-hit walks - the reference's binary tree in k_shadow (the default) and the 8-wide quantised tree (rtb_wide.h)
-    in the persistent k_shadow_wide with 0 / 64 / all-that-fit nodes of the tree top staged in shared memory by a bulk
-    copy - give the reference's film and shadow-ray counters on the mesh scenes, bit for bit.  (rtb_trace_batch and the
-    CPU build of the headers exercise the wide walk inline as well.)"""
+    """The any-hit walks - the reference's binary tree in k_shadow and the 8-wide quantised tree (rtb_wide.h) in the
+    persistent k_shadow_wide (the default) with 0 / 64 / all-that-fit nodes of the tree top staged in shared memory by a
+    bulk copy, the split pair of kernels - as well as the one-ray-per-thread closest-hit kernel (k_traverse instead of the persistent k_traverse_p) and k_shade without
+    its material binning give the reference's film and ray counters, bit for bit.  (rtb_trace_batch and the CPU build of
+    the headers exercise the wide walk inline as well.)"""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
-    for scene in ("mesh_small", "textures"):
+    for scene in ("mesh_small", "textures", "materials"):
         with capi.Context(device=0) as c:
             meta, img, counters = render_golden_case(c, scene, "mis")
         want = util.load_sum(util.golden("%s_mis.sum" % scene), meta["width"], meta["height"])
         util.assert_bit_identical(img, want, "%s/mis with %s" % (scene, env))
         assert counters["numShadowRays"] == meta["numShadowRays"] and counters["numShadowRaysHit"] == meta["numShadowRaysHit"]
+        assert counters["numRays"] == meta["numRays"]
 
 
 @pytest.mark.parametrize("graph", ["1", "0"])
