@@ -25,6 +25,7 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "rtb_integrator.h"
 #include "rtb_postprocess.h"
@@ -1111,6 +1112,33 @@ __global__ void __launch_bounds__(256) k_scatter_shard(const float* __restrict__
     }
 }
 
+// The same for a destination in MAPPED HOST memory, where the shape of the writes decides the PCIe efficiency: 16-byte
+// stores, consecutive lanes on consecutive addresses.  The shard's pixels are taken in raster order (rasterOrder[k] = slot
+// of its k-th pixel, rasterPix[k] = that pixel's raster index); a run of the shard's pixels in one raster row is a tile
+// row segment, a multiple of four pixels long when width and tile size are multiples of four, so the shard's floats in
+// raster order split into float4 chunks none of which straddles two runs: chunk q starts in pixel k0 = 4q / 3 and lands
+// at float rasterPix[k0] * 3 + (4q - 3 k0) of the frame.  A warp writes 512 contiguous bytes (less at the end of a run)
+// where k_scatter_shard writes 96 four-byte words in three strided sweeps: the 8-GPU end-to-end figure of the bench
+// was bound by exactly that (3.1 MB per rank and step at ~6 GB/s).
+__global__ void __launch_bounds__(256) k_scatter_shard_rows(const float* __restrict__ src, float4* dstRaster, const uint32_t* __restrict__ rasterOrder,
+                                                            const uint32_t* __restrict__ rasterPix, uint32_t numChunks)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < numChunks; q += stride)
+    {
+        const uint32_t f0 = 4u * q, k0 = f0 / 3u, c0 = f0 - 3u * k0;
+        float v[4];
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; ++j)
+        {
+            const uint32_t f = c0 + j, k = k0 + f / 3u, ch = f % 3u;
+            v[j] = src[(size_t)rasterOrder[k] * 3u + ch];
+        }
+        const size_t dstFloat = (size_t)rasterPix[k0] * 3u + c0;       // a multiple of 4 (see above)
+        dstRaster[dstFloat >> 2] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 // front buffer (Viewport::PostProcessTile): pixel slots -> tone-mapped 0x00RRGGBB in raster order; `blurred` (the
 // RTB_BLOOM_LEVELS blurred raster images back to back) is only read when P.bloomFactor > 0; `frozenRaster` (optional):
 // per raster pixel, the pass count at which adaptive rendering dropped it (0 = still sampled)
@@ -1346,6 +1374,7 @@ struct RtbContext
     uint32_t maxBatchFilm = 1;     // ... as the film size alone would have it (alloc_shadow lowers maxBatch for scenes with many lights)
     DevArray<uint32_t> pixelList;     // this shard
     DevArray<uint32_t> pixelListAll;  // all shards back to back, padded with 0xFFFFFFFF
+    DevArray<uint32_t> rasterOrder, rasterPix;   // this shard's slots / raster indices in raster order (k_scatter_shard_rows); empty unless width and tile size are multiples of 4
     std::vector<uint32_t> hostPixelList;   // this shard's list, kept for rtb_set_active_tiles
     DevArray<uint32_t> activeList;    // adaptive rendering: the pixel slots that still get samples ...
     uint32_t numActive = 0;
@@ -1471,7 +1500,7 @@ static void free_vcm(RtbContext* c)
 static void free_film(RtbContext* c)
 {
     free_vcm(c);
-    c->pixelList.release(); c->pixelListAll.release(); c->sum.release(); c->sum2.release(); c->raster.release(); c->activeList.release(); c->hasActiveList = false; c->frozen.release(); c->hostFrozen.clear(); c->raster2.release(); c->pixelError.release(); c->rowError.release(); c->blockRows.release(); c->front.release(); c->blurred.release(); c->blurScratch.release();
+    c->pixelList.release(); c->pixelListAll.release(); c->rasterOrder.release(); c->rasterPix.release(); c->sum.release(); c->sum2.release(); c->raster.release(); c->activeList.release(); c->hasActiveList = false; c->frozen.release(); c->hostFrozen.clear(); c->raster2.release(); c->pixelError.release(); c->rowError.release(); c->blockRows.release(); c->front.release(); c->blurred.release(); c->blurScratch.release();
     for (int i = 0; i < RTB_SNAP_RING; ++i) c->rasterAsync[i].release();
     c->snapshots.release(); c->snapshotCapacity = 0;
     for (RtbContext::Slot& t : c->slots)
@@ -1837,6 +1866,17 @@ int rtb_resize(RtbContext* c, uint32_t width, uint32_t height)
     c->hostPixelList = lists[c->shardIndex];
     RTB_CUDA(c->pixelList.upload(lists[c->shardIndex], c->stream));
     RTB_CUDA(c->pixelListAll.upload(all, c->stream));
+    c->rasterOrder.release(); c->rasterPix.release();
+    if (width % 4u == 0 && ts % 4u == 0 && c->numPixels != 0)
+    {
+        const std::vector<uint32_t>& mine = lists[c->shardIndex];
+        std::vector<uint32_t> order(mine.size()), pix(mine.size());
+        for (uint32_t i = 0; i < (uint32_t)order.size(); ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return mine[a] < mine[b]; });
+        for (size_t k = 0; k < order.size(); ++k) pix[k] = mine[order[k]];
+        RTB_CUDA(c->rasterOrder.upload(order, c->stream));
+        RTB_CUDA(c->rasterPix.upload(pix, c->stream));
+    }
     RTB_CUDA(cudaStreamSynchronize(c->stream));
 
     // passes per wavefront: enough paths in flight to keep 148 SMs busy through the deep (sparse) bounces, bounded by memory
@@ -2057,7 +2097,7 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
             {
                 // persistent CTAs; shared memory: barrier + staged tree top + one stack panel per 128 threads
                 const size_t perCta = (233472u - 1024u * RTB_SW_MINBLOCKS) / RTB_SW_MINBLOCKS;
-                const size_t stacks = (size_t)(RTB_SW_THREADS / 128) * c->widePanelBytes;
+                const size_t stacks = (size_t)((RTB_SW_THREADS + 127) / 128) * c->widePanelBytes;
                 size_t hot = perCta > stacks + 256u ? (perCta - stacks - 256u) / sizeof(WNode) : 0u;
                 if (hot > c->hotTotal) hot = c->hotTotal;
                 if (c->hotOverride >= 0 && (size_t)c->hotOverride < hot) hot = (size_t)c->hotOverride;      // (-1: all that fit)
@@ -3020,7 +3060,10 @@ int rtb_scatter_shard(RtbContext* c, const void* shardFilmDevice, int which, voi
     RTB_CUDA(join_slots(c));
     if (!shardFilmDevice && c->numShards == 1) { int rc = vcm_fold(c); if (rc != RTB_OK) return rc; }
     const float* src = shardFilmDevice ? (const float*)shardFilmDevice : (which == 0 ? c->sum.ptr : c->sum2.ptr);
-    k_scatter_shard<<<c->numSMs * 4, 256, 0, c->stream>>>(src, (float*)rasterDst, c->pixelList.ptr, c->numPixels);
+    if (c->rasterOrder.ptr && ((uintptr_t)rasterDst & 15u) == 0)
+        k_scatter_shard_rows<<<c->numSMs * 4, 256, 0, c->stream>>>(src, (float4*)rasterDst, c->rasterOrder.ptr, c->rasterPix.ptr, (uint32_t)((size_t)c->numPixels * 3u / 4u));
+    else
+        k_scatter_shard<<<c->numSMs * 4, 256, 0, c->stream>>>(src, (float*)rasterDst, c->pixelList.ptr, c->numPixels);
     RTB_CUDA(cudaGetLastError());
     c->counters.numKernelLaunches++;
     return RTB_OK;

@@ -165,8 +165,12 @@ RTB_HD bool wide_confirm(const WideView& W, const Ray& ray, float tMax, uint32_t
     if (!triangle_ray_occludes(ray, v0, e1, e2, tMax)) return false;
     if (leaf == RTB_WIDE_NO_LEAF) return true;
     const DNode n = load_node(W.refNodes, leaf);
+    // (a mesh-local ray comes from make_ray_unsafe: originDivDir IS origin * invDir - forming the product here instead of
+    //  reading the member lets the kernel drop three registers from the state it carries through the walk)
+    Ray r = ray;
+    r.originDivDir = ray.origin * ray.invDir;
     float d;
-    return box_ray_finite(ray, n.minx, n.miny, n.minz, n.maxx, n.maxy, n.maxz, d) && d < tMax;
+    return box_ray_finite(r, n.minx, n.miny, n.minz, n.maxx, n.maxy, n.maxz, d) && d < tMax;
 }
 
 // Any-hit walk of one mesh for a ray that passed wide_ray_ok().  Stack: groups of pending children, two words each

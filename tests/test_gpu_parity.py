@@ -5,6 +5,7 @@ this box (oracle/_ref), against the reference itself run live on the same inputs
 Bar: BIT-EXACT float32 sum buffers, hit records, sampler integers and ray counters (oracle = exact-math build of the
 reference: IEEE div/sqrt, no FMA contraction; see DESIGN.md "Oracle").
 """
+import ctypes as C
 import json
 import os
 
@@ -822,3 +823,35 @@ def test_single_light_sampling_statistics_against_the_live_reference(tmp_path, s
     assert counters["single"]["numPrimaryRays"] == meta["numPrimaryRays"] == w * h * passes
     assert abs(counters["single"]["numShadowRays"] - meta["numShadowRays"]) <= 0.02 * meta["numShadowRays"]
     assert counters["single"]["numShadowRays"] < counters["all"]["numShadowRays"]
+
+
+@pytest.mark.parametrize("w,h,tile", [(64, 64, 8), (96, 40, 32), (62, 50, 8)])
+def test_shards_scattered_into_one_mapped_host_frame(w, h, tile):
+    """rtb_scatter_shard - what every rank of an N-GPU end-to-end run does with its own pixels: four shard contexts write
+    into ONE page-locked, device-mapped raster frame; the frame equals the unsharded film bit for bit.  Widths that are a
+    multiple of four take k_scatter_shard_rows (16-byte stores along the raster rows), 62 the pixel-by-pixel fallback."""
+    lib = capi.load_library()
+    sf = capi.SceneFile(util.golden("cornell.rtb"))
+    ps = capi.PassScript(util.golden("cornell.passes"))
+    cam = capi.camera_for(sf, w, h)
+    passes = 3
+    with capi.Context(device=0) as c:
+        c.upload_scene(sf); c.resize(w, h)
+        c.render_passes(cam, ps.seeds[:passes], ps.offsets[:passes], 0)
+        full, full2 = c.read_sum(), c.read_sum(1)
+    frame, frame2 = capi.PinnedImage(w, h), capi.PinnedImage(w, h)
+    frame.array[:] = -1.0; frame2.array[:] = -1.0
+    n = 4
+    for s in range(n):
+        with capi.Context(device=0, num_shards=n, shard_index=s, tile_size=tile) as c:
+            c.upload_scene(sf); c.resize(w, h)
+            c.render_passes(cam, ps.seeds[:passes], ps.offsets[:passes], 0)
+            for which, f in ((0, frame), (1, frame2)):
+                dev = lib.rtb_host_device_pointer(C.c_void_p(f.ptr))
+                assert dev, lib.rtb_last_error()
+                rc = lib.rtb_scatter_shard(c.h, None, which, C.c_void_p(dev))
+                assert rc == 0, lib.rtb_last_error()
+            c.synchronize()
+    util.assert_bit_identical(frame.array, full, "scattered host frame")
+    util.assert_bit_identical(frame2.array, full2, "scattered host frame, secondary sum")
+    frame.close(); frame2.close()

@@ -23,6 +23,9 @@ for rep in range(5):
     from raytracer_b200 import capi
     capi.load_library().rtb_join(vp.context()); e1.record(); vp.synchronize(); torch.cuda.synchronize()
     best = min(best, e0.elapsed_time(e1))
+if os.environ.get("SHARD_PROBE_PROFILE"):      # per-depth breakdown of one wavefront (set RTB_PROFILE_DEPTHS=1 as well)
+    lib = capi.load_library()
+    vp.reset(); lib.rtb_set_profiling(vp.context(), 1); vp.render(steps); vp.synchronize(); lib.rtb_set_profiling(vp.context(), 0)
 c = vp.counters()
 print("shard 0 of %d, %d steps: best %.3f ms (%.3f ms per step), graph=%s" % (n, steps, best, best / steps, os.environ.get("RTB_GRAPH", "1")))
 vp.close(); scene.close()
