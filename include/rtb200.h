@@ -355,8 +355,10 @@ int  rtb_render_pass(RtbContext* ctx, const RtbPassDesc* pass);
  * to `count` calls of rtb_render_pass */
 int  rtb_render_passes(RtbContext* ctx, const RtbPassDesc* passes, uint32_t count);
 int  rtb_synchronize(RtbContext* ctx);
-/* Passes are enqueued on the context's own wavefront streams (several wavefronts in flight; the film still receives
- * them in pass order).  Everything in this API that looks at the result (rtb_read_*, rtb_unshard_*, rtb_get_counters,
+/* Passes are enqueued on the context's wavefront stream(s).  What ships is ONE wavefront slot: a context runs one kernel
+ * at a time, on the stream of RtbCreateDesc (or one shared stream per device if none was given); with RTB_SLOTS = 2..4 in
+ * the environment several wavefronts are in flight on streams of their own (the film still receives them in pass order;
+ * such contexts run without the tail kernel; measured gain: 2 %).  Everything in this API that looks at the result (rtb_read_*, rtb_unshard_*, rtb_get_counters,
  * rtb_film_device_buffer, rtb_reset, rtb_synchronize) orders itself after them.  rtb_join does only that: it makes the
  * main stream (RtbCreateDesc::stream) wait, on the device, for every pass enqueued so far - for callers that go on to
  * enqueue their own work on that stream.  It does not block the host. */
