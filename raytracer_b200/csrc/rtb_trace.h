@@ -285,8 +285,6 @@ RTB_HD void load_node_pair(const DNode* nodes, uint32_t index, DNode& a, DNode& 
 #endif
 }
 
-#define RTB_NUM_LEAVES(info) ((info) & 0x3FFFFFFFu)
-#define RTB_ENTRY_OBJECT 0xFFFFFFFFu    // stack entry {k, RTB_ENTRY_OBJECT}: "traverse object k" (otherwise {childIndex, leafInfo} of a node)
 
 // IShape::Traverse (Shape.cpp:19-45) / LightSceneObject::Traverse (SceneObject_Light.cpp:27-38) for analytic shapes
 RTB_HD void analytic_closest(const DObjectTrace& obj, const Ray& ray, uint32_t objectID, Hit& hit)
@@ -326,14 +324,15 @@ RTB_HD bool analytic_shadow(const DObjectTrace& obj, const Ray& ray, float maxDi
     return isect.nearDist < maxDistance;
 }
 
-// One stack entry = what a node visit needs: {childIndex, leafInfo}.  A node's box is only needed when its parent
-// is visited (both children sit in one aligned 64-byte block), so neither a popped node nor the nearer child we
-// descend into is ever fetched again: memory traffic is exactly one 64-byte block per visited inner node.
-struct StackEntry { uint32_t a, b; };
-
-// Stack storage.  An entry is packed into 32 bits: index (26 bits) | count (6 bits), count 0 = inner node (index of its
-// first child), 1..62 = leaf with that many items starting at index, 63 = "traverse object `index`".  rtb_upload_scene
-// refuses trees that do not fit (>= 2^26 nodes / items, leaves with more than 62 items).
+// One 32-bit word says what a node visit needs: index (26 bits) | count (6 bits).  count 0 = inner node (index of its
+// first child), 1..62 = leaf with that many items starting at index, 63 = "traverse object `index`" (stack only).
+// rtb_upload_scene refuses trees that do not fit (>= 2^26 nodes / items, leaves with more than 62 items) and stores that
+// word in the `leafInfo` slot of every node of the DEVICE copy (build_host_scene, rtb_upload.h: the reference's
+// numLeaves : 30 | splitAxis : 2 word is not needed by any walk), so the walks carry ONE register per pending node, a
+// push is a plain store of the far child's word and a pop a plain load - no pack / unpack arithmetic on the way (push and
+// pop were 13 % of k_traverse_p's warp instructions at 3 active lanes).  A node's box is only needed when its parent is
+// visited (both children sit in one aligned 64-byte block), so neither a popped node nor the nearer child we descend
+// into is ever fetched again: memory traffic is exactly one 64-byte block per visited inner node.
 //
 // On the device the whole stack lives in SHARED memory (RTB_SMEM_STACK = 1, the default): entry i of thread t at
 // sstack[i * RTB_STACK_THREADS + t], so whatever depth each lane of a warp is at, the 32 lanes touch 32 different
@@ -357,16 +356,17 @@ struct StackEntry { uint32_t a, b; };
 #define RTB_PACK_MAX_INDEX ((1u << RTB_PACK_INDEX_BITS) - 1u)
 #define RTB_PACK_OBJECT 63u
 #define RTB_PACK_MAX_LEAF 62u
+#define RTB_NODE_COUNT(p) ((p) >> RTB_PACK_INDEX_BITS)
+#define RTB_NODE_INDEX(p) ((p) & RTB_PACK_MAX_INDEX)
+#define RTB_OBJECT_ENTRY(i) ((i) | (RTB_PACK_OBJECT << RTB_PACK_INDEX_BITS))
+RTB_HD uint32_t pack_node_word(uint32_t childIndex, uint32_t referenceLeafInfo) { return childIndex | ((referenceLeafInfo & 0x3FFFFFFFu) << RTB_PACK_INDEX_BITS); }
 
-// b = leafInfo of a node (numLeaves | splitAxis << 30), or RTB_ENTRY_OBJECT
 // the kernels hand the stack over as a 32-bit shared-space byte address (word 0 of this thread's column) behind an
 // optimisation barrier: with a generic pointer the compiler re-derived the address (thread id, CTA shared window:
 // 5 instructions incl. S2R / S2UR) in every iteration of the node loop instead of keeping it in a register
 typedef uint32_t SharedStack;
-RTB_HD void stk_put(uint32_t* stack, SharedStack sstack, uint32_t i, uint32_t a, uint32_t b)
+RTB_HD void stk_put(uint32_t* stack, SharedStack sstack, uint32_t i, uint32_t packed)
 {
-    const uint32_t count = b == 0xFFFFFFFFu ? RTB_PACK_OBJECT : (b & 0x3FFFFFFFu);
-    const uint32_t packed = a | (count << RTB_PACK_INDEX_BITS);
 #if RTB_SSTACK
     (void)stack;
     asm volatile("st.shared.u32 [%0], %1;" :: "r"(sstack + i * (RTB_STACK_THREADS * 4u)), "r"(packed));
@@ -376,28 +376,21 @@ RTB_HD void stk_put(uint32_t* stack, SharedStack sstack, uint32_t i, uint32_t a,
 #endif
 }
 
-RTB_HD StackEntry stk_get(const uint32_t* stack, SharedStack sstack, uint32_t i)
+RTB_HD uint32_t stk_get(const uint32_t* stack, SharedStack sstack, uint32_t i)
 {
 #if RTB_SSTACK
     (void)stack;
     uint32_t packed;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(packed) : "r"(sstack + i * (RTB_STACK_THREADS * 4u)));
+    return packed;
 #else
     (void)sstack;
-    const uint32_t packed = stack[i];
+    return stack[i];
 #endif
-    StackEntry e;
-    e.a = packed & RTB_PACK_MAX_INDEX;
-    const uint32_t count = packed >> RTB_PACK_INDEX_BITS;
-    e.b = count == RTB_PACK_OBJECT ? 0xFFFFFFFFu : count;
-    return e;
 }
 
-RTB_HD void node_header(const DNode* nodes, uint32_t index, uint32_t& childIndex, uint32_t& leafInfo)
-{
-    childIndex = nodes[index].childIndex;
-    leafInfo = nodes[index].leafInfo;
-}
+// the packed word of node `index` itself (the root, when a walk starts)
+RTB_HD uint32_t node_header(const DNode* nodes, uint32_t index) { return nodes[index].leafInfo; }
 
 // Scene::Traverse (Scene.cpp:219-243) = GenericTraverse<Scene> -> Scene::Traverse_Leaf -> Traverse_Object ->
 // GenericTraverse<MeshShape> -> MeshShape::Traverse_Leaf, flattened into ONE loop over ONE stack so that all lanes of
@@ -445,11 +438,11 @@ RTB_HD void scene_traverse_from(const SceneView& S, const WorldRay& worldRaySour
     const bool worldFinite = ray_is_finite(ray);
     bool finite = worldFinite;
     uint32_t objectID = 0;
-    bool have = false;                 // {curChild, curInfo} describe a node still to be visited
-    uint32_t curChild = 0, curInfo = 0;
+    bool have = false;                 // `cur` (packed word) describes a node still to be visited
+    uint32_t cur = 0;
 
-    if (S.numObjects == 1) { stk_put(stack, sstack, 0, 0u, RTB_ENTRY_OBJECT); stackSize = 1; }      // BVH bypass, Scene.cpp:231-235
-    else if (S.numTlasNodes != 0) { node_header(S.tlas, 0, curChild, curInfo); have = true; }
+    if (S.numObjects == 1) { stk_put(stack, sstack, 0, RTB_OBJECT_ENTRY(0u)); stackSize = 1; }      // BVH bypass, Scene.cpp:231-235
+    else if (S.numTlasNodes != 0) { cur = node_header(S.tlas, 0); have = true; }
 
     for (;;)
     {
@@ -457,10 +450,10 @@ RTB_HD void scene_traverse_from(const SceneView& S, const WorldRay& worldRaySour
         auto innerNodes = [&](auto modeTag)
         {
             constexpr int kMode = decltype(modeTag)::value;
-            while (have && RTB_NUM_LEAVES(curInfo) == 0)
+            while (have && RTB_NODE_COUNT(cur) == 0)
             {
                 DNode a, b;
-                load_node_pair(nodes, curChild, a, b);
+                load_node_pair(nodes, cur, a, b);       // (an inner node's word is the index of its first child)
                 float distanceA, distanceB;
                 bool hitA, hitB;
                 if (kMode == 1 || (kMode == 0 && finite))
@@ -480,18 +473,16 @@ RTB_HD void scene_traverse_from(const SceneView& S, const WorldRay& worldRaySour
                 {
                     // visit the nearer child first, push the other (Traversal_Single.h:65-75)
                     const bool bFirst = distanceB < distanceA;
-                    stk_put(stack, sstack, stackSize++, bFirst ? a.childIndex : b.childIndex, bFirst ? a.leafInfo : b.leafInfo);
-                    curChild = bFirst ? b.childIndex : a.childIndex;
-                    curInfo = bFirst ? b.leafInfo : a.leafInfo;
+                    stk_put(stack, sstack, stackSize++, bFirst ? a.leafInfo : b.leafInfo);
+                    cur = bFirst ? b.leafInfo : a.leafInfo;
                 }
-                else if (hitA) { curChild = a.childIndex; curInfo = a.leafInfo; }
-                else if (hitB) { curChild = b.childIndex; curInfo = b.leafInfo; }
+                else if (hitA) cur = a.leafInfo;
+                else if (hitB) cur = b.leafInfo;
                 else if (stackSize > popFloor)
                 {
                     // both children missed: take the next pending node of this mesh right here, so that the lane stays in
                     // the inner loop with the rest of its warp instead of idling until every lane has left it
-                    const StackEntry e = stk_get(stack, sstack, --stackSize);
-                    curChild = e.a; curInfo = e.b;
+                    cur = stk_get(stack, sstack, --stackSize);
                 }
                 else have = false;
 #if defined(__CUDA_ARCH__) && RTB_TRAV_VOTE > 0
@@ -508,18 +499,18 @@ RTB_HD void scene_traverse_from(const SceneView& S, const WorldRay& worldRaySour
 #endif
 
 #if RTB_TRAV_VOTE > 0
-        if (have && RTB_NUM_LEAVES(curInfo) == 0) continue;       // left the node loop by vote: carry on with the same node
+        if (have && RTB_NODE_COUNT(cur) == 0) continue;       // left the node loop by vote: carry on with the same node
 #endif
         if (have)
         {
-            const uint32_t numLeaves = RTB_NUM_LEAVES(curInfo);
+            const uint32_t numLeaves = RTB_NODE_COUNT(cur), firstItem = RTB_NODE_INDEX(cur);
             if (inBlas)
             {
                 // MeshShape::Traverse_Leaf, MeshShape.cpp:134-168
                 if (kCount) cnt->triTests += numLeaves;
                 for (uint32_t i = 0; i < numLeaves; ++i)
                 {
-                    const uint32_t triangleIndex = curChild + i;
+                    const uint32_t triangleIndex = firstItem + i;
                     V3 v0, e1, e2;
                     load_tri(tris, triangleIndex, v0, e1, e2);
                     float u, v, distance;
@@ -536,7 +527,7 @@ RTB_HD void scene_traverse_from(const SceneView& S, const WorldRay& worldRaySour
             else
             {
                 // Scene::Traverse_Leaf, Scene.cpp:167-178: objects in order -> push in reverse
-                for (uint32_t i = numLeaves; i-- > 0;) { stk_put(stack, sstack, stackSize, curChild + i, RTB_ENTRY_OBJECT); stackSize++; }
+                for (uint32_t i = numLeaves; i-- > 0;) { stk_put(stack, sstack, stackSize, RTB_OBJECT_ENTRY(firstItem + i)); stackSize++; }
             }
             have = false;
         }
@@ -548,11 +539,11 @@ RTB_HD void scene_traverse_from(const SceneView& S, const WorldRay& worldRaySour
             inBlas = false; popFloor = 0xFFFFFFFFu; nodes = S.tlas; ray = worldRaySource.load(); finite = worldFinite;
         }
         if (stackSize == 0) break;
-        const StackEntry e = stk_get(stack, sstack, --stackSize);
-        if (e.b == RTB_ENTRY_OBJECT)
+        const uint32_t e = stk_get(stack, sstack, --stackSize);
+        if (RTB_NODE_COUNT(e) == RTB_PACK_OBJECT)
         {
             // Scene::Traverse_Object, Scene.cpp:128-145
-            objectID = e.a;
+            objectID = RTB_NODE_INDEX(e);
             const DObjectTrace& obj = S.objTrace[objectID];
             const Ray localRay = transform_ray_unsafe(obj.invTransform, worldRaySource.load());
             if (obj.kind == RTB_OBJECT_SHAPE && obj.shapeType == RTB_SHAPE_MESH)
@@ -561,7 +552,7 @@ RTB_HD void scene_traverse_from(const SceneView& S, const WorldRay& worldRaySour
                 if (mesh.numNodes != 0)
                 {
                     inBlas = true; blasBase = stackSize; popFloor = stackSize; nodes = mesh.nodes; tris = mesh.tris; ray = localRay; finite = ray_is_finite(localRay);
-                    node_header(nodes, 0, curChild, curInfo);
+                    cur = node_header(nodes, 0);
                     have = true;
                 }
             }
@@ -572,7 +563,7 @@ RTB_HD void scene_traverse_from(const SceneView& S, const WorldRay& worldRaySour
         }
         else
         {
-            curChild = e.a; curInfo = e.b; have = true;
+            cur = e; have = true;
         }
     }
 }
@@ -584,7 +575,7 @@ RTB_HD void scene_traverse_from(const SceneView& S, const WorldRay& worldRaySour
 // one above - hit records are bit-identical - only the interleaving between lanes differs.
 struct TraverseWalk
 {
-    uint32_t stackSize, blasBase, popFloor, objectID, curChild, curInfo;
+    uint32_t stackSize, blasBase, popFloor, objectID, cur;
     bool inBlas, finite, worldFinite, have;
     const DNode* nodes;
     const DTri* tris;
@@ -600,9 +591,9 @@ struct TraverseWalk
         stackSize = 0; blasBase = 0; popFloor = 0xFFFFFFFFu; inBlas = false; nodes = S.tlas; tris = nullptr;
         ray = worldRaySource.load();
         worldFinite = ray_is_finite(ray); finite = worldFinite;
-        objectID = 0; have = false; curChild = 0; curInfo = 0;
-        if (S.numObjects == 1) { stk_put(stack, sstack, 0, 0u, RTB_ENTRY_OBJECT); stackSize = 1; }
-        else if (S.numTlasNodes != 0) { node_header(S.tlas, 0, curChild, curInfo); have = true; }
+        objectID = 0; have = false; cur = 0;
+        if (S.numObjects == 1) { stk_put(stack, sstack, 0, RTB_OBJECT_ENTRY(0u)); stackSize = 1; }
+        else if (S.numTlasNodes != 0) { cur = node_header(S.tlas, 0); have = true; }
         else return false;
         return true;
     }
@@ -611,10 +602,10 @@ struct TraverseWalk
     template <bool kCount, typename WorldRay>
     RTB_HD bool step(const SceneView& S, uint32_t* stack, const WorldRay& worldRaySource, TraceCounters* cnt, SharedStack sstack = 0)
     {
-        while (have && RTB_NUM_LEAVES(curInfo) == 0)
+        while (have && RTB_NODE_COUNT(cur) == 0)
         {
             DNode a, b;
-            load_node_pair(nodes, curChild, a, b);
+            load_node_pair(nodes, cur, a, b);       // (an inner node's word is the index of its first child)
             float distanceA, distanceB;
             bool hitA, hitB;
             if (finite)
@@ -633,32 +624,30 @@ struct TraverseWalk
             if (hitA && hitB)
             {
                 const bool bFirst = distanceB < distanceA;
-                stk_put(stack, sstack, stackSize++, bFirst ? a.childIndex : b.childIndex, bFirst ? a.leafInfo : b.leafInfo);
-                curChild = bFirst ? b.childIndex : a.childIndex;
-                curInfo = bFirst ? b.leafInfo : a.leafInfo;
+                stk_put(stack, sstack, stackSize++, bFirst ? a.leafInfo : b.leafInfo);
+                cur = bFirst ? b.leafInfo : a.leafInfo;
             }
-            else if (hitA) { curChild = a.childIndex; curInfo = a.leafInfo; }
-            else if (hitB) { curChild = b.childIndex; curInfo = b.leafInfo; }
+            else if (hitA) cur = a.leafInfo;
+            else if (hitB) cur = b.leafInfo;
             else if (stackSize > popFloor)
             {
-                const StackEntry e = stk_get(stack, sstack, --stackSize);
-                curChild = e.a; curInfo = e.b;
+                cur = stk_get(stack, sstack, --stackSize);
             }
             else have = false;
 #if defined(__CUDA_ARCH__) && RTB_TRAV_VOTE > 0
             if (__popc(__activemask()) < RTB_TRAV_VOTE) break;
 #endif
         }
-        if (have && RTB_NUM_LEAVES(curInfo) == 0) return true;         // left the node loop by vote
+        if (have && RTB_NODE_COUNT(cur) == 0) return true;         // left the node loop by vote
         if (have)
         {
-            const uint32_t numLeaves = RTB_NUM_LEAVES(curInfo);
+            const uint32_t numLeaves = RTB_NODE_COUNT(cur), firstItem = RTB_NODE_INDEX(cur);
             if (inBlas)
             {
                 if (kCount) cnt->triTests += numLeaves;
                 for (uint32_t i = 0; i < numLeaves; ++i)
                 {
-                    const uint32_t triangleIndex = curChild + i;
+                    const uint32_t triangleIndex = firstItem + i;
                     V3 v0, e1, e2;
                     load_tri(tris, triangleIndex, v0, e1, e2);
                     float u, v, distance;
@@ -670,7 +659,7 @@ struct TraverseWalk
             }
             else
             {
-                for (uint32_t i = numLeaves; i-- > 0;) { stk_put(stack, sstack, stackSize, curChild + i, RTB_ENTRY_OBJECT); stackSize++; }
+                for (uint32_t i = numLeaves; i-- > 0;) { stk_put(stack, sstack, stackSize, RTB_OBJECT_ENTRY(firstItem + i)); stackSize++; }
             }
             have = false;
         }
@@ -679,10 +668,10 @@ struct TraverseWalk
             inBlas = false; popFloor = 0xFFFFFFFFu; nodes = S.tlas; ray = worldRaySource.load(); finite = worldFinite;
         }
         if (stackSize == 0) return false;
-        const StackEntry e = stk_get(stack, sstack, --stackSize);
-        if (e.b == RTB_ENTRY_OBJECT)
+        const uint32_t e = stk_get(stack, sstack, --stackSize);
+        if (RTB_NODE_COUNT(e) == RTB_PACK_OBJECT)
         {
-            objectID = e.a;
+            objectID = RTB_NODE_INDEX(e);
             const DObjectTrace& obj = S.objTrace[objectID];
             const Ray localRay = transform_ray_unsafe(obj.invTransform, worldRaySource.load());
             if (obj.kind == RTB_OBJECT_SHAPE && obj.shapeType == RTB_SHAPE_MESH)
@@ -691,7 +680,7 @@ struct TraverseWalk
                 if (mesh.numNodes != 0)
                 {
                     inBlas = true; blasBase = stackSize; popFloor = stackSize; nodes = mesh.nodes; tris = mesh.tris; ray = localRay; finite = ray_is_finite(localRay);
-                    node_header(nodes, 0, curChild, curInfo);
+                    cur = node_header(nodes, 0);
                     have = true;
                 }
             }
@@ -702,7 +691,7 @@ struct TraverseWalk
         }
         else
         {
-            curChild = e.a; curInfo = e.b; have = true;
+            cur = e; have = true;
         }
         return true;
     }
@@ -764,8 +753,8 @@ struct ShadowWalk
     const DTri* tris;
     Ray ray;
     float maxDistance;
-    uint32_t curChild, curInfo;
-    uint32_t pendChild, pendInfo;          // a mesh leaf whose triangle tests are postponed
+    uint32_t cur;
+    uint32_t pend;                         // a mesh leaf whose triangle tests are postponed (its packed word; 0 = none)
     uint32_t wideMesh;                     // kEnterWide: the mesh whose 8-wide tree the caller walks with `ray` (mesh-local), then leave_wide()
 
     // false: nothing to traverse (the ray is unoccluded)
@@ -777,18 +766,18 @@ struct ShadowWalk
         nodes = S.tlas; tris = nullptr;
         ray = worldRaySource.load(); maxDistance = tMax;
         worldFinite = ray_is_finite(ray); finite = worldFinite;
-        have = false; curChild = 0; curInfo = 0; pendChild = 0; pendInfo = 0;
-        if (S.numObjects == 1) { stk_put(stack, sstack, 0, 0u, RTB_ENTRY_OBJECT); stackSize = 1; }
-        else if (S.numTlasNodes != 0) { node_header(S.tlas, 0, curChild, curInfo); have = true; }
+        have = false; cur = 0; pend = 0;
+        if (S.numObjects == 1) { stk_put(stack, sstack, 0, RTB_OBJECT_ENTRY(0u)); stackSize = 1; }
+        else if (S.numTlasNodes != 0) { cur = node_header(S.tlas, 0); have = true; }
         else return false;
         return true;
     }
 
     template <bool kCount>
-    RTB_HD bool leaf_occludes(uint32_t first, uint32_t info, TraceCounters* cnt) const
+    RTB_HD bool leaf_occludes(uint32_t leaf, TraceCounters* cnt) const
     {
         // MeshShape::Traverse_Leaf_Shadow, MeshShape.cpp:175-207
-        const uint32_t numLeaves = RTB_NUM_LEAVES(info);
+        const uint32_t numLeaves = RTB_NODE_COUNT(leaf), first = RTB_NODE_INDEX(leaf);
         if (kCount) cnt->triTests += numLeaves;
         bool occluded = false;
         for (uint32_t i = 0; i < numLeaves; ++i)
@@ -808,19 +797,18 @@ struct ShadowWalk
     {
         while (have)
         {
-            if (RTB_NUM_LEAVES(curInfo) != 0)
+            if (RTB_NODE_COUNT(cur) != 0)
             {
-                if (inBlas && pendInfo == 0 && stackSize > popFloor)
+                if (inBlas && pend == 0 && stackSize > popFloor)
                 {
-                    pendChild = curChild; pendInfo = curInfo;
-                    const StackEntry e = stk_get(stack, sstack, --stackSize);
-                    curChild = e.a; curInfo = e.b;
+                    pend = cur;
+                    cur = stk_get(stack, sstack, --stackSize);
                     continue;
                 }
                 break;
             }
             DNode a, b;
-            load_node_pair(nodes, curChild, a, b);
+            load_node_pair(nodes, cur, a, b);       // (an inner node's word is the index of its first child)
             float distanceA, distanceB;
             bool hitA, hitB;
             if (kMode == 1 || (kMode == 0 && finite))
@@ -839,17 +827,16 @@ struct ShadowWalk
             if (hitA && hitB)
             {
                 const bool swap = distanceB < distanceA;
-                stk_put(stack, sstack, stackSize++, swap ? a.childIndex : b.childIndex, swap ? a.leafInfo : b.leafInfo);
-                curChild = swap ? b.childIndex : a.childIndex; curInfo = swap ? b.leafInfo : a.leafInfo;
+                stk_put(stack, sstack, stackSize++, swap ? a.leafInfo : b.leafInfo);
+                cur = swap ? b.leafInfo : a.leafInfo;
             }
-            else if (hitA) { curChild = a.childIndex; curInfo = a.leafInfo; }
-            else if (hitB) { curChild = b.childIndex; curInfo = b.leafInfo; }
+            else if (hitA) cur = a.leafInfo;
+            else if (hitB) cur = b.leafInfo;
             else if (stackSize > popFloor)
             {
                 // both children missed: take the next pending node of this mesh right here, so that the lane stays in
                 // the node loop with the rest of its warp instead of idling until every lane has left it
-                const StackEntry e = stk_get(stack, sstack, --stackSize);
-                curChild = e.a; curInfo = e.b;
+                cur = stk_get(stack, sstack, --stackSize);
             }
             else have = false;
 #if defined(__CUDA_ARCH__) && RTB_SHADOW_VOTE > 0
@@ -865,7 +852,7 @@ struct ShadowWalk
     {
         nodes = S.tlas; ray = worldRaySource.load(); finite = worldFinite;
         // (what step() left behind when it returned kEnterWide, restated so that none of it has to live through the wide walk)
-        have = false; inBlas = false; pendInfo = 0; pendChild = 0; popFloor = 0xFFFFFFFFu; blasBase = 0; curChild = 0; curInfo = 0; tris = nullptr;
+        have = false; inBlas = false; pend = 0; popFloor = 0xFFFFFFFFu; blasBase = 0; cur = 0; tris = nullptr;
     }
 
     // kSuspendWide: a mesh that has an 8-wide tree is not walked here; step() returns kEnterWide with the mesh-local ray
@@ -884,24 +871,24 @@ struct ShadowWalk
         node_phase<kCount, 0>(stack, cnt, sstack);
 #endif
 
-        if (pendInfo != 0)
+        if (pend != 0)
         {
-            if (leaf_occludes<kCount>(pendChild, pendInfo, cnt)) return kOccluded;
-            pendInfo = 0;
+            if (leaf_occludes<kCount>(pend, cnt)) return kOccluded;
+            pend = 0;
         }
 #if RTB_SHADOW_VOTE > 0
-        if (have && RTB_NUM_LEAVES(curInfo) == 0) return kContinue;       // left the node loop by vote: carry on with the same node
+        if (have && RTB_NODE_COUNT(cur) == 0) return kContinue;       // left the node loop by vote: carry on with the same node
 #endif
         if (have)
         {
             if (inBlas)
             {
-                if (leaf_occludes<kCount>(curChild, curInfo, cnt)) return kOccluded;
+                if (leaf_occludes<kCount>(cur, cnt)) return kOccluded;
             }
             else
             {
                 // Scene::Traverse_Leaf_Shadow, Scene.cpp:180-194: one stack entry per object of the top-level leaf
-                for (uint32_t i = RTB_NUM_LEAVES(curInfo); i-- > 0;) { stk_put(stack, sstack, stackSize, curChild + i, RTB_ENTRY_OBJECT); stackSize++; }
+                for (uint32_t i = RTB_NODE_COUNT(cur); i-- > 0;) { stk_put(stack, sstack, stackSize, RTB_OBJECT_ENTRY(RTB_NODE_INDEX(cur) + i)); stackSize++; }
             }
             have = false;
         }
@@ -911,11 +898,11 @@ struct ShadowWalk
             inBlas = false; popFloor = 0xFFFFFFFFu; nodes = S.tlas; ray = worldRaySource.load(); finite = worldFinite;
         }
         if (stackSize == 0) return kVisible;
-        const StackEntry e = stk_get(stack, sstack, --stackSize);
-        if (e.b == RTB_ENTRY_OBJECT)
+        const uint32_t e = stk_get(stack, sstack, --stackSize);
+        if (RTB_NODE_COUNT(e) == RTB_PACK_OBJECT)
         {
             // Scene::Traverse_Object_Shadow, Scene.cpp:147-165
-            const DObjectTrace& obj = S.objTrace[e.a];
+            const DObjectTrace& obj = S.objTrace[RTB_NODE_INDEX(e)];
             const Ray localRay = transform_ray_unsafe(obj.invTransform, worldRaySource.load());
             if (obj.kind == RTB_OBJECT_SHAPE && obj.shapeType == RTB_SHAPE_MESH)
             {
@@ -934,7 +921,7 @@ struct ShadowWalk
                 if (mesh.numNodes != 0)
                 {
                     inBlas = true; blasBase = stackSize; popFloor = stackSize; nodes = mesh.nodes; tris = mesh.tris; ray = localRay; finite = ray_is_finite(localRay);
-                    node_header(nodes, 0, curChild, curInfo);
+                    cur = node_header(nodes, 0);
                     have = true;
                 }
             }
@@ -945,7 +932,7 @@ struct ShadowWalk
         }
         else
         {
-            curChild = e.a; curInfo = e.b; have = true;
+            cur = e; have = true;
         }
         return kContinue;
     }

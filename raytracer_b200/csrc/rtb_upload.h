@@ -274,6 +274,11 @@ inline bool build_host_scene(const RtbSceneDesc& d, HostScene& out, std::string&
         err = "BVH too deep for the traversal stack";
         return false;
     }
+    // the walks read ONE packed word per node (rtb_trace.h): index | count << 26, kept in the leafInfo slot of OUR copies
+    // of the trees (the caller's arrays stay in the reference's format; everything above, the any-hit tree's collapse
+    // included, has read that format by now)
+    for (DNode& n : out.tlas) n.leafInfo = pack_node_word(n.childIndex, n.leafInfo);
+    for (HostMesh& m : out.meshes) for (DNode& n : m.nodes) n.leafInfo = pack_node_word(n.childIndex, n.leafInfo);
     return true;
 }
 
