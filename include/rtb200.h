@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RTB_API_VERSION 3   /* 2: textures (RtbTexture, RtbMaterialTextures, RtbSceneDesc::textures ...)  3: RTB_RENDERER_VCM, rtb_set_vcm_params, rtb_vcm_* */
+#define RTB_API_VERSION 4   /* 2: textures (RtbTexture, RtbMaterialTextures, RtbSceneDesc::textures ...)  3: RTB_RENDERER_VCM, rtb_set_vcm_params, rtb_vcm_*  4: RTB_RENDERER_LIGHT_TRACER */
 
 typedef enum RtbStatus
 {
@@ -232,7 +232,11 @@ typedef enum RtbRenderer
     RTB_RENDERER_PATH_TRACER     = 0,  /* "Path Tracer"     Core/Rendering/PathTracer.cpp    */
     RTB_RENDERER_PATH_TRACER_MIS = 1,  /* "Path Tracer MIS" Core/Rendering/PathTracerMIS.cpp */
     RTB_RENDERER_DEBUG           = 2,  /* "Debug"           Core/Rendering/DebugRenderer.cpp */
-    RTB_RENDERER_VCM             = 3   /* "VCM"             Core/Rendering/VertexConnectionAndMerging.cpp (rtb_set_vcm_params) */
+    RTB_RENDERER_VCM             = 3,  /* "VCM"             Core/Rendering/VertexConnectionAndMerging.cpp (rtb_set_vcm_params) */
+    RTB_RENDERER_LIGHT_TRACER    = 4   /* "Light Tracer"    Core/Rendering/LightTracer.cpp: one light sub-path per pixel and pass, every vertex connected
+                                          to the camera and splatted (Film::AccumulateColor(pos, ...)); draws from a generator seeded by
+                                          (pixel, pass, RtbVcmParams::lightPathSeed) where the reference uses per-thread generators:
+                                          reproducible here, statistical against the reference; rendered one pass at a time like VCM */
 } RtbRenderer;
 
 /* DebugRenderingMode, Core/Rendering/DebugRenderer.h:7-33 (same numeric values) */

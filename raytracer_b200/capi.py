@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("RTB200_LIB", os.path.join(_HERE, "librtb200.so"))   #
 
 RTB_INVALID_OBJECT = 0xFFFFFFFF
 RTB_LIGHT_OBJECT = 0xFFFFFFFE
-RTB_RENDERER_PATH_TRACER, RTB_RENDERER_PATH_TRACER_MIS, RTB_RENDERER_DEBUG, RTB_RENDERER_VCM = 0, 1, 2, 3
+RTB_RENDERER_PATH_TRACER, RTB_RENDERER_PATH_TRACER_MIS, RTB_RENDERER_DEBUG, RTB_RENDERER_VCM, RTB_RENDERER_LIGHT_TRACER = 0, 1, 2, 3, 4
 RTB_COMM_ID_BYTES = 128
 RTB_TRACE_CLOSEST, RTB_TRACE_SHADOW = 0, 1
 RTB_LIGHT_SAMPLING_SINGLE, RTB_LIGHT_SAMPLING_ALL = 0, 1

@@ -390,7 +390,8 @@ RTB_HD float camera_pdf_w(const M4& localToWorld, float tanHalfFoV, float aspect
 struct CameraConnection { M4 localToWorld, worldToScreen; float tanHalfFoV, aspectRatio; };
 
 template <bool kTex = true, typename Rng, typename Splat>
-RTB_HD uint32_t light_trace_path(const SceneView& S, const CameraConnection& camera, uint32_t maxRayDepth, Rng& rng, Splat& splat)
+RTB_HD uint32_t light_trace_path(const SceneView& S, const CameraConnection& camera, uint32_t maxRayDepth, Rng& rng, Splat& splat, SharedStack sstack = 0,
+                                 unsigned long long* shadowRays = nullptr, unsigned long long* visible = nullptr)
 {
     if (S.numLights == 0) return 0;
     const float lightPickingProbability = 1.0f / (float)S.numLights;
@@ -413,7 +414,7 @@ RTB_HD uint32_t light_trace_path(const SceneView& S, const CameraConnection& cam
     {
         Hit hit;
         hit.objectId = RTB_INVALID_OBJECT; hit.subObjectId = 0; hit.distance = INFINITY; hit.u = 0.0f; hit.v = 0.0f;
-        scene_traverse<false>(S, ray, hit, nullptr);
+        scene_traverse<false>(S, ray, hit, nullptr, sstack);
         if (hit.distance == INFINITY) break;                       // ray missed
         if (hit.subObjectId == RTB_LIGHT_OBJECT) break;         // we hit a light directly
         evaluate_intersection<kTex>(S, ray, hit, vx, RTB_NO_MATERIAL);
@@ -437,8 +438,10 @@ RTB_HD uint32_t light_trace_path(const SceneView& S, const CameraConnection& cam
                 if (camera_world_to_film(camera.worldToScreen, vx.position, filmX, filmY))
                 {
                     const Ray shadowRay = make_ray(vx.position + vx.normal * 0.0001f, dirToCamera);
-                    if (!scene_traverse_shadow<false>(S, shadowRay, cameraDistance * 0.999f, nullptr))
+                    if (shadowRays) (*shadowRays)++;
+                    if (!scene_traverse_shadow<false>(S, shadowRay, cameraDistance * 0.999f, nullptr, sstack))
                     {
+                        if (visible) (*visible)++;
                         const float cameraPdfA = camera_pdf_w(camera.localToWorld, camera.tanHalfFoV, camera.aspectRatio, neg(dirToCamera)) / cameraDistanceSqr;
                         const V4 contribution = (cameraFactor * throughput) * cameraPdfA;
                         splat(filmX, filmY, xyz(contribution));

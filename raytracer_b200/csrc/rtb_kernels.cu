@@ -1934,7 +1934,7 @@ int rtb_reset(RtbContext* c)
 
 static int fill_pass_params(RtbContext* c, const RtbPassDesc* pass, PassParams& P, bool uploadSeed)
 {
-    if (pass->renderer > RTB_RENDERER_VCM) return fail(RTB_ERR_INVALID_ARG, "unknown renderer id %u", pass->renderer);   // CreateRenderer, Renderer.cpp:45-69
+    if (pass->renderer > RTB_RENDERER_LIGHT_TRACER) return fail(RTB_ERR_INVALID_ARG, "unknown renderer id %u", pass->renderer);   // CreateRenderer, Renderer.cpp:45-69
     if (pass->maxRayDepth >= 255u || pass->maxRayDepth >= RTB_MAX_DEPTH_SLOTS) return fail(RTB_ERR_INVALID_ARG, "maxRayDepth %u too large (limit %u)", pass->maxRayDepth, RTB_MAX_DEPTH_SLOTS - 1);
     if (pass->camera.barrelDistortionVariableFactor != 0.0f) return fail(RTB_ERR_UNSUPPORTED, "variable barrel distortion draws from a per-thread RNG in the reference and is not supported");
     if (pass->numSeedDims > 0 && !pass->seed) return fail(RTB_ERR_INVALID_ARG, "seed pointer is null");
@@ -2269,8 +2269,10 @@ static int vcm_fold(RtbContext* c)
 static int render_vcm_pass(RtbContext* c, const RtbPassDesc* pass)
 {
     RtbContext::Vcm& v = c->vcm;
-    if (c->hasActiveList) return fail(RTB_ERR_UNSUPPORTED, "VCM: adaptive rendering (rtb_set_active_tiles) is not supported");
-    if (c->numShards > 1 && v.params.useVertexMerging) return fail(RTB_ERR_UNSUPPORTED, "VCM: vertex merging needs the photons of every shard; sharded contexts support vertex connection only");
+    // RTB_RENDERER_LIGHT_TRACER shares the splat machinery (raster splat buffers, fold, all-reduce when sharded) and nothing else
+    const bool lightTracer = pass->renderer == RTB_RENDERER_LIGHT_TRACER;
+    if (c->hasActiveList) return fail(RTB_ERR_UNSUPPORTED, "VCM / Light Tracer: adaptive rendering (rtb_set_active_tiles) is not supported");
+    if (!lightTracer && c->numShards > 1 && v.params.useVertexMerging) return fail(RTB_ERR_UNSUPPORTED, "VCM: vertex merging needs the photons of every shard; sharded contexts support vertex connection only");
     PassParams P;
     int rc = fill_pass_params(c, pass, P, false);
     if (rc != RTB_OK) return rc;
@@ -2302,8 +2304,8 @@ static int render_vcm_pass(RtbContext* c, const RtbPassDesc* pass)
     for (uint32_t p = 0; p <= pass->passIndex; ++p)
         bidir_begin_pass(V.pass, p, (float)(c->width * c->height), v.params.initialMergingRadius, v.params.minMergingRadius, v.params.mergingRadiusMultiplier);
     // photons of the previous pass of this frame, if that is what the buffer holds
-    const bool havePhotons = v.params.useVertexMerging && pass->passIndex > 0 && v.lastPassIndex + 1u == pass->passIndex;
-    if (v.params.useVertexMerging && pass->passIndex > 0 && !havePhotons)
+    const bool havePhotons = !lightTracer && v.params.useVertexMerging && pass->passIndex > 0 && v.lastPassIndex + 1u == pass->passIndex;
+    if (!lightTracer && v.params.useVertexMerging && pass->passIndex > 0 && !havePhotons)
         return fail(RTB_ERR_INVALID_ARG, "VCM: pass %u merges with the photons of pass %u, which was not the previous pass rendered", pass->passIndex, pass->passIndex - 1u);
     V.camera.localToWorld = P.camLocalToWorld; V.camera.tanHalfFoV = P.tanHalfFoV; V.camera.aspectRatio = P.aspectRatio;
     V.camera.worldToScreen = camera_world_to_screen(P.camLocalToWorld, P.aspectRatio, P.tanHalfFoV);
@@ -2319,6 +2321,21 @@ static int render_vcm_pass(RtbContext* c, const RtbPassDesc* pass)
 
     const int blocks256 = c->numSMs * 4;
     uint32_t launches = 0;
+    if (lightTracer)
+    {
+        // LightTracer::RenderPixel returns black for the pixel itself (LightTracer.cpp:174): the film only receives the splats
+        const int blocks = (int)std::min<size_t>((size_t)c->numSMs * 16, std::max<size_t>(1, ((size_t)c->numPixels + 127) / 128));
+        if (c->textures.count > 0) k_light_tracer<true><<<blocks, 128, c->stackBytes, s>>>(c->view, P, V, c->pixelList.ptr, c->numPixels, c->totals.ptr);
+        else k_light_tracer<false><<<blocks, 128, c->stackBytes, s>>>(c->view, P, V, c->pixelList.ptr, c->numPixels, c->totals.ptr);
+        RTB_CUDA(cudaGetLastError());
+        v.splatsPending = true;
+        v.lastPassIndex = 0xFFFFFFFEu;                 // no photons of this pass for a later VCM pass to merge with
+        c->counters.numPrimaryRays += c->numPixels;
+        c->counters.numKernelLaunches += 1;
+        c->passesSinceReset += 1;
+        if (c->numShards == 1) return vcm_fold(c);
+        return RTB_OK;
+    }
     if (!havePhotons) RTB_CUDA(cudaMemsetAsync(v.photonCount.ptr + prev, 0, sizeof(uint32_t), s));
     if (havePhotons)
     {
@@ -2374,7 +2391,7 @@ extern "C" int rtb_render_passes(RtbContext* c, const RtbPassDesc* passes, uint3
             if (needed > pass->numSeedDims)
                 return fail(RTB_ERR_INVALID_ARG, "rtb_render_pass: VCM needs %u sample dimensions (lights=%u, maxPathLength=%u) but only %u are seeded", needed, c->numLights, c->vcm.params.maxPathLength, pass->numSeedDims);
         }
-        else if (pass->renderer != RTB_RENDERER_DEBUG)
+        else if (pass->renderer != RTB_RENDERER_DEBUG && pass->renderer != RTB_RENDERER_LIGHT_TRACER)       // (the Light Tracer draws nothing from the pixel sampler)
         {
             const uint32_t L = pass->renderer == RTB_RENDERER_PATH_TRACER_MIS ? (pass->lightSamplingStrategy == RTB_LIGHT_SAMPLING_ALL ? c->numLights : (c->numLights ? 1u : 0u)) : 0u;
             const uint32_t D = pass->maxRayDepth;
@@ -2399,7 +2416,7 @@ extern "C" int rtb_render_passes(RtbContext* c, const RtbPassDesc* passes, uint3
     uint32_t i = 0;
     while (i < count)
     {
-        if (passes[i].renderer == RTB_RENDERER_VCM)
+        if (passes[i].renderer == RTB_RENDERER_VCM || passes[i].renderer == RTB_RENDERER_LIGHT_TRACER)
         {
             int rc = render_vcm_pass(c, passes + i);
             if (rc != RTB_OK) return rc;

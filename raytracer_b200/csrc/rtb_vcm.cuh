@@ -277,6 +277,66 @@ __global__ void __launch_bounds__(128, 3) k_vcm_light(const __grid_constant__ Sc
     }
 }
 
+// Film::AccumulateColor(pos, value, rng), Film.cpp:41-77, onto the raster splat buffers: nearest pixel, a random +1 step in x by
+// the fractional part (Random::GetVector4 draws four lanes)
+struct FilmSplat
+{
+    const PassParams& P;
+    const VcmDevice& V;
+    DeviceRng& rng;
+    __device__ void operator()(float filmX, float filmY, const V3& value) const
+    {
+        const float cx = filmX * (float)P.width + 0.0f, cy = filmY * (float)P.height + 0.5f;
+        int32_t ix = cvt_rn(cx);
+        const float ux = rng.next_float();
+        rng.next_float(); rng.next_float(); rng.next_float();
+        if (ux < cx - (float)ix) ix++;
+        const int32_t y = (int32_t)(P.height - 1u) - (int32_t)cy;
+        if ((uint32_t)ix < P.width && (uint32_t)y < P.height)
+        {
+            const size_t o = ((size_t)y * P.width + (uint32_t)ix) * 3u;
+            atomicAdd(V.splat + o, value.x); atomicAdd(V.splat + o + 1, value.y); atomicAdd(V.splat + o + 2, value.z);
+            if (V.splat2) { atomicAdd(V.splat2 + o, value.x); atomicAdd(V.splat2 + o + 1, value.y); atomicAdd(V.splat2 + o + 2, value.z); }
+        }
+    }
+};
+
+// The reference's "Light Tracer" renderer (LightTracer::RenderPixel, LightTracer.cpp:26-175): one light sub-path per pixel and
+// pass, every vertex connected to the camera and splatted; the pixel itself receives nothing.  The loop is rtb_bidir.h's
+// light_trace_path (pinned against the reference on the CPU, tests/test_hostsim_parity.py); one thread per sub-path like
+// the VCM kernels, numbers from the same counter-seeded generator.
+template <bool kTex>
+__global__ void __launch_bounds__(128, 3) k_light_tracer(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const __grid_constant__ VcmDevice V,
+                                                         const uint32_t* __restrict__ pixelList, uint32_t numPixels, Totals* tot)
+{
+    extern __shared__ uint32_t smemStack[];
+    SharedStack sstack = (SharedStack)__cvta_generic_to_shared(smemStack) + threadIdx.x * 4u;
+    asm volatile("" : "+r"(sstack));
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long rays = 0, shadowRays = 0, visible = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < numPixels; i += stride)
+    {
+        const uint32_t pix = pixelList[i];
+        DeviceRng rng;
+        rng.state = hash64(((uint64_t)pix << 32) ^ (uint64_t)P.passIndex ^ (((uint64_t)V.seedHi << 32 | V.seedLo) * 0x9E3779B97F4A7C15ULL)) | 1ull;
+        FilmSplat splat = { P, V, rng };
+        rays += light_trace_path<kTex>(S, V.camera, P.maxRayDepth, rng, splat, sstack, &shadowRays, &visible);
+    }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        rays += __shfl_down_sync(0xFFFFFFFFu, rays, o);
+        shadowRays += __shfl_down_sync(0xFFFFFFFFu, shadowRays, o);
+        visible += __shfl_down_sync(0xFFFFFFFFu, visible, o);
+    }
+    if (lane == 0)
+    {
+        if (rays) atomicAdd(&tot->numRays, rays);
+        if (shadowRays) atomicAdd(&tot->numShadowRays, shadowRays);
+        if (visible) atomicAdd(&tot->numShadowRaysHit, visible);
+    }
+}
+
 // MergeVertices, VertexConnectionAndMerging.cpp:808-906 + HashGrid::Process (HashGrid.h:84-146): the 2 x 2 x 2 block of
 // cells around the query point, every photon within radiusVM
 __device__ __forceinline__ V4 vcm_merge(const VcmDevice& V, const BidirPath& cameraPath, const Vertex& vx)

@@ -322,7 +322,8 @@ public:
         else if (name == "Path Tracer MIS") mRenderer = RTB_RENDERER_PATH_TRACER_MIS;
         else if (name == "Debug") mRenderer = RTB_RENDERER_DEBUG;
         else if (name == "VCM") mRenderer = RTB_RENDERER_VCM;          // VertexConnectionAndMerging; its public members: SetVcmParams
-        else { mError = "Unknown renderer name: '" + name + "' (supported: 'Path Tracer', 'Path Tracer MIS', 'Debug', 'VCM')"; return false; }
+        else if (name == "Light Tracer") mRenderer = RTB_RENDERER_LIGHT_TRACER;
+        else { mError = "Unknown renderer name: '" + name + "' (supported: 'Path Tracer', 'Path Tracer MIS', 'Debug', 'VCM', 'Light Tracer')"; return false; }
         return true;
     }
     // VertexConnectionAndMerging::mUseVertexConnection ... mMergingRadiusMultiplier (VertexConnectionAndMerging.h:48-56)

@@ -123,3 +123,77 @@ def test_vcm_sharded_connection_only_matches_unsharded(tmp_path):
     finally:
         for c in ctxs:
             c.close()
+
+
+@pytest.mark.skipif(not util.oracle_available("exact"), reason="prebuilt oracle/_ref/exact did not travel to this box")
+@pytest.mark.parametrize("scene,passes,mean_tolerance,min_correlation", [
+    ("cornell", 200, 0.03, 0.995),
+    ("materials", 200, 0.04, 0.8),      # point / spot lights and specular surfaces: two runs of the REFERENCE with different seeds correlate at 0.87 here
+])
+def test_light_tracer_statistics_against_the_live_reference(tmp_path, scene, passes, mean_tolerance, min_correlation):
+    """RTB_RENDERER_LIGHT_TRACER (k_light_tracer; reference: LightTracer::RenderPixel, LightTracer.cpp:26-175): one light
+    sub-path per pixel and pass, its vertices connected to the camera and splatted.  Statistical bar, as for VCM (the
+    reference draws from per-thread generators): mean colour per channel, 8 x 8-block image, secondary sum, and the number
+    of path rays within the sampling noise of the reference's."""
+    w = h = 48
+    scn = os.path.join(util.GOLDEN, "scenes")
+    common = ["--scene", os.path.join(scn, scene + ".json"), "--data", scn + "/", "--width", w, "--height", h]
+    refp, ref2p, passp, flatp = (str(tmp_path / n) for n in ("ref.sum", "ref.sum2", "ref.passes", "scene.rtb"))
+    meta = util.run_rtref(["render", *common, "--passes", passes, "--dims", 256, "--depth", 8, "--renderer", "Light Tracer",
+                           "--dump-sum", refp, "--dump-sum2", ref2p, "--dump-passes", passp])
+    util.run_rtref(["flat", *common, "--out", flatp])
+    ref, ref2 = util.load_sum(refp, w, h), util.load_sum(ref2p, w, h)
+    sf = capi.SceneFile(flatp)
+    ps = capi.PassScript(passp)
+    with capi.Context(device=0) as ctx:
+        ctx.upload_scene(sf)
+        ctx.resize(w, h)
+        ctx.render_passes(capi.camera_for(sf, w, h), ps.seeds[:passes], ps.offsets[:passes], 0, renderer=capi.RTB_RENDERER_LIGHT_TRACER, max_depth=8)
+        got, got2, counters = ctx.read_sum(), ctx.read_sum(1), ctx.counters()
+    a, b = ref / passes, got / passes
+    assert np.isfinite(b).all() and (b >= 0).all() and b.mean() > 0
+    ma, mb = a.mean(axis=(0, 1)), b.mean(axis=(0, 1))
+    assert (np.abs(ma - mb) <= mean_tolerance * ma).all(), (ma, mb)
+    blocks = lambda x: x.reshape(6, 8, 6, 8, 3).mean(axis=(1, 3)).ravel()
+    assert np.corrcoef(blocks(a), blocks(b))[0, 1] >= min_correlation
+    m2a, m2b = ref2.mean(axis=(0, 1)), got2.mean(axis=(0, 1))
+    assert (np.abs(m2a - m2b) <= 2.0 * mean_tolerance * m2a).all(), (m2a, m2b)
+    assert counters["numPrimaryRays"] == w * h * passes
+    assert counters["numRays"] >= w * h * passes * 0.5 and counters["numShadowRaysHit"] <= counters["numShadowRays"]
+
+
+def test_light_tracer_is_reproducible_and_shards_add_up():
+    """Same seeds, same image (up to the order of the float atomics); the splats of two shards' light paths, summed like the
+    all-reduce of a multi-GPU caller and folded, give the unsharded image."""
+    import torch
+    sf = capi.SceneFile(util.golden("cornell.rtb"))
+    ps = capi.PassScript(util.golden("cornell.passes"))
+    w = h = 64
+    n = 4
+    imgs = []
+    for _ in range(2):
+        with capi.Context(device=0) as ctx:
+            ctx.upload_scene(sf); ctx.resize(w, h)
+            ctx.render_passes(capi.camera_for(sf, w, h), ps.seeds[:n], ps.offsets[:n], 0, renderer=capi.RTB_RENDERER_LIGHT_TRACER)
+            imgs.append(ctx.read_sum())
+    whole = imgs[0]
+    assert np.allclose(imgs[0], imgs[1], rtol=1e-4, atol=1e-5) and whole.mean() > 0
+    ctxs = [capi.Context(device=0, num_shards=2, shard_index=s) for s in range(2)]
+    try:
+        bufs = []
+        for c in ctxs:
+            c.upload_scene(sf); c.resize(w, h)
+            c.render_passes(capi.camera_for(sf, w, h), ps.seeds[:n], ps.offsets[:n], 0, renderer=capi.RTB_RENDERER_LIGHT_TRACER)
+            c.synchronize()
+            bufs.append(c.vcm_splat_buffers())
+        total = [bufs[0][k] + bufs[1][k] for k in range(2)]
+        acc = np.zeros_like(whole)
+        for c, b in zip(ctxs, bufs):
+            b[0].copy_(total[0]); b[1].copy_(total[1])
+            torch.cuda.synchronize()
+            c.vcm_fold_splats()
+            acc += c.read_sum()
+        assert np.allclose(acc, whole, rtol=2e-4, atol=1e-5)
+    finally:
+        for c in ctxs:
+            c.close()
