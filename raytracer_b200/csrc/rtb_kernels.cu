@@ -45,7 +45,8 @@ using namespace rtb;
 // 64 registers -> 8 CTAs of 128 threads per SM: the traversal kernels are latency bound, occupancy is worth more than
 // the few spilled bytes (measured: 72 regs / 7 CTAs 4.4 ms, 64 regs / 8 CTAs 3.6 ms per pass for k_traverse)
 #ifndef RTB_SHADE_MINBLOCKS
-#define RTB_SHADE_MINBLOCKS 6     // measured k_shade per 8 passes: 4 CTAs/SM (128 regs) 9.13 ms, 5: 8.81, 6 (80 regs): 8.20, 8: 8.60
+#define RTB_SHADE_MINBLOCKS 5     // k_shade per 8 passes, one kernel per integrator: 4 CTAs/SM (116 regs, no spills) 8.91 ms, 5 (96 regs) 8.30, 6 (80 regs) 8.63
+                                  // (with the three integrators in one kernel: 4: 9.13, 5: 8.81, 6: 8.20 on the round-1 build, 8.72 now)
 #endif
 #ifndef RTB_TRAV_MINBLOCKS
 #define RTB_TRAV_MINBLOCKS 8
@@ -159,7 +160,7 @@ struct RayInShadowQueue
     }
 };
 
-__device__ __forceinline__ void load_path(const PathBuf& b, uint32_t i, const Wavefront& W, uint32_t width, uint32_t numSeedDims, PathState& ps)
+__device__ __forceinline__ void load_path(const PathBuf& b, uint32_t i, const Wavefront& W, uint32_t width, uint32_t numSeedDims, PathState& ps, bool needRaster = true)
 {
     load_ray(b, i, ps.ray);
     const float4 t = b.p3[i];
@@ -173,11 +174,19 @@ __device__ __forceinline__ void load_path(const PathBuf& b, uint32_t i, const Wa
     ps.lastSpecular = (m.z >> 19) & 1u;
     ps.lastMaterial = (m.z >> 20) == 0xFFFu ? RTB_NO_MATERIAL : (m.z >> 20);
     ps.lastPdfW = __uint_as_float(m.w);
-    const uint32_t pix = W.pixelList[ps.pixel];
-    ps.rasterPixel = pix;
-    const uint32_t x = pix % width, y = pix / width;
-    ps.sampler.bnOffset = 4u * (128u * (y & 127u) + (x & 127u));
     ps.sampler.seedBase = ps.passSlot * numSeedDims;
+    // The raster position is behind a dependent gather (slot -> pixelList), and what needs it is rare: the blue-noise offset
+    // serves sampler dimensions 0..3 only (GenericSampler.cpp:88-96) - a path is past them after its first vertex - and the
+    // raster index keys the `Single` light pick.  Paths that need neither skip the gather (ncu, round 2: 10 % of k_shade's
+    // stall samples sat on this load and on the division by the width behind it).
+    if (needRaster || ps.sampler.dim < 4u)
+    {
+        const uint32_t pix = W.pixelList[ps.pixel];
+        ps.rasterPixel = pix;
+        const uint32_t x = pix % width, y = pix / width;
+        ps.sampler.bnOffset = 4u * (128u * (y & 127u) + (x & 127u));
+    }
+    else { ps.rasterPixel = 0u; ps.sampler.bnOffset = 0u; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -244,6 +253,9 @@ __global__ void __launch_bounds__(128, RTB_TRAV_MINBLOCKS) k_traverse(const __gr
 // Closest-hit rays on persistent warps (RTB_TRAV_KERNEL=persistent): RTB_TRAV_MINBLOCKS CTAs per SM stay resident, a warp
 // draws paths from the queue with one atomic whenever at least RTB_TP_REFILL of its lanes are idle, and every lane runs
 // the resumable TraverseWalk.  Same visits per ray as k_traverse, fuller warps.
+// (measured and dropped, round 2: `prefetch.global.L2` of the queue entries 2 048 / 8 192 positions ahead of the cursor in both
+//  persistent kernels - k_shadow_wide 18.31 -> 18.78 ms per 8 passes, k_traverse_p unchanged; the same for the path state of
+//  k_shade's tile during its sort, 8.63 -> 8.73: the queues stream from HBM but their latency is already covered)
 #ifndef RTB_TP_REFILL
 #define RTB_TP_REFILL 24      // (k_traverse_p per launch on the bench: 4: 1.387, 8: 1.338, 12: 1.285, 20: 1.197, 24: 1.174, 28: 1.175 ms; k_traverse 1.246)
 #endif
@@ -345,7 +357,7 @@ struct DeviceSink
 // A path owns its pixel's pass colour and its own shadow-ray slots, so the order in which paths are shaded cannot change
 // the film (the compacted output order is not deterministic to begin with: one atomic per warp).
 #ifndef RTB_SHADE_TILE
-#define RTB_SHADE_TILE 1024u
+#define RTB_SHADE_TILE 512u        // a multiple of 128 (k_shade per 8 passes at 5 CTAs / SM: 256: 8.39 ms, 512: 8.16, 1024: 8.30, 2048: 9.16)
 #endif
 #define RTB_SHADE_BINS 32u
 
@@ -367,7 +379,10 @@ __device__ __forceinline__ uint32_t shade_key(const SceneView& S, uint32_t objec
     return 2u + (bsdf < 14u ? bsdf : 14u) + (mesh ? 0u : 15u);       // 2..16 mesh, 17..31 analytic shapes
 }
 
-template <bool kTex, bool kSort>
+// kRenderer: one instantiation per integrator, so that a launch carries one integrator's code only (the three together
+// are 13 600 SASS instructions against a 32 KB instruction cache, and the register allocation of the common part was
+// the worst case of the three)
+template <bool kTex, bool kSort, uint32_t kRenderer>
 __global__ void __launch_bounds__(128, RTB_SHADE_MINBLOCKS) k_shade(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const __grid_constant__ Wavefront W, uint32_t depth)
 {
     const uint32_t count = W.ctl->tailTaken ? 0u : W.ctl->pathCount[depth];
@@ -387,12 +402,26 @@ __global__ void __launch_bounds__(128, RTB_SHADE_MINBLOCKS) k_shade(const __grid
         __syncthreads();                                   // the previous tile's order is no longer read
         if (threadIdx.x < RTB_SHADE_BINS) binCursor[threadIdx.x] = 0u;
         __syncthreads();
-        for (uint32_t j = threadIdx.x; j < tileCount; j += 128u)
+        // (a key is the end of a chain of dependent loads - hit, object, shape, mesh, triangle, material: the thread's
+        //  RTB_SHADE_TILE / 128 chains are written side by side so that their latencies overlap instead of adding up)
         {
-            const uint4 h0 = W.hit0[tileBase + j];
-            const uint32_t key = shade_key(S, h0.x, h0.y);
-            tileKeys[j] = (uint8_t)key;
-            atomicAdd(&binCursor[key], 1u);
+            constexpr uint32_t kPerThread = RTB_SHADE_TILE / 128u;
+            uint4 h0[kPerThread];
+            uint32_t keys[kPerThread];
+#pragma unroll
+            for (uint32_t k = 0; k < kPerThread; ++k)
+            {
+                const uint32_t j = threadIdx.x + 128u * k;
+                h0[k] = j < tileCount ? W.hit0[tileBase + j] : make_uint4(RTB_INVALID_OBJECT, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < kPerThread; ++k) keys[k] = shade_key(S, h0[k].x, h0[k].y);
+#pragma unroll
+            for (uint32_t k = 0; k < kPerThread; ++k)
+            {
+                const uint32_t j = threadIdx.x + 128u * k;
+                if (j < tileCount) { tileKeys[j] = (uint8_t)keys[k]; atomicAdd(&binCursor[keys[k]], 1u); }
+            }
         }
         __syncthreads();
         if (threadIdx.x < 32u)
@@ -421,7 +450,7 @@ __global__ void __launch_bounds__(128, RTB_SHADE_MINBLOCKS) k_shade(const __grid
         PathState ps;
         if (valid)
         {
-            load_path(in, i, W, P.width, P.numSeedDims, ps);
+            load_path(in, i, W, P.width, P.numSeedDims, ps, kRenderer == RTB_RENDERER_PATH_TRACER_MIS && !P.lightSamplingAll);
             const uint4 h0 = W.hit0[i];
             Hit hit;
             hit.objectId = h0.x; hit.subObjectId = h0.y; hit.distance = __uint_as_float(h0.z); hit.u = __uint_as_float(h0.w);
@@ -431,8 +460,8 @@ __global__ void __launch_bounds__(128, RTB_SHADE_MINBLOCKS) k_shade(const __grid
             const float4 pc = W.passColor[colorIndex];
             DeviceSink sink(W, i * W.raysPerPath);
             sink.result = v3(pc.x, pc.y, pc.z);
-            if (P.renderer == RTB_RENDERER_PATH_TRACER_MIS) alive = shade_vertex_mis<kTex>(S, P, ps, hit, sink, numShadow);
-            else if (P.renderer == RTB_RENDERER_PATH_TRACER) alive = shade_vertex_pt<kTex>(S, P, ps, hit, sink);
+            if (kRenderer == RTB_RENDERER_PATH_TRACER_MIS) alive = shade_vertex_mis<kTex>(S, P, ps, hit, sink, numShadow);
+            else if (kRenderer == RTB_RENDERER_PATH_TRACER) alive = shade_vertex_pt<kTex>(S, P, ps, hit, sink);
             else shade_debug<kTex>(S, P, ps, hit, sink);
             if (sink.dirty) W.passColor[colorIndex] = make_float4(sink.result.x, sink.result.y, sink.result.z, 0.0f);
             if (numShadow)
@@ -442,34 +471,33 @@ __global__ void __launch_bounds__(128, RTB_SHADE_MINBLOCKS) k_shade(const __grid
                 shadowRaysLocal += numShadow;
             }
         }
-        // stream compaction of the survivors (one atomic per warp)
+        // stream compaction of the survivors, compacted lists of the paths that own shadow rays and of the rays themselves
+        // (warp prefix sum): three queue counters, bumped by lanes 0..2 in ONE atomic instruction - one L2 round trip per
+        // warp and iteration where three atomics in a row cost two (ncu, round 2: 7 % of k_shade's stall samples)
         const uint32_t aliveMask = __ballot_sync(0xFFFFFFFFu, alive);
-        if (aliveMask)
-        {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&W.ctl->pathCount[depth + 1], __popc(aliveMask));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (alive) store_path(out, base + __popc(aliveMask & ((1u << lane) - 1u)), ps);
-        }
-        // compacted lists of the paths that own shadow rays and of the rays themselves (warp prefix sum, two atomics per warp)
         const uint32_t shMask = __ballot_sync(0xFFFFFFFFu, numShadow != 0);
+        uint32_t incl = numShadow;
         if (shMask)
         {
-            uint32_t incl = numShadow;
             for (int o = 1; o < 32; o <<= 1)
             {
                 const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
                 if (lane >= (uint32_t)o) incl += up;
             }
-            const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            uint32_t pathBase = 0, rayBase = 0;
-            if (lane == 0)
-            {
-                pathBase = atomicAdd(&W.ctl->shadowPathCount[depth], __popc(shMask));
-                rayBase = atomicAdd(&W.ctl->shadowRayCount[depth], total);
-            }
-            pathBase = __shfl_sync(0xFFFFFFFFu, pathBase, 0);
-            rayBase = __shfl_sync(0xFFFFFFFFu, rayBase, 0);
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        uint32_t got = 0;
+        {
+            uint32_t* const counter = lane == 0u ? &W.ctl->pathCount[depth + 1] : lane == 1u ? &W.ctl->shadowPathCount[depth] : &W.ctl->shadowRayCount[depth];
+            const uint32_t amount = lane == 0u ? (uint32_t)__popc(aliveMask) : lane == 1u ? (uint32_t)__popc(shMask) : total;
+            if (lane < 3u && amount != 0u) got = atomicAdd(counter, amount);
+        }
+        const uint32_t base = __shfl_sync(0xFFFFFFFFu, got, 0);
+        const uint32_t pathBase = __shfl_sync(0xFFFFFFFFu, got, 1);
+        const uint32_t rayBase = __shfl_sync(0xFFFFFFFFu, got, 2);
+        if (alive) store_path(out, base + __popc(aliveMask & ((1u << lane) - 1u)), ps);
+        if (shMask)
+        {
             if (numShadow)
             {
                 W.shList[pathBase + __popc(shMask & ((1u << lane) - 1u))] = i;
@@ -482,6 +510,15 @@ __global__ void __launch_bounds__(128, RTB_SHADE_MINBLOCKS) k_shade(const __grid
     // counters: one atomic per warp
     for (int o = 16; o > 0; o >>= 1) shadowRaysLocal += __shfl_down_sync(0xFFFFFFFFu, shadowRaysLocal, o);
     if (lane == 0 && shadowRaysLocal) atomicAdd(&W.tot->numShadowRays, shadowRaysLocal);
+}
+
+// k_shade of the pass' integrator (the wavefront runs "Path Tracer", "Path Tracer MIS" and "Debug")
+template <bool kTex, bool kSort>
+static void launch_shade(int blocks, cudaStream_t s, const SceneView& S, const PassParams& P, const Wavefront& W, uint32_t depth)
+{
+    if (P.renderer == RTB_RENDERER_PATH_TRACER_MIS) k_shade<kTex, kSort, RTB_RENDERER_PATH_TRACER_MIS><<<blocks, 128, 0, s>>>(S, P, W, depth);
+    else if (P.renderer == RTB_RENDERER_PATH_TRACER) k_shade<kTex, kSort, RTB_RENDERER_PATH_TRACER><<<blocks, 128, 0, s>>>(S, P, W, depth);
+    else k_shade<kTex, kSort, RTB_RENDERER_DEBUG><<<blocks, 128, 0, s>>>(S, P, W, depth);
 }
 
 // RTB_SHADOW_REFILL = n > 0: persistent warps that fetch new shadow rays when at least n lanes are idle.  Measured on the
@@ -1654,15 +1691,15 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
     if (const char* t = getenv("RTB_CARVEOUT"))
     {
         const int pct = atoi(t);
-        const void* all[] = { (const void*)k_raygen, (const void*)k_traverse<false>, (const void*)k_traverse<true>, (const void*)k_shade<false, false>, (const void*)k_shade<true, false>, (const void*)k_shade<false, true>, (const void*)k_shade<true, true>,
+        const void* all[] = { (const void*)k_raygen, (const void*)k_traverse<false>, (const void*)k_traverse<true>, (const void*)k_shade<false, false, RTB_RENDERER_PATH_TRACER_MIS>, (const void*)k_shade<true, false, RTB_RENDERER_PATH_TRACER_MIS>, (const void*)k_shade<false, true, RTB_RENDERER_PATH_TRACER_MIS>, (const void*)k_shade<true, true, RTB_RENDERER_PATH_TRACER_MIS>,
                               (const void*)k_shadow<false>, (const void*)k_shadow<true>, (const void*)k_tail<false>, (const void*)k_tail<true>, (const void*)k_resolve,
                               (const void*)k_film, (const void*)k_unshard, (const void*)k_front };
         for (const void* f : all) cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     }
     // wavefront slots (see RtbContext::Slot).  The default is ONE slot that runs on the main stream, i.e. strictly one
-    // kernel at a time: with several slots (RTB_SLOTS=4: +3 % device-resident, +9-12 % end to end on the bench) the
-    // traversal kernels returned different hits for the same ray whenever kernels of different streams overlapped,
-    // in some builds of the same source and not in others, and the cause is not understood yet.
+    // kernel at a time.  Several slots (RTB_SLOTS=2..4: +2 % device-resident on the bench) overlap the kernels of
+    // consecutive wavefronts; round 1 saw different hits for the same ray in that mode, round 2 bisected it to k_tail
+    // (DESIGN.md section 4c), which such contexts therefore run without (next paragraph).
     int numSlots = 1;
     if (const char* t = getenv("RTB_SLOTS")) numSlots = atoi(t) >= 1 && atoi(t) <= 16 ? atoi(t) : numSlots;
     c->slotsOwnStreams = numSlots > 1;
@@ -2066,11 +2103,11 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
         // (a tile of RTB_SHADE_TILE paths per CTA and loop iteration)
         if (c->sortShade)
         {
-            if (textured) k_shade<true, true><<<blocksShade, 128, 0, s>>>(c->view, P, W, d);
-            else k_shade<false, true><<<blocksShade, 128, 0, s>>>(c->view, P, W, d);
+            if (textured) launch_shade<true, true>(blocksShade, s, c->view, P, W, d);
+            else launch_shade<false, true>(blocksShade, s, c->view, P, W, d);
         }
-        else if (textured) k_shade<true, false><<<blocksShade, 128, 0, s>>>(c->view, P, W, d);
-        else k_shade<false, false><<<blocksShade, 128, 0, s>>>(c->view, P, W, d);
+        else if (textured) launch_shade<true, false>(blocksShade, s, c->view, P, W, d);
+        else launch_shade<false, false>(blocksShade, s, c->view, P, W, d);
         if (prof) marks.push_back(next_event(c, ev, s));
         if (shadows)
         {

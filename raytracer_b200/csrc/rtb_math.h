@@ -109,7 +109,17 @@ RTB_HD float sqr_length3(const V3& a) { return dot3(a, a); }
 RTB_HD float length3(const V3& a) { return sqrtf(dot3(a, a)); }
 // Normalize3: v / sqrt(dot3) (IEEE div + sqrt)                        Vector4ImplSSE.h:511-517
 // FastNormalize3 is the same in the exact-math oracle (oracle patch P9)
-RTB_HD V3 normalize3(const V3& a) { const float l = sqrtf(dot3(a, a)); return v3(a.x / l, a.y / l, a.z / l); }
+// (device: a ZERO numerator sends nvcc's IEEE division into its slow-path subroutine - 34 instructions to produce a signed
+//  zero.  Normals and tangents of axis-aligned geometry have zero components all the time: ncu on k_shade, round 2, showed
+//  7 % of its warp instructions in that subroutine at 3 of 32 lanes.  0 / l = +-0 for every l that is not 0 or NaN.)
+RTB_HD float div_or_zero(float x, float l)
+{
+#if defined(__CUDA_ARCH__)
+    if (x == 0.0f && l == l && l != 0.0f) return __uint_as_float((__float_as_uint(x) ^ __float_as_uint(l)) & 0x80000000u);
+#endif
+    return x / l;
+}
+RTB_HD V3 normalize3(const V3& a) { const float l = sqrtf(dot3(a, a)); return v3(div_or_zero(a.x, l), div_or_zero(a.y, l), div_or_zero(a.z, l)); }
 
 // Reflect3(i, n) = fnmadd(d + d, n, i), d = dot3(i, n)                Vector4Impl.h:114-119
 RTB_HD V3 reflect3(const V3& i, const V3& n) { const float d = dot3(i, n); return neg_mul_add(d + d, n, i); }

@@ -39,6 +39,8 @@ def reference_vcm(tmp_path, scene, w, h, passes, connection, merging, dims=256):
 
 @pytest.mark.skipif(not util.oracle_available("exact"), reason="prebuilt oracle/_ref/exact did not travel to this box")
 @pytest.mark.parametrize("scene,passes,connection,merging,mean_tolerance,min_correlation", [
+    # (tolerances: the camera paths of both sides draw the SAME pass script, which takes most of the noise out of the
+    #  difference - over 8 reference seeds the CPU model's mean colour stays within 0.5 % of the reference's in the 2 % rows)
     ("cornell", 30, 1, 1, 0.02, 0.999),          # VCM as the reference configures it
     ("materials", 30, 1, 1, 0.02, 0.999),        # all nine BSDFs, six lights of five types
     ("textures", 40, 1, 1, 0.03, 0.995),         # textured materials, environment map
@@ -128,7 +130,10 @@ def test_vcm_sharded_connection_only_matches_unsharded(tmp_path):
 @pytest.mark.skipif(not util.oracle_available("exact"), reason="prebuilt oracle/_ref/exact did not travel to this box")
 @pytest.mark.parametrize("scene,passes,mean_tolerance,min_correlation", [
     ("cornell", 200, 0.03, 0.995),
-    ("materials", 200, 0.04, 0.8),      # point / spot lights and specular surfaces: two runs of the REFERENCE with different seeds correlate at 0.87 here
+    # point / spot lights and specular surfaces, and no shared camera samples to correlate the two sides: at 200 passes two
+    # runs of the REFERENCE with different seeds differ by 3 % (one standard deviation) in the mean colour and correlate at
+    # 0.87 (a 200-pass version of this row failed on one box in three) - hence 3 200 passes, 3.7 standard deviations
+    ("materials", 3200, 0.04, 0.8),
 ])
 def test_light_tracer_statistics_against_the_live_reference(tmp_path, scene, passes, mean_tolerance, min_correlation):
     """RTB_RENDERER_LIGHT_TRACER (k_light_tracer; reference: LightTracer::RenderPixel, LightTracer.cpp:26-175): one light
