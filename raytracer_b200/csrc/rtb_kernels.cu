@@ -360,6 +360,9 @@ struct DeviceSink
 #define RTB_SHADE_TILE 512u        // a multiple of 128 (k_shade per 8 passes at 5 CTAs / SM: 256: 8.39 ms, 512: 8.16, 1024: 8.30, 2048: 9.16)
 #endif
 #define RTB_SHADE_BINS 32u
+// (measured and dropped, round 2: asking for the NEXT path's state between the issue of the queue atomics and the first use of
+//  their results - with `prefetch.global.L1` 7.86 -> 7.89 ms per 8 passes, with real loads into registers 8.35: the waits that
+//  ncu's per-line view shows on those loads are covered by the other warps, the kernel does not get faster by moving them)
 
 __device__ __forceinline__ uint32_t shade_key(const SceneView& S, uint32_t objectId, uint32_t subObjectId)
 {
@@ -440,6 +443,7 @@ __global__ void __launch_bounds__(128, RTB_SHADE_MINBLOCKS) k_shade(const __grid
         __syncthreads();
     }
     // (loop bound rounded up to a whole warp so that every lane takes part in the ballots)
+    const bool needRaster = kRenderer == RTB_RENDERER_PATH_TRACER_MIS && !P.lightSamplingAll;
 #pragma unroll 1
     for (uint32_t j = threadIdx.x; j < ((tileCount + 31u) & ~31u); j += 128u)
     {
@@ -450,9 +454,9 @@ __global__ void __launch_bounds__(128, RTB_SHADE_MINBLOCKS) k_shade(const __grid
         PathState ps;
         if (valid)
         {
-            load_path(in, i, W, P.width, P.numSeedDims, ps, kRenderer == RTB_RENDERER_PATH_TRACER_MIS && !P.lightSamplingAll);
-            const uint4 h0 = W.hit0[i];
             Hit hit;
+            load_path(in, i, W, P.width, P.numSeedDims, ps, needRaster);
+            const uint4 h0 = W.hit0[i];
             hit.objectId = h0.x; hit.subObjectId = h0.y; hit.distance = __uint_as_float(h0.z); hit.u = __uint_as_float(h0.w);
             hit.v = W.hit1[i];
 

@@ -29,14 +29,19 @@ def main():
         # the rows that carry a line number hold that line's totals; the SASS rows below them repeat the parts
         if hdr is None or len(r) < len(hdr) - 2 or not r[0].isdigit():
             continue
+        # (ncu does not escape quotes inside the source text: find the "-","-" of the two SASS columns instead of counting)
+        k = next((i for i in range(2, len(r) - 1) if r[i] == "-" and r[i + 1] == "-"), None)
+        if k is None:
+            continue
+        r = [r[0], ",".join(r[1:k])] + r[k:]
         r = r + ["0"] * (len(hdr) - len(r))
         key = (fpath.split("/")[-1], int(r[0]), r[1].strip()[:90])
         d = cur[key]
         for name in ("# Samples", "Instructions Executed", "Thread Instructions Executed"):
-            d[name] += float(r[hdr.index(name)] or 0)
+            d[name] += float(r[hdr.index(name)].replace("-", "0") or 0)
         for i, name in enumerate(hdr):
             if name.startswith("stall_") and "Not Issued" not in name:
-                d[name] += float(r[i] or 0)
+                d[name] += float((r[i] if r[i] != "-" else "0") or 0)
     for ki, k in enumerate(kernels):
         ts = sum(d["# Samples"] for d in k.values()); ti = sum(d["Instructions Executed"] for d in k.values())
         print("=== kernel %d: %.0f samples, %.1f M warp instructions" % (ki, ts, ti / 1e6))
