@@ -11,16 +11,20 @@ csv.field_size_limit(1 << 30)
 
 def main():
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-    kernels, cur, fpath, hdr = [], None, None, None
+    kernels, names, cur, fpath, hdr = [], [], None, None, None
     seen_files = set()
     for r in csv.reader(open(sys.argv[1])):
         if not r:
             continue
         if r[0] == "File Path":
             fpath = r[1]
-            # a file seen again = the next kernel's listing
-            if cur is None or fpath in seen_files:
-                cur = defaultdict(lambda: defaultdict(float)); kernels.append(cur); seen_files = set()
+            continue
+        if r[0] == "Function Name":
+            # one (file, kernel) section per source file a launch touched: a new launch starts when the kernel changes or a
+            # file comes round again
+            fn = r[1].split("(")[0].replace("void ", "").strip()
+            if cur is None or fn != names[-1] or fpath in seen_files:
+                cur = defaultdict(lambda: defaultdict(float)); kernels.append(cur); names.append(fn); seen_files = set()
             seen_files.add(fpath)
             continue
         if r[0] == "Line No":
@@ -44,7 +48,7 @@ def main():
                 d[name] += float((r[i] if r[i] != "-" else "0") or 0)
     for ki, k in enumerate(kernels):
         ts = sum(d["# Samples"] for d in k.values()); ti = sum(d["Instructions Executed"] for d in k.values())
-        print("=== kernel %d: %.0f samples, %.1f M warp instructions" % (ki, ts, ti / 1e6))
+        print("=== [%d] %s: %.0f samples, %.1f M warp instructions" % (ki, names[ki], ts, ti / 1e6))
         tot = defaultdict(float)
         for d in k.values():
             for n, v in d.items():
