@@ -81,7 +81,9 @@ struct Totals
     unsigned long long numRays, numShadowRays, numShadowRaysHit, numBoxTests, numTriTests, numShadowBoxTests, numShadowTriTests;
 };
 
+#if !RTB_TU_TAIL
 #include "rtb_vcm.cuh"
+#endif
 
 #define RTB_ALL_ACTIVE 0xFFFFFFFFu
 
@@ -192,6 +194,17 @@ __device__ __forceinline__ void load_path(const PathBuf& b, uint32_t i, const Wa
 // ---------------------------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------------------------
+// This file is compiled TWICE (build.sh): as the library proper, and once more with -DRTB_TU_TAIL=1 -Xptxas -O1 for k_tail alone.
+// ptxas' code for k_tail at -O2 and -O3 returns different hits / path lengths for a few hundred paths per frame whenever CTAs of
+// other streams' kernels are co-resident on its SMs, from identical inputs (checksummed) and whatever its register budget,
+// load flavour or vote exits; the -O1 code of the same source is bit-identical in every repetition.
+#ifndef RTB_TU_TAIL
+#define RTB_TU_TAIL 0
+#endif
+void rtb_launch_tail(bool textured, int blocks, size_t smemBytes, cudaStream_t stream, const SceneView& S, const PassParams& P, const struct Wavefront& W, uint32_t depth);
+void rtb_configure_tail(int maxDynamicSmem, int carveoutPercent /* < 0: leave it */);
+
+#if !RTB_TU_TAIL
 
 __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const __grid_constant__ Wavefront W)
 {
@@ -988,6 +1001,8 @@ __global__ void __launch_bounds__(RTB_SM_THREADS, RTB_SM_MINBLOCKS) k_shadow_mes
     }
 }
 
+#endif  // !RTB_TU_TAIL
+
 // ---- the tail of a wavefront ---------------------------------------------------------------------------------------------
 // Once only a few ten thousand paths are left, every further bounce costs four launches whose run time is one warp's
 // latency, not throughput (a 1/8 shard rendered pass by pass spends more than half of its 2.2 ms there).  k_tail is
@@ -995,6 +1010,7 @@ __global__ void __launch_bounds__(RTB_SM_THREADS, RTB_SM_MINBLOCKS) k_shadow_mes
 // remaining path to its end in ONE launch: the reference's per-pixel loop (PathTracerMIS.cpp:270-396) on one thread per
 // path, shadow rays traced on the spot in light order.  Same per-vertex functions, same order of the float additions
 // (emission, then the NEE sum of the vertex, then the next vertex), so the film is bit-identical to the wavefront path.
+#if RTB_TU_TAIL
 struct TailSink
 {
     const SceneView& S;
@@ -1018,6 +1034,12 @@ struct TailSink
     }
 };
 
+#ifndef RTB_TAIL_DISCARD
+#define RTB_TAIL_DISCARD 0
+#endif
+#ifndef RTB_TAIL_PROBE
+#define RTB_TAIL_PROBE 0
+#endif
 #ifndef RTB_TAIL_MINBLOCKS
 #define RTB_TAIL_MINBLOCKS 4       // 2 compiles it free of spills (255 registers)
 #endif
@@ -1038,12 +1060,20 @@ __global__ void __launch_bounds__(128, RTB_TAIL_MINBLOCKS) k_tail(const __grid_c
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
     unsigned long long rays = 0, shadowRays = 0, visible = 0;
+#if RTB_TAIL_PROBE      // (section 4c probe: order-independent checksums of what this kernel read and found, in the unused test counters)
+    unsigned long long probePaths = 0, probeIn = 0, probeHits = 0, probeColor = 0;
+#endif
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
     {
         PathState ps;
         load_path(in, i, W, P.width, P.numSeedDims, ps);
         const uint32_t colorIndex = ps.passSlot * W.numPixels + ps.pixel;
         const float4 pc = W.passColor[colorIndex];
+#if RTB_TAIL_PROBE
+        probePaths++;
+        probeIn += (unsigned long long)__float_as_uint(ps.ray.origin.x) + __float_as_uint(ps.ray.dir.y) + __float_as_uint(ps.throughput.x) + ps.pixel + ps.sampler.salt + ps.sampler.dim;
+        probeColor += (unsigned long long)__float_as_uint(pc.x) + __float_as_uint(pc.y) + __float_as_uint(pc.z);
+#endif
         TailSink sink(S, sstack);
         sink.result = v3(pc.x, pc.y, pc.z);
         for (;;)
@@ -1051,6 +1081,9 @@ __global__ void __launch_bounds__(128, RTB_TAIL_MINBLOCKS) k_tail(const __grid_c
             Hit hit;
             hit.objectId = RTB_INVALID_OBJECT; hit.subObjectId = 0; hit.distance = INFINITY; hit.u = 0.0f; hit.v = 0.0f;
             scene_traverse<false>(S, ps.ray, hit, nullptr, sstack);
+#if RTB_TAIL_PROBE
+            if (ps.depth == depth) probeHits += (unsigned long long)hit.objectId + hit.subObjectId + __float_as_uint(hit.distance);
+#endif
             rays++;
             uint32_t numShadow = 0;
             bool alive;
@@ -1058,7 +1091,9 @@ __global__ void __launch_bounds__(128, RTB_TAIL_MINBLOCKS) k_tail(const __grid_c
             else alive = shade_vertex_pt<kTex>(S, P, ps, hit, sink);
             if (!alive) break;
         }
+#if !RTB_TAIL_DISCARD      // (section 4c probe: a k_tail that does all its work and writes nothing)
         W.passColor[colorIndex] = make_float4(sink.result.x, sink.result.y, sink.result.z, 0.0f);
+#endif
         shadowRays += sink.shadowRays; visible += sink.visible;
     }
     for (int o = 16; o > 0; o >>= 1)
@@ -1073,9 +1108,33 @@ __global__ void __launch_bounds__(128, RTB_TAIL_MINBLOCKS) k_tail(const __grid_c
         if (shadowRays) atomicAdd(&W.tot->numShadowRays, shadowRays);
         if (visible) atomicAdd(&W.tot->numShadowRaysHit, visible);
     }
+#if RTB_TAIL_PROBE
+    atomicAdd(&W.tot->numBoxTests, probePaths); atomicAdd(&W.tot->numTriTests, probeIn);
+    atomicAdd(&W.tot->numShadowBoxTests, probeHits); atomicAdd(&W.tot->numShadowTriTests, probeColor);
+#endif
     if (blockIdx.x == 0 && threadIdx.x == 0) W.ctl->tailTaken = depth + 1u;
 }
 
+
+void rtb_launch_tail(bool textured, int blocks, size_t smemBytes, cudaStream_t stream, const SceneView& S, const PassParams& P, const Wavefront& W, uint32_t depth)
+{
+    if (textured) k_tail<true><<<blocks, 128, smemBytes, stream>>>(S, P, W, depth);
+    else k_tail<false><<<blocks, 128, smemBytes, stream>>>(S, P, W, depth);
+}
+
+void rtb_configure_tail(int maxDynamicSmem, int carveoutPercent)
+{
+    cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxDynamicSmem);
+    cudaFuncSetAttribute(k_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxDynamicSmem);
+    if (carveoutPercent >= 0)
+    {
+        cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carveoutPercent);
+        cudaFuncSetAttribute(k_tail<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carveoutPercent);
+    }
+}
+#endif  // RTB_TU_TAIL
+
+#if !RTB_TU_TAIL
 // PathTracerMIS::SampleLights: accumulatedColor += SampleLight(light) in light order (PathTracerMIS.cpp:142-148), then
 // resultColor.MulAndAccumulate(throughput, accumulatedColor) (PathTracerMIS.cpp:320)
 __global__ void __launch_bounds__(256) k_resolve(const __grid_constant__ Wavefront W, uint32_t depth)
@@ -1680,8 +1739,7 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
         cudaFuncSetAttribute(k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
         cudaFuncSetAttribute(k_trace_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
         cudaFuncSetAttribute(k_trace_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
-        cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
-        cudaFuncSetAttribute(k_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxStack);
+        rtb_configure_tail(maxStack, -1);
         cudaFuncSetAttribute(k_shadow_wide<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         cudaFuncSetAttribute(k_shadow_wide<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         cudaFuncSetAttribute(k_shadow_wide<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
@@ -1695,25 +1753,29 @@ int rtb_create(const RtbCreateDesc* desc, RtbContext** outCtx)
     if (const char* t = getenv("RTB_CARVEOUT"))
     {
         const int pct = atoi(t);
-        const void* all[] = { (const void*)k_raygen, (const void*)k_traverse<false>, (const void*)k_traverse<true>, (const void*)k_shade<false, false, RTB_RENDERER_PATH_TRACER_MIS>, (const void*)k_shade<true, false, RTB_RENDERER_PATH_TRACER_MIS>, (const void*)k_shade<false, true, RTB_RENDERER_PATH_TRACER_MIS>, (const void*)k_shade<true, true, RTB_RENDERER_PATH_TRACER_MIS>,
-                              (const void*)k_shadow<false>, (const void*)k_shadow<true>, (const void*)k_tail<false>, (const void*)k_tail<true>, (const void*)k_resolve,
+        const void* all[] = { (const void*)k_raygen, (const void*)k_traverse<false>, (const void*)k_traverse<true>, (const void*)k_traverse_p<false>, (const void*)k_traverse_p<true>,
+                              (const void*)k_shade<false, false, RTB_RENDERER_PATH_TRACER_MIS>, (const void*)k_shade<true, false, RTB_RENDERER_PATH_TRACER_MIS>, (const void*)k_shade<false, true, RTB_RENDERER_PATH_TRACER_MIS>, (const void*)k_shade<true, true, RTB_RENDERER_PATH_TRACER_MIS>,
+                              (const void*)k_shade<false, false, RTB_RENDERER_PATH_TRACER>, (const void*)k_shade<true, false, RTB_RENDERER_PATH_TRACER>, (const void*)k_shade<false, true, RTB_RENDERER_PATH_TRACER>, (const void*)k_shade<true, true, RTB_RENDERER_PATH_TRACER>,
+                              (const void*)k_shade<false, false, RTB_RENDERER_DEBUG>, (const void*)k_shade<true, false, RTB_RENDERER_DEBUG>, (const void*)k_shade<false, true, RTB_RENDERER_DEBUG>, (const void*)k_shade<true, true, RTB_RENDERER_DEBUG>,
+                              (const void*)k_shadow<false>, (const void*)k_shadow<true>, (const void*)k_shadow_wide<false, false>, (const void*)k_shadow_wide<true, false>, (const void*)k_shadow_wide<false, true>, (const void*)k_shadow_wide<true, true>,
+                              (const void*)k_shadow_top<false>, (const void*)k_shadow_top<true>, (const void*)k_shadow_mesh<false>, (const void*)k_shadow_mesh<true>,
+                              (const void*)k_resolve,
                               (const void*)k_film, (const void*)k_unshard, (const void*)k_front };
         for (const void* f : all) cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        rtb_configure_tail((int)((size_t)RTB_MAX_SMEM_STACK_ENTRIES * RTB_STACK_THREADS * sizeof(uint32_t)), pct);
     }
     // wavefront slots (see RtbContext::Slot).  The default is ONE slot that runs on the main stream, i.e. strictly one
     // kernel at a time.  Several slots (RTB_SLOTS=2..4: +2 % device-resident on the bench) overlap the kernels of
     // consecutive wavefronts; round 1 saw different hits for the same ray in that mode, round 2 bisected it to k_tail
-    // (DESIGN.md section 4c), which such contexts therefore run without (next paragraph).
+    // and to the optimisation level ptxas builds it at.
     int numSlots = 1;
     if (const char* t = getenv("RTB_SLOTS")) numSlots = atoi(t) >= 1 && atoi(t) <= 16 ? atoi(t) : numSlots;
     c->slotsOwnStreams = numSlots > 1;
     if (c->slotsOwnStreams) c->exclusiveStream = true;
-    // Round-2 bisect of the overlap problem (gpurun_out/r2b): with k_tail out of the picture every
-    // renderer is bit-identical under overlapping wavefronts (MIS, PT, debug; RTB_SLOTS=2 and 4); with it, a few hundred
-    // paths per frame differ.  k_tail is the one kernel that keeps spilled state (the world-space ray) alive across
-    // whole traversals while launches of other streams come and go on its SM.  Slots and the tail kernel solve the same
-    // problem (small wavefronts), so several slots simply run without it.
-    if (c->slotsOwnStreams && !getenv("RTB_TAIL_WITH_SLOTS")) c->tailThreshold = 0;
+    // (Round 2 bisected the overlap problem to k_tail and then to ptxas' -O2 / -O3 code for it: the kernel is built at ptxas -O1
+    //  in a translation unit of its own, see "compiled TWICE" above and DESIGN.md section 4c, and contexts with several slots
+    //  keep it.  RTB_NO_TAIL_WITH_SLOTS=1 restores the earlier workaround, slots without the tail kernel.)
+    if (c->slotsOwnStreams && getenv("RTB_NO_TAIL_WITH_SLOTS")) c->tailThreshold = 0;
     c->serializeSlots = getenv("RTB_SERIALIZE_SLOTS") != nullptr;
     c->profileDepths = getenv("RTB_PROFILE_DEPTHS") != nullptr;
     c->noWide = getenv("RTB_NO_WIDE") != nullptr;
@@ -2159,8 +2221,7 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
         if (tailBlocks > 0 && d < depthLimit)
         {
             // does nothing unless at most tailThreshold paths are left, then finishes them all (see k_tail)
-            if (textured) k_tail<true><<<tailBlocks, 128, c->stackBytes, s>>>(c->view, P, W, d + 1);
-            else k_tail<false><<<tailBlocks, 128, c->stackBytes, s>>>(c->view, P, W, d + 1);
+            rtb_launch_tail(textured, tailBlocks, c->stackBytes, s, c->view, P, W, d + 1);
         }
         if (prof) marks.push_back(next_event(c, ev, s));
     }
@@ -3196,3 +3257,4 @@ int rtb_get_pass_timings(RtbContext* c, RtbPassTimings* out)
 }
 
 } // extern "C"
+#endif  // !RTB_TU_TAIL

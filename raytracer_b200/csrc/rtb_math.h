@@ -13,7 +13,7 @@
 
 #if defined(__CUDACC__)
 #define RTB_HD __host__ __device__ __forceinline__
-#define RTB_HD_NOINLINE __host__ __device__ __noinline__
+#define RTB_HD_NOINLINE static __host__ __device__ __noinline__        // (static: the header is part of two translation units)
 #else
 #define RTB_HD inline __attribute__((always_inline))
 #define RTB_HD_NOINLINE inline

@@ -76,7 +76,7 @@ RTB_HD V3 wide_ray_eps(const Ray& r, float maxAbs)
 
 // byte k (0..3) of w as the float 1 + byte * 2^-15 (exact): one PRMT on the device
 #if defined(__CUDACC__)
-__constant__ uint32_t g_wideOne = 0x3F800000u;      // bits of 1.0f, see wide_byte_float
+static __constant__ uint32_t g_wideOne = 0x3F800000u;      // bits of 1.0f, see wide_byte_float (static: the library is two translation units)
 #endif
 // (`one` = 0x3F800000 held in a register the compiler cannot see through: PRMT takes one immediate, and with both the
 //  constant and the selector known ptxas kept the constant as the immediate and rebuilt the SELECTOR in a register

@@ -372,8 +372,9 @@ def test_wavefronts_in_flight_are_bit_identical(scene, slots, monkeypatch):
     """Pass-by-pass rendering against ONE batched wavefront of the same passes: film, secondary film and ray counters must
     be equal, every time.  With RTB_SLOTS = 2 / 4 every pass goes to its own wavefront slot / stream and several
     wavefronts overlap on the GPU - the configuration in which round 1 saw a few hundred paths per frame go wrong.  Round
-    2 bisected that to k_tail: contexts with several slots run without it, and this test keeps
-    watch (with RTB_TAIL_WITH_SLOTS=1 it reproduces the problem)."""
+    2 bisected that to k_tail and then to the code ptxas generates for it at -O2 / -O3: the kernel is
+    built at ptxas -O1 and stays in the launch chain of every context, and this test keeps watch (a library built with
+    RTB_TAIL_PTXAS=-O3 reproduces the problem here)."""
     monkeypatch.setenv("RTB_SLOTS", slots)
     meta = json.load(open(util.golden("%s_mis.json" % scene)))
     sf = capi.SceneFile(util.golden(scene + ".rtb"))
