@@ -362,7 +362,7 @@ int  rtb_synchronize(RtbContext* ctx);
 /* Passes are enqueued on the context's wavefront stream(s).  What ships is ONE wavefront slot: a context runs one kernel
  * at a time, on the stream of RtbCreateDesc (or one shared stream per device if none was given); with RTB_SLOTS = 2..4 in
  * the environment several wavefronts are in flight on streams of their own (the film still receives them in pass order;
- * such contexts run without the tail kernel; measured gain: 2 %).  Everything in this API that looks at the result (rtb_read_*, rtb_unshard_*, rtb_get_counters,
+ * bit-identical, tested with 2 and 4 slots; measured gain: 2 % device resident).  Everything in this API that looks at the result (rtb_read_*, rtb_unshard_*, rtb_get_counters,
  * rtb_film_device_buffer, rtb_reset, rtb_synchronize) orders itself after them.  rtb_join does only that: it makes the
  * main stream (RtbCreateDesc::stream) wait, on the device, for every pass enqueued so far - for callers that go on to
  * enqueue their own work on that stream.  It does not block the host. */
