@@ -251,7 +251,9 @@ def run_gpu(args):
     # rtb_film_snapshots leaves the film as of each of them on the device, from where each frame is (all-gathered when
     # sharded,) un-permuted to raster order and copied out asynchronously.
     vp.reset()
-    E2E_GROUP = 8 if world == 1 else 16      # steps submitted per call (a 1/N shard's wavefront of 8 passes is too small to run the GPU efficiently)
+    # steps submitted per call.  N > 1: two groups per 20-step region, so that the shard scatter of one group (on the context's
+    # second stream, rtb_scatter_shard_async) crosses PCIe while the next group renders
+    E2E_GROUP = 8 if world == 1 else (10 if args.steps < 32 else 16)
     e2e_steps = max(E2E_GROUP, (min(args.steps, 32) // E2E_GROUP) * E2E_GROUP)
     snap_ptr, snap_stride = C.c_void_p(), C.c_uint64()
     rc = lib.rtb_film_snapshots(ctx, E2E_GROUP, C.byref(snap_ptr), C.byref(snap_stride))
@@ -300,7 +302,7 @@ def run_gpu(args):
             for i in range(E2E_GROUP):
                 k = e2e_count[0] & 1
                 e2e_count[0] += 1
-                rc = lib.rtb_scatter_shard(ctx, C.c_void_p(snap_addr[i]), 0, C.c_void_p(dev_base + k * frame_bytes))
+                rc = lib.rtb_scatter_shard_async(ctx, C.c_void_p(snap_addr[i]), 0, C.c_void_p(dev_base + k * frame_bytes))
                 assert rc == 0, lib.rtb_last_error()
 
     e2e_group()
@@ -448,7 +450,7 @@ def run_gpu(args):
                     "h2d_bytes_per_step": DIMS * 4 + C.sizeof(capi.RtbPassDesc), "d2h_bytes_per_step": WIDTH * HEIGHT * 12,
                     "group": E2E_GROUP, "repeats_s": [r[0] for r in e2e_repeats],
                     "api": ("raytracer_b200.host_api.Viewport.render(8) (ViewportB200::Render x 8, one call) with rtb_film_snapshots; the frame as of EVERY pass is copied into a page-locked host frame (rtb_unshard_film_async), synchronize at the end" if world == 1 else
-                            "Viewport.render(%d) on every rank with rtb_film_snapshots;" % E2E_GROUP + " for EVERY pass every rank writes its own pixels into ONE page-locked host frame in shared memory (rtb_scatter_shard, one PCIe link per rank, no collective); synchronize + barrier at the end")},
+                            "Viewport.render(%d) on every rank with rtb_film_snapshots;" % E2E_GROUP + " for EVERY pass every rank writes its own pixels into ONE page-locked host frame in shared memory (rtb_scatter_shard_async on the context's second stream, under the next group's wavefront; one PCIe link per rank, no collective); synchronize + barrier at the end")},
             "wall_s_timed_region": wall_s, "e2e_frame_check": "ok" if e2e_ok else "FAILED",
             "clocks": sampler.summary(),
             "roofline": roofline,

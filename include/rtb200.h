@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RTB_API_VERSION 4   /* 2: textures (RtbTexture, RtbMaterialTextures, RtbSceneDesc::textures ...)  3: RTB_RENDERER_VCM, rtb_set_vcm_params, rtb_vcm_*  4: RTB_RENDERER_LIGHT_TRACER */
+#define RTB_API_VERSION 5   /* 2: textures (RtbTexture, RtbMaterialTextures, RtbSceneDesc::textures ...)  3: RTB_RENDERER_VCM, rtb_set_vcm_params, rtb_vcm_*  4: RTB_RENDERER_LIGHT_TRACER  5: rtb_scatter_shard_async */
 
 typedef enum RtbStatus
 {
@@ -399,6 +399,10 @@ int  rtb_unshard_film_async(RtbContext* ctx, const void* gatheredDevice, float* 
  *     rtb_block_errors accept.  For VCM it first all-reduces the splat buffers and folds them into the film.
  *     rtb_comm_init_all is the single-process flavour (ncclCommInitAll over the contexts' devices). */
 int  rtb_scatter_shard(RtbContext* ctx, const void* shardFilmDevice /* NULL: own film */, int which, void* rasterDst);
+/* the same for a film SNAPSHOT (rtb_film_snapshots), on the context's second stream: the stores cross PCIe while the passes
+ * enqueued after this call render (the renderer's next k_film waits for the scatter before it overwrites the snapshots).
+ * Complete after rtb_synchronize.  What a progressive multi-GPU display calls once per frame of a group of passes. */
+int  rtb_scatter_shard_async(RtbContext* ctx, const void* shardFilmSnapshotDevice, int which, void* rasterDst);
 #define RTB_COMM_ID_BYTES 128
 int  rtb_comm_unique_id(void* outId /* RTB_COMM_ID_BYTES */);                                   /* ncclGetUniqueId: rank 0 calls it and hands the bytes to the others */
 int  rtb_comm_init(RtbContext* ctx, const void* id /* RTB_COMM_ID_BYTES */);                  /* ncclCommInitRank(numShards, id, shardIndex) */

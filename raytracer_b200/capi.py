@@ -155,7 +155,7 @@ EXPORTED_SYMBOLS = [
     "rtb_resize", "rtb_reset", "rtb_render_pass", "rtb_render_passes", "rtb_synchronize", "rtb_join", "rtb_read_sum", "rtb_film_device_buffer", "rtb_film_snapshots",
     "rtb_unshard_film", "rtb_read_sum_async", "rtb_unshard_film_async", "rtb_host_alloc", "rtb_host_free", "rtb_get_counters", "rtb_trace_batch", "rtb_trace_batch_device", "rtb_texture_batch", "rtb_sample_batch",
     "rtb_set_vcm_params", "rtb_vcm_splat_buffers", "rtb_vcm_fold_splats",
-    "rtb_scatter_shard", "rtb_comm_unique_id", "rtb_comm_init", "rtb_comm_init_all", "rtb_finish_frame", "rtb_finish_frame_all",
+    "rtb_scatter_shard", "rtb_scatter_shard_async", "rtb_comm_unique_id", "rtb_comm_init", "rtb_comm_init_all", "rtb_finish_frame", "rtb_finish_frame_all",
     "rtb_host_register", "rtb_host_unregister", "rtb_host_device_pointer",
     "rtb_primary_rays", "rtb_set_profiling", "rtb_get_pass_timings", "rtb_read_front", "rtb_block_errors", "rtb_set_active_tiles",
 ]
@@ -214,6 +214,7 @@ def load_library(path=None):
     lib.rtb_vcm_splat_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.rtb_vcm_fold_splats.argtypes = [C.c_void_p]
     lib.rtb_scatter_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.rtb_scatter_shard_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.rtb_comm_unique_id.argtypes = [C.c_void_p]
     lib.rtb_comm_init.argtypes = [C.c_void_p, C.c_char_p]
     lib.rtb_comm_init_all.argtypes = [C.POINTER(C.c_void_p), C.c_uint32]

@@ -1492,6 +1492,8 @@ struct RtbContext
     // wraps, so a group of frames (rtb_film_snapshots) can be in flight on the copy stream while the next passes render
     DevArray<float> rasterAsync[RTB_SNAP_RING];
     cudaStream_t copyStream = nullptr;
+    cudaEvent_t scatterReady = nullptr, scatterDone = nullptr;     // rtb_scatter_shard_async: source complete / last scatter complete
+    bool scatterPending = false;                                   // a scatter on the copy stream may still read a film snapshot
     cudaEvent_t snapReady[RTB_SNAP_RING] = {}, snapCopied[RTB_SNAP_RING] = {};
     uint32_t snapIndex = 0;
 
@@ -1832,6 +1834,7 @@ void rtb_destroy(RtbContext* c)
     {
         cudaStreamSynchronize(c->copyStream);
         for (int i = 0; i < RTB_SNAP_RING; ++i) { cudaEventDestroy(c->snapReady[i]); cudaEventDestroy(c->snapCopied[i]); }
+        cudaEventDestroy(c->scatterReady); cudaEventDestroy(c->scatterDone);
         cudaStreamDestroy(c->copyStream);
     }
     if (c->ownStream) cudaStreamDestroy(c->stream);
@@ -2276,6 +2279,7 @@ static int render_batch(RtbContext* c, const RtbPassDesc* passes, uint32_t batch
         snap = c->snapshots.ptr + (size_t)snapshotIndex * c->shardSlots * 3;
         snapCount = std::min(batch, c->snapshotCapacity - snapshotIndex);
     }
+    if (snap && c->scatterPending) { RTB_CUDA(cudaStreamWaitEvent(s, c->scatterDone, 0)); c->scatterPending = false; }     // (rtb_scatter_shard_async of the previous call's snapshots)
     k_film<<<blocks256, 256, 0, s>>>(W, c->sum.ptr, c->sum2.ptr, snap, (size_t)c->shardSlots * 3, snapCount);
     RTB_CUDA(cudaEventRecord(slot.filmDone, s));
     c->lastFilm = slot.filmDone;
@@ -2609,21 +2613,28 @@ int rtb_unshard_film(RtbContext* c, const void* gatheredDevice, float* hostRgb)
 // Asynchronous read-back: the film is snapshotted to one of two raster buffers on the render stream, and copied to the
 // host on a second stream, so the copy of pass k overlaps the kernels of pass k+1.  `gatheredDevice` null: this
 // context's own film (rtb_read_sum semantics), else the all-gathered shard films (rtb_unshard_film semantics).
+// the second stream of a context (read-backs, rtb_scatter_shard_async) and its events
+static int ensure_copy_stream(RtbContext* c)
+{
+    if (c->copyStream) return RTB_OK;
+    RTB_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+    for (int i = 0; i < RTB_SNAP_RING; ++i)
+    {
+        RTB_CUDA(cudaEventCreateWithFlags(&c->snapReady[i], cudaEventDisableTiming));
+        RTB_CUDA(cudaEventCreateWithFlags(&c->snapCopied[i], cudaEventDisableTiming));
+        RTB_CUDA(cudaEventRecord(c->snapCopied[i], c->copyStream));
+    }
+    RTB_CUDA(cudaEventCreateWithFlags(&c->scatterReady, cudaEventDisableTiming));
+    RTB_CUDA(cudaEventCreateWithFlags(&c->scatterDone, cudaEventDisableTiming));
+    return RTB_OK;
+}
+
 static int read_back_async(RtbContext* c, const void* gatheredDevice, float* hostRgb, int which)
 {
     if (!c || !hostRgb) return fail(RTB_ERR_INVALID_ARG, "null argument");
     if (!c->sum.ptr) return fail(RTB_ERR_INVALID_ARG, "viewport has no size");
     RTB_CUDA(cudaSetDevice(c->device));
-    if (!c->copyStream)
-    {
-        RTB_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
-        for (int i = 0; i < RTB_SNAP_RING; ++i)
-        {
-            RTB_CUDA(cudaEventCreateWithFlags(&c->snapReady[i], cudaEventDisableTiming));
-            RTB_CUDA(cudaEventCreateWithFlags(&c->snapCopied[i], cudaEventDisableTiming));
-            RTB_CUDA(cudaEventRecord(c->snapCopied[i], c->copyStream));
-        }
-    }
+    { const int rc = ensure_copy_stream(c); if (rc != RTB_OK) return rc; }
     RTB_CUDA(join_slots(c));
     const uint32_t b = c->snapIndex++ % RTB_SNAP_RING;
     const size_t n = (size_t)c->width * c->height * 3;
@@ -3184,6 +3195,30 @@ int rtb_scatter_shard(RtbContext* c, const void* shardFilmDevice, int which, voi
     else
         k_scatter_shard<<<c->numSMs * 4, 256, 0, c->stream>>>(src, (float*)rasterDst, c->pixelList.ptr, c->numPixels);
     RTB_CUDA(cudaGetLastError());
+    c->counters.numKernelLaunches++;
+    return RTB_OK;
+}
+
+int rtb_scatter_shard_async(RtbContext* c, const void* shardFilmDevice, int which, void* rasterDst)
+{
+    if (!c || !rasterDst || !shardFilmDevice) return fail(RTB_ERR_INVALID_ARG, "null argument (the asynchronous scatter takes a film snapshot, not the live film)");
+    if (!c->sum.ptr) return fail(RTB_ERR_INVALID_ARG, "viewport has no size");
+    (void)which;
+    RTB_CUDA(cudaSetDevice(c->device));
+    { const int rc = ensure_copy_stream(c); if (rc != RTB_OK) return rc; }
+    RTB_CUDA(join_slots(c));
+    // the stores go over PCIe while the next wavefront renders: the kernel runs on the copy stream, after everything enqueued
+    // so far (the wavefront whose k_film wrote the snapshot), with a small grid - it waits on the bus, not on the SMs
+    RTB_CUDA(cudaEventRecord(c->scatterReady, c->stream));
+    RTB_CUDA(cudaStreamWaitEvent(c->copyStream, c->scatterReady, 0));
+    const float* src = (const float*)shardFilmDevice;
+    if (c->rasterOrder.ptr && ((uintptr_t)rasterDst & 15u) == 0)
+        k_scatter_shard_rows<<<c->numSMs, 256, 0, c->copyStream>>>(src, (float4*)rasterDst, c->rasterOrder.ptr, c->rasterPix.ptr, (uint32_t)((size_t)c->numPixels * 3u / 4u));
+    else
+        k_scatter_shard<<<c->numSMs, 256, 0, c->copyStream>>>(src, (float*)rasterDst, c->pixelList.ptr, c->numPixels);
+    RTB_CUDA(cudaGetLastError());
+    RTB_CUDA(cudaEventRecord(c->scatterDone, c->copyStream));
+    c->scatterPending = true;
     c->counters.numKernelLaunches++;
     return RTB_OK;
 }

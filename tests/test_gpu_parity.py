@@ -856,3 +856,40 @@ def test_shards_scattered_into_one_mapped_host_frame(w, h, tile):
     util.assert_bit_identical(frame.array, full, "scattered host frame")
     util.assert_bit_identical(frame2.array, full2, "scattered host frame, secondary sum")
     frame.close(); frame2.close()
+
+
+def test_snapshots_scattered_on_the_second_stream_under_the_next_passes():
+    """rtb_scatter_shard_async - the end-to-end path of an N-GPU run: two shard contexts render groups of passes with film
+    snapshots; after every group each pass' frame is scattered into a page-locked raster frame on the context's SECOND stream
+    while the next group already renders (the next k_film waits for the scatter before it overwrites the snapshots).  The
+    frame of every pass of every group equals the unsharded film after that many passes, bit for bit."""
+    lib = capi.load_library()
+    sf = capi.SceneFile(util.golden("mesh_small.rtb"))
+    ps = capi.PassScript(util.golden("mesh_small.passes"))
+    w, h, group, groups, n = 128, 96, 2, 2, 2
+    cam = capi.camera_for(sf, w, h)
+    want = []
+    with capi.Context(device=0) as c:
+        c.upload_scene(sf); c.resize(w, h)
+        for p in range(group * groups):
+            c.render_passes(cam, ps.seeds[p:p + 1], ps.offsets[p:p + 1], p)
+            want.append(c.read_sum())
+    frames = [capi.PinnedImage(w, h) for _ in range(group * groups)]
+    for f in frames:
+        f.array[:] = -1.0
+    for s in range(n):
+        with capi.Context(device=0, num_shards=n, shard_index=s) as c:
+            c.upload_scene(sf); c.resize(w, h)
+            snap, stride = C.c_void_p(), C.c_uint64()
+            assert lib.rtb_film_snapshots(c.h, group, C.byref(snap), C.byref(stride)) == 0, lib.rtb_last_error()
+            for g in range(groups):
+                c.render_passes(cam, ps.seeds[g * group:(g + 1) * group], ps.offsets[g * group:(g + 1) * group], g * group)
+                for i in range(group):
+                    dev = lib.rtb_host_device_pointer(C.c_void_p(frames[g * group + i].ptr))
+                    rc = lib.rtb_scatter_shard_async(c.h, C.c_void_p(snap.value + 4 * stride.value * i), 0, C.c_void_p(dev))
+                    assert rc == 0, lib.rtb_last_error()
+            c.synchronize()
+            lib.rtb_film_snapshots(c.h, 0, None, None)
+    for p, f in enumerate(frames):
+        util.assert_bit_identical(f.array, want[p], "frame of pass %d, scattered asynchronously" % p)
+        f.close()
