@@ -161,7 +161,8 @@ RTB_HD void box_blur_line(const Src& src, const Dst& dst, const uint32_t radius,
     uint32_t begin = 0u, end = 0u, out = 0u;
     for (uint32_t j = 0; j < radius; ++j) val += src(begin++);
     for (uint32_t j = 0; j <= radius; ++j) { val += src(begin++) - first; dst(out++, val * factor); }
-    // (src and dst never alias: the loads of a batch are issued together, only the running sum is sequential)
+    // (src and dst never alias: the loads of a batch are issued together, only the running sum is sequential.  Issuing the
+    //  NEXT batch's loads before this batch's sums - a software pipeline - was measured slower, 0.73 against 0.60 ms per launch)
     uint32_t j = radius + 1u;
     const uint32_t stop = width - radius;
     for (; j + RTB_BLUR_BATCH <= stop; j += RTB_BLUR_BATCH)
