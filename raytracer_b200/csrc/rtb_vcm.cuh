@@ -375,6 +375,9 @@ __device__ __forceinline__ V4 vcm_merge(const VcmDevice& V, const BidirPath& cam
 __device__ __forceinline__ V4 vcm_mul_add(const V4& a, const V4& b, const V4& c) { return v4(fma_(a.x, b.x, c.x), fma_(a.y, b.y, c.y), fma_(a.z, b.z, c.z), fma_(a.w, b.w, c.w)); }
 
 // the camera path of VertexConnectionAndMerging::RenderPixel, :176-288
+// (measured and dropped, round 2: both path kernels as ONE loop over path vertices per warp on a persistent grid, lanes taking
+//  their next pixel whenever their path ends - `bench.py --config c5` 39.6 -> 63 ms per pass: the lanes of a warp stop
+//  walking neighbouring pixels' paths, and the incoherence costs more than the idle lanes did)
 template <bool kTex>
 __global__ void __launch_bounds__(128, 3) k_vcm_camera(const __grid_constant__ SceneView S, const __grid_constant__ PassParams P, const __grid_constant__ VcmDevice V,
                                                        const uint32_t* __restrict__ pixelList, uint32_t numPixels, float4* __restrict__ passColor, Totals* tot)
